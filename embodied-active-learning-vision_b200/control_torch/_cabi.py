@@ -1,0 +1,182 @@
+"""ctypes binding of libklerg_b200.so (see include/klerg_b200.h).
+
+The library is the product: there is no CPU fallback.  Loading fails loudly if
+the shared object is missing, and every wrapper raises ``RuntimeError`` when the
+C side returns a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.path.join(PKG_ROOT, "libklerg_b200.so")
+CSRC = os.path.join(PKG_ROOT, "csrc")
+INCLUDE = os.path.join(REPO_ROOT, "include")
+
+MAX_D, MAX_S, MAX_A, MAX_H = 8, 24, 8, 256
+DYN_SINGLE, DYN_DOUBLE, DYN_SPEED, DYN_ROLL = 0, 1, 2, 3
+RED_SUM, RED_MAX, RED_MIN = 0, 1, 2
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class KernelSpec(C.Structure):
+    _fields_ = [("D", C.c_int32), ("S", C.c_int32), ("explr", C.c_int32 * MAX_D),
+                ("scale", C.c_float * MAX_D), ("nu", C.c_float)]
+
+
+class DynSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("S", C.c_int32), ("A", C.c_int32), ("dt", C.c_float),
+                ("rpw", C.c_int32 * 3), ("has_ang_map", C.c_int32),
+                ("rot_lo", C.c_float * 3), ("rot_hi", C.c_float * 3),
+                ("ang_lo", C.c_float * 3), ("ang_hi", C.c_float * 3)]
+
+
+class BarrierSpec(C.Structure):
+    _fields_ = [("n", C.c_int32), ("lo", C.c_float * MAX_S), ("hi", C.c_float * MAX_S),
+                ("weight", C.c_float * MAX_S), ("power", C.c_float * MAX_S)]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into libklerg_b200.so (in-tree)."""
+    srcs = sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + [
+        os.path.join(INCLUDE, "klerg_b200.h")]
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+_P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+_KS, _DS, _BS = C.POINTER(KernelSpec), C.POINTER(DynSpec), C.POINTER(BarrierSpec)
+
+# name -> argtypes (restype int unless listed in _RESTYPES); mirrors include/klerg_b200.h
+SIGNATURES = {
+    "klerg_last_error": [],
+    "klerg_abi_version": [],
+    "klerg_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "klerg_workspace_bytes": [_I64],
+    "klerg_pack_samples": [_KS, _P, _I64, _P, _I64, _P],
+    "klerg_footprint": [_KS, C.c_int, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P],
+    "klerg_vector_stats": [_P, _I64, _P, _P, _P],
+    "klerg_renormalize": [_P, _I64, _F, _P, _P, _P],
+    "klerg_renormalize_with_stats": [_P, _I64, _P, _F, _P, _P],
+    "klerg_cost_norm": [_P, _I64, _P, _P],
+    "klerg_kl_gradient": [_KS, _P, _I64, _P, _I64, _I64, _P, _P, _P, _P],
+    "klerg_kl_gradient_fused": [_KS, _P, _I64, _P, _I64, _I64, _P, _P, C.c_int, _P, _F, _P, _P, _P, _P],
+    "klerg_kl_cost_partial": [_P, _I64, _I64, _I64, _P, C.c_int, _P, _F, _P, _P, _P],
+    "klerg_kl_cost_final": [_P, C.c_int, _I64, _P, _P, _P, _P],
+    "klerg_target_stage1": [_P, _I32, _I64, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
+    "klerg_combine_blocks": [_P, C.c_int, C.c_int, C.POINTER(C.c_int), _P, _P],
+    "klerg_target_exponent": [_P, _I64, _P, _P],
+    "klerg_target_stage2": [C.c_int, _P, _I32, _I64, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P,
+                            _P, _P, _P],
+    "klerg_target_stage3": [_P, _I64, _P, C.c_int, _F, _F, _P, _P, _P, _P],
+    "klerg_rollout": [_DS, _BS, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P],
+    "klerg_barrier_eval": [_BS, _P, _I64, _I32, _P, _P, _P],
+    "klerg_adjoint": [_DS, _KS, _I64, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float), _F,
+                      C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
+    "klerg_gather_rows": [_P, _I32, _P, _I64, _P, _P],
+}
+_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t}
+
+
+def load():
+    """dlopen the library and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the KL-ergodic path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("control_torch (B200 build) needs a CUDA device; there is no CPU fallback")
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().klerg_last_error()
+        raise RuntimeError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def farr(vals, n=None):
+    vals = [float(v) for v in vals]
+    n = n or len(vals)
+    return (C.c_float * n)(*vals)
+
+
+def kernel_spec(D, S, explr, scale, nu=1.0):
+    k = KernelSpec()
+    k.D, k.S, k.nu = int(D), int(S), float(nu)
+    for d in range(int(D)):
+        k.explr[d] = int(explr[d])
+        k.scale[d] = float(scale[d])
+    return k
+
+
+def dyn_spec(kind, S, A, dt, rpw=(0, 0, 0), ang_map=None):
+    d = DynSpec()
+    d.kind, d.S, d.A, d.dt = int(kind), int(S), int(A), float(dt)
+    for i in range(3):
+        d.rpw[i] = int(rpw[i])
+    d.has_ang_map = 0
+    if ang_map is not None:
+        rot, ang = ang_map  # [3,2] each
+        d.has_ang_map = 1
+        for i in range(3):
+            d.rot_lo[i], d.rot_hi[i] = float(rot[i][0]), float(rot[i][1])
+            d.ang_lo[i], d.ang_hi[i] = float(ang[i][0]), float(ang[i][1])
+    return d
+
+
+def barrier_spec(lo, hi, weight, power):
+    b = BarrierSpec()
+    b.n = len(lo)
+    if b.n > MAX_S:
+        raise ValueError("barrier has more rows than KLERG_MAX_S")
+    for i in range(b.n):
+        b.lo[i], b.hi[i], b.weight[i], b.power[i] = float(lo[i]), float(hi[i]), float(weight[i]), float(power[i])
+    return b

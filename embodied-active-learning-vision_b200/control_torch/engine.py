@@ -1,0 +1,279 @@
+"""Device-side operations of the KL-ergodic path on top of the C ABI.
+
+Every function takes/returns CUDA tensors and enqueues work on torch's current
+stream; nothing here does arithmetic on the host.  ``ShardGroup`` carries the
+(optional) sample-sharding communicator: per-rank partial totals are exchanged
+with one small all-gather per phase and combined in rank order on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _cabi as cabi
+
+FLOOR = 1e-6  # renormalize() clamp (klerg_utils.py:45)
+
+
+def _dev():
+    cabi.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Workspace:
+    """Scratch memory handed to the C side (zero-filled once, reused per stream)."""
+
+    def __init__(self):
+        self.G = 0
+        self.buf = None
+
+    def get(self, G=1):
+        if self.buf is None or G > self.G:
+            G = max(int(G), 8, self.G)
+            nbytes = cabi.load().klerg_workspace_bytes(G)
+            self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=_dev())
+            self.G = G
+        return C.c_void_p(self.buf.data_ptr())
+
+
+_workspaces = {}
+
+
+def workspace(G=1):
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = Workspace()
+    return ws.get(G)
+
+
+class ShardGroup:
+    """Sample-sharding communicator (world 1 = no communication)."""
+
+    def __init__(self, process_group=None):
+        self.pg = process_group
+        if process_group is None:
+            self.world, self.rank = 1, 0
+        else:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+
+    def gather_blocks(self, block):
+        """[...] per-rank block -> [world, ...] (rank order), one all-gather."""
+        if self.world == 1:
+            return block.unsqueeze(0)
+        import torch.distributed as dist
+        out = torch.empty((self.world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block.contiguous(), group=self.pg)
+        return out
+
+    def shard_bounds(self, n_total):
+        """Contiguous [lo, hi) slice of the sample axis owned by this rank."""
+        base, rem = divmod(int(n_total), self.world)
+        lo = self.rank * base + min(self.rank, rem)
+        return lo, lo + base + (1 if self.rank < rem else 0)
+
+
+SINGLE = ShardGroup()
+
+
+def padded(n):
+    return max(4, (int(n) + 3) // 4 * 4)
+
+
+def pack_samples(spec, samples):
+    """[N,D] raw samples -> packed/scaled SoA [D, ld] (klerg_pack_samples)."""
+    n = samples.shape[0]
+    ld = padded(n)
+    packed = torch.empty((spec.D, ld), dtype=torch.float32, device=samples.device)
+    cabi.check(cabi.load().klerg_pack_samples(C.byref(spec), cabi.ptr(samples), n, cabi.ptr(packed), ld,
+                                              cabi.stream_ptr()), "klerg_pack_samples")
+    return packed
+
+
+def footprint(spec, mode, states, packed, n, add_in=None, out=None):
+    """states [G,T,S] (or [T,S]) -> (out [G, ld], totals [G,2] float64)."""
+    if states.dim() == 2:
+        states = states.unsqueeze(0)
+    G, T, S = states.shape
+    assert S == spec.S, (S, spec.S)
+    if T > 0 and not (states.stride(2) == 1 and states.stride(1) == S):
+        states = states.contiguous()  # rows must be dense; segments may be strided views
+    seg_stride = states.stride(0) if (T > 0 and G > 1) else T * S
+    states_ptr = C.c_void_p(states.data_ptr()) if T > 0 else None
+    ld = packed.shape[1]
+    if out is None:
+        out = torch.empty((G, ld), dtype=torch.float32, device=packed.device)
+    totals = torch.empty((G, 2), dtype=torch.float64, device=packed.device)
+    cabi.check(cabi.load().klerg_footprint(
+        C.byref(spec), int(mode), states_ptr, G, T, seg_stride, cabi.ptr(packed), int(n), ld,
+        cabi.ptr(add_in), cabi.ptr(out), out.stride(0), cabi.ptr(totals), workspace(G), cabi.stream_ptr()),
+        "klerg_footprint")
+    return out, totals
+
+
+def vector_stats(x):
+    stats = torch.empty(4, dtype=torch.float64, device=x.device)
+    cabi.check(cabi.load().klerg_vector_stats(cabi.ptr(x), x.numel(), cabi.ptr(stats), workspace(), cabi.stream_ptr()),
+               "klerg_vector_stats")
+    return stats
+
+
+def renormalize(x, floor=FLOOR):
+    out = torch.empty_like(x)
+    cabi.check(cabi.load().klerg_renormalize(cabi.ptr(x), x.numel(), float(floor), cabi.ptr(out), workspace(),
+                                             cabi.stream_ptr()), "klerg_renormalize")
+    return out
+
+
+def renormalize_sharded(x, totals_w, floor=FLOOR):
+    """renormalize() of a sample-sharded vector: totals_w [world,2] = per-rank {sum, max}."""
+    stats = combine_blocks(totals_w.contiguous(), [cabi.RED_SUM, cabi.RED_MAX])
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    cabi.check(cabi.load().klerg_renormalize_with_stats(cabi.ptr(x), x.numel(), cabi.ptr(stats), float(floor),
+                                                        cabi.ptr(out), cabi.stream_ptr()), "klerg_renormalize_with_stats")
+    return out
+
+
+def cost_norm_(x):
+    cabi.check(cabi.load().klerg_cost_norm(cabi.ptr(x), x.numel(), workspace(), cabi.stream_ptr()), "klerg_cost_norm")
+    return x
+
+
+def kl_gradient(spec, states, packed, n, w):
+    states = states.contiguous()
+    H = states.shape[0]
+    dgdx = torch.empty((H, spec.S), dtype=torch.float32, device=packed.device)
+    cabi.check(cabi.load().klerg_kl_gradient(C.byref(spec), cabi.ptr(states), H, cabi.ptr(packed), int(n),
+                                             packed.shape[1], cabi.ptr(w), cabi.ptr(dgdx), workspace(),
+                                             cabi.stream_ptr()), "klerg_kl_gradient")
+    return dgdx
+
+
+def kl_gradient_fused(spec, states, packed, n, v, totals_w, p, floor=FLOOR):
+    """-> (grad_part [H,D] float64, kl_part [2] float64) for this rank's samples."""
+    states = states.contiguous()
+    H = states.shape[0]
+    grad_part = torch.empty((H, spec.D), dtype=torch.float64, device=packed.device)
+    kl_part = torch.empty(2, dtype=torch.float64, device=packed.device)
+    cabi.check(cabi.load().klerg_kl_gradient_fused(
+        C.byref(spec), cabi.ptr(states), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(v),
+        cabi.ptr(totals_w), totals_w.shape[0], cabi.ptr(p), float(floor), cabi.ptr(grad_part), cabi.ptr(kl_part),
+        workspace(), cabi.stream_ptr()), "klerg_kl_gradient_fused")
+    return grad_part, kl_part
+
+
+def kl_cost(v, n, totals_w, p, p_stats, barrier_sum, group=SINGLE, floor=FLOOR):
+    """KL(p||q) + barrier for G candidates: v [G, ld] -> cost [G]."""
+    G = v.shape[0]
+    kl_part = torch.empty((G, 2), dtype=torch.float64, device=v.device)
+    lib = cabi.load()
+    cabi.check(lib.klerg_kl_cost_partial(cabi.ptr(v), v.stride(0), G, int(n), cabi.ptr(totals_w), totals_w.shape[0],
+                                         cabi.ptr(p), float(floor), cabi.ptr(kl_part), workspace(G),
+                                         cabi.stream_ptr()), "klerg_kl_cost_partial")
+    parts = group.gather_blocks(kl_part)
+    cost = torch.empty(G, dtype=torch.float32, device=v.device)
+    cabi.check(lib.klerg_kl_cost_final(cabi.ptr(parts), parts.shape[0], G, cabi.ptr(p_stats), cabi.ptr(barrier_sum),
+                                       cabi.ptr(cost), cabi.stream_ptr()), "klerg_kl_cost_final")
+    return cost
+
+
+def combine_blocks(blocks, kinds):
+    """[world, n] float64 -> [n] with per-column sum/max/min (rank order)."""
+    world, n = blocks.shape
+    out = torch.empty(n, dtype=torch.float64, device=blocks.device)
+    arr = (C.c_int * n)(*kinds)
+    cabi.check(cabi.load().klerg_combine_blocks(cabi.ptr(blocks.contiguous()), world, n, arr, cabi.ptr(out),
+                                                cabi.stream_ptr()), "klerg_combine_blocks")
+    return out
+
+
+def target_weight(mode, samples, lim_lo, lim_hi, spread, p_raw, n_total, temp, renorm, group=SINGLE, floor=FLOOR):
+    """get_target_dist weighting (klerg.py:452-486) -> (p [N], p_stats [1] float64).
+
+    mode 0: p ** mean(spread')   mode 1: p + (1-spread')*min p   mode 2: unchanged.
+    ``spread`` None = empty memory buffer.  ``renorm`` applies renormalize().
+    """
+    lib = cabi.load()
+    n, D = samples.shape
+    lo, hi = cabi.farr(lim_lo), cabi.farr(lim_hi)
+    dev = samples.device
+    acc1 = torch.empty(4, dtype=torch.float64, device=dev)
+    cabi.check(lib.klerg_target_stage1(cabi.ptr(samples), D, n, lo, hi, cabi.ptr(spread), cabi.ptr(p_raw),
+                                       cabi.ptr(acc1), workspace(), cabi.stream_ptr()), "klerg_target_stage1")
+    acc1 = combine_blocks(group.gather_blocks(acc1), [cabi.RED_MAX, cabi.RED_SUM, cabi.RED_SUM, cabi.RED_MIN])
+    expo = torch.empty(3, dtype=torch.float64, device=dev)
+    cabi.check(lib.klerg_target_exponent(cabi.ptr(acc1), int(n_total), cabi.ptr(expo), cabi.stream_ptr()),
+               "klerg_target_exponent")
+    p2 = torch.empty(n, dtype=torch.float32, device=dev)
+    acc2 = torch.empty(2, dtype=torch.float64, device=dev)
+    cabi.check(lib.klerg_target_stage2(int(mode), cabi.ptr(samples), D, n, lo, hi, cabi.ptr(spread), cabi.ptr(p_raw),
+                                       cabi.ptr(expo), cabi.ptr(p2), cabi.ptr(acc2), workspace(), cabi.stream_ptr()),
+               "klerg_target_stage2")
+    acc2 = combine_blocks(group.gather_blocks(acc2), [cabi.RED_SUM, cabi.RED_MAX])
+    p = torch.empty(n, dtype=torch.float32, device=dev)
+    p_stats = torch.empty(1, dtype=torch.float64, device=dev)
+    cabi.check(lib.klerg_target_stage3(cabi.ptr(p2), n, cabi.ptr(acc2), int(bool(renorm)), float(floor), float(temp),
+                                       cabi.ptr(p), cabi.ptr(p_stats), workspace(), cabi.stream_ptr()),
+               "klerg_target_stage3")
+    p_stats = combine_blocks(group.gather_blocks(p_stats), [cabi.RED_SUM])
+    return p, p_stats, expo
+
+
+def rollout(dyn, bar, x0, u, R0=None, want_lin=False, want_R=False):
+    """u [B,H,A] (or [H,A]) -> dict(traj [B,H+1,S], barrier [B], dbarr, P, R)."""
+    if u.dim() == 2:
+        u = u.unsqueeze(0)
+    u = u.contiguous()
+    B, H, A = u.shape
+    dev = u.device
+    S = dyn.S
+    traj = torch.empty((B, H + 1, S), dtype=torch.float32, device=dev)
+    bsum = torch.empty(B, dtype=torch.float32, device=dev)
+    dbarr = torch.empty((B, H, S), dtype=torch.float32, device=dev) if want_lin else None
+    P = torch.empty((B, H, A * A), dtype=torch.float32, device=dev) if (want_lin and dyn.kind == cabi.DYN_ROLL) else None
+    R_out = torch.empty((B, 9), dtype=torch.float32, device=dev) if want_R else None
+    cabi.check(cabi.load().klerg_rollout(C.byref(dyn), C.byref(bar) if bar is not None else None, cabi.ptr(x0),
+                                         cabi.ptr(R0), cabi.ptr(u), B, H, cabi.ptr(traj), cabi.ptr(bsum),
+                                         cabi.ptr(dbarr), cabi.ptr(P), cabi.ptr(R_out), cabi.stream_ptr()),
+               "klerg_rollout")
+    return dict(traj=traj, barrier=bsum, dbarr=dbarr, P=P, R=R_out)
+
+
+def barrier_eval(bar, x, want_value=True, want_grad=True):
+    x = x.contiguous()
+    T, S = x.shape
+    value = torch.empty(T, dtype=torch.float32, device=x.device) if want_value else None
+    grad = torch.empty((T, S), dtype=torch.float32, device=x.device) if want_grad else None
+    cabi.check(cabi.load().klerg_barrier_eval(C.byref(bar) if bar is not None else None, cabi.ptr(x), T, S,
+                                              cabi.ptr(value), cabi.ptr(grad), cabi.stream_ptr()), "klerg_barrier_eval")
+    return value, grad
+
+
+def adjoint(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl_hi):
+    """grad_parts [world,H,D] float64 -> dgdx [H,S], du [H,A], djdlam [H], u_star [H,A]."""
+    world, H, D = grad_parts.shape
+    dev = grad_parts.device
+    S, A = dyn.S, dyn.A
+    dgdx = torch.empty((H, S), dtype=torch.float32, device=dev)
+    du = torch.empty((H, A), dtype=torch.float32, device=dev)
+    dj = torch.empty(H, dtype=torch.float32, device=dev)
+    ustar = torch.empty((H, A), dtype=torch.float32, device=dev)
+    cabi.check(cabi.load().klerg_adjoint(
+        C.byref(dyn), C.byref(spec), H, cabi.ptr(grad_parts.contiguous()), world, cabi.ptr(dbarr.contiguous()),
+        cabi.ptr(P), cabi.ptr(traj.contiguous()), cabi.ptr(u.contiguous()), cabi.farr(rinv), float(alpha),
+        cabi.farr(ctrl_lo), cabi.farr(ctrl_hi), cabi.ptr(dgdx), cabi.ptr(du), cabi.ptr(dj), cabi.ptr(ustar),
+        cabi.stream_ptr()), "klerg_adjoint")
+    return dgdx, du, dj, ustar
+
+
+def gather_rows(table, idx):
+    """table [cap,S] float32, idx [M] int64 (device) -> [M,S]."""
+    M, S = idx.numel(), table.shape[1]
+    out = torch.empty((M, S), dtype=torch.float32, device=table.device)
+    if M:
+        cabi.check(cabi.load().klerg_gather_rows(cabi.ptr(table), S, cabi.ptr(idx), M, cabi.ptr(out),
+                                                 cabi.stream_ptr()), "klerg_gather_rows")
+    return out

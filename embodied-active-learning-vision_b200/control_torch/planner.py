@@ -1,0 +1,107 @@
+"""Device-resident evaluation context of the KL-ergodic planner.
+
+One ``PlannerContext`` holds everything an *eval* needs on the GPU - packed
+workspace samples, target density p, history footprint q_base, the planner
+model and barrier - and exposes the two batched operations the reference
+performs through Python loops:
+
+* ``costs(U)``      = ``Robot.get_cost`` for B candidate control sequences
+                      (klerg.py:686-710): rollout, barrier, footprint over the
+                      post-step states, renormalise, KL(p||q);
+* ``gradient(u)``   = ``Robot.forward`` + footprint + ``Robot.backward``
+                      (klerg.py:409-450): rollout with linearisation, footprint
+                      over the pre-step states, importance ratio, dgdx for all
+                      H steps, adjoint sweep -> du, djdlam, u*.
+
+With a ``ShardGroup`` of world > 1 each rank holds a contiguous slice of the
+samples; the only traffic is one all-gather of [G,2] totals after the forward
+pass and one of [H*D+2] partials after the gradient pass.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi as cabi
+from . import engine
+
+
+class PlannerContext:
+    def __init__(self, dyn, barrier_spec, explr_locs, horizon, rinv_diag, ctrl_lo, ctrl_hi, alpha=1.0,
+                 group=engine.SINGLE, floor=engine.FLOOR):
+        cabi.require_cuda()
+        self.dyn = dyn
+        self.bar = barrier_spec
+        self.explr_locs = [int(i) for i in explr_locs]
+        self.H = int(horizon)
+        self.rinv = [float(v) for v in rinv_diag]
+        self.ctrl_lo = [float(v) for v in ctrl_lo]
+        self.ctrl_hi = [float(v) for v in ctrl_hi]
+        self.alpha = float(alpha)
+        self.group = group
+        self.floor = floor
+        self.spec = None
+        self.n = 0
+        self.evals = dict(cost=0, grad=0, fwd_pairs=0, grad_pairs=0)
+
+    # -- per-step inputs ---------------------------------------------------------
+    def set_samples(self, samples_dev, scale, nu=1.0):
+        """samples_dev [n_local, D] raw (this rank's slice); scale = std as the reference uses it."""
+        D = samples_dev.shape[1]
+        self.spec = cabi.kernel_spec(D, self.dyn.S, self.explr_locs, [float(s) for s in scale], nu)
+        self.samples = samples_dev
+        self.n = samples_dev.shape[0]
+        self.packed = engine.pack_samples(self.spec, samples_dev)
+
+    def set_target(self, p, p_stats):
+        self.p, self.p_stats = p, p_stats
+
+    def set_history(self, hist_dev):
+        """q_base = footprint of the drawn history rows (zeros when empty, klerg.py:496-498)."""
+        out, _ = engine.footprint(self.spec, 0, hist_dev, self.packed, self.n)
+        self.q_base = out[0]
+        return self.q_base
+
+    def set_state(self, x0_dev):
+        self.x0 = x0_dev.contiguous()
+
+    # -- evals -------------------------------------------------------------------
+    def costs(self, U):
+        """U [B,H,A] on the device -> cost [B] (KL + barrier), all on the device."""
+        if U.dim() == 2:
+            U = U.unsqueeze(0)
+        B = U.shape[0]
+        ro = engine.rollout(self.dyn, self.bar, self.x0, U)
+        v, totals = engine.footprint(self.spec, 0, ro["traj"][:, 1:, :], self.packed, self.n, add_in=self.q_base)
+        totals_w = self.group.gather_blocks(totals)
+        self.evals["cost"] += B
+        self.evals["fwd_pairs"] += B * self.H * self.n
+        return engine.kl_cost(v, self.n, totals_w, self.p, self.p_stats, ro["barrier"], self.group, self.floor)
+
+    def gradient(self, u, keep=False):
+        """u [H,A] on the device -> dict(du, djdlam, u_star, dgdx, ...) on the device."""
+        ro = engine.rollout(self.dyn, self.bar, self.x0, u, want_lin=True)
+        traj = ro["traj"][0]
+        pre = traj[: self.H]
+        v, totals = engine.footprint(self.spec, 0, pre, self.packed, self.n, add_in=self.q_base)
+        totals_w = self.group.gather_blocks(totals)
+        gpart, klpart = engine.kl_gradient_fused(self.spec, pre, self.packed, self.n, v[0], totals_w, self.p, self.floor)
+        if self.group.world > 1:
+            packed = self.group.gather_blocks(torch.cat([gpart.reshape(-1), klpart]))
+            gparts = packed[:, :-2].reshape(self.group.world, self.H, self.spec.D).contiguous()
+            klparts = packed[:, -2:]
+        else:
+            gparts, klparts = gpart.unsqueeze(0), klpart.unsqueeze(0)
+        P = ro["P"][0] if ro["P"] is not None else None
+        dgdx, du, dj, ustar = engine.adjoint(self.dyn, self.spec, gparts, ro["dbarr"][0], P, traj,
+                                             u.reshape(self.H, -1), self.rinv, self.alpha, self.ctrl_lo, self.ctrl_hi)
+        self.evals["grad"] += 1
+        self.evals["fwd_pairs"] += self.H * self.n
+        self.evals["grad_pairs"] += self.H * self.n
+        out = dict(du=du, djdlam=dj, u_star=ustar, dgdx=dgdx, traj=pre, kl_parts=klparts)
+        if keep:
+            out.update(v=v[0], totals=totals_w)
+        return out
+
+    def q_from(self, v, totals_w):
+        """renormalize(q_base + q_iter) given the forward output (for plot_data)."""
+        return engine.renormalize_sharded(v[: self.n], totals_w.reshape(totals_w.shape[0], -1)[:, :2], self.floor)

@@ -1,0 +1,145 @@
+// Shared device helpers for libklerg_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "klerg_b200.h"
+
+namespace klerg {
+
+// ---- workspace layout (see klerg_workspace_bytes) ---------------------------
+// HEAD: [misc counters 64 x int][misc partials MAXBLK x 8 doubles]
+//       [gradient partials GRAD_MAXBLK x MAX_H*MAX_D doubles]
+// then one SEG record per segment g: [counter + pad 64 B][MAXBLK x 2 doubles]
+constexpr int MAXBLK = 1184;      // 148 SMs x 8
+constexpr int GRAD_MAXBLK = 296;  // 148 SMs x 2
+constexpr size_t HEAD_COUNTERS = 256;
+constexpr size_t HEAD_MISC = (size_t)MAXBLK * 8 * sizeof(double);
+constexpr size_t HEAD_GRAD = (size_t)GRAD_MAXBLK * KLERG_MAX_H * KLERG_MAX_D * sizeof(double);
+constexpr size_t HEAD_BYTES = HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD;
+constexpr size_t SEG_BYTES = 64 + (size_t)MAXBLK * 2 * sizeof(double);
+
+__host__ __device__ inline int* ws_misc_counter(void* ws, int slot) { return (int*)ws + slot; }
+__host__ __device__ inline double* ws_misc_partials(void* ws) { return (double*)((char*)ws + HEAD_COUNTERS); }
+__host__ __device__ inline double* ws_grad_partials(void* ws) {
+  return (double*)((char*)ws + HEAD_COUNTERS + HEAD_MISC);
+}
+__host__ __device__ inline int* ws_seg_counter(void* ws, int64_t g) {
+  return (int*)((char*)ws + HEAD_BYTES + (size_t)g * SEG_BYTES);
+}
+__host__ __device__ inline double* ws_seg_partials(void* ws, int64_t g) {
+  return (double*)((char*)ws + HEAD_BYTES + (size_t)g * SEG_BYTES + 64);
+}
+
+// ---- math -------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 0.5*log2(e): psi = exp(-0.5*sum d^2/scale) = 2^-(sum (d*a)^2), a = sqrt(HALF_LOG2E/scale)
+constexpr double HALF_LOG2E = 0.72134752044448170368;
+
+enum { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+
+__device__ __forceinline__ double red_combine(int kind, double a, double b) {
+  return kind == RED_SUM ? a + b : (kind == RED_MAX ? fmax(a, b) : fmin(a, b));
+}
+__device__ __forceinline__ double red_identity(int kind) {
+  return kind == RED_SUM ? 0.0 : (kind == RED_MAX ? -INFINITY : INFINITY);
+}
+
+__device__ __forceinline__ double warp_reduce(int kind, double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = red_combine(kind, v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-level reduction of NQ quantities followed by a deterministic grid-level
+// reduction done by the last block to finish ("ticket" pattern).  `nblk` blocks
+// take part; block `blk` writes partials[blk*NQ + q]; the last block combines all
+// partials in block order and writes out[q].  The counter is left at zero.
+// Returns true in the last block (all threads).  Requires blockDim.x <= 1024.
+template <int NQ>
+__device__ __forceinline__ bool grid_reduce(const int (&kind)[NQ], double (&val)[NQ], double* partials,
+                                            int* counter, int blk, int nblk, double* out) {
+  __shared__ double sh_red[32][NQ];
+  __shared__ int sh_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double v = warp_reduce(kind[q], val[q]);
+    if (lane == 0) sh_red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double v = sh_red[0][q];
+      for (int w = 1; w < nwarp; ++w) v = red_combine(kind[q], v, sh_red[w][q]);
+      partials[(size_t)blk * NQ + q] = v;
+    }
+    __threadfence();
+    int ticket = atomicAdd(counter, 1);
+    sh_last = (ticket == nblk - 1);
+  }
+  __syncthreads();
+  const bool last = sh_last != 0;
+  if (last) {
+    __threadfence();
+    // fixed-order combine: thread q-stripes, then a warp tree (order fixed by layout)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double v = red_identity(kind[q]);
+      for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+        v = red_combine(kind[q], v, __ldcg(&partials[(size_t)b * NQ + q]));
+      v = warp_reduce(kind[q], v);
+      __syncthreads();
+      if (lane == 0) sh_red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        double v = sh_red[0][q];
+        for (int w = 1; w < nwarp; ++w) v = red_combine(kind[q], v, sh_red[w][q]);
+        out[q] = v;
+      }
+      *counter = 0;
+    }
+  }
+  return last;
+}
+
+// Sum / max of `world` rank blocks of [G][2] totals for segment g.
+__device__ __forceinline__ void gather_totals(const double* totals, int world, int64_t G, int64_t g,
+                                              double& sum, double& mx) {
+  sum = 0.0;
+  mx = -INFINITY;
+  for (int r = 0; r < world; ++r) {
+    sum += totals[((size_t)r * G + g) * 2 + 0];
+    mx = fmax(mx, totals[((size_t)r * G + g) * 2 + 1]);
+  }
+}
+
+struct KernelDev {
+  int D, S;
+  int explr[KLERG_MAX_D];
+  float a[KLERG_MAX_D];       // sqrt(HALF_LOG2E/|scale|)
+  float gfac[KLERG_MAX_D];    // -1/(a*|scale|*nu): scaled-difference sum -> dgdx
+  float inv_nu;
+};
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+int sm_count();
+bool make_kernel_dev(const klerg_kernel_spec* k, KernelDev& out);
+
+}  // namespace klerg

@@ -1,0 +1,487 @@
+// Pairwise Gaussian-kernel passes of the KL-ergodic objective (sm_100a).
+//
+//   footprint_kernel : q_i = add_i + sum_j / max_j psi(state_j, s_i)     (a2, a3)
+//   grad_kernel      : dgdx_t = sum_i w_i * (-(x_t - s_i)/scale) * psi    (a4)
+//
+// Both work in pre-scaled coordinates (x' = x*a_d, a_d = sqrt(0.5*log2e/|scale_d|))
+// so one pair costs D FADD + D FFMA + 1 MUFU.EX2 (+1 FADD / +1 FMUL + D FFMA).
+// States are staged in shared memory and read as warp-wide broadcasts; samples
+// stream from the packed SoA array with coalesced 128-bit loads.
+#include <cstdio>
+
+#include "klerg_common.cuh"
+
+namespace klerg {
+
+// ---------------------------------------------------------------------------
+// pack: AoS [N][D] -> scaled SoA [D][ld]
+// ---------------------------------------------------------------------------
+__global__ void pack_samples_kernel(KernelDev k, const float* __restrict__ samples, int64_t N,
+                                    float* __restrict__ packed, int64_t ld) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += stride) {
+    for (int d = 0; d < k.D; ++d) {
+      float v = (i < N) ? samples[i * k.D + d] * k.a[d] : 0.f;
+      packed[(int64_t)d * ld + i] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// forward: footprint (sum) / spread (max)
+// ---------------------------------------------------------------------------
+constexpr int FP_THREADS = 256;
+constexpr int FP_CHUNK = 1024;  // state rows staged per pass
+
+struct FootArgs {
+  KernelDev k;
+  const float* states;
+  int64_t G, T, seg_stride;
+  const float* packed;
+  int64_t N, ld;
+  const float* add_in;
+  float* out;
+  int64_t out_stride;
+  double* totals;
+  void* ws;
+  int64_t ntiles;
+};
+
+template <int D>
+struct StateRow {
+  static constexpr int DP = (D <= 1) ? 1 : (D <= 2) ? 2 : (D <= 4) ? 4 : 8;
+};
+
+template <int D>
+__device__ __forceinline__ void load_state(const float* sh, int j, float (&x)[D]) {
+  constexpr int DP = StateRow<D>::DP;
+  const float* r = sh + j * DP;
+  if constexpr (DP == 1) {
+    x[0] = r[0];
+  } else if constexpr (DP == 2) {
+    float2 v = *reinterpret_cast<const float2*>(r);
+    x[0] = v.x;
+    if constexpr (D > 1) x[1] = v.y;
+  } else {
+    float4 v = *reinterpret_cast<const float4*>(r);
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = v.z;
+    if constexpr (D > 3) x[3] = v.w;
+    if constexpr (DP == 8) {
+      float4 w = *reinterpret_cast<const float4*>(r + 4);
+      x[4] = w.x;
+      if constexpr (D > 5) x[5] = w.y;
+      if constexpr (D > 6) x[6] = w.z;
+      if constexpr (D > 7) x[7] = w.w;
+    }
+  }
+}
+
+// Load SPT consecutive samples (SPT in {1,2,4}) of dimension d starting at i0.
+template <int SPT>
+__device__ __forceinline__ void load_samples(const float* __restrict__ p, int64_t i0, float (&s)[SPT]) {
+  if constexpr (SPT == 4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(p + i0));
+    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+  } else if constexpr (SPT == 2) {
+    float2 v = __ldg(reinterpret_cast<const float2*>(p + i0));
+    s[0] = v.x; s[1] = v.y;
+  } else {
+    s[0] = __ldg(p + i0);
+  }
+}
+
+template <int D, int MODE, int SPT>
+__global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a) {
+  constexpr int DP = StateRow<D>::DP;
+  constexpr int TILE = FP_THREADS * SPT;
+  __shared__ __align__(16) float sh[FP_CHUNK * DP];
+  const int tid = threadIdx.x;
+  const int nchunk = (int)((a.T + FP_CHUNK - 1) / FP_CHUNK);
+
+  for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
+    const float* st = a.states + g * a.seg_stride;
+    double tsum = 0.0, tmax = -INFINITY;
+
+    auto stage = [&](int c) {
+      const int64_t j0 = (int64_t)c * FP_CHUNK;
+      const int rows = (int)min((int64_t)FP_CHUNK, a.T - j0);
+      for (int e = tid; e < rows * DP; e += FP_THREADS) {
+        int j = e / DP, d = e - j * DP;
+        sh[e] = (d < D) ? st[(j0 + j) * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
+      }
+      return rows;
+    };
+
+    int rows_single = 0;
+    if (nchunk == 1) {
+      __syncthreads();
+      rows_single = stage(0);
+      __syncthreads();
+    }
+
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int64_t i0 = tile * TILE + (int64_t)tid * SPT;
+      float s[D][SPT];
+      float acc[SPT];
+      const bool inb = i0 < a.ld;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (inb) {
+          load_samples<SPT>(a.packed + (int64_t)d * a.ld, i0, s[d]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) s[d][q] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) acc[q] = (MODE == 0) ? 0.f : -INFINITY;
+
+      for (int c = 0; c < nchunk; ++c) {
+        int rows = rows_single;
+        if (nchunk > 1) {
+          __syncthreads();
+          rows = stage(c);
+          __syncthreads();
+        }
+#pragma unroll 4
+        for (int j = 0; j < rows; ++j) {
+          float x[D];
+          load_state<D>(sh, j, x);
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) {
+            float df = x[0] - s[0][q];
+            float e = -df * df;
+#pragma unroll
+            for (int d = 1; d < D; ++d) {
+              df = x[d] - s[d][q];
+              e = fmaf(-df, df, e);
+            }
+            if (MODE == 0) acc[q] += ex2_approx(e);
+            else acc[q] = fmaxf(acc[q], e);
+          }
+        }
+      }
+
+      // epilogue: scale, add base, store, local totals
+      float o[SPT];
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        float v = (MODE == 0) ? acc[q] : ex2_approx(acc[q]);
+        v *= a.k.inv_nu;
+        const int64_t i = i0 + q;
+        if (a.add_in != nullptr && i < a.N) v += a.add_in[i];
+        o[q] = v;
+        if (i < a.N) {
+          tsum += (double)v;
+          tmax = fmax(tmax, (double)v);
+        }
+      }
+      float* op = a.out + g * a.out_stride + i0;
+      if (SPT == 4 && i0 + 3 < a.N && ((a.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0)) {
+        *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < SPT; ++q)
+          if (i0 + q < a.N) op[q] = o[q];
+      }
+    }
+
+    const int kinds[2] = {RED_SUM, RED_MAX};
+    double vals[2] = {tsum, tmax};
+    grid_reduce<2>(kinds, vals, ws_seg_partials(a.ws, g), ws_seg_counter(a.ws, g), blockIdx.x, gridDim.x,
+                   a.totals + g * 2);
+    __syncthreads();
+  }
+}
+
+template <int D, int MODE>
+static int launch_footprint_spt(const FootArgs& a0, cudaStream_t stream) {
+  FootArgs a = a0;
+  const int sms = sm_count();
+  // choose samples-per-thread so that small workspaces still fill the chip
+  int spt = 4;
+  if (a.N * a.G < (int64_t)sms * FP_THREADS * 4 * 2) spt = 1;
+  const int tile = FP_THREADS * spt;
+  a.ntiles = (a.N + tile - 1) / tile;
+  int64_t gx = a.ntiles < 1 ? 1 : a.ntiles;
+  int64_t gy = a.G;
+  if (gy > 65535) gy = 65535;
+  const int64_t cap = (int64_t)sms * 8 < MAXBLK ? (int64_t)sms * 8 : MAXBLK;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (spt == 4)
+    footprint_kernel<D, MODE, 4><<<grid, FP_THREADS, 0, stream>>>(a);
+  else
+    footprint_kernel<D, MODE, 1><<<grid, FP_THREADS, 0, stream>>>(a);
+  return check_launch("footprint_kernel");
+}
+
+template <int MODE>
+static int launch_footprint_d(const FootArgs& a, cudaStream_t stream) {
+  switch (a.k.D) {
+    case 1: return launch_footprint_spt<1, MODE>(a, stream);
+    case 2: return launch_footprint_spt<2, MODE>(a, stream);
+    case 3: return launch_footprint_spt<3, MODE>(a, stream);
+    case 4: return launch_footprint_spt<4, MODE>(a, stream);
+    case 5: return launch_footprint_spt<5, MODE>(a, stream);
+    case 6: return launch_footprint_spt<6, MODE>(a, stream);
+    default: set_error("footprint: D=%d not instantiated (1..6)", a.k.D); return -2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// gradient
+// ---------------------------------------------------------------------------
+constexpr int GR_WARPS = 8;
+constexpr int GR_THREADS = GR_WARPS * 32;
+constexpr int GR_TILE = GR_THREADS * 4;  // samples per tile (w staged in smem)
+
+struct GradArgs {
+  KernelDev k;
+  const float* states;  // [H][S]
+  int64_t H;
+  const float* packed;
+  int64_t N, ld;
+  const float* w;       // explicit importance ratio (FUSED = false)
+  const float* v;       // FUSED: q_base + q_iter
+  const float* p;       // FUSED
+  const double* totals; // FUSED: [world][1][2]
+  int world;
+  float floor;
+  double* grad_out;     // [H][D] (FUSED) or nullptr
+  float* dgdx;          // [H][S] (explicit form) or nullptr
+  double* kl_out;       // [2] FUSED
+  void* ws;
+  int64_t ntiles;
+};
+
+template <int D, int WT, bool FUSED>
+__global__ void __launch_bounds__(GR_THREADS) grad_kernel(const GradArgs a) {
+  __shared__ __align__(16) float sh_w[GR_TILE];
+  __shared__ float sh_part[GR_WARPS * WT * D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = (blockIdx.y * GR_WARPS + warp) * WT;
+
+  float xs[WT][D];
+#pragma unroll
+  for (int kk = 0; kk < WT; ++kk) {
+    const int64_t t = t0 + kk;
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      xs[kk][d] = (t < a.H) ? a.states[t * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
+  }
+  float acc[WT][D];
+#pragma unroll
+  for (int kk = 0; kk < WT; ++kk)
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[kk][d] = 0.f;
+
+  double vsum = 1.0, maxc = 1.0;
+  if (FUSED) {
+    double vmax;
+    gather_totals(a.totals, a.world, 1, 0, vsum, vmax);
+    maxc = fmax(vmax / vsum, (double)a.floor);
+  }
+  const float inv_vsum_f = (float)vsum;  // divide by the fp32 sum like the reference
+  const float maxc_f = (float)maxc;
+  double kl_a = 0.0, kl_c = 0.0;
+
+  for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    __syncthreads();
+    {
+      const int64_t i0 = tile * GR_TILE + (int64_t)tid * 4;
+      float wv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t i = i0 + q;
+        float wq = 0.f;
+        if (i < a.N) {
+          if (FUSED) {
+            const float c = fmaxf(a.v[i] / inv_vsum_f, a.floor);
+            const float pi = a.p[i];
+            wq = pi * maxc_f / c;
+            if (blockIdx.y == 0) {
+              kl_a += (double)(pi * (logf(pi) - logf(c)));
+              kl_c += (double)c;
+            }
+          } else {
+            wq = a.w[i];
+          }
+        }
+        wv[q] = wq;
+      }
+      *reinterpret_cast<float4*>(&sh_w[tid * 4]) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int it = 0; it < GR_TILE / 128; ++it) {
+      const int off = (it * 32 + lane) * 4;
+      const int64_t i0 = tile * GR_TILE + off;
+      if (i0 >= a.ld) continue;
+      float s[D][4];
+#pragma unroll
+      for (int d = 0; d < D; ++d) load_samples<4>(a.packed + (int64_t)d * a.ld, i0, s[d]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&sh_w[off]);
+      const float wq[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int kk = 0; kk < WT; ++kk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float df[D];
+          df[0] = xs[kk][0] - s[0][q];
+          float e = -df[0] * df[0];
+#pragma unroll
+          for (int d = 1; d < D; ++d) {
+            df[d] = xs[kk][d] - s[d][q];
+            e = fmaf(-df[d], df[d], e);
+          }
+          const float wp = wq[q] * ex2_approx(e);
+#pragma unroll
+          for (int d = 0; d < D; ++d) acc[kk][d] = fmaf(wp, df[d], acc[kk][d]);
+        }
+      }
+    }
+  }
+
+  // lanes -> warp totals -> block partial [H_blk][D] in global (doubles)
+#pragma unroll
+  for (int kk = 0; kk < WT; ++kk)
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      float v = warp_sum_f(acc[kk][d]);
+      if (lane == 0) sh_part[(warp * WT + kk) * D + d] = v;
+    }
+  __syncthreads();
+  // this block covers states [blockIdx.y*GR_WARPS*WT, +GR_WARPS*WT)
+  const int nval = GR_WARPS * WT * D;
+  const int nblkx = gridDim.x;
+  double* parts = ws_grad_partials(a.ws);  // [blockIdx.x][H*D]
+  const int64_t HD = a.H * D;
+  for (int e = tid; e < nval; e += GR_THREADS) {
+    const int64_t t = (int64_t)blockIdx.y * GR_WARPS * WT + e / D;
+    if (t < a.H) parts[(size_t)blockIdx.x * HD + t * D + (e % D)] = (double)sh_part[e];
+  }
+  // KL partials ride along in the misc partial area (only blockIdx.y == 0 contributes)
+  const int kinds[2] = {RED_SUM, RED_SUM};
+  double vals[2] = {kl_a, kl_c};
+  double kl_tmp[2];
+  __shared__ double sh_kl[2];
+  const int blk_lin = blockIdx.y * gridDim.x + blockIdx.x;
+  const int nblk = gridDim.x * gridDim.y;
+  const bool last = grid_reduce<2>(kinds, vals, ws_misc_partials(a.ws), ws_misc_counter(a.ws, 0), blk_lin, nblk,
+                                   sh_kl);
+  (void)kl_tmp;
+  if (last) {
+    __syncthreads();
+    // fixed-order sum over x-blocks of the gradient partials
+    for (int64_t e = tid; e < HD; e += GR_THREADS) {
+      double sacc = 0.0;
+      for (int b = 0; b < nblkx; ++b) sacc += __ldcg(&parts[(size_t)b * HD + e]);
+      const int d = (int)(e % D);
+      const double gval = sacc * (double)a.k.gfac[d];
+      if (a.grad_out) a.grad_out[e] = gval;
+      if (a.dgdx) a.dgdx[(e / D) * a.k.S + a.k.explr[d]] = (float)gval;
+    }
+    if (FUSED && tid == 0 && a.kl_out) {
+      a.kl_out[0] = sh_kl[0];
+      a.kl_out[1] = sh_kl[1];
+    }
+  }
+}
+
+template <int D, int WT, bool FUSED>
+static int launch_grad(GradArgs a, cudaStream_t stream) {
+  a.ntiles = (a.N + GR_TILE - 1) / GR_TILE;
+  const int gy = (int)((a.H + GR_WARPS * WT - 1) / (GR_WARPS * WT));
+  int64_t gx = a.ntiles < 1 ? 1 : a.ntiles;
+  int64_t cap = (int64_t)sm_count() * 2 / gy;
+  if (cap < 1) cap = 1;
+  if (cap > GRAD_MAXBLK) cap = GRAD_MAXBLK;
+  if (gx > cap) gx = cap;
+  if ((int64_t)gx * gy > MAXBLK) { set_error("grad: grid too large"); return -2; }
+  grad_kernel<D, WT, FUSED><<<dim3((unsigned)gx, (unsigned)gy), GR_THREADS, 0, stream>>>(a);
+  return check_launch("grad_kernel");
+}
+
+template <int D, bool FUSED>
+static int launch_grad_wt(const GradArgs& a, cudaStream_t stream) {
+  const int64_t per_warp = (a.H + GR_WARPS - 1) / GR_WARPS;
+  if (per_warp <= 1) return launch_grad<D, 1, FUSED>(a, stream);
+  if (per_warp <= 2) return launch_grad<D, 2, FUSED>(a, stream);
+  if (per_warp <= 4) return launch_grad<D, 4, FUSED>(a, stream);
+  return launch_grad<D, 7, FUSED>(a, stream);
+}
+
+template <bool FUSED>
+static int launch_grad_d(const GradArgs& a, cudaStream_t stream) {
+  switch (a.k.D) {
+    case 1: return launch_grad_wt<1, FUSED>(a, stream);
+    case 2: return launch_grad_wt<2, FUSED>(a, stream);
+    case 3: return launch_grad_wt<3, FUSED>(a, stream);
+    case 4: return launch_grad_wt<4, FUSED>(a, stream);
+    case 5: return launch_grad_wt<5, FUSED>(a, stream);
+    case 6: return launch_grad_wt<6, FUSED>(a, stream);
+    default: set_error("gradient: D=%d not instantiated (1..6)", a.k.D); return -2;
+  }
+}
+
+}  // namespace klerg
+
+using namespace klerg;
+
+extern "C" int klerg_pack_samples(const klerg_kernel_spec* k, const float* samples, int64_t N, float* packed,
+                                  int64_t ld, void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (ld < N || (ld & 3)) { set_error("pack_samples: ld must be >= N and a multiple of 4"); return -1; }
+  if (ld == 0) return 0;
+  int64_t blocks = (ld + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  pack_samples_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kd, samples, N, packed, ld);
+  return check_launch("pack_samples_kernel");
+}
+
+extern "C" int klerg_footprint(const klerg_kernel_spec* k, int mode, const float* states, int64_t G, int64_t T,
+                               int64_t seg_stride, const float* packed, int64_t N, int64_t ld,
+                               const float* add_in, float* out, int64_t out_stride, double* totals,
+                               void* workspace, void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (G < 1 || N < 0 || T < 0 || ld < N || (ld & 3)) { set_error("footprint: bad sizes"); return -1; }
+  if (!workspace || !totals || !out) { set_error("footprint: null output/workspace"); return -1; }
+  FootArgs a{kd, states, G, T, seg_stride, packed, N, ld, add_in, out, out_stride, totals, workspace, 0};
+  if (mode == 0) return launch_footprint_d<0>(a, (cudaStream_t)stream);
+  if (mode == 1) return launch_footprint_d<1>(a, (cudaStream_t)stream);
+  set_error("footprint: mode must be 0 (sum) or 1 (max)");
+  return -1;
+}
+
+extern "C" int klerg_kl_gradient(const klerg_kernel_spec* k, const float* states, int64_t H, const float* packed,
+                                 int64_t N, int64_t ld, const float* w, float* dgdx, void* workspace,
+                                 void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (H < 1 || H > KLERG_MAX_H) { set_error("kl_gradient: H out of range"); return -1; }
+  cudaError_t e = cudaMemsetAsync(dgdx, 0, sizeof(float) * H * kd.S, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error("kl_gradient: memset failed: %s", cudaGetErrorString(e)); return -4; }
+  GradArgs a{};
+  a.k = kd; a.states = states; a.H = H; a.packed = packed; a.N = N; a.ld = ld; a.w = w;
+  a.dgdx = dgdx; a.ws = workspace; a.world = 1; a.floor = 0.f;
+  return launch_grad_d<false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int klerg_kl_gradient_fused(const klerg_kernel_spec* k, const float* states, int64_t H,
+                                       const float* packed, int64_t N, int64_t ld, const float* v,
+                                       const double* totals, int world, const float* p, float floor,
+                                       double* grad_part, double* kl_part, void* workspace, void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (H < 1 || H > KLERG_MAX_H) { set_error("kl_gradient_fused: H out of range"); return -1; }
+  GradArgs a{};
+  a.k = kd; a.states = states; a.H = H; a.packed = packed; a.N = N; a.ld = ld; a.v = v; a.p = p;
+  a.totals = totals; a.world = world; a.floor = floor; a.grad_out = grad_part; a.kl_out = kl_part;
+  a.ws = workspace;
+  return launch_grad_d<true>(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,778 @@
+// Planner-side kernels: vector statistics / renormalise / cost_norm, KL cost,
+// target-density weighting, rollout + barrier + linearisation, adjoint sweep,
+// memory-buffer row gather.  All tiny next to the pairwise passes; written so a
+// whole planner iteration stays on the device (no host arithmetic).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "klerg_common.cuh"
+
+namespace klerg {
+
+// ---------------------------------------------------------------------------
+// host utilities
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return -4;
+  }
+  return 0;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached = n;
+  }
+  return cached;
+}
+
+bool make_kernel_dev(const klerg_kernel_spec* k, KernelDev& out) {
+  if (!k) { set_error("kernel spec is null"); return false; }
+  if (k->D < 1 || k->D > KLERG_MAX_D || k->S < 1) { set_error("kernel spec: D=%d S=%d out of range", k->D, k->S); return false; }
+  out.D = k->D;
+  out.S = k->S;
+  const double nu = (double)k->nu;
+  out.inv_nu = (float)(1.0 / nu);
+  for (int d = 0; d < KLERG_MAX_D; ++d) {
+    out.explr[d] = 0;
+    out.a[d] = 0.f;
+    out.gfac[d] = 0.f;
+  }
+  for (int d = 0; d < k->D; ++d) {
+    if (k->explr[d] < 0 || k->explr[d] >= k->S) { set_error("kernel spec: explr[%d]=%d outside [0,%d)", d, k->explr[d], k->S); return false; }
+    const double sc = fabs((double)k->scale[d]);
+    if (!(sc > 0.0)) { set_error("kernel spec: scale[%d] must be non-zero", d); return false; }
+    const double a = sqrt(HALF_LOG2E / sc);
+    out.explr[d] = k->explr[d];
+    out.a[d] = (float)a;
+    out.gfac[d] = (float)(-1.0 / ((double)(float)a * sc * nu));
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// vector statistics, renormalize, cost_norm
+// ---------------------------------------------------------------------------
+constexpr int EW_THREADS = 256;
+
+static int ew_blocks(int64_t N) {
+  int64_t b = (N + EW_THREADS * 4 - 1) / (EW_THREADS * 4);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) vector_stats_kernel(const float* __restrict__ x, int64_t N,
+                                                                    double* stats, void* ws) {
+  double s = 0.0, mx = -INFINITY, mn = INFINITY, nn = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (v != v) { nn += 1.0; continue; }
+    s += (double)v;
+    mx = fmax(mx, (double)v);
+    mn = fmin(mn, (double)v);
+  }
+  const int kinds[4] = {RED_SUM, RED_MAX, RED_MIN, RED_SUM};
+  double vals[4] = {s, mx, mn, nn};
+  grid_reduce<4>(kinds, vals, ws_misc_partials(ws), ws_misc_counter(ws, 1), blockIdx.x, gridDim.x, stats);
+}
+
+// out = c / max c,  c = max(x / sum, floor); stats = {sum, max, ...} of x
+__global__ void renorm_apply_kernel(const float* __restrict__ x, int64_t N, const double* __restrict__ stats,
+                                    float floor, float* __restrict__ out) {
+  const float sum = (float)stats[0];
+  const float maxc = fmaxf((float)stats[1] / sum, floor);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fmaxf(x[i] / sum, floor) / maxc;
+}
+
+// NaN -> 1e-6 and accumulate the sum of the sanitised vector
+__global__ void __launch_bounds__(EW_THREADS) cost_norm_pass1(float* __restrict__ x, int64_t N, double* stats, void* ws) {
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (v != v) { v = 1e-6f; x[i] = v; }
+    s += (double)v;
+  }
+  const int kinds[1] = {RED_SUM};
+  double vals[1] = {s};
+  grid_reduce<1>(kinds, vals, ws_misc_partials(ws), ws_misc_counter(ws, 1), blockIdx.x, gridDim.x, stats);
+}
+
+__global__ void cost_norm_pass2(float* __restrict__ x, int64_t N, const double* __restrict__ stats) {
+  const float sum = (float)stats[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = x[i] / sum;
+}
+
+// ---------------------------------------------------------------------------
+// KL cost of get_cost (klerg.py:694-699) for G candidates
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) kl_cost_partial_kernel(const float* __restrict__ v, int64_t v_stride,
+                                                                       int64_t G, int64_t N,
+                                                                       const double* __restrict__ totals, int world,
+                                                                       const float* __restrict__ p, float floor,
+                                                                       double* kl_part, void* ws) {
+  for (int64_t g = blockIdx.y; g < G; g += gridDim.y) {
+    double vsum, vmax;
+    gather_totals(totals, world, G, g, vsum, vmax);
+    const float vs = (float)vsum;
+    const float maxc = fmaxf((float)vmax / vs, floor);
+    const float* vg = v + g * v_stride;
+    double sa = 0.0, sc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+      float c = fmaxf(vg[i] / vs, floor);
+      if (c != c) c = 1e-6f * maxc;  // cost_norm: NaN in q -> 1e-6 (q = c/maxc)
+      float pi = p[i];
+      if (pi != pi) pi = 1e-6f;
+      sa += (double)(pi * (logf(pi) - logf(c)));
+      sc += (double)c;
+    }
+    const int kinds[2] = {RED_SUM, RED_SUM};
+    double vals[2] = {sa, sc};
+    grid_reduce<2>(kinds, vals, ws_seg_partials(ws, g), ws_seg_counter(ws, g), blockIdx.x, gridDim.x, kl_part + g * 2);
+    __syncthreads();
+  }
+}
+
+__global__ void kl_cost_final_kernel(const double* __restrict__ kl_part, int world, int64_t G,
+                                     const double* __restrict__ p_stats, const float* __restrict__ barrier_sum,
+                                     float* __restrict__ cost) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  double sa = 0.0, sc = 0.0;
+  for (int r = 0; r < world; ++r) {
+    sa += kl_part[((size_t)r * G + g) * 2 + 0];
+    sc += kl_part[((size_t)r * G + g) * 2 + 1];
+  }
+  const double sp = p_stats[0];
+  const double dkl = sa / sp - log(sp) + log(sc);
+  cost[g] = (float)dkl + (barrier_sum ? barrier_sum[g] : 0.f);
+}
+
+// ---------------------------------------------------------------------------
+// target-density weighting (klerg.py:452-486)
+// ---------------------------------------------------------------------------
+struct LimDev {
+  int D;
+  float lo[KLERG_MAX_D], hi[KLERG_MAX_D];
+};
+
+__device__ __forceinline__ bool outside_box(const float* __restrict__ samples, int64_t i, const LimDev& L) {
+  bool out = false;
+  for (int d = 0; d < L.D; ++d) {
+    const float s = samples[i * L.D + d];
+    out |= (s < L.lo[d]) | (s > L.hi[d]);
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) target_stage1_kernel(const float* __restrict__ samples, LimDev L, int64_t N,
+                                                                     const float* __restrict__ spread,
+                                                                     const float* __restrict__ p, double* acc, void* ws) {
+  double smax = -INFINITY, sin_ = 0.0, nout = 0.0, pmin = INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    pmin = fmin(pmin, (double)p[i]);
+    if (spread) {
+      const float s = spread[i];
+      smax = fmax(smax, (double)s);
+      if (outside_box(samples, i, L)) nout += 1.0;
+      else sin_ += (double)s;
+    }
+  }
+  if (!spread) smax = 1.0;
+  const int kinds[4] = {RED_MAX, RED_SUM, RED_SUM, RED_MIN};
+  double vals[4] = {smax, sin_, nout, pmin};
+  grid_reduce<4>(kinds, vals, ws_misc_partials(ws), ws_misc_counter(ws, 1), blockIdx.x, gridDim.x, acc);
+}
+
+__global__ void __launch_bounds__(EW_THREADS) target_stage2_kernel(int mode, const float* __restrict__ samples, LimDev L,
+                                                                     int64_t N, const float* __restrict__ spread,
+                                                                     const float* __restrict__ p,
+                                                                     const double* __restrict__ expo,
+                                                                     float* __restrict__ p2, double* acc, void* ws) {
+  const float ex = (float)expo[0];
+  const float pmin = (float)expo[1];
+  const float smax = (float)expo[2];
+  double s = 0.0, mx = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = p[i];
+    if (mode == 0) {
+      v = powf(v, ex);
+    } else if (mode == 1) {
+      float sp = 0.f;  // empty buffer: spread = zeros(1)
+      if (spread) sp = outside_box(samples, i, L) ? 1.f : spread[i] / smax;
+      v = v + (1.f - sp) * pmin;
+    }
+    p2[i] = v;
+    s += (double)v;
+    mx = fmax(mx, (double)v);
+  }
+  const int kinds[2] = {RED_SUM, RED_MAX};
+  double vals[2] = {s, mx};
+  grid_reduce<2>(kinds, vals, ws_misc_partials(ws), ws_misc_counter(ws, 1), blockIdx.x, gridDim.x, acc);
+}
+
+__global__ void __launch_bounds__(EW_THREADS) target_stage3_kernel(const float* __restrict__ p2, int64_t N,
+                                                                     const double* __restrict__ acc2, int renorm,
+                                                                     float floor, float temp, float* __restrict__ p,
+                                                                     double* p_stats, void* ws) {
+  const float sum = (float)acc2[0];
+  const float maxc = fmaxf((float)acc2[1] / sum, floor);
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = p2[i];
+    if (renorm) v = fmaxf(v / sum, floor) / maxc;
+    if (temp != 1.0f) v = powf(v, temp);
+    p[i] = v;
+    s += (double)((v != v) ? 1e-6f : v);  // cost_norm sanitises NaN before summing
+  }
+  const int kinds[1] = {RED_SUM};
+  double vals[1] = {s};
+  grid_reduce<1>(kinds, vals, ws_misc_partials(ws), ws_misc_counter(ws, 1), blockIdx.x, gridDim.x, p_stats);
+}
+
+// ---------------------------------------------------------------------------
+// dynamics + barrier (dynamics.py, barrier.py)
+// ---------------------------------------------------------------------------
+struct DynDev {
+  int kind, S, A;
+  float dt;
+  int rpw[3];
+  int has_map;
+  float rot_lo[3], rot_hi[3], ang_lo[3], ang_hi[3];
+};
+struct BarDev {
+  int n;
+  float lo[KLERG_MAX_S], hi[KLERG_MAX_S], w[KLERG_MAX_S], pw[KLERG_MAX_S];
+};
+
+__device__ __forceinline__ float powi_or_f(float d, float pw) {
+  if (pw == 4.f) { const float d2 = d * d; return d2 * d2; }
+  if (pw == 3.f) return d * d * d;
+  if (pw == 2.f) return d * d;
+  if (pw == 1.f) return d;
+  return powf(d, pw);
+}
+
+__device__ float barrier_value(const BarDev& b, const float* x) {
+  float acc = 0.f;
+  for (int i = 0; i < b.n; ++i) {
+    const float xi = x[i];
+    if (xi <= b.lo[i]) acc += b.w[i] * powi_or_f(xi - b.lo[i], b.pw[i]);
+    if (xi >= b.hi[i]) acc += b.w[i] * powi_or_f(xi - b.hi[i], b.pw[i]);
+  }
+  return acc;
+}
+
+__device__ void barrier_grad(const BarDev& b, const float* x, int S, float* g) {
+  for (int i = 0; i < S; ++i) {
+    float acc = 0.f;
+    if (i < b.n) {
+      const float xi = x[i];
+      if (xi <= b.lo[i]) acc += b.pw[i] * b.w[i] * powi_or_f(xi - b.lo[i], b.pw[i] - 1.f);
+      if (xi >= b.hi[i]) acc += b.pw[i] * b.w[i] * powi_or_f(xi - b.hi[i], b.pw[i] - 1.f);
+    }
+    g[i] = acc;
+  }
+}
+
+__device__ __forceinline__ float affine_map(float v, float ilo, float ihi, float olo, float ohi) {
+  return (v - ilo) / (ihi - ilo) * (ohi - olo) + olo;
+}
+
+__device__ void euler_xyz_to_matrix(const float* rot, float* R) {
+  // Rz(yaw) * Ry(pitch) * Rx(roll)   (rotations.py:70-96, order flipped to match scipy)
+  float sr, cr, sp, cp, sy, cy;
+  sincosf(rot[0], &sr, &cr);
+  sincosf(rot[1], &sp, &cp);
+  sincosf(rot[2], &sy, &cy);
+  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
+}
+
+__device__ __forceinline__ float py_mod(float x, float m) {
+  float r = fmodf(x, m);
+  if (r < 0.f) r += m;
+  return r;
+}
+
+// Rn = expm(hat(w) dt) * R via Rodrigues; new angles = wrap(euler_XYZ(Rn))   (dynamics.py:213-222)
+__device__ void advance_rotation(const float* R, const float* w, float dt, float* Rn, float* rot) {
+  const float kx = w[0] * dt, ky = w[1] * dt, kz = w[2] * dt;
+  const float th2 = kx * kx + ky * ky + kz * kz;
+  float A, B;  // sin(th)/th, (1-cos(th))/th^2
+  if (th2 < 1e-8f) {
+    A = 1.f - th2 / 6.f;
+    B = 0.5f - th2 / 24.f;
+  } else {
+    const float th = sqrtf(th2);
+    float s, c;
+    sincosf(th, &s, &c);
+    A = s / th;
+    B = (1.f - c) / th2;
+  }
+  // E = I + A K + B K^2,  K = hat(k)
+  float E[9];
+  E[0] = 1.f - B * (ky * ky + kz * kz); E[1] = -A * kz + B * kx * ky;         E[2] = A * ky + B * kx * kz;
+  E[3] = A * kz + B * kx * ky;          E[4] = 1.f - B * (kx * kx + kz * kz); E[5] = -A * kx + B * ky * kz;
+  E[6] = -A * ky + B * kx * kz;         E[7] = A * kx + B * ky * kz;          E[8] = 1.f - B * (kx * kx + ky * ky);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = E[r * 3] * R[c] + E[r * 3 + 1] * R[3 + c] + E[r * 3 + 2] * R[6 + c];
+  const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
+  float r0 = atan2f(Rn[7], Rn[8]);
+  float r1 = asinf(-Rn[6]);
+  float r2 = atan2f(Rn[3], Rn[0]);
+  rot[0] = py_mod(r0, two_pi);
+  rot[1] = py_mod(r1 + pi, two_pi) - pi;
+  rot[2] = py_mod(r2 + pi, two_pi) - pi;
+}
+
+// d(pos rate)/d(vel) block: 0.8 I, with the rpw x rpw entries replaced by E(rot) R   (dynamics.py:189-211,283-289)
+__device__ void lin_block(const DynDev& d, const float* x, const float* R, float* P) {
+  const int a = d.A;
+  for (int i = 0; i < a * a; ++i) P[i] = 0.f;
+  for (int i = 0; i < a; ++i) P[i * a + i] = 0.8f;
+  if (d.kind != KLERG_DYN_ROLL) return;
+  float rot[3];
+  for (int k = 0; k < 3; ++k) {
+    rot[k] = x[d.rpw[k]];
+    if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
+  }
+  rot[1] += 1e-5f;
+  float s0, c0;
+  sincosf(rot[0], &s0, &c0);
+  const float t1 = tanf(rot[1]), c1 = cosf(rot[1]);
+  const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / c1, c0 / c1};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      P[d.rpw[r] * a + d.rpw[c]] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
+}
+
+// One RK4 step (closed form: A is nilpotent of index 2, so RK4 == exact cubic).
+__device__ void dyn_step(const DynDev& d, const float* x, float* R, const float* u, float* xn) {
+  const int a = d.A;
+  const float dt = d.dt;
+  if (d.kind == KLERG_DYN_SINGLE) {
+    for (int i = 0; i < a; ++i) xn[i] = x[i] + dt * u[i];
+    return;
+  }
+  const float c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
+  for (int i = 0; i < a; ++i) {
+    xn[i] = x[i] + (c1 * x[a + i] + c2 * u[i]);
+    xn[a + i] = x[a + i] + dt * u[i];
+  }
+  if (d.kind == KLERG_DYN_SPEED) {
+    for (int i = 0; i < a; ++i) xn[2 * a + i] = fabsf(xn[a + i]);
+  } else if (d.kind == KLERG_DYN_ROLL) {
+    float w[3], Rn[9], rot[3];
+    for (int k = 0; k < 3; ++k) w[k] = x[a + d.rpw[k]];
+    advance_rotation(R, w, dt, Rn, rot);
+    for (int k = 0; k < 3; ++k) {
+      float v = rot[k];
+      if (d.has_map) v = affine_map(v, d.ang_lo[k], d.ang_hi[k], d.rot_lo[k], d.rot_hi[k]);
+      xn[d.rpw[k]] = v;
+    }
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  }
+}
+
+__global__ void rollout_kernel(DynDev d, BarDev bar, const float* __restrict__ x0, const float* __restrict__ R0,
+                               const float* __restrict__ u, int64_t B, int64_t H, float* __restrict__ traj,
+                               float* __restrict__ barrier_sum, float* __restrict__ dbarr, float* __restrict__ P,
+                               float* __restrict__ R_out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float x[KLERG_MAX_S], xn[KLERG_MAX_S], R[9], ut[KLERG_MAX_A];
+  const int S = d.S, a = d.A;
+  for (int i = 0; i < S; ++i) x[i] = x0[i];
+  if (d.kind == KLERG_DYN_ROLL) {
+    if (R0) {
+      for (int i = 0; i < 9; ++i) R[i] = R0[i];
+    } else {
+      float rot[3];
+      for (int k = 0; k < 3; ++k) {
+        rot[k] = x[d.rpw[k]];
+        if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
+      }
+      euler_xyz_to_matrix(rot, R);
+    }
+  } else {
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
+  }
+  float* tr = traj + b * (H + 1) * S;
+  for (int i = 0; i < S; ++i) tr[i] = x[i];
+  float bsum = 0.f;
+  for (int64_t t = 0; t < H; ++t) {
+    if (dbarr) barrier_grad(bar, x, S, dbarr + (b * H + t) * S);
+    if (P) lin_block(d, x, R, P + (b * H + t) * a * a);
+    for (int i = 0; i < a; ++i) ut[i] = u[(b * H + t) * a + i];
+    dyn_step(d, x, R, ut, xn);
+    for (int i = 0; i < S; ++i) {
+      x[i] = xn[i];
+      tr[(t + 1) * S + i] = xn[i];
+    }
+    bsum += barrier_value(bar, x);
+  }
+  if (barrier_sum) barrier_sum[b] = bsum;
+  if (R_out)
+    for (int i = 0; i < 9; ++i) R_out[b * 9 + i] = R[i];
+}
+
+__global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int64_t T, int S, float* __restrict__ value,
+                                    float* __restrict__ grad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float row[KLERG_MAX_S], g[KLERG_MAX_S];
+  for (int i = 0; i < S; ++i) row[i] = x[t * S + i];
+  if (value) value[t] = barrier_value(bar, row);
+  if (grad) {
+    barrier_grad(bar, row, S, g);
+    for (int i = 0; i < S; ++i) grad[t * S + i] = g[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// adjoint sweep (klerg.py:433-450, 590-593), default policy (dmudx = 0)
+// ---------------------------------------------------------------------------
+struct AdjArgs {
+  DynDev d;
+  KernelDev k;
+  int64_t H;
+  const double* grad_part;
+  int world;
+  const float* dbarr;
+  const float* P;
+  const float* traj;
+  const float* u;
+  float rinv[KLERG_MAX_A];
+  float alpha;
+  float clo[KLERG_MAX_A], chi[KLERG_MAX_A];
+  float* dgdx;
+  float* du;
+  float* djdlam;
+  float* u_star;
+};
+
+__global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
+  const int S = a.d.S, A = a.d.A, D = a.k.D;
+  const int64_t H = a.H;
+  // phase 1: dgdx[H][S] = sum over ranks of the explored-dim partials
+  for (int64_t e = threadIdx.x; e < H * S; e += blockDim.x) a.dgdx[e] = 0.f;
+  __syncthreads();
+  for (int64_t e = threadIdx.x; e < H * D; e += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < a.world; ++r) s += a.grad_part[(size_t)r * H * D + e];
+    a.dgdx[(e / D) * S + a.k.explr[e % D]] = (float)s;
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  // phase 2: lane i < A carries component i of rho_p, rho_v (and rho_m for SPEED)
+  const int i = threadIdx.x;
+  const bool act = i < A;
+  const bool single = a.d.kind == KLERG_DYN_SINGLE;
+  const bool speed = a.d.kind == KLERG_DYN_SPEED;
+  const float h = -a.d.dt;
+  float rp = 0.f, rv = 0.f, rm = 0.f;
+  for (int64_t t = H - 1; t >= 0; --t) {
+    float gp = 0.f, gv = 0.f, gm = 0.f;
+    if (act) {
+      gp = a.dgdx[t * S + i] - a.dbarr[t * S + i];
+      if (!single) gv = a.dgdx[t * S + A + i] - a.dbarr[t * S + A + i];
+      if (speed) gm = a.dgdx[t * S + 2 * A + i] - a.dbarr[t * S + 2 * A + i];
+    }
+    float btr;  // (B^T rho)_i
+    if (single) {
+      rp = rp + h * gp;
+      btr = rp;
+    } else {
+      float ptr_ = 0.f, ptg = 0.f;  // (P^T rho_p)_i, (P^T g_p)_i
+      if (a.P) {
+        const float* Pt = a.P + t * A * A;
+        for (int kk = 0; kk < A; ++kk) {
+          const float rk = __shfl_sync(0xffffffffu, rp, kk);
+          const float gk = __shfl_sync(0xffffffffu, gp, kk);
+          const float pk = act ? Pt[kk * A + i] : 0.f;
+          ptr_ = fmaf(pk, rk, ptr_);
+          ptg = fmaf(pk, gk, ptg);
+        }
+      } else {
+        ptr_ = 0.8f * rp;
+        ptg = 0.8f * gp;
+      }
+      const float rv_n = rv + h * (gv - ptr_) - 0.5f * h * h * ptg;
+      rp = rp + h * gp;
+      rv = rv_n;
+      btr = rv;
+      if (speed) {
+        rm = rm + h * gm;
+        float sg = 0.f;
+        if (act) {
+          const float vel = a.traj[t * S + A + i];
+          sg = (vel < 0.f) ? -1.f : 1.f;
+        }
+        btr = rv + sg * rm;
+      }
+    }
+    const float dui = act ? -a.rinv[i] * btr : 0.f;
+    const float dj = warp_sum_f(act ? btr * dui : 0.f);
+    if (act) {
+      a.du[t * A + i] = dui;
+      const float us = a.u[t * A + i] + a.alpha * dui;
+      a.u_star[t * A + i] = fminf(fmaxf(us, a.clo[i]), a.chi[i]);
+    }
+    if (i == 0) a.djdlam[t] = dj;
+  }
+}
+
+struct CombineArgs {
+  int n, world;
+  int kind[8];
+};
+
+__global__ void combine_blocks_kernel(CombineArgs c, const double* __restrict__ blocks, double* __restrict__ out) {
+  const int q = threadIdx.x;
+  if (q >= c.n) return;
+  double v = red_identity(c.kind[q]);
+  for (int r = 0; r < c.world; ++r) v = red_combine(c.kind[q], v, blocks[(size_t)r * c.n + q]);
+  out[q] = v;
+}
+
+// expo = {mean_i spread'_i, min p, max spread} from acc = {smax, sum_inside, n_outside, min p}
+__global__ void target_exponent_kernel(const double* __restrict__ acc, int64_t N_total, double* __restrict__ expo) {
+  if (threadIdx.x == 0) {
+    const float smax = (float)acc[0];
+    const float mean = (float)(((double)((float)acc[1] / smax) + acc[2]) / (double)N_total);
+    expo[0] = (double)mean;
+    expo[1] = acc[3];
+    expo[2] = acc[0];
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, int S, const int64_t* __restrict__ idx, int64_t M,
+                                   float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < M * S; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = e / S;
+    out[e] = table[idx[m] * S + (e - m * S)];
+  }
+}
+
+static bool make_dyn(const klerg_dyn_spec* s, DynDev& d) {
+  if (!s) { set_error("dyn spec is null"); return false; }
+  if (s->kind < 0 || s->kind > 3 || s->S < 1 || s->S > KLERG_MAX_S || s->A < 1 || s->A > KLERG_MAX_A) {
+    set_error("dyn spec out of range (kind=%d S=%d A=%d)", s->kind, s->S, s->A);
+    return false;
+  }
+  const int need = s->kind == KLERG_DYN_SINGLE ? s->A : (s->kind == KLERG_DYN_SPEED ? 3 * s->A : 2 * s->A);
+  if (s->S != need) { set_error("dyn spec: S=%d inconsistent with kind %d, A=%d", s->S, s->kind, s->A); return false; }
+  d.kind = s->kind; d.S = s->S; d.A = s->A; d.dt = s->dt; d.has_map = s->has_ang_map;
+  for (int k = 0; k < 3; ++k) {
+    d.rpw[k] = s->rpw[k];
+    d.rot_lo[k] = s->rot_lo[k]; d.rot_hi[k] = s->rot_hi[k];
+    d.ang_lo[k] = s->ang_lo[k]; d.ang_hi[k] = s->ang_hi[k];
+    if (s->kind == KLERG_DYN_ROLL && (s->rpw[k] < 0 || s->rpw[k] >= s->A)) { set_error("dyn spec: rpw index out of range"); return false; }
+  }
+  return true;
+}
+
+static bool make_bar(const klerg_barrier_spec* s, BarDev& b) {
+  memset(&b, 0, sizeof(b));
+  if (!s) return true;  // NoBarrier
+  if (s->n < 0 || s->n > KLERG_MAX_S) { set_error("barrier spec: n out of range"); return false; }
+  b.n = s->n;
+  for (int i = 0; i < s->n; ++i) { b.lo[i] = s->lo[i]; b.hi[i] = s->hi[i]; b.w[i] = s->weight[i]; b.pw[i] = s->power[i]; }
+  return true;
+}
+
+static bool make_lim(int D, const float* lo, const float* hi, LimDev& L) {
+  if (D < 1 || D > KLERG_MAX_D) { set_error("target: D out of range"); return false; }
+  L.D = D;
+  for (int d = 0; d < D; ++d) { L.lo[d] = lo ? lo[d] : -INFINITY; L.hi[d] = hi ? hi[d] : INFINITY; }
+  return true;
+}
+
+}  // namespace klerg
+
+using namespace klerg;
+
+extern "C" const char* klerg_last_error(void) { return g_err; }
+extern "C" int klerg_abi_version(void) { return 1; }
+
+extern "C" int klerg_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("device_info: %s", cudaGetErrorString(e)); return -4; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("device_info: %s", cudaGetErrorString(e)); return -4; }
+  if (sms) *sms = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return 0;
+}
+
+extern "C" size_t klerg_workspace_bytes(int64_t G) {
+  if (G < 1) G = 1;
+  return HEAD_BYTES + (size_t)G * SEG_BYTES;
+}
+
+extern "C" int klerg_vector_stats(const float* x, int64_t N, double* stats, void* ws, void* stream) {
+  vector_stats_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(x, N, stats, ws);
+  return check_launch("vector_stats_kernel");
+}
+
+extern "C" int klerg_renormalize(const float* x, int64_t N, float floor, float* out, void* ws, void* stream) {
+  double* stats = ws_misc_partials(ws) + (size_t)MAXBLK * 4;  // tail of the misc area
+  vector_stats_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(x, N, stats, ws);
+  renorm_apply_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(x, N, stats, floor, out);
+  return check_launch("renormalize");
+}
+
+extern "C" int klerg_renormalize_with_stats(const float* x, int64_t N, const double* stats, float floor, float* out,
+                                            void* stream) {
+  renorm_apply_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(x, N, stats, floor, out);
+  return check_launch("renorm_apply_kernel");
+}
+
+extern "C" int klerg_cost_norm(float* x, int64_t N, void* ws, void* stream) {
+  double* stats = ws_misc_partials(ws) + (size_t)MAXBLK * 4;
+  cost_norm_pass1<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(x, N, stats, ws);
+  cost_norm_pass2<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(x, N, stats);
+  return check_launch("cost_norm");
+}
+
+extern "C" int klerg_kl_cost_partial(const float* v, int64_t v_stride, int64_t G, int64_t N, const double* totals,
+                                     int world, const float* p, float floor, double* kl_part, void* ws,
+                                     void* stream) {
+  if (G < 1) { set_error("kl_cost_partial: G < 1"); return -1; }
+  int gx = ew_blocks(N);
+  if (G > 1) {
+    // many candidates: keep the total CTA count near 8 waves
+    int64_t cap = ((int64_t)sm_count() * 8 + G - 1) / G;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = (int)cap;
+  }
+  const unsigned gy = (unsigned)(G > 65535 ? 65535 : G);
+  kl_cost_partial_kernel<<<dim3(gx, gy), EW_THREADS, 0, (cudaStream_t)stream>>>(v, v_stride, G, N, totals, world, p,
+                                                                                 floor, kl_part, ws);
+  return check_launch("kl_cost_partial_kernel");
+}
+
+extern "C" int klerg_kl_cost_final(const double* kl_part, int world, int64_t G, const double* p_stats,
+                                   const float* barrier_sum, float* cost, void* stream) {
+  kl_cost_final_kernel<<<(unsigned)((G + 127) / 128), 128, 0, (cudaStream_t)stream>>>(kl_part, world, G, p_stats,
+                                                                                      barrier_sum, cost);
+  return check_launch("kl_cost_final_kernel");
+}
+
+extern "C" int klerg_target_stage1(const float* samples, int32_t D, int64_t N, const float* lim_lo,
+                                   const float* lim_hi, const float* spread, const float* p, double* acc, void* ws,
+                                   void* stream) {
+  LimDev L;
+  if (!make_lim(D, lim_lo, lim_hi, L)) return -1;
+  target_stage1_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(samples, L, N, spread, p, acc, ws);
+  return check_launch("target_stage1_kernel");
+}
+
+extern "C" int klerg_combine_blocks(const double* blocks, int world, int n, const int* kinds, double* out,
+                                    void* stream) {
+  if (n < 1 || n > 8 || world < 1) { set_error("combine_blocks: n in 1..8, world >= 1"); return -1; }
+  CombineArgs c{};
+  c.n = n; c.world = world;
+  for (int q = 0; q < n; ++q) {
+    if (kinds[q] < 0 || kinds[q] > 2) { set_error("combine_blocks: bad kind"); return -1; }
+    c.kind[q] = kinds[q];
+  }
+  combine_blocks_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c, blocks, out);
+  return check_launch("combine_blocks_kernel");
+}
+
+extern "C" int klerg_target_exponent(const double* acc, int64_t N_total, double* expo, void* stream) {
+  if (N_total < 1) { set_error("target_exponent: N_total < 1"); return -1; }
+  target_exponent_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, N_total, expo);
+  return check_launch("target_exponent_kernel");
+}
+
+extern "C" int klerg_target_stage2(int mode, const float* samples, int32_t D, int64_t N, const float* lim_lo,
+                                   const float* lim_hi, const float* spread, const float* p, const double* expo,
+                                   float* p2, double* acc, void* ws, void* stream) {
+  LimDev L;
+  if (!make_lim(D, lim_lo, lim_hi, L)) return -1;
+  if (mode < 0 || mode > 2) { set_error("target_stage2: bad mode"); return -1; }
+  target_stage2_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(mode, samples, L, N, spread, p, expo,
+                                                                               p2, acc, ws);
+  return check_launch("target_stage2_kernel");
+}
+
+extern "C" int klerg_target_stage3(const float* p2, int64_t N, const double* acc2, int renorm, float floor,
+                                   float temp, float* p, double* p_stats, void* ws, void* stream) {
+  target_stage3_kernel<<<ew_blocks(N), EW_THREADS, 0, (cudaStream_t)stream>>>(p2, N, acc2, renorm, floor, temp, p,
+                                                                               p_stats, ws);
+  return check_launch("target_stage3_kernel");
+}
+
+extern "C" int klerg_rollout(const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar, const float* x0,
+                             const float* R0, const float* u, int64_t B, int64_t H, float* traj,
+                             float* barrier_sum, float* dbarr, float* P, float* R_out, void* stream) {
+  DynDev d;
+  BarDev b;
+  if (!make_dyn(dyn, d) || !make_bar(bar, b)) return -1;
+  if (B < 1 || H < 0) { set_error("rollout: bad sizes"); return -1; }
+  const int threads = B >= 128 ? 128 : 32;
+  rollout_kernel<<<(unsigned)((B + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      d, b, x0, R0, u, B, H, traj, barrier_sum, dbarr, P, R_out);
+  return check_launch("rollout_kernel");
+}
+
+extern "C" int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x, int64_t T, int32_t S, float* value,
+                                  float* grad, void* stream) {
+  BarDev b;
+  if (!make_bar(bar, b)) return -1;
+  if (S < 1 || S > KLERG_MAX_S) { set_error("barrier_eval: S out of range"); return -1; }
+  if (T < 1) return 0;
+  barrier_eval_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(b, x, T, S, value, grad);
+  return check_launch("barrier_eval_kernel");
+}
+
+extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H,
+                             const double* grad_part, int world, const float* dbarr, const float* P,
+                             const float* traj, const float* u, const float* Rinv_diag, float alpha,
+                             const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
+                             float* u_star, void* stream) {
+  AdjArgs a{};
+  if (!make_dyn(dyn, a.d) || !make_kernel_dev(k, a.k)) return -1;
+  if (H < 1 || H > KLERG_MAX_H) { set_error("adjoint: H out of range"); return -1; }
+  a.H = H; a.grad_part = grad_part; a.world = world; a.dbarr = dbarr; a.P = P; a.traj = traj; a.u = u;
+  a.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
+  for (int i = 0; i < a.d.A; ++i) { a.rinv[i] = Rinv_diag[i]; a.clo[i] = ctrl_lo[i]; a.chi[i] = ctrl_hi[i]; }
+  adjoint_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("adjoint_kernel");
+}
+
+extern "C" int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t M, float* out,
+                                 void* stream) {
+  if (M < 1) return 0;
+  int64_t blocks = (M * S + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, S, idx, M, out);
+  return check_launch("gather_rows_kernel");
+}

@@ -1,0 +1,213 @@
+/*
+ * klerg_b200.h -- C ABI of the B200-native KL-ergodic hot path (libklerg_b200.so).
+ *
+ * Drop-in boundary for franka_test/scripts/control_torch of
+ * apinosky/embodied-active-learning-vision.  The reference has no native
+ * interface for this path (it is torch-CPU Python), so each
+ * entry point cites the reference *function* whose arithmetic it replaces
+ * (paths relative to franka_test/scripts/control_torch).  The Python mirror in
+ * embodied-active-learning-vision_b200/control_torch binds these with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter is a `const klerg_*_spec*` (small host struct, read at
+ *     call time) or is documented as host memory;
+ *   - nothing is allocated inside: outputs and `workspace` are caller-owned;
+ *     `workspace` must be at least klerg_workspace_bytes() bytes, zero-filled
+ *     once at allocation (kernels leave it zeroed where they need zeros);
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*); no call synchronises the device;
+ *   - return value 0 = success, negative = error (see klerg_last_error());
+ *     no exceptions cross the boundary;
+ *   - fp32 data, row-major; indices int64 (torch.randperm's dtype);
+ *   - reentrant per stream, not thread-safe per workspace.
+ */
+#ifndef KLERG_B200_H
+#define KLERG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLERG_MAX_D 8   /* explored dimensions        (reference uses 2..6) */
+#define KLERG_MAX_S 24  /* planner state dimension    (12 for xyzrpw)       */
+#define KLERG_MAX_A 8   /* controls                                         */
+#define KLERG_MAX_H 256 /* planning horizon                                 */
+
+/* Gaussian-like pairwise kernel psi (klerg_utils.py:7-10). `scale[d]` is the
+ * reference's `std[d]`: it divides the squared difference UN-squared and its
+ * absolute value is used (klerg_utils.py:20,27,13). */
+typedef struct klerg_kernel_spec {
+  int32_t D;                  /* len(explr_idx)                              */
+  int32_t S;                  /* columns per state row                        */
+  int32_t explr[KLERG_MAX_D]; /* explored columns of a state row              */
+  float scale[KLERG_MAX_D];
+  float nu;                   /* psi is divided by nu                         */
+} klerg_kernel_spec;
+
+enum { KLERG_DYN_SINGLE = 0, KLERG_DYN_DOUBLE = 1, KLERG_DYN_SPEED = 2, KLERG_DYN_ROLL = 3 };
+
+/* Integrator models of dynamics.py (SingleIntegratorEnv :67, DoubleIntegratorEnv
+ * :81, DoubleIntegratorSpeedEnv :97, DoubleIntegratorRollEnv :224). */
+typedef struct klerg_dyn_spec {
+  int32_t kind;
+  int32_t S; /* num_states  */
+  int32_t A; /* num_actions */
+  float dt;
+  int32_t rpw[3];      /* ROLL: indices of roll,pitch,yaw among the positions  */
+  int32_t has_ang_map; /* ROLL: affine rot<->angle map (klerg.py:147-149)      */
+  float rot_lo[3], rot_hi[3]; /* "robot_lim" side of the map                   */
+  float ang_lo[3], ang_hi[3]; /* "tray_lim" (real angle) side of the map       */
+} klerg_dyn_spec;
+
+/* BarrierFunction (barrier.py:40-90): limits already shrunk by b_buff. n = 0
+ * stands for NoBarrier (barrier.py:147-159). */
+typedef struct klerg_barrier_spec {
+  int32_t n;
+  float lo[KLERG_MAX_S], hi[KLERG_MAX_S];
+  float weight[KLERG_MAX_S], power[KLERG_MAX_S];
+} klerg_barrier_spec;
+
+const char* klerg_last_error(void);
+int klerg_abi_version(void);
+/* SM count / compute capability of the current device (host out-pointers). */
+int klerg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Upper bound of workspace bytes for G segments (candidates/targets). */
+size_t klerg_workspace_bytes(int64_t G);
+
+/* ---- workspace samples --------------------------------------------------- */
+
+/* AoS samples [N,D] (layout of env_sampler.sample, klerg.py:375) -> packed SoA
+ * [D][ld] pre-multiplied by sqrt(0.5*log2(e)/|scale_d|) so that
+ * psi = 2^-(sum_d (t'_d - s'_d)^2).  ld >= N, ld % 4 == 0. */
+int klerg_pack_samples(const klerg_kernel_spec* k, const float* samples, int64_t N, float* packed,
+                       int64_t ld, void* stream);
+
+/* ---- a2 / a3: traj_footprint_vec, traj_spread_vec (klerg_utils.py:17-29) -- */
+
+/* For every segment g < G and sample i < N:
+ *   out[g*out_stride + i] = (add_in ? add_in[i] : 0) + red_j psi(states[g][j], s_i)
+ * red = sum (mode 0) or max (mode 1), j < T, states[g] = states + g*seg_stride
+ * (rows of k->S floats).  totals[g*2+{0,1}] = {sum_i out, max_i out} (this
+ * rank's samples only).  T = 0 yields add_in (or zeros), as klerg.py:497-498. */
+int klerg_footprint(const klerg_kernel_spec* k, int mode, const float* states, int64_t G, int64_t T,
+                    int64_t seg_stride, const float* packed, int64_t N, int64_t ld, const float* add_in,
+                    float* out, int64_t out_stride, double* totals, void* workspace, void* stream);
+
+/* ---- a5 / a6: renormalize, cost_norm (klerg_utils.py:38-58) --------------- */
+
+/* stats[0..3] = {sum, max, min, #nan} of x[0..N). */
+int klerg_vector_stats(const float* x, int64_t N, double* stats, void* workspace, void* stream);
+/* out = c / max(c), c = max(x/sum, floor) -- closed form of renormalize(). */
+int klerg_renormalize(const float* x, int64_t N, float floor, float* out, void* workspace, void* stream);
+/* Same with externally supplied (e.g. rank-combined) stats = {sum, max} on the device. */
+int klerg_renormalize_with_stats(const float* x, int64_t N, const double* stats, float floor, float* out,
+                                 void* stream);
+/* in place: NaN -> 1e-6, then x /= sum(x). */
+int klerg_cost_norm(float* x, int64_t N, void* workspace, void* stream);
+
+/* ---- a4: kldiv_grad_vec (klerg_utils.py:12-15, 31-36) -------------------- */
+
+/* dgdx[t][explr[d]] = sum_i w_i * (-(x_td - s_id)/|scale_d|) * psi(x_t, s_i)
+ * for t < H (the reference loops t on the host, klerg.py:440-443); other
+ * columns of dgdx[H][S] are zero.  Explicit importance ratio w[N]. */
+int klerg_kl_gradient(const klerg_kernel_spec* k, const float* states, int64_t H, const float* packed,
+                      int64_t N, int64_t ld, const float* w, float* dgdx, void* workspace, void* stream);
+
+/* Planner form: the importance ratio p/q of klerg.py:436 is formed on the fly
+ * from v = q_base + q_iter (output of klerg_footprint), its global totals
+ * (`world` rank blocks of [sum,max], summed/maxed in rank order) and p:
+ *   c_i = max(v_i/sum v, floor), q_i = c_i/max c, w_i = p_i/q_i.
+ * Writes this rank's partial gradient grad_part[H][D] (explored dims only,
+ * doubles) and kl_part[2] = {sum_i p_i (log p_i - log c_i), sum_i c_i}. */
+int klerg_kl_gradient_fused(const klerg_kernel_spec* k, const float* states, int64_t H,
+                            const float* packed, int64_t N, int64_t ld, const float* v,
+                            const double* totals, int world, const float* p, float floor,
+                            double* grad_part, double* kl_part, void* workspace, void* stream);
+
+/* ---- a11: KL(p||q) cost of get_cost (klerg.py:686-710) -------------------- */
+
+/* Per candidate g: kl_part[g*2+{0,1}] = {sum_i p_i (log p_i - log c_i), sum_i c_i}
+ * over this rank's samples, c from v[g] and totals[world][G][2]. */
+int klerg_kl_cost_partial(const float* v, int64_t v_stride, int64_t G, int64_t N, const double* totals,
+                          int world, const float* p, float floor, double* kl_part, void* workspace,
+                          void* stream);
+/* cost[g] = Sa/sum_p - log(sum_p) + log(Sc) + barrier_sum[g], with {Sa,Sc}
+ * summed over `world` blocks of kl_part[G][2] and sum_p = p_stats[0]. */
+int klerg_kl_cost_final(const double* kl_part, int world, int64_t G, const double* p_stats,
+                        const float* barrier_sum, float* cost, void* stream);
+
+/* ---- a7: get_target_dist weighting (klerg.py:452-486) --------------------- */
+
+/* stage 1: acc[0..3] = {max_i spread_i, sum_{i inside} spread_i, #outside, min_i p_i}
+ * `samples` are the raw AoS samples, lim_lo/hi (host, D floats) = robot_lim
+ * rows of the explored dims (klerg.py:454).  spread may be NULL (empty buffer:
+ * klerg.py:476-477) in which case acc = {1, 0, 0, min p}. */
+int klerg_target_stage1(const float* samples, int32_t D, int64_t N, const float* lim_lo,
+                        const float* lim_hi, const float* spread, const float* p, double* acc,
+                        void* workspace, void* stream);
+/* Rank combine for sharded runs: blocks = `world` rank blocks of n doubles,
+ * kinds[q] (host) = 0 sum, 1 max, 2 min; out[q] = reduction over ranks. */
+int klerg_combine_blocks(const double* blocks, int world, int n, const int* kinds, double* out, void* stream);
+/* expo = {mean_i spread'_i (klerg.py:474-481), min p, max spread} from the
+ * (rank-combined) stage-1 acc and the global sample count. */
+int klerg_target_exponent(const double* acc, int64_t N_total, double* expo, void* stream);
+/* stage 2: mode 0 (weight_temp / plot): p2 = p ** expo[0];
+ *          mode 1 (weight_env): p2 = p + (1 - spread'_i) * expo[1], spread' as klerg.py:474-475;
+ *          mode 2: p2 = p.   acc[0..1] = {sum p2, max p2}.  expo = device doubles
+ *          {exponent, min p, max spread}. */
+int klerg_target_stage2(int mode, const float* samples, int32_t D, int64_t N, const float* lim_lo,
+                        const float* lim_hi, const float* spread, const float* p, const double* expo,
+                        float* p2, double* acc, void* workspace, void* stream);
+/* stage 3: p = (renormalize(p2)) ** temp given acc2 = {sum p2, max p2} (device);
+ * `renorm` = 0 skips the renormalize (no weighting flags set).  p_stats[0] = sum p. */
+int klerg_target_stage3(const float* p2, int64_t N, const double* acc2, int renorm, float floor, float temp,
+                        float* p, double* p_stats, void* workspace, void* stream);
+
+/* ---- a9/a11/a15/a16-a18: rollout, barrier, linearisation ------------------ */
+
+/* One thread per candidate b < B rolls u[b][H][A] out from x0[S] (and R0[9] for
+ * ROLL, row-major) with RK4 (dynamics.py:7-13,58-65):
+ *   traj[b][0] = x0, traj[b][t+1] = step(traj[b][t], u[b][t])      [B][H+1][S]
+ *   barrier_sum[b] = sum_t barr(traj[b][t+1])                     (klerg.py:708)
+ *   dbarr[b][t]    = dbarr(traj[b][t])            [B][H][S]       (klerg.py:425), may be NULL
+ *   P[b][t]        = d(pos rate)/d(vel) block of A_t  [B][H][A*A]  (klerg.py:423), may be NULL
+ *   R_out[b]       = rotation matrix after the last step [B][9], may be NULL. */
+int klerg_rollout(const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar, const float* x0,
+                  const float* R0, const float* u, int64_t B, int64_t H, float* traj,
+                  float* barrier_sum, float* dbarr, float* P, float* R_out, void* stream);
+
+/* barr(x_t) and dbarr(x_t) for T rows of S floats (barrier.py:70-87). */
+int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x, int64_t T, int32_t S,
+                       float* value, float* grad, void* stream);
+
+/* ---- a10: adjoint sweep of Robot.backward (klerg.py:433-450, 590-593) ----- */
+
+/* grad_part: `world` blocks of [H][D] doubles (klerg_kl_gradient_fused), summed
+ * in rank order.  rho_H = 0; for t = H-1..0 one RK4 step of
+ * rho' = dgdx_t - dbarr_t - A_t^T rho with step -dt (default policy: dmudx = 0),
+ * du_t = -Rinv B_t^T rho, djdlam_t = rho B_t du_t, u_star = clamp(u + alpha du).
+ * P may be NULL (0.8*I).  Rinv_diag, ctrl_lo, ctrl_hi are HOST arrays of A
+ * floats (diag of R^-1, control_lim columns, klerg.py:193,197).
+ * Outputs: dgdx[H][S], du[H][A], djdlam[H], u_star[H][A]. */
+int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H,
+                  const double* grad_part, int world, const float* dbarr, const float* P,
+                  const float* traj, const float* u, const float* Rinv_diag, float alpha,
+                  const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
+                  float* u_star, void* stream);
+
+/* ---- a19: memory-buffer selection (memory_buffer.py:52-63) ---------------- */
+
+/* out[m] = table[idx[m]] for m < M; idx are the host-drawn torch.randperm
+ * indices (int64).  Returns -3 via a device flag check only in debug builds. */
+int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t M, float* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLERG_B200_H */

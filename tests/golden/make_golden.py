@@ -66,7 +66,7 @@ def record_robot_case(rk, name, case):
         du, dj = orig_back(samples, p, q, nu, grad_list, traj_list)
         A = torch.stack([g[0] for g in grad_list])
         dbarr = torch.stack([g[2] for g in grad_list])
-        log.append(("grad", dict(q=q.clone(), traj=traj_list.clone(), du=du.clone(), djdlam=dj.clone(), A=A, dbarr=dbarr)))
+        log.append(("grad", dict(u=r.u.clone(), q=q.clone(), traj=traj_list.clone(), du=du.clone(), djdlam=dj.clone(), A=A, dbarr=dbarr)))
         return du, dj
 
     r.get_cost, r.backward = cost_hook, back_hook

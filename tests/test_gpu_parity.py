@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path, called through the C ABI / the reference-shaped
+Python API, against the CPU oracle and the golden vectors recorded from the live
+reference.  Tolerances: bit-exact for samples / indices / buffer rows; 1e-4
+relative for fp32 cost, q, gradients (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cases import ROBOT_CASES, MixtureTarget, robot_kwargs, seed_buffer_states  # noqa: E402
+from oracle import klerg_oracle as ko  # noqa: E402
+
+RTOL = 1e-4
+
+
+def rel_close(a, b, rtol=RTOL, atol_frac=0.0, what=""):
+    """|a-b| <= rtol*|b| + atol_frac*max|b| elementwise (atol_frac for sign-cancelling sums)."""
+    a = np.asarray(torch.as_tensor(a).detach().cpu().numpy(), dtype=np.float64)
+    b = np.asarray(torch.as_tensor(b).detach().cpu().numpy(), dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = np.abs(b).max() if b.size else 0.0
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol_frac * scale + 1e-37, err_msg=what)
+
+
+@pytest.fixture(scope="module")
+def ct():
+    import control_torch.klerg_utils as ku
+    import control_torch.barrier as kb
+    import control_torch.dynamics as kd
+    import control_torch.memory_buffer as km
+    import control_torch.klerg as kk
+    import control_torch.engine as ke
+    import control_torch._cabi as cabi
+    from types import SimpleNamespace
+    return SimpleNamespace(ku=ku, kb=kb, kd=kd, km=km, kk=kk, ke=ke, cabi=cabi)
+
+
+@pytest.fixture(scope="module")
+def utils(golden_dir):
+    return np.load(os.path.join(golden_dir, "utils.npz"))
+
+
+def test_library_is_native_sm100(ct):
+    import ctypes as C
+    lib = ct.cabi.load()
+    sms, major, minor = C.c_int(), C.c_int(), C.c_int()
+    assert lib.klerg_device_info(C.byref(sms), C.byref(major), C.byref(minor)) == 0
+    assert major.value == 10, "kernels are built for sm_100a only"
+    assert sms.value > 0
+
+
+@pytest.mark.parametrize("D", [2, 3, 4, 6])
+def test_pairwise_utils_vs_golden_and_oracle(ct, utils, D):
+    t = lambda k: torch.from_numpy(utils[f"D{D}/{k}"])
+    traj, samples, std, nu, w = t("traj"), t("samples"), t("std"), t("nu"), t("w")
+    explr = torch.arange(D)
+    fp = ct.ku.traj_footprint_vec(traj, samples, explr, std, nu)
+    assert fp.device.type == "cpu" and fp.dtype == torch.float32
+    rel_close(fp, utils[f"D{D}/footprint"], what="footprint/golden")
+    rel_close(fp, ko.footprint_sum(traj, samples, explr, std, nu), what="footprint/oracle")
+    rel_close(ct.ku.traj_spread_vec(traj, samples, explr, std, nu), utils[f"D{D}/spread"], what="spread")
+    g = torch.stack([ct.ku.kldiv_grad_vec(x, samples, explr, std, w, nu) for x in traj[:5]])
+    rel_close(g, utils[f"D{D}/grad"], atol_frac=1e-5, what="kldiv_grad_vec")
+    q = torch.from_numpy(utils[f"D{D}/footprint"])
+    rel_close(ct.ku.renormalize(q.clone()), utils[f"D{D}/renorm"], what="renormalize")
+    rel_close(ct.ku.cost_norm(q.clone()), utils[f"D{D}/cost_norm"], what="cost_norm")
+
+
+def test_renormalize_floor_nan_and_dim(ct, utils):
+    x = torch.from_numpy(utils["floor/x"])
+    rel_close(ct.ku.renormalize(x.clone()), utils["floor/renorm"])
+    xn = torch.from_numpy(utils["floor/x_nan"]).clone()
+    out = ct.ku.cost_norm(xn)
+    assert out is xn  # in place like the reference
+    rel_close(xn, utils["floor/cost_norm_nan"])
+    two = torch.stack([x, x.flip(0)])
+    r = ct.ku.renormalize(two, dim=1)
+    rel_close(r[0], utils["floor/renorm"])
+    rel_close(r[1], utils["floor/renorm"][::-1].copy())
+
+
+def test_pairwise_edge_cases(ct):
+    g = torch.Generator().manual_seed(3)
+    samples = torch.rand(5, 2, generator=g)
+    std = torch.tensor([0.05, 0.07])
+    empty = torch.zeros(0, 4)
+    assert torch.equal(ct.ku.traj_footprint_vec(empty, samples, [0, 1], std, 1.0), torch.zeros(5))
+    # ragged sizes around the tile / vector boundaries, non-trivial explr columns
+    for n in (1, 3, 4, 255, 257, 1023, 1025, 4099):
+        s = torch.rand(n, 2, generator=g) * 2 - 1
+        traj = torch.rand(1031, 4, generator=g) * 2 - 1
+        explr = torch.tensor([2, 0])
+        rel_close(ct.ku.traj_footprint_vec(traj, s, explr, std, 1.0), ko.footprint_sum(traj, s, explr, std, torch.ones(1)))
+        rel_close(ct.ku.traj_spread_vec(traj, s, explr, std, 1.0), ko.spread_max(traj, s, explr, std, torch.ones(1)))
+
+
+def test_barrier(ct, utils):
+    lim = torch.from_numpy(utils["barrier/lim"])
+    xs = torch.from_numpy(utils["barrier/x"])
+    bar = ct.kb.BarrierFunction(b_lim=lim, barr_weight=5.0, b_buff=0.1, power=[4.0] * 6)
+    rel_close(bar(xs), utils["barrier/value"], rtol=1e-5)
+    rel_close(torch.stack([bar.dbarr(x) for x in xs[:8]]), utils["barrier/grad"][:8], rtol=1e-5)
+    rel_close(bar.barr(xs[3]), utils["barrier/value"][3], rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind,st", [("double", "xyz"), ("speed", "xy"), ("roll", "xyzrpw"), ("single", "xyz")])
+def test_dynamics(ct, utils, kind, st):
+    cls = dict(double=ct.kd.DoubleIntegratorEnv, speed=ct.kd.DoubleIntegratorSpeedEnv,
+               roll=ct.kd.DoubleIntegratorRollEnv, single=ct.kd.SingleIntegratorEnv)[kind]
+    x0 = torch.from_numpy(utils[f"dyn_{kind}/x0"])
+    u = torch.from_numpy(utils[f"dyn_{kind}/u"])
+    env = cls(dt=0.2, x0=x0.clone(), states=st)
+    xs, As, Bs = [env.state.clone()], [], []
+    for ut in u:
+        a, b = env.get_lin(env.state.clone(), ut)
+        As.append(a)
+        Bs.append(b)
+        xs.append(env.step(ut).clone())
+    rel_close(torch.stack(xs), utils[f"dyn_{kind}/traj"], rtol=2e-5, atol_frac=2e-6, what="traj")
+    rel_close(torch.stack(As), utils[f"dyn_{kind}/A"], rtol=2e-5, atol_frac=2e-6, what="A")
+    rel_close(torch.stack(Bs), utils[f"dyn_{kind}/B"], rtol=0, what="B")
+    if kind == "roll":
+        rel_close(env.R, utils["dyn_roll/R_final"], rtol=2e-5, atol_frac=2e-6)
+        env2 = cls(dt=0.2, x0=x0.clone(), states=st)
+        y = torch.stack([env2.step(ut, save=False).clone() for ut in u[:4]])
+        rel_close(y, utils["dyn_roll/nosave"], rtol=2e-5, atol_frac=2e-6)
+        rel_close(env2.R, utils["dyn_roll/nosave_R"], rtol=2e-5, atol_frac=2e-6)
+
+
+def test_buffer_bit_exact(ct, utils):
+    torch.manual_seed(99)
+    buf = ct.km.MemoryBuffer_torch(7, 4, dtype=torch.float32)
+    assert tuple(buf.sample(5).shape) == tuple(utils["buffer/empty_sample_shape"])
+    for i, row in enumerate(torch.from_numpy(utils["buffer/seq"])):
+        buf.push(row)
+        assert np.array_equal(buf.sample(3).numpy(), utils[f"buffer/draw{i}"])
+        assert [len(buf), buf.position, int(buf.full_buffer)] == utils[f"buffer/len{i}"].tolist()
+    assert np.array_equal(buf.get_all().numpy(), utils["buffer/all"])
+    assert np.array_equal(buf.get_all_device().cpu().numpy(), utils["buffer/all"])
+    assert np.array_equal(buf.get_recent(5).numpy(), utils["buffer/recent5"])
+    assert np.array_equal(buf.sample(100).numpy(), utils["buffer/big_draw"])
+
+
+def make_robot(ct, name, cls=None):
+    case = ROBOT_CASES[name]
+    torch.manual_seed(1234)
+    target = MixtureTarget(case["D"], seed=7)
+    if case["states"] == "xyzrpw":
+        target.mu[:, 3] = target.mu[:, 3] * 0.5 + 3.1
+    r = (cls or ct.kk.Robot)(**robot_kwargs(case, target))
+    if case.get("weight_env"):
+        r.weight_env, r.weight_temp = True, False
+    r.test(case["n"])
+    for s in seed_buffer_states(r.robot.state, case):
+        r.memory_buffer.push(s)
+    return r, case
+
+
+@pytest.mark.parametrize("name", list(ROBOT_CASES))
+def test_evals_vs_golden(ct, golden_dir, name):
+    """Every get_cost / forward+backward evaluation the reference made, re-run on the GPU on
+    the reference's own inputs (samples, p, q_base, x0, u)."""
+    gold = np.load(os.path.join(golden_dir, f"robot_{name}.npz"))
+    r, case = make_robot(ct, name)
+    dev = torch.device("cuda")
+    n_cost = n_grad = 0
+    for k in range(int(gold["n_steps"])):
+        pre = f"step{k}/"
+        ctx = r._context()
+        samples = torch.from_numpy(gold[pre + "samples"]).to(dev)
+        ctx.set_samples(samples, r.std.tolist(), 1.0)
+        ctx.set_state(torch.from_numpy(gold[pre + "state_before"]).to(dev))
+        p = torch.from_numpy(gold[pre + "p"]).to(dev)
+        ctx.set_target(p, ct.ke.vector_stats(p)[:1].contiguous())
+        ctx.q_base = torch.zeros(ct.ke.padded(samples.shape[0]), device=dev)
+        ctx.q_base[: samples.shape[0]] = torch.from_numpy(gold[pre + "q_base"]).to(dev)
+        # history footprint itself
+        hist = torch.from_numpy(gold[pre + "hist"]).to(dev)
+        qb, _ = ct.ke.footprint(ctx.spec, 0, hist, ctx.packed, ctx.n)
+        rel_close(qb[0, : ctx.n], gold[pre + "q_base"], what=f"{pre}q_base")
+        us, costs = [], []
+        i = 0
+        while pre + f"cost{i}/u" in gold:
+            us.append(torch.from_numpy(gold[pre + f"cost{i}/u"]))
+            costs.append(gold[pre + f"cost{i}/cost"].reshape(()))
+            i += 1
+        got = ctx.costs(torch.stack(us).to(dev)).cpu()
+        rel_close(got, np.array(costs), what=f"{pre}costs")
+        n_cost += i
+        j = 0
+        while pre + f"grad{j}/du" in gold:
+            traj = torch.from_numpy(gold[pre + f"grad{j}/traj"])
+            u = torch.from_numpy(gold[pre + f"grad{j}/u"])
+            g = ctx.gradient(u.to(dev), keep=True)
+            rel_close(g["traj"], traj, rtol=2e-5, atol_frac=2e-6, what=f"{pre}grad{j}/traj")
+            q = ctx.q_from(g["v"], g["totals"])
+            rel_close(q, gold[pre + f"grad{j}/q"], what=f"{pre}grad{j}/q")
+            rel_close(g["du"], gold[pre + f"grad{j}/du"], rtol=RTOL, atol_frac=2e-5, what=f"{pre}grad{j}/du")
+            rel_close(g["djdlam"], gold[pre + f"grad{j}/djdlam"], rtol=RTOL, atol_frac=2e-5, what=f"{pre}grad{j}/djdlam")
+            j += 1
+        n_grad += j
+    assert n_cost > 0 and n_grad > 0
+
+
+@pytest.mark.parametrize("name", list(ROBOT_CASES))
+def test_robot_sequences_vs_golden(ct, golden_dir, name):
+    """Whole Robot.step() sequences through the reference-shaped API.  RNG-driven data
+    (samples, buffer selection) must be bit-exact; numbers within tolerance for as long as
+    the data-dependent control flow agrees (a 1e-6 difference may legitimately flip a
+    near-tie; such a flip is reported, and must not happen before step 3)."""
+    gold = np.load(os.path.join(golden_dir, f"robot_{name}.npz"))
+    r, case = make_robot(ct, name)
+    n_steps = int(gold["n_steps"])
+    matched = 0
+    for k in range(n_steps):
+        pre = f"step{k}/"
+        if not np.allclose(r.u.numpy(), gold[pre + "u_before"], rtol=1e-3, atol=1e-4):
+            break
+        st, vel, ctrl = r.step(case["n"], case["m"], save_update=True)
+        assert isinstance(st, np.ndarray) and isinstance(vel, np.ndarray) and isinstance(ctrl, np.ndarray)
+        # bit-exact: host RNG stream
+        assert np.array_equal(r.ctx.samples.cpu().numpy(), gold[pre + "samples"]), "samples must be bit-exact"
+        assert r.memory_buffer.position == int(gold[pre + "buf_pos"])
+        hist = r.memory_buffer.device_buffer[r.last_hist_idx.cuda()].cpu().numpy() if len(r.last_hist_idx) else None
+        if np.allclose(r.u.numpy(), gold[pre + "u_after"], rtol=1e-3, atol=1e-4):
+            matched += 1
+            rel_close(r.ctx.p, gold[pre + "p"], what=f"{pre}p")
+            rel_close(r.ctx.q_base[: r.ctx.n], gold[pre + "q_base"], what=f"{pre}q_base")
+            rel_close(st, gold[pre + "ret_state"], rtol=1e-3, atol_frac=1e-4)
+            rel_close(ctrl, gold[pre + "ret_ctrl"], rtol=1e-3, atol_frac=1e-4)
+            rel_close(r.last_plan, gold[pre + "last_plan"], rtol=1e-3, atol_frac=1e-4)
+            if case.get("plot"):
+                for i in (0, 3):
+                    rel_close(r.plot_data[i], gold[pre + f"plot{i}"], rtol=1e-3, atol_frac=1e-4, what=f"plot{i}")
+                for i in (1, 2, 4, 5, 6):
+                    rel_close(r.plot_data[i], gold[pre + f"plot{i}"], rtol=2e-4, atol_frac=1e-5, what=f"plot{i}")
+        else:
+            break
+    assert matched >= min(3, n_steps), f"sequence diverged after {matched} steps"
+    print(f"{name}: {matched}/{n_steps} steps in lockstep with the reference")
