@@ -74,6 +74,8 @@ _KS, _DS, _BS = C.POINTER(KernelSpec), C.POINTER(DynSpec), C.POINTER(BarrierSpec
 SIGNATURES = {
     "klerg_last_error": [],
     "klerg_abi_version": [],
+    "klerg_launch_count": [],
+    "klerg_peak_probe": [C.c_int, C.c_int, C.c_int, _P, _P],
     "klerg_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "klerg_workspace_bytes": [_I64],
     "klerg_pack_samples": [_KS, _P, _I64, _P, _I64, _P],
@@ -98,7 +100,8 @@ SIGNATURES = {
                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_gather_rows": [_P, _I32, _P, _I64, _P, _P],
 }
-_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t}
+_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t,
+             "klerg_launch_count": C.c_longlong}
 
 
 def load():

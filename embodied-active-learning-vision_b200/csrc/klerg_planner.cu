@@ -22,7 +22,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -616,6 +619,39 @@ using namespace klerg;
 
 extern "C" const char* klerg_last_error(void) { return g_err; }
 extern "C" int klerg_abi_version(void) { return 1; }
+extern "C" long long klerg_launch_count(void) { return g_launches; }
+
+// ---- peak-rate microbenchmarks (roofline denominators, used by bench.py only) ----
+namespace klerg {
+template <int KIND>
+__global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float* out) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + 1e-3f * (float)(threadIdx.x + i);
+  const float m = 0.999f, c = 1e-4f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (KIND == 0) a[i] = fmaf(a[i], m, c);       // FFMA
+        else a[i] = ex2_approx(a[i] * -0.5f);          // MUFU.EX2 (+1 FMUL)
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;  // keep the chain alive
+}
+}  // namespace klerg
+
+extern "C" int klerg_peak_probe(int kind, int iters, int blocks, float* out, void* stream) {
+  if (kind == 0) klerg::peak_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, out);
+  else if (kind == 1) klerg::peak_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, out);
+  else { set_error("peak_probe: kind 0 (FFMA) or 1 (EX2)"); return -1; }
+  return check_launch("peak_kernel");
+}
 
 extern "C" int klerg_device_info(int* sms, int* major, int* minor) {
   int dev = 0;
