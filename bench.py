@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-evals", type=int, default=0,
+                    help="run this many eager evals inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -315,6 +317,15 @@ def cuda_arm(args):
     for i in range(max(args.warmup, 3)):
         eval_on(i)
     torch.cuda.synchronize()
+
+    if args.profile_evals:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(args.profile_evals):
+            eval_on(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     # ---- timed region: exactly K evals ----------------------------------------------------------
     launches0 = lib.klerg_launch_count()

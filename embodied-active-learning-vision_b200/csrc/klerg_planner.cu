@@ -399,46 +399,144 @@ __device__ void dyn_step(const DynDev& d, const float* x, float* R, const float*
   }
 }
 
-__global__ void rollout_kernel(DynDev d, BarDev bar, const float* __restrict__ x0, const float* __restrict__ R0,
-                               const float* __restrict__ u, int64_t B, int64_t H, float* __restrict__ traj,
-                               float* __restrict__ barrier_sum, float* __restrict__ dbarr, float* __restrict__ P,
-                               float* __restrict__ R_out) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per candidate; lane i < A owns (pos_i, vel_i[, mag_i]).  Controls are staged in
+// shared memory so the serial recurrence only touches registers and smem; lane 0 carries the
+// rotation matrix of the ROLL model and hands the new angles to the owning lanes by shuffle.
+constexpr int RO_WARPS = 4;
+
+__device__ __forceinline__ float barrier_term(float x, float lo, float hi, float w, float pw) {
+  float acc = 0.f;
+  if (x <= lo) acc += w * powi_or_f(x - lo, pw);
+  if (x >= hi) acc += w * powi_or_f(x - hi, pw);
+  return acc;
+}
+__device__ __forceinline__ float barrier_dterm(float x, float lo, float hi, float w, float pw) {
+  float acc = 0.f;
+  if (x <= lo) acc += pw * w * powi_or_f(x - lo, pw - 1.f);
+  if (x >= hi) acc += pw * w * powi_or_f(x - hi, pw - 1.f);
+  return acc;
+}
+
+__global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(DynDev d, BarDev bar, const float* __restrict__ x0,
+                                                                 const float* __restrict__ R0,
+                                                                 const float* __restrict__ u, int64_t B, int64_t H,
+                                                                 float* __restrict__ traj,
+                                                                 float* __restrict__ barrier_sum,
+                                                                 float* __restrict__ dbarr, float* __restrict__ P,
+                                                                 float* __restrict__ R_out) {
+  extern __shared__ float sh_u[];  // [RO_WARPS][H*A]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * RO_WARPS + warp;
   if (b >= B) return;
-  float x[KLERG_MAX_S], xn[KLERG_MAX_S], R[9], ut[KLERG_MAX_A];
   const int S = d.S, a = d.A;
-  for (int i = 0; i < S; ++i) x[i] = x0[i];
-  if (d.kind == KLERG_DYN_ROLL) {
+  const bool single = d.kind == KLERG_DYN_SINGLE, speed = d.kind == KLERG_DYN_SPEED, roll = d.kind == KLERG_DYN_ROLL;
+  float* us = sh_u + (size_t)warp * H * a;
+  for (int64_t e = lane; e < H * a; e += 32) us[e] = u[b * H * a + e];
+  __syncwarp();
+
+  const bool act = lane < a;
+  float pos = act ? x0[lane] : 0.f;
+  float vel = (act && !single) ? x0[a + lane] : 0.f;
+  float mag = (act && speed) ? x0[2 * a + lane] : 0.f;
+  // barrier rows owned by this lane: position row `lane`, velocity row `a + lane`
+  float blo_p = 0.f, bhi_p = 0.f, bw_p = 0.f, bpw_p = 1.f, blo_v = 0.f, bhi_v = 0.f, bw_v = 0.f, bpw_v = 1.f;
+  bool has_p = false, has_v = false, has_m = false;
+  float blo_m = 0.f, bhi_m = 0.f, bw_m = 0.f, bpw_m = 1.f;
+  if (act && lane < bar.n) { has_p = true; blo_p = bar.lo[lane]; bhi_p = bar.hi[lane]; bw_p = bar.w[lane]; bpw_p = bar.pw[lane]; }
+  if (act && !single && a + lane < bar.n) { has_v = true; blo_v = bar.lo[a + lane]; bhi_v = bar.hi[a + lane]; bw_v = bar.w[a + lane]; bpw_v = bar.pw[a + lane]; }
+  if (act && speed && 2 * a + lane < bar.n) { has_m = true; blo_m = bar.lo[2 * a + lane]; bhi_m = bar.hi[2 * a + lane]; bw_m = bar.w[2 * a + lane]; bpw_m = bar.pw[2 * a + lane]; }
+
+  float R[9];
+  int my_rot = -1;  // which of roll/pitch/yaw this lane's position is (ROLL)
+  if (roll) {
+    for (int k = 0; k < 3; ++k)
+      if (lane == d.rpw[k]) my_rot = k;
+    float rot[3];
+    for (int k = 0; k < 3; ++k) {
+      rot[k] = __shfl_sync(0xffffffffu, pos, d.rpw[k]);
+      if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
+    }
     if (R0) {
       for (int i = 0; i < 9; ++i) R[i] = R0[i];
     } else {
-      float rot[3];
-      for (int k = 0; k < 3; ++k) {
-        rot[k] = x[d.rpw[k]];
-        if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
-      }
       euler_xyz_to_matrix(rot, R);
     }
-  } else {
-    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.f : 0.f;
   }
   float* tr = traj + b * (H + 1) * S;
-  for (int i = 0; i < S; ++i) tr[i] = x[i];
+  const float dt = d.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
   float bsum = 0.f;
-  for (int64_t t = 0; t < H; ++t) {
-    if (dbarr) barrier_grad(bar, x, S, dbarr + (b * H + t) * S);
-    if (P) lin_block(d, x, R, P + (b * H + t) * a * a);
-    for (int i = 0; i < a; ++i) ut[i] = u[(b * H + t) * a + i];
-    dyn_step(d, x, R, ut, xn);
-    for (int i = 0; i < S; ++i) {
-      x[i] = xn[i];
-      tr[(t + 1) * S + i] = xn[i];
+  for (int64_t t = 0; t <= H; ++t) {
+    if (act) {
+      tr[t * S + lane] = pos;
+      if (!single) tr[t * S + a + lane] = vel;
+      if (speed) tr[t * S + 2 * a + lane] = mag;
     }
-    bsum += barrier_value(bar, x);
+    if (t > 0 && act) {
+      if (has_p) bsum += barrier_term(pos, blo_p, bhi_p, bw_p, bpw_p);
+      if (has_v) bsum += barrier_term(vel, blo_v, bhi_v, bw_v, bpw_v);
+      if (has_m) bsum += barrier_term(mag, blo_m, bhi_m, bw_m, bpw_m);
+    }
+    if (t == H) break;
+    if (dbarr && act) {
+      float* db = dbarr + (b * H + t) * S;
+      db[lane] = has_p ? barrier_dterm(pos, blo_p, bhi_p, bw_p, bpw_p) : 0.f;
+      if (!single) db[a + lane] = has_v ? barrier_dterm(vel, blo_v, bhi_v, bw_v, bpw_v) : 0.f;
+      if (speed) db[2 * a + lane] = has_m ? barrier_dterm(mag, blo_m, bhi_m, bw_m, bpw_m) : 0.f;
+    }
+    float w3[3] = {0.f, 0.f, 0.f}, rot3[3] = {0.f, 0.f, 0.f};
+    if (roll) {
+      for (int k = 0; k < 3; ++k) {
+        w3[k] = __shfl_sync(0xffffffffu, vel, d.rpw[k]);
+        rot3[k] = __shfl_sync(0xffffffffu, pos, d.rpw[k]);
+      }
+    }
+    if (P) {
+      float* Pt = P + (b * H + t) * a * a;
+      for (int e = lane; e < a * a; e += 32) Pt[e] = (e / a == e % a) ? 0.8f : 0.f;
+      __syncwarp();
+      if (roll && lane == 0) {
+        float rot[3];
+        for (int k = 0; k < 3; ++k)
+          rot[k] = d.has_map ? affine_map(rot3[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]) : rot3[k];
+        rot[1] += 1e-5f;
+        float s0, c0;
+        sincosf(rot[0], &s0, &c0);
+        const float t1 = tanf(rot[1]), cc1 = cosf(rot[1]);
+        const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / cc1, c0 / cc1};
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            Pt[d.rpw[r] * a + d.rpw[c]] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
+      }
+    }
+    const float ut = act ? us[t * a + lane] : 0.f;
+    if (single) {
+      pos = pos + dt * ut;
+    } else {
+      pos = pos + (c1 * vel + c2 * ut);
+      vel = vel + dt * ut;
+      if (speed) mag = fabsf(vel);
+    }
+    if (roll) {
+      float Rn[9], nr[3];
+      advance_rotation(R, w3, dt, Rn, nr);  // every lane computes it redundantly (no divergence)
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+      if (my_rot >= 0) {
+        float v = my_rot == 0 ? nr[0] : (my_rot == 1 ? nr[1] : nr[2]);
+        if (d.has_map) v = affine_map(v, d.ang_lo[my_rot], d.ang_hi[my_rot], d.rot_lo[my_rot], d.rot_hi[my_rot]);
+        pos = v;
+      }
+    }
   }
-  if (barrier_sum) barrier_sum[b] = bsum;
-  if (R_out)
-    for (int i = 0; i < 9; ++i) R_out[b * 9 + i] = R[i];
+  bsum = warp_sum_f(bsum);
+  if (lane == 0 && barrier_sum) barrier_sum[b] = bsum;
+  if (lane == 0 && R_out) {
+    if (!roll) {
+      for (int i = 0; i < 9; ++i) R_out[b * 9 + i] = (i % 4 == 0) ? 1.f : 0.f;
+    } else {
+      for (int i = 0; i < 9; ++i) R_out[b * 9 + i] = R[i];
+    }
+  }
 }
 
 __global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int64_t T, int S, float* __restrict__ value,
@@ -477,31 +575,48 @@ struct AdjArgs {
 };
 
 __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
+  extern __shared__ float sh[];  // g[H][S] | P[H][A*A] (optional) | sgn[H][A] (SPEED) | u[H][A]
   const int S = a.d.S, A = a.d.A, D = a.k.D;
   const int64_t H = a.H;
-  // phase 1: dgdx[H][S] = sum over ranks of the explored-dim partials
-  for (int64_t e = threadIdx.x; e < H * S; e += blockDim.x) a.dgdx[e] = 0.f;
+  const bool single = a.d.kind == KLERG_DYN_SINGLE, speed = a.d.kind == KLERG_DYN_SPEED;
+  float* sg = sh;
+  float* sP = sg + H * S;
+  float* ssgn = sP + (a.P ? H * A * A : 0);
+  float* su = ssgn + (speed ? H * A : 0);
+  // phase 1 (all threads): g = dgdx - dbarr staged in smem, dgdx[H][S] written out
+  for (int64_t e = threadIdx.x; e < H * S; e += blockDim.x) sg[e] = 0.f;
   __syncthreads();
   for (int64_t e = threadIdx.x; e < H * D; e += blockDim.x) {
     double s = 0.0;
     for (int r = 0; r < a.world; ++r) s += a.grad_part[(size_t)r * H * D + e];
-    a.dgdx[(e / D) * S + a.k.explr[e % D]] = (float)s;
+    sg[(e / D) * S + a.k.explr[e % D]] = (float)s;
+  }
+  __syncthreads();
+  for (int64_t e = threadIdx.x; e < H * S; e += blockDim.x) {
+    const float g = sg[e];
+    a.dgdx[e] = g;
+    sg[e] = g - a.dbarr[e];
+  }
+  if (a.P)
+    for (int64_t e = threadIdx.x; e < H * A * A; e += blockDim.x) sP[e] = a.P[e];
+  for (int64_t e = threadIdx.x; e < H * A; e += blockDim.x) {
+    su[e] = a.u[e];
+    if (speed) ssgn[e] = (a.traj[(e / A) * S + A + (e % A)] < 0.f) ? -1.f : 1.f;
   }
   __syncthreads();
   if (threadIdx.x >= 32) return;
-  // phase 2: lane i < A carries component i of rho_p, rho_v (and rho_m for SPEED)
+  // phase 2 (one warp): lane i < A carries component i of rho_p, rho_v (and rho_m for SPEED)
   const int i = threadIdx.x;
   const bool act = i < A;
-  const bool single = a.d.kind == KLERG_DYN_SINGLE;
-  const bool speed = a.d.kind == KLERG_DYN_SPEED;
   const float h = -a.d.dt;
+  const float rinv = act ? a.rinv[i] : 0.f, clo = act ? a.clo[i] : 0.f, chi = act ? a.chi[i] : 0.f;
   float rp = 0.f, rv = 0.f, rm = 0.f;
   for (int64_t t = H - 1; t >= 0; --t) {
     float gp = 0.f, gv = 0.f, gm = 0.f;
     if (act) {
-      gp = a.dgdx[t * S + i] - a.dbarr[t * S + i];
-      if (!single) gv = a.dgdx[t * S + A + i] - a.dbarr[t * S + A + i];
-      if (speed) gm = a.dgdx[t * S + 2 * A + i] - a.dbarr[t * S + 2 * A + i];
+      gp = sg[t * S + i];
+      if (!single) gv = sg[t * S + A + i];
+      if (speed) gm = sg[t * S + 2 * A + i];
     }
     float btr;  // (B^T rho)_i
     if (single) {
@@ -510,7 +625,7 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
     } else {
       float ptr_ = 0.f, ptg = 0.f;  // (P^T rho_p)_i, (P^T g_p)_i
       if (a.P) {
-        const float* Pt = a.P + t * A * A;
+        const float* Pt = sP + t * A * A;
         for (int kk = 0; kk < A; ++kk) {
           const float rk = __shfl_sync(0xffffffffu, rp, kk);
           const float gk = __shfl_sync(0xffffffffu, gp, kk);
@@ -528,20 +643,15 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
       btr = rv;
       if (speed) {
         rm = rm + h * gm;
-        float sg = 0.f;
-        if (act) {
-          const float vel = a.traj[t * S + A + i];
-          sg = (vel < 0.f) ? -1.f : 1.f;
-        }
-        btr = rv + sg * rm;
+        btr = rv + (act ? ssgn[t * A + i] : 0.f) * rm;
       }
     }
-    const float dui = act ? -a.rinv[i] * btr : 0.f;
+    const float dui = act ? -rinv * btr : 0.f;
     const float dj = warp_sum_f(act ? btr * dui : 0.f);
     if (act) {
       a.du[t * A + i] = dui;
-      const float us = a.u[t * A + i] + a.alpha * dui;
-      a.u_star[t * A + i] = fminf(fmaxf(us, a.clo[i]), a.chi[i]);
+      const float us = su[t * A + i] + a.alpha * dui;
+      a.u_star[t * A + i] = fminf(fmaxf(us, clo), chi);
     }
     if (i == 0) a.djdlam[t] = dj;
   }
@@ -773,8 +883,9 @@ extern "C" int klerg_rollout(const klerg_dyn_spec* dyn, const klerg_barrier_spec
   BarDev b;
   if (!make_dyn(dyn, d) || !make_bar(bar, b)) return -1;
   if (B < 1 || H < 0) { set_error("rollout: bad sizes"); return -1; }
-  const int threads = B >= 128 ? 128 : 32;
-  rollout_kernel<<<(unsigned)((B + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+  if (H > KLERG_MAX_H) { set_error("rollout: H > KLERG_MAX_H"); return -1; }
+  const size_t smem = (size_t)RO_WARPS * H * d.A * sizeof(float);
+  rollout_kernel<<<(unsigned)((B + RO_WARPS - 1) / RO_WARPS), RO_WARPS * 32, smem, (cudaStream_t)stream>>>(
       d, b, x0, R0, u, B, H, traj, barrier_sum, dbarr, P, R_out);
   return check_launch("rollout_kernel");
 }
@@ -800,7 +911,17 @@ extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec*
   a.H = H; a.grad_part = grad_part; a.world = world; a.dbarr = dbarr; a.P = P; a.traj = traj; a.u = u;
   a.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
   for (int i = 0; i < a.d.A; ++i) { a.rinv[i] = Rinv_diag[i]; a.clo[i] = ctrl_lo[i]; a.chi[i] = ctrl_hi[i]; }
-  adjoint_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a);
+  const bool speed = a.d.kind == KLERG_DYN_SPEED;
+  const size_t smem = sizeof(float) * (size_t)H * (a.d.S + (P ? a.d.A * a.d.A : 0) + (speed ? a.d.A : 0) + a.d.A);
+  if (smem > 48 * 1024) {
+    static bool raised = false;
+    if (!raised) {
+      cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      raised = true;
+    }
+    if (smem > 200 * 1024) { set_error("adjoint: horizon too long for shared-memory staging"); return -1; }
+  }
+  adjoint_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("adjoint_kernel");
 }
 
