@@ -40,6 +40,10 @@ class DynSpec(C.Structure):
                 ("ang_lo", C.c_float * 3), ("ang_hi", C.c_float * 3)]
 
 
+class Peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * 8)]
+
+
 class BarrierSpec(C.Structure):
     _fields_ = [("n", C.c_int32), ("lo", C.c_float * MAX_S), ("hi", C.c_float * MAX_S),
                 ("weight", C.c_float * MAX_S), ("power", C.c_float * MAX_S)]
@@ -69,6 +73,7 @@ _lib = None
 
 _P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 _KS, _DS, _BS = C.POINTER(KernelSpec), C.POINTER(DynSpec), C.POINTER(BarrierSpec)
+_PS, _FP = C.POINTER(Peers), C.POINTER(C.c_float)
 
 # name -> argtypes (restype int unless listed in _RESTYPES); mirrors include/klerg_b200.h
 SIGNATURES = {
@@ -99,8 +104,13 @@ SIGNATURES = {
     "klerg_adjoint": [_DS, _KS, _I64, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float), _F,
                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_gather_rows": [_P, _I32, _P, _I64, _P, _P],
+    "klerg_mailbox_bytes": [],
+    "klerg_eval_gradient": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _P, _F, _FP, _F, _FP, _FP,
+                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "klerg_eval_costs": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P,
+                         _P, _P],
 }
-_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t,
+_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t,
              "klerg_launch_count": C.c_longlong}
 
 

@@ -269,6 +269,55 @@ def adjoint(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl
     return dgdx, du, dj, ustar
 
 
+class EvalBuffers:
+    """Caller-owned outputs/scratch of the fused evals for one (H, S, A, ld) shape.
+
+    Two alternating output sets, so the results of the previous gradient eval stay valid
+    while the next one runs (the planner keeps the last accepted iterate for plot_data)."""
+
+    def __init__(self, H, S, A, ld, device, n_sets=2, max_g=8):
+        f32 = dict(dtype=torch.float32, device=device)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.H, self.S, self.A, self.ld, self.max_g = H, S, A, ld, max_g
+        self.sets = []
+        for _ in range(n_sets):
+            self.sets.append(dict(
+                v=torch.empty(ld, **f32), traj=torch.empty((H + 1, S), **f32), totals=torch.empty((1, 2), **f64),
+                cost=torch.empty(1, **f32), dgdx=torch.empty((H, S), **f32), du=torch.empty((H, A), **f32),
+                djdlam=torch.empty(H, **f32), u_star=torch.empty((H, A), **f32), kl=torch.empty(2, **f64)))
+        self.turn = 0
+        self.v_costs = torch.empty((max_g, ld), **f32)
+
+    def next_set(self):
+        self.turn = (self.turn + 1) % len(self.sets)
+        return self.sets[self.turn]
+
+
+def eval_gradient(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, p, p_stats, rinv, alpha, ctrl_lo, ctrl_hi, out,
+                  floor=FLOOR):
+    """One fused launch: rollout + footprint + renormalize + gradient + adjoint (klerg_eval_gradient)."""
+    H = u.shape[-2]
+    cabi.check(cabi.load().klerg_eval_gradient(
+        C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, peers, cabi.ptr(x0), cabi.ptr(R0),
+        cabi.ptr(u), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(q_base), cabi.ptr(p), cabi.ptr(p_stats),
+        float(floor), rinv, float(alpha), ctrl_lo, ctrl_hi, cabi.ptr(out["v"]), cabi.ptr(out["traj"]),
+        cabi.ptr(out["totals"]), cabi.ptr(out["cost"]), cabi.ptr(out["dgdx"]), cabi.ptr(out["du"]),
+        cabi.ptr(out["djdlam"]), cabi.ptr(out["u_star"]), cabi.ptr(out["kl"]), workspace(8), cabi.stream_ptr()),
+        "klerg_eval_gradient")
+    return out
+
+
+def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, v_scratch, cost, floor=FLOOR):
+    """One fused launch: get_cost of G <= 8 candidates U [G,H,A] -> cost [G] (klerg_eval_costs)."""
+    G, H, _ = U.shape
+    cabi.check(cabi.load().klerg_eval_costs(
+        C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, peers, cabi.ptr(x0), cabi.ptr(R0),
+        cabi.ptr(U), G, H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(q_base), cabi.ptr(p), cabi.ptr(p_stats),
+        float(floor), cabi.ptr(v_scratch), None, None, cabi.ptr(cost), workspace(8), cabi.stream_ptr()),
+        "klerg_eval_costs")
+    return cost
+
+
 def gather_rows(table, idx):
     """table [cap,S] float32, idx [M] int64 (device) -> [M,S]."""
     M, S = idx.numel(), table.shape[1]

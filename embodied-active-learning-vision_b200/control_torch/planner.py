@@ -27,7 +27,7 @@ from . import engine
 
 class PlannerContext:
     def __init__(self, dyn, barrier_spec, explr_locs, horizon, rinv_diag, ctrl_lo, ctrl_hi, alpha=1.0,
-                 group=engine.SINGLE, floor=engine.FLOOR):
+                 group=engine.SINGLE, floor=engine.FLOOR, fused=True):
         cabi.require_cuda()
         self.dyn = dyn
         self.bar = barrier_spec
@@ -42,6 +42,10 @@ class PlannerContext:
         self.spec = None
         self.n = 0
         self.evals = dict(cost=0, grad=0, fwd_pairs=0, grad_pairs=0)
+        self.fused = fused and group.world == 1
+        self.R0 = None
+        self._rinv_c, self._lo_c, self._hi_c = cabi.farr(self.rinv), cabi.farr(self.ctrl_lo), cabi.farr(self.ctrl_hi)
+        self.buf = None
 
     # -- per-step inputs ---------------------------------------------------------
     def set_samples(self, samples_dev, scale, nu=1.0):
@@ -51,6 +55,9 @@ class PlannerContext:
         self.samples = samples_dev
         self.n = samples_dev.shape[0]
         self.packed = engine.pack_samples(self.spec, samples_dev)
+        ld = self.packed.shape[1]
+        if self.buf is None or self.buf.ld != ld:
+            self.buf = engine.EvalBuffers(self.H, self.dyn.S, self.dyn.A, ld, samples_dev.device)
 
     def set_target(self, p, p_stats):
         self.p, self.p_stats = p, p_stats
@@ -70,6 +77,16 @@ class PlannerContext:
         if U.dim() == 2:
             U = U.unsqueeze(0)
         B = U.shape[0]
+        if self.fused:
+            U = U.contiguous()
+            cost = torch.empty(B, dtype=torch.float32, device=U.device)
+            for b0 in range(0, B, self.buf.max_g):
+                b1 = min(B, b0 + self.buf.max_g)
+                engine.eval_costs(self.spec, self.dyn, self.bar, None, self.x0, self.R0, U[b0:b1], self.packed, self.n,
+                                  self.q_base, self.p, self.p_stats, self.buf.v_costs, cost[b0:b1], self.floor)
+            self.evals["cost"] += B
+            self.evals["fwd_pairs"] += B * self.H * self.n
+            return cost
         ro = engine.rollout(self.dyn, self.bar, self.x0, U)
         v, totals = engine.footprint(self.spec, 0, ro["traj"][:, 1:, :], self.packed, self.n, add_in=self.q_base)
         totals_w = self.group.gather_blocks(totals)
@@ -79,6 +96,18 @@ class PlannerContext:
 
     def gradient(self, u, keep=False):
         """u [H,A] on the device -> dict(du, djdlam, u_star, dgdx, ...) on the device."""
+        if self.fused:
+            o = engine.eval_gradient(self.spec, self.dyn, self.bar, None, self.x0, self.R0, u.reshape(self.H, -1).contiguous(),
+                                     self.packed, self.n, self.q_base, self.p, self.p_stats, self._rinv_c, self.alpha,
+                                     self._lo_c, self._hi_c, self.buf.next_set(), self.floor)
+            self.evals["grad"] += 1
+            self.evals["fwd_pairs"] += self.H * self.n
+            self.evals["grad_pairs"] += self.H * self.n
+            out = dict(du=o["du"], djdlam=o["djdlam"], u_star=o["u_star"], dgdx=o["dgdx"], traj=o["traj"][: self.H],
+                       kl_parts=o["kl"].unsqueeze(0), cost=o["cost"])
+            if keep:
+                out.update(v=o["v"], totals=o["totals"].unsqueeze(0))
+            return out
         ro = engine.rollout(self.dyn, self.bar, self.x0, u, want_lin=True)
         traj = ro["traj"][0]
         pre = traj[: self.H]

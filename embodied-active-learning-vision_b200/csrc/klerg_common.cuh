@@ -9,20 +9,39 @@ namespace klerg {
 
 // ---- workspace layout (see klerg_workspace_bytes) ---------------------------
 // HEAD: [misc counters 64 x int][misc partials MAXBLK x 8 doubles]
-//       [gradient partials GRAD_MAXBLK x MAX_H*MAX_D doubles]
+//       [gradient partials GRAD_MAXBLK x MAX_H*MAX_D doubles][fused-eval region, see FUSED_*]
 // then one SEG record per segment g: [counter + pad 64 B][MAXBLK x 2 doubles]
 constexpr int MAXBLK = 1184;      // 148 SMs x 8
 constexpr int GRAD_MAXBLK = 296;  // 148 SMs x 2
 constexpr size_t HEAD_COUNTERS = 256;
 constexpr size_t HEAD_MISC = (size_t)MAXBLK * 8 * sizeof(double);
 constexpr size_t HEAD_GRAD = (size_t)GRAD_MAXBLK * KLERG_MAX_H * KLERG_MAX_D * sizeof(double);
-constexpr size_t HEAD_BYTES = HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD;
+// fused eval kernels (klerg_fused.cu): control words, world totals, per-CTA partials
+constexpr int FUSED_MAXBLK = 608;  // >= 148 SMs x 4, multiple of 32
+constexpr int FUSED_MAXG = 8;      // candidates per fused cost launch
+constexpr size_t FUSED_CTRL = 256;                                     // u32: [0] arrive-1 [1] arrive-2 [2] go [3] epoch
+constexpr size_t FUSED_WORLD = (size_t)FUSED_MAXG * 2 * sizeof(double);  // {sum, max} per candidate, all ranks combined
+constexpr size_t FUSED_TOT = (size_t)FUSED_MAXBLK * FUSED_MAXG * 2 * sizeof(double);
+constexpr size_t FUSED_KL = FUSED_TOT;
+constexpr size_t FUSED_GRAD = (size_t)FUSED_MAXBLK * KLERG_MAX_H * KLERG_MAX_D * sizeof(double);
+constexpr size_t FUSED_BYTES = FUSED_CTRL + FUSED_WORLD + FUSED_TOT + FUSED_KL + FUSED_GRAD;
+constexpr size_t HEAD_BYTES = HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + FUSED_BYTES;
 constexpr size_t SEG_BYTES = 64 + (size_t)MAXBLK * 2 * sizeof(double);
 
 __host__ __device__ inline int* ws_misc_counter(void* ws, int slot) { return (int*)ws + slot; }
 __host__ __device__ inline double* ws_misc_partials(void* ws) { return (double*)((char*)ws + HEAD_COUNTERS); }
 __host__ __device__ inline double* ws_grad_partials(void* ws) {
   return (double*)((char*)ws + HEAD_COUNTERS + HEAD_MISC);
+}
+__host__ __device__ inline char* ws_fused_base(void* ws) { return (char*)ws + HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD; }
+__host__ __device__ inline unsigned* ws_fused_ctrl(void* ws) { return (unsigned*)ws_fused_base(ws); }
+__host__ __device__ inline double* ws_fused_world(void* ws) { return (double*)(ws_fused_base(ws) + FUSED_CTRL); }
+__host__ __device__ inline double* ws_fused_tot(void* ws) { return (double*)(ws_fused_base(ws) + FUSED_CTRL + FUSED_WORLD); }
+__host__ __device__ inline double* ws_fused_kl(void* ws) {
+  return (double*)(ws_fused_base(ws) + FUSED_CTRL + FUSED_WORLD + FUSED_TOT);
+}
+__host__ __device__ inline double* ws_fused_grad(void* ws) {
+  return (double*)(ws_fused_base(ws) + FUSED_CTRL + FUSED_WORLD + FUSED_TOT + FUSED_KL);
 }
 __host__ __device__ inline int* ws_seg_counter(void* ws, int64_t g) {
   return (int*)((char*)ws + HEAD_BYTES + (size_t)g * SEG_BYTES);

@@ -1,0 +1,903 @@
+// Fused KL-ergodic evals: ONE cooperative launch per eval (sm_100a).
+//
+//   eval_grad_kernel : Robot.forward + footprint + renormalize + importance ratio +
+//                      kldiv_grad_vec for all H steps + Robot.backward   (klerg.py:409-450, 505-523)
+//                      -> du, djdlam, u*, dgdx, KL cost of the plan
+//   eval_cost_kernel : Robot.get_cost for G <= 8 candidate control sequences (klerg.py:686-710;
+//                      the <= 5 line-search windows of klerg.py:712-751 are one launch)
+//
+// Every CTA redoes the tiny rollout in shared memory (no broadcast needed), owns a contiguous
+// slice of the workspace samples, and the grid meets twice:
+//   (1) after the forward pair pass, to agree on sum/max of q = q_base + q_iter (renormalize
+//       needs both before the importance ratio exists);
+//   (2) after the gradient / KL pass, where the last CTA to arrive reduces the per-CTA
+//       partials in a fixed order and runs the adjoint sweep.
+// With several ranks (samples sharded over GPUs) the same two meeting points carry the
+// cross-GPU exchange: the leader CTA stores its rank's totals into every peer's mailbox over
+// NVLink (plain st.global on peer-mapped pointers, release flag) and spins on its own mailbox,
+// so the collective is a few hundred bytes of P2P stores inside the kernel - no NCCL launch.
+#include <cooperative_groups.h>
+
+#include <cstdio>
+
+#include "klerg_common.cuh"
+#include "klerg_dyn.cuh"
+#include "klerg_pair.cuh"
+
+namespace klerg {
+
+// ---- mailbox layout (symmetric across ranks; see klerg_mailbox_bytes) ----------------------
+constexpr int MB_MAXW = 8;                       // ranks
+constexpr int MB_A_STRIDE = 32;                  // doubles per (parity, rank) slot of exchange A; [31] = flag
+constexpr int MB_B_PAYLOAD = KLERG_MAX_H * KLERG_MAX_D + 2 * FUSED_MAXG;
+constexpr int MB_B_STRIDE = MB_B_PAYLOAD + 16;   // [MB_B_STRIDE-1] = flag
+constexpr size_t MB_A_BYTES = (size_t)2 * MB_MAXW * MB_A_STRIDE * sizeof(double);
+constexpr size_t MB_BYTES = MB_A_BYTES + (size_t)2 * MB_MAXW * MB_B_STRIDE * sizeof(double);
+
+__device__ __forceinline__ double* mb_a(void* base, int par, int r) {
+  return (double*)base + (size_t)(par * MB_MAXW + r) * MB_A_STRIDE;
+}
+__device__ __forceinline__ double* mb_b(void* base, int par, int r) {
+  return (double*)((char*)base + MB_A_BYTES) + (size_t)(par * MB_MAXW + r) * MB_B_STRIDE;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct Peers {
+  int world, rank;
+  void* mail[MB_MAXW];  // mail[r] = rank r's mailbox mapped into this process (mail[rank] = local)
+};
+
+struct EvalArgs {
+  KernelDev k;
+  DynDev d;
+  BarDev bar;
+  AdjParams ap;
+  Peers peers;
+  // inputs
+  const float* x0;       // [S]
+  const float* R0;       // [9] or NULL
+  const float* u;        // [G][H][A]
+  int G, H;
+  const float* packed;   // [D][ld] scaled samples of this rank
+  int64_t N, ld;
+  const float* q_base;   // [N] or NULL
+  const float* p;        // [N]
+  const double* p_stats; // [1] = sum p over all ranks
+  float floor;
+  // scratch
+  float* v;              // [G][ld]
+  void* ws;
+  // gradient-mode schedule
+  int nchr, nsub, rounds;  // state chunks per round, sample sub-streams, rounds
+  int ts;                  // samples staged per tile (multiple of 64)
+  // outputs
+  float* traj;           // [G][H+1][S] or NULL
+  double* totals;        // [G][2] {sum, max} of q_base + q_iter over all ranks, or NULL
+  float* cost;           // [G]
+  float* dgdx;           // [H][S]
+  float* du;             // [H][A]
+  float* djdlam;         // [H]
+  float* u_star;         // [H][A]
+  double* kl_out;        // [2] {sum p(log p - log c), sum c} over all ranks, or NULL
+};
+
+// block reduction of NQ doubles (fixed order); result valid in thread 0
+template <int NQ>
+__device__ __forceinline__ void block_reduce(const int (&kind)[NQ], double (&val)[NQ], double* sh_red /* [32*NQ] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const double v = warp_reduce(kind[q], val[q]);
+    if (lane == 0) sh_red[warp * NQ + q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double v = sh_red[q];
+      for (int w = 1; w < nwarp; ++w) v = red_combine(kind[q], v, sh_red[w * NQ + q]);
+      val[q] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Meeting point 1: every CTA has written part_tot[blk][g][2]; on return world_tot[g][2]
+// (all CTAs, all ranks) is readable by every thread.  The last CTA to arrive is the leader.
+// ---------------------------------------------------------------------------
+__device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_flag, double* sh_red) {
+  unsigned* ctrl = ws_fused_ctrl(a.ws);
+  const unsigned nblk = gridDim.x;
+  const unsigned go_val = 2u * epoch + 1u;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&ctrl[0], 1u);
+    *sh_flag = (t == nblk - 1);
+  }
+  __syncthreads();
+  if (*sh_flag) {
+    // leader: combine the per-CTA partials (thread b loads CTA b's pair, fixed-order block tree)
+    __threadfence();
+    double* world = ws_fused_world(a.ws);
+    const double* part = ws_fused_tot(a.ws);
+    const int nq = 2 * G;
+    const int par = epoch & 1;
+    for (int g = 0; g < G; ++g) {
+      double vals[2] = {0.0, -INFINITY};
+      for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x) {
+        vals[0] += __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 0]);
+        vals[1] = fmax(vals[1], __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 1]));
+      }
+      const int kinds[2] = {RED_SUM, RED_MAX};
+      block_reduce<2>(kinds, vals, sh_red);
+      if (threadIdx.x == 0) {
+        if (a.peers.world > 1) {
+          for (int r = 0; r < a.peers.world; ++r) {
+            double* slot = mb_a(a.peers.mail[r], par, a.peers.rank);
+            slot[2 * g] = vals[0];
+            slot[2 * g + 1] = vals[1];
+          }
+        } else {
+          world[2 * g] = vals[0];
+          world[2 * g + 1] = vals[1];
+        }
+      }
+    }
+    if (a.peers.world > 1) {
+      // all-gather over NVLink: payload stores above, then one release flag per peer; wait for every rank's flag
+      if (threadIdx.x == 0) __threadfence_system();
+      __syncthreads();
+      if ((int)threadIdx.x < a.peers.world) {
+        st_release_sys_u64((unsigned long long*)&mb_a(a.peers.mail[threadIdx.x], par, a.peers.rank)[MB_A_STRIDE - 1],
+                           (unsigned long long)epoch + 1ull);
+        const unsigned long long* f =
+            (const unsigned long long*)&mb_a(a.peers.mail[a.peers.rank], par, threadIdx.x)[MB_A_STRIDE - 1];
+        while (ld_acquire_sys_u64(f) != (unsigned long long)epoch + 1ull) {
+        }
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < nq) {
+        const int q = threadIdx.x;
+        double v = (q & 1) ? -INFINITY : 0.0;
+        for (int r = 0; r < a.peers.world; ++r) {
+          const double x = ld_volatile_f64(&mb_a(a.peers.mail[a.peers.rank], par, r)[q]);
+          v = (q & 1) ? fmax(v, x) : v + x;
+        }
+        world[q] = v;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      ctrl[0] = 0;
+      __threadfence();
+      st_release_u32(&ctrl[2], go_val);
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      while (ld_acquire_u32(&ctrl[2]) != go_val) {
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Meeting point 2: returns true (all threads) in the last CTA to arrive.
+__device__ bool meet_last(const EvalArgs& a, int* sh_flag) {
+  unsigned* ctrl = ws_fused_ctrl(a.ws);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(&ctrl[1], 1u);
+    *sh_flag = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  const bool last = *sh_flag != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// Cross-rank all-gather of `n` doubles held in shared memory (sh_vals) by the last CTA:
+// on return sh_vals[i] = sum over ranks (rank order) of the ranks' sh_vals[i].
+__device__ void exchange_sum(const EvalArgs& a, unsigned epoch, double* sh_vals, int n) {
+  if (a.peers.world <= 1) return;
+  const int par = epoch & 1;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * a.peers.world; e += blockDim.x) {
+    const int r = e / n, i = e - r * n;
+    mb_b(a.peers.mail[r], par, a.peers.rank)[i] = sh_vals[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < a.peers.world) {
+    st_release_sys_u64((unsigned long long*)&mb_b(a.peers.mail[threadIdx.x], par, a.peers.rank)[MB_B_STRIDE - 1],
+                       (unsigned long long)epoch + 1ull);
+    const unsigned long long* f =
+        (const unsigned long long*)&mb_b(a.peers.mail[a.peers.rank], par, threadIdx.x)[MB_B_STRIDE - 1];
+    while (ld_acquire_sys_u64(f) != (unsigned long long)epoch + 1ull) {
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = 0.0;
+    for (int r = 0; r < a.peers.world; ++r) v += ld_volatile_f64(&mb_b(a.peers.mail[a.peers.rank], par, r)[i]);
+    sh_vals[i] = v;
+  }
+  __syncthreads();
+}
+
+// contiguous sample slice of this CTA: [lo, hi) with lo % 8 == 0, hi <= ld
+__device__ __forceinline__ void cta_slice(int64_t N, int64_t ld, int64_t& lo, int64_t& hi) {
+  int64_t per = (N + gridDim.x - 1) / gridDim.x;
+  per = (per + 7) & ~(int64_t)7;
+  lo = (int64_t)blockIdx.x * per;
+  hi = lo + per;
+  if (hi > ld) hi = ld;
+  if (lo > ld) lo = ld;
+}
+
+// Forward pair pass of one trajectory (T duplicated rows at sh_x2) over this CTA's slice:
+// v[i] = q_base[i] + inv_nu * sum_t psi; returns the slice's {sum, max} of v over i < N.
+template <int D>
+__device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+                                              int64_t hi, double& tsum, double& tmax) {
+  for (int64_t i0 = lo + (int64_t)threadIdx.x * 4; i0 < hi; i0 += (int64_t)blockDim.x * 4) {
+    u64 s2[D][2], acc[2];
+    float emin[4];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
+      s2[d][0] = pack2(s.x, s.y);
+      s2[d][1] = pack2(s.z, s.w);
+    }
+    acc[0] = acc[1] = pack2(0.f, 0.f);
+    pair_forward<D, 2, 0>(sh_x2, T, s2, acc, emin);
+    float o[4];
+    unpack2(acc[0], o[0], o[1]);
+    unpack2(acc[1], o[2], o[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + q;
+      float v = o[q] * a.k.inv_nu;
+      if (i < a.N) {
+        if (a.q_base) v += a.q_base[i];
+        tsum += (double)v;
+        tmax = fmax(tmax, (double)v);
+      }
+      o[q] = v;
+    }
+    *reinterpret_cast<float4*>(v_out + i0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory carve-up
+// ---------------------------------------------------------------------------
+struct SmemPlan {
+  size_t u, traj, dbarr, P, x2, xs, tile, part, red, misc, total;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+template <int D>
+__host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, int ts, int nwarps, int WT) {
+  SmemPlan p;
+  size_t o = 0;
+  p.u = o;     o = align16(o + sizeof(float) * H * A);
+  p.traj = o;  o = align16(o + sizeof(float) * (H + 1) * S);
+  p.dbarr = o; o = align16(o + sizeof(float) * H * S);
+  p.P = o;     o = align16(o + (roll ? sizeof(float) * H * A * A : 0));
+  p.x2 = o;    o = align16(o + sizeof(u64) * H * Row2<D>::DP);
+  p.xs = o;    o = align16(o + sizeof(float) * H * D);
+  size_t tile = sizeof(float) * (size_t)(D + 1) * ts;
+  const size_t adj = sizeof(float) * ((size_t)H * S + (size_t)H * A) + sizeof(double) * ((size_t)H * D + 2) + 8;
+  if (tile < adj) tile = adj;  // the adjoint phase reuses the tile area
+  p.tile = o;  o = align16(o + tile);
+  p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
+  p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
+  p.misc = o;  o = align16(o + 64);
+  p.total = o;
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// gradient eval
+// ---------------------------------------------------------------------------
+template <int D, int WT, int MAXT>
+__global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int H = a.H, S = a.d.S, A = a.d.A;
+  const bool roll = a.d.kind == KLERG_DYN_ROLL, speed = a.d.kind == KLERG_DYN_SPEED;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const SmemPlan sp = plan_grad<D>(H, S, A, roll, a.ts, nwarps, WT);
+  float* s_u = (float*)(smem + sp.u);
+  float* s_traj = (float*)(smem + sp.traj);
+  float* s_dbarr = (float*)(smem + sp.dbarr);
+  float* s_P = roll ? (float*)(smem + sp.P) : nullptr;
+  u64* s_x2 = (u64*)(smem + sp.x2);
+  float* s_xs = (float*)(smem + sp.xs);
+  float* s_tile = (float*)(smem + sp.tile);
+  float* s_part = (float*)(smem + sp.part);
+  double* s_red = (double*)(smem + sp.red);
+  int* s_flag = (int*)(smem + sp.misc);
+  unsigned* s_epoch = (unsigned*)(smem + sp.misc) + 1;
+  float* s_bsum = (float*)(smem + sp.misc) + 2;
+  constexpr int DP = Row2<D>::DP;
+
+  // ---- phase 0: rollout (every CTA, one warp) -----------------------------------------------
+  for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
+  if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
+  __syncthreads();
+  if (warp == 0) {
+    const float bs = rollout_warp(a.d, a.bar, a.x0, a.R0, s_u, H, s_traj, s_dbarr, s_P, nullptr);
+    if (lane == 0) *s_bsum = bs;
+  }
+  __syncthreads();
+  const unsigned epoch = *s_epoch;
+  for (int e = tid; e < H * DP; e += blockDim.x) {
+    const int t = e / DP, d = e - t * DP;
+    float v = 0.f;
+    if (d < D) {
+      v = s_traj[t * S + a.k.explr[d]] * a.k.a[d];  // pre-step states (Robot.forward, klerg.py:419-431)
+      s_xs[t * D + d] = v;
+    }
+    s_x2[e] = pack2(v, v);
+  }
+  if (blockIdx.x == 0 && a.traj)
+    for (int e = tid; e < (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
+  __syncthreads();
+
+  // ---- phase 1: forward pair pass, slice totals -------------------------------------------------
+  int64_t lo, hi;
+  cta_slice(a.N, a.ld, lo, hi);
+  {
+    double tsum = 0.0, tmax = -INFINITY;
+    forward_slice<D>(a, s_x2, H, a.v, lo, hi, tsum, tmax);
+    const int kinds[2] = {RED_SUM, RED_MAX};
+    double vals[2] = {tsum, tmax};
+    block_reduce<2>(kinds, vals, s_red);
+    if (tid == 0) {
+      double* part = ws_fused_tot(a.ws) + (size_t)blockIdx.x * FUSED_MAXG * 2;
+      part[0] = vals[0];
+      part[1] = vals[1];
+    }
+  }
+  meet_totals(a, 1, epoch, s_flag, s_red);
+  const double vsum = __ldcg(&ws_fused_world(a.ws)[0]);
+  const double vmax = __ldcg(&ws_fused_world(a.ws)[1]);
+  if (blockIdx.x == 0 && tid == 0 && a.totals) {
+    a.totals[0] = vsum;
+    a.totals[1] = vmax;
+  }
+  const float vsum_f = (float)vsum;  // the reference divides by the fp32 sum
+  const float maxc_f = (float)fmax(vmax / vsum, (double)a.floor);
+
+  // ---- phase 2: importance ratio + gradient pair pass ----------------------------------------------
+  const int ts = a.ts;
+  const int HD = H * D;
+  const int nblk = gridDim.x;
+  const int gstride = (nblk + 31) & ~31;  // partial layout [e][gstride]: the final reduce reads rows coalesced
+  double kl_a = 0.0, kl_c = 0.0;
+  for (int r = 0; r < a.rounds; ++r) {
+    const int cw = warp % a.nchr, sub = warp / a.nchr;
+    const int t0 = (r * a.nchr + cw) * WT;
+    const bool active = sub < a.nsub && t0 < H;
+    u64 xs2[WT][D], acc[WT][D];
+#pragma unroll
+    for (int k = 0; k < WT; ++k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float x = (active && t0 + k < H) ? s_xs[(t0 + k) * D + d] : 0.f;
+        xs2[k][d] = pack2(x, x);
+        acc[k][d] = pack2(0.f, 0.f);
+      }
+    for (int64_t base = lo; base < hi; base += ts) {
+      const int cnt = (int)min((int64_t)ts, hi - base);
+      const int cnt64 = (cnt + 63) & ~63;
+      __syncthreads();
+      for (int e = tid; e < cnt64; e += blockDim.x) {
+        const int64_t i = base + e;
+        float w = 0.f;
+        if (e < cnt && i < a.N) {
+          const float c = fmaxf(a.v[i] / vsum_f, a.floor);
+          const float pi = a.p[i];
+          w = pi * maxc_f / c;  // p/q with q = c / max c  (klerg.py:436)
+          if (r == 0) {
+            kl_a += (double)(pi * (logf(pi) - logf(c)));
+            kl_c += (double)c;
+          }
+#pragma unroll
+          for (int d = 0; d < D; ++d) s_tile[d * ts + e] = __ldg(a.packed + (int64_t)d * a.ld + i);
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) s_tile[d * ts + e] = 0.f;
+        }
+        s_tile[D * ts + e] = w;
+      }
+      __syncthreads();
+      if (active) {
+        for (int pb = sub * 64; pb < cnt64; pb += a.nsub * 64) {
+          const int i = pb + 2 * lane;
+          u64 s2[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&s_tile[d * ts + i]);
+          const u64 w2 = *reinterpret_cast<const u64*>(&s_tile[D * ts + i]);
+          pair_gradient<D, WT>(xs2, s2, w2, acc);
+        }
+      }
+    }
+    // lanes -> warp sums -> CTA partial for this round's states
+#pragma unroll
+    for (int k = 0; k < WT; ++k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float x, y;
+        unpack2(acc[k][d], x, y);
+        const float v = warp_sum_f(x + y);
+        if (lane == 0) s_part[(warp * WT + k) * D + d] = v;
+      }
+    __syncthreads();
+    double* gpart = ws_fused_grad(a.ws);
+    for (int e = tid; e < a.nchr * WT * D; e += blockDim.x) {
+      const int c = e / (WT * D), kd = e - c * (WT * D);
+      const int t = (r * a.nchr + c) * WT + kd / D;
+      if (t < H) {
+        float v = 0.f;
+        for (int sb = 0; sb < a.nsub; ++sb) v += s_part[((sb * a.nchr + c) * WT) * D + kd];
+        gpart[(size_t)(t * D + kd % D) * gstride + blockIdx.x] = (double)v;
+      }
+    }
+  }
+  {
+    const int kinds[2] = {RED_SUM, RED_SUM};
+    double vals[2] = {kl_a, kl_c};
+    block_reduce<2>(kinds, vals, s_red);
+    if (tid == 0) {
+      double* part = ws_fused_kl(a.ws) + (size_t)blockIdx.x * FUSED_MAXG * 2;
+      part[0] = vals[0];
+      part[1] = vals[1];
+    }
+  }
+
+  // ---- phase 3: the last CTA reduces the partials and runs the adjoint --------------------------------
+  if (!meet_last(a, s_flag)) return;
+  float* s_g = s_tile;                           // [H][S]
+  float* s_sgn = s_g + H * S;                    // [H][A]
+  double* s_val = (double*)(s_sgn + H * A + ((H * S + H * A) & 1));  // [HD + 2], 8-byte aligned
+  {
+    const double* gpart = ws_fused_grad(a.ws);
+    const double* klp = ws_fused_kl(a.ws);
+    for (int e = warp; e < HD + 2; e += nwarps) {
+      double v = 0.0;
+      if (e < HD) {
+        for (int b = lane; b < nblk; b += 32) v += __ldcg(&gpart[(size_t)e * gstride + b]);
+      } else {
+        for (int b = lane; b < nblk; b += 32) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + (e - HD)]);
+      }
+      v = warp_reduce(RED_SUM, v);
+      if (lane == 0) s_val[e] = v;
+    }
+  }
+  __syncthreads();
+  exchange_sum(a, epoch, s_val, HD + 2);
+  for (int e = tid; e < H * S; e += blockDim.x) s_g[e] = 0.f;
+  __syncthreads();
+  for (int e = tid; e < HD; e += blockDim.x) {
+    const int d = e % D;
+    s_g[(e / D) * S + a.k.explr[d]] = (float)(s_val[e] * (double)a.k.gfac[d]);
+  }
+  __syncthreads();
+  for (int e = tid; e < H * S; e += blockDim.x) {
+    const float g = s_g[e];
+    a.dgdx[e] = g;
+    s_g[e] = g - s_dbarr[e];
+  }
+  if (speed)
+    for (int e = tid; e < H * A; e += blockDim.x) s_sgn[e] = (s_traj[(e / A) * S + A + (e % A)] < 0.f) ? -1.f : 1.f;
+  __syncthreads();
+  if (warp == 0) adjoint_warp(a.d, a.ap, H, s_g, s_P, s_sgn, s_u, a.du, a.djdlam, a.u_star);
+  if (tid == 32 || (blockDim.x <= 32 && tid == 0)) {
+    const double sa = s_val[HD], sc = s_val[HD + 1];
+    if (a.kl_out) {
+      a.kl_out[0] = sa;
+      a.kl_out[1] = sc;
+    }
+    if (a.cost) {
+      const double spv = a.p_stats[0];
+      // KL of the PRE-step footprint (what backward() differentiates) + barrier of the post-step states
+      a.cost[0] = (float)(sa / spv - log(spv) + log(sc)) + *s_bsum;
+    }
+    unsigned* ctrl = ws_fused_ctrl(a.ws);
+    ctrl[1] = 0;
+    ctrl[3] = epoch + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// cost eval of G <= FUSED_MAXG candidates
+// ---------------------------------------------------------------------------
+template <int D>
+__host__ __device__ inline SmemPlan plan_cost(int G, int H, int S, int A) {
+  SmemPlan p{};
+  size_t o = 0;
+  p.u = o;    o = align16(o + sizeof(float) * (size_t)G * H * A);
+  p.traj = o; o = align16(o + sizeof(float) * (size_t)G * (H + 1) * S);
+  p.x2 = o;   o = align16(o + sizeof(u64) * (size_t)G * H * Row2<D>::DP);
+  p.red = o;  o = align16(o + sizeof(double) * 32 * 2 * FUSED_MAXG);
+  p.misc = o; o = align16(o + 64 + sizeof(float) * FUSED_MAXG);
+  p.total = o;
+  return p;
+}
+
+template <int D>
+__global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int H = a.H, S = a.d.S, A = a.d.A, G = a.G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const SmemPlan sp = plan_cost<D>(G, H, S, A);
+  float* s_u = (float*)(smem + sp.u);
+  float* s_traj = (float*)(smem + sp.traj);
+  u64* s_x2 = (u64*)(smem + sp.x2);
+  double* s_red = (double*)(smem + sp.red);
+  int* s_flag = (int*)(smem + sp.misc);
+  unsigned* s_epoch = (unsigned*)(smem + sp.misc) + 1;
+  float* s_bsum = (float*)(smem + sp.misc + 64);
+  constexpr int DP = Row2<D>::DP;
+
+  for (int e = tid; e < G * H * A; e += blockDim.x) s_u[e] = a.u[e];
+  if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
+  __syncthreads();
+  for (int g = warp; g < G; g += nwarps) {
+    const float bs = rollout_warp(a.d, a.bar, a.x0, a.R0, s_u + (size_t)g * H * A, H, s_traj + (size_t)g * (H + 1) * S,
+                                  nullptr, nullptr, nullptr);
+    if (lane == 0) s_bsum[g] = bs;
+  }
+  __syncthreads();
+  const unsigned epoch = *s_epoch;
+  for (int e = tid; e < G * H * DP; e += blockDim.x) {
+    const int g = e / (H * DP), r = e - g * (H * DP);
+    const int t = r / DP, d = r - t * DP;
+    float v = 0.f;
+    if (d < D) v = s_traj[((size_t)g * (H + 1) + t + 1) * S + a.k.explr[d]] * a.k.a[d];  // post-step states (klerg.py:688-691)
+    s_x2[e] = pack2(v, v);
+  }
+  if (blockIdx.x == 0 && a.traj)
+    for (int e = tid; e < G * (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
+  __syncthreads();
+
+  int64_t lo, hi;
+  cta_slice(a.N, a.ld, lo, hi);
+  for (int g = 0; g < G; ++g) {
+    double tsum = 0.0, tmax = -INFINITY;
+    forward_slice<D>(a, s_x2 + (size_t)g * H * DP, H, a.v + (size_t)g * a.ld, lo, hi, tsum, tmax);
+    const int kinds[2] = {RED_SUM, RED_MAX};
+    double vals[2] = {tsum, tmax};
+    block_reduce<2>(kinds, vals, s_red);
+    if (tid == 0) {
+      double* part = ws_fused_tot(a.ws) + ((size_t)blockIdx.x * FUSED_MAXG + g) * 2;
+      part[0] = vals[0];
+      part[1] = vals[1];
+    }
+  }
+  meet_totals(a, G, epoch, s_flag, s_red);
+  if (blockIdx.x == 0 && tid < 2 * G && a.totals) a.totals[tid] = __ldcg(&ws_fused_world(a.ws)[tid]);
+
+  // KL partials: sum_i p_i (log p_i - log c_i), sum_i c_i   (klerg.py:694-699 in closed form)
+  float vs[FUSED_MAXG], maxc[FUSED_MAXG];
+  double sa[FUSED_MAXG], sc[FUSED_MAXG];
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    sa[g] = sc[g] = 0.0;
+    vs[g] = maxc[g] = 1.f;
+    if (g < G) {
+      const double vsum = __ldcg(&ws_fused_world(a.ws)[2 * g]), vmax = __ldcg(&ws_fused_world(a.ws)[2 * g + 1]);
+      vs[g] = (float)vsum;
+      maxc[g] = fmaxf((float)vmax / vs[g], a.floor);
+    }
+  }
+  const int64_t hiN = hi < a.N ? hi : a.N;
+  for (int64_t i = lo + tid; i < hiN; i += blockDim.x) {
+    float pi = a.p[i];
+    if (pi != pi) pi = 1e-6f;
+    const float lp = logf(pi);
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g) {
+      if (g < G) {
+        float c = fmaxf(a.v[(size_t)g * a.ld + i] / vs[g], a.floor);
+        if (c != c) c = 1e-6f * maxc[g];  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
+        sa[g] += (double)(pi * (lp - logf(c)));
+        sc[g] += (double)c;
+      }
+    }
+  }
+  for (int g = 0; g < G; ++g) {
+    const int kinds[2] = {RED_SUM, RED_SUM};
+    double vals[2] = {0.0, 0.0};
+#pragma unroll
+    for (int gg = 0; gg < FUSED_MAXG; ++gg)
+      if (gg == g) {
+        vals[0] = sa[gg];
+        vals[1] = sc[gg];
+      }
+    block_reduce<2>(kinds, vals, s_red);
+    if (tid == 0) {
+      double* part = ws_fused_kl(a.ws) + ((size_t)blockIdx.x * FUSED_MAXG + g) * 2;
+      part[0] = vals[0];
+      part[1] = vals[1];
+    }
+  }
+
+  if (!meet_last(a, s_flag)) return;
+  double* s_val = s_red;  // [2G]
+  {
+    const double* klp = ws_fused_kl(a.ws);
+    const int nblk = gridDim.x;
+    for (int e = warp; e < 2 * G; e += nwarps) {
+      double v = 0.0;
+      for (int b = lane; b < nblk; b += 32) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + e]);
+      v = warp_reduce(RED_SUM, v);
+      if (lane == 0) s_val[e] = v;
+    }
+  }
+  __syncthreads();
+  exchange_sum(a, epoch, s_val, 2 * G);
+  if (tid < G) {
+    const double spv = a.p_stats[0];
+    const double dkl = s_val[2 * tid] / spv - log(spv) + log(s_val[2 * tid + 1]);
+    a.cost[tid] = (float)dkl + s_bsum[tid];
+  }
+  if (tid == 0) {
+    unsigned* ctrl = ws_fused_ctrl(a.ws);
+    ctrl[1] = 0;
+    ctrl[3] = epoch + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct GradSchedule {
+  int wt, nwarps, nchr, nsub, rounds;
+  double eff;
+};
+
+static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 18 : 17); }
+
+// Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
+// CTA's warps with as few idle slots as possible.
+static GradSchedule plan_schedule(int D, int H) {
+  const int maxw = grad_max_warps(D);
+  const int wts_small[4] = {5, 3, 2, 1};
+  const int wts_big[3] = {3, 2, 1};
+  const int* wts = D <= 4 ? wts_small : wts_big;
+  const int nw = D <= 4 ? 4 : 3;
+  GradSchedule best{};
+  best.eff = -1.0;
+  for (int i = 0; i < nw; ++i) {
+    const int wt = wts[i];
+    const int nch = (H + wt - 1) / wt;
+    GradSchedule s{};
+    s.wt = wt;
+    if (nch <= maxw) {
+      s.rounds = 1;
+      s.nchr = nch;
+    } else {
+      s.rounds = (nch + maxw - 1) / maxw;
+      s.nchr = (nch + s.rounds - 1) / s.rounds;
+    }
+    s.nsub = maxw / s.nchr;
+    s.nwarps = s.nchr * s.nsub;
+    // useful pair slots / issued pair slots, discounted when few warps are resident or the tile is restaged
+    s.eff = (double)H / ((double)s.rounds * s.nchr * wt) * (0.5 + 0.5 * s.nwarps / maxw) / (1.0 + 0.02 * (s.rounds - 1));
+    if (s.eff > best.eff + 1e-9) best = s;
+  }
+  return best;
+}
+
+template <typename K>
+static int coop_launch(K kernel, int nblk, int nthreads, size_t smem, const EvalArgs& a, cudaStream_t stream,
+                       const char* what) {
+  EvalArgs args = a;
+  void* pargs[1] = {(void*)&args};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)nblk), dim3((unsigned)nthreads), pargs,
+                                              smem, stream);
+  if (e != cudaSuccess) {
+    set_error("%s: cooperative launch failed (grid %d x %d threads, %zu B smem): %s", what, nblk, nthreads, smem,
+              cudaGetErrorString(e));
+    cudaGetLastError();
+    return -4;
+  }
+  return check_launch(what);
+}
+
+// resident CTAs per SM for a kernel/block/smem combination (cached per kernel pointer + shape).
+// The dynamic shared-memory limit of a kernel is only ever raised.
+template <typename K>
+static int resident_ctas(K kernel, int nthreads, size_t smem) {
+  struct Key {
+    const void* k;
+    int t;
+    size_t s;
+    int n;
+  };
+  static Key cache[64];
+  static int ncache = 0;
+  static const void* raised_k[64];
+  static size_t raised_s[64];
+  static int nraised = 0;
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].k == (const void*)kernel && cache[i].t == nthreads && cache[i].s == smem) return cache[i].n;
+  if (smem > 48 * 1024) {
+    int slot = -1;
+    for (int i = 0; i < nraised; ++i)
+      if (raised_k[i] == (const void*)kernel) slot = i;
+    if (slot < 0 && nraised < 64) {
+      slot = nraised++;
+      raised_k[slot] = (const void*)kernel;
+      raised_s[slot] = 0;
+    }
+    if (slot < 0 || raised_s[slot] < smem) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (slot >= 0) raised_s[slot] = smem;
+    }
+  }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, nthreads, smem) != cudaSuccess) n = 0;
+  cudaGetLastError();
+  if (ncache < 64) cache[ncache++] = Key{(const void*)kernel, nthreads, smem, n};
+  return n;
+}
+
+static int pick_grid(int64_t N, int per_sm, int min_samples_per_cta) {
+  int64_t nblk = (N + min_samples_per_cta - 1) / min_samples_per_cta;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  if (nblk > cap) nblk = cap;
+  if (nblk > FUSED_MAXBLK) nblk = FUSED_MAXBLK;
+  if (nblk < 1) nblk = 1;
+  return (int)nblk;
+}
+
+template <int D, int WT>
+static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, cudaStream_t stream) {
+  constexpr int MAXT = (D <= 3 ? 20 : (D == 4 ? 18 : 17)) * 32;
+  auto kernel = eval_grad_kernel<D, WT, MAXT>;
+  const int nthreads = s.nwarps * 32;
+  const bool roll = a.d.kind == KLERG_DYN_ROLL;
+  // tile: up to 2048 samples, but no more than one CTA's slice at full grid
+  int64_t per = (a.N + sm_count() - 1) / sm_count();
+  int ts = 2048;
+  while (ts > 64 && ts / 2 >= per) ts /= 2;
+  a.ts = ts;
+  a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds;
+  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, ts, s.nwarps, WT);
+  if (sp.total > 200 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
+  const int per_sm = resident_ctas(kernel, nthreads, sp.total);
+  if (per_sm < 1) { set_error("eval_gradient: kernel does not fit on an SM (threads=%d smem=%zu)", nthreads, sp.total); return -4; }
+  const int nblk = pick_grid(a.N, 1, 128);
+  return coop_launch(kernel, nblk, nthreads, sp.total, a, stream, "eval_grad_kernel");
+}
+
+template <int D>
+static int launch_grad_d(EvalArgs& a, cudaStream_t stream) {
+  const GradSchedule s = plan_schedule(D, a.H);
+  switch (s.wt) {
+    case 1: return launch_grad_wt<D, 1>(a, s, stream);
+    case 2: return launch_grad_wt<D, 2>(a, s, stream);
+    case 3: return launch_grad_wt<D, 3>(a, s, stream);
+    case 5:
+      if constexpr (D <= 4) return launch_grad_wt<D, 5>(a, s, stream);
+  }
+  set_error("eval_gradient: no schedule for D=%d H=%d", D, a.H);
+  return -2;
+}
+
+template <int D>
+static int launch_cost_d(EvalArgs& a, cudaStream_t stream) {
+  auto kernel = eval_cost_kernel<D>;
+  const SmemPlan sp = plan_cost<D>(a.G, a.H, a.d.S, a.d.A);
+  if (sp.total > 200 * 1024) { set_error("eval_costs: G*H too large for shared-memory staging"); return -1; }
+  int nthreads = 512;
+  const int per_sm = resident_ctas(kernel, nthreads, sp.total);
+  if (per_sm < 1) { set_error("eval_costs: kernel does not fit on an SM"); return -4; }
+  const int nblk = pick_grid(a.N, 1, 256);
+  return coop_launch(kernel, nblk, nthreads, sp.total, a, stream, "eval_cost_kernel");
+}
+
+static bool fill_common(EvalArgs& a, const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                        const klerg_peers* peers) {
+  if (!make_kernel_dev(k, a.k) || !make_dyn(dyn, a.d) || !make_bar(bar, a.bar)) return false;
+  a.peers.world = 1;
+  a.peers.rank = 0;
+  for (int r = 0; r < MB_MAXW; ++r) a.peers.mail[r] = nullptr;
+  if (peers && peers->world > 1) {
+    if (peers->world > MB_MAXW || peers->rank < 0 || peers->rank >= peers->world) { set_error("peers: world/rank out of range"); return false; }
+    a.peers.world = peers->world;
+    a.peers.rank = peers->rank;
+    for (int r = 0; r < peers->world; ++r) {
+      if (!peers->mailbox[r]) { set_error("peers: mailbox[%d] is null", r); return false; }
+      a.peers.mail[r] = peers->mailbox[r];
+    }
+  }
+  return true;
+}
+
+}  // namespace klerg
+
+using namespace klerg;
+
+extern "C" size_t klerg_mailbox_bytes(void) { return MB_BYTES; }
+
+extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                                   const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
+                                   const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
+                                   const double* p_stats, float floor, const float* Rinv_diag, float alpha,
+                                   const float* ctrl_lo, const float* ctrl_hi, float* v_scratch, float* traj,
+                                   double* totals, float* cost, float* dgdx, float* du, float* djdlam, float* u_star,
+                                   double* kl_out, void* workspace, void* stream) {
+  EvalArgs a{};
+  if (!fill_common(a, k, dyn, bar, peers)) return -1;
+  if (H < 1 || H > KLERG_MAX_H) { set_error("eval_gradient: H out of range"); return -1; }
+  if (N < 1 || ld < N || (ld & 3)) { set_error("eval_gradient: bad sample sizes"); return -1; }
+  if (!workspace || !v_scratch || !dgdx || !du || !djdlam || !u_star) { set_error("eval_gradient: null output/workspace"); return -1; }
+  for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
+  a.ap.alpha = alpha;
+  a.x0 = x0; a.R0 = R0; a.u = u; a.G = 1; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base; a.p = p;
+  a.p_stats = p_stats; a.floor = floor; a.v = v_scratch; a.ws = workspace; a.traj = traj; a.totals = totals; a.cost = cost;
+  a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star; a.kl_out = kl_out;
+  switch (a.k.D) {
+    case 1: return launch_grad_d<1>(a, (cudaStream_t)stream);
+    case 2: return launch_grad_d<2>(a, (cudaStream_t)stream);
+    case 3: return launch_grad_d<3>(a, (cudaStream_t)stream);
+    case 4: return launch_grad_d<4>(a, (cudaStream_t)stream);
+    case 5: return launch_grad_d<5>(a, (cudaStream_t)stream);
+    case 6: return launch_grad_d<6>(a, (cudaStream_t)stream);
+    default: set_error("eval_gradient: D=%d not instantiated (1..6)", a.k.D); return -2;
+  }
+}
+
+extern "C" int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                                const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t G,
+                                int64_t H, const float* packed, int64_t N, int64_t ld, const float* q_base,
+                                const float* p, const double* p_stats, float floor, float* v_scratch, float* traj,
+                                double* totals, float* cost, void* workspace, void* stream) {
+  EvalArgs a{};
+  if (!fill_common(a, k, dyn, bar, peers)) return -1;
+  if (H < 1 || H > KLERG_MAX_H) { set_error("eval_costs: H out of range"); return -1; }
+  if (G < 1 || G > FUSED_MAXG) { set_error("eval_costs: G must be in 1..%d", FUSED_MAXG); return -1; }
+  if (N < 1 || ld < N || (ld & 3)) { set_error("eval_costs: bad sample sizes"); return -1; }
+  if (!workspace || !v_scratch || !cost) { set_error("eval_costs: null output/workspace"); return -1; }
+  a.x0 = x0; a.R0 = R0; a.u = u; a.G = (int)G; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base;
+  a.p = p; a.p_stats = p_stats; a.floor = floor; a.v = v_scratch; a.ws = workspace; a.traj = traj; a.totals = totals;
+  a.cost = cost;
+  switch (a.k.D) {
+    case 1: return launch_cost_d<1>(a, (cudaStream_t)stream);
+    case 2: return launch_cost_d<2>(a, (cudaStream_t)stream);
+    case 3: return launch_cost_d<3>(a, (cudaStream_t)stream);
+    case 4: return launch_cost_d<4>(a, (cudaStream_t)stream);
+    case 5: return launch_cost_d<5>(a, (cudaStream_t)stream);
+    case 6: return launch_cost_d<6>(a, (cudaStream_t)stream);
+    default: set_error("eval_costs: D=%d not instantiated (1..6)", a.k.D); return -2;
+  }
+}

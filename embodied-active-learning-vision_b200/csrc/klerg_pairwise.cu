@@ -10,6 +10,7 @@
 #include <cstdio>
 
 #include "klerg_common.cuh"
+#include "klerg_pair.cuh"
 
 namespace klerg {
 
@@ -28,10 +29,15 @@ __global__ void pack_samples_kernel(KernelDev k, const float* __restrict__ sampl
 }
 
 // ---------------------------------------------------------------------------
-// forward: footprint (sum) / spread (max)
+// forward: footprint (sum) / spread (max), packed f32x2 pair math (klerg_pair.cuh)
 // ---------------------------------------------------------------------------
 constexpr int FP_THREADS = 256;
-constexpr int FP_CHUNK = 1024;  // state rows staged per pass
+
+// state rows staged per pass: 32 KB (D <= 4) / 36 KB (D <= 6) of duplicated {x, x} rows
+template <int D>
+struct FootChunk {
+  static constexpr int ROWS = Row2<D>::DP <= 4 ? 1024 : 768;
+};
 
 struct FootArgs {
   KernelDev k;
@@ -47,69 +53,40 @@ struct FootArgs {
   int64_t ntiles;
 };
 
-template <int D>
-struct StateRow {
-  static constexpr int DP = (D <= 1) ? 1 : (D <= 2) ? 2 : (D <= 4) ? 4 : 8;
-};
-
-template <int D>
-__device__ __forceinline__ void load_state(const float* sh, int j, float (&x)[D]) {
-  constexpr int DP = StateRow<D>::DP;
-  const float* r = sh + j * DP;
-  if constexpr (DP == 1) {
-    x[0] = r[0];
-  } else if constexpr (DP == 2) {
-    float2 v = *reinterpret_cast<const float2*>(r);
-    x[0] = v.x;
-    if constexpr (D > 1) x[1] = v.y;
+// Load SPT consecutive samples of one dimension starting at i0 as SPT/2 packed pairs.
+template <int P>
+__device__ __forceinline__ void load_sample_pairs(const float* __restrict__ p, int64_t i0, u64 (&s)[P]) {
+  if constexpr (P == 2) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + i0));
+    s[0] = pack2(v.x, v.y);
+    s[1] = pack2(v.z, v.w);
   } else {
-    float4 v = *reinterpret_cast<const float4*>(r);
-    x[0] = v.x;
-    x[1] = v.y;
-    x[2] = v.z;
-    if constexpr (D > 3) x[3] = v.w;
-    if constexpr (DP == 8) {
-      float4 w = *reinterpret_cast<const float4*>(r + 4);
-      x[4] = w.x;
-      if constexpr (D > 5) x[5] = w.y;
-      if constexpr (D > 6) x[6] = w.z;
-      if constexpr (D > 7) x[7] = w.w;
-    }
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p + i0));
+    s[0] = pack2(v.x, v.y);
   }
 }
 
-// Load SPT consecutive samples (SPT in {1,2,4}) of dimension d starting at i0.
-template <int SPT>
-__device__ __forceinline__ void load_samples(const float* __restrict__ p, int64_t i0, float (&s)[SPT]) {
-  if constexpr (SPT == 4) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p + i0));
-    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-  } else if constexpr (SPT == 2) {
-    float2 v = __ldg(reinterpret_cast<const float2*>(p + i0));
-    s[0] = v.x; s[1] = v.y;
-  } else {
-    s[0] = __ldg(p + i0);
-  }
-}
-
-template <int D, int MODE, int SPT>
+template <int D, int MODE, int P>
 __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a) {
-  constexpr int DP = StateRow<D>::DP;
+  constexpr int DP = Row2<D>::DP;
+  constexpr int SPT = 2 * P;
   constexpr int TILE = FP_THREADS * SPT;
-  __shared__ __align__(16) float sh[FP_CHUNK * DP];
+  constexpr int CHUNK = FootChunk<D>::ROWS;
+  __shared__ __align__(16) u64 sh[CHUNK * DP];
   const int tid = threadIdx.x;
-  const int nchunk = (int)((a.T + FP_CHUNK - 1) / FP_CHUNK);
+  const int nchunk = (int)((a.T + CHUNK - 1) / CHUNK);
 
   for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
     const float* st = a.states + g * a.seg_stride;
     double tsum = 0.0, tmax = -INFINITY;
 
     auto stage = [&](int c) {
-      const int64_t j0 = (int64_t)c * FP_CHUNK;
-      const int rows = (int)min((int64_t)FP_CHUNK, a.T - j0);
+      const int64_t j0 = (int64_t)c * CHUNK;
+      const int rows = (int)min((int64_t)CHUNK, a.T - j0);
       for (int e = tid; e < rows * DP; e += FP_THREADS) {
-        int j = e / DP, d = e - j * DP;
-        sh[e] = (d < D) ? st[(j0 + j) * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
+        const int j = e / DP, d = e - j * DP;
+        const float v = (d < D) ? st[(j0 + j) * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
+        sh[e] = pack2(v, v);
       }
       return rows;
     };
@@ -123,20 +100,25 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
 
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const int64_t i0 = tile * TILE + (int64_t)tid * SPT;
-      float s[D][SPT];
-      float acc[SPT];
+      u64 s2[D][P], acc[P];
+      float emin[SPT];
       const bool inb = i0 < a.ld;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         if (inb) {
-          load_samples<SPT>(a.packed + (int64_t)d * a.ld, i0, s[d]);
+          u64 t[P];
+          load_sample_pairs<P>(a.packed + (int64_t)d * a.ld, i0, t);
+#pragma unroll
+          for (int q = 0; q < P; ++q) s2[d][q] = t[q];
         } else {
 #pragma unroll
-          for (int q = 0; q < SPT; ++q) s[d][q] = 0.f;
+          for (int q = 0; q < P; ++q) s2[d][q] = pack2(0.f, 0.f);
         }
       }
 #pragma unroll
-      for (int q = 0; q < SPT; ++q) acc[q] = (MODE == 0) ? 0.f : -INFINITY;
+      for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) emin[q] = INFINITY;
 
       for (int c = 0; c < nchunk; ++c) {
         int rows = rows_single;
@@ -145,30 +127,16 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
           rows = stage(c);
           __syncthreads();
         }
-#pragma unroll 4
-        for (int j = 0; j < rows; ++j) {
-          float x[D];
-          load_state<D>(sh, j, x);
-#pragma unroll
-          for (int q = 0; q < SPT; ++q) {
-            float df = x[0] - s[0][q];
-            float e = -df * df;
-#pragma unroll
-            for (int d = 1; d < D; ++d) {
-              df = x[d] - s[d][q];
-              e = fmaf(-df, df, e);
-            }
-            if (MODE == 0) acc[q] += ex2_approx(e);
-            else acc[q] = fmaxf(acc[q], e);
-          }
-        }
+        pair_forward<D, P, MODE>(sh, rows, s2, acc, emin);
       }
 
       // epilogue: scale, add base, store, local totals
       float o[SPT];
 #pragma unroll
+      for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
+#pragma unroll
       for (int q = 0; q < SPT; ++q) {
-        float v = (MODE == 0) ? acc[q] : ex2_approx(acc[q]);
+        float v = (MODE == 0) ? o[q] : ex2_neg(emin[q]);  // T = 0: 2^-inf = 0
         v *= a.k.inv_nu;
         const int64_t i = i0 + q;
         if (a.add_in != nullptr && i < a.N) v += a.add_in[i];
@@ -202,7 +170,7 @@ static int launch_footprint_spt(const FootArgs& a0, cudaStream_t stream) {
   const int sms = sm_count();
   // choose samples-per-thread so that small workspaces still fill the chip
   int spt = 4;
-  if (a.N * a.G < (int64_t)sms * FP_THREADS * 4 * 2) spt = 1;
+  if (a.N * a.G < (int64_t)sms * FP_THREADS * 4 * 2) spt = 2;
   const int tile = FP_THREADS * spt;
   a.ntiles = (a.N + tile - 1) / tile;
   int64_t gx = a.ntiles < 1 ? 1 : a.ntiles;
@@ -212,7 +180,7 @@ static int launch_footprint_spt(const FootArgs& a0, cudaStream_t stream) {
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)gy);
   if (spt == 4)
-    footprint_kernel<D, MODE, 4><<<grid, FP_THREADS, 0, stream>>>(a);
+    footprint_kernel<D, MODE, 2><<<grid, FP_THREADS, 0, stream>>>(a);
   else
     footprint_kernel<D, MODE, 1><<<grid, FP_THREADS, 0, stream>>>(a);
   return check_launch("footprint_kernel");
@@ -234,6 +202,13 @@ static int launch_footprint_d(const FootArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------
 // gradient
 // ---------------------------------------------------------------------------
+template <int SPT>
+__device__ __forceinline__ void load_samples(const float* __restrict__ p, int64_t i0, float (&s)[SPT]) {
+  static_assert(SPT == 4, "gradient tiles read four samples per lane");
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p + i0));
+  s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+}
+
 constexpr int GR_WARPS = 8;
 constexpr int GR_THREADS = GR_WARPS * 32;
 constexpr int GR_TILE = GR_THREADS * 4;  // samples per tile (w staged in smem)

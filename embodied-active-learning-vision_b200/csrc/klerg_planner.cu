@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "klerg_common.cuh"
+#include "klerg_dyn.cuh"
 
 namespace klerg {
 
@@ -253,169 +254,10 @@ __global__ void __launch_bounds__(EW_THREADS) target_stage3_kernel(const float* 
   grid_reduce<1>(kinds, vals, ws_misc_partials(ws), ws_misc_counter(ws, 1), blockIdx.x, gridDim.x, p_stats);
 }
 
-// ---------------------------------------------------------------------------
-// dynamics + barrier (dynamics.py, barrier.py)
-// ---------------------------------------------------------------------------
-struct DynDev {
-  int kind, S, A;
-  float dt;
-  int rpw[3];
-  int has_map;
-  float rot_lo[3], rot_hi[3], ang_lo[3], ang_hi[3];
-};
-struct BarDev {
-  int n;
-  float lo[KLERG_MAX_S], hi[KLERG_MAX_S], w[KLERG_MAX_S], pw[KLERG_MAX_S];
-};
+// dynamics, barrier, rollout and adjoint device code lives in klerg_dyn.cuh
 
-__device__ __forceinline__ float powi_or_f(float d, float pw) {
-  if (pw == 4.f) { const float d2 = d * d; return d2 * d2; }
-  if (pw == 3.f) return d * d * d;
-  if (pw == 2.f) return d * d;
-  if (pw == 1.f) return d;
-  return powf(d, pw);
-}
-
-__device__ float barrier_value(const BarDev& b, const float* x) {
-  float acc = 0.f;
-  for (int i = 0; i < b.n; ++i) {
-    const float xi = x[i];
-    if (xi <= b.lo[i]) acc += b.w[i] * powi_or_f(xi - b.lo[i], b.pw[i]);
-    if (xi >= b.hi[i]) acc += b.w[i] * powi_or_f(xi - b.hi[i], b.pw[i]);
-  }
-  return acc;
-}
-
-__device__ void barrier_grad(const BarDev& b, const float* x, int S, float* g) {
-  for (int i = 0; i < S; ++i) {
-    float acc = 0.f;
-    if (i < b.n) {
-      const float xi = x[i];
-      if (xi <= b.lo[i]) acc += b.pw[i] * b.w[i] * powi_or_f(xi - b.lo[i], b.pw[i] - 1.f);
-      if (xi >= b.hi[i]) acc += b.pw[i] * b.w[i] * powi_or_f(xi - b.hi[i], b.pw[i] - 1.f);
-    }
-    g[i] = acc;
-  }
-}
-
-__device__ __forceinline__ float affine_map(float v, float ilo, float ihi, float olo, float ohi) {
-  return (v - ilo) / (ihi - ilo) * (ohi - olo) + olo;
-}
-
-__device__ void euler_xyz_to_matrix(const float* rot, float* R) {
-  // Rz(yaw) * Ry(pitch) * Rx(roll)   (rotations.py:70-96, order flipped to match scipy)
-  float sr, cr, sp, cp, sy, cy;
-  sincosf(rot[0], &sr, &cr);
-  sincosf(rot[1], &sp, &cp);
-  sincosf(rot[2], &sy, &cy);
-  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
-  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
-  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
-}
-
-__device__ __forceinline__ float py_mod(float x, float m) {
-  float r = fmodf(x, m);
-  if (r < 0.f) r += m;
-  return r;
-}
-
-// Rn = expm(hat(w) dt) * R via Rodrigues; new angles = wrap(euler_XYZ(Rn))   (dynamics.py:213-222)
-__device__ void advance_rotation(const float* R, const float* w, float dt, float* Rn, float* rot) {
-  const float kx = w[0] * dt, ky = w[1] * dt, kz = w[2] * dt;
-  const float th2 = kx * kx + ky * ky + kz * kz;
-  float A, B;  // sin(th)/th, (1-cos(th))/th^2
-  if (th2 < 1e-8f) {
-    A = 1.f - th2 / 6.f;
-    B = 0.5f - th2 / 24.f;
-  } else {
-    const float th = sqrtf(th2);
-    float s, c;
-    sincosf(th, &s, &c);
-    A = s / th;
-    B = (1.f - c) / th2;
-  }
-  // E = I + A K + B K^2,  K = hat(k)
-  float E[9];
-  E[0] = 1.f - B * (ky * ky + kz * kz); E[1] = -A * kz + B * kx * ky;         E[2] = A * ky + B * kx * kz;
-  E[3] = A * kz + B * kx * ky;          E[4] = 1.f - B * (kx * kx + kz * kz); E[5] = -A * kx + B * ky * kz;
-  E[6] = -A * ky + B * kx * kz;         E[7] = A * kx + B * ky * kz;          E[8] = 1.f - B * (kx * kx + ky * ky);
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = E[r * 3] * R[c] + E[r * 3 + 1] * R[3 + c] + E[r * 3 + 2] * R[6 + c];
-  const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
-  float r0 = atan2f(Rn[7], Rn[8]);
-  float r1 = asinf(-Rn[6]);
-  float r2 = atan2f(Rn[3], Rn[0]);
-  rot[0] = py_mod(r0, two_pi);
-  rot[1] = py_mod(r1 + pi, two_pi) - pi;
-  rot[2] = py_mod(r2 + pi, two_pi) - pi;
-}
-
-// d(pos rate)/d(vel) block: 0.8 I, with the rpw x rpw entries replaced by E(rot) R   (dynamics.py:189-211,283-289)
-__device__ void lin_block(const DynDev& d, const float* x, const float* R, float* P) {
-  const int a = d.A;
-  for (int i = 0; i < a * a; ++i) P[i] = 0.f;
-  for (int i = 0; i < a; ++i) P[i * a + i] = 0.8f;
-  if (d.kind != KLERG_DYN_ROLL) return;
-  float rot[3];
-  for (int k = 0; k < 3; ++k) {
-    rot[k] = x[d.rpw[k]];
-    if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
-  }
-  rot[1] += 1e-5f;
-  float s0, c0;
-  sincosf(rot[0], &s0, &c0);
-  const float t1 = tanf(rot[1]), c1 = cosf(rot[1]);
-  const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / c1, c0 / c1};
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c)
-      P[d.rpw[r] * a + d.rpw[c]] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
-}
-
-// One RK4 step (closed form: A is nilpotent of index 2, so RK4 == exact cubic).
-__device__ void dyn_step(const DynDev& d, const float* x, float* R, const float* u, float* xn) {
-  const int a = d.A;
-  const float dt = d.dt;
-  if (d.kind == KLERG_DYN_SINGLE) {
-    for (int i = 0; i < a; ++i) xn[i] = x[i] + dt * u[i];
-    return;
-  }
-  const float c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
-  for (int i = 0; i < a; ++i) {
-    xn[i] = x[i] + (c1 * x[a + i] + c2 * u[i]);
-    xn[a + i] = x[a + i] + dt * u[i];
-  }
-  if (d.kind == KLERG_DYN_SPEED) {
-    for (int i = 0; i < a; ++i) xn[2 * a + i] = fabsf(xn[a + i]);
-  } else if (d.kind == KLERG_DYN_ROLL) {
-    float w[3], Rn[9], rot[3];
-    for (int k = 0; k < 3; ++k) w[k] = x[a + d.rpw[k]];
-    advance_rotation(R, w, dt, Rn, rot);
-    for (int k = 0; k < 3; ++k) {
-      float v = rot[k];
-      if (d.has_map) v = affine_map(v, d.ang_lo[k], d.ang_hi[k], d.rot_lo[k], d.rot_hi[k]);
-      xn[d.rpw[k]] = v;
-    }
-    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
-  }
-}
-
-// One warp per candidate; lane i < A owns (pos_i, vel_i[, mag_i]).  Controls are staged in
-// shared memory so the serial recurrence only touches registers and smem; lane 0 carries the
-// rotation matrix of the ROLL model and hands the new angles to the owning lanes by shuffle.
+// One warp per candidate (rollout_warp); controls staged in shared memory.
 constexpr int RO_WARPS = 4;
-
-__device__ __forceinline__ float barrier_term(float x, float lo, float hi, float w, float pw) {
-  float acc = 0.f;
-  if (x <= lo) acc += w * powi_or_f(x - lo, pw);
-  if (x >= hi) acc += w * powi_or_f(x - hi, pw);
-  return acc;
-}
-__device__ __forceinline__ float barrier_dterm(float x, float lo, float hi, float w, float pw) {
-  float acc = 0.f;
-  if (x <= lo) acc += pw * w * powi_or_f(x - lo, pw - 1.f);
-  if (x >= hi) acc += pw * w * powi_or_f(x - hi, pw - 1.f);
-  return acc;
-}
 
 __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(DynDev d, BarDev bar, const float* __restrict__ x0,
                                                                  const float* __restrict__ R0,
@@ -429,114 +271,12 @@ __global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(DynDev d, BarDev
   const int64_t b = (int64_t)blockIdx.x * RO_WARPS + warp;
   if (b >= B) return;
   const int S = d.S, a = d.A;
-  const bool single = d.kind == KLERG_DYN_SINGLE, speed = d.kind == KLERG_DYN_SPEED, roll = d.kind == KLERG_DYN_ROLL;
   float* us = sh_u + (size_t)warp * H * a;
   for (int64_t e = lane; e < H * a; e += 32) us[e] = u[b * H * a + e];
   __syncwarp();
-
-  const bool act = lane < a;
-  float pos = act ? x0[lane] : 0.f;
-  float vel = (act && !single) ? x0[a + lane] : 0.f;
-  float mag = (act && speed) ? x0[2 * a + lane] : 0.f;
-  // barrier rows owned by this lane: position row `lane`, velocity row `a + lane`
-  float blo_p = 0.f, bhi_p = 0.f, bw_p = 0.f, bpw_p = 1.f, blo_v = 0.f, bhi_v = 0.f, bw_v = 0.f, bpw_v = 1.f;
-  bool has_p = false, has_v = false, has_m = false;
-  float blo_m = 0.f, bhi_m = 0.f, bw_m = 0.f, bpw_m = 1.f;
-  if (act && lane < bar.n) { has_p = true; blo_p = bar.lo[lane]; bhi_p = bar.hi[lane]; bw_p = bar.w[lane]; bpw_p = bar.pw[lane]; }
-  if (act && !single && a + lane < bar.n) { has_v = true; blo_v = bar.lo[a + lane]; bhi_v = bar.hi[a + lane]; bw_v = bar.w[a + lane]; bpw_v = bar.pw[a + lane]; }
-  if (act && speed && 2 * a + lane < bar.n) { has_m = true; blo_m = bar.lo[2 * a + lane]; bhi_m = bar.hi[2 * a + lane]; bw_m = bar.w[2 * a + lane]; bpw_m = bar.pw[2 * a + lane]; }
-
-  float R[9];
-  int my_rot = -1;  // which of roll/pitch/yaw this lane's position is (ROLL)
-  if (roll) {
-    for (int k = 0; k < 3; ++k)
-      if (lane == d.rpw[k]) my_rot = k;
-    float rot[3];
-    for (int k = 0; k < 3; ++k) {
-      rot[k] = __shfl_sync(0xffffffffu, pos, d.rpw[k]);
-      if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
-    }
-    if (R0) {
-      for (int i = 0; i < 9; ++i) R[i] = R0[i];
-    } else {
-      euler_xyz_to_matrix(rot, R);
-    }
-  }
-  float* tr = traj + b * (H + 1) * S;
-  const float dt = d.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
-  float bsum = 0.f;
-  for (int64_t t = 0; t <= H; ++t) {
-    if (act) {
-      tr[t * S + lane] = pos;
-      if (!single) tr[t * S + a + lane] = vel;
-      if (speed) tr[t * S + 2 * a + lane] = mag;
-    }
-    if (t > 0 && act) {
-      if (has_p) bsum += barrier_term(pos, blo_p, bhi_p, bw_p, bpw_p);
-      if (has_v) bsum += barrier_term(vel, blo_v, bhi_v, bw_v, bpw_v);
-      if (has_m) bsum += barrier_term(mag, blo_m, bhi_m, bw_m, bpw_m);
-    }
-    if (t == H) break;
-    if (dbarr && act) {
-      float* db = dbarr + (b * H + t) * S;
-      db[lane] = has_p ? barrier_dterm(pos, blo_p, bhi_p, bw_p, bpw_p) : 0.f;
-      if (!single) db[a + lane] = has_v ? barrier_dterm(vel, blo_v, bhi_v, bw_v, bpw_v) : 0.f;
-      if (speed) db[2 * a + lane] = has_m ? barrier_dterm(mag, blo_m, bhi_m, bw_m, bpw_m) : 0.f;
-    }
-    float w3[3] = {0.f, 0.f, 0.f}, rot3[3] = {0.f, 0.f, 0.f};
-    if (roll) {
-      for (int k = 0; k < 3; ++k) {
-        w3[k] = __shfl_sync(0xffffffffu, vel, d.rpw[k]);
-        rot3[k] = __shfl_sync(0xffffffffu, pos, d.rpw[k]);
-      }
-    }
-    if (P) {
-      float* Pt = P + (b * H + t) * a * a;
-      for (int e = lane; e < a * a; e += 32) Pt[e] = (e / a == e % a) ? 0.8f : 0.f;
-      __syncwarp();
-      if (roll && lane == 0) {
-        float rot[3];
-        for (int k = 0; k < 3; ++k)
-          rot[k] = d.has_map ? affine_map(rot3[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]) : rot3[k];
-        rot[1] += 1e-5f;
-        float s0, c0;
-        sincosf(rot[0], &s0, &c0);
-        const float t1 = tanf(rot[1]), cc1 = cosf(rot[1]);
-        const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / cc1, c0 / cc1};
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c)
-            Pt[d.rpw[r] * a + d.rpw[c]] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
-      }
-    }
-    const float ut = act ? us[t * a + lane] : 0.f;
-    if (single) {
-      pos = pos + dt * ut;
-    } else {
-      pos = pos + (c1 * vel + c2 * ut);
-      vel = vel + dt * ut;
-      if (speed) mag = fabsf(vel);
-    }
-    if (roll) {
-      float Rn[9], nr[3];
-      advance_rotation(R, w3, dt, Rn, nr);  // every lane computes it redundantly (no divergence)
-#pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = Rn[i];
-      if (my_rot >= 0) {
-        float v = my_rot == 0 ? nr[0] : (my_rot == 1 ? nr[1] : nr[2]);
-        if (d.has_map) v = affine_map(v, d.ang_lo[my_rot], d.ang_hi[my_rot], d.rot_lo[my_rot], d.rot_hi[my_rot]);
-        pos = v;
-      }
-    }
-  }
-  bsum = warp_sum_f(bsum);
+  const float bsum = rollout_warp(d, bar, x0, R0, us, (int)H, traj + b * (H + 1) * S, dbarr ? dbarr + b * H * S : nullptr,
+                                  P ? P + b * H * a * a : nullptr, R_out ? R_out + b * 9 : nullptr);
   if (lane == 0 && barrier_sum) barrier_sum[b] = bsum;
-  if (lane == 0 && R_out) {
-    if (!roll) {
-      for (int i = 0; i < 9; ++i) R_out[b * 9 + i] = (i % 4 == 0) ? 1.f : 0.f;
-    } else {
-      for (int i = 0; i < 9; ++i) R_out[b * 9 + i] = R[i];
-    }
-  }
 }
 
 __global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int64_t T, int S, float* __restrict__ value,
@@ -553,7 +293,7 @@ __global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int
 }
 
 // ---------------------------------------------------------------------------
-// adjoint sweep (klerg.py:433-450, 590-593), default policy (dmudx = 0)
+// adjoint sweep (klerg.py:433-450, 590-593): stage inputs in shared memory, then adjoint_warp
 // ---------------------------------------------------------------------------
 struct AdjArgs {
   DynDev d;
@@ -565,9 +305,7 @@ struct AdjArgs {
   const float* P;
   const float* traj;
   const float* u;
-  float rinv[KLERG_MAX_A];
-  float alpha;
-  float clo[KLERG_MAX_A], chi[KLERG_MAX_A];
+  AdjParams ap;
   float* dgdx;
   float* du;
   float* djdlam;
@@ -578,7 +316,7 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
   extern __shared__ float sh[];  // g[H][S] | P[H][A*A] (optional) | sgn[H][A] (SPEED) | u[H][A]
   const int S = a.d.S, A = a.d.A, D = a.k.D;
   const int64_t H = a.H;
-  const bool single = a.d.kind == KLERG_DYN_SINGLE, speed = a.d.kind == KLERG_DYN_SPEED;
+  const bool speed = a.d.kind == KLERG_DYN_SPEED;
   float* sg = sh;
   float* sP = sg + H * S;
   float* ssgn = sP + (a.P ? H * A * A : 0);
@@ -605,56 +343,7 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
   }
   __syncthreads();
   if (threadIdx.x >= 32) return;
-  // phase 2 (one warp): lane i < A carries component i of rho_p, rho_v (and rho_m for SPEED)
-  const int i = threadIdx.x;
-  const bool act = i < A;
-  const float h = -a.d.dt;
-  const float rinv = act ? a.rinv[i] : 0.f, clo = act ? a.clo[i] : 0.f, chi = act ? a.chi[i] : 0.f;
-  float rp = 0.f, rv = 0.f, rm = 0.f;
-  for (int64_t t = H - 1; t >= 0; --t) {
-    float gp = 0.f, gv = 0.f, gm = 0.f;
-    if (act) {
-      gp = sg[t * S + i];
-      if (!single) gv = sg[t * S + A + i];
-      if (speed) gm = sg[t * S + 2 * A + i];
-    }
-    float btr;  // (B^T rho)_i
-    if (single) {
-      rp = rp + h * gp;
-      btr = rp;
-    } else {
-      float ptr_ = 0.f, ptg = 0.f;  // (P^T rho_p)_i, (P^T g_p)_i
-      if (a.P) {
-        const float* Pt = sP + t * A * A;
-        for (int kk = 0; kk < A; ++kk) {
-          const float rk = __shfl_sync(0xffffffffu, rp, kk);
-          const float gk = __shfl_sync(0xffffffffu, gp, kk);
-          const float pk = act ? Pt[kk * A + i] : 0.f;
-          ptr_ = fmaf(pk, rk, ptr_);
-          ptg = fmaf(pk, gk, ptg);
-        }
-      } else {
-        ptr_ = 0.8f * rp;
-        ptg = 0.8f * gp;
-      }
-      const float rv_n = rv + h * (gv - ptr_) - 0.5f * h * h * ptg;
-      rp = rp + h * gp;
-      rv = rv_n;
-      btr = rv;
-      if (speed) {
-        rm = rm + h * gm;
-        btr = rv + (act ? ssgn[t * A + i] : 0.f) * rm;
-      }
-    }
-    const float dui = act ? -rinv * btr : 0.f;
-    const float dj = warp_sum_f(act ? btr * dui : 0.f);
-    if (act) {
-      a.du[t * A + i] = dui;
-      const float us = su[t * A + i] + a.alpha * dui;
-      a.u_star[t * A + i] = fminf(fmaxf(us, clo), chi);
-    }
-    if (i == 0) a.djdlam[t] = dj;
-  }
+  adjoint_warp(a.d, a.ap, (int)H, sg, a.P ? sP : nullptr, ssgn, su, a.du, a.djdlam, a.u_star);
 }
 
 struct CombineArgs {
@@ -689,7 +378,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, int S, const
   }
 }
 
-static bool make_dyn(const klerg_dyn_spec* s, DynDev& d) {
+bool make_dyn(const klerg_dyn_spec* s, DynDev& d) {
   if (!s) { set_error("dyn spec is null"); return false; }
   if (s->kind < 0 || s->kind > 3 || s->S < 1 || s->S > KLERG_MAX_S || s->A < 1 || s->A > KLERG_MAX_A) {
     set_error("dyn spec out of range (kind=%d S=%d A=%d)", s->kind, s->S, s->A);
@@ -707,7 +396,7 @@ static bool make_dyn(const klerg_dyn_spec* s, DynDev& d) {
   return true;
 }
 
-static bool make_bar(const klerg_barrier_spec* s, BarDev& b) {
+bool make_bar(const klerg_barrier_spec* s, BarDev& b) {
   memset(&b, 0, sizeof(b));
   if (!s) return true;  // NoBarrier
   if (s->n < 0 || s->n > KLERG_MAX_S) { set_error("barrier spec: n out of range"); return false; }
@@ -909,8 +598,8 @@ extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec*
   if (!make_dyn(dyn, a.d) || !make_kernel_dev(k, a.k)) return -1;
   if (H < 1 || H > KLERG_MAX_H) { set_error("adjoint: H out of range"); return -1; }
   a.H = H; a.grad_part = grad_part; a.world = world; a.dbarr = dbarr; a.P = P; a.traj = traj; a.u = u;
-  a.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
-  for (int i = 0; i < a.d.A; ++i) { a.rinv[i] = Rinv_diag[i]; a.clo[i] = ctrl_lo[i]; a.chi[i] = ctrl_hi[i]; }
+  a.ap.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
+  for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
   const bool speed = a.d.kind == KLERG_DYN_SPEED;
   const size_t smem = sizeof(float) * (size_t)H * (a.d.S + (P ? a.d.A * a.d.A : 0) + (speed ? a.d.A : 0) + a.d.A);
   if (smem > 48 * 1024) {

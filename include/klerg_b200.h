@@ -205,6 +205,49 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
                   const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
                   float* u_star, void* stream);
 
+/* ---- fused evals: one cooperative launch per eval ------------------------- */
+
+/* Sample-sharding peers (samples of one workspace split over the GPUs of a
+ * box).  mailbox[r] is rank r's exchange buffer
+ * (klerg_mailbox_bytes() bytes, zero-filled once) mapped into THIS process -
+ * peer-to-peer device memory reachable over NVLink; mailbox[rank] is the local
+ * one.  NULL / world <= 1 = single GPU.  All ranks must issue the same
+ * sequence of fused evals on a mailbox set. */
+typedef struct klerg_peers {
+  int32_t world, rank;
+  void* mailbox[8];
+} klerg_peers;
+size_t klerg_mailbox_bytes(void);
+
+/* One planner iteration up to the control update (klerg.py:505-523):
+ *   forward(): rollout of u[H][A] from x0 (pre-step states, linearisation, dbarr)
+ *   q = renormalize(q_base + footprint(traj))          (sum/max over ALL ranks)
+ *   backward(): dgdx_t = kldiv_grad_vec(x_t, samples, p/q), adjoint sweep
+ * -> dgdx[H][S], du[H][A], djdlam[H], u_star = clamp(u + alpha du)[H][A].
+ * Also: traj[H+1][S] (may be NULL), totals[2] = {sum, max} of q_base + q_iter,
+ * kl_out[2] = {sum_i p_i (log p_i - log c_i), sum_i c_i}, cost[1] = KL of that
+ * footprint + barrier sum (each may be NULL).  v_scratch: ld floats (receives
+ * q_base + q_iter of this rank's samples).  Rinv_diag / ctrl_lo / ctrl_hi are
+ * HOST arrays of A floats.  Replaces klerg_rollout + klerg_footprint +
+ * klerg_kl_gradient_fused + klerg_adjoint with a single launch. */
+int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                        const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
+                        const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
+                        const double* p_stats, float floor, const float* Rinv_diag, float alpha,
+                        const float* ctrl_lo, const float* ctrl_hi, float* v_scratch, float* traj,
+                        double* totals, float* cost, float* dgdx, float* du, float* djdlam, float* u_star,
+                        double* kl_out, void* workspace, void* stream);
+
+/* Robot.get_cost (klerg.py:686-710) for G <= 8 candidate control sequences
+ * u[G][H][A] in one launch (the line-search windows of klerg.py:712-751):
+ * cost[g] = KL(p || renormalize(q_base + footprint(post-step states))) + barrier.
+ * v_scratch: G*ld floats; traj[G][H+1][S] and totals[G][2] may be NULL. */
+int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                     const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t G,
+                     int64_t H, const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
+                     const double* p_stats, float floor, float* v_scratch, float* traj, double* totals,
+                     float* cost, void* workspace, void* stream);
+
 /* ---- a19: memory-buffer selection (memory_buffer.py:52-63) ---------------- */
 
 /* out[m] = table[idx[m]] for m < M; idx are the host-drawn torch.randperm
