@@ -85,8 +85,8 @@ __device__ __forceinline__ float py_mod(float x, float m) {
   return r;
 }
 
-// Rn = expm(hat(w) dt) * R via Rodrigues; new angles = wrap(euler_XYZ(Rn))   (dynamics.py:213-222)
-__device__ inline void advance_rotation(const float* R, const float* w, float dt, float* Rn, float* rot) {
+// E = expm(hat(w) dt) via Rodrigues (= torch.matrix_exp of the skew matrix, dynamics.py:213-217)
+__device__ inline void rodrigues(const float* w, float dt, float* E) {
   const float kx = w[0] * dt, ky = w[1] * dt, kz = w[2] * dt;
   const float th2 = kx * kx + ky * ky + kz * kz;
   float A, B;  // sin(th)/th, (1-cos(th))/th^2
@@ -101,146 +101,209 @@ __device__ inline void advance_rotation(const float* R, const float* w, float dt
     B = (1.f - c) / th2;
   }
   // E = I + A K + B K^2,  K = hat(k)
-  float E[9];
   E[0] = 1.f - B * (ky * ky + kz * kz); E[1] = -A * kz + B * kx * ky;         E[2] = A * ky + B * kx * kz;
   E[3] = A * kz + B * kx * ky;          E[4] = 1.f - B * (kx * kx + kz * kz); E[5] = -A * kx + B * ky * kz;
   E[6] = -A * ky + B * kx * kz;         E[7] = A * kx + B * ky * kz;          E[8] = 1.f - B * (kx * kx + ky * ky);
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = E[r * 3] * R[c] + E[r * 3 + 1] * R[3 + c] + E[r * 3 + 2] * R[6 + c];
+}
+
+// wrap(euler_XYZ(R)): roll in [0, 2pi), pitch / yaw in [-pi, pi)   (rotations.py:142-181, dynamics.py:219-222)
+__device__ inline void wrapped_euler_xyz(const float* Rn, float* rot) {
   const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
-  float r0 = atan2f(Rn[7], Rn[8]);
-  float r1 = asinf(-Rn[6]);
-  float r2 = atan2f(Rn[3], Rn[0]);
+  const float r0 = atan2f(Rn[7], Rn[8]);
+  const float r1 = asinf(-Rn[6]);
+  const float r2 = atan2f(Rn[3], Rn[0]);
   rot[0] = py_mod(r0, two_pi);
   rot[1] = py_mod(r1 + pi, two_pi) - pi;
   rot[2] = py_mod(r2 + pi, two_pi) - pi;
 }
 
+__device__ __forceinline__ void matmul3(const float* E, const float* R, float* Rn) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = E[r * 3] * R[c] + E[r * 3 + 1] * R[3 + c] + E[r * 3 + 2] * R[6 + c];
+}
+
+// floats of scratch rollout_block needs at s_rot for the ROLL model: per candidate E_t [H][9], R_t [H+1][9]
+__host__ __device__ inline int rollout_rot_floats(int G, int H) { return G * (2 * H + 1) * 9; }
+
 // ---------------------------------------------------------------------------
-// rollout: ONE WARP rolls one control sequence us[H][A] out from x0 with RK4 (closed form:
-// A is nilpotent of index 2, so RK4 == the exact cubic; dynamics.py:7-13,58-65).
-// Lane i < A owns (pos_i, vel_i[, mag_i]); every lane carries the ROLL rotation matrix.
-//   traj[t]  (t = 0..H)   state before step t / after step t-1, [H+1][S]    (may be NULL)
-//   dbarr[t] (t < H)      dbarr(traj[t]), [H][S]                            (may be NULL)
-//   P[t]     (t < H)      d(pos rate)/d(vel) block of A_t, [H][A*A]         (may be NULL)
-// Pointers may be global or shared.  Returns sum_t barr(traj[t+1]) (klerg.py:708) in every lane.
+// rollout of G control sequences by a whole CTA (every thread must call it).
+//
+// The RK4 step of the integrator models is exact and closed-form (A is nilpotent of index 2,
+// dynamics.py:7-13,58-65), so only three short recurrences are serial: velocity / position
+// running sums (one lane per candidate and control) and, for the ROLL model, R_{t+1} = E_t R_t
+// (one lane per candidate).  Everything else - Rodrigues matrices E_t, Euler angles,
+// linearisation blocks, wall barrier and its derivative - is evaluated for all time steps in
+// parallel.
+//
+//   s_u     [G][H][A]    controls (shared)
+//   s_traj  [G][H+1][S]  traj[t] = state before step t (Robot.forward) = state after step t-1 (get_cost)
+//   s_dbarr [G][H][S]    dbarr(traj[t]), t < H            (may be NULL)
+//   s_P     [G][H][A*A]  d(pos rate)/d(vel) block of A_t  (ROLL only; may be NULL)
+//   s_rot   scratch of rollout_rot_floats(G, H) floats    (ROLL only)
+//   s_red   scratch of 32 floats
+//   s_bsum  [G]          sum_t barr(traj[t+1])  (klerg.py:708)
+//   R_out   [G][9]       rotation after the last step (global or shared, may be NULL)
+// Ends with a __syncthreads().
 // ---------------------------------------------------------------------------
-__device__ inline float rollout_warp(const DynDev& d, const BarDev& bar, const float* x0, const float* R0,
-                                     const float* us, int H, float* traj, float* dbarr, float* P, float* R_out) {
-  const int lane = threadIdx.x & 31;
+__device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const float* x0, const float* R0,
+                                     const float* s_u, int G, int H, float* s_traj, float* s_dbarr, float* s_P,
+                                     float* s_rot, float* s_red, float* s_bsum, float* R_out) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int S = d.S, a = d.A;
   const bool single = d.kind == KLERG_DYN_SINGLE, speed = d.kind == KLERG_DYN_SPEED, roll = d.kind == KLERG_DYN_ROLL;
-  const bool act = lane < a;
-  float pos = act ? x0[lane] : 0.f;
-  float vel = (act && !single) ? x0[a + lane] : 0.f;
-  float mag = (act && speed) ? x0[2 * a + lane] : 0.f;
-  // barrier rows owned by this lane: position row `lane`, velocity row `a + lane`, magnitude row `2a + lane`
-  float blo_p = 0.f, bhi_p = 0.f, bw_p = 0.f, bpw_p = 1.f, blo_v = 0.f, bhi_v = 0.f, bw_v = 0.f, bpw_v = 1.f;
-  float blo_m = 0.f, bhi_m = 0.f, bw_m = 0.f, bpw_m = 1.f;
-  bool has_p = false, has_v = false, has_m = false;
-  if (act && lane < bar.n) { has_p = true; blo_p = bar.lo[lane]; bhi_p = bar.hi[lane]; bw_p = bar.w[lane]; bpw_p = bar.pw[lane]; }
-  if (act && !single && a + lane < bar.n) { has_v = true; blo_v = bar.lo[a + lane]; bhi_v = bar.hi[a + lane]; bw_v = bar.w[a + lane]; bpw_v = bar.pw[a + lane]; }
-  if (act && speed && 2 * a + lane < bar.n) { has_m = true; blo_m = bar.lo[2 * a + lane]; bhi_m = bar.hi[2 * a + lane]; bw_m = bar.w[2 * a + lane]; bpw_m = bar.pw[2 * a + lane]; }
-
-  float R[9];
-  int my_rot = -1;  // which of roll/pitch/yaw this lane's position is (ROLL)
-  if (roll) {
-    for (int k = 0; k < 3; ++k)
-      if (lane == d.rpw[k]) my_rot = k;
-    float rot[3];
-    for (int k = 0; k < 3; ++k) {
-      rot[k] = __shfl_sync(0xffffffffu, pos, d.rpw[k]);
-      if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
-    }
-    if (R0) {
-      for (int i = 0; i < 9; ++i) R[i] = R0[i];
-    } else {
-      euler_xyz_to_matrix(rot, R);
-    }
-  }
   const float dt = d.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
-  float bsum = 0.f;
-  for (int t = 0; t <= H; ++t) {
-    if (act && traj) {
-      traj[t * S + lane] = pos;
-      if (!single) traj[t * S + a + lane] = vel;
-      if (speed) traj[t * S + 2 * a + lane] = mag;
-    }
-    if (t > 0 && act) {
-      if (has_p) bsum += barrier_term(pos, blo_p, bhi_p, bw_p, bpw_p);
-      if (has_v) bsum += barrier_term(vel, blo_v, bhi_v, bw_v, bpw_v);
-      if (has_m) bsum += barrier_term(mag, blo_m, bhi_m, bw_m, bpw_m);
-    }
-    if (t == H) break;
-    if (dbarr && act) {
-      float* db = dbarr + t * S;
-      db[lane] = has_p ? barrier_dterm(pos, blo_p, bhi_p, bw_p, bpw_p) : 0.f;
-      if (!single) db[a + lane] = has_v ? barrier_dterm(vel, blo_v, bhi_v, bw_v, bpw_v) : 0.f;
-      if (speed) db[2 * a + lane] = has_m ? barrier_dterm(mag, blo_m, bhi_m, bw_m, bpw_m) : 0.f;
-    }
-    float w3[3] = {0.f, 0.f, 0.f}, rot3[3] = {0.f, 0.f, 0.f};
-    if (roll) {
-      for (int k = 0; k < 3; ++k) {
-        w3[k] = __shfl_sync(0xffffffffu, vel, d.rpw[k]);
-        rot3[k] = __shfl_sync(0xffffffffu, pos, d.rpw[k]);
+  // (A) running sums, one lane per (candidate, control)
+  for (int l = tid; l < G * a; l += nthr) {
+    const int g = l / a, i = l - g * a;
+    const float* us = s_u + (size_t)g * H * a;
+    float* tr = s_traj + (size_t)g * (H + 1) * S;
+    float pos = x0[i];
+    float vel = single ? 0.f : x0[a + i];
+    float mag = speed ? x0[2 * a + i] : 0.f;
+#pragma unroll 4
+    for (int t = 0; t <= H; ++t) {
+      tr[t * S + i] = pos;
+      if (!single) tr[t * S + a + i] = vel;
+      if (speed) tr[t * S + 2 * a + i] = mag;
+      if (t == H) break;
+      const float ut = us[t * a + i];
+      if (single) {
+        pos = pos + dt * ut;
+      } else {
+        pos = pos + (c1 * vel + c2 * ut);
+        vel = vel + dt * ut;
+        if (speed) mag = fabsf(vel);
       }
     }
-    if (P) {
-      // 0.8 I, with the rpw x rpw entries replaced by E(rot) R   (dynamics.py:189-211,283-289)
-      float* Pt = P + t * a * a;
-      for (int e = lane; e < a * a; e += 32) Pt[e] = (e / a == e % a) ? 0.8f : 0.f;
-      __syncwarp();
-      if (roll && lane == 0) {
+  }
+  __syncthreads();
+  if (roll) {
+    float* s_E = s_rot;               // [G][H][9]
+    float* s_R = s_rot + G * H * 9;   // [G][H+1][9]
+    // (B) E_t from the pre-step angular velocity, all (g, t) in parallel; R_0
+    for (int e = tid; e < G * H; e += nthr) {
+      const int g = e / H, t = e - g * H;
+      float w3[3], E[9];
+      for (int k = 0; k < 3; ++k) w3[k] = s_traj[((size_t)g * (H + 1) + t) * S + a + d.rpw[k]];
+      rodrigues(w3, dt, E);
+      for (int i = 0; i < 9; ++i) s_E[e * 9 + i] = E[i];
+    }
+    if (tid == nthr - 1) {
+      float R[9];
+      if (R0) {
+        for (int i = 0; i < 9; ++i) R[i] = R0[i];
+      } else {
         float rot[3];
-        for (int k = 0; k < 3; ++k)
-          rot[k] = d.has_map ? affine_map(rot3[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]) : rot3[k];
+        for (int k = 0; k < 3; ++k) {
+          rot[k] = x0[d.rpw[k]];
+          if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
+        }
+        euler_xyz_to_matrix(rot, R);
+      }
+      for (int g = 0; g < G; ++g)
+        for (int i = 0; i < 9; ++i) s_R[(size_t)g * (H + 1) * 9 + i] = R[i];
+    }
+    __syncthreads();
+    // (C) serial chain of 3x3 products, one lane per candidate
+    if (tid < G) {
+      float* Rg = s_R + (size_t)tid * (H + 1) * 9;
+      const float* Eg = s_E + (size_t)tid * H * 9;
+      float R[9];
+      for (int i = 0; i < 9; ++i) R[i] = Rg[i];
+      for (int t = 0; t < H; ++t) {
+        float E[9], Rn[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) E[i] = Eg[t * 9 + i];
+        matmul3(E, R, Rn);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          R[i] = Rn[i];
+          Rg[(t + 1) * 9 + i] = Rn[i];
+        }
+      }
+    }
+    __syncthreads();
+    // (D1) angles of R_t overwrite the integrated angle positions (dynamics.py:291-301)
+    for (int e = tid; e < G * H; e += nthr) {
+      const int g = e / H, t = 1 + (e - g * H);
+      float rot[3];
+      wrapped_euler_xyz(s_R + ((size_t)g * (H + 1) + t) * 9, rot);
+      for (int k = 0; k < 3; ++k) {
+        float v = rot[k];
+        if (d.has_map) v = affine_map(v, d.ang_lo[k], d.ang_hi[k], d.rot_lo[k], d.rot_hi[k]);
+        s_traj[((size_t)g * (H + 1) + t) * S + d.rpw[k]] = v;
+      }
+    }
+    if (R_out)
+      for (int e = tid; e < G * 9; e += nthr) R_out[e] = s_R[((size_t)(e / 9) * (H + 1) + H) * 9 + e % 9];
+    __syncthreads();
+    // (D2) linearisation block: 0.8 I with the rpw x rpw entries replaced by E(rot) R (dynamics.py:189-211,283-289)
+    if (s_P) {
+      for (int e = tid; e < G * H * a * a; e += nthr) {
+        const int r = (e % (a * a)) / a, c = e % a;
+        s_P[e] = (r == c) ? 0.8f : 0.f;
+      }
+      __syncthreads();
+      for (int e = tid; e < G * H; e += nthr) {
+        const int g = e / H, t = e - g * H;
+        float rot[3];
+        for (int k = 0; k < 3; ++k) {
+          rot[k] = s_traj[((size_t)g * (H + 1) + t) * S + d.rpw[k]];
+          if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
+        }
         rot[1] += 1e-5f;
         float s0, c0;
         sincosf(rot[0], &s0, &c0);
         const float t1 = tanf(rot[1]), cc1 = cosf(rot[1]);
         const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / cc1, c0 / cc1};
+        const float* R = s_R + ((size_t)g * (H + 1) + t) * 9;
+        float* Pt = s_P + (size_t)e * a * a;
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c)
             Pt[d.rpw[r] * a + d.rpw[c]] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
       }
     }
-    const float ut = act ? us[t * a + lane] : 0.f;
-    if (single) {
-      pos = pos + dt * ut;
-    } else {
-      pos = pos + (c1 * vel + c2 * ut);
-      vel = vel + dt * ut;
-      if (speed) mag = fabsf(vel);
-    }
-    if (roll) {
-      float Rn[9], nr[3];
-      advance_rotation(R, w3, dt, Rn, nr);  // every lane computes it redundantly (no divergence)
-#pragma unroll
-      for (int i = 0; i < 9; ++i) R[i] = Rn[i];
-      if (my_rot >= 0) {
-        float v = my_rot == 0 ? nr[0] : (my_rot == 1 ? nr[1] : nr[2]);
-        if (d.has_map) v = affine_map(v, d.ang_lo[my_rot], d.ang_hi[my_rot], d.rot_lo[my_rot], d.rot_hi[my_rot]);
-        pos = v;
+  } else if (R_out) {
+    for (int e = tid; e < G * 9; e += nthr) R_out[e] = ((e % 9) % 4 == 0) ? 1.f : 0.f;
+  }
+  // (E) wall barrier of the post-step states and its derivative at the pre-step states
+  for (int g = 0; g < G; ++g) {
+    const float* tr = s_traj + (size_t)g * (H + 1) * S;
+    float bsum = 0.f;
+    for (int e = tid; e < H * S; e += nthr) {
+      const int t = e / S, i = e - t * S;
+      float db = 0.f;
+      if (i < bar.n) {
+        const float lo = bar.lo[i], hi = bar.hi[i], w = bar.w[i], pw = bar.pw[i];
+        bsum += barrier_term(tr[(t + 1) * S + i], lo, hi, w, pw);
+        if (s_dbarr) db = barrier_dterm(tr[e], lo, hi, w, pw);
       }
+      if (s_dbarr) s_dbarr[(size_t)g * H * S + e] = db;
+    }
+    bsum = warp_sum_f(bsum);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = bsum;
+    __syncthreads();
+    if (tid == 0) {
+      float v = 0.f;
+      for (int w = 0; w < (nthr + 31) / 32; ++w) v += s_red[w];
+      s_bsum[g] = v;
     }
   }
-  bsum = warp_sum_f(bsum);
-  if (lane == 0 && R_out) {
-    if (!roll) {
-      for (int i = 0; i < 9; ++i) R_out[i] = (i % 4 == 0) ? 1.f : 0.f;
-    } else {
-      for (int i = 0; i < 9; ++i) R_out[i] = R[i];
-    }
-  }
-  return bsum;
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
-// adjoint sweep (klerg.py:433-450, 590-593), default policy (dmudx = 0): ONE WARP.
-// rho_H = 0; for t = H-1..0 one RK4 step of rho' = g_t - A_t^T rho with step -dt, where
-// g = dgdx - dbarr is staged in shared memory; du_t = -Rinv B^T rho, djdlam_t = rho B du_t,
-// u_star = clamp(u + alpha du).  Lane i < A carries component i of rho_p, rho_v (rho_m for SPEED).
-//   sg [H][S] (smem), sP [H][A*A] or NULL (0.8 I), ssgn [H][A] sign(vel) (SPEED), su [H][A].
+// adjoint sweep (klerg.py:433-450, 590-593), default policy (dmudx = 0), by a whole CTA.
+// rho_H = 0; for t = H-1..0 one RK4 step of rho' = g_t - A_t^T rho with step -dt, g = dgdx - dbarr:
+//   rho_p <- rho_p + h g_p,   rho_v <- rho_v + h (g_v - P^T rho_p) - h^2/2 P^T g_p        (h = -dt)
+// rho_p does not depend on rho_v, so the sweep is three running sums (one lane per control) around
+// a time-parallel P^T product; du_t = -Rinv B^T rho, djdlam_t = rho B du_t, u* = clamp(u + alpha du)
+// are evaluated for all t in parallel.
+//   sg [H][S] (shared), sP [H][A*A] or NULL (0.8 I), s_traj for sign(vel) (SPEED), su [H][A],
+//   s_scr scratch of adjoint_scratch_floats(H, A) floats.   Ends with a __syncthreads().
 // ---------------------------------------------------------------------------
 struct AdjParams {
   float rinv[KLERG_MAX_A];
@@ -248,59 +311,78 @@ struct AdjParams {
   float alpha;
 };
 
-__device__ inline void adjoint_warp(const DynDev& d, const AdjParams& ap, int H, const float* sg, const float* sP,
-                                    const float* ssgn, const float* su, float* du, float* djdlam, float* u_star) {
+__host__ __device__ inline int adjoint_scratch_floats(int H, int A) { return 5 * H * A; }
+
+__device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H, const float* sg, const float* sP,
+                                     const float* s_traj, const float* su, float* s_scr, float* du, float* djdlam,
+                                     float* u_star) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
   const int S = d.S, A = d.A;
   const bool single = d.kind == KLERG_DYN_SINGLE, speed = d.kind == KLERG_DYN_SPEED;
-  const int i = threadIdx.x & 31;
-  const bool act = i < A;
   const float h = -d.dt;
-  const float rinv = act ? ap.rinv[i] : 0.f, clo = act ? ap.clo[i] : 0.f, chi = act ? ap.chi[i] : 0.f;
-  float rp = 0.f, rv = 0.f, rm = 0.f;
-  for (int t = H - 1; t >= 0; --t) {
-    float gp = 0.f, gv = 0.f, gm = 0.f;
-    if (act) {
-      gp = sg[t * S + i];
-      if (!single) gv = sg[t * S + A + i];
-      if (speed) gm = sg[t * S + 2 * A + i];
+  float* s_rp = s_scr;              // rho_p before the update of step t
+  float* s_rm = s_rp + H * A;       // rho_m after the update (SPEED)
+  float* s_a = s_rm + H * A;        // g_v - P^T rho_p
+  float* s_b = s_a + H * A;         // P^T g_p
+  float* s_btr = s_b + H * A;       // B^T rho after step t
+  if (tid < A) {
+    float rp = 0.f, rm = 0.f;
+#pragma unroll 4
+    for (int t = H - 1; t >= 0; --t) {
+      s_rp[t * A + tid] = rp;
+      rp = rp + h * sg[t * S + tid];
+      if (single) s_btr[t * A + tid] = rp;
+      if (speed) {
+        rm = rm + h * sg[t * S + 2 * A + tid];
+        s_rm[t * A + tid] = rm;
+      }
     }
-    float btr;  // (B^T rho)_i
-    if (single) {
-      rp = rp + h * gp;
-      btr = rp;
-    } else {
-      float ptr_ = 0.f, ptg = 0.f;  // (P^T rho_p)_i, (P^T g_p)_i
+  }
+  __syncthreads();
+  if (!single) {
+    for (int e = tid; e < H * A; e += nthr) {
+      const int t = e / A, i = e - t * A;
+      float ptr_ = 0.f, ptg = 0.f;
       if (sP) {
         const float* Pt = sP + t * A * A;
-        for (int kk = 0; kk < A; ++kk) {
-          const float rk = __shfl_sync(0xffffffffu, rp, kk);
-          const float gk = __shfl_sync(0xffffffffu, gp, kk);
-          const float pk = act ? Pt[kk * A + i] : 0.f;
-          ptr_ = fmaf(pk, rk, ptr_);
-          ptg = fmaf(pk, gk, ptg);
+        for (int k = 0; k < A; ++k) {
+          const float pk = Pt[k * A + i];
+          ptr_ = fmaf(pk, s_rp[t * A + k], ptr_);
+          ptg = fmaf(pk, sg[t * S + k], ptg);
         }
       } else {
-        ptr_ = 0.8f * rp;
-        ptg = 0.8f * gp;
+        ptr_ = 0.8f * s_rp[e];
+        ptg = 0.8f * sg[t * S + i];
       }
-      const float rv_n = rv + h * (gv - ptr_) - 0.5f * h * h * ptg;
-      rp = rp + h * gp;
-      rv = rv_n;
-      btr = rv;
-      if (speed) {
-        rm = rm + h * gm;
-        btr = rv + (act ? ssgn[t * A + i] : 0.f) * rm;
+      s_a[e] = sg[t * S + A + i] - ptr_;
+      s_b[e] = ptg;
+    }
+    __syncthreads();
+    if (tid < A) {
+      float rv = 0.f;
+#pragma unroll 4
+      for (int t = H - 1; t >= 0; --t) {
+        rv = rv + h * s_a[t * A + tid] - 0.5f * h * h * s_b[t * A + tid];
+        float btr = rv;
+        if (speed) btr = rv + ((s_traj[t * S + A + tid] < 0.f) ? -1.f : 1.f) * s_rm[t * A + tid];
+        s_btr[t * A + tid] = btr;
       }
     }
-    const float dui = act ? -rinv * btr : 0.f;
-    const float dj = warp_sum_f(act ? btr * dui : 0.f);
-    if (act) {
+    __syncthreads();
+  }
+  for (int t = tid; t < H; t += nthr) {
+    float dj = 0.f;
+    for (int i = 0; i < A; ++i) {
+      const float btr = s_btr[t * A + i];
+      const float dui = -ap.rinv[i] * btr;
+      dj += btr * dui;
       du[t * A + i] = dui;
       const float us = su[t * A + i] + ap.alpha * dui;
-      u_star[t * A + i] = fminf(fmaxf(us, clo), chi);
+      u_star[t * A + i] = fminf(fmaxf(us, ap.clo[i]), ap.chi[i]);
     }
-    if (i == 0) djdlam[t] = dj;
+    djdlam[t] = dj;
   }
+  __syncthreads();
 }
 
 bool make_dyn(const klerg_dyn_spec* s, DynDev& d);

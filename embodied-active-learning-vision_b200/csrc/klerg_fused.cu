@@ -312,8 +312,10 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.x2 = o;    o = align16(o + sizeof(u64) * H * Row2<D>::DP);
   p.xs = o;    o = align16(o + sizeof(float) * H * D);
   size_t tile = sizeof(float) * (size_t)(D + 1) * ts;
-  const size_t adj = sizeof(float) * ((size_t)H * S + (size_t)H * A) + sizeof(double) * ((size_t)H * D + 2) + 8;
-  if (tile < adj) tile = adj;  // the adjoint phase reuses the tile area
+  const size_t adj = sizeof(double) * ((size_t)H * D + 2) + sizeof(float) * ((size_t)H * S + adjoint_scratch_floats(H, A));
+  const size_t rot = roll ? sizeof(float) * rollout_rot_floats(1, H) : 0;
+  if (tile < adj) tile = adj;  // the adjoint phase and the ROLL rollout reuse the tile area
+  if (tile < rot) tile = rot;
   p.tile = o;  o = align16(o + tile);
   p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
   p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
@@ -329,7 +331,7 @@ template <int D, int WT, int MAXT>
 __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = a.H, S = a.d.S, A = a.d.A;
-  const bool roll = a.d.kind == KLERG_DYN_ROLL, speed = a.d.kind == KLERG_DYN_SPEED;
+  const bool roll = a.d.kind == KLERG_DYN_ROLL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const SmemPlan sp = plan_grad<D>(H, S, A, roll, a.ts, nwarps, WT);
   float* s_u = (float*)(smem + sp.u);
@@ -350,11 +352,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
   if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
   __syncthreads();
-  if (warp == 0) {
-    const float bs = rollout_warp(a.d, a.bar, a.x0, a.R0, s_u, H, s_traj, s_dbarr, s_P, nullptr);
-    if (lane == 0) *s_bsum = bs;
-  }
-  __syncthreads();
+  rollout_block(a.d, a.bar, a.x0, a.R0, s_u, 1, H, s_traj, s_dbarr, s_P, s_tile, (float*)s_red, s_bsum, nullptr);
   const unsigned epoch = *s_epoch;
   for (int e = tid; e < H * DP; e += blockDim.x) {
     const int t = e / DP, d = e - t * DP;
@@ -483,9 +481,9 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
 
   // ---- phase 3: the last CTA reduces the partials and runs the adjoint --------------------------------
   if (!meet_last(a, s_flag)) return;
-  float* s_g = s_tile;                           // [H][S]
-  float* s_sgn = s_g + H * S;                    // [H][A]
-  double* s_val = (double*)(s_sgn + H * A + ((H * S + H * A) & 1));  // [HD + 2], 8-byte aligned
+  double* s_val = (double*)s_tile;               // [HD + 2]
+  float* s_g = (float*)(s_val + HD + 2);         // [H][S]
+  float* s_scr = s_g + H * S;                    // adjoint scratch
   {
     const double* gpart = ws_fused_grad(a.ws);
     const double* klp = ws_fused_kl(a.ws);
@@ -514,11 +512,9 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     a.dgdx[e] = g;
     s_g[e] = g - s_dbarr[e];
   }
-  if (speed)
-    for (int e = tid; e < H * A; e += blockDim.x) s_sgn[e] = (s_traj[(e / A) * S + A + (e % A)] < 0.f) ? -1.f : 1.f;
   __syncthreads();
-  if (warp == 0) adjoint_warp(a.d, a.ap, H, s_g, s_P, s_sgn, s_u, a.du, a.djdlam, a.u_star);
-  if (tid == 32 || (blockDim.x <= 32 && tid == 0)) {
+  adjoint_block(a.d, a.ap, H, s_g, s_P, s_traj, s_u, s_scr, a.du, a.djdlam, a.u_star);
+  if (tid == 0) {
     const double sa = s_val[HD], sc = s_val[HD + 1];
     if (a.kl_out) {
       a.kl_out[0] = sa;
@@ -539,12 +535,13 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
 // cost eval of G <= FUSED_MAXG candidates
 // ---------------------------------------------------------------------------
 template <int D>
-__host__ __device__ inline SmemPlan plan_cost(int G, int H, int S, int A) {
+__host__ __device__ inline SmemPlan plan_cost(int G, int H, int S, int A, bool roll) {
   SmemPlan p{};
   size_t o = 0;
   p.u = o;    o = align16(o + sizeof(float) * (size_t)G * H * A);
   p.traj = o; o = align16(o + sizeof(float) * (size_t)G * (H + 1) * S);
   p.x2 = o;   o = align16(o + sizeof(u64) * (size_t)G * H * Row2<D>::DP);
+  p.tile = o; o = align16(o + (roll ? sizeof(float) * rollout_rot_floats(G, H) : 0));
   p.red = o;  o = align16(o + sizeof(double) * 32 * 2 * FUSED_MAXG);
   p.misc = o; o = align16(o + 64 + sizeof(float) * FUSED_MAXG);
   p.total = o;
@@ -556,7 +553,7 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int H = a.H, S = a.d.S, A = a.d.A, G = a.G;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const SmemPlan sp = plan_cost<D>(G, H, S, A);
+  const SmemPlan sp = plan_cost<D>(G, H, S, A, a.d.kind == KLERG_DYN_ROLL);
   float* s_u = (float*)(smem + sp.u);
   float* s_traj = (float*)(smem + sp.traj);
   u64* s_x2 = (u64*)(smem + sp.x2);
@@ -569,12 +566,8 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
   for (int e = tid; e < G * H * A; e += blockDim.x) s_u[e] = a.u[e];
   if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
   __syncthreads();
-  for (int g = warp; g < G; g += nwarps) {
-    const float bs = rollout_warp(a.d, a.bar, a.x0, a.R0, s_u + (size_t)g * H * A, H, s_traj + (size_t)g * (H + 1) * S,
-                                  nullptr, nullptr, nullptr);
-    if (lane == 0) s_bsum[g] = bs;
-  }
-  __syncthreads();
+  rollout_block(a.d, a.bar, a.x0, a.R0, s_u, G, H, s_traj, nullptr, nullptr, (float*)(smem + sp.tile), (float*)s_red,
+                s_bsum, nullptr);
   const unsigned epoch = *s_epoch;
   for (int e = tid; e < G * H * DP; e += blockDim.x) {
     const int g = e / (H * DP), r = e - g * (H * DP);
@@ -816,7 +809,7 @@ static int launch_grad_d(EvalArgs& a, cudaStream_t stream) {
 template <int D>
 static int launch_cost_d(EvalArgs& a, cudaStream_t stream) {
   auto kernel = eval_cost_kernel<D>;
-  const SmemPlan sp = plan_cost<D>(a.G, a.H, a.d.S, a.d.A);
+  const SmemPlan sp = plan_cost<D>(a.G, a.H, a.d.S, a.d.A, a.d.kind == KLERG_DYN_ROLL);
   if (sp.total > 200 * 1024) { set_error("eval_costs: G*H too large for shared-memory staging"); return -1; }
   int nthreads = 512;
   const int per_sm = resident_ctas(kernel, nthreads, sp.total);

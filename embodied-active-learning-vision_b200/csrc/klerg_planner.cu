@@ -256,27 +256,47 @@ __global__ void __launch_bounds__(EW_THREADS) target_stage3_kernel(const float* 
 
 // dynamics, barrier, rollout and adjoint device code lives in klerg_dyn.cuh
 
-// One warp per candidate (rollout_warp); controls staged in shared memory.
-constexpr int RO_WARPS = 4;
+// One CTA per candidate (rollout_block): controls, trajectory and linearisation staged in shared memory.
+constexpr int RO_THREADS = 64;
 
-__global__ void __launch_bounds__(RO_WARPS * 32) rollout_kernel(DynDev d, BarDev bar, const float* __restrict__ x0,
-                                                                 const float* __restrict__ R0,
-                                                                 const float* __restrict__ u, int64_t B, int64_t H,
-                                                                 float* __restrict__ traj,
-                                                                 float* __restrict__ barrier_sum,
-                                                                 float* __restrict__ dbarr, float* __restrict__ P,
-                                                                 float* __restrict__ R_out) {
-  extern __shared__ float sh_u[];  // [RO_WARPS][H*A]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = (int64_t)blockIdx.x * RO_WARPS + warp;
-  if (b >= B) return;
-  const int S = d.S, a = d.A;
-  float* us = sh_u + (size_t)warp * H * a;
-  for (int64_t e = lane; e < H * a; e += 32) us[e] = u[b * H * a + e];
-  __syncwarp();
-  const float bsum = rollout_warp(d, bar, x0, R0, us, (int)H, traj + b * (H + 1) * S, dbarr ? dbarr + b * H * S : nullptr,
-                                  P ? P + b * H * a * a : nullptr, R_out ? R_out + b * 9 : nullptr);
-  if (lane == 0 && barrier_sum) barrier_sum[b] = bsum;
+__host__ __device__ inline size_t rollout_smem_floats(int kind, int S, int A, int64_t H, bool want_dbarr, bool want_P) {
+  size_t n = (size_t)H * A + (size_t)(H + 1) * S + 34;
+  if (want_dbarr) n += (size_t)H * S;
+  if (kind == KLERG_DYN_ROLL) {
+    n += rollout_rot_floats(1, (int)H);
+    if (want_P) n += (size_t)H * A * A;
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(RO_THREADS) rollout_kernel(DynDev d, BarDev bar, const float* __restrict__ x0,
+                                                             const float* __restrict__ R0,
+                                                             const float* __restrict__ u, int64_t B, int64_t H64,
+                                                             float* __restrict__ traj,
+                                                             float* __restrict__ barrier_sum,
+                                                             float* __restrict__ dbarr, float* __restrict__ P,
+                                                             float* __restrict__ R_out) {
+  extern __shared__ float sh[];
+  const int H = (int)H64, S = d.S, a = d.A;
+  const bool roll = d.kind == KLERG_DYN_ROLL;
+  const int64_t b = blockIdx.x;
+  float* s_u = sh;
+  float* s_traj = s_u + H * a;
+  float* s_red = s_traj + (H + 1) * S;   // 32 + 1 (bsum) + pad
+  float* s_dbarr = s_red + 34;
+  float* s_rot = s_dbarr + (dbarr ? H * S : 0);
+  float* s_P = s_rot + (roll ? rollout_rot_floats(1, H) : 0);
+  for (int e = threadIdx.x; e < H * a; e += blockDim.x) s_u[e] = u[b * H * a + e];
+  __syncthreads();
+  rollout_block(d, bar, x0, R0, s_u, 1, H, s_traj, dbarr ? s_dbarr : nullptr, (P && roll) ? s_P : nullptr, s_rot, s_red,
+                s_red + 32, R_out ? R_out + b * 9 : nullptr);
+  for (int e = threadIdx.x; e < (H + 1) * S; e += blockDim.x) traj[b * (H + 1) * S + e] = s_traj[e];
+  if (dbarr)
+    for (int e = threadIdx.x; e < H * S; e += blockDim.x) dbarr[b * H * S + e] = s_dbarr[e];
+  if (P)
+    for (int e = threadIdx.x; e < H * a * a; e += blockDim.x)
+      P[b * H * a * a + e] = roll ? s_P[e] : (((e % (a * a)) / a == e % a) ? 0.8f : 0.f);
+  if (threadIdx.x == 0 && barrier_sum) barrier_sum[b] = s_red[32];
 }
 
 __global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int64_t T, int S, float* __restrict__ value,
@@ -293,7 +313,7 @@ __global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int
 }
 
 // ---------------------------------------------------------------------------
-// adjoint sweep (klerg.py:433-450, 590-593): stage inputs in shared memory, then adjoint_warp
+// adjoint sweep (klerg.py:433-450, 590-593): stage inputs in shared memory, then adjoint_block
 // ---------------------------------------------------------------------------
 struct AdjArgs {
   DynDev d;
@@ -313,14 +333,15 @@ struct AdjArgs {
 };
 
 __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
-  extern __shared__ float sh[];  // g[H][S] | P[H][A*A] (optional) | sgn[H][A] (SPEED) | u[H][A]
+  extern __shared__ float sh[];  // g[H][S] | P[H][A*A] (optional) | traj[H][S] (SPEED) | u[H][A] | scratch
   const int S = a.d.S, A = a.d.A, D = a.k.D;
   const int64_t H = a.H;
   const bool speed = a.d.kind == KLERG_DYN_SPEED;
   float* sg = sh;
   float* sP = sg + H * S;
-  float* ssgn = sP + (a.P ? H * A * A : 0);
-  float* su = ssgn + (speed ? H * A : 0);
+  float* straj = sP + (a.P ? H * A * A : 0);
+  float* su = straj + (speed ? H * S : 0);
+  float* s_scr = su + H * A;
   // phase 1 (all threads): g = dgdx - dbarr staged in smem, dgdx[H][S] written out
   for (int64_t e = threadIdx.x; e < H * S; e += blockDim.x) sg[e] = 0.f;
   __syncthreads();
@@ -337,13 +358,11 @@ __global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
   }
   if (a.P)
     for (int64_t e = threadIdx.x; e < H * A * A; e += blockDim.x) sP[e] = a.P[e];
-  for (int64_t e = threadIdx.x; e < H * A; e += blockDim.x) {
-    su[e] = a.u[e];
-    if (speed) ssgn[e] = (a.traj[(e / A) * S + A + (e % A)] < 0.f) ? -1.f : 1.f;
-  }
+  for (int64_t e = threadIdx.x; e < H * A; e += blockDim.x) su[e] = a.u[e];
+  if (speed)
+    for (int64_t e = threadIdx.x; e < H * S; e += blockDim.x) straj[e] = a.traj[e];
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  adjoint_warp(a.d, a.ap, (int)H, sg, a.P ? sP : nullptr, ssgn, su, a.du, a.djdlam, a.u_star);
+  adjoint_block(a.d, a.ap, (int)H, sg, a.P ? sP : nullptr, straj, su, s_scr, a.du, a.djdlam, a.u_star);
 }
 
 struct CombineArgs {
@@ -573,8 +592,16 @@ extern "C" int klerg_rollout(const klerg_dyn_spec* dyn, const klerg_barrier_spec
   if (!make_dyn(dyn, d) || !make_bar(bar, b)) return -1;
   if (B < 1 || H < 0) { set_error("rollout: bad sizes"); return -1; }
   if (H > KLERG_MAX_H) { set_error("rollout: H > KLERG_MAX_H"); return -1; }
-  const size_t smem = (size_t)RO_WARPS * H * d.A * sizeof(float);
-  rollout_kernel<<<(unsigned)((B + RO_WARPS - 1) / RO_WARPS), RO_WARPS * 32, smem, (cudaStream_t)stream>>>(
+  const size_t smem = sizeof(float) * rollout_smem_floats(d.kind, d.S, d.A, H, dbarr != nullptr, P != nullptr);
+  if (smem > 48 * 1024) {
+    static size_t raised = 0;
+    if (smem > 200 * 1024) { set_error("rollout: horizon too long for shared-memory staging"); return -1; }
+    if (smem > raised) {
+      cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      raised = smem;
+    }
+  }
+  rollout_kernel<<<(unsigned)B, RO_THREADS, smem, (cudaStream_t)stream>>>(
       d, b, x0, R0, u, B, H, traj, barrier_sum, dbarr, P, R_out);
   return check_launch("rollout_kernel");
 }
@@ -601,7 +628,8 @@ extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec*
   a.ap.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
   for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
   const bool speed = a.d.kind == KLERG_DYN_SPEED;
-  const size_t smem = sizeof(float) * (size_t)H * (a.d.S + (P ? a.d.A * a.d.A : 0) + (speed ? a.d.A : 0) + a.d.A);
+  const size_t smem = sizeof(float) * ((size_t)H * (a.d.S + (P ? a.d.A * a.d.A : 0) + (speed ? a.d.S : 0) + a.d.A) +
+                                       adjoint_scratch_floats((int)H, a.d.A));
   if (smem > 48 * 1024) {
     static bool raised = false;
     if (!raised) {
