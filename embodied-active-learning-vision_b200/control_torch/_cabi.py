@@ -105,12 +105,14 @@ SIGNATURES = {
                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_gather_rows": [_P, _I32, _P, _I64, _P, _P],
     "klerg_mailbox_bytes": [],
+    "klerg_debug_stamps_offset": [],
+    "klerg_fused_fault_offset": [],
     "klerg_eval_gradient": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _P, _F, _FP, _F, _FP, _FP,
                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "klerg_eval_costs": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P,
                          _P, _P],
 }
-_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t,
+_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
              "klerg_launch_count": C.c_longlong}
 
 

@@ -294,15 +294,18 @@ class EvalBuffers:
 
 
 def eval_gradient(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, p, p_stats, rinv, alpha, ctrl_lo, ctrl_hi, out,
-                  floor=FLOOR):
-    """One fused launch: rollout + footprint + renormalize + gradient + adjoint (klerg_eval_gradient)."""
+                  floor=FLOOR, want_cost=False):
+    """One fused launch: rollout + footprint + renormalize + gradient + adjoint (klerg_eval_gradient).
+
+    ``want_cost`` also accumulates the KL of the differentiated footprint (not needed by the planner)."""
     H = u.shape[-2]
     cabi.check(cabi.load().klerg_eval_gradient(
         C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, peers, cabi.ptr(x0), cabi.ptr(R0),
         cabi.ptr(u), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(q_base), cabi.ptr(p), cabi.ptr(p_stats),
         float(floor), rinv, float(alpha), ctrl_lo, ctrl_hi, cabi.ptr(out["v"]), cabi.ptr(out["traj"]),
-        cabi.ptr(out["totals"]), cabi.ptr(out["cost"]), cabi.ptr(out["dgdx"]), cabi.ptr(out["du"]),
-        cabi.ptr(out["djdlam"]), cabi.ptr(out["u_star"]), cabi.ptr(out["kl"]), workspace(8), cabi.stream_ptr()),
+        cabi.ptr(out["totals"]), cabi.ptr(out["cost"]) if want_cost else None, cabi.ptr(out["dgdx"]),
+        cabi.ptr(out["du"]), cabi.ptr(out["djdlam"]), cabi.ptr(out["u_star"]),
+        cabi.ptr(out["kl"]) if want_cost else None, workspace(8), cabi.stream_ptr()),
         "klerg_eval_gradient")
     return out
 
@@ -316,6 +319,24 @@ def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, 
         float(floor), cabi.ptr(v_scratch), None, None, cabi.ptr(cost), workspace(8), cabi.stream_ptr()),
         "klerg_eval_costs")
     return cost
+
+
+def debug_stamps():
+    """SM-cycle stamps of the last fused gradient eval on the current stream's workspace (8 int64)."""
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces[key]
+    off = cabi.load().klerg_debug_stamps_offset()
+    return ws.buf[off:off + 64].view(torch.int64).cpu().tolist()
+
+
+def fused_fault():
+    """True if a fused eval on the current stream's workspace gave up waiting at a meeting point."""
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.buf is None:
+        return False
+    off = cabi.load().klerg_fused_fault_offset()
+    return bool(ws.buf[off:off + 4].view(torch.int32).item())
 
 
 def gather_rows(table, idx):

@@ -94,17 +94,18 @@ class PlannerContext:
         self.evals["fwd_pairs"] += B * self.H * self.n
         return engine.kl_cost(v, self.n, totals_w, self.p, self.p_stats, ro["barrier"], self.group, self.floor)
 
-    def gradient(self, u, keep=False):
+    def gradient(self, u, keep=False, want_cost=False):
         """u [H,A] on the device -> dict(du, djdlam, u_star, dgdx, ...) on the device."""
         if self.fused:
             o = engine.eval_gradient(self.spec, self.dyn, self.bar, None, self.x0, self.R0, u.reshape(self.H, -1).contiguous(),
                                      self.packed, self.n, self.q_base, self.p, self.p_stats, self._rinv_c, self.alpha,
-                                     self._lo_c, self._hi_c, self.buf.next_set(), self.floor)
+                                     self._lo_c, self._hi_c, self.buf.next_set(), self.floor, want_cost=want_cost)
             self.evals["grad"] += 1
             self.evals["fwd_pairs"] += self.H * self.n
             self.evals["grad_pairs"] += self.H * self.n
-            out = dict(du=o["du"], djdlam=o["djdlam"], u_star=o["u_star"], dgdx=o["dgdx"], traj=o["traj"][: self.H],
-                       kl_parts=o["kl"].unsqueeze(0), cost=o["cost"])
+            out = dict(du=o["du"], djdlam=o["djdlam"], u_star=o["u_star"], dgdx=o["dgdx"], traj=o["traj"][: self.H])
+            if want_cost:
+                out.update(kl_parts=o["kl"].unsqueeze(0), cost=o["cost"])
             if keep:
                 out.update(v=o["v"], totals=o["totals"].unsqueeze(0))
             return out

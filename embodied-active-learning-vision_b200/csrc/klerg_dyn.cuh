@@ -19,12 +19,16 @@ struct BarDev {
   float lo[KLERG_MAX_S], hi[KLERG_MAX_S], w[KLERG_MAX_S], pw[KLERG_MAX_S];
 };
 
+// Rarely-taken math is kept out of line: the fused kernels run these phases once per launch from a cold
+// instruction cache, where straight-line code size is what costs time.
+static __device__ __noinline__ float pow_generic(float d, float pw) { return powf(d, pw); }
+
 __device__ __forceinline__ float powi_or_f(float d, float pw) {
   if (pw == 4.f) { const float d2 = d * d; return d2 * d2; }
   if (pw == 3.f) return d * d * d;
   if (pw == 2.f) return d * d;
   if (pw == 1.f) return d;
-  return powf(d, pw);
+  return pow_generic(d, pw);
 }
 
 // barr(x) = sum_i w_i [(x_i <= lo_i)(x_i - lo_i)^pw + (x_i >= hi_i)(x_i - hi_i)^pw]   (barrier.py:70-76)
@@ -68,7 +72,7 @@ __device__ __forceinline__ float affine_map(float v, float ilo, float ihi, float
   return (v - ilo) / (ihi - ilo) * (ohi - olo) + olo;
 }
 
-__device__ inline void euler_xyz_to_matrix(const float* rot, float* R) {
+static __device__ __noinline__ void euler_xyz_to_matrix(const float* rot, float* R) {
   // Rz(yaw) * Ry(pitch) * Rx(roll)   (rotations.py:70-96, order flipped to match scipy)
   float sr, cr, sp, cp, sy, cy;
   sincosf(rot[0], &sr, &cr);
@@ -86,7 +90,7 @@ __device__ __forceinline__ float py_mod(float x, float m) {
 }
 
 // E = expm(hat(w) dt) via Rodrigues (= torch.matrix_exp of the skew matrix, dynamics.py:213-217)
-__device__ inline void rodrigues(const float* w, float dt, float* E) {
+static __device__ __noinline__ void rodrigues(const float* w, float dt, float* E) {
   const float kx = w[0] * dt, ky = w[1] * dt, kz = w[2] * dt;
   const float th2 = kx * kx + ky * ky + kz * kz;
   float A, B;  // sin(th)/th, (1-cos(th))/th^2
@@ -107,7 +111,7 @@ __device__ inline void rodrigues(const float* w, float dt, float* E) {
 }
 
 // wrap(euler_XYZ(R)): roll in [0, 2pi), pitch / yaw in [-pi, pi)   (rotations.py:142-181, dynamics.py:219-222)
-__device__ inline void wrapped_euler_xyz(const float* Rn, float* rot) {
+static __device__ __noinline__ void wrapped_euler_xyz(const float* Rn, float* rot) {
   const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
   const float r0 = atan2f(Rn[7], Rn[8]);
   const float r1 = asinf(-Rn[6]);
@@ -115,6 +119,17 @@ __device__ inline void wrapped_euler_xyz(const float* Rn, float* rot) {
   rot[0] = py_mod(r0, two_pi);
   rot[1] = py_mod(r1 + pi, two_pi) - pi;
   rot[2] = py_mod(r2 + pi, two_pi) - pi;
+}
+
+// E(roll, pitch + 1e-5) R: the rpw x rpw block of d(pos rate)/d(vel)   (dynamics.py:189-211,283-289)
+static __device__ __noinline__ void euler_rate_block(const float* rot_in, const float* R, float* out9) {
+  float rot1 = rot_in[1] + 1e-5f;
+  float s0, c0;
+  sincosf(rot_in[0], &s0, &c0);
+  const float t1 = tanf(rot1), cc1 = cosf(rot1);
+  const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / cc1, c0 / cc1};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out9[r * 3 + c] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
 }
 
 __device__ __forceinline__ void matmul3(const float* E, const float* R, float* Rn) {
@@ -162,21 +177,32 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
     float pos = x0[i];
     float vel = single ? 0.f : x0[a + i];
     float mag = speed ? x0[2 * a + i] : 0.f;
-#pragma unroll 4
-    for (int t = 0; t <= H; ++t) {
-      tr[t * S + i] = pos;
-      if (!single) tr[t * S + a + i] = vel;
-      if (speed) tr[t * S + 2 * a + i] = mag;
-      if (t == H) break;
-      const float ut = us[t * a + i];
-      if (single) {
-        pos = pos + dt * ut;
-      } else {
-        pos = pos + (c1 * vel + c2 * ut);
-        vel = vel + dt * ut;
-        if (speed) mag = fabsf(vel);
+    // chunks of 8 steps: controls are fetched into registers first so the loads overlap the recurrence
+    for (int t0 = 0; t0 < H; t0 += 8) {
+      float ub[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ub[k] = (t0 + k < H) ? us[(t0 + k) * a + i] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + k;
+        if (t < H) {
+          tr[t * S + i] = pos;
+          if (!single) tr[t * S + a + i] = vel;
+          if (speed) tr[t * S + 2 * a + i] = mag;
+          const float ut = ub[k];
+          if (single) {
+            pos = pos + dt * ut;
+          } else {
+            pos = pos + (c1 * vel + c2 * ut);
+            vel = vel + dt * ut;
+            if (speed) mag = fabsf(vel);
+          }
+        }
       }
     }
+    tr[H * S + i] = pos;
+    if (!single) tr[H * S + a + i] = vel;
+    if (speed) tr[H * S + 2 * a + i] = mag;
   }
   __syncthreads();
   if (roll) {
@@ -253,16 +279,11 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
           rot[k] = s_traj[((size_t)g * (H + 1) + t) * S + d.rpw[k]];
           if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
         }
-        rot[1] += 1e-5f;
-        float s0, c0;
-        sincosf(rot[0], &s0, &c0);
-        const float t1 = tanf(rot[1]), cc1 = cosf(rot[1]);
-        const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / cc1, c0 / cc1};
-        const float* R = s_R + ((size_t)g * (H + 1) + t) * 9;
+        float blk[9];
+        euler_rate_block(rot, s_R + ((size_t)g * (H + 1) + t) * 9, blk);
         float* Pt = s_P + (size_t)e * a * a;
         for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c)
-            Pt[d.rpw[r] * a + d.rpw[c]] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
+          for (int c = 0; c < 3; ++c) Pt[d.rpw[r] * a + d.rpw[c]] = blk[r * 3 + c];
       }
     }
   } else if (R_out) {
@@ -327,14 +348,26 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
   float* s_btr = s_b + H * A;       // B^T rho after step t
   if (tid < A) {
     float rp = 0.f, rm = 0.f;
-#pragma unroll 4
-    for (int t = H - 1; t >= 0; --t) {
-      s_rp[t * A + tid] = rp;
-      rp = rp + h * sg[t * S + tid];
-      if (single) s_btr[t * A + tid] = rp;
-      if (speed) {
-        rm = rm + h * sg[t * S + 2 * A + tid];
-        s_rm[t * A + tid] = rm;
+    for (int t0 = H - 1; t0 >= 0; t0 -= 8) {
+      float gp[8], gm[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 - k;
+        gp[k] = (t >= 0) ? sg[t * S + tid] : 0.f;
+        gm[k] = (speed && t >= 0) ? sg[t * S + 2 * A + tid] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 - k;
+        if (t >= 0) {
+          s_rp[t * A + tid] = rp;
+          rp = rp + h * gp[k];
+          if (single) s_btr[t * A + tid] = rp;
+          if (speed) {
+            rm = rm + h * gm[k];
+            s_rm[t * A + tid] = rm;
+          }
+        }
       }
     }
   }
@@ -360,12 +393,24 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
     __syncthreads();
     if (tid < A) {
       float rv = 0.f;
-#pragma unroll 4
-      for (int t = H - 1; t >= 0; --t) {
-        rv = rv + h * s_a[t * A + tid] - 0.5f * h * h * s_b[t * A + tid];
-        float btr = rv;
-        if (speed) btr = rv + ((s_traj[t * S + A + tid] < 0.f) ? -1.f : 1.f) * s_rm[t * A + tid];
-        s_btr[t * A + tid] = btr;
+      for (int t0 = H - 1; t0 >= 0; t0 -= 8) {
+        float av[8], bv[8], sv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int t = t0 - k;
+          av[k] = (t >= 0) ? s_a[t * A + tid] : 0.f;
+          bv[k] = (t >= 0) ? s_b[t * A + tid] : 0.f;
+          sv[k] = 0.f;
+          if (speed && t >= 0) sv[k] = ((s_traj[t * S + A + tid] < 0.f) ? -1.f : 1.f) * s_rm[t * A + tid];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int t = t0 - k;
+          if (t >= 0) {
+            rv = rv + h * av[k] - 0.5f * h * h * bv[k];
+            s_btr[t * A + tid] = speed ? rv + sv[k] : rv;
+          }
+        }
       }
     }
     __syncthreads();

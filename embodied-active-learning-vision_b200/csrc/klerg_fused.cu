@@ -63,6 +63,29 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
   return v;
 }
 
+// Bounded spins: a meeting point that is never reached (a lost peer, a launch that was not
+// co-resident) must not hang the GPU.  After SPIN_LIMIT polls the waiter records a sticky fault
+// in ctrl[5] and carries on with whatever is there; klerg_fused_fault() reports it.
+constexpr long long SPIN_LIMIT = 1ll << 22;
+#define KLERG_SPIN_UNTIL(cond, ctrl)                 \
+  for (long long spin_ = 0; !(cond); ++spin_) {      \
+    if (spin_ > SPIN_LIMIT) {                        \
+      (ctrl)[5] = 1u;                                \
+      break;                                         \
+    }                                                \
+  }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct Peers {
   int world, rank;
   void* mail[MB_MAXW];  // mail[r] = rank r's mailbox mapped into this process (mail[rank] = local)
@@ -113,12 +136,12 @@ __device__ __forceinline__ void block_reduce(const int (&kind)[NQ], double (&val
     if (lane == 0) sh_red[warp * NQ + q] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      double v = sh_red[q];
-      for (int w = 1; w < nwarp; ++w) v = red_combine(kind[q], v, sh_red[w * NQ + q]);
-      val[q] = v;
+      double v = lane < nwarp ? sh_red[lane * NQ + q] : red_identity(kind[q]);
+      v = warp_reduce(kind[q], v);
+      if (lane == 0) val[q] = v;
     }
   }
 }
@@ -127,11 +150,43 @@ __device__ __forceinline__ void block_reduce(const int (&kind)[NQ], double (&val
 // Meeting point 1: every CTA has written part_tot[blk][g][2]; on return world_tot[g][2]
 // (all CTAs, all ranks) is readable by every thread.  The last CTA to arrive is the leader.
 // ---------------------------------------------------------------------------
-__device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_flag, double* sh_red) {
+__device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_flag, double* sh_world /* [2G] */) {
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   const unsigned nblk = gridDim.x;
-  const unsigned go_val = 2u * epoch + 1u;
+  const double* part = ws_fused_tot(a.ws);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
+  if (a.peers.world <= 1) {
+    // single GPU: count arrivals, then every CTA combines the per-CTA partials itself (one L2 round trip)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(&ctrl[0], 1u);
+      KLERG_SPIN_UNTIL(ld_acquire_u32(&ctrl[0]) >= nblk, ctrl)
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int g = 0; g < G; ++g) {
+        double s = 0.0, m = -INFINITY;
+        for (unsigned b = lane; b < nblk; b += 32) {
+          s += __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 0]);
+          m = fmax(m, __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 1]));
+        }
+        s = warp_reduce(RED_SUM, s);
+        m = warp_reduce(RED_MAX, m);
+        if (lane == 0) {
+          sh_world[2 * g] = s;
+          sh_world[2 * g + 1] = m;
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  // several ranks: the last CTA to arrive combines, exchanges with the peers over NVLink and publishes
+  const unsigned go_val = 2u * epoch + 1u;
+  double* world = ws_fused_world(a.ws);
+  const int par = epoch & 1;
+  const int nq = 2 * G;
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned t = atomicAdd(&ctrl[0], 1u);
@@ -139,68 +194,50 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_fl
   }
   __syncthreads();
   if (*sh_flag) {
-    // leader: combine the per-CTA partials (thread b loads CTA b's pair, fixed-order block tree)
     __threadfence();
-    double* world = ws_fused_world(a.ws);
-    const double* part = ws_fused_tot(a.ws);
-    const int nq = 2 * G;
-    const int par = epoch & 1;
-    for (int g = 0; g < G; ++g) {
-      double vals[2] = {0.0, -INFINITY};
-      for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x) {
-        vals[0] += __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 0]);
-        vals[1] = fmax(vals[1], __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 1]));
-      }
-      const int kinds[2] = {RED_SUM, RED_MAX};
-      block_reduce<2>(kinds, vals, sh_red);
-      if (threadIdx.x == 0) {
-        if (a.peers.world > 1) {
-          for (int r = 0; r < a.peers.world; ++r) {
-            double* slot = mb_a(a.peers.mail[r], par, a.peers.rank);
-            slot[2 * g] = vals[0];
-            slot[2 * g + 1] = vals[1];
-          }
-        } else {
-          world[2 * g] = vals[0];
-          world[2 * g + 1] = vals[1];
+    if (warp == 0) {
+      for (int g = 0; g < G; ++g) {
+        double s = 0.0, m = -INFINITY;
+        for (unsigned b = lane; b < nblk; b += 32) {
+          s += __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 0]);
+          m = fmax(m, __ldcg(&part[((size_t)b * FUSED_MAXG + g) * 2 + 1]));
+        }
+        s = warp_reduce(RED_SUM, s);
+        m = warp_reduce(RED_MAX, m);
+        // all-gather over NVLink: lane r stores this rank's pair into rank r's mailbox
+        if (lane < a.peers.world) {
+          double* slot = mb_a(a.peers.mail[lane], par, a.peers.rank);
+          slot[2 * g] = s;
+          slot[2 * g + 1] = m;
         }
       }
-    }
-    if (a.peers.world > 1) {
-      // all-gather over NVLink: payload stores above, then one release flag per peer; wait for every rank's flag
-      if (threadIdx.x == 0) __threadfence_system();
-      __syncthreads();
-      if ((int)threadIdx.x < a.peers.world) {
-        st_release_sys_u64((unsigned long long*)&mb_a(a.peers.mail[threadIdx.x], par, a.peers.rank)[MB_A_STRIDE - 1],
+      __threadfence_system();
+      __syncwarp();
+      if (lane < a.peers.world) {
+        st_release_sys_u64((unsigned long long*)&mb_a(a.peers.mail[lane], par, a.peers.rank)[MB_A_STRIDE - 1],
                            (unsigned long long)epoch + 1ull);
         const unsigned long long* f =
-            (const unsigned long long*)&mb_a(a.peers.mail[a.peers.rank], par, threadIdx.x)[MB_A_STRIDE - 1];
-        while (ld_acquire_sys_u64(f) != (unsigned long long)epoch + 1ull) {
-        }
+            (const unsigned long long*)&mb_a(a.peers.mail[a.peers.rank], par, lane)[MB_A_STRIDE - 1];
+        KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)epoch + 1ull, ctrl)
       }
-      __syncthreads();
-      if ((int)threadIdx.x < nq) {
-        const int q = threadIdx.x;
-        double v = (q & 1) ? -INFINITY : 0.0;
+      __syncwarp();
+      if (lane < nq) {
+        double v = (lane & 1) ? -INFINITY : 0.0;
         for (int r = 0; r < a.peers.world; ++r) {
-          const double x = ld_volatile_f64(&mb_a(a.peers.mail[a.peers.rank], par, r)[q]);
-          v = (q & 1) ? fmax(v, x) : v + x;
+          const double x = ld_volatile_f64(&mb_a(a.peers.mail[a.peers.rank], par, r)[lane]);
+          v = (lane & 1) ? fmax(v, x) : v + x;
         }
-        world[q] = v;
+        world[lane] = v;
       }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      ctrl[0] = 0;
       __threadfence();
-      st_release_u32(&ctrl[2], go_val);
+      __syncwarp();
+      if (lane == 0) st_release_u32(&ctrl[2], go_val);
     }
-  } else {
-    if (threadIdx.x == 0) {
-      while (ld_acquire_u32(&ctrl[2]) != go_val) {
-      }
-    }
+  } else if (threadIdx.x == 0) {
+    KLERG_SPIN_UNTIL(ld_acquire_u32(&ctrl[2]) == go_val, ctrl)
   }
+  __syncthreads();
+  if ((int)threadIdx.x < nq) sh_world[threadIdx.x] = __ldcg(&world[threadIdx.x]);
   __syncthreads();
 }
 
@@ -236,8 +273,8 @@ __device__ void exchange_sum(const EvalArgs& a, unsigned epoch, double* sh_vals,
                        (unsigned long long)epoch + 1ull);
     const unsigned long long* f =
         (const unsigned long long*)&mb_b(a.peers.mail[a.peers.rank], par, threadIdx.x)[MB_B_STRIDE - 1];
-    while (ld_acquire_sys_u64(f) != (unsigned long long)epoch + 1ull) {
-    }
+    unsigned* ctrl = ws_fused_ctrl(a.ws);
+    KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)epoch + 1ull, ctrl)
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -260,36 +297,59 @@ __device__ __forceinline__ void cta_slice(int64_t N, int64_t ld, int64_t& lo, in
 
 // Forward pair pass of one trajectory (T duplicated rows at sh_x2) over this CTA's slice:
 // v[i] = q_base[i] + inv_nu * sum_t psi; returns the slice's {sum, max} of v over i < N.
-template <int D>
-__device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
-                                              int64_t hi, double& tsum, double& tmax) {
-  for (int64_t i0 = lo + (int64_t)threadIdx.x * 4; i0 < hi; i0 += (int64_t)blockDim.x * 4) {
-    u64 s2[D][2], acc[2];
-    float emin[4];
+template <int D, int P>
+__device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+                                                int64_t hi, double& tsum, double& tmax) {
+  constexpr int SPT = 2 * P;
+  for (int64_t i0 = lo + (int64_t)threadIdx.x * SPT; i0 < hi; i0 += (int64_t)blockDim.x * SPT) {
+    u64 s2[D][P], acc[P];
+    float emin[SPT];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
-      s2[d][0] = pack2(s.x, s.y);
-      s2[d][1] = pack2(s.z, s.w);
+      if constexpr (P == 2) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+        s2[d][1] = pack2(s.z, s.w);
+      } else {
+        const float2 s = __ldg(reinterpret_cast<const float2*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+      }
     }
-    acc[0] = acc[1] = pack2(0.f, 0.f);
-    pair_forward<D, 2, 0>(sh_x2, T, s2, acc, emin);
-    float o[4];
-    unpack2(acc[0], o[0], o[1]);
-    unpack2(acc[1], o[2], o[3]);
+    float qb[SPT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? a.q_base[i0 + q] : 0.f;
+#pragma unroll
+    for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
+    pair_forward<D, P, 0>(sh_x2, T, s2, acc, emin);
+    float o[SPT];
+#pragma unroll
+    for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
       const int64_t i = i0 + q;
       float v = o[q] * a.k.inv_nu;
       if (i < a.N) {
-        if (a.q_base) v += a.q_base[i];
+        if (a.q_base) v += qb[q];
         tsum += (double)v;
         tmax = fmax(tmax, (double)v);
       }
       o[q] = v;
     }
-    *reinterpret_cast<float4*>(v_out + i0) = make_float4(o[0], o[1], o[2], o[3]);
+    if constexpr (P == 2)
+      *reinterpret_cast<float4*>(v_out + i0) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      *reinterpret_cast<float2*>(v_out + i0) = make_float2(o[0], o[1]);
   }
+}
+
+// small slices use one packed pair per thread so that more warps share the latency-bound work
+template <int D>
+__device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+                                              int64_t hi, double& tsum, double& tmax) {
+  if (hi - lo <= (int64_t)blockDim.x * 2)
+    forward_slice_p<D, 1>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
+  else
+    forward_slice_p<D, 2>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
 }
 
 // ---------------------------------------------------------------------------
@@ -311,7 +371,7 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.P = o;     o = align16(o + (roll ? sizeof(float) * H * A * A : 0));
   p.x2 = o;    o = align16(o + sizeof(u64) * H * Row2<D>::DP);
   p.xs = o;    o = align16(o + sizeof(float) * H * D);
-  size_t tile = sizeof(float) * (size_t)(D + 1) * ts;
+  size_t tile = sizeof(float) * (size_t)2 * (D + 2) * ts;  // two cp.async buffers of rows s_0..s_{D-1}, v->w, p
   const size_t adj = sizeof(double) * ((size_t)H * D + 2) + sizeof(float) * ((size_t)H * S + adjoint_scratch_floats(H, A));
   const size_t rot = roll ? sizeof(float) * rollout_rot_floats(1, H) : 0;
   if (tile < adj) tile = adj;  // the adjoint phase and the ROLL rollout reuse the tile area
@@ -348,7 +408,9 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   float* s_bsum = (float*)(smem + sp.misc) + 2;
   constexpr int DP = Row2<D>::DP;
 
-  // ---- phase 0: rollout (every CTA, one warp) -----------------------------------------------
+  long long stamp[8];
+  stamp[0] = clock64();
+  // ---- phase 0: rollout (every CTA) ---------------------------------------------------------------
   for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
   if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
   __syncthreads();
@@ -367,6 +429,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     for (int e = tid; e < (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
   __syncthreads();
 
+  stamp[1] = clock64();
   // ---- phase 1: forward pair pass, slice totals -------------------------------------------------
   int64_t lo, hi;
   cta_slice(a.N, a.ld, lo, hi);
@@ -382,9 +445,12 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
       part[1] = vals[1];
     }
   }
-  meet_totals(a, 1, epoch, s_flag, s_red);
-  const double vsum = __ldcg(&ws_fused_world(a.ws)[0]);
-  const double vmax = __ldcg(&ws_fused_world(a.ws)[1]);
+  stamp[2] = clock64();
+  double* s_world = s_red + 32 * 2;  // [2]
+  meet_totals(a, 1, epoch, s_flag, s_world);
+  stamp[3] = clock64();
+  const double vsum = s_world[0];
+  const double vmax = s_world[1];
   if (blockIdx.x == 0 && tid == 0 && a.totals) {
     a.totals[0] = vsum;
     a.totals[1] = vmax;
@@ -398,6 +464,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   const int nblk = gridDim.x;
   const int gstride = (nblk + 31) & ~31;  // partial layout [e][gstride]: the final reduce reads rows coalesced
   double kl_a = 0.0, kl_c = 0.0;
+  const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
   for (int r = 0; r < a.rounds; ++r) {
     const int cw = warp % a.nchr, sub = warp / a.nchr;
     const int t0 = (r * a.nchr + cw) * WT;
@@ -411,28 +478,61 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
         xs2[k][d] = pack2(x, x);
         acc[k][d] = pack2(0.f, 0.f);
       }
-    for (int64_t base = lo; base < hi; base += ts) {
+    // Sample tiles stream global -> shared with cp.async, one tile ahead of the pair math:
+    // rows s_0..s_{D-1} (scaled samples), q_base + q_iter (turned into the importance ratio in place), p.
+    const int nt = (int)((hi - lo + ts - 1) / ts);
+    auto issue_tile = [&](int k) {
+      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * ts;
+      const int64_t base = lo + (int64_t)k * ts;
+      const int cnt = (int)min((int64_t)ts, hi - base);  // multiple of 4
+      const int nch = cnt >> 2;
+      for (int c = tid; c < (D + 1) * nch; c += blockDim.x) {
+        const int row = c / nch, q4 = (c - row * nch) << 2;
+        const float* src = (row < D ? a.packed + (int64_t)row * a.ld : a.v) + base + q4;
+        cp_async16(buf + (size_t)row * ts + q4, src);
+      }
+      float* prow = buf + (size_t)(D + 1) * ts;
+      for (int c = tid; c < nch; c += blockDim.x) {
+        const int64_t i = base + ((int64_t)c << 2);
+        if (i + 3 < a.N) {
+          cp_async16(prow + (c << 2), a.p + i);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (i + q < a.N) cp_async4(prow + (c << 2) + q, a.p + i + q);
+            else prow[(c << 2) + q] = 0.f;
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    issue_tile(0);
+    for (int k = 0; k < nt; ++k) {
+      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * ts;
+      const int64_t base = lo + (int64_t)k * ts;
       const int cnt = (int)min((int64_t)ts, hi - base);
       const int cnt64 = (cnt + 63) & ~63;
-      __syncthreads();
+      cp_async_wait_all();
+      __syncthreads();  // tile k has landed for everyone; everyone is done with tile k-1
+      if (k + 1 < nt) issue_tile(k + 1);
+      float* wrow = buf + (size_t)D * ts;
+      const float* prow = buf + (size_t)(D + 1) * ts;
       for (int e = tid; e < cnt64; e += blockDim.x) {
         const int64_t i = base + e;
         float w = 0.f;
         if (e < cnt && i < a.N) {
-          const float c = fmaxf(a.v[i] / vsum_f, a.floor);
-          const float pi = a.p[i];
-          w = pi * maxc_f / c;  // p/q with q = c / max c  (klerg.py:436)
-          if (r == 0) {
+          const float c = fmaxf(__fdividef(wrow[e], vsum_f), a.floor);
+          const float pi = prow[e];
+          w = __fdividef(pi * maxc_f, c);  // p/q with q = c / max c  (klerg.py:436)
+          if (want_kl && r == 0) {
             kl_a += (double)(pi * (logf(pi) - logf(c)));
             kl_c += (double)c;
           }
+        } else if (e >= cnt) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) s_tile[d * ts + e] = __ldg(a.packed + (int64_t)d * a.ld + i);
-        } else {
-#pragma unroll
-          for (int d = 0; d < D; ++d) s_tile[d * ts + e] = 0.f;
+          for (int d = 0; d < D; ++d) buf[(size_t)d * ts + e] = 0.f;
         }
-        s_tile[D * ts + e] = w;
+        wrow[e] = w;
       }
       __syncthreads();
       if (active) {
@@ -440,12 +540,13 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
           const int i = pb + 2 * lane;
           u64 s2[D];
 #pragma unroll
-          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&s_tile[d * ts + i]);
-          const u64 w2 = *reinterpret_cast<const u64*>(&s_tile[D * ts + i]);
+          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * ts + i]);
+          const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
           pair_gradient<D, WT>(xs2, s2, w2, acc);
         }
       }
     }
+    __syncthreads();
     // lanes -> warp sums -> CTA partial for this round's states
 #pragma unroll
     for (int k = 0; k < WT; ++k)
@@ -480,25 +581,35 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   }
 
   // ---- phase 3: the last CTA reduces the partials and runs the adjoint --------------------------------
+  stamp[4] = clock64();
   if (!meet_last(a, s_flag)) return;
+  stamp[5] = clock64();
   double* s_val = (double*)s_tile;               // [HD + 2]
   float* s_g = (float*)(s_val + HD + 2);         // [H][S]
   float* s_scr = s_g + H * S;                    // adjoint scratch
   {
+    // 4 lanes per entry, each summing every 4th CTA partial (independent loads), then a 2-step shuffle tree
     const double* gpart = ws_fused_grad(a.ws);
     const double* klp = ws_fused_kl(a.ws);
-    for (int e = warp; e < HD + 2; e += nwarps) {
+    const int n4 = (HD + 2) * 4;
+    for (int idx = tid; idx < ((n4 + 31) & ~31); idx += blockDim.x) {  // whole warps take part in the shuffles
+      const int e = idx >> 2, part = idx & 3;
       double v = 0.0;
-      if (e < HD) {
-        for (int b = lane; b < nblk; b += 32) v += __ldcg(&gpart[(size_t)e * gstride + b]);
+      if (idx >= n4) {
+      } else if (e < HD) {
+#pragma unroll 8
+        for (int b = part; b < nblk; b += 4) v += __ldcg(&gpart[(size_t)e * gstride + b]);
       } else {
-        for (int b = lane; b < nblk; b += 32) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + (e - HD)]);
+#pragma unroll 8
+        for (int b = part; b < nblk; b += 4) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + (e - HD)]);
       }
-      v = warp_reduce(RED_SUM, v);
-      if (lane == 0) s_val[e] = v;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (part == 0 && idx < n4) s_val[e] = v;
     }
   }
   __syncthreads();
+  stamp[6] = clock64();
   exchange_sum(a, epoch, s_val, HD + 2);
   for (int e = tid; e < H * S; e += blockDim.x) s_g[e] = 0.f;
   __syncthreads();
@@ -526,8 +637,13 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
       a.cost[0] = (float)(sa / spv - log(spv) + log(sc)) + *s_bsum;
     }
     unsigned* ctrl = ws_fused_ctrl(a.ws);
+    ctrl[0] = 0;
     ctrl[1] = 0;
     ctrl[3] = epoch + 1;
+    // phase stamps of the CTA that finished last (SM cycles since its start): debugging / profiling aid
+    stamp[7] = clock64();
+    long long* dbg = (long long*)(ctrl + 16);
+    for (int i = 0; i < 8; ++i) dbg[i] = stamp[i] - stamp[0];
   }
 }
 
@@ -594,8 +710,9 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
       part[1] = vals[1];
     }
   }
-  meet_totals(a, G, epoch, s_flag, s_red);
-  if (blockIdx.x == 0 && tid < 2 * G && a.totals) a.totals[tid] = __ldcg(&ws_fused_world(a.ws)[tid]);
+  double* s_world = s_red + 32 * 2;  // [2G]
+  meet_totals(a, G, epoch, s_flag, s_world);
+  if (blockIdx.x == 0 && tid < 2 * G && a.totals) a.totals[tid] = s_world[tid];
 
   // KL partials: sum_i p_i (log p_i - log c_i), sum_i c_i   (klerg.py:694-699 in closed form)
   float vs[FUSED_MAXG], maxc[FUSED_MAXG];
@@ -605,7 +722,7 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
     sa[g] = sc[g] = 0.0;
     vs[g] = maxc[g] = 1.f;
     if (g < G) {
-      const double vsum = __ldcg(&ws_fused_world(a.ws)[2 * g]), vmax = __ldcg(&ws_fused_world(a.ws)[2 * g + 1]);
+      const double vsum = s_world[2 * g], vmax = s_world[2 * g + 1];
       vs[g] = (float)vsum;
       maxc[g] = fmaxf((float)vmax / vs[g], a.floor);
     }
@@ -647,11 +764,17 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
   {
     const double* klp = ws_fused_kl(a.ws);
     const int nblk = gridDim.x;
-    for (int e = warp; e < 2 * G; e += nwarps) {
+    const int n4 = 2 * G * 4;
+    for (int idx = tid; idx < ((n4 + 31) & ~31); idx += blockDim.x) {  // whole warps take part in the shuffles
+      const int e = idx >> 2, part = idx & 3;
       double v = 0.0;
-      for (int b = lane; b < nblk; b += 32) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + e]);
-      v = warp_reduce(RED_SUM, v);
-      if (lane == 0) s_val[e] = v;
+      if (idx < n4) {
+#pragma unroll 8
+        for (int b = part; b < nblk; b += 4) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + e]);
+      }
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (part == 0 && idx < n4) s_val[e] = v;
     }
   }
   __syncthreads();
@@ -663,6 +786,7 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
   }
   if (tid == 0) {
     unsigned* ctrl = ws_fused_ctrl(a.ws);
+    ctrl[0] = 0;
     ctrl[1] = 0;
     ctrl[3] = epoch + 1;
   }
@@ -841,6 +965,8 @@ static bool fill_common(EvalArgs& a, const klerg_kernel_spec* k, const klerg_dyn
 using namespace klerg;
 
 extern "C" size_t klerg_mailbox_bytes(void) { return MB_BYTES; }
+extern "C" size_t klerg_fused_fault_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 5 * sizeof(unsigned); }
+extern "C" size_t klerg_debug_stamps_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 64; }
 
 extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
                                    const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
@@ -854,6 +980,7 @@ extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_s
   if (H < 1 || H > KLERG_MAX_H) { set_error("eval_gradient: H out of range"); return -1; }
   if (N < 1 || ld < N || (ld & 3)) { set_error("eval_gradient: bad sample sizes"); return -1; }
   if (!workspace || !v_scratch || !dgdx || !du || !djdlam || !u_star) { set_error("eval_gradient: null output/workspace"); return -1; }
+  if (((uintptr_t)packed | (uintptr_t)p | (uintptr_t)v_scratch) & 15) { set_error("eval_gradient: packed, p and v_scratch must be 16-byte aligned"); return -1; }
   for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
   a.ap.alpha = alpha;
   a.x0 = x0; a.R0 = R0; a.u = u; a.G = 1; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base; a.p = p;

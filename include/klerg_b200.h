@@ -218,6 +218,12 @@ typedef struct klerg_peers {
   void* mailbox[8];
 } klerg_peers;
 size_t klerg_mailbox_bytes(void);
+/* Byte offset inside `workspace` of 8 int64 SM-cycle stamps left by the last klerg_eval_gradient
+ * (start, rollout, forward, meet-1, gradient, meet-2, reduce, end; relative to start). */
+size_t klerg_debug_stamps_offset(void);
+/* Byte offset inside `workspace` of a sticky uint32 fault word: non-zero after a fused eval gave
+ * up waiting at a meeting point (results of that eval are undefined). */
+size_t klerg_fused_fault_offset(void);
 
 /* One planner iteration up to the control update (klerg.py:505-523):
  *   forward(): rollout of u[H][A] from x0 (pre-step states, linearisation, dbarr)

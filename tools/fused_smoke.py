@@ -36,6 +36,13 @@ for fused in (False, True):
     c = ctx.costs(U)
     gr = ctx.gradient(U[0], keep=True)
     torch.cuda.synchronize()
+    if fused:
+        for _ in range(5):
+            ctx.gradient(U[0])
+        torch.cuda.synchronize()
+        st = engine.debug_stamps()
+        names = ["rollout", "forward", "meet1", "gradient", "meet2", "reduce", "adjoint+end"]
+        print("phase cycles:", {k: st[i + 1] - st[i] for i, k in enumerate(names)}, "total", st[7])
     res[fused] = dict(cost=c.cpu(), du=gr["du"].cpu(), dj=gr["djdlam"].cpu(), us=gr["u_star"].cpu(), dgdx=gr["dgdx"].cpu(),
                       v=gr["v"][:n].cpu(), tot=gr["totals"].cpu())
 for k in res[True]:
