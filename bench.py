@@ -284,7 +284,7 @@ def cuda_arm(args):
     torch.manual_seed(1234 + rank)
     probe = Robot(process_group=None, **kw)  # only used to build specs (dyn, barrier, limits)
     bytes_per_set = engine.padded(n) * 4 * (D + 3)
-    n_sets = max(2, int(L2_BYTES * 1.5 / bytes_per_set) + 1)
+    n_sets = min(96, max(2, int(L2_BYTES * 1.5 / bytes_per_set) + 1))
     hist = wl.random_walk_history(args.workload, m, seed=rank).to(dev)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     lo = torch.tensor([a for a, _ in lims]) * 1.15

@@ -62,7 +62,8 @@ def build(force=False, verbose=False):
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + srcs
+    extra = ["-DKLERG_STAMPS"] if os.environ.get("KLERG_STAMPS") else []  # phase stamps in the fused evals
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-o", LIB_PATH] + srcs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
@@ -105,6 +106,9 @@ SIGNATURES = {
                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_gather_rows": [_P, _I32, _P, _I64, _P, _P],
     "klerg_mailbox_bytes": [],
+    "klerg_mailbox_create": [C.POINTER(C.c_void_p), C.c_char_p],
+    "klerg_mailbox_open": [C.c_char_p, C.POINTER(C.c_void_p)],
+    "klerg_mailbox_close": [_P, C.c_int],
     "klerg_debug_stamps_offset": [],
     "klerg_fused_fault_offset": [],
     "klerg_eval_gradient": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _P, _F, _FP, _F, _FP, _FP,

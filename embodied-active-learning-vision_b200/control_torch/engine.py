@@ -64,9 +64,41 @@ class ShardGroup:
         if self.world == 1:
             return block.unsqueeze(0)
         import torch.distributed as dist
-        out = torch.empty((self.world,) + tuple(block.shape), dtype=block.dtype, device=block.device)
-        dist.all_gather_into_tensor(out, block.contiguous(), group=self.pg)
-        return out
+        block = block.contiguous()
+        flat = torch.empty((self.world * block.shape[0],) + tuple(block.shape[1:]), dtype=block.dtype,
+                           device=block.device)  # concatenation along dim 0 (the form every backend accepts)
+        dist.all_gather_into_tensor(flat, block, group=self.pg)
+        return flat.view((self.world,) + tuple(block.shape))
+
+    def peers(self):
+        """klerg_peers for the fused evals: every rank's NVLink mailbox mapped into this process.
+
+        Built once per group: each rank allocates its mailbox (klerg_mailbox_create), the 64-byte
+        CUDA-IPC handles travel through the process group's object all-gather, and every rank maps
+        the others (klerg_mailbox_open).  Returns None for a single rank."""
+        if self.world == 1:
+            return None
+        if getattr(self, "_peers", None) is not None:
+            return self._peers
+        import torch.distributed as dist
+        lib = cabi.load()
+        mine, handle = C.c_void_p(), C.create_string_buffer(64)
+        cabi.check(lib.klerg_mailbox_create(C.byref(mine), handle), "klerg_mailbox_create")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=self.pg)
+        peers = cabi.Peers()
+        peers.world, peers.rank = self.world, self.rank
+        for r in range(self.world):
+            if r == self.rank:
+                peers.mailbox[r] = mine.value
+            else:
+                ptr = C.c_void_p()
+                cabi.check(lib.klerg_mailbox_open(handles[r], C.byref(ptr)), "klerg_mailbox_open")
+                peers.mailbox[r] = ptr.value
+        torch.cuda.synchronize()
+        dist.barrier(group=self.pg)
+        self._peers = peers
+        return peers
 
     def shard_bounds(self, n_total):
         """Contiguous [lo, hi) slice of the sample axis owned by this rank."""

@@ -19,6 +19,8 @@ pass and one of [H*D+2] partials after the gradient pass.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _cabi as cabi
@@ -42,7 +44,9 @@ class PlannerContext:
         self.spec = None
         self.n = 0
         self.evals = dict(cost=0, grad=0, fwd_pairs=0, grad_pairs=0)
-        self.fused = fused and group.world == 1
+        self.fused = fused
+        self.peers = group.peers() if fused else None
+        self._peers_ref = C.byref(self.peers) if self.peers is not None else None
         self.R0 = None
         self._rinv_c, self._lo_c, self._hi_c = cabi.farr(self.rinv), cabi.farr(self.ctrl_lo), cabi.farr(self.ctrl_hi)
         self.buf = None
@@ -82,7 +86,7 @@ class PlannerContext:
             cost = torch.empty(B, dtype=torch.float32, device=U.device)
             for b0 in range(0, B, self.buf.max_g):
                 b1 = min(B, b0 + self.buf.max_g)
-                engine.eval_costs(self.spec, self.dyn, self.bar, None, self.x0, self.R0, U[b0:b1], self.packed, self.n,
+                engine.eval_costs(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, U[b0:b1], self.packed, self.n,
                                   self.q_base, self.p, self.p_stats, self.buf.v_costs, cost[b0:b1], self.floor)
             self.evals["cost"] += B
             self.evals["fwd_pairs"] += B * self.H * self.n
@@ -97,7 +101,7 @@ class PlannerContext:
     def gradient(self, u, keep=False, want_cost=False):
         """u [H,A] on the device -> dict(du, djdlam, u_star, dgdx, ...) on the device."""
         if self.fused:
-            o = engine.eval_gradient(self.spec, self.dyn, self.bar, None, self.x0, self.R0, u.reshape(self.H, -1).contiguous(),
+            o = engine.eval_gradient(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, u.reshape(self.H, -1).contiguous(),
                                      self.packed, self.n, self.q_base, self.p, self.p_stats, self._rinv_c, self.alpha,
                                      self._lo_c, self._hi_c, self.buf.next_set(), self.floor, want_cost=want_cost)
             self.evals["grad"] += 1

@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdio>
+#include <cstring>
 
 #include "klerg_common.cuh"
 #include "klerg_dyn.cuh"
@@ -32,13 +33,18 @@ constexpr int MB_A_STRIDE = 32;                  // doubles per (parity, rank) s
 constexpr int MB_B_PAYLOAD = KLERG_MAX_H * KLERG_MAX_D + 2 * FUSED_MAXG;
 constexpr int MB_B_STRIDE = MB_B_PAYLOAD + 16;   // [MB_B_STRIDE-1] = flag
 constexpr size_t MB_A_BYTES = (size_t)2 * MB_MAXW * MB_A_STRIDE * sizeof(double);
-constexpr size_t MB_BYTES = MB_A_BYTES + (size_t)2 * MB_MAXW * MB_B_STRIDE * sizeof(double);
+constexpr size_t MB_EPOCH_OFF = MB_A_BYTES + (size_t)2 * MB_MAXW * MB_B_STRIDE * sizeof(double);  // u64, written by the owner only
+constexpr size_t MB_BYTES = MB_EPOCH_OFF + 64;
 
 __device__ __forceinline__ double* mb_a(void* base, int par, int r) {
   return (double*)base + (size_t)(par * MB_MAXW + r) * MB_A_STRIDE;
 }
 __device__ __forceinline__ double* mb_b(void* base, int par, int r) {
   return (double*)((char*)base + MB_A_BYTES) + (size_t)(par * MB_MAXW + r) * MB_B_STRIDE;
+}
+
+__device__ __forceinline__ unsigned long long* mb_epoch(void* base) {
+  return (unsigned long long*)((char*)base + MB_EPOCH_OFF);
 }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -85,6 +91,15 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Phase stamps (clock64 at the phase boundaries of eval_grad_kernel) are compiled in with -DKLERG_STAMPS.
+#ifdef KLERG_STAMPS
+#define KLERG_STAMP_DECL long long stamp[8]
+#define KLERG_STAMP(i) stamp[i] = clock64()
+#else
+#define KLERG_STAMP_DECL
+#define KLERG_STAMP(i)
+#endif
 
 struct Peers {
   int world, rank;
@@ -150,7 +165,8 @@ __device__ __forceinline__ void block_reduce(const int (&kind)[NQ], double (&val
 // Meeting point 1: every CTA has written part_tot[blk][g][2]; on return world_tot[g][2]
 // (all CTAs, all ranks) is readable by every thread.  The last CTA to arrive is the leader.
 // ---------------------------------------------------------------------------
-__device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_flag, double* sh_world /* [2G] */) {
+__device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, unsigned mepoch, int* sh_flag,
+                            double* sh_world /* [2G] */) {
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   const unsigned nblk = gridDim.x;
   const double* part = ws_fused_tot(a.ws);
@@ -185,7 +201,7 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_fl
   // several ranks: the last CTA to arrive combines, exchanges with the peers over NVLink and publishes
   const unsigned go_val = 2u * epoch + 1u;
   double* world = ws_fused_world(a.ws);
-  const int par = epoch & 1;
+  const int par = mepoch & 1;
   const int nq = 2 * G;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -215,10 +231,10 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, int* sh_fl
       __syncwarp();
       if (lane < a.peers.world) {
         st_release_sys_u64((unsigned long long*)&mb_a(a.peers.mail[lane], par, a.peers.rank)[MB_A_STRIDE - 1],
-                           (unsigned long long)epoch + 1ull);
+                           (unsigned long long)mepoch + 1ull);
         const unsigned long long* f =
             (const unsigned long long*)&mb_a(a.peers.mail[a.peers.rank], par, lane)[MB_A_STRIDE - 1];
-        KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)epoch + 1ull, ctrl)
+        KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)mepoch + 1ull, ctrl)
       }
       __syncwarp();
       if (lane < nq) {
@@ -258,9 +274,9 @@ __device__ bool meet_last(const EvalArgs& a, int* sh_flag) {
 
 // Cross-rank all-gather of `n` doubles held in shared memory (sh_vals) by the last CTA:
 // on return sh_vals[i] = sum over ranks (rank order) of the ranks' sh_vals[i].
-__device__ void exchange_sum(const EvalArgs& a, unsigned epoch, double* sh_vals, int n) {
+__device__ void exchange_sum(const EvalArgs& a, unsigned mepoch, double* sh_vals, int n) {
   if (a.peers.world <= 1) return;
-  const int par = epoch & 1;
+  const int par = mepoch & 1;
   __syncthreads();
   for (int e = threadIdx.x; e < n * a.peers.world; e += blockDim.x) {
     const int r = e / n, i = e - r * n;
@@ -270,11 +286,11 @@ __device__ void exchange_sum(const EvalArgs& a, unsigned epoch, double* sh_vals,
   __syncthreads();
   if ((int)threadIdx.x < a.peers.world) {
     st_release_sys_u64((unsigned long long*)&mb_b(a.peers.mail[threadIdx.x], par, a.peers.rank)[MB_B_STRIDE - 1],
-                       (unsigned long long)epoch + 1ull);
+                       (unsigned long long)mepoch + 1ull);
     const unsigned long long* f =
         (const unsigned long long*)&mb_b(a.peers.mail[a.peers.rank], par, threadIdx.x)[MB_B_STRIDE - 1];
     unsigned* ctrl = ws_fused_ctrl(a.ws);
-    KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)epoch + 1ull, ctrl)
+    KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)mepoch + 1ull, ctrl)
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -379,7 +395,7 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.tile = o;  o = align16(o + tile);
   p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
   p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
-  p.misc = o;  o = align16(o + 64);
+  p.misc = o;  o = align16(o + 16 + sizeof(float) * (KLERG_MAX_S + 9));
   p.total = o;
   return p;
 }
@@ -408,14 +424,20 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   float* s_bsum = (float*)(smem + sp.misc) + 2;
   constexpr int DP = Row2<D>::DP;
 
-  long long stamp[8];
-  stamp[0] = clock64();
+  KLERG_STAMP_DECL;
+  KLERG_STAMP(0);
   // ---- phase 0: rollout (every CTA) ---------------------------------------------------------------
+  float* s_x0 = (float*)(smem + sp.misc) + 4;  // [S] (+ [9] R0)
   for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
-  if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
+  if (tid < S) s_x0[tid] = a.x0[tid];
+  if (a.R0 && tid >= 32 && tid < 41) s_x0[KLERG_MAX_S + tid - 32] = a.R0[tid - 32];
+  if (tid == 0) {
+    s_epoch[0] = ws_fused_ctrl(a.ws)[3];
+    s_epoch[2] = a.peers.world > 1 ? (unsigned)*mb_epoch(a.peers.mail[a.peers.rank]) : 0u;
+  }
   __syncthreads();
-  rollout_block(a.d, a.bar, a.x0, a.R0, s_u, 1, H, s_traj, s_dbarr, s_P, s_tile, (float*)s_red, s_bsum, nullptr);
-  const unsigned epoch = *s_epoch;
+  rollout_block(a.d, a.bar, s_x0, a.R0 ? s_x0 + KLERG_MAX_S : nullptr, s_u, 1, H, s_traj, s_dbarr, s_P, s_tile, (float*)s_red, s_bsum, nullptr);
+  const unsigned epoch = s_epoch[0], mepoch = s_epoch[2];
   for (int e = tid; e < H * DP; e += blockDim.x) {
     const int t = e / DP, d = e - t * DP;
     float v = 0.f;
@@ -429,7 +451,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     for (int e = tid; e < (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
   __syncthreads();
 
-  stamp[1] = clock64();
+  KLERG_STAMP(1);
   // ---- phase 1: forward pair pass, slice totals -------------------------------------------------
   int64_t lo, hi;
   cta_slice(a.N, a.ld, lo, hi);
@@ -445,10 +467,10 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
       part[1] = vals[1];
     }
   }
-  stamp[2] = clock64();
+  KLERG_STAMP(2);
   double* s_world = s_red + 32 * 2;  // [2]
-  meet_totals(a, 1, epoch, s_flag, s_world);
-  stamp[3] = clock64();
+  meet_totals(a, 1, epoch, mepoch, s_flag, s_world);
+  KLERG_STAMP(3);
   const double vsum = s_world[0];
   const double vmax = s_world[1];
   if (blockIdx.x == 0 && tid == 0 && a.totals) {
@@ -558,18 +580,18 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
         if (lane == 0) s_part[(warp * WT + k) * D + d] = v;
       }
     __syncthreads();
-    double* gpart = ws_fused_grad(a.ws);
+    float* gpart = (float*)ws_fused_grad(a.ws);  // [H*D][gstride] fp32 (the CTA sums are fp32 values)
     for (int e = tid; e < a.nchr * WT * D; e += blockDim.x) {
       const int c = e / (WT * D), kd = e - c * (WT * D);
       const int t = (r * a.nchr + c) * WT + kd / D;
       if (t < H) {
         float v = 0.f;
         for (int sb = 0; sb < a.nsub; ++sb) v += s_part[((sb * a.nchr + c) * WT) * D + kd];
-        gpart[(size_t)(t * D + kd % D) * gstride + blockIdx.x] = (double)v;
+        gpart[(size_t)(t * D + kd % D) * gstride + blockIdx.x] = v;
       }
     }
   }
-  {
+  if (want_kl) {
     const int kinds[2] = {RED_SUM, RED_SUM};
     double vals[2] = {kl_a, kl_c};
     block_reduce<2>(kinds, vals, s_red);
@@ -581,36 +603,59 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   }
 
   // ---- phase 3: the last CTA reduces the partials and runs the adjoint --------------------------------
-  stamp[4] = clock64();
+  KLERG_STAMP(4);
   if (!meet_last(a, s_flag)) return;
-  stamp[5] = clock64();
+  KLERG_STAMP(5);
   double* s_val = (double*)s_tile;               // [HD + 2]
   float* s_g = (float*)(s_val + HD + 2);         // [H][S]
   float* s_scr = s_g + H * S;                    // adjoint scratch
   {
-    // 4 lanes per entry, each summing every 4th CTA partial (independent loads), then a 2-step shuffle tree
-    const double* gpart = ws_fused_grad(a.ws);
-    const double* klp = ws_fused_kl(a.ws);
-    const int n4 = (HD + 2) * 4;
-    for (int idx = tid; idx < ((n4 + 31) & ~31); idx += blockDim.x) {  // whole warps take part in the shuffles
-      const int e = idx >> 2, part = idx & 3;
+    // 8 lanes per entry, each summing float4 groups of CTA partials in double (independent loads), then a
+    // 3-step shuffle tree: fixed order, so the result does not depend on which CTA arrived last
+    const float* gpart = (const float*)ws_fused_grad(a.ws);
+    const int n8 = HD * 8;
+    for (int idx = tid; idx < ((n8 + 31) & ~31); idx += blockDim.x) {  // whole warps take part in the shuffles
+      const int e = idx >> 3, part = idx & 7;
       double v = 0.0;
-      if (idx >= n4) {
-      } else if (e < HD) {
-#pragma unroll 8
-        for (int b = part; b < nblk; b += 4) v += __ldcg(&gpart[(size_t)e * gstride + b]);
-      } else {
-#pragma unroll 8
-        for (int b = part; b < nblk; b += 4) v += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + (e - HD)]);
+      if (idx < n8) {
+        const float* row = gpart + (size_t)e * gstride;
+#pragma unroll 4
+        for (int b = part * 4; b < nblk; b += 32) {
+          const float4 x = __ldcg(reinterpret_cast<const float4*>(row + b));
+          v += (double)x.x;
+          if (b + 1 < nblk) v += (double)x.y;
+          if (b + 2 < nblk) v += (double)x.z;
+          if (b + 3 < nblk) v += (double)x.w;
+        }
       }
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (part == 0 && idx < n4) s_val[e] = v;
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      if (part == 0 && idx < n8) s_val[e] = v;
+    }
+    if (want_kl) {
+      const double* klp = ws_fused_kl(a.ws);
+      if (warp == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int b = lane; b < nblk; b += 32) {
+          s0 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 0]);
+          s1 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 1]);
+        }
+        s0 = warp_reduce(RED_SUM, s0);
+        s1 = warp_reduce(RED_SUM, s1);
+        if (lane == 0) {
+          s_val[HD] = s0;
+          s_val[HD + 1] = s1;
+        }
+      }
+    } else if (tid == 0) {
+      s_val[HD] = 0.0;
+      s_val[HD + 1] = 1.0;
     }
   }
   __syncthreads();
-  stamp[6] = clock64();
-  exchange_sum(a, epoch, s_val, HD + 2);
+  KLERG_STAMP(6);
+  exchange_sum(a, mepoch, s_val, HD + 2);
   for (int e = tid; e < H * S; e += blockDim.x) s_g[e] = 0.f;
   __syncthreads();
   for (int e = tid; e < HD; e += blockDim.x) {
@@ -640,10 +685,13 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     ctrl[0] = 0;
     ctrl[1] = 0;
     ctrl[3] = epoch + 1;
-    // phase stamps of the CTA that finished last (SM cycles since its start): debugging / profiling aid
-    stamp[7] = clock64();
+    if (a.peers.world > 1) *mb_epoch(a.peers.mail[a.peers.rank]) = (unsigned long long)mepoch + 1ull;
+#ifdef KLERG_STAMPS
+    // phase stamps of the CTA that finished last (SM cycles since its start): profiling aid
+    KLERG_STAMP(7);
     long long* dbg = (long long*)(ctrl + 16);
     for (int i = 0; i < 8; ++i) dbg[i] = stamp[i] - stamp[0];
+#endif
   }
 }
 
@@ -680,11 +728,14 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
   constexpr int DP = Row2<D>::DP;
 
   for (int e = tid; e < G * H * A; e += blockDim.x) s_u[e] = a.u[e];
-  if (tid == 0) *s_epoch = ws_fused_ctrl(a.ws)[3];
+  if (tid == 0) {
+    s_epoch[0] = ws_fused_ctrl(a.ws)[3];
+    s_epoch[2] = a.peers.world > 1 ? (unsigned)*mb_epoch(a.peers.mail[a.peers.rank]) : 0u;
+  }
   __syncthreads();
   rollout_block(a.d, a.bar, a.x0, a.R0, s_u, G, H, s_traj, nullptr, nullptr, (float*)(smem + sp.tile), (float*)s_red,
                 s_bsum, nullptr);
-  const unsigned epoch = *s_epoch;
+  const unsigned epoch = s_epoch[0], mepoch = s_epoch[2];
   for (int e = tid; e < G * H * DP; e += blockDim.x) {
     const int g = e / (H * DP), r = e - g * (H * DP);
     const int t = r / DP, d = r - t * DP;
@@ -711,7 +762,7 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
     }
   }
   double* s_world = s_red + 32 * 2;  // [2G]
-  meet_totals(a, G, epoch, s_flag, s_world);
+  meet_totals(a, G, epoch, mepoch, s_flag, s_world);
   if (blockIdx.x == 0 && tid < 2 * G && a.totals) a.totals[tid] = s_world[tid];
 
   // KL partials: sum_i p_i (log p_i - log c_i), sum_i c_i   (klerg.py:694-699 in closed form)
@@ -778,7 +829,7 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
     }
   }
   __syncthreads();
-  exchange_sum(a, epoch, s_val, 2 * G);
+  exchange_sum(a, mepoch, s_val, 2 * G);
   if (tid < G) {
     const double spv = a.p_stats[0];
     const double dkl = s_val[2 * tid] / spv - log(spv) + log(s_val[2 * tid + 1]);
@@ -789,6 +840,7 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
     ctrl[0] = 0;
     ctrl[1] = 0;
     ctrl[3] = epoch + 1;
+    if (a.peers.world > 1) *mb_epoch(a.peers.mail[a.peers.rank]) = (unsigned long long)mepoch + 1ull;
   }
 }
 
@@ -965,6 +1017,53 @@ static bool fill_common(EvalArgs& a, const klerg_kernel_spec* k, const klerg_dyn
 using namespace klerg;
 
 extern "C" size_t klerg_mailbox_bytes(void) { return MB_BYTES; }
+
+// Mailboxes are plain cudaMalloc allocations shared between the one-process-per-GPU ranks with CUDA IPC.
+extern "C" int klerg_mailbox_create(void** ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is exchanged as 64 bytes");
+  if (!ptr || !handle64) { set_error("mailbox_create: null argument"); return -1; }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, MB_BYTES);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, MB_BYTES);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("mailbox_create: %s", cudaGetErrorString(e));
+    if (p) cudaFree(p);
+    cudaGetLastError();
+    return -4;
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return 0;
+}
+
+extern "C" int klerg_mailbox_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) { set_error("mailbox_open: null argument"); return -1; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    set_error("mailbox_open: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return -4;
+  }
+  *ptr = p;
+  return 0;
+}
+
+extern "C" int klerg_mailbox_close(void* ptr, int owner) {
+  if (!ptr) return 0;
+  cudaError_t e = owner ? cudaFree(ptr) : cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) {
+    set_error("mailbox_close: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return -4;
+  }
+  return 0;
+}
 extern "C" size_t klerg_fused_fault_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 5 * sizeof(unsigned); }
 extern "C" size_t klerg_debug_stamps_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 64; }
 

@@ -218,6 +218,13 @@ typedef struct klerg_peers {
   void* mailbox[8];
 } klerg_peers;
 size_t klerg_mailbox_bytes(void);
+/* Mailbox plumbing for one-process-per-GPU ranks (CUDA IPC): create allocates and zero-fills this
+ * rank's mailbox and returns its 64-byte IPC handle (host memory) to be sent to the peers by any
+ * means (e.g. torch.distributed.all_gather_object); open maps a peer's mailbox; close unmaps /
+ * frees.  The reference has no equivalent (single process, CPU). */
+int klerg_mailbox_create(void** ptr, unsigned char* handle64);
+int klerg_mailbox_open(const unsigned char* handle64, void** ptr);
+int klerg_mailbox_close(void* ptr, int owner);
 /* Byte offset inside `workspace` of 8 int64 SM-cycle stamps left by the last klerg_eval_gradient
  * (start, rollout, forward, meet-1, gradient, meet-2, reduce, end; relative to start). */
 size_t klerg_debug_stamps_offset(void);

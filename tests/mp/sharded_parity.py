@@ -1,0 +1,97 @@
+"""Sample-sharded fused evals vs the single-GPU result (run under torchrun, one rank per GPU).
+
+Every rank owns a contiguous slice of the workspace samples; the totals of q and the
+gradient partials cross NVLink inside the fused kernels (peer mailboxes).  Rank 0 also
+evaluates the whole workspace on its own and all ranks must agree with it.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "embodied-active-learning-vision_b200")]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import workloads as wl  # noqa: E402
+from control_torch import engine  # noqa: E402
+from control_torch.klerg import Robot  # noqa: E402
+from control_torch.planner import PlannerContext  # noqa: E402
+
+
+def build_ctx(probe, group, smp, p_raw, lo, hi, n_total, hist, x0, H, fused=True):
+    ctx = PlannerContext(probe.planner.spec, probe.barrier.spec(), probe.explr_locs.tolist(), H,
+                         torch.diagonal(probe.R_inv).tolist(), probe.control_lim[:, 0].tolist(),
+                         probe.control_lim[:, 1].tolist(), alpha=1.0, group=group, fused=fused)
+    ctx.set_samples(smp, probe.std.tolist(), 1.0)
+    ctx.set_state(x0)
+    p, p_stats, _ = engine.target_weight(2, smp, lo.tolist(), hi.tolist(), None, p_raw, n_total, 1.0, True, group)
+    ctx.set_target(p, p_stats)
+    ctx.set_history(hist)
+    return ctx
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    n_total = int(sys.argv[2]) if len(sys.argv) > 2 else 100_003
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    group = engine.ShardGroup(dist.group.WORLD)
+    w = wl.WORKLOADS[name]
+    lims = [wl.LIMS[s] for s in w["states"]]
+    D, H = len(lims), w["H"]
+    target = wl.make_target("gmm", lims, seed=1, device=dev)
+    kw = wl.robot_kwargs(name, target, n_samples=n_total)
+    probe = Robot(process_group=None, **kw)
+    g = torch.Generator().manual_seed(0)
+    lo = torch.tensor([a for a, _ in lims]) * 1.15
+    hi = torch.tensor([b for _, b in lims]) * 1.15
+    smp_all = (lo + torch.rand(n_total, D, generator=g) * (hi - lo)).to(dev)
+    p_all = target.pdf_torch(smp_all).contiguous()
+    hist = wl.random_walk_history(name, min(w["M"], 2000)).to(dev)
+    x0 = torch.tensor(kw["x0"], dtype=torch.float32, device=dev)
+    a, b = group.shard_bounds(n_total)
+    ctx = build_ctx(probe, group, smp_all[a:b].contiguous(), p_all[a:b].contiguous(), lo, hi, n_total, hist, x0, H)
+    U = wl.random_controls((5, H, D), seed=3).to(dev)
+    ok = True
+    for it in range(3):  # several evals: mailbox epochs / parity buffers must keep working
+        c = ctx.costs(U)
+        gr = ctx.gradient(U[it], keep=True)
+        torch.cuda.synchronize()
+        got = dict(cost=c, du=gr["du"], dj=gr["djdlam"], us=gr["u_star"], dgdx=gr["dgdx"], tot=gr["totals"].reshape(-1))
+        # all ranks must hold identical results (they drive identical host control flow)
+        for k, v in got.items():
+            ref = v.clone()
+            dist.broadcast(ref, 0)
+            if not torch.equal(ref, v):
+                print(f"[rank {rank}] {k} differs from rank 0 (max abs {float((ref - v).abs().max())})")
+                ok = False
+        if rank == 0:
+            single = build_ctx(probe, engine.SINGLE, smp_all, p_all, lo, hi, n_total, hist, x0, H)
+            c1 = single.costs(U)
+            g1 = single.gradient(U[it], keep=True)
+            want = dict(cost=c1, du=g1["du"], dj=g1["djdlam"], us=g1["u_star"], dgdx=g1["dgdx"],
+                        tot=g1["totals"].reshape(-1))
+            for k in want:
+                x, y = got[k].double().cpu().numpy(), want[k].double().cpu().numpy()
+                err = np.abs(x - y).max() / (np.abs(y).max() + 1e-30)
+                print(f"iter {it} {k}: max err / max|ref| = {err:.3e}")
+                if not err < 1e-5:
+                    ok = False
+        dist.barrier()
+    if engine.fused_fault():
+        print(f"[rank {rank}] fused eval reported a meeting-point fault")
+        ok = False
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    if rank == 0:
+        print("SHARDED_PARITY", "OK" if flag.item() == 0 else "FAIL", f"world={world} n_total={n_total} workload={name}")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,13 @@ for fused in (False, True):
     c = ctx.costs(U)
     gr = ctx.gradient(U[0], keep=True)
     torch.cuda.synchronize()
+    if fused and os.environ.get("PROFILE"):
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        ctx.gradient(U[0])
+        ctx.costs(U)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if fused:
         for _ in range(5):
             ctx.gradient(U[0])
