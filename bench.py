@@ -5,23 +5,26 @@
   python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on the host CPU
 
 Metric: state-sample pairs/s (BASELINE.json "metric"); evals/s is printed beside it.
-A *step* is one planner eval on one batch of synthetic input:
-rollout + barrier -> footprint of the H planned states over the N workspace samples
-(+ cached history footprint) -> renormalise -> KL -> importance ratio -> gradient for
-all H states -> adjoint -> du, djdlam, u*.  2*H*N pairs per eval.
+A *step* is one fused planner eval on one batch of synthetic input:
+rollout + barrier -> footprint of the H planned states over the workspace samples
+(+ cached history footprint) -> renormalise -> importance ratio -> gradient for all H
+states -> adjoint -> du, djdlam, u*.  2*H*N pairs per eval, ONE kernel launch.
 
-Workload (N=1): config[1] of BASELINE.json = "c2": 3-D xyz workspace, horizon 50, 1e5
-samples, 3000 history rows, p from a random-init VAE-style uncertainty head.  With
-N GPUs every rank owns 1e5 samples of an N*1e5-sample workspace (weak scaling) and
-the per-eval totals / gradient partials cross NVLink in two small all-gathers.
+Workload: "c4" = configs[3] of BASELINE.json, the 1e7-sample 6-D end-effector-pose
+workspace the north_star quotes its roofline / scaling target on (H=50, 1e5-state
+memory buffer).  It fits one GPU; with N GPUs the SAME 1e7 samples are sharded
+(strong scaling) and the totals / gradient partials cross NVLink inside the kernel.
+The other configs are reachable with --workload (c2 numbers ride along under "also").
 
-`value`     inputs resident in HBM; K evals replayed from a CUDA graph over a ring of
-            independent input sets larger than L2; timed with CUDA events.
+`value`     inputs resident in HBM; K evals replayed from a CUDA graph over >= 2
+            independent input sets (each larger than L2); timed with CUDA events.
 `e2e`       the same metric through the reference-shaped public API (`Robot.step()`):
             host RNG samples -> H2D, target density, full planner step, D2H of the plan.
-`roofline`  dominant kernel alone, CUDA events, against the measured FP32/MUFU issue peaks.
+`roofline`  the fused eval kernel (the only kernel in the timed region), against the
+            FP32-pipe / MUFU peaks measured on this box with the library's probes.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -35,25 +38,28 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-import numpy as np  # noqa: E402
+import numpy as np  # noqa: E402,F401
 import torch  # noqa: E402
 
 import workloads as wl  # noqa: E402
 
 L2_BYTES = 126 * 2 ** 20
+METRIC = "klerg_state_sample_pairs_per_s"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(wl.WORKLOADS))
-    ap.add_argument("--samples", type=int, default=0, help="override samples per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--workload", default="c4", choices=list(wl.WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="override the workspace size (total samples)")
+    ap.add_argument("--weak", action="store_true", help="--samples per GPU instead of sharding a fixed workspace")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary c2 measurement")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-evals", type=int, default=0,
                     help="run this many eager evals inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
@@ -102,26 +108,34 @@ def reference_arm(args):
         return
     w = wl.WORKLOADS[args.workload]
     n_full = args.samples or w["N"]
-    m = min(w["M"], 3000)
-    # bounded sample: probe one step at reduced size, then pick N so K steps fit ~150 s
-    probe_n = min(n_full, 10_000)
+    m = min(w["M"], 1000)
+    # bounded sample: probe one step at reduced size, then pick N so that all steps fit ~120 s
+    probe_n = min(n_full, 4_000)
     probe = run_oracle_steps(args.workload, probe_n, m, 1, 1)
     rate = probe["pairs"] / probe["seconds"]
     per_step_pairs_full = probe["pairs"] * (n_full / probe_n)
     budget = 150.0
-    n = n_full
-    if per_step_pairs_full / rate * (args.steps + args.warmup) > budget:
-        n = int(max(1000, min(n_full, n_full * budget / (per_step_pairs_full / rate * (args.steps + args.warmup)))))
-    res = run_oracle_steps(args.workload, n, m, args.steps, args.warmup)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    n_min = min(n_full, 500)
+    t_full = per_step_pairs_full / rate  # seconds of one full-size Robot.step() on these cores
+    n = int(max(n_min, min(n_full, n_full * budget / (t_full * (steps + warm)))))
+    t_n = t_full * n / n_full
+    if t_n * (steps + warm) > 1.5 * budget:  # even the smallest sample does not fit K steps: time fewer steps, say so
+        steps = max(1, int(1.5 * budget / t_n) - warm)
+    res = run_oracle_steps(args.workload, n, m, steps, warm)
     value = res["pairs"] / res["seconds"]
-    sample = (f"{args.steps} full Robot.step() calls of the oracle port (torch CPU fp32) at N={n} samples "
-              f"(workload {args.workload} has N={n_full}), M={m}")
+    clamp = "" if steps == max(1, args.steps) else f" ({args.steps} steps requested; clamped to fit the time budget)"
+    sample = (f"{steps}{clamp} full Robot.step() calls of the oracle port (torch CPU fp32, all host threads) at N={n} samples "
+              f"(workload {args.workload} has N={n_full}), M={m}; the reference itself is Python and cannot travel to "
+              f"the GPU box, the port is pinned to it by tests/golden")
     line = {
-        "impl": "reference", "metric": "klerg_state_sample_pairs_per_s", "value": value, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": res["seconds"] / max(res["steps"], 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": res["seconds"] / max(res["steps"], 1) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_per_gpu=n, note="host CPU, oracle port of control_torch"),
+        "config": workload_config(args.workload, n_total=n, n_local=n,
+                                  note="host CPU, oracle port of control_torch; a step here is one whole Robot.step() "
+                                       "(history + spread + ~13 evals)"),
         "evals_per_s": res["evals"] / res["seconds"],
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -130,11 +144,14 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(args, n_per_gpu, note=""):
-    w = wl.WORKLOADS[args.workload]
-    return {"workload": f"{args.workload}: states={w['states']} H={w['H']} N={n_per_gpu}/GPU M={w['M']} "
+def workload_config(name, n_total, n_local, note=""):
+    w = wl.WORKLOADS[name]
+    big = n_local * 4 * (len(w["states"]) + 3) > L2_BYTES
+    return {"workload": f"{name}: states={w['states']} H={w['H']} N={n_total} (per GPU {n_local}) M={w['M']} "
                         f"target={w['target']} barrier=on R=0.5 dt=0.2",
-            "pairs_per_eval": 2 * w["H"] * n_per_gpu, "l2_policy": "ring of independent input sets > 126 MB L2",
+            "pairs_per_eval": 2 * w["H"] * n_total,
+            "l2_policy": ("alternating independent input sets, each larger than the 126 MB L2" if big else
+                          "ring of independent input sets, together larger than the 126 MB L2"),
             "note": note}
 
 
@@ -206,156 +223,129 @@ def time_events(fn, reps):
     return start.elapsed_time(end) / reps  # ms
 
 
-def graph_time(fn, reps):
-    """ms per call of `fn` with launch gaps removed: `reps` calls captured in one CUDA graph."""
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    gr = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        fn()
-        with torch.cuda.graph(gr, stream=side):
-            keep = [fn() for _ in range(reps)]
-    torch.cuda.current_stream().wait_stream(side)
-    gr.replay()
-    ms = min(time_events(gr.replay, 2) for _ in range(3)) / reps
-    del keep
-    return ms
-
-
 def measure_peaks(cabi, sms):
-    """FFMA and MUFU.EX2 issue rates (ops/s) measured on this box: roofline denominators."""
+    """Lane-op rates measured on this box (roofline denominators): scalar FFMA, packed FFMA2, MUFU.EX2."""
     lib = cabi.load()
     out = torch.zeros(4, device="cuda")
     res = {}
-    for kind, name in ((0, "ffma_per_s"), (1, "ex2_per_s")):
+    for kind, name, lanes in ((0, "ffma_per_s", 1), (2, "ffma2_lane_ops_per_s", 2), (1, "ex2_per_s", 1)):
         iters, blocks = 2000, sms * 8
-        f = lambda: cabi.check(lib.klerg_peak_probe(kind, iters, blocks, cabi.ptr(out), cabi.stream_ptr()), "peak")
+        f = lambda: cabi.check(lib.klerg_peak_probe(kind, iters, blocks, cabi.ptr(out), cabi.stream_ptr()), "peak")  # noqa: E731
         f()
         ms = min(time_events(f, 3) for _ in range(3))
-        res[name] = blocks * 256 * iters * 64 / (ms * 1e-3)
+        res[name] = blocks * 256 * iters * 64 * lanes / (ms * 1e-3)
+    res["fp32_lane_ops_per_s"] = max(res["ffma_per_s"], res["ffma2_lane_ops_per_s"])
     return res
 
 
-def roofline_time(D, kind, pairs, peaks, bytes_moved, hbm_gbs):
-    """Seconds at the issue roofline: minimal instruction mix of one pair
-    forward: D FADD + D FFMA + 1 FADD on the FP32 pipes + 1 MUFU.EX2; gradient: + 1 FMUL + D FFMA."""
-    fp32 = (2 * D + 1) if kind == "forward" else (3 * D + 1)
-    t_fp32 = pairs * fp32 / peaks["ffma_per_s"]
-    t_mufu = pairs * 1 / peaks["ex2_per_s"]
-    t_issue = pairs * (fp32 + 1) / peaks["ffma_per_s"]  # one issue slot per warp instruction, 4 schedulers/SM
-    t_hbm = bytes_moved / (hbm_gbs * 1e9)
-    terms = {"fp32": t_fp32, "mufu": t_mufu, "issue": t_issue, "hbm": t_hbm}
-    bound = max(terms, key=terms.get)
-    return terms[bound], bound, terms
+def eval_roofline(D, H, n_local, peaks, hbm_gbs):
+    """Seconds one fused eval needs at the roofline, with the minimal instruction mix of a pair
+    (DESIGN.md): forward D FADD + 1 FMUL + (D-1) FFMA + 1 FADD = 2D+1 lane-ops + 1 MUFU.EX2;
+    gradient D FADD + 1 FMUL + (D-1) FFMA + 1 FMUL + D FFMA = 3D+1 lane-ops + 1 MUFU.EX2."""
+    pairs = H * n_local
+    fp32, mufu = peaks["fp32_lane_ops_per_s"], peaks["ex2_per_s"]
+    t_fwd = max(pairs * (2 * D + 1) / fp32, pairs / mufu)
+    t_grad = max(pairs * (3 * D + 1) / fp32, pairs / mufu)
+    bytes_fwd = n_local * 4 * (D + 2)        # samples + q_base in, q out
+    bytes_grad = n_local * 4 * (D + 2)       # samples + q + p in
+    t_hbm = (bytes_fwd + bytes_grad) / (hbm_gbs * 1e9)
+    bound = "fp32+mufu"
+    t = t_fwd + t_grad
+    if t_hbm > t:
+        t, bound = t_hbm, "hbm"
+    flops = pairs * (4 * D + 1) + pairs * (6 * D + 1)  # algorithmic flop per pair, SURVEY.md 8(d)
+    return dict(seconds=t, bound=bound, flops=flops, bytes=bytes_fwd + bytes_grad,
+                fwd_bound="mufu" if pairs / mufu > pairs * (2 * D + 1) / fp32 else "fp32",
+                grad_bound="mufu" if pairs / mufu > pairs * (3 * D + 1) / fp32 else "fp32")
 
 
-def cuda_arm(args):
-    from control_torch import _cabi as cabi
-    from control_torch import engine
-    from control_torch.klerg import Robot
-    from control_torch.planner import PlannerContext
-
-    cabi.load()
-    world, rank, local, pg = dist_setup(args)
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    group = engine.ShardGroup(pg)
-    dev = torch.device("cuda", local)
-    lib = cabi.load()
-    import ctypes as C
-    sms = C.c_int()
-    lib.klerg_device_info(C.byref(sms), None, None)
-    sms = sms.value
-
-    w = wl.WORKLOADS[args.workload]
+def build_sets(name, n_total, rank, group, dev, engine, Robot, PlannerContext, max_sets=96):
+    """Independent input sets (samples, p, q_base, u) resident in HBM; every rank holds its slice."""
+    w = wl.WORKLOADS[name]
     st = w["states"]
     D, H = len(st), w["H"]
-    n = args.samples or w["N"]  # per GPU (weak scaling)
-    m = w["M"]
     lims = [wl.LIMS[s] for s in st]
-    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    hbm_gbs, hbm_src = 6650.0, "fallback"
-    if os.path.exists(peaks_file):
-        hbm_gbs, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured"
-
-    # ---- inputs: a ring of independent (samples, p, q_base, u) sets larger than L2 ------------
     target = wl.make_target(w["target"], lims, seed=1, device=dev)
-    kw = wl.robot_kwargs(args.workload, target, n_samples=n * world)
-    torch.manual_seed(1234 + rank)
+    kw = wl.robot_kwargs(name, target, n_samples=n_total)
+    torch.manual_seed(1234)
     probe = Robot(process_group=None, **kw)  # only used to build specs (dyn, barrier, limits)
+    lo_i, hi_i = group.shard_bounds(n_total)
+    n = hi_i - lo_i
     bytes_per_set = engine.padded(n) * 4 * (D + 3)
-    n_sets = min(96, max(2, int(L2_BYTES * 1.5 / bytes_per_set) + 1))
-    hist = wl.random_walk_history(args.workload, m, seed=rank).to(dev)
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    n_sets = min(max_sets, max(2, int(L2_BYTES * 1.5 / bytes_per_set) + 1))
+    hist = wl.random_walk_history(name, w["M"], seed=0).to(dev)
     lo = torch.tensor([a for a, _ in lims]) * 1.15
     hi = torch.tensor([b for _, b in lims]) * 1.15
-    sets = []
     x0 = torch.tensor(kw["x0"], dtype=torch.float32, device=dev)
+    sets = []
     for s in range(n_sets):
         ctx = PlannerContext(probe.planner.spec, probe.barrier.spec(), probe.explr_locs.tolist(), H,
                              torch.diagonal(probe.R_inv).tolist(), probe.control_lim[:, 0].tolist(),
                              probe.control_lim[:, 1].tolist(), alpha=1.0, group=group)
-        smp = (lo + torch.rand(n, D, generator=g) * (hi - lo)).to(dev)
+        g = torch.Generator(device=dev).manual_seed(100 + 17 * s + rank)
+        smp = lo.to(dev) + torch.rand(n, D, generator=g, device=dev) * (hi - lo).to(dev)
         ctx.set_samples(smp, probe.std.tolist(), 1.0)
         ctx.set_state(x0)
-        p_raw = target.pdf_torch(smp).contiguous()
-        p, p_stats, _ = engine.target_weight(2, smp, lo.tolist(), hi.tolist(), None, p_raw, n * world, 1.0, True, group)
+        p_raw = torch.cat([target.pdf_torch(c) for c in smp.split(1_000_000)]).contiguous()
+        p, p_stats, _ = engine.target_weight(2, smp, lo.tolist(), hi.tolist(), None, p_raw, n_total, 1.0, True, group)
         ctx.set_target(p, p_stats)
         ctx.set_history(hist)
         ctx.samples = None  # raw samples are not read by an eval
-        ctx.u = wl.random_controls((H, D), seed=1000 * rank + s).to(dev)
+        ctx.buf.v_costs = None  # candidate scratch is not needed for gradient evals
+        ctx.u = wl.random_controls((H, D), seed=1000 + s).to(dev)
         sets.append(ctx)
-    del smp, p_raw
+        del smp, p_raw
     torch.cuda.synchronize()
+    return dict(sets=sets, n=n, n_sets=n_sets, bytes_per_set=bytes_per_set, D=D, H=H, kw=kw, probe=probe, target=target)
+
+
+def timed_evals(args, S, K, warmup, world, rank, lib, dev):
+    """K fused evals over the ring of input sets: CUDA-graph replay, CUDA events, max over ranks."""
+    sets, n_sets = S["sets"], S["n_sets"]
 
     def eval_on(i):
         c = sets[i % n_sets]
         return c.gradient(c.u)
 
-    # ---- warm-up (eager) ------------------------------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(warmup, 3)):
         eval_on(i)
     torch.cuda.synchronize()
-
     if args.profile_evals:
-        torch.cuda.synchronize()
         torch.cuda.profiler.start()
         for i in range(args.profile_evals):
             eval_on(i)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        return
-
-    # ---- timed region: exactly K evals ----------------------------------------------------------
-    launches0 = lib.klerg_launch_count()
+        return None
     use_graph = not args.no_graph
-    graphs = []
-    K = args.steps
+    graphs, reps, rem = [], 0, 0
+    launches_per_eval = 1.0
     if use_graph:
         try:
-            cyc = min(n_sets, K)
+            cyc = min(n_sets * 4, K)
             reps, rem = divmod(K, cyc)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                engine.workspace(1)
+                for i in range(3):  # allocate this stream's workspace and warm it outside the capture
+                    eval_on(i)
+                side.synchronize()
+                c0 = lib.klerg_launch_count()
                 for length in ([cyc] + ([rem] if rem else [])):
                     gr = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(gr, stream=side):
                         keep = [eval_on(i) for i in range(length)]
                     graphs.append((gr, length, keep))
+                launches_per_eval = (lib.klerg_launch_count() - c0) / (cyc + rem)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            launches_per_eval = (lib.klerg_launch_count() - launches0) / (cyc + rem)
             for gr, _, _ in graphs:  # warm the instantiated graphs
                 gr.replay()
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
-            use_graph = False
-            graphs = []
+            use_graph, graphs = False, []
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -374,89 +364,116 @@ def cuda_arm(args):
     end.record()
     torch.cuda.synchronize()
     ms_total = start.elapsed_time(end)
-    if use_graph:
-        gpu_launches = int(round(launches_per_eval * K))
-    else:
-        gpu_launches = int(lib.klerg_launch_count() - launches1)
+    gpu_launches = int(round(launches_per_eval * K)) if use_graph else int(lib.klerg_launch_count() - launches1)
     if world > 1:
+        import torch.distributed as dist
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         dist.barrier()
-    pairs_per_eval = 2 * H * n * world
+    return dict(ms_total=ms_total, gpu_launches=gpu_launches, use_graph=use_graph)
+
+
+def cuda_arm(args):
+    from control_torch import _cabi as cabi
+    from control_torch import engine
+    from control_torch.klerg import Robot
+    from control_torch.planner import PlannerContext
+
+    lib = cabi.load()
+    world, rank, local, pg = dist_setup(args)
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    group = engine.ShardGroup(pg)
+    dev = torch.device("cuda", local)
+    sms = C.c_int()
+    lib.klerg_device_info(C.byref(sms), None, None)
+    sms = sms.value
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_gbs, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_file):
+        hbm_gbs, hbm_src = json.load(open(peaks_file))["hbm_gbs"], "measured"
+
+    w = wl.WORKLOADS[args.workload]
+    n_total = (args.samples or w["N"]) * (world if args.weak else 1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    S = build_sets(args.workload, n_total, rank, group, dev, engine, Robot, PlannerContext)
+    D, H, n = S["D"], S["H"], S["n"]
+    K = args.steps
+    res = timed_evals(args, S, K, args.warmup, world, rank, lib, dev)
+    if res is None:
+        return
+    ms_total = res["ms_total"]
+    pairs_per_eval = 2 * H * n_total
     value = pairs_per_eval * K / (ms_total * 1e-3)
     evals_per_s = K / (ms_total * 1e-3)
+    clocks = sampler.stop() if sampler else None
+    if engine.fused_fault():
+        raise SystemExit("fused eval reported a meeting-point fault; the measurement is void")
 
-    # ---- per-kernel timing and roofline (rank 0's view; single-GPU kernels) -----------------------
-    kernels = {}
-    roof = None
+    # ---- roofline of the fused eval kernel (the only kernel launched in the timed region) ------------
+    roof, peaks = None, None
     if rank == 0:
         peaks = measure_peaks(cabi, sms)
-        c0 = sets[0]
-        ro = engine.rollout(c0.dyn, c0.bar, c0.x0, c0.u, want_lin=True)
-        pre = ro["traj"][0][:H].contiguous()
-        outs = {}
-
-        def k_fwd(i=[0]):
-            c = sets[i[0] % n_sets]
-            i[0] += 1
-            outs["v"], outs["tot"] = engine.footprint(c.spec, 0, pre, c.packed, c.n, add_in=c.q_base)
-            return outs["v"]
-
-        def k_grad(i=[0]):
-            c = sets[i[0] % n_sets]
-            i[0] += 1
-            return engine.kl_gradient_fused(c.spec, pre, c.packed, c.n, outs["v"][0], outs["tot"].unsqueeze(0), c.p)
-
-        k_fwd()
-        k_grad()
-        torch.cuda.synchronize()
-        reps_k = n_sets
-        for name, fn, kind in (("footprint_kernel", k_fwd, "forward"), ("grad_kernel", k_grad, "gradient")):
-            ms = graph_time(fn, reps_k)
-            pairs = H * n
-            bytes_moved = n * 4 * (D + 2) if kind == "forward" else n * 4 * (D + 2)
-            t_roof, bound, terms = roofline_time(D, kind, pairs, peaks, bytes_moved, hbm_gbs)
-            flops_pair = (4 * D + 1) if kind == "forward" else (6 * D + 1)
-            kernels[name] = {"ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "frac_of_issue_roofline": t_roof / (ms * 1e-3),
-                             "bound": bound, "algorithmic_tflops": pairs * flops_pair / (ms * 1e-3) / 1e12,
-                             "hbm_gbs": bytes_moved / (ms * 1e-3) / 1e9}
-        dom = max(kernels, key=lambda k: kernels[k]["ms"])
-        kd = kernels[dom]
-        kind = "forward" if dom == "footprint_kernel" else "gradient"
-        flops_pair = (4 * D + 1) if kind == "forward" else (6 * D + 1)
-        peak_tflops = kd["algorithmic_tflops"] / kd["frac_of_issue_roofline"]
-        roof = {"kernel": dom, "bound": "fp32+mufu issue (" + kd["bound"] + ")", "achieved": kd["algorithmic_tflops"],
-                "peak": peak_tflops, "unit": "TFLOP/s", "frac": kd["frac_of_issue_roofline"], "traffic": None,
-                "peak_basis": (f"pairs/s at the tighter of FP32-pipe, MUFU and issue-slot limits, measured on this box: "
-                               f"FFMA {peaks['ffma_per_s']:.3e}/s, MUFU.EX2 {peaks['ex2_per_s']:.3e}/s; x {flops_pair} "
-                               f"algorithmic flop/pair (SURVEY 8d)"),
-                "hbm": {"achieved_gbs": kd["hbm_gbs"], "peak_gbs": hbm_gbs, "peak_source": hbm_src,
-                        "frac": kd["hbm_gbs"] / hbm_gbs},
+        rf = eval_roofline(D, H, n, peaks, hbm_gbs)
+        t_launch = ms_total / K * 1e-3
+        roof = {"kernel": "eval_grad_kernel (rollout + footprint + renormalize + gradient + adjoint, one launch per eval)",
+                "bound": "fp32" if rf["bound"] != "hbm" else "hbm",
+                "achieved": rf["flops"] / t_launch / 1e12, "peak": rf["flops"] / rf["seconds"] / 1e12, "unit": "TFLOP/s",
+                "frac": rf["seconds"] / t_launch, "traffic": None,
+                "launch_us": t_launch * 1e6, "roofline_us": rf["seconds"] * 1e6,
+                "peak_basis": (f"FP32-pipe and MUFU peaks measured on this box with the library's probes: packed FFMA2 "
+                               f"{peaks['ffma2_lane_ops_per_s']:.3e} lane-ops/s, scalar FFMA {peaks['ffma_per_s']:.3e}/s, "
+                               f"MUFU.EX2 {peaks['ex2_per_s']:.3e}/s; time = H*N*max((2D+1)/fp32, 1/mufu) forward "
+                               f"[{rf['fwd_bound']}-bound] + H*N*max((3D+1)/fp32, 1/mufu) gradient [{rf['grad_bound']}-bound]; "
+                               f"achieved/peak in algorithmic flop ((4D+1)+(6D+1) per state-sample pair, SURVEY 8d). "
+                               f"MEASURED_PEAKS.json holds only HBM and bf16 tensor peaks, neither of which bounds this kernel."),
+                "hbm": {"achieved_gbs": rf["bytes"] / t_launch / 1e9, "peak_gbs": hbm_gbs, "peak_source": hbm_src,
+                        "frac": rf["bytes"] / t_launch / 1e9 / hbm_gbs},
                 "measured_peaks": peaks}
+
+    # ---- secondary workload: c2 (configs[1]) evals, same protocol, short -----------------------------
+    also = None
+    if not args.no_also and args.workload != "c2":
+        n2 = wl.WORKLOADS["c2"]["N"]
+        S2 = build_sets("c2", n2, rank, group, dev, engine, Robot, PlannerContext)
+        r2 = timed_evals(args, S2, 2000, 20, world, rank, lib, dev)
+        if rank == 0:
+            rf2 = eval_roofline(S2["D"], S2["H"], S2["n"], peaks, hbm_gbs)
+            t2 = r2["ms_total"] / 2000 * 1e-3
+            also = {"c2": {"workload": workload_config("c2", n2, S2["n"])["workload"],
+                           "pairs_per_s": 2 * S2["H"] * n2 / t2, "evals_per_s": 1.0 / t2,
+                           "us_per_eval": t2 * 1e6, "roofline_frac": rf2["seconds"] / t2,
+                           "note": "1e5 samples leave ~650 samples per SM: the eval is latency-bound (launch, two grid "
+                                   "meeting points, serial rollout/adjoint), not throughput-bound"}}
+        del S2
 
     # ---- e2e: Robot.step() through the public API with host buffers ---------------------------------
     e2e = None
     if not args.no_e2e:
+        kw, m = S["kw"], w["M"]
+        del S["sets"][:]  # free the resident sets; the planner owns its buffers
+        torch.cuda.empty_cache()
         torch.manual_seed(7)
         robot = Robot(process_group=pg, **kw)
         robot.test(1000)
         for row in wl.random_walk_history(args.workload, min(m, robot.memory_buffer.capacity), seed=5):
             robot.memory_buffer.push(row)
-        n_tot = n * world
         pairs = 0
-        for k in range(3 + args.e2e_steps):
-            if k == 3:
+        nwarm = 2
+        for k in range(nwarm + args.e2e_steps):
+            if k == nwarm:
                 torch.cuda.synchronize()
                 if world > 1:
+                    import torch.distributed as dist
                     dist.barrier()
                 t0 = time.perf_counter()
                 c0_, g0_ = robot.stats["cost_evals"], robot.stats["grad_evals"]
                 pairs = 0
             m_all = len(robot.memory_buffer)
-            robot.step(n_tot, m, save_update=True)
-            if k >= 3:
-                pairs += min(m, m_all) * n_tot + m_all * n_tot
+            robot.step(n_total, m, save_update=True)
+            if k >= nwarm:
+                pairs += min(m, m_all) * n_total + m_all * n_total
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         if world > 1:
@@ -464,39 +481,42 @@ def cuda_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_e2e = float(t.item())
         ce, ge = robot.stats["cost_evals"] - c0_, robot.stats["grad_evals"] - g0_
-        pairs += (ce + 2 * ge) * H * n_tot
+        pairs += (ce + 2 * ge) * H * n_total
         steps_e = args.e2e_steps
-        h2d = n_tot // world * D * 4 + min(m, m_all) * 8 + (ce + ge) // steps_e * H * D * 4 + 2 * D * 4
+        h2d = n * D * 4 + n * 4 + min(m, m_all) * 8 + (ce + ge) // steps_e * H * D * 4 + 2 * D * 4
         d2h = (ge // steps_e) * (H * 4 + H * D * 4) + (ce // steps_e) * 4 + (H + 1) * 2 * D * 4 + 2 * D * 4
         e2e = {"value": pairs / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "control_torch.klerg.Robot.step(num_target_samples=N, num_traj_samples=M, save_update=True)",
                "steps": steps_e, "ms_per_robot_step": t_e2e / steps_e * 1e3, "evals_per_s": (ce + ge) / t_e2e,
-               "evals_per_robot_step": (ce + ge) / steps_e, "target_device": str(dev)}
-
-    clocks = sampler.stop() if sampler else None
+               "evals_per_robot_step": (ce + ge) / steps_e,
+               "note": "samples drawn by the host torch RNG (reference order) and copied H2D every step together with the "
+                       "target density values; history (M x N) and spread (M_all x N) passes included"}
 
     # ---- cpu_baseline: the oracle port on this box's host cores (rank 0, N=1 only) ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = min(n, 20_000)
-        res = run_oracle_steps(args.workload, n_cpu, min(m, 3000), 2, 1)
-        cpu = {"value": res["pairs"] / res["seconds"], "unit": "pairs/s", "cores": res["cores"], "kind": "port",
-               "sample": f"2 OracleRobot.step() calls (torch CPU fp32, all host threads) at N={n_cpu}, M={min(m, 3000)}, "
-                         f"H={H}: {res['evals']} evals in {res['seconds']:.2f} s",
-               "evals_per_s": res["evals"] / res["seconds"]}
+        n_cpu = min(n_total, 8_000 if D > 3 else 20_000)
+        m_cpu = min(w["M"], 1000)
+        r_cpu = run_oracle_steps(args.workload, n_cpu, m_cpu, 2, 1)
+        cpu = {"value": r_cpu["pairs"] / r_cpu["seconds"], "unit": "pairs/s", "cores": r_cpu["cores"], "kind": "port",
+               "sample": f"2 OracleRobot.step() calls (torch CPU fp32, all host threads) at N={n_cpu}, M={m_cpu}, "
+                         f"H={H}: {r_cpu['evals']} evals in {r_cpu['seconds']:.2f} s",
+               "evals_per_s": r_cpu["evals"] / r_cpu["seconds"]}
 
     if rank == 0:
         line = {
-            "metric": "klerg_state_sample_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n, note=("CUDA graph replay" if use_graph else "eager launches")
-                                      + f", {n_sets} input sets x {bytes_per_set / 2**20:.1f} MiB"),
-            "evals_per_s": evals_per_s, "gpu_launches": gpu_launches, "clocks": clocks, "e2e": e2e,
-            "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, n_total, n,
+                                      note=("CUDA graph replay" if res["use_graph"] else "eager launches")
+                                      + f", {S['n_sets']} input sets x {S['bytes_per_set'] / 2**20:.1f} MiB per GPU"),
+            "evals_per_s": evals_per_s, "gpu_launches": res["gpu_launches"], "clocks": clocks, "e2e": e2e,
+            "roofline": roof, "cpu_baseline": cpu, "also": also,
         }
         print(json.dumps(line))
     if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

@@ -852,16 +852,16 @@ struct GradSchedule {
   double eff;
 };
 
-static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 18 : 17); }
+static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
 
 // Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
 // CTA's warps with as few idle slots as possible.
 static GradSchedule plan_schedule(int D, int H) {
   const int maxw = grad_max_warps(D);
-  const int wts_small[4] = {5, 3, 2, 1};
+  const int wts_small[5] = {5, 4, 3, 2, 1};
   const int wts_big[3] = {3, 2, 1};
   const int* wts = D <= 4 ? wts_small : wts_big;
-  const int nw = D <= 4 ? 4 : 3;
+  const int nw = D <= 4 ? 5 : 3;
   GradSchedule best{};
   best.eff = -1.0;
   for (int i = 0; i < nw; ++i) {
@@ -950,7 +950,7 @@ static int pick_grid(int64_t N, int per_sm, int min_samples_per_cta) {
 
 template <int D, int WT>
 static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, cudaStream_t stream) {
-  constexpr int MAXT = (D <= 3 ? 20 : (D == 4 ? 18 : 17)) * 32;
+  constexpr int MAXT = (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
   auto kernel = eval_grad_kernel<D, WT, MAXT>;
   const int nthreads = s.nwarps * 32;
   const bool roll = a.d.kind == KLERG_DYN_ROLL;
@@ -975,6 +975,9 @@ static int launch_grad_d(EvalArgs& a, cudaStream_t stream) {
     case 1: return launch_grad_wt<D, 1>(a, s, stream);
     case 2: return launch_grad_wt<D, 2>(a, s, stream);
     case 3: return launch_grad_wt<D, 3>(a, s, stream);
+    case 4:
+      if constexpr (D <= 4) return launch_grad_wt<D, 4>(a, s, stream);
+      break;
     case 5:
       if constexpr (D <= 4) return launch_grad_wt<D, 5>(a, s, stream);
   }

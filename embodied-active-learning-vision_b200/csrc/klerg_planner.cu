@@ -462,12 +462,39 @@ __global__ void __launch_bounds__(256) peak_kernel(int iters, float seed, float*
   for (int i = 0; i < 8; ++i) s += a[i];
   if (s == 123.456f) out[0] = s;  // keep the chain alive
 }
+// FFMA2 (fma.rn.f32x2): two fp32 lanes per instruction, three register operands
+__global__ void __launch_bounds__(256) peak_kernel_packed(int iters, float seed, float* out) {
+  unsigned long long a[8], b[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float x = seed + 1e-3f * (float)(threadIdx.x + i);
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(a[i]) : "f"(x));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(b[i]) : "f"(0.999f + 1e-6f * (float)i));
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(c[i]) : "f"(1e-4f + 1e-6f * (float)i));
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b[i]), "l"(c[i]));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo, hi;
+    asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a[i]));
+    s += lo + hi;
+  }
+  if (s == 123.456f) out[0] = s;
+}
 }  // namespace klerg
 
 extern "C" int klerg_peak_probe(int kind, int iters, int blocks, float* out, void* stream) {
   if (kind == 0) klerg::peak_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, out);
   else if (kind == 1) klerg::peak_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, out);
-  else { set_error("peak_probe: kind 0 (FFMA) or 1 (EX2)"); return -1; }
+  else if (kind == 2) klerg::peak_kernel_packed<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0.5f, out);
+  else { set_error("peak_probe: kind 0 (FFMA), 1 (EX2) or 2 (FFMA2)"); return -1; }
   return check_launch("peak_kernel");
 }
 

@@ -77,7 +77,8 @@ int klerg_abi_version(void);
 /* Number of kernel launches issued through this library since load (bench accounting). */
 long long klerg_launch_count(void);
 /* Peak-rate probe for the roofline denominators: `blocks` CTAs x 256 threads each
- * run iters*64 dependent-chain-of-8 FFMA (kind 0) or MUFU.EX2 (kind 1) ops. */
+ * run iters*64 dependent-chain-of-8 FFMA (kind 0), MUFU.EX2 (kind 1) or packed
+ * FFMA2 (kind 2: two fp32 lanes per instruction) ops. */
 int klerg_peak_probe(int kind, int iters, int blocks, float* out, void* stream);
 /* SM count / compute capability of the current device (host out-pointers). */
 int klerg_device_info(int* sm_count, int* cc_major, int* cc_minor);
