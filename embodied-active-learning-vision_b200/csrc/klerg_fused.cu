@@ -503,26 +503,27 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     // Sample tiles stream global -> shared with cp.async, one tile ahead of the pair math:
     // rows s_0..s_{D-1} (scaled samples), q_base + q_iter (turned into the importance ratio in place), p.
     const int nt = (int)((hi - lo + ts - 1) / ts);
+    // Thread t owns 4-sample chunks t, t + blockDim, ... of a tile: it copies all rows of its chunks and, once its
+    // own copies have landed, turns v into the importance ratio for them - one CTA barrier per tile.
     auto issue_tile = [&](int k) {
       float* buf = s_tile + (size_t)(k & 1) * (D + 2) * ts;
       const int64_t base = lo + (int64_t)k * ts;
       const int cnt = (int)min((int64_t)ts, hi - base);  // multiple of 4
       const int nch = cnt >> 2;
-      for (int c = tid; c < (D + 1) * nch; c += blockDim.x) {
-        const int row = c / nch, q4 = (c - row * nch) << 2;
-        const float* src = (row < D ? a.packed + (int64_t)row * a.ld : a.v) + base + q4;
-        cp_async16(buf + (size_t)row * ts + q4, src);
-      }
-      float* prow = buf + (size_t)(D + 1) * ts;
       for (int c = tid; c < nch; c += blockDim.x) {
-        const int64_t i = base + ((int64_t)c << 2);
+        const int q4 = c << 2;
+        const int64_t i = base + q4;
+#pragma unroll
+        for (int d = 0; d < D; ++d) cp_async16(buf + (size_t)d * ts + q4, a.packed + (int64_t)d * a.ld + i);
+        cp_async16(buf + (size_t)D * ts + q4, a.v + i);
+        float* prow = buf + (size_t)(D + 1) * ts + q4;
         if (i + 3 < a.N) {
-          cp_async16(prow + (c << 2), a.p + i);
+          cp_async16(prow, a.p + i);
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (i + q < a.N) cp_async4(prow + (c << 2) + q, a.p + i + q);
-            else prow[(c << 2) + q] = 0.f;
+            if (i + q < a.N) cp_async4(prow + q, a.p + i + q);
+            else prow[q] = 0.f;
           }
         }
       }
@@ -534,29 +535,32 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
       const int64_t base = lo + (int64_t)k * ts;
       const int cnt = (int)min((int64_t)ts, hi - base);
       const int cnt64 = (cnt + 63) & ~63;
-      cp_async_wait_all();
-      __syncthreads();  // tile k has landed for everyone; everyone is done with tile k-1
-      if (k + 1 < nt) issue_tile(k + 1);
       float* wrow = buf + (size_t)D * ts;
       const float* prow = buf + (size_t)(D + 1) * ts;
-      for (int e = tid; e < cnt64; e += blockDim.x) {
-        const int64_t i = base + e;
-        float w = 0.f;
-        if (e < cnt && i < a.N) {
-          const float c = fmaxf(__fdividef(wrow[e], vsum_f), a.floor);
-          const float pi = prow[e];
-          w = __fdividef(pi * maxc_f, c);  // p/q with q = c / max c  (klerg.py:436)
-          if (want_kl && r == 0) {
-            kl_a += (double)(pi * (logf(pi) - logf(c)));
-            kl_c += (double)c;
-          }
-        } else if (e >= cnt) {
+      cp_async_wait_all();  // this thread's chunks of tile k
+      for (int c = tid; c < (cnt64 >> 2); c += blockDim.x) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) buf[(size_t)d * ts + e] = 0.f;
+        for (int q = 0; q < 4; ++q) {
+          const int e = (c << 2) + q;
+          const int64_t i = base + e;
+          float w = 0.f;
+          if (e < cnt && i < a.N) {
+            const float cc = fmaxf(__fdividef(wrow[e], vsum_f), a.floor);
+            const float pi = prow[e];
+            w = __fdividef(pi * maxc_f, cc);  // p/q with q = c / max c  (klerg.py:436)
+            if (want_kl && r == 0) {
+              kl_a += (double)(pi * (logf(pi) - logf(cc)));
+              kl_c += (double)cc;
+            }
+          } else if (e >= cnt) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) buf[(size_t)d * ts + e] = 0.f;
+          }
+          wrow[e] = w;
         }
-        wrow[e] = w;
       }
-      __syncthreads();
+      __syncthreads();  // tile k is ready for everyone; everyone is done with tile k-1
+      if (k + 1 < nt) issue_tile(k + 1);
       if (active) {
         for (int pb = sub * 64; pb < cnt64; pb += a.nsub * 64) {
           const int i = pb + 2 * lane;

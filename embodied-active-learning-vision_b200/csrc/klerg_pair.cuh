@@ -88,7 +88,7 @@ __device__ __forceinline__ u64 sqdist2(const u64 (&x)[D], const u64 (&s)[D], u64
 template <int D, int P, int MODE>
 __device__ __forceinline__ void pair_forward(const u64* __restrict__ sh_x2, int T, const u64 (&s2)[D][P], u64 (&acc)[P],
                                              float (&emin)[2 * P]) {
-#pragma unroll 4
+#pragma unroll 8
   for (int j = 0; j < T; ++j) {
     u64 x[D];
     load_state2<D>(sh_x2, j, x);
