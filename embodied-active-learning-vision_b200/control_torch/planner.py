@@ -136,6 +136,39 @@ class PlannerContext:
             out.update(v=v[0], totals=totals_w)
         return out
 
+    # -- K belief targets over one workspace (fingerprint test mode, BASELINE config 5) ------------------
+    def set_targets(self, P, P_stats):
+        """P [K, n_local] target densities p_k on the device, P_stats [K, 1] = their global sums."""
+        self.P, self.P_stats = P.contiguous(), P_stats.contiguous()
+
+    def costs_targets(self, U):
+        """cost[k, b] = KL(p_k || q_b) + barrier_b for every target k and candidate b."""
+        saved = (self.p, self.p_stats)
+        out = []
+        try:
+            for k in range(self.P.shape[0]):
+                self.set_target(self.P[k], self.P_stats[k])
+                out.append(self.costs(U).clone())
+        finally:
+            self.p, self.p_stats = saved
+        return torch.stack(out)
+
+    def gradient_targets(self, u):
+        """Per-target gradient eval: dict of [K, ...] stacked du, djdlam, u_star, dgdx (one fused launch per target;
+        the forward pass is recomputed per target - a shared-psi multi-target kernel is the next step)."""
+        saved = (self.p, self.p_stats)
+        keys = ("du", "djdlam", "u_star", "dgdx")
+        acc = {k: [] for k in keys}
+        try:
+            for k in range(self.P.shape[0]):
+                self.set_target(self.P[k], self.P_stats[k])
+                g = self.gradient(u)
+                for key in keys:
+                    acc[key].append(g[key].clone())
+        finally:
+            self.p, self.p_stats = saved
+        return {k: torch.stack(v) for k, v in acc.items()}
+
     def q_from(self, v, totals_w):
         """renormalize(q_base + q_iter) given the forward output (for plot_data)."""
         return engine.renormalize_sharded(v[: self.n], totals_w.reshape(totals_w.shape[0], -1)[:, :2], self.floor)

@@ -1,0 +1,115 @@
+"""Scaled-down BASELINE configs 3, 4, 5 on the GPU against the CPU oracle (tolerance 1e-4 relative,
+BASELINE.json north_star): batched candidate costs, 6-D pose workspace with a long history, K belief
+targets.  Full sizes are covered by size-independent properties (candidate-order invariance, the
+batch equals the one-by-one evaluation, sharding invariance in test_sharding.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import workloads as wl  # noqa: E402
+from oracle import klerg_oracle as ko  # noqa: E402
+
+RTOL = 1e-4
+
+
+def close(a, b, rtol=RTOL, atol_frac=0.0, what=""):
+    a = torch.as_tensor(a).detach().double().cpu().numpy()
+    b = torch.as_tensor(b).detach().double().cpu().numpy()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol_frac * (np.abs(b).max() if b.size else 0) + 1e-37, err_msg=what)
+
+
+def setup(name, n, m, H=None, seed=0):
+    from control_torch import engine
+    from control_torch.klerg import Robot
+    from control_torch.planner import PlannerContext
+    w = wl.WORKLOADS[name]
+    H = H or w["H"]
+    lims = [wl.LIMS[s] for s in w["states"]]
+    D = len(lims)
+    dev = torch.device("cuda")
+    target = wl.make_target("gmm", lims, seed=1, device="cpu")
+    kw = wl.robot_kwargs(name, target, n_samples=n, horizon=H, cap=max(m, 8))
+    torch.manual_seed(seed)
+    probe = Robot(**kw)
+    oracle = ko.OracleRobot(**kw)
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.tensor([a for a, _ in lims]) * 1.15
+    hi = torch.tensor([b for _, b in lims]) * 1.15
+    samples = lo + torch.rand(n, D, generator=g) * (hi - lo)
+    hist = wl.random_walk_history(name, m, seed=seed)
+    p_raw = target.pdf_torch(samples)
+    p = ko.renormalize(p_raw.clone())
+    q_base = ko.footprint_sum(hist, samples, oracle.explr_locs, oracle.std, torch.ones(1))
+    ctx = PlannerContext(probe.planner.spec, probe.barrier.spec(), probe.explr_locs.tolist(), H,
+                         torch.diagonal(probe.R_inv).tolist(), probe.control_lim[:, 0].tolist(),
+                         probe.control_lim[:, 1].tolist(), alpha=1.0)
+    ctx.set_samples(samples.to(dev), probe.std.tolist(), 1.0)
+    ctx.set_state(torch.tensor(kw["x0"], dtype=torch.float32, device=dev))
+    ctx.set_target(p.to(dev), engine.vector_stats(p.to(dev))[:1].contiguous())
+    ctx.set_history(hist.to(dev))
+    close(ctx.q_base[:n], q_base, what="history footprint")
+    return dict(ctx=ctx, oracle=oracle, samples=samples, p=p, q_base=q_base, D=D, H=H, dev=dev, engine=engine)
+
+
+def oracle_grad(o, samples, p, q_base, u):
+    o.u = u.clone()
+    _, lin, traj = o.forward(0)
+    q = ko.renormalize(q_base + ko.footprint_sum(traj, samples, o.explr_locs, o.std, torch.ones(1)))
+    du, dj = o.backward(samples, p.clone(), q, torch.ones(1), lin, traj)
+    return du, dj
+
+
+def test_config3_batched_candidates():
+    """64 candidates x H=50 x 2e4 samples in chunks of 8 per launch; 6 of them against the oracle."""
+    s = setup("c3", 20_000, 300)
+    u0 = wl.random_controls((s["H"], s["D"]), seed=1)
+    g = torch.Generator().manual_seed(2)
+    U = u0.unsqueeze(0) + 0.1 * torch.randn(64, s["H"], s["D"], generator=g)
+    got = s["ctx"].costs(U.to(s["dev"])).cpu()
+    for b in (0, 7, 8, 31, 62, 63):
+        want = s["oracle"].get_cost(s["samples"], s["p"].clone(), s["q_base"], U[b])
+        close(got[b], want.reshape(()), what=f"candidate {b}")
+    # the batch is the one-by-one evaluation, in any order
+    perm = torch.randperm(64, generator=g)
+    got_perm = s["ctx"].costs(U[perm].to(s["dev"])).cpu()
+    assert torch.equal(got_perm, got[perm])
+    one = torch.stack([s["ctx"].costs(U[b:b + 1].to(s["dev"]))[0] for b in (3, 40)]).cpu()
+    assert torch.equal(one, got[[3, 40]])
+
+
+def test_config4_pose_workspace_long_history():
+    """6-D pose (roll dynamics), 3e4 samples, 2000 history states: cost + gradient eval vs the oracle."""
+    s = setup("c4", 30_000, 2_000, H=20)
+    U = wl.random_controls((3, s["H"], s["D"]), seed=5)
+    got = s["ctx"].costs(U.to(s["dev"])).cpu()
+    for b in range(3):
+        want = s["oracle"].get_cost(s["samples"], s["p"].clone(), s["q_base"], U[b])
+        close(got[b], want.reshape(()), rtol=5e-4, what=f"cost {b}")  # quartic barrier amplifies the fp32 matrix_exp difference
+    g = s["ctx"].gradient(U[0].to(s["dev"]))
+    du, dj = oracle_grad(s["oracle"], s["samples"], s["p"], s["q_base"], U[0])
+    close(g["du"], du, rtol=RTOL, atol_frac=5e-5, what="du")
+    close(g["djdlam"], dj, rtol=RTOL, atol_frac=5e-5, what="djdlam")
+
+
+def test_config5_belief_targets():
+    """4 belief targets over one workspace: per-target cost and gradient vs the oracle, target by target."""
+    s = setup("c5", 20_000, 300, H=20)
+    lims = [wl.LIMS[c] for c in wl.WORKLOADS["c5"]["states"]]
+    P = torch.stack([ko.renormalize(wl.make_target("gmm", lims, seed=10 + k).pdf_torch(s["samples"])) for k in range(4)])
+    Pd = P.to(s["dev"])
+    stats = torch.stack([s["engine"].vector_stats(Pd[k])[:1] for k in range(4)])
+    s["ctx"].set_targets(Pd, stats)
+    U = wl.random_controls((2, s["H"], s["D"]), seed=9)
+    costs = s["ctx"].costs_targets(U.to(s["dev"])).cpu()
+    grads = s["ctx"].gradient_targets(U[0].to(s["dev"]))
+    assert costs.shape == (4, 2) and grads["du"].shape == (4, s["H"], s["D"])
+    for k in range(4):
+        for b in range(2):
+            want = s["oracle"].get_cost(s["samples"], P[k].clone(), s["q_base"], U[b])
+            close(costs[k, b], want.reshape(()), what=f"target {k} cost {b}")
+        du, dj = oracle_grad(s["oracle"], s["samples"], P[k], s["q_base"], U[0])
+        close(grads["du"][k], du, rtol=RTOL, atol_frac=5e-5, what=f"target {k} du")
+        close(grads["djdlam"][k], dj, rtol=RTOL, atol_frac=5e-5, what=f"target {k} djdlam")
