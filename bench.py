@@ -417,10 +417,16 @@ def cuda_arm(args):
         peaks = measure_peaks(cabi, sms)
         rf = eval_roofline(D, H, n, peaks, hbm_gbs)
         t_launch = ms_total / K * 1e-3
+        traffic = None
+        try:  # measured once per round with ncu --set full (not re-measured live: ncu cannot run inside the bench)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(f"{args.workload}:{n}")
+            traffic = tr["bytes"] if tr else None
+        except (OSError, ValueError):
+            pass
         roof = {"kernel": "eval_grad_kernel (rollout + footprint + renormalize + gradient + adjoint, one launch per eval)",
                 "bound": "fp32" if rf["bound"] != "hbm" else "hbm",
                 "achieved": rf["flops"] / t_launch / 1e12, "peak": rf["flops"] / rf["seconds"] / 1e12, "unit": "TFLOP/s",
-                "frac": rf["seconds"] / t_launch, "traffic": None,
+                "frac": rf["seconds"] / t_launch, "traffic": traffic, "algorithmic_bytes": rf["bytes"],
                 "launch_us": t_launch * 1e6, "roofline_us": rf["seconds"] * 1e6,
                 "peak_basis": (f"FP32-pipe and MUFU peaks measured on this box with the library's probes: packed FFMA2 "
                                f"{peaks['ffma2_lane_ops_per_s']:.3e} lane-ops/s, scalar FFMA {peaks['ffma_per_s']:.3e}/s, "
@@ -447,6 +453,22 @@ def cuda_arm(args):
                            "note": "1e5 samples leave ~650 samples per SM: the eval is latency-bound (launch, two grid "
                                    "meeting points, serial rollout/adjoint), not throughput-bound"}}
         del S2
+
+    # ---- with several GPUs: the same eval with the per-GPU workspace held fixed (weak scaling) -------
+    if world > 1 and not args.weak and not args.no_also:
+        del S["sets"][:]
+        torch.cuda.empty_cache()
+        Sw = build_sets(args.workload, (args.samples or w["N"]) * world, rank, group, dev, engine, Robot, PlannerContext)
+        rw = timed_evals(args, Sw, 100, 5, world, rank, lib, dev)
+        if rank == 0:
+            tw = rw["ms_total"] / 100 * 1e-3
+            also = dict(also or {})
+            also["weak_scaling"] = {"workload": workload_config(args.workload, (args.samples or w["N"]) * world, Sw["n"])["workload"],
+                                    "pairs_per_s": 2 * H * (args.samples or w["N"]) * world / tw, "us_per_eval": tw * 1e6,
+                                    "note": "per-GPU samples held at the single-GPU workload; the headline value above "
+                                            "shards the fixed 1e7-sample workspace (strong scaling)"}
+        del Sw
+        torch.cuda.empty_cache()
 
     # ---- e2e: Robot.step() through the public API with host buffers ---------------------------------
     e2e = None

@@ -332,13 +332,21 @@ class Robot(object):
         self.last_hist_idx = hist_idx
         return samples, hist_dev, torch.ones(1)
 
-    def _pdf(self, samples_host, uniform):
-        """The target density is an INPUT of the path (VAE / belief grid); evaluated where it lives."""
+    def _pdf(self, samples_host, uniform, samples_dev=None):
+        """The target density is an INPUT of the path (VAE / belief grid); evaluated where it lives.
+
+        Returns (values for this rank's slice, pre_renorm).  ``pdf_torch`` is point-wise (vae.py:244-275), so a
+        sharded controller evaluates it on its own slice only - reusing the samples already on the device when
+        the target lives there; ``init_uniform_grid`` normalises over the whole batch and is evaluated in full."""
+        tdev = torch.device(self.target_dist.device)
         if uniform:
-            return self.target_dist.init_uniform_grid(samples_host.clone().to(self.target_dist.device)).squeeze(), True
+            full = self.target_dist.init_uniform_grid(samples_host.clone().to(tdev)).squeeze()
+            return self._shard(full), True
         if self.use_prior:
             raise NotImplementedError("use_prior is not ported")
-        return self.target_dist.pdf_torch(samples_host.clone().to(self.target_dist.device)).squeeze(), False
+        if samples_dev is not None and tdev == samples_dev.device:
+            return self.target_dist.pdf_torch(samples_dev.clone()).squeeze(), False
+        return self.target_dist.pdf_torch(self._shard(samples_host).clone().to(tdev)).squeeze(), False
 
     def _shard(self, t):
         lo, hi = self.group.shard_bounds(t.shape[0])
@@ -346,8 +354,8 @@ class Robot(object):
 
     def _target_on_device(self, samples_host, samples_dev, scale_spec, temp, uniform=False, plot=False):
         """get_target_dist (klerg.py:452-486) -> (p, p_stats) on the device for this rank's sample slice."""
-        p_raw, pre_renorm = self._pdf(samples_host, uniform)
-        p_raw = self._shard(p_raw.detach().to(torch.float32)).to(self.cuda, non_blocking=True).contiguous()
+        p_raw, pre_renorm = self._pdf(samples_host, uniform, samples_dev)
+        p_raw = p_raw.detach().to(torch.float32).to(self.cuda, non_blocking=True).contiguous()
         n_total = samples_host.shape[0]
         lo = self.robot_lim[:, 0].tolist()
         hi = self.robot_lim[:, 1].tolist()

@@ -29,22 +29,38 @@ namespace klerg {
 
 // ---- mailbox layout (symmetric across ranks; see klerg_mailbox_bytes) ----------------------
 constexpr int MB_MAXW = 8;                       // ranks
-constexpr int MB_A_STRIDE = 32;                  // doubles per (parity, rank) slot of exchange A; [31] = flag
-constexpr int MB_B_PAYLOAD = KLERG_MAX_H * KLERG_MAX_D + 2 * FUSED_MAXG;
-constexpr int MB_B_STRIDE = MB_B_PAYLOAD + 16;   // [MB_B_STRIDE-1] = flag
-constexpr size_t MB_A_BYTES = (size_t)2 * MB_MAXW * MB_A_STRIDE * sizeof(double);
-constexpr size_t MB_EPOCH_OFF = MB_A_BYTES + (size_t)2 * MB_MAXW * MB_B_STRIDE * sizeof(double);  // u64, written by the owner only
+// Every value travels as two 8-byte words {32 payload bits, 32-bit tag} (the "LL" scheme of NCCL): a
+// naturally aligned 8-byte store is single-copy atomic, so data and flag arrive together and neither
+// a system fence nor a separate flag round trip is needed.  tag = mailbox epoch + 1.
+constexpr int MB_A_VALS = 2 * FUSED_MAXG;                              // exchange A: {sum, max} per candidate
+constexpr int MB_B_VALS = KLERG_MAX_H * KLERG_MAX_D + 2 * FUSED_MAXG;  // exchange B: gradient partials + KL terms
+constexpr size_t MB_A_BYTES = (size_t)2 * MB_MAXW * MB_A_VALS * 16;
+constexpr size_t MB_B_BYTES = (size_t)2 * MB_MAXW * MB_B_VALS * 16;
+constexpr size_t MB_EPOCH_OFF = MB_A_BYTES + MB_B_BYTES;  // u64, written by the owner only
 constexpr size_t MB_BYTES = MB_EPOCH_OFF + 64;
 
-__device__ __forceinline__ double* mb_a(void* base, int par, int r) {
-  return (double*)base + (size_t)(par * MB_MAXW + r) * MB_A_STRIDE;
+__device__ __forceinline__ unsigned long long* mb_a(void* base, int par, int r) {
+  return (unsigned long long*)base + (size_t)(par * MB_MAXW + r) * MB_A_VALS * 2;
 }
-__device__ __forceinline__ double* mb_b(void* base, int par, int r) {
-  return (double*)((char*)base + MB_A_BYTES) + (size_t)(par * MB_MAXW + r) * MB_B_STRIDE;
+__device__ __forceinline__ unsigned long long* mb_b(void* base, int par, int r) {
+  return (unsigned long long*)((char*)base + MB_A_BYTES) + (size_t)(par * MB_MAXW + r) * MB_B_VALS * 2;
 }
-
 __device__ __forceinline__ unsigned long long* mb_epoch(void* base) {
   return (unsigned long long*)((char*)base + MB_EPOCH_OFF);
+}
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long t = (unsigned long long)tag << 32;
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot), "l"((bits & 0xffffffffull) | t) : "memory");
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(slot + 1), "l"((bits >> 32) | t) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* slot, unsigned tag, double& v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w0) : "l"(slot) : "memory");
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w1) : "l"(slot + 1) : "memory");
+  if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) return false;
+  v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
 }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -202,6 +218,7 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, unsigned m
   const unsigned go_val = 2u * epoch + 1u;
   double* world = ws_fused_world(a.ws);
   const int par = mepoch & 1;
+  const unsigned tag = mepoch + 1u;
   const int nq = 2 * G;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -220,27 +237,19 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, unsigned m
         }
         s = warp_reduce(RED_SUM, s);
         m = warp_reduce(RED_MAX, m);
-        // all-gather over NVLink: lane r stores this rank's pair into rank r's mailbox
+        // all-gather over NVLink: lane r stores this rank's pair into rank r's mailbox (data + tag per word)
         if (lane < a.peers.world) {
-          double* slot = mb_a(a.peers.mail[lane], par, a.peers.rank);
-          slot[2 * g] = s;
-          slot[2 * g + 1] = m;
+          unsigned long long* slot = mb_a(a.peers.mail[lane], par, a.peers.rank) + 4 * g;
+          ll_store(slot, s, tag);
+          ll_store(slot + 2, m, tag);
         }
       }
-      __threadfence_system();
-      __syncwarp();
-      if (lane < a.peers.world) {
-        st_release_sys_u64((unsigned long long*)&mb_a(a.peers.mail[lane], par, a.peers.rank)[MB_A_STRIDE - 1],
-                           (unsigned long long)mepoch + 1ull);
-        const unsigned long long* f =
-            (const unsigned long long*)&mb_a(a.peers.mail[a.peers.rank], par, lane)[MB_A_STRIDE - 1];
-        KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)mepoch + 1ull, ctrl)
-      }
-      __syncwarp();
       if (lane < nq) {
         double v = (lane & 1) ? -INFINITY : 0.0;
         for (int r = 0; r < a.peers.world; ++r) {
-          const double x = ld_volatile_f64(&mb_a(a.peers.mail[a.peers.rank], par, r)[lane]);
+          const unsigned long long* slot = mb_a(a.peers.mail[a.peers.rank], par, r) + 2 * lane;
+          double x = 0.0;
+          KLERG_SPIN_UNTIL(ll_try_load(slot, tag, x), ctrl)
           v = (lane & 1) ? fmax(v, x) : v + x;
         }
         world[lane] = v;
@@ -277,25 +286,21 @@ __device__ bool meet_last(const EvalArgs& a, int* sh_flag) {
 __device__ void exchange_sum(const EvalArgs& a, unsigned mepoch, double* sh_vals, int n) {
   if (a.peers.world <= 1) return;
   const int par = mepoch & 1;
+  const unsigned tag = mepoch + 1u;
+  unsigned* ctrl = ws_fused_ctrl(a.ws);
   __syncthreads();
   for (int e = threadIdx.x; e < n * a.peers.world; e += blockDim.x) {
     const int r = e / n, i = e - r * n;
-    mb_b(a.peers.mail[r], par, a.peers.rank)[i] = sh_vals[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < a.peers.world) {
-    st_release_sys_u64((unsigned long long*)&mb_b(a.peers.mail[threadIdx.x], par, a.peers.rank)[MB_B_STRIDE - 1],
-                       (unsigned long long)mepoch + 1ull);
-    const unsigned long long* f =
-        (const unsigned long long*)&mb_b(a.peers.mail[a.peers.rank], par, threadIdx.x)[MB_B_STRIDE - 1];
-    unsigned* ctrl = ws_fused_ctrl(a.ws);
-    KLERG_SPIN_UNTIL(ld_acquire_sys_u64(f) == (unsigned long long)mepoch + 1ull, ctrl)
+    ll_store(mb_b(a.peers.mail[r], par, a.peers.rank) + 2 * i, sh_vals[i], tag);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double v = 0.0;
-    for (int r = 0; r < a.peers.world; ++r) v += ld_volatile_f64(&mb_b(a.peers.mail[a.peers.rank], par, r)[i]);
+    for (int r = 0; r < a.peers.world; ++r) {
+      double x = 0.0;
+      KLERG_SPIN_UNTIL(ll_try_load(mb_b(a.peers.mail[a.peers.rank], par, r) + 2 * i, tag, x), ctrl)
+      v += x;
+    }
     sh_vals[i] = v;
   }
   __syncthreads();
@@ -617,25 +622,38 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     // 8 lanes per entry, each summing float4 groups of CTA partials in double (independent loads), then a
     // 3-step shuffle tree: fixed order, so the result does not depend on which CTA arrived last
     const float* gpart = (const float*)ws_fused_grad(a.ws);
-    const int n8 = HD * 8;
-    for (int idx = tid; idx < ((n8 + 31) & ~31); idx += blockDim.x) {  // whole warps take part in the shuffles
-      const int e = idx >> 3, part = idx & 7;
-      double v = 0.0;
-      if (idx < n8) {
-        const float* row = gpart + (size_t)e * gstride;
-#pragma unroll 4
-        for (int b = part * 4; b < nblk; b += 32) {
-          const float4 x = __ldcg(reinterpret_cast<const float4*>(row + b));
-          v += (double)x.x;
-          if (b + 1 < nblk) v += (double)x.y;
-          if (b + 2 < nblk) v += (double)x.z;
-          if (b + 3 < nblk) v += (double)x.w;
+    const int n8 = HD * 8, n8r = (n8 + 31) & ~31;  // whole warps take part in the shuffles
+    constexpr int NIT = 4;
+    for (int idx0 = tid; idx0 < n8r; idx0 += NIT * blockDim.x) {
+      double vv[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {  // all loads of a batch are issued before the first shuffle
+        const int idx = idx0 + it * blockDim.x;
+        double v = 0.0;
+        if (idx < n8) {
+          const float* row = gpart + (size_t)(idx >> 3) * gstride;
+#pragma unroll 5
+          for (int b = (idx & 7) * 4; b < nblk; b += 32) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(row + b));
+            v += (double)x.x;
+            if (b + 1 < nblk) v += (double)x.y;
+            if (b + 2 < nblk) v += (double)x.z;
+            if (b + 3 < nblk) v += (double)x.w;
+          }
+        }
+        vv[it] = v;
+      }
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int idx = idx0 + it * blockDim.x;
+        if (idx < n8r) {
+          double v = vv[it];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          if ((idx & 7) == 0 && idx < n8) s_val[idx >> 3] = v;
         }
       }
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      if (part == 0 && idx < n8) s_val[e] = v;
     }
     if (want_kl) {
       const double* klp = ws_fused_kl(a.ws);
