@@ -72,35 +72,29 @@ __device__ __forceinline__ float affine_map(float v, float ilo, float ihi, float
   return (v - ilo) / (ihi - ilo) * (ohi - olo) + olo;
 }
 
-static __device__ __noinline__ void euler_xyz_to_matrix(const float* rot, float* R) {
-  // Rz(yaw) * Ry(pitch) * Rx(roll)   (rotations.py:70-96, order flipped to match scipy)
-  float sr, cr, sp, cp, sy, cy;
-  sincosf(rot[0], &sr, &cr);
-  sincosf(rot[1], &sp, &cp);
-  sincosf(rot[2], &sy, &cy);
-  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
-  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
-  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
-}
-
 __device__ __forceinline__ float py_mod(float x, float m) {
   float r = fmodf(x, m);
   if (r < 0.f) r += m;
   return r;
 }
 
-// E = expm(hat(w) dt) via Rodrigues (= torch.matrix_exp of the skew matrix, dynamics.py:213-217)
-static __device__ __noinline__ void rodrigues(const float* w, float dt, float* E) {
+static __device__ __noinline__ void sincos_ni(float x, float* s, float* c) { sincosf(x, s, c); }
+static __device__ __noinline__ float atan2_ni(float y, float x) { return atan2f(y, x); }
+
+// E = expm(hat(w) dt) via Rodrigues (= torch.matrix_exp of the skew matrix, dynamics.py:213-217).
+// sin(th)/th and (1-cos(th))/th^2 from their series for th < 1 (truncation < 3e-8; |w| dt is a fraction of a
+// radian for any admissible velocity), from sincos otherwise.
+__device__ inline void rodrigues(const float* w, float dt, float* E) {
   const float kx = w[0] * dt, ky = w[1] * dt, kz = w[2] * dt;
   const float th2 = kx * kx + ky * ky + kz * kz;
-  float A, B;  // sin(th)/th, (1-cos(th))/th^2
-  if (th2 < 1e-8f) {
-    A = 1.f - th2 / 6.f;
-    B = 0.5f - th2 / 24.f;
+  float A, B;
+  if (th2 < 1.f) {
+    A = 1.f + th2 * (-1.f / 6.f + th2 * (1.f / 120.f + th2 * (-1.f / 5040.f + th2 * (1.f / 362880.f))));
+    B = 0.5f + th2 * (-1.f / 24.f + th2 * (1.f / 720.f + th2 * (-1.f / 40320.f + th2 * (1.f / 3628800.f))));
   } else {
     const float th = sqrtf(th2);
     float s, c;
-    sincosf(th, &s, &c);
+    sincos_ni(th, &s, &c);
     A = s / th;
     B = (1.f - c) / th2;
   }
@@ -110,23 +104,40 @@ static __device__ __noinline__ void rodrigues(const float* w, float dt, float* E
   E[6] = -A * ky + B * kx * kz;         E[7] = A * kx + B * ky * kz;          E[8] = 1.f - B * (kx * kx + ky * ky);
 }
 
-// wrap(euler_XYZ(R)): roll in [0, 2pi), pitch / yaw in [-pi, pi)   (rotations.py:142-181, dynamics.py:219-222)
-static __device__ __noinline__ void wrapped_euler_xyz(const float* Rn, float* rot) {
+// wrap(euler_XYZ(R)): roll in [0, 2pi), pitch / yaw in [-pi, pi)   (rotations.py:142-181, dynamics.py:219-222).
+// atan2 / asin already return values within one period, so the reference's modulo reduces to one conditional
+// add / subtract (same arithmetic as torch's `%` on that range).
+__device__ inline void wrapped_euler_xyz(const float* Rn, float* rot) {
   const float two_pi = 6.283185307179586f, pi = 3.141592653589793f;
-  const float r0 = atan2f(Rn[7], Rn[8]);
+  float r0 = atan2_ni(Rn[7], Rn[8]);
   const float r1 = asinf(-Rn[6]);
-  const float r2 = atan2f(Rn[3], Rn[0]);
-  rot[0] = py_mod(r0, two_pi);
-  rot[1] = py_mod(r1 + pi, two_pi) - pi;
-  rot[2] = py_mod(r2 + pi, two_pi) - pi;
+  const float r2 = atan2_ni(Rn[3], Rn[0]);
+  if (r0 < 0.f) r0 += two_pi;
+  float t2 = r2 + pi;
+  if (t2 >= two_pi) t2 -= two_pi;
+  rot[0] = r0;
+  rot[1] = (r1 + pi) - pi;
+  rot[2] = t2 - pi;
+}
+
+__device__ inline void euler_xyz_to_matrix(const float* rot, float* R) {
+  // Rz(yaw) * Ry(pitch) * Rx(roll)   (rotations.py:70-96, order flipped to match scipy)
+  float sr, cr, sp, cp, sy, cy;
+  sincos_ni(rot[0], &sr, &cr);
+  sincos_ni(rot[1], &sp, &cp);
+  sincos_ni(rot[2], &sy, &cy);
+  R[0] = cy * cp; R[1] = cy * sp * sr - sy * cr; R[2] = cy * sp * cr + sy * sr;
+  R[3] = sy * cp; R[4] = sy * sp * sr + cy * cr; R[5] = sy * sp * cr - cy * sr;
+  R[6] = -sp;     R[7] = cp * sr;                R[8] = cp * cr;
 }
 
 // E(roll, pitch + 1e-5) R: the rpw x rpw block of d(pos rate)/d(vel)   (dynamics.py:189-211,283-289)
-static __device__ __noinline__ void euler_rate_block(const float* rot_in, const float* R, float* out9) {
-  float rot1 = rot_in[1] + 1e-5f;
-  float s0, c0;
-  sincosf(rot_in[0], &s0, &c0);
-  const float t1 = tanf(rot1), cc1 = cosf(rot1);
+__device__ inline void euler_rate_block(const float* rot_in, const float* R, float* out9) {
+  const float rot1 = rot_in[1] + 1e-5f;
+  float s0, c0, s1, cc1;
+  sincos_ni(rot_in[0], &s0, &c0);
+  sincos_ni(rot1, &s1, &cc1);
+  const float t1 = s1 / cc1;
   const float Em[9] = {1.f, s0 * t1, c0 * t1, 0.f, c0, -s0, 0.f, s0 / cc1, c0 / cc1};
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) out9[r * 3 + c] = Em[r * 3] * R[c] + Em[r * 3 + 1] * R[3 + c] + Em[r * 3 + 2] * R[6 + c];
@@ -162,13 +173,23 @@ __host__ __device__ inline int rollout_rot_floats(int G, int H) { return G * (2 
 //   R_out   [G][9]       rotation after the last step (global or shared, may be NULL)
 // Ends with a __syncthreads().
 // ---------------------------------------------------------------------------
+#ifdef KLERG_STAMPS
+__device__ long long g_ro_stamp[8];
+#define RO_STAMP(i) if (blockIdx.x == 0 && threadIdx.x == 0) g_ro_stamp[i] = clock64()
+#else
+#define RO_STAMP(i)
+#endif
+
 __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const float* x0, const float* R0,
                                      const float* s_u, int G, int H, float* s_traj, float* s_dbarr, float* s_P,
                                      float* s_rot, float* s_red, float* s_bsum, float* R_out) {
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int S = d.S, a = d.A;
-  const bool single = d.kind == KLERG_DYN_SINGLE, speed = d.kind == KLERG_DYN_SPEED, roll = d.kind == KLERG_DYN_ROLL;
-  const float dt = d.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
+  const PinnedParams pp = pin_params(s_red, d.S, d.A, H, d.kind, d.dt);
+  const int S = pp.S, a = pp.A, kind = pp.kind;
+  H = pp.H;
+  const bool single = kind == KLERG_DYN_SINGLE, speed = kind == KLERG_DYN_SPEED, roll = kind == KLERG_DYN_ROLL;
+  const float dt = pp.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
+  RO_STAMP(0);
   // (A) running sums, one lane per (candidate, control)
   for (int l = tid; l < G * a; l += nthr) {
     const int g = l / a, i = l - g * a;
@@ -177,34 +198,31 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
     float pos = x0[i];
     float vel = single ? 0.f : x0[a + i];
     float mag = speed ? x0[2 * a + i] : 0.f;
-    // chunks of 8 steps: controls are fetched into registers first so the loads overlap the recurrence
-    for (int t0 = 0; t0 < H; t0 += 8) {
-      float ub[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) ub[k] = (t0 + k < H) ? us[(t0 + k) * a + i] : 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int t = t0 + k;
-        if (t < H) {
-          tr[t * S + i] = pos;
-          if (!single) tr[t * S + a + i] = vel;
-          if (speed) tr[t * S + 2 * a + i] = mag;
-          const float ut = ub[k];
-          if (single) {
-            pos = pos + dt * ut;
-          } else {
-            pos = pos + (c1 * vel + c2 * ut);
-            vel = vel + dt * ut;
-            if (speed) mag = fabsf(vel);
-          }
-        }
+    // rolled on purpose (this code runs once per launch from a cold instruction cache, where size is what
+    // costs time); the control is fetched two steps ahead so the shared-memory latency overlaps the recurrence
+    float u0 = H > 0 ? us[i] : 0.f, u1 = H > 1 ? us[a + i] : 0.f;
+#pragma unroll 1
+    for (int t = 0; t < H; ++t) {
+      const float u2 = (t + 2 < H) ? us[(t + 2) * a + i] : 0.f;
+      tr[t * S + i] = pos;
+      if (!single) tr[t * S + a + i] = vel;
+      if (speed) tr[t * S + 2 * a + i] = mag;
+      if (single) {
+        pos = pos + dt * u0;
+      } else {
+        pos = pos + (c1 * vel + c2 * u0);
+        vel = vel + dt * u0;
+        if (speed) mag = fabsf(vel);
       }
+      u0 = u1;
+      u1 = u2;
     }
     tr[H * S + i] = pos;
     if (!single) tr[H * S + a + i] = vel;
     if (speed) tr[H * S + 2 * a + i] = mag;
   }
   __syncthreads();
+  RO_STAMP(1);
   if (roll) {
     float* s_E = s_rot;               // [G][H][9]
     float* s_R = s_rot + G * H * 9;   // [G][H+1][9]
@@ -289,6 +307,7 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
   } else if (R_out) {
     for (int e = tid; e < G * 9; e += nthr) R_out[e] = ((e % 9) % 4 == 0) ? 1.f : 0.f;
   }
+  RO_STAMP(2);
   // (E) wall barrier of the post-step states and its derivative at the pre-step states
   for (int g = 0; g < G; ++g) {
     const float* tr = s_traj + (size_t)g * (H + 1) * S;
@@ -303,6 +322,7 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
       }
       if (s_dbarr) s_dbarr[(size_t)g * H * S + e] = db;
     }
+    RO_STAMP(3);
     bsum = warp_sum_f(bsum);
     __syncthreads();
     if ((tid & 31) == 0) s_red[tid >> 5] = bsum;
@@ -314,6 +334,7 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
     }
   }
   __syncthreads();
+  RO_STAMP(4);
 }
 
 // ---------------------------------------------------------------------------
@@ -332,15 +353,17 @@ struct AdjParams {
   float alpha;
 };
 
-__host__ __device__ inline int adjoint_scratch_floats(int H, int A) { return 5 * H * A; }
+__host__ __device__ inline int adjoint_scratch_floats(int H, int A) { return 5 * H * A + 8; }
 
 __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H, const float* sg, const float* sP,
                                      const float* s_traj, const float* su, float* s_scr, float* du, float* djdlam,
                                      float* u_star) {
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int S = d.S, A = d.A;
-  const bool single = d.kind == KLERG_DYN_SINGLE, speed = d.kind == KLERG_DYN_SPEED;
-  const float h = -d.dt;
+  const PinnedParams pp = pin_params(s_scr + 5 * H * d.A, d.S, d.A, H, d.kind, d.dt);
+  const int S = pp.S, A = pp.A, kind = pp.kind;
+  H = pp.H;
+  const bool single = kind == KLERG_DYN_SINGLE, speed = kind == KLERG_DYN_SPEED;
+  const float h = -pp.dt;
   float* s_rp = s_scr;              // rho_p before the update of step t
   float* s_rm = s_rp + H * A;       // rho_m after the update (SPEED)
   float* s_a = s_rm + H * A;        // g_v - P^T rho_p
@@ -348,27 +371,22 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
   float* s_btr = s_b + H * A;       // B^T rho after step t
   if (tid < A) {
     float rp = 0.f, rm = 0.f;
-    for (int t0 = H - 1; t0 >= 0; t0 -= 8) {
-      float gp[8], gm[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int t = t0 - k;
-        gp[k] = (t >= 0) ? sg[t * S + tid] : 0.f;
-        gm[k] = (speed && t >= 0) ? sg[t * S + 2 * A + tid] : 0.f;
+    // rolled, operands fetched two steps ahead (see rollout_block)
+    float g0 = H > 0 ? sg[(H - 1) * S + tid] : 0.f, g1 = H > 1 ? sg[(H - 2) * S + tid] : 0.f;
+    float m0 = (speed && H > 0) ? sg[(H - 1) * S + 2 * A + tid] : 0.f, m1 = (speed && H > 1) ? sg[(H - 2) * S + 2 * A + tid] : 0.f;
+#pragma unroll 1
+    for (int t = H - 1; t >= 0; --t) {
+      const float g2 = (t >= 2) ? sg[(t - 2) * S + tid] : 0.f;
+      const float m2 = (speed && t >= 2) ? sg[(t - 2) * S + 2 * A + tid] : 0.f;
+      s_rp[t * A + tid] = rp;
+      rp = rp + h * g0;
+      if (single) s_btr[t * A + tid] = rp;
+      if (speed) {
+        rm = rm + h * m0;
+        s_rm[t * A + tid] = rm;
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int t = t0 - k;
-        if (t >= 0) {
-          s_rp[t * A + tid] = rp;
-          rp = rp + h * gp[k];
-          if (single) s_btr[t * A + tid] = rp;
-          if (speed) {
-            rm = rm + h * gm[k];
-            s_rm[t * A + tid] = rm;
-          }
-        }
-      }
+      g0 = g1; g1 = g2;
+      m0 = m1; m1 = m2;
     }
   }
   __syncthreads();
@@ -393,24 +411,18 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
     __syncthreads();
     if (tid < A) {
       float rv = 0.f;
-      for (int t0 = H - 1; t0 >= 0; t0 -= 8) {
-        float av[8], bv[8], sv[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int t = t0 - k;
-          av[k] = (t >= 0) ? s_a[t * A + tid] : 0.f;
-          bv[k] = (t >= 0) ? s_b[t * A + tid] : 0.f;
-          sv[k] = 0.f;
-          if (speed && t >= 0) sv[k] = ((s_traj[t * S + A + tid] < 0.f) ? -1.f : 1.f) * s_rm[t * A + tid];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int t = t0 - k;
-          if (t >= 0) {
-            rv = rv + h * av[k] - 0.5f * h * h * bv[k];
-            s_btr[t * A + tid] = speed ? rv + sv[k] : rv;
-          }
-        }
+      float a0 = H > 0 ? s_a[(H - 1) * A + tid] : 0.f, a1 = H > 1 ? s_a[(H - 2) * A + tid] : 0.f;
+      float b0 = H > 0 ? s_b[(H - 1) * A + tid] : 0.f, b1 = H > 1 ? s_b[(H - 2) * A + tid] : 0.f;
+#pragma unroll 1
+      for (int t = H - 1; t >= 0; --t) {
+        const float a2 = (t >= 2) ? s_a[(t - 2) * A + tid] : 0.f;
+        const float b2 = (t >= 2) ? s_b[(t - 2) * A + tid] : 0.f;
+        rv = rv + h * a0 - 0.5f * h * h * b0;
+        float btr = rv;
+        if (speed) btr = rv + ((s_traj[t * S + A + tid] < 0.f) ? -1.f : 1.f) * s_rm[t * A + tid];
+        s_btr[t * A + tid] = btr;
+        a0 = a1; a1 = a2;
+        b0 = b1; b1 = b2;
       }
     }
     __syncthreads();

@@ -110,7 +110,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Phase stamps (clock64 at the phase boundaries of eval_grad_kernel) are compiled in with -DKLERG_STAMPS.
 #ifdef KLERG_STAMPS
-#define KLERG_STAMP_DECL long long stamp[8]
+#define KLERG_STAMP_DECL long long stamp[16]
 #define KLERG_STAMP(i) stamp[i] = clock64()
 #else
 #define KLERG_STAMP_DECL
@@ -267,18 +267,31 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, unsigned m
 }
 
 // Meeting point 2: returns true (all threads) in the last CTA to arrive.
-__device__ bool meet_last(const EvalArgs& a, int* sh_flag) {
+__device__ bool meet_last(const EvalArgs& a, int* sh_flag, int slot = 1) {
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned t = atomicAdd(&ctrl[1], 1u);
+    const unsigned t = atomicAdd(&ctrl[slot], 1u);
     *sh_flag = (t == gridDim.x - 1);
   }
   __syncthreads();
   const bool last = *sh_flag != 0;
   if (last) __threadfence();
   return last;
+}
+
+// Plain grid barrier on ctrl[slot] (the counter is reset by the CTA that finishes the launch).
+__device__ void meet_all(const EvalArgs& a, int slot) {
+  unsigned* ctrl = ws_fused_ctrl(a.ws);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&ctrl[slot], 1u);
+    KLERG_SPIN_UNTIL(ld_acquire_u32(&ctrl[slot]) >= gridDim.x, ctrl)
+    __threadfence();
+  }
+  __syncthreads();
 }
 
 // Cross-rank all-gather of `n` doubles held in shared memory (sh_vals) by the last CTA:
@@ -441,7 +454,9 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     s_epoch[2] = a.peers.world > 1 ? (unsigned)*mb_epoch(a.peers.mail[a.peers.rank]) : 0u;
   }
   __syncthreads();
+  KLERG_STAMP(8);
   rollout_block(a.d, a.bar, s_x0, a.R0 ? s_x0 + KLERG_MAX_S : nullptr, s_u, 1, H, s_traj, s_dbarr, s_P, s_tile, (float*)s_red, s_bsum, nullptr);
+  KLERG_STAMP(9);
   const unsigned epoch = s_epoch[0], mepoch = s_epoch[2];
   for (int e = tid; e < H * DP; e += blockDim.x) {
     const int t = e / DP, d = e - t * DP;
@@ -611,69 +626,45 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     }
   }
 
-  // ---- phase 3: the last CTA reduces the partials and runs the adjoint --------------------------------
+  // ---- phase 3: every CTA reduces a few gradient entries over all CTA partials (fixed order), then the last
+  //      CTA to finish collects the H*D sums, exchanges them with the peers and runs the adjoint ----------------
   KLERG_STAMP(4);
-  if (!meet_last(a, s_flag)) return;
+  meet_all(a, 1);
+  double* gfin = (double*)((char*)ws_fused_grad(a.ws) + FUSED_GRAD / 2);  // [H*D]
+  {
+    const float* gpart = (const float*)ws_fused_grad(a.ws);
+    for (int e = blockIdx.x * nwarps + warp; e < HD; e += nblk * nwarps) {
+      const float* row = gpart + (size_t)e * gstride;
+      double v = 0.0;
+      for (int b = lane; b < nblk; b += 32) v += (double)__ldcg(row + b);
+      v = warp_reduce(RED_SUM, v);
+      if (lane == 0) gfin[e] = v;
+    }
+  }
+  if (!meet_last(a, s_flag, 4)) return;
   KLERG_STAMP(5);
   double* s_val = (double*)s_tile;               // [HD + 2]
   float* s_g = (float*)(s_val + HD + 2);         // [H][S]
   float* s_scr = s_g + H * S;                    // adjoint scratch
-  {
-    // 8 lanes per entry, each summing float4 groups of CTA partials in double (independent loads), then a
-    // 3-step shuffle tree: fixed order, so the result does not depend on which CTA arrived last
-    const float* gpart = (const float*)ws_fused_grad(a.ws);
-    const int n8 = HD * 8, n8r = (n8 + 31) & ~31;  // whole warps take part in the shuffles
-    constexpr int NIT = 4;
-    for (int idx0 = tid; idx0 < n8r; idx0 += NIT * blockDim.x) {
-      double vv[NIT];
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {  // all loads of a batch are issued before the first shuffle
-        const int idx = idx0 + it * blockDim.x;
-        double v = 0.0;
-        if (idx < n8) {
-          const float* row = gpart + (size_t)(idx >> 3) * gstride;
-#pragma unroll 5
-          for (int b = (idx & 7) * 4; b < nblk; b += 32) {
-            const float4 x = __ldcg(reinterpret_cast<const float4*>(row + b));
-            v += (double)x.x;
-            if (b + 1 < nblk) v += (double)x.y;
-            if (b + 2 < nblk) v += (double)x.z;
-            if (b + 3 < nblk) v += (double)x.w;
-          }
-        }
-        vv[it] = v;
+  for (int e = tid; e < HD; e += blockDim.x) s_val[e] = __ldcg(&gfin[e]);
+  if (want_kl) {
+    const double* klp = ws_fused_kl(a.ws);
+    if (warp == 0) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int b = lane; b < nblk; b += 32) {
+        s0 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 0]);
+        s1 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 1]);
       }
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int idx = idx0 + it * blockDim.x;
-        if (idx < n8r) {
-          double v = vv[it];
-          v += __shfl_xor_sync(0xffffffffu, v, 1);
-          v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if ((idx & 7) == 0 && idx < n8) s_val[idx >> 3] = v;
-        }
+      s0 = warp_reduce(RED_SUM, s0);
+      s1 = warp_reduce(RED_SUM, s1);
+      if (lane == 0) {
+        s_val[HD] = s0;
+        s_val[HD + 1] = s1;
       }
     }
-    if (want_kl) {
-      const double* klp = ws_fused_kl(a.ws);
-      if (warp == 0) {
-        double s0 = 0.0, s1 = 0.0;
-        for (int b = lane; b < nblk; b += 32) {
-          s0 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 0]);
-          s1 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 1]);
-        }
-        s0 = warp_reduce(RED_SUM, s0);
-        s1 = warp_reduce(RED_SUM, s1);
-        if (lane == 0) {
-          s_val[HD] = s0;
-          s_val[HD + 1] = s1;
-        }
-      }
-    } else if (tid == 0) {
-      s_val[HD] = 0.0;
-      s_val[HD + 1] = 1.0;
-    }
+  } else if (tid == 0) {
+    s_val[HD] = 0.0;
+    s_val[HD + 1] = 1.0;
   }
   __syncthreads();
   KLERG_STAMP(6);
@@ -706,13 +697,15 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     unsigned* ctrl = ws_fused_ctrl(a.ws);
     ctrl[0] = 0;
     ctrl[1] = 0;
+    ctrl[4] = 0;
     ctrl[3] = epoch + 1;
     if (a.peers.world > 1) *mb_epoch(a.peers.mail[a.peers.rank]) = (unsigned long long)mepoch + 1ull;
 #ifdef KLERG_STAMPS
     // phase stamps of the CTA that finished last (SM cycles since its start): profiling aid
     KLERG_STAMP(7);
     long long* dbg = (long long*)(ctrl + 16);
-    for (int i = 0; i < 8; ++i) dbg[i] = stamp[i] - stamp[0];
+    for (int i = 0; i < 10; ++i) dbg[i] = stamp[i] - stamp[0];
+    for (int i = 0; i < 5; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];
 #endif
   }
 }
