@@ -389,6 +389,10 @@ __device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x
 // ---------------------------------------------------------------------------
 // shared-memory carve-up
 // ---------------------------------------------------------------------------
+// Row stride (floats) of the staged sample tiles: a compile-time constant so that the D+2 row addresses of a
+// tile are immediates off one base register (no address chain, fewer live registers in the pair loop).
+constexpr int TS_ROW = 2048;
+
 struct SmemPlan {
   size_t u, traj, dbarr, P, x2, xs, tile, part, red, misc, total;
 };
@@ -405,7 +409,8 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.P = o;     o = align16(o + (roll ? sizeof(float) * H * A * A : 0));
   p.x2 = o;    o = align16(o + sizeof(u64) * H * Row2<D>::DP);
   p.xs = o;    o = align16(o + sizeof(float) * H * D);
-  size_t tile = sizeof(float) * (size_t)2 * (D + 2) * ts;  // two cp.async buffers of rows s_0..s_{D-1}, v->w, p
+  (void)ts;
+  size_t tile = sizeof(float) * (size_t)2 * (D + 2) * TS_ROW;  // two cp.async buffers of rows s_0..s_{D-1}, v->w, p
   const size_t adj = sizeof(double) * ((size_t)H * D + 2) + sizeof(float) * ((size_t)H * S + adjoint_scratch_floats(H, A));
   const size_t rot = roll ? sizeof(float) * rollout_rot_floats(1, H) : 0;
   if (tile < adj) tile = adj;  // the adjoint phase and the ROLL rollout reuse the tile area
@@ -413,7 +418,7 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.tile = o;  o = align16(o + tile);
   p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
   p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
-  p.misc = o;  o = align16(o + 16 + sizeof(float) * (KLERG_MAX_S + 9));
+  p.misc = o;  o = align16(o + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16);
   p.total = o;
   return p;
 }
@@ -502,6 +507,10 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
 
   // ---- phase 2: importance ratio + gradient pair pass ----------------------------------------------
   const int ts = a.ts;
+  // loop-invariant launch parameters of the pair loop, pinned through shared memory (see pin_params)
+  if (tid == 0) s_flag[4 + KLERG_MAX_S + 9] = a.nsub * 64;
+  __syncthreads();
+  const int pb_step = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 9];
   const int HD = H * D;
   const int nblk = gridDim.x;
   const int gstride = (nblk + 31) & ~31;  // partial layout [e][gstride]: the final reduce reads rows coalesced
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     // Thread t owns 4-sample chunks t, t + blockDim, ... of a tile: it copies all rows of its chunks and, once its
     // own copies have landed, turns v into the importance ratio for them - one CTA barrier per tile.
     auto issue_tile = [&](int k) {
-      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * ts;
+      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * TS_ROW;
       const int64_t base = lo + (int64_t)k * ts;
       const int cnt = (int)min((int64_t)ts, hi - base);  // multiple of 4
       const int nch = cnt >> 2;
@@ -534,9 +543,9 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
         const int q4 = c << 2;
         const int64_t i = base + q4;
 #pragma unroll
-        for (int d = 0; d < D; ++d) cp_async16(buf + (size_t)d * ts + q4, a.packed + (int64_t)d * a.ld + i);
-        cp_async16(buf + (size_t)D * ts + q4, a.v + i);
-        float* prow = buf + (size_t)(D + 1) * ts + q4;
+        for (int d = 0; d < D; ++d) cp_async16(buf + (size_t)d * TS_ROW + q4, a.packed + (int64_t)d * a.ld + i);
+        cp_async16(buf + (size_t)D * TS_ROW + q4, a.v + i);
+        float* prow = buf + (size_t)(D + 1) * TS_ROW + q4;
         if (i + 3 < a.N) {
           cp_async16(prow, a.p + i);
         } else {
@@ -551,12 +560,12 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     };
     issue_tile(0);
     for (int k = 0; k < nt; ++k) {
-      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * ts;
+      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * TS_ROW;
       const int64_t base = lo + (int64_t)k * ts;
       const int cnt = (int)min((int64_t)ts, hi - base);
       const int cnt64 = (cnt + 63) & ~63;
-      float* wrow = buf + (size_t)D * ts;
-      const float* prow = buf + (size_t)(D + 1) * ts;
+      float* wrow = buf + (size_t)D * TS_ROW;
+      const float* prow = buf + (size_t)(D + 1) * TS_ROW;
       cp_async_wait_all();  // this thread's chunks of tile k
       for (int c = tid; c < (cnt64 >> 2); c += blockDim.x) {
 #pragma unroll
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
             }
           } else if (e >= cnt) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) buf[(size_t)d * ts + e] = 0.f;
+            for (int d = 0; d < D; ++d) buf[(size_t)d * TS_ROW + e] = 0.f;
           }
           wrow[e] = w;
         }
@@ -582,11 +591,11 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
       __syncthreads();  // tile k is ready for everyone; everyone is done with tile k-1
       if (k + 1 < nt) issue_tile(k + 1);
       if (active) {
-        for (int pb = sub * 64; pb < cnt64; pb += a.nsub * 64) {
+        for (int pb = sub * 64; pb < cnt64; pb += pb_step) {
           const int i = pb + 2 * lane;
           u64 s2[D];
 #pragma unroll
-          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * ts + i]);
+          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TS_ROW + i]);
           const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
           pair_gradient<D, WT>(xs2, s2, w2, acc);
         }
@@ -976,7 +985,7 @@ static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, cudaStream_t strea
   a.ts = ts;
   a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds;
   const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, ts, s.nwarps, WT);
-  if (sp.total > 200 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
+  if (sp.total > 220 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
   const int per_sm = resident_ctas(kernel, nthreads, sp.total);
   if (per_sm < 1) { set_error("eval_gradient: kernel does not fit on an SM (threads=%d smem=%zu)", nthreads, sp.total); return -4; }
   const int nblk = pick_grid(a.N, 1, 128);
