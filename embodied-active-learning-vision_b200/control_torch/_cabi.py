@@ -86,6 +86,7 @@ SIGNATURES = {
     "klerg_workspace_bytes": [_I64],
     "klerg_pack_samples": [_KS, _P, _I64, _P, _I64, _P],
     "klerg_footprint": [_KS, C.c_int, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P],
+    "klerg_psi_matrix": [_KS, _P, _I64, _P, _I64, _P, _P, _P],
     "klerg_vector_stats": [_P, _I64, _P, _P, _P],
     "klerg_renormalize": [_P, _I64, _F, _P, _P, _P],
     "klerg_renormalize_with_stats": [_P, _I64, _P, _F, _P, _P],

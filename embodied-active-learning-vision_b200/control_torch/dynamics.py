@@ -11,6 +11,17 @@ import torch
 from . import _cabi as cabi
 from . import engine
 
+def rk4_integrate(f, dt, xt, ut):
+    """Generic RK4 step of x' = f(x, u) for a caller-supplied f (reference dynamics.py:7-13).  The planner's own
+    models never go through it (their RK4 step is closed-form inside the CUDA kernels); it is kept for callers
+    that integrate their own vector field and runs on whatever device the tensors live on."""
+    stages = []
+    for c in (0.0, 0.5, 0.5, 1.0):  # classical Butcher tableau
+        x_stage = xt if not stages else xt + c * stages[-1]
+        stages.append(dt * f(x_stage, ut))
+    return xt + (stages[0] + 2.0 * (stages[1] + stages[2]) + stages[3]) / 6.0
+
+
 _KINDS = {"single": cabi.DYN_SINGLE, "double": cabi.DYN_DOUBLE, "speed": cabi.DYN_SPEED, "roll": cabi.DYN_ROLL}
 
 

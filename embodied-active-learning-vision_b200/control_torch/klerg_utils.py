@@ -35,6 +35,35 @@ def _pairwise(mode, traj, samples, explr_idx, std, nu):
     return out[0, : s_dev.shape[0]].to(device=samples.device, dtype=samples.dtype)
 
 
+def _psi(traj, samples, std, nu, want_psi, want_dpsi):
+    import ctypes as C
+    t = _f32_dev(traj).reshape(-1, traj.shape[-1])
+    s = _f32_dev(samples).reshape(-1, samples.shape[-1])
+    D = s.shape[1]
+    spec = _spec(D, list(range(D)), std, nu)
+    n, T = s.shape[0], t.shape[0]
+    psi = torch.empty((n, T), dtype=torch.float32, device=s.device) if want_psi else None
+    dpsi = torch.empty((n, T, D), dtype=torch.float32, device=s.device) if want_dpsi else None
+    cabi.check(cabi.load().klerg_psi_matrix(C.byref(spec), cabi.ptr(t), T, cabi.ptr(s), n, cabi.ptr(psi), cabi.ptr(dpsi),
+                                            cabi.stream_ptr()), "klerg_psi_matrix")
+    return psi, dpsi
+
+
+def psi_fn(traj, samples, std, nu):
+    """psi[i, j] = exp(-0.5 sum_d (traj_jd - samples_id)^2 / std_d) / nu  (reference klerg_utils.py:7-10).
+
+    traj [1, T, D] (or [T, D]), samples [N, 1, D] (or [N, D]) -> [N, T].  |std| is used, as every caller of the
+    reference passes abs(std)."""
+    psi, _ = _psi(traj, samples, std, nu, True, False)
+    return psi.to(device=samples.device, dtype=samples.dtype)
+
+
+def dpsi_dx_fn(x_explr, samples, std, nu):
+    """-(x - s_i)/std * psi(x, s_i) for one state x [D] -> [N, D]  (reference klerg_utils.py:12-15)."""
+    _, dpsi = _psi(x_explr.reshape(1, -1), samples, std, nu, False, True)
+    return dpsi[:, 0, :].to(device=samples.device, dtype=samples.dtype)
+
+
 def traj_footprint_vec(traj, samples, explr_idx, std, nu):
     """q_i = sum_j psi(traj_j[explr], samples_i)   (reference klerg_utils.py:17-22)."""
     return _pairwise(0, traj, samples, explr_idx, std, nu)

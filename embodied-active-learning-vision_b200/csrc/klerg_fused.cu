@@ -144,6 +144,7 @@ struct EvalArgs {
   void* ws;
   // gradient-mode schedule
   int nchr, nsub, rounds;  // state chunks per round, sample sub-streams, rounds
+  int nwide;               // mixed schedule: the last `nwide` warps own WT+1 states, the others WT
   int ts;                  // samples staged per tile (multiple of 64)
   // outputs
   float* traj;           // [G][H+1][S] or NULL
@@ -426,13 +427,16 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
 // ---------------------------------------------------------------------------
 // gradient eval
 // ---------------------------------------------------------------------------
-template <int D, int WT, int MAXT>
+// MIXED: one chunk per warp, the last a.nwide warps own WT+1 states and the others WT, so that H states tile
+// any warp count exactly (no idle state slots) and the warp count can be a multiple of the 4 SM sub-partitions.
+template <int D, int WT, int MAXT, bool MIXED>
 __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int WTA = MIXED ? WT + 1 : WT;  // accumulator rows per warp
   const int H = a.H, S = a.d.S, A = a.d.A;
   const bool roll = a.d.kind == KLERG_DYN_ROLL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const SmemPlan sp = plan_grad<D>(H, S, A, roll, a.ts, nwarps, WT);
+  const SmemPlan sp = plan_grad<D>(H, S, A, roll, a.ts, nwarps, WTA);
   float* s_u = (float*)(smem + sp.u);
   float* s_traj = (float*)(smem + sp.traj);
   float* s_dbarr = (float*)(smem + sp.dbarr);
@@ -517,15 +521,23 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   double kl_a = 0.0, kl_c = 0.0;
   const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
   for (int r = 0; r < a.rounds; ++r) {
-    const int cw = warp % a.nchr, sub = warp / a.nchr;
-    const int t0 = (r * a.nchr + cw) * WT;
-    const bool active = sub < a.nsub && t0 < H;
-    u64 xs2[WT][D], acc[WT][D];
+    int cw = warp % a.nchr, sub = warp / a.nchr;
+    int t0 = (r * a.nchr + cw) * WT, my_wt = WT;
+    bool active = sub < a.nsub && t0 < H;
+    if (MIXED) {
+      const int narrow = nwarps - a.nwide;
+      const bool wide = warp >= narrow;
+      t0 = warp * WT + (wide ? warp - narrow : 0);
+      my_wt = WT + (wide ? 1 : 0);
+      sub = 0;
+      active = true;
+    }
+    u64 xs2[WTA][D], acc[WTA][D];
 #pragma unroll
-    for (int k = 0; k < WT; ++k)
+    for (int k = 0; k < WTA; ++k)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
-        const float x = (active && t0 + k < H) ? s_xs[(t0 + k) * D + d] : 0.f;
+        const float x = (active && k < my_wt && t0 + k < H) ? s_xs[(t0 + k) * D + d] : 0.f;
         xs2[k][d] = pack2(x, x);
         acc[k][d] = pack2(0.f, 0.f);
       }
@@ -597,23 +609,39 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
 #pragma unroll
           for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TS_ROW + i]);
           const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
-          pair_gradient<D, WT>(xs2, s2, w2, acc);
+          pair_gradient<D, WTA>(xs2, s2, w2, acc, my_wt == WTA);
         }
       }
     }
     __syncthreads();
     // lanes -> warp sums -> CTA partial for this round's states
 #pragma unroll
-    for (int k = 0; k < WT; ++k)
+    for (int k = 0; k < WTA; ++k)
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         float x, y;
         unpack2(acc[k][d], x, y);
         const float v = warp_sum_f(x + y);
-        if (lane == 0) s_part[(warp * WT + k) * D + d] = v;
+        if (lane == 0) s_part[(warp * WTA + k) * D + d] = v;
       }
     __syncthreads();
     float* gpart = (float*)ws_fused_grad(a.ws);  // [H*D][gstride] fp32 (the CTA sums are fp32 values)
+    if (MIXED) {
+      const int narrow = nwarps - a.nwide, narrow_states = narrow * WT;
+      for (int e = tid; e < HD; e += blockDim.x) {
+        const int t = e / D, d = e - t * D;
+        int w, k;
+        if (t < narrow_states) {
+          w = t / WT;
+          k = t - w * WT;
+        } else {
+          const int tt = t - narrow_states;
+          w = narrow + tt / (WT + 1);
+          k = tt - (w - narrow) * (WT + 1);
+        }
+        gpart[(size_t)e * gstride + blockIdx.x] = s_part[(w * WTA + k) * D + d];
+      }
+    } else
     for (int e = tid; e < a.nchr * WT * D; e += blockDim.x) {
       const int c = e / (WT * D), kd = e - c * (WT * D);
       const int t = (r * a.nchr + c) * WT + kd / D;
@@ -874,6 +902,8 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
 struct GradSchedule {
   int wt, nwarps, nchr, nsub, rounds;
   double eff;
+  bool mixed;
+  int nwide;
 };
 
 static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
@@ -881,6 +911,16 @@ static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
 // Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
 // CTA's warps with as few idle slots as possible.
 static GradSchedule plan_schedule(int D, int H) {
+  if (D >= 4) {
+    // mixed schedule: 16 warps (4 per SM sub-partition, 128 registers), H = q*16 + r -> r warps own q+1 states.
+    // Needs q >= 2 (fewer states per warp would re-read the staged samples too often for the shared-memory bandwidth).
+    const int nw = 16, q = H / nw, r = H % nw, wtmax = D == 4 ? 5 : 4;
+    if (q >= 2 && r > 0 && q + 1 <= wtmax) {
+      GradSchedule m{};
+      m.wt = q; m.nwarps = nw; m.nchr = nw; m.nsub = 1; m.rounds = 1; m.eff = 1.0; m.mixed = true; m.nwide = r;
+      return m;
+    }
+  }
   const int maxw = grad_max_warps(D);
   const int wts_small[5] = {5, 4, 3, 2, 1};
   const int wts_big[3] = {3, 2, 1};
@@ -972,10 +1012,10 @@ static int pick_grid(int64_t N, int per_sm, int min_samples_per_cta) {
   return (int)nblk;
 }
 
-template <int D, int WT>
+template <int D, int WT, bool MIXED = false>
 static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, cudaStream_t stream) {
-  constexpr int MAXT = (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
-  auto kernel = eval_grad_kernel<D, WT, MAXT>;
+  constexpr int MAXT = MIXED ? 512 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
+  auto kernel = eval_grad_kernel<D, WT, MAXT, MIXED>;
   const int nthreads = s.nwarps * 32;
   const bool roll = a.d.kind == KLERG_DYN_ROLL;
   // tile: up to 2048 samples, but no more than one CTA's slice at full grid
@@ -983,8 +1023,8 @@ static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, cudaStream_t strea
   int ts = 2048;
   while (ts > 64 && ts / 2 >= per) ts /= 2;
   a.ts = ts;
-  a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds;
-  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, ts, s.nwarps, WT);
+  a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds; a.nwide = s.nwide;
+  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, ts, s.nwarps, MIXED ? WT + 1 : WT);
   if (sp.total > 220 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
   const int per_sm = resident_ctas(kernel, nthreads, sp.total);
   if (per_sm < 1) { set_error("eval_gradient: kernel does not fit on an SM (threads=%d smem=%zu)", nthreads, sp.total); return -4; }
@@ -995,6 +1035,17 @@ static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, cudaStream_t strea
 template <int D>
 static int launch_grad_d(EvalArgs& a, cudaStream_t stream) {
   const GradSchedule s = plan_schedule(D, a.H);
+  if constexpr (D >= 4) {
+    if (s.mixed) {
+      if (s.wt == 2) return launch_grad_wt<D, 2, true>(a, s, stream);
+      if (s.wt == 3) return launch_grad_wt<D, 3, true>(a, s, stream);
+      if constexpr (D == 4) {
+        if (s.wt == 4) return launch_grad_wt<D, 4, true>(a, s, stream);
+      }
+      set_error("eval_gradient: no mixed schedule for D=%d H=%d", D, a.H);
+      return -2;
+    }
+  }
   switch (s.wt) {
     case 1: return launch_grad_wt<D, 1>(a, s, stream);
     case 2: return launch_grad_wt<D, 2>(a, s, stream);

@@ -113,10 +113,13 @@ __device__ __forceinline__ void pair_forward(const u64* __restrict__ sh_x2, int 
 // Gradient pair update: WT duplicated states (registers) against one packed sample pair with
 // packed importance weights w2:  acc[k][d] += w * psi * (x'_kd - s'_d)   (klerg_utils.py:12-15,31-36;
 // the -1/(a*|scale|*nu) factor is applied once at the end, KernelDev::gfac).
+// `full` = false skips the last state (warp-uniform): warps of one CTA may own WT-1 or WT states.
 template <int D, int WT>
-__device__ __forceinline__ void pair_gradient(const u64 (&xs2)[WT][D], const u64 (&s2)[D], u64 w2, u64 (&acc)[WT][D]) {
+__device__ __forceinline__ void pair_gradient(const u64 (&xs2)[WT][D], const u64 (&s2)[D], u64 w2, u64 (&acc)[WT][D],
+                                              bool full = true) {
 #pragma unroll
   for (int k = 0; k < WT; ++k) {
+    if (k == WT - 1 && !full) break;
     u64 df[D];
     const u64 e = sqdist2<D>(xs2[k], s2, df);
     float e0, e1;

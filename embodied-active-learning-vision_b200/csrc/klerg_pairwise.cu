@@ -402,9 +402,44 @@ static int launch_grad_d(const GradArgs& a, cudaStream_t stream) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// a1: the kernel matrix itself (psi_fn, klerg_utils.py:7-10) and its derivative for one state
+// (dpsi_dx_fn, :12-15).  Not on the planner's path (it never materialises N x T); exported for the
+// callers of the reference's free functions.
+// ---------------------------------------------------------------------------
+__global__ void psi_matrix_kernel(KernelDev k, const float* __restrict__ states, int64_t T,
+                                  const float* __restrict__ samples, int64_t N, float* __restrict__ psi,
+                                  float* __restrict__ dpsi) {
+  const int64_t total = N * T;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / T, j = e - i * T;
+    float acc = 0.f, df[KLERG_MAX_D];
+    for (int d = 0; d < k.D; ++d) {
+      df[d] = (states[j * k.S + k.explr[d]] - samples[i * k.D + d]) * k.a[d];
+      acc = fmaf(df[d], df[d], acc);
+    }
+    const float v = ex2_approx(-acc) * k.inv_nu;
+    if (psi) psi[e] = v;
+    if (dpsi)  // -(x - s)/|scale| * psi, one row of D values per (sample, state)
+      for (int d = 0; d < k.D; ++d) dpsi[e * k.D + d] = df[d] * k.gfac[d] * (v / k.inv_nu);
+  }
+}
+
 }  // namespace klerg
 
 using namespace klerg;
+
+extern "C" int klerg_psi_matrix(const klerg_kernel_spec* k, const float* states, int64_t T, const float* samples,
+                                int64_t N, float* psi, float* dpsi, void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (T < 0 || N < 0) { set_error("psi_matrix: bad sizes"); return -1; }
+  if (T * N == 0) return 0;
+  int64_t blocks = (T * N + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  psi_matrix_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kd, states, T, samples, N, psi, dpsi);
+  return check_launch("psi_matrix_kernel");
+}
 
 extern "C" int klerg_pack_samples(const klerg_kernel_spec* k, const float* samples, int64_t N, float* packed,
                                   int64_t ld, void* stream) {

@@ -104,6 +104,12 @@ int klerg_footprint(const klerg_kernel_spec* k, int mode, const float* states, i
                     int64_t seg_stride, const float* packed, int64_t N, int64_t ld, const float* add_in,
                     float* out, int64_t out_stride, double* totals, void* workspace, void* stream);
 
+/* a1: psi_fn / dpsi_dx_fn (klerg_utils.py:7-15) materialised: psi[N][T] = psi(states_j[explr], samples_i)
+ * and / or dpsi[N][T][D] = -(x_j - s_i)/|scale| * psi * nu (dpsi_dx_fn divides by nu once, through psi).
+ * `samples` are the raw AoS samples [N][D].  Either output may be NULL. */
+int klerg_psi_matrix(const klerg_kernel_spec* k, const float* states, int64_t T, const float* samples, int64_t N,
+                     float* psi, float* dpsi, void* stream);
+
 /* ---- a5 / a6: renormalize, cost_norm (klerg_utils.py:38-58) --------------- */
 
 /* stats[0..3] = {sum, max, min, #nan} of x[0..N). */

@@ -80,9 +80,11 @@ def test_config3_batched_candidates():
     assert torch.equal(one, got[[3, 40]])
 
 
-def test_config4_pose_workspace_long_history():
-    """6-D pose (roll dynamics), 3e4 samples, 2000 history states: cost + gradient eval vs the oracle."""
-    s = setup("c4", 30_000, 2_000, H=20)
+@pytest.mark.parametrize("H", [20, 50])
+def test_config4_pose_workspace_long_history(H):
+    """6-D pose (roll dynamics), 3e4 samples, 2000 history states: cost + gradient eval vs the oracle.
+    H=50 exercises the mixed schedule (14 warps own 3 states, 2 warps own 4), H=20 the uniform one."""
+    s = setup("c4", 30_000, 2_000, H=H)
     U = wl.random_controls((3, s["H"], s["D"]), seed=5)
     got = s["ctx"].costs(U.to(s["dev"])).cpu()
     for b in range(3):

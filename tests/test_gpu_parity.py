@@ -69,6 +69,20 @@ def test_pairwise_utils_vs_golden_and_oracle(ct, utils, D):
     rel_close(ct.ku.cost_norm(q.clone()), utils[f"D{D}/cost_norm"], what="cost_norm")
 
 
+def test_kernel_matrix_functions(ct, utils):
+    """psi_fn / dpsi_dx_fn (klerg_utils.py:7-15) and the generic rk4_integrate (dynamics.py:7-13)."""
+    t = lambda k: torch.from_numpy(utils[f"D3/{k}"])
+    traj, samples, std, nu = t("traj")[:, :3].contiguous(), t("samples"), torch.abs(t("std")), t("nu")
+    want = ko.kernel_matrix(traj.unsqueeze(0), samples.unsqueeze(1), std, nu)
+    rel_close(ct.ku.psi_fn(traj.unsqueeze(0), samples.unsqueeze(1), std, nu), want, what="psi_fn")
+    x = traj[4]
+    want_d = -(x - samples) / std * ko.kernel_matrix(x.reshape(1, 1, -1), samples.unsqueeze(1), std, nu)
+    rel_close(ct.ku.dpsi_dx_fn(x, samples, std, nu), want_d, atol_frac=1e-6, what="dpsi_dx_fn")
+    f = lambda xx, uu: torch.stack([xx[1], -xx[0] + uu[0]])
+    x0, u0 = torch.tensor([0.3, -0.2]), torch.tensor([0.5])
+    rel_close(ct.kd.rk4_integrate(f, 0.1, x0, u0), ko.rk4(f, 0.1, x0, u0), rtol=1e-6, what="rk4_integrate")
+
+
 def test_renormalize_floor_nan_and_dim(ct, utils):
     x = torch.from_numpy(utils["floor/x"])
     rel_close(ct.ku.renormalize(x.clone()), utils["floor/renorm"])
