@@ -1,0 +1,80 @@
+"""Error behaviour of the C ABI (no GPU needed: arguments are validated on the host before any launch).
+The reference raises Python exceptions for bad arguments; the library returns a negative status and a
+message through klerg_last_error(), and the ctypes layer turns that into RuntimeError."""
+import ctypes as C
+
+import pytest
+
+from control_torch import _cabi as cabi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return cabi.load()
+
+
+def spec(D=2, S=4, scale=0.05):
+    return cabi.kernel_spec(D, S, list(range(D)), [scale] * D, 1.0)
+
+
+def err(lib):
+    return lib.klerg_last_error().decode()
+
+
+def test_kernel_spec_validation(lib):
+    bad = spec()
+    bad.D = 9  # > KLERG_MAX_D
+    assert lib.klerg_pack_samples(C.byref(bad), None, 0, None, 0, None) == -1
+    assert "out of range" in err(lib)
+    bad = spec(scale=0.0)
+    assert lib.klerg_pack_samples(C.byref(bad), None, 4, None, 4, None) == -1
+    assert "non-zero" in err(lib)
+    bad = spec()
+    bad.explr[1] = 7  # column outside the state row
+    assert lib.klerg_footprint(C.byref(bad), 0, None, 1, 0, 0, None, 4, 4, None, None, 4, None, None, None) == -1
+    assert "explr" in err(lib)
+
+
+def test_size_validation(lib):
+    k = spec()
+    assert lib.klerg_pack_samples(C.byref(k), None, 8, None, 6, None) == -1  # ld < N
+    assert lib.klerg_footprint(C.byref(k), 2, None, 1, 0, 0, None, 4, 4, None, C.c_void_p(8), 4, C.c_void_p(8),
+                               C.c_void_p(8), None) == -1  # mode must be 0 / 1
+    assert "mode" in err(lib)
+    assert lib.klerg_kl_gradient(C.byref(k), None, 0, None, 4, 4, None, None, None, None) == -1  # H < 1
+    dyn = cabi.dyn_spec(cabi.DYN_DOUBLE, 5, 2, 0.1)  # S must be 2A
+    assert lib.klerg_rollout(C.byref(dyn), None, None, None, None, 1, 3, None, None, None, None, None, None) == -1
+    assert "inconsistent" in err(lib)
+
+
+def test_fused_eval_validation(lib):
+    k = spec(D=3, S=6)
+    dyn = cabi.dyn_spec(cabi.DYN_DOUBLE, 6, 3, 0.2)
+    three = cabi.farr([1.0] * 3)
+    args = (C.byref(k), C.byref(dyn), None, None, None, None, None)
+    # horizon out of range
+    assert lib.klerg_eval_gradient(*args, 0, None, 8, 8, None, None, None, 1e-6, three, 1.0, three, three, None, None,
+                                   None, None, None, None, None, None, None, None, None) == -1
+    assert "H out of range" in err(lib)
+    # more candidates than one fused launch takes
+    assert lib.klerg_eval_costs(*args, 9, 4, None, 8, 8, None, None, None, 1e-6, None, None, None, None, None, None) == -1
+    assert "G must be" in err(lib)
+    # sample leading dimension must be a multiple of 4 and >= N
+    assert lib.klerg_eval_costs(*args, 2, 4, None, 8, 6, None, None, None, 1e-6, None, None, None, None, None, None) == -1
+    peers = cabi.Peers()
+    peers.world, peers.rank = 9, 0
+    assert lib.klerg_eval_costs(C.byref(k), C.byref(dyn), None, C.byref(peers), None, None, None, 2, 4, None, 8, 8, None,
+                                None, None, 1e-6, None, None, None, None, None, None) == -1
+    assert "world/rank" in err(lib)
+
+
+def test_python_layer_raises_without_gpu_or_on_status():
+    import torch
+    with pytest.raises(RuntimeError, match="status -1"):
+        cabi.check(-1, "klerg_something")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            cabi.require_cuda()
+        from control_torch import klerg_utils as ku
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ku.traj_footprint_vec(torch.zeros(3, 4), torch.zeros(5, 2), [0, 1], torch.tensor([0.1, 0.1]), 1.0)
