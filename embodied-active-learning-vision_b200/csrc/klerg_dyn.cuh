@@ -173,6 +173,29 @@ __host__ __device__ inline int rollout_rot_floats(int G, int H) { return G * (2 
 //   R_out   [G][9]       rotation after the last step (global or shared, may be NULL)
 // Ends with a __syncthreads().
 // ---------------------------------------------------------------------------
+// Running sum by ONE warp: out[k] = init + x[0] + ... + x[k] (inclusive) or init + x[0] + ... + x[k-1] (exclusive)
+// for k < n, 32 elements per pass with a 5-step shuffle scan and a carry between passes.  `get(k)` supplies x[k],
+// `put(k, v)` receives the result.  A lone warp executing a serial recurrence costs ~100 cycles per step (every
+// instruction waits for its predecessor); the scan does 32 steps in about as many cycles.  Returns init + total.
+template <typename Get, typename Put>
+__device__ __forceinline__ float warp_running_sum(int n, float init, bool exclusive, Get get, Put put) {
+  const int lane = threadIdx.x & 31;
+  float carry = init;
+  for (int base = 0; base < n; base += 32) {
+    const int k = base + lane;
+    const float own = k < n ? get(k) : 0.f;
+    float v = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (k < n) put(k, carry + (exclusive ? v - own : v));
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  return carry;
+}
+
 #ifdef KLERG_STAMPS
 __device__ long long g_ro_stamp[8];
 #define RO_STAMP(i) if (blockIdx.x == 0 && threadIdx.x == 0) g_ro_stamp[i] = clock64()
@@ -190,36 +213,30 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
   const bool single = kind == KLERG_DYN_SINGLE, speed = kind == KLERG_DYN_SPEED, roll = kind == KLERG_DYN_ROLL;
   const float dt = pp.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
   RO_STAMP(0);
-  // (A) running sums, one lane per (candidate, control)
-  for (int l = tid; l < G * a; l += nthr) {
+  // (A) running sums, one warp per (candidate, control): vel_t = v0 + dt sum_{k<t} u_k, then
+  //     pos_t = p0 + sum_{k<t} (0.8 dt vel_k + 0.4 dt^2 u_k)  (the closed-form RK4 step summed over time)
+  for (int l = tid >> 5; l < G * a; l += nthr >> 5) {
     const int g = l / a, i = l - g * a;
     const float* us = s_u + (size_t)g * H * a;
     float* tr = s_traj + (size_t)g * (H + 1) * S;
-    float pos = x0[i];
-    float vel = single ? 0.f : x0[a + i];
-    float mag = speed ? x0[2 * a + i] : 0.f;
-    // rolled on purpose (this code runs once per launch from a cold instruction cache, where size is what
-    // costs time); the control is fetched two steps ahead so the shared-memory latency overlaps the recurrence
-    float u0 = H > 0 ? us[i] : 0.f, u1 = H > 1 ? us[a + i] : 0.f;
-#pragma unroll 1
-    for (int t = 0; t < H; ++t) {
-      const float u2 = (t + 2 < H) ? us[(t + 2) * a + i] : 0.f;
-      tr[t * S + i] = pos;
-      if (!single) tr[t * S + a + i] = vel;
-      if (speed) tr[t * S + 2 * a + i] = mag;
-      if (single) {
-        pos = pos + dt * u0;
-      } else {
-        pos = pos + (c1 * vel + c2 * u0);
-        vel = vel + dt * u0;
-        if (speed) mag = fabsf(vel);
-      }
-      u0 = u1;
-      u1 = u2;
+    const float p0 = x0[i], v0 = single ? 0.f : x0[a + i];
+    if ((tid & 31) == 0) {
+      tr[i] = p0;
+      if (!single) tr[a + i] = v0;
+      if (speed) tr[2 * a + i] = x0[2 * a + i];
     }
-    tr[H * S + i] = pos;
-    if (!single) tr[H * S + a + i] = vel;
-    if (speed) tr[H * S + 2 * a + i] = mag;
+    if (single) {
+      warp_running_sum(H, p0, false, [&](int k) { return dt * us[k * a + i]; }, [&](int k, float v) { tr[(k + 1) * S + i] = v; });
+    } else {
+      warp_running_sum(H, v0, false, [&](int k) { return dt * us[k * a + i]; },
+                       [&](int k, float v) {
+                         tr[(k + 1) * S + a + i] = v;
+                         if (speed) tr[(k + 1) * S + 2 * a + i] = fabsf(v);
+                       });
+      __syncwarp();
+      warp_running_sum(H, p0, false, [&](int k) { return c1 * tr[k * S + a + i] + c2 * us[k * a + i]; },
+                       [&](int k, float v) { tr[(k + 1) * S + i] = v; });
+    }
   }
   __syncthreads();
   RO_STAMP(1);
@@ -369,25 +386,17 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
   float* s_a = s_rm + H * A;        // g_v - P^T rho_p
   float* s_b = s_a + H * A;         // P^T g_p
   float* s_btr = s_b + H * A;       // B^T rho after step t
-  if (tid < A) {
-    float rp = 0.f, rm = 0.f;
-    // rolled, operands fetched two steps ahead (see rollout_block)
-    float g0 = H > 0 ? sg[(H - 1) * S + tid] : 0.f, g1 = H > 1 ? sg[(H - 2) * S + tid] : 0.f;
-    float m0 = (speed && H > 0) ? sg[(H - 1) * S + 2 * A + tid] : 0.f, m1 = (speed && H > 1) ? sg[(H - 2) * S + 2 * A + tid] : 0.f;
-#pragma unroll 1
-    for (int t = H - 1; t >= 0; --t) {
-      const float g2 = (t >= 2) ? sg[(t - 2) * S + tid] : 0.f;
-      const float m2 = (speed && t >= 2) ? sg[(t - 2) * S + 2 * A + tid] : 0.f;
-      s_rp[t * A + tid] = rp;
-      rp = rp + h * g0;
-      if (single) s_btr[t * A + tid] = rp;
-      if (speed) {
-        rm = rm + h * m0;
-        s_rm[t * A + tid] = rm;
-      }
-      g0 = g1; g1 = g2;
-      m0 = m1; m1 = m2;
-    }
+  // rho_p (and rho_m) are running sums of h*g from the end of the horizon: one warp per control
+  for (int i = tid >> 5; i < A; i += nthr >> 5) {
+    // value BEFORE the update of step t = sum over later steps (exclusive), value after = inclusive
+    warp_running_sum(H, 0.f, !single, [&](int k) { return h * sg[(H - 1 - k) * S + i]; },
+                     [&](int k, float v) {
+                       if (single) s_btr[(H - 1 - k) * A + i] = v;
+                       else s_rp[(H - 1 - k) * A + i] = v;
+                     });
+    if (speed)
+      warp_running_sum(H, 0.f, false, [&](int k) { return h * sg[(H - 1 - k) * S + 2 * A + i]; },
+                       [&](int k, float v) { s_rm[(H - 1 - k) * A + i] = v; });
   }
   __syncthreads();
   if (!single) {
@@ -409,21 +418,18 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
       s_b[e] = ptg;
     }
     __syncthreads();
-    if (tid < A) {
-      float rv = 0.f;
-      float a0 = H > 0 ? s_a[(H - 1) * A + tid] : 0.f, a1 = H > 1 ? s_a[(H - 2) * A + tid] : 0.f;
-      float b0 = H > 0 ? s_b[(H - 1) * A + tid] : 0.f, b1 = H > 1 ? s_b[(H - 2) * A + tid] : 0.f;
-#pragma unroll 1
-      for (int t = H - 1; t >= 0; --t) {
-        const float a2 = (t >= 2) ? s_a[(t - 2) * A + tid] : 0.f;
-        const float b2 = (t >= 2) ? s_b[(t - 2) * A + tid] : 0.f;
-        rv = rv + h * a0 - 0.5f * h * h * b0;
-        float btr = rv;
-        if (speed) btr = rv + ((s_traj[t * S + A + tid] < 0.f) ? -1.f : 1.f) * s_rm[t * A + tid];
-        s_btr[t * A + tid] = btr;
-        a0 = a1; a1 = a2;
-        b0 = b1; b1 = b2;
-      }
+    for (int i = tid >> 5; i < A; i += nthr >> 5) {
+      warp_running_sum(H, 0.f, false,
+                       [&](int k) {
+                         const int t = H - 1 - k;
+                         return h * s_a[t * A + i] - 0.5f * h * h * s_b[t * A + i];
+                       },
+                       [&](int k, float rv) {
+                         const int t = H - 1 - k;
+                         float btr = rv;
+                         if (speed) btr = rv + ((s_traj[t * S + A + i] < 0.f) ? -1.f : 1.f) * s_rm[t * A + i];
+                         s_btr[t * A + i] = btr;
+                       });
     }
     __syncthreads();
   }
