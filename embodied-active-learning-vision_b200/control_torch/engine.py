@@ -358,7 +358,7 @@ def debug_stamps():
     key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
     ws = _workspaces[key]
     off = cabi.load().klerg_debug_stamps_offset()
-    return ws.buf[off:off + 120].view(torch.int64).cpu().tolist()
+    return ws.buf[off:off + 144].view(torch.int64).cpu().tolist()
 
 
 def fused_fault():

@@ -267,25 +267,44 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
         for (int i = 0; i < 9; ++i) s_R[(size_t)g * (H + 1) * 9 + i] = R[i];
     }
     __syncthreads();
-    // (C) serial chain of 3x3 products, one lane per candidate
-    if (tid < G) {
-      float* Rg = s_R + (size_t)tid * (H + 1) * 9;
-      const float* Eg = s_E + (size_t)tid * H * 9;
-      float R[9];
-      for (int i = 0; i < 9; ++i) R[i] = Rg[i];
-      for (int t = 0; t < H; ++t) {
-        float E[9], Rn[9];
+    RO_STAMP(5);
+    // (C) R_{t+1} = E_t E_{t-1} ... E_0 R_0: matrix products are associative, so one warp per candidate forms
+    //     the running products with a shuffle scan (32 steps per pass) instead of a serial chain
+    for (int g = tid >> 5; g < G; g += nthr >> 5) {
+      const int lane = tid & 31;
+      float* Rg = s_R + (size_t)g * (H + 1) * 9;
+      const float* Eg = s_E + (size_t)g * H * 9;
+      float carry[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) E[i] = Eg[t * 9 + i];
-        matmul3(E, R, Rn);
+      for (int i = 0; i < 9; ++i) carry[i] = Rg[i];
+      for (int base = 0; base < H; base += 32) {
+        const int k = base + lane;
+        float v[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          R[i] = Rn[i];
-          Rg[(t + 1) * 9 + i] = Rn[i];
+        for (int i = 0; i < 9; ++i) v[i] = (k < H) ? Eg[k * 9 + i] : ((i % 4 == 0) ? 1.f : 0.f);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float t[9], n[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) t[i] = __shfl_up_sync(0xffffffffu, v[i], o);
+          matmul3(v, t, n);  // later * earlier
+          if (lane >= o) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = n[i];
+          }
         }
+        float r[9];
+        matmul3(v, carry, r);
+        if (k < H) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Rg[(k + 1) * 9 + i] = r[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) carry[i] = __shfl_sync(0xffffffffu, r[i], 31);
       }
     }
     __syncthreads();
+    RO_STAMP(6);
     // (D1) angles of R_t overwrite the integrated angle positions (dynamics.py:291-301)
     for (int e = tid; e < G * H; e += nthr) {
       const int g = e / H, t = 1 + (e - g * H);
@@ -300,6 +319,7 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
     if (R_out)
       for (int e = tid; e < G * 9; e += nthr) R_out[e] = s_R[((size_t)(e / 9) * (H + 1) + H) * 9 + e % 9];
     __syncthreads();
+    RO_STAMP(7);
     // (D2) linearisation block: 0.8 I with the rpw x rpw entries replaced by E(rot) R (dynamics.py:189-211,283-289)
     if (s_P) {
       for (int e = tid; e < G * H * a * a; e += nthr) {

@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     KLERG_STAMP(7);
     long long* dbg = (long long*)(ctrl + 16);
     for (int i = 0; i < 10; ++i) dbg[i] = stamp[i] - stamp[0];
-    for (int i = 0; i < 5; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];
+    for (int i = 0; i < 8; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];
 #endif
   }
 }
