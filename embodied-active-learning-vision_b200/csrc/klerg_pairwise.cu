@@ -120,6 +120,12 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
 #pragma unroll
       for (int q = 0; q < SPT; ++q) emin[q] = INFINITY;
 
+      // long state lists (history of 1e5 rows): every staged chunk is summed in a fresh accumulator and then
+      // added to the running total, so the fp32 rounding error grows with sqrt(rows per chunk) + sqrt(chunks)
+      // instead of sqrt(rows)
+      u64 total[P];
+#pragma unroll
+      for (int q = 0; q < P; ++q) total[q] = pack2(0.f, 0.f);
       for (int c = 0; c < nchunk; ++c) {
         int rows = rows_single;
         if (nchunk > 1) {
@@ -128,6 +134,17 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
           __syncthreads();
         }
         pair_forward<D, P, MODE>(sh, rows, s2, acc, emin);
+        if (MODE == 0 && nchunk > 1) {
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            total[q] = add2(total[q], acc[q]);
+            acc[q] = pack2(0.f, 0.f);
+          }
+        }
+      }
+      if (MODE == 0 && nchunk > 1) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) acc[q] = total[q];
       }
 
       // epilogue: scale, add base, store, local totals
