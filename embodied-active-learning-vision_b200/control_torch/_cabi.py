@@ -114,6 +114,8 @@ SIGNATURES = {
     "klerg_fused_fault_offset": [],
     "klerg_eval_gradient": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _P, _F, _FP, _F, _FP, _FP,
                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "klerg_eval_gradient_targets": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _I64, _P, _F, _FP, _F,
+                                    _FP, _FP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "klerg_eval_costs": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P,
                          _P, _P],
 }

@@ -342,6 +342,26 @@ def eval_gradient(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, p, p_stat
     return out
 
 
+def eval_gradient_targets(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, P, P_stats, rinv, alpha, ctrl_lo, ctrl_hi,
+                          v_scratch, floor=FLOOR):
+    """One fused launch for K belief targets P [K, stride]: shared rollout / forward pass / q, per-target gradient
+    and adjoint (klerg_eval_gradient_targets) -> dict of [K, ...] tensors."""
+    K, stride = P.shape
+    H, A, S = u.shape[-2], dyn.A, dyn.S
+    dev = P.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = dict(dgdx=torch.empty((K, H, S), **f32), du=torch.empty((K, H, A), **f32), djdlam=torch.empty((K, H), **f32),
+               u_star=torch.empty((K, H, A), **f32), traj=torch.empty((H + 1, S), **f32),
+               totals=torch.empty((1, 2), dtype=torch.float64, device=dev))
+    cabi.check(cabi.load().klerg_eval_gradient_targets(
+        C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, peers, cabi.ptr(x0), cabi.ptr(R0),
+        cabi.ptr(u), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(q_base), cabi.ptr(P), K, stride,
+        cabi.ptr(P_stats), float(floor), rinv, float(alpha), ctrl_lo, ctrl_hi, cabi.ptr(v_scratch), cabi.ptr(out["traj"]),
+        cabi.ptr(out["totals"]), None, cabi.ptr(out["dgdx"]), cabi.ptr(out["du"]), cabi.ptr(out["djdlam"]),
+        cabi.ptr(out["u_star"]), None, workspace(8), cabi.stream_ptr()), "klerg_eval_gradient_targets")
+    return out
+
+
 def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, v_scratch, cost, floor=FLOOR):
     """One fused launch: get_cost of G <= 8 candidates U [G,H,A] -> cost [G] (klerg_eval_costs)."""
     G, H, _ = U.shape

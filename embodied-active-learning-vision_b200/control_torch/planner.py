@@ -139,7 +139,11 @@ class PlannerContext:
     # -- K belief targets over one workspace (fingerprint test mode, BASELINE config 5) ------------------
     def set_targets(self, P, P_stats):
         """P [K, n_local] target densities p_k on the device, P_stats [K, 1] = their global sums."""
-        self.P, self.P_stats = P.contiguous(), P_stats.contiguous()
+        K, n = P.shape
+        ld = self.packed.shape[1]
+        self.P = torch.zeros((K, ld), dtype=torch.float32, device=P.device)  # rows padded to the sample stride
+        self.P[:, :n] = P
+        self.P_stats = P_stats.reshape(K).contiguous()
 
     def costs_targets(self, U):
         """cost[k, b] = KL(p_k || q_b) + barrier_b for every target k and candidate b."""
@@ -147,27 +151,40 @@ class PlannerContext:
         out = []
         try:
             for k in range(self.P.shape[0]):
-                self.set_target(self.P[k], self.P_stats[k])
+                self.set_target(self.P[k, : self.n].contiguous(), self.P_stats[k: k + 1])
                 out.append(self.costs(U).clone())
         finally:
             self.p, self.p_stats = saved
         return torch.stack(out)
 
     def gradient_targets(self, u):
-        """Per-target gradient eval: dict of [K, ...] stacked du, djdlam, u_star, dgdx (one fused launch per target;
-        the forward pass is recomputed per target - a shared-psi multi-target kernel is the next step)."""
-        saved = (self.p, self.p_stats)
-        keys = ("du", "djdlam", "u_star", "dgdx")
-        acc = {k: [] for k in keys}
-        try:
-            for k in range(self.P.shape[0]):
-                self.set_target(self.P[k], self.P_stats[k])
-                g = self.gradient(u)
-                for key in keys:
-                    acc[key].append(g[key].clone())
-        finally:
-            self.p, self.p_stats = saved
-        return {k: torch.stack(v) for k, v in acc.items()}
+        """Per-target gradient eval: dict of [K, ...] stacked du, djdlam, u_star, dgdx.  One fused launch: rollout,
+        forward pair pass and q are shared by the targets, the gradient pair pass and the adjoint run per target
+        (up to 32 targets per launch)."""
+        K = self.P.shape[0]
+        u = u.reshape(self.H, -1).contiguous()
+        if not self.fused:
+            saved, acc = (self.p, self.p_stats), {k: [] for k in ("du", "djdlam", "u_star", "dgdx")}
+            try:
+                for k in range(K):
+                    self.set_target(self.P[k, : self.n].contiguous(), self.P_stats[k: k + 1])
+                    g = self.gradient(u)
+                    for key in acc:
+                        acc[key].append(g[key].clone())
+            finally:
+                self.p, self.p_stats = saved
+            return {k: torch.stack(v) for k, v in acc.items()}
+        outs = []
+        for k0 in range(0, K, 32):
+            k1 = min(K, k0 + 32)
+            outs.append(engine.eval_gradient_targets(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, u,
+                                                     self.packed, self.n, self.q_base, self.P[k0:k1], self.P_stats[k0:k1],
+                                                     self._rinv_c, self.alpha, self._lo_c, self._hi_c, self.buf.sets[0]["v"],
+                                                     self.floor))
+        self.evals["grad"] += K
+        self.evals["fwd_pairs"] += self.H * self.n * len(outs)
+        self.evals["grad_pairs"] += self.H * self.n * K
+        return {k: torch.cat([o[k] for o in outs]) for k in ("du", "djdlam", "u_star", "dgdx")}
 
     def q_from(self, v, totals_w):
         """renormalize(q_base + q_iter) given the forward output (for plot_data)."""

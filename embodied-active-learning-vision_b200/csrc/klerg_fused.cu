@@ -136,8 +136,10 @@ struct EvalArgs {
   const float* packed;   // [D][ld] scaled samples of this rank
   int64_t N, ld;
   const float* q_base;   // [N] or NULL
-  const float* p;        // [N]
-  const double* p_stats; // [1] = sum p over all ranks
+  const float* p;        // [K][p_stride] target densities (K = 1: [N])
+  int K;                 // belief targets sharing one workspace / trajectory (gradient eval)
+  int64_t p_stride;
+  const double* p_stats; // [K] = sum p_k over all ranks
   float floor;
   // scratch
   float* v;              // [G][ld]
@@ -219,7 +221,7 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, unsigned m
   const unsigned go_val = 2u * epoch + 1u;
   double* world = ws_fused_world(a.ws);
   const int par = mepoch & 1;
-  const unsigned tag = mepoch + 1u;
+  const unsigned tag = ((mepoch + 1u) << 6) | 63u;
   const int nq = 2 * G;
   if (threadIdx.x == 0) {
     __threadfence();
@@ -268,13 +270,13 @@ __device__ void meet_totals(const EvalArgs& a, int G, unsigned epoch, unsigned m
 }
 
 // Meeting point 2: returns true (all threads) in the last CTA to arrive.
-__device__ bool meet_last(const EvalArgs& a, int* sh_flag, int slot = 1) {
+__device__ bool meet_last(const EvalArgs& a, int* sh_flag, int slot = 1, unsigned round = 0) {
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned t = atomicAdd(&ctrl[slot], 1u);
-    *sh_flag = (t == gridDim.x - 1);
+    *sh_flag = (t == (round + 1u) * gridDim.x - 1u);
   }
   __syncthreads();
   const bool last = *sh_flag != 0;
@@ -283,13 +285,13 @@ __device__ bool meet_last(const EvalArgs& a, int* sh_flag, int slot = 1) {
 }
 
 // Plain grid barrier on ctrl[slot] (the counter is reset by the CTA that finishes the launch).
-__device__ void meet_all(const EvalArgs& a, int slot) {
+__device__ void meet_all(const EvalArgs& a, int slot, unsigned round = 0) {
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(&ctrl[slot], 1u);
-    KLERG_SPIN_UNTIL(ld_acquire_u32(&ctrl[slot]) >= gridDim.x, ctrl)
+    KLERG_SPIN_UNTIL(ld_acquire_u32(&ctrl[slot]) >= (round + 1u) * gridDim.x, ctrl)
     __threadfence();
   }
   __syncthreads();
@@ -297,10 +299,12 @@ __device__ void meet_all(const EvalArgs& a, int slot) {
 
 // Cross-rank all-gather of `n` doubles held in shared memory (sh_vals) by the last CTA:
 // on return sh_vals[i] = sum over ranks (rank order) of the ranks' sh_vals[i].
-__device__ void exchange_sum(const EvalArgs& a, unsigned mepoch, double* sh_vals, int n) {
+__device__ void exchange_sum(const EvalArgs& a, unsigned mepoch, double* sh_vals, int n, unsigned round = 0) {
   if (a.peers.world <= 1) return;
-  const int par = mepoch & 1;
-  const unsigned tag = mepoch + 1u;
+  // one use per target: slots alternate with (epoch + target), the tag names both (a rank can run at most one
+  // exchange ahead of a peer, because finishing an exchange needs every peer's contribution to it)
+  const int par = (mepoch + round) & 1;
+  const unsigned tag = ((mepoch + 1u) << 6) | (round & 31u);
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   __syncthreads();
   for (int e = threadIdx.x; e < n * a.peers.world; e += blockDim.x) {
@@ -518,8 +522,10 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   const int HD = H * D;
   const int nblk = gridDim.x;
   const int gstride = (nblk + 31) & ~31;  // partial layout [e][gstride]: the final reduce reads rows coalesced
-  double kl_a = 0.0, kl_c = 0.0;
   const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
+  for (int kt = 0; kt < a.K; ++kt) {  // belief targets: the forward pass above is shared, p_k differs
+  const float* p_k = a.p + (int64_t)kt * a.p_stride;
+  double kl_a = 0.0, kl_c = 0.0;
   for (int r = 0; r < a.rounds; ++r) {
     int cw = warp % a.nchr, sub = warp / a.nchr;
     int t0 = (r * a.nchr + cw) * WT, my_wt = WT;
@@ -559,11 +565,11 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
         cp_async16(buf + (size_t)D * TS_ROW + q4, a.v + i);
         float* prow = buf + (size_t)(D + 1) * TS_ROW + q4;
         if (i + 3 < a.N) {
-          cp_async16(prow, a.p + i);
+          cp_async16(prow, p_k + i);
         } else {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (i + q < a.N) cp_async4(prow + q, a.p + i + q);
+            if (i + q < a.N) cp_async4(prow + q, p_k + i + q);
             else prow[q] = 0.f;
           }
         }
@@ -657,7 +663,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     double vals[2] = {kl_a, kl_c};
     block_reduce<2>(kinds, vals, s_red);
     if (tid == 0) {
-      double* part = ws_fused_kl(a.ws) + (size_t)blockIdx.x * FUSED_MAXG * 2;
+      double* part = ws_fused_kl(a.ws) + (size_t)blockIdx.x * FUSED_MAXG * 2 + (kt & 1) * 2;
       part[0] = vals[0];
       part[1] = vals[1];
     }
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   // ---- phase 3: every CTA reduces a few gradient entries over all CTA partials (fixed order), then the last
   //      CTA to finish collects the H*D sums, exchanges them with the peers and runs the adjoint ----------------
   KLERG_STAMP(4);
-  meet_all(a, 1);
+  meet_all(a, 1, kt);
   double* gfin = (double*)((char*)ws_fused_grad(a.ws) + FUSED_GRAD / 2);  // [H*D]
   {
     const float* gpart = (const float*)ws_fused_grad(a.ws);
@@ -678,7 +684,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
       if (lane == 0) gfin[e] = v;
     }
   }
-  if (!meet_last(a, s_flag, 4)) return;
+  if (!meet_last(a, s_flag, 4, kt)) continue;
   KLERG_STAMP(5);
   double* s_val = (double*)s_tile;               // [HD + 2]
   float* s_g = (float*)(s_val + HD + 2);         // [H][S]
@@ -689,8 +695,8 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     if (warp == 0) {
       double s0 = 0.0, s1 = 0.0;
       for (int b = lane; b < nblk; b += 32) {
-        s0 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 0]);
-        s1 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + 1]);
+        s0 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + (kt & 1) * 2 + 0]);
+        s1 += __ldcg(&klp[(size_t)b * FUSED_MAXG * 2 + (kt & 1) * 2 + 1]);
       }
       s0 = warp_reduce(RED_SUM, s0);
       s1 = warp_reduce(RED_SUM, s1);
@@ -705,7 +711,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   }
   __syncthreads();
   KLERG_STAMP(6);
-  exchange_sum(a, mepoch, s_val, HD + 2);
+  exchange_sum(a, mepoch, s_val, HD + 2, kt);
   for (int e = tid; e < H * S; e += blockDim.x) s_g[e] = 0.f;
   __syncthreads();
   for (int e = tid; e < HD; e += blockDim.x) {
@@ -715,28 +721,31 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   __syncthreads();
   for (int e = tid; e < H * S; e += blockDim.x) {
     const float g = s_g[e];
-    a.dgdx[e] = g;
+    a.dgdx[(size_t)kt * H * S + e] = g;
     s_g[e] = g - s_dbarr[e];
   }
   __syncthreads();
-  adjoint_block(a.d, a.ap, H, s_g, s_P, s_traj, s_u, s_scr, a.du, a.djdlam, a.u_star);
+  adjoint_block(a.d, a.ap, H, s_g, s_P, s_traj, s_u, s_scr, a.du + (size_t)kt * H * A, a.djdlam + (size_t)kt * H,
+                a.u_star + (size_t)kt * H * A);
   if (tid == 0) {
     const double sa = s_val[HD], sc = s_val[HD + 1];
     if (a.kl_out) {
-      a.kl_out[0] = sa;
-      a.kl_out[1] = sc;
+      a.kl_out[2 * kt] = sa;
+      a.kl_out[2 * kt + 1] = sc;
     }
     if (a.cost) {
-      const double spv = a.p_stats[0];
+      const double spv = a.p_stats[kt];
       // KL of the PRE-step footprint (what backward() differentiates) + barrier of the post-step states
-      a.cost[0] = (float)(sa / spv - log(spv) + log(sc)) + *s_bsum;
+      a.cost[kt] = (float)(sa / spv - log(spv) + log(sc)) + *s_bsum;
     }
     unsigned* ctrl = ws_fused_ctrl(a.ws);
-    ctrl[0] = 0;
-    ctrl[1] = 0;
-    ctrl[4] = 0;
-    ctrl[3] = epoch + 1;
-    if (a.peers.world > 1) *mb_epoch(a.peers.mail[a.peers.rank]) = (unsigned long long)mepoch + 1ull;
+    if (kt == a.K - 1) {  // the CTA that finishes the last target closes the launch
+      ctrl[0] = 0;
+      ctrl[1] = 0;
+      ctrl[4] = 0;
+      ctrl[3] = epoch + 1;
+      if (a.peers.world > 1) *mb_epoch(a.peers.mail[a.peers.rank]) = (unsigned long long)mepoch + 1ull;
+    }
 #ifdef KLERG_STAMPS
     // phase stamps of the CTA that finished last (SM cycles since its start): profiling aid
     KLERG_STAMP(7);
@@ -745,6 +754,8 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     for (int i = 0; i < 8; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];
 #endif
   }
+  __syncthreads();  // the CTA that ran the adjoint reuses its tile area for the next target
+  }  // targets
 }
 
 // ---------------------------------------------------------------------------
@@ -1145,14 +1156,17 @@ extern "C" int klerg_mailbox_close(void* ptr, int owner) {
 extern "C" size_t klerg_fused_fault_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 5 * sizeof(unsigned); }
 extern "C" size_t klerg_debug_stamps_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 64; }
 
-extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
-                                   const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
-                                   const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
-                                   const double* p_stats, float floor, const float* Rinv_diag, float alpha,
-                                   const float* ctrl_lo, const float* ctrl_hi, float* v_scratch, float* traj,
-                                   double* totals, float* cost, float* dgdx, float* du, float* djdlam, float* u_star,
-                                   double* kl_out, void* workspace, void* stream) {
+extern "C" int klerg_eval_gradient_targets(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn,
+                                           const klerg_barrier_spec* bar, const klerg_peers* peers, const float* x0,
+                                           const float* R0, const float* u, int64_t H, const float* packed, int64_t N,
+                                           int64_t ld, const float* q_base, const float* p, int64_t K, int64_t p_stride,
+                                           const double* p_stats, float floor, const float* Rinv_diag, float alpha,
+                                           const float* ctrl_lo, const float* ctrl_hi, float* v_scratch, float* traj,
+                                           double* totals, float* cost, float* dgdx, float* du, float* djdlam,
+                                           float* u_star, double* kl_out, void* workspace, void* stream) {
   EvalArgs a{};
+  if (K < 1 || K > 32) { set_error("eval_gradient: K must be in 1..32 targets per launch"); return -1; }
+  if (K > 1 && (p_stride < N || (p_stride & 3))) { set_error("eval_gradient: p_stride must be >= N and a multiple of 4"); return -1; }
   if (!fill_common(a, k, dyn, bar, peers)) return -1;
   if (H < 1 || H > KLERG_MAX_H) { set_error("eval_gradient: H out of range"); return -1; }
   if (N < 1 || ld < N || (ld & 3)) { set_error("eval_gradient: bad sample sizes"); return -1; }
@@ -1161,6 +1175,7 @@ extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_s
   for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
   a.ap.alpha = alpha;
   a.x0 = x0; a.R0 = R0; a.u = u; a.G = 1; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base; a.p = p;
+  a.K = (int)K; a.p_stride = p_stride;
   a.p_stats = p_stats; a.floor = floor; a.v = v_scratch; a.ws = workspace; a.traj = traj; a.totals = totals; a.cost = cost;
   a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star; a.kl_out = kl_out;
   switch (a.k.D) {
@@ -1172,6 +1187,18 @@ extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_s
     case 6: return launch_grad_d<6>(a, (cudaStream_t)stream);
     default: set_error("eval_gradient: D=%d not instantiated (1..6)", a.k.D); return -2;
   }
+}
+
+extern "C" int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                                   const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
+                                   const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
+                                   const double* p_stats, float floor, const float* Rinv_diag, float alpha,
+                                   const float* ctrl_lo, const float* ctrl_hi, float* v_scratch, float* traj,
+                                   double* totals, float* cost, float* dgdx, float* du, float* djdlam, float* u_star,
+                                   double* kl_out, void* workspace, void* stream) {
+  return klerg_eval_gradient_targets(k, dyn, bar, peers, x0, R0, u, H, packed, N, ld, q_base, p, 1, 0, p_stats, floor,
+                                     Rinv_diag, alpha, ctrl_lo, ctrl_hi, v_scratch, traj, totals, cost, dgdx, du, djdlam,
+                                     u_star, kl_out, workspace, stream);
 }
 
 extern "C" int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
@@ -1187,7 +1214,7 @@ extern "C" int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec
   if (!workspace || !v_scratch || !cost) { set_error("eval_costs: null output/workspace"); return -1; }
   a.x0 = x0; a.R0 = R0; a.u = u; a.G = (int)G; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base;
   a.p = p; a.p_stats = p_stats; a.floor = floor; a.v = v_scratch; a.ws = workspace; a.traj = traj; a.totals = totals;
-  a.cost = cost;
+  a.cost = cost; a.K = 1; a.p_stride = 0;
   switch (a.k.D) {
     case 1: return launch_cost_d<1>(a, (cudaStream_t)stream);
     case 2: return launch_cost_d<2>(a, (cudaStream_t)stream);

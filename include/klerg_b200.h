@@ -258,6 +258,19 @@ int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, c
                         double* totals, float* cost, float* dgdx, float* du, float* djdlam, float* u_star,
                         double* kl_out, void* workspace, void* stream);
 
+/* The same for K <= 32 belief targets p_k over one workspace and one trajectory (fingerprint test mode,
+ * test_fingerprint_main.py swaps robot.target_dist between beliefs; BASELINE config 5): the rollout, the
+ * forward pair pass and q are shared, the gradient pair pass / reduction / adjoint run once per target inside
+ * the same launch.  p[K][p_stride] (p_stride >= N, multiple of 4), p_stats[K]; outputs are [K][...] stacked:
+ * cost[K], dgdx[K][H][S], du[K][H][A], djdlam[K][H], u_star[K][H][A], kl_out[K][2]. */
+int klerg_eval_gradient_targets(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                                const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
+                                const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
+                                int64_t K, int64_t p_stride, const double* p_stats, float floor,
+                                const float* Rinv_diag, float alpha, const float* ctrl_lo, const float* ctrl_hi,
+                                float* v_scratch, float* traj, double* totals, float* cost, float* dgdx, float* du,
+                                float* djdlam, float* u_star, double* kl_out, void* workspace, void* stream);
+
 /* Robot.get_cost (klerg.py:686-710) for G <= 8 candidate control sequences
  * u[G][H][A] in one launch (the line-search windows of klerg.py:712-751):
  * cost[g] = KL(p || renormalize(q_base + footprint(post-step states))) + barrier.

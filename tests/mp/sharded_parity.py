@@ -82,6 +82,30 @@ def main():
                 if not err < 1e-5:
                     ok = False
         dist.barrier()
+    # K belief targets in one launch: per-target exchanges alternate mailbox slots inside the kernel
+    K = 3
+    P_all = torch.stack([wl.make_target("gmm", lims, seed=30 + k, device=dev).pdf_torch(smp_all) for k in range(K)])
+    stats = torch.stack([P_all[k].double().sum().reshape(1) for k in range(K)])
+    ctx.set_targets(P_all[:, a:b].contiguous(), stats)
+    gt = ctx.gradient_targets(U[1])
+    torch.cuda.synchronize()
+    for key, v in gt.items():
+        ref = v.clone()
+        dist.broadcast(ref, 0)
+        if not torch.equal(ref, v):
+            print(f"[rank {rank}] targets/{key} differs from rank 0")
+            ok = False
+    if rank == 0:
+        single = build_ctx(probe, engine.SINGLE, smp_all, p_all, lo, hi, n_total, hist, x0, H)
+        single.set_targets(P_all.contiguous(), stats)
+        g1 = single.gradient_targets(U[1])
+        for key in gt:
+            x, y = gt[key].double().cpu().numpy(), g1[key].double().cpu().numpy()
+            err = np.abs(x - y).max() / (np.abs(y).max() + 1e-30)
+            print(f"targets {key}: max err / max|ref| = {err:.3e}")
+            if not err < 1e-5:
+                ok = False
+    dist.barrier()
     if engine.fused_fault():
         print(f"[rank {rank}] fused eval reported a meeting-point fault")
         ok = False
