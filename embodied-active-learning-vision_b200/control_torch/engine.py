@@ -41,7 +41,7 @@ _workspaces = {}
 
 
 def workspace(G=1):
-    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    key = (torch.cuda.current_device(), cabi.raw_stream())
     ws = _workspaces.get(key)
     if ws is None:
         ws = _workspaces[key] = Workspace()
@@ -313,10 +313,12 @@ class EvalBuffers:
         self.H, self.S, self.A, self.ld, self.max_g = H, S, A, ld, max_g
         self.sets = []
         for _ in range(n_sets):
+            # djdlam and u_star are what the host control flow reads after every gradient eval: one buffer, one D2H
+            host_pack = torch.empty(H + H * A, **f32)
             self.sets.append(dict(
                 v=torch.empty(ld, **f32), traj=torch.empty((H + 1, S), **f32), totals=torch.empty((1, 2), **f64),
                 cost=torch.empty(1, **f32), dgdx=torch.empty((H, S), **f32), du=torch.empty((H, A), **f32),
-                djdlam=torch.empty(H, **f32), u_star=torch.empty((H, A), **f32), kl=torch.empty(2, **f64)))
+                host_pack=host_pack, djdlam=host_pack[:H], u_star=host_pack[H:].view(H, A), kl=torch.empty(2, **f64)))
         self.turn = 0
         self.v_costs = torch.empty((max_g, ld), **f32)
 
@@ -375,7 +377,7 @@ def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, 
 
 def debug_stamps():
     """SM-cycle stamps of the last fused gradient eval on the current stream's workspace (8 int64)."""
-    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    key = (torch.cuda.current_device(), cabi.raw_stream())
     ws = _workspaces[key]
     off = cabi.load().klerg_debug_stamps_offset()
     return ws.buf[off:off + 144].view(torch.int64).cpu().tolist()
@@ -383,7 +385,7 @@ def debug_stamps():
 
 def fused_fault():
     """True if a fused eval on the current stream's workspace gave up waiting at a meeting point."""
-    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    key = (torch.cuda.current_device(), cabi.raw_stream())
     ws = _workspaces.get(key)
     if ws is None or ws.buf is None:
         return False

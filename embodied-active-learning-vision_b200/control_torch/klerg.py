@@ -398,7 +398,10 @@ class Robot(object):
         samples, hist_dev, nu = self.get_samples(num_target_samples, num_traj_samples)
         with torch.no_grad():
             H = self.horizon
+            prev = getattr(self, "ctx", None)
             ctx = self.ctx = self._context()
+            if prev is not None:
+                ctx.buf = prev.buf  # eval scratch / output buffers are reused from step to step when the shapes match
             samples_dev = self._shard(samples).to(self.cuda, non_blocking=True).contiguous()
             ctx.set_samples(samples_dev, self.std.tolist(), 1.0)
             ctx.set_state(self.robot.state.to(self.cuda, non_blocking=True))
@@ -416,8 +419,12 @@ class Robot(object):
                 g = ctx.gradient(u_tmp.to(self.cuda, non_blocking=True), keep=self.plot_data is not None)
                 self.stats["grad_evals"] += 1
                 prev_accepted, accepted = accepted, g
-                djdlam = g["djdlam"].cpu()
-                u_star = g["u_star"].cpu()
+                if "host_pack" in g:  # fused eval: djdlam and u* share one buffer -> a single D2H copy
+                    pack = g["host_pack"].cpu()
+                    djdlam, u_star = pack[:H], pack[H:].view(H, -1)
+                else:
+                    djdlam = g["djdlam"].cpu()
+                    u_star = g["u_star"].cpu()
                 t_app = torch.argmin(djdlam).item()
                 if djdlam[t_app] < 0:
                     u_app = u_star[t_app]

@@ -60,7 +60,7 @@ class PlannerContext:
         self.n = samples_dev.shape[0]
         self.packed = engine.pack_samples(self.spec, samples_dev)
         ld = self.packed.shape[1]
-        if self.buf is None or self.buf.ld != ld:
+        if self.buf is None or self.buf.ld != ld or self.buf.H != self.H or self.buf.A != self.dyn.A or self.buf.S != self.dyn.S:
             self.buf = engine.EvalBuffers(self.H, self.dyn.S, self.dyn.A, ld, samples_dev.device)
 
     def set_target(self, p, p_stats):
@@ -107,7 +107,8 @@ class PlannerContext:
             self.evals["grad"] += 1
             self.evals["fwd_pairs"] += self.H * self.n
             self.evals["grad_pairs"] += self.H * self.n
-            out = dict(du=o["du"], djdlam=o["djdlam"], u_star=o["u_star"], dgdx=o["dgdx"], traj=o["traj"][: self.H])
+            out = dict(du=o["du"], djdlam=o["djdlam"], u_star=o["u_star"], dgdx=o["dgdx"], traj=o["traj"][: self.H],
+                       host_pack=o["host_pack"])
             if want_cost:
                 out.update(kl_parts=o["kl"].unsqueeze(0), cost=o["cost"])
             if keep:
