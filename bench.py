@@ -454,6 +454,43 @@ def cuda_arm(args):
                                    "meeting points, serial rollout/adjoint), not throughput-bound"}}
         del S2
 
+    # ---- the other BASELINE configs, single GPU, short: c1 eval, c3 batched candidates, c5 belief targets ----
+    if also is not None and world == 1 and rank == 0:
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            return time_events(fn, reps) * 1e-3
+
+        S1 = build_sets("c1", wl.WORKLOADS["c1"]["N"], rank, group, dev, engine, Robot, PlannerContext, max_sets=8)
+        r1 = timed_evals(args, S1, 2000, 20, world, rank, lib, dev)
+        also["c1"] = {"workload": workload_config("c1", wl.WORKLOADS["c1"]["N"], S1["n"])["workload"],
+                      "us_per_eval": r1["ms_total"] / 2000 * 1e3, "evals_per_s": 2000 / (r1["ms_total"] * 1e-3)}
+        del S1
+        S3 = build_sets("c3", wl.WORKLOADS["c3"]["N"], rank, group, dev, engine, Robot, PlannerContext, max_sets=2)
+        c3 = S3["sets"][0]
+        c3.buf.v_costs = torch.empty((c3.buf.max_g, c3.buf.ld), dtype=torch.float32, device=dev)
+        gU = torch.Generator().manual_seed(2)
+        U3 = (c3.u.cpu().unsqueeze(0) + 0.1 * torch.randn(1024, S3["H"], S3["D"], generator=gU)).to(dev)
+        t3 = timed(lambda: c3.costs(U3), 3)
+        also["c3"] = {"workload": workload_config("c3", wl.WORKLOADS["c3"]["N"], S3["n"])["workload"] + " B=1024 candidates",
+                      "ms_per_batch": t3 * 1e3, "pairs_per_s": 1024 * S3["H"] * S3["n"] / t3, "candidates_per_s": 1024 / t3,
+                      "launches_per_batch": 128,
+                      "roofline_frac": 1024 * S3["H"] * S3["n"] * max((2 * S3["D"] + 1) / peaks["fp32_lane_ops_per_s"],
+                                                                    1 / peaks["ex2_per_s"]) / t3,
+                      "note": "get_cost of 1024 candidates: 8 candidates per fused launch, forward pair pass only"}
+        lims5 = [wl.LIMS[c] for c in wl.WORKLOADS["c5"]["states"]]
+        n5 = S3["n"]
+        smp5 = torch.rand(n5, S3["D"], device=dev) * 2.3 - 1.15
+        P5 = torch.stack([wl.make_target("gmm", lims5, seed=20 + k, device=dev).pdf_torch(smp5) for k in range(16)])
+        st5 = torch.stack([engine.vector_stats(P5[k].contiguous())[:1] for k in range(16)])
+        c3.set_targets(P5.contiguous(), st5)
+        t5 = timed(lambda: c3.gradient_targets(c3.u), 5)
+        also["c5"] = {"workload": "c5: states=xyz H=50 N=1000000 K=16 belief targets", "ms_per_16_target_gradient": t5 * 1e3,
+                      "pairs_per_s": (1 + 16) * S3["H"] * n5 / t5,
+                      "note": "one launch: shared rollout / forward pass / q, per-target gradient pass + adjoint"}
+        del S3, c3, U3, P5, smp5
+        torch.cuda.empty_cache()
+
     # ---- with several GPUs: the same eval with the per-GPU workspace held fixed (weak scaling) -------
     if world > 1 and not args.weak and not args.no_also:
         del S["sets"][:]

@@ -180,6 +180,41 @@ __device__ __forceinline__ void block_reduce(const int (&kind)[NQ], double (&val
   }
 }
 
+// Block reduction of G pairs {a_g, b_g} in one go (two barriers in total instead of two per candidate):
+// kind_b = RED_MAX or RED_SUM for the second member; results for all g valid in thread 0.
+__device__ __forceinline__ void block_reduce_pairs(int G, int kind_b, double (&va)[FUSED_MAXG], double (&vb)[FUSED_MAXG],
+                                                   double* sh_red /* [32 * 2 * FUSED_MAXG] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    if (g < G) {
+      const double x = warp_reduce(RED_SUM, va[g]);
+      const double y = warp_reduce(kind_b, vb[g]);
+      if (lane == 0) {
+        sh_red[(warp * FUSED_MAXG + g) * 2 + 0] = x;
+        sh_red[(warp * FUSED_MAXG + g) * 2 + 1] = y;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g) {
+      if (g < G) {
+        double x = lane < nwarp ? sh_red[(lane * FUSED_MAXG + g) * 2 + 0] : 0.0;
+        double y = lane < nwarp ? sh_red[(lane * FUSED_MAXG + g) * 2 + 1] : red_identity(kind_b);
+        x = warp_reduce(RED_SUM, x);
+        y = warp_reduce(kind_b, y);
+        if (lane == 0) {
+          va[g] = x;
+          vb[g] = y;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Meeting point 1: every CTA has written part_tot[blk][g][2]; on return world_tot[g][2]
 // (all CTAs, all ranks) is readable by every thread.  The last CTA to arrive is the leader.
@@ -381,14 +416,98 @@ __device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const u64* sh
   }
 }
 
-// small slices use one packed pair per thread so that more warps share the latency-bound work
+// Samples per thread-iteration: 2 (one packed pair) or 4.  A slice of n samples costs ceil(n / (threads * 2P)) * P
+// pair-iterations per thread; for slices of a few samples per thread the quantisation decides (e.g. 6757 samples on
+// 512 threads: 4 iterations of two pairs = 8, or 7 iterations of one pair = 7).
+__device__ __forceinline__ bool narrow_pairs(int64_t lo, int64_t hi) {
+  const int64_t n = hi - lo, bd = blockDim.x;
+  const int64_t it1 = (n + bd * 2 - 1) / (bd * 2), it2 = (n + bd * 4 - 1) / (bd * 4);
+  return it1 < 2 * it2 || it1 <= 1;
+}
+
 template <int D>
 __device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
                                               int64_t hi, double& tsum, double& tmax) {
-  if (hi - lo <= (int64_t)blockDim.x * 2)
+  if (narrow_pairs(lo, hi))
     forward_slice_p<D, 1>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
   else
     forward_slice_p<D, 2>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
+}
+
+// Forward pair pass of G candidate trajectories over this CTA's slice: samples are loaded once per thread and swept
+// against every candidate (the per-candidate totals live in a small indexed array: two local-memory accesses per
+// H pairs); v[g][i] to HBM, per-CTA {sum, max} partials per candidate.
+template <int D, int P>
+__device__ __forceinline__ void forward_candidates(const EvalArgs& a, const u64* s_x2, int G, int H, int64_t lo, int64_t hi,
+                                                   double* s_red) {
+  constexpr int SPT = 2 * P, DP = Row2<D>::DP;
+  const int tid = threadIdx.x;
+  double tsum[FUSED_MAXG], tmax[FUSED_MAXG];
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    tsum[g] = 0.0;
+    tmax[g] = -INFINITY;
+  }
+  for (int64_t i0 = lo + (int64_t)tid * SPT; i0 < hi; i0 += (int64_t)blockDim.x * SPT) {
+    u64 s2[D][P];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if constexpr (P == 2) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+        s2[d][1] = pack2(s.z, s.w);
+      } else {
+        const float2 s = __ldg(reinterpret_cast<const float2*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+      }
+    }
+    float qb[SPT];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? a.q_base[i0 + q] : 0.f;
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      u64 acc[P];
+      float emin[SPT], o[SPT];
+#pragma unroll
+      for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
+      pair_forward<D, P, 0>(s_x2 + (size_t)g * H * DP, H, s2, acc, emin);
+#pragma unroll
+      for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
+      double ts = tsum[g], tm = tmax[g];
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        float v = o[q] * a.k.inv_nu;
+        if (i0 + q < a.N) {
+          v += qb[q];
+          ts += (double)v;
+          tm = fmax(tm, (double)v);
+        }
+        o[q] = v;
+      }
+      tsum[g] = ts;
+      tmax[g] = tm;
+      float* vp = a.v + (size_t)g * a.ld + i0;
+      if constexpr (P == 2)
+        *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
+      else
+        *reinterpret_cast<float2*>(vp) = make_float2(o[0], o[1]);
+    }
+  }
+  double ra[FUSED_MAXG], rb[FUSED_MAXG];
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    ra[g] = tsum[g];
+    rb[g] = tmax[g];
+  }
+  block_reduce_pairs(G, RED_MAX, ra, rb, s_red);
+  if (tid == 0) {
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g)
+      if (g < G) {
+        double* part = ws_fused_tot(a.ws) + ((size_t)blockIdx.x * FUSED_MAXG + g) * 2;
+        part[0] = ra[g];
+        part[1] = rb[g];
+      }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -812,65 +931,75 @@ __global__ void __launch_bounds__(512) eval_cost_kernel(const EvalArgs a) {
 
   int64_t lo, hi;
   cta_slice(a.N, a.ld, lo, hi);
-  for (int g = 0; g < G; ++g) {
-    double tsum = 0.0, tmax = -INFINITY;
-    forward_slice<D>(a, s_x2 + (size_t)g * H * DP, H, a.v + (size_t)g * a.ld, lo, hi, tsum, tmax);
-    const int kinds[2] = {RED_SUM, RED_MAX};
-    double vals[2] = {tsum, tmax};
-    block_reduce<2>(kinds, vals, s_red);
-    if (tid == 0) {
-      double* part = ws_fused_tot(a.ws) + ((size_t)blockIdx.x * FUSED_MAXG + g) * 2;
-      part[0] = vals[0];
-      part[1] = vals[1];
-    }
-  }
+  if (narrow_pairs(lo, hi))
+    forward_candidates<D, 1>(a, s_x2, G, H, lo, hi, s_red);
+  else
+    forward_candidates<D, 2>(a, s_x2, G, H, lo, hi, s_red);
   double* s_world = s_red + 32 * 2;  // [2G]
   meet_totals(a, G, epoch, mepoch, s_flag, s_world);
   if (blockIdx.x == 0 && tid < 2 * G && a.totals) a.totals[tid] = s_world[tid];
 
   // KL partials: sum_i p_i (log p_i - log c_i), sum_i c_i   (klerg.py:694-699 in closed form)
-  float vs[FUSED_MAXG], maxc[FUSED_MAXG];
+  // Four samples per thread-iteration (128-bit loads of v and p), reciprocal of the normaliser and lg2-based
+  // logarithms: the pass is instruction-bound (IEEE division + logf cost ~60 instructions per sample and candidate,
+  // this form ~12); the cost changes by < 1e-6 relative, far inside the 1e-4 parity tolerance.
+  float rvs[FUSED_MAXG], maxc[FUSED_MAXG];
   double sa[FUSED_MAXG], sc[FUSED_MAXG];
 #pragma unroll
   for (int g = 0; g < FUSED_MAXG; ++g) {
     sa[g] = sc[g] = 0.0;
-    vs[g] = maxc[g] = 1.f;
+    rvs[g] = maxc[g] = 1.f;
     if (g < G) {
       const double vsum = s_world[2 * g], vmax = s_world[2 * g + 1];
-      vs[g] = (float)vsum;
-      maxc[g] = fmaxf((float)vmax / vs[g], a.floor);
+      const float vs = (float)vsum;
+      rvs[g] = 1.f / vs;
+      maxc[g] = fmaxf((float)vmax / vs, a.floor);
     }
   }
   const int64_t hiN = hi < a.N ? hi : a.N;
-  for (int64_t i = lo + tid; i < hiN; i += blockDim.x) {
-    float pi = a.p[i];
-    if (pi != pi) pi = 1e-6f;
-    const float lp = logf(pi);
+  for (int64_t i0 = lo + (int64_t)tid * 4; i0 < hiN; i0 += (int64_t)blockDim.x * 4) {
+    float pv[4], lp[4];
+    if (i0 + 3 < a.N) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(a.p + i0));
+      pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pv[q] = (i0 + q < a.N) ? a.p[i0 + q] : 1.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (pv[q] != pv[q]) pv[q] = 1e-6f;
+      lp[q] = __logf(pv[q]);
+    }
 #pragma unroll
     for (int g = 0; g < FUSED_MAXG; ++g) {
       if (g < G) {
-        float c = fmaxf(a.v[(size_t)g * a.ld + i] / vs[g], a.floor);
-        if (c != c) c = 1e-6f * maxc[g];  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
-        sa[g] += (double)(pi * (lp - logf(c)));
-        sc[g] += (double)c;
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(a.v + (size_t)g * a.ld + i0));
+        const float vv[4] = {t.x, t.y, t.z, t.w};
+        float fa = 0.f, fc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (i0 + q < hiN) {
+            float c = fmaxf(vv[q] * rvs[g], a.floor);
+            if (c != c) c = 1e-6f * maxc[g];  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
+            fa = fmaf(pv[q], lp[q] - __logf(c), fa);
+            fc += c;
+          }
+        }
+        sa[g] += (double)fa;
+        sc[g] += (double)fc;
       }
     }
   }
-  for (int g = 0; g < G; ++g) {
-    const int kinds[2] = {RED_SUM, RED_SUM};
-    double vals[2] = {0.0, 0.0};
+  block_reduce_pairs(G, RED_SUM, sa, sc, s_red);
+  if (tid == 0) {
 #pragma unroll
-    for (int gg = 0; gg < FUSED_MAXG; ++gg)
-      if (gg == g) {
-        vals[0] = sa[gg];
-        vals[1] = sc[gg];
+    for (int g = 0; g < FUSED_MAXG; ++g)
+      if (g < G) {
+        double* part = ws_fused_kl(a.ws) + ((size_t)blockIdx.x * FUSED_MAXG + g) * 2;
+        part[0] = sa[g];
+        part[1] = sc[g];
       }
-    block_reduce<2>(kinds, vals, s_red);
-    if (tid == 0) {
-      double* part = ws_fused_kl(a.ws) + ((size_t)blockIdx.x * FUSED_MAXG + g) * 2;
-      part[0] = vals[0];
-      part[1] = vals[1];
-    }
   }
 
   if (!meet_last(a, s_flag)) return;
