@@ -63,10 +63,24 @@ def build(force=False, verbose=False):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DKLERG_STAMPS"] if os.environ.get("KLERG_STAMPS") else []  # phase stamps in the fused evals
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", INCLUDE, "-o", LIB_PATH] + srcs
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + ["-I", INCLUDE]
+    objdir = os.path.join(PKG_ROOT, "build")
+    os.makedirs(objdir, exist_ok=True)
+    # one nvcc per translation unit, in parallel (the fused evals are the long pole), then one link
+    procs = []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc] + flags + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((obj, cmd, subprocess.Popen(cmd)))
+    for obj, cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [o for o, _, _ in procs]
     if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+        print(" ".join(link))
+    subprocess.run(link, check=True)
     return LIB_PATH
 
 
