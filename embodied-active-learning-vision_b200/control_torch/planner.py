@@ -64,6 +64,12 @@ class PlannerContext:
             self.buf = engine.EvalBuffers(self.H, self.dyn.S, self.dyn.A, ld, samples_dev.device)
 
     def set_target(self, p, p_stats):
+        """p [n_local] (or already padded to the sample stride ld), p_stats [1] = global sum of p."""
+        ld = self.packed.shape[1]
+        if p.numel() < ld:  # the fused evals copy whole tile rows with TMA: rows are padded to the sample stride
+            pad = torch.zeros(ld, dtype=torch.float32, device=p.device)
+            pad[: p.numel()] = p
+            p = pad
         self.p, self.p_stats = p, p_stats
 
     def set_history(self, hist_dev):

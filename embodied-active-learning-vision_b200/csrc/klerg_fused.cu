@@ -105,6 +105,36 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
 }
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// one contiguous run of `bytes` (multiple of 16, both sides 16-byte aligned) global -> shared
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -542,7 +572,7 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.tile = o;  o = align16(o + tile);
   p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
   p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
-  p.misc = o;  o = align16(o + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16);
+  p.misc = o;  o = align16(o + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 32);
   p.total = o;
   return p;
 }
@@ -578,6 +608,12 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   KLERG_STAMP(0);
   // ---- phase 0: rollout (every CTA) ---------------------------------------------------------------
   float* s_x0 = (float*)(smem + sp.misc) + 4;  // [S] (+ [9] R0)
+  unsigned long long* s_bar = (unsigned long long*)(smem + ((sp.misc + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 7) & ~(size_t)7));  // [2]
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
   if (tid < S) s_x0[tid] = a.x0[tid];
   if (a.R0 && tid >= 32 && tid < 41) s_x0[KLERG_MAX_S + tid - 32] = a.R0[tid - 32];
@@ -620,6 +656,18 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     }
   }
   KLERG_STAMP(2);
+  // The first sample tile of the gradient pass (samples, this CTA's own v, p) does not depend on the grid-wide
+  // totals: its TMA copies are issued now and land while the CTAs meet.
+  fence_proxy_async();  // v was written with ordinary stores and is read back by TMA
+  __syncthreads();
+  if (tid == 0 && hi > lo) {
+    const unsigned bytes = 4u * (unsigned)min((int64_t)a.ts, hi - lo);
+    mbar_expect_tx(&s_bar[0], (D + 2) * bytes);
+#pragma unroll
+    for (int d = 0; d < D; ++d) tma_bulk_g2s(s_tile + (size_t)d * TS_ROW, a.packed + (int64_t)d * a.ld + lo, bytes, &s_bar[0]);
+    tma_bulk_g2s(s_tile + (size_t)D * TS_ROW, a.v + lo, bytes, &s_bar[0]);
+    tma_bulk_g2s(s_tile + (size_t)(D + 1) * TS_ROW, a.p + lo, bytes, &s_bar[0]);
+  }
   double* s_world = s_red + 32 * 2;  // [2]
   meet_totals(a, 1, epoch, mepoch, s_flag, s_world);
   KLERG_STAMP(3);
@@ -642,6 +690,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
   const int nblk = gridDim.x;
   const int gstride = (nblk + 31) & ~31;  // partial layout [e][gstride]: the final reduce reads rows coalesced
   const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
+  int tile_seq = 0;  // tiles streamed so far in this launch (same in every thread)
   for (int kt = 0; kt < a.K; ++kt) {  // belief targets: the forward pass above is shared, p_k differs
   const float* p_k = a.p + (int64_t)kt * a.p_stride;
   double kl_a = 0.0, kl_c = 0.0;
@@ -669,41 +718,37 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
     // Sample tiles stream global -> shared with cp.async, one tile ahead of the pair math:
     // rows s_0..s_{D-1} (scaled samples), q_base + q_iter (turned into the importance ratio in place), p.
     const int nt = (int)((hi - lo + ts - 1) / ts);
-    // Thread t owns 4-sample chunks t, t + blockDim, ... of a tile: it copies all rows of its chunks and, once its
-    // own copies have landed, turns v into the importance ratio for them - one CTA barrier per tile.
+    // One thread issues the D+2 row copies of a tile as TMA bulk copies (contiguous runs, no descriptors) that
+    // complete on the tile buffer's mbarrier; everybody else keeps computing.  Tile g of this launch uses buffer
+    // g & 1 and the (g >> 1)-th phase of its barrier.
     auto issue_tile = [&](int k) {
-      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * TS_ROW;
-      const int64_t base = lo + (int64_t)k * ts;
-      const int cnt = (int)min((int64_t)ts, hi - base);  // multiple of 4
-      const int nch = cnt >> 2;
-      for (int c = tid; c < nch; c += blockDim.x) {
-        const int q4 = c << 2;
-        const int64_t i = base + q4;
+      if (tid == 0) {
+        const int gidx = tile_seq + k;
+        float* buf = s_tile + (size_t)(gidx & 1) * (D + 2) * TS_ROW;
+        const int64_t base = lo + (int64_t)k * ts;
+        const unsigned bytes = 4u * (unsigned)min((int64_t)ts, hi - base);  // multiple of 16
+        fence_proxy_async();  // the buffer was last written with ordinary stores (importance ratio, padding)
+        mbar_expect_tx(&s_bar[gidx & 1], (D + 2) * bytes);
 #pragma unroll
-        for (int d = 0; d < D; ++d) cp_async16(buf + (size_t)d * TS_ROW + q4, a.packed + (int64_t)d * a.ld + i);
-        cp_async16(buf + (size_t)D * TS_ROW + q4, a.v + i);
-        float* prow = buf + (size_t)(D + 1) * TS_ROW + q4;
-        if (i + 3 < a.N) {
-          cp_async16(prow, p_k + i);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (i + q < a.N) cp_async4(prow + q, p_k + i + q);
-            else prow[q] = 0.f;
-          }
-        }
+        for (int d = 0; d < D; ++d)
+          tma_bulk_g2s(buf + (size_t)d * TS_ROW, a.packed + (int64_t)d * a.ld + base, bytes, &s_bar[gidx & 1]);
+        tma_bulk_g2s(buf + (size_t)D * TS_ROW, a.v + base, bytes, &s_bar[gidx & 1]);
+        tma_bulk_g2s(buf + (size_t)(D + 1) * TS_ROW, p_k + base, bytes, &s_bar[gidx & 1]);
       }
-      cp_async_commit();
     };
-    issue_tile(0);
+    if (nt > 0 && tile_seq > 0) issue_tile(0);  // the very first tile of the launch was issued before the meeting point
     for (int k = 0; k < nt; ++k) {
-      float* buf = s_tile + (size_t)(k & 1) * (D + 2) * TS_ROW;
+      const int gidx = tile_seq + k;
+      float* buf = s_tile + (size_t)(gidx & 1) * (D + 2) * TS_ROW;
       const int64_t base = lo + (int64_t)k * ts;
       const int cnt = (int)min((int64_t)ts, hi - base);
       const int cnt64 = (cnt + 63) & ~63;
       float* wrow = buf + (size_t)D * TS_ROW;
       const float* prow = buf + (size_t)(D + 1) * TS_ROW;
-      cp_async_wait_all();  // this thread's chunks of tile k
+      {
+        unsigned* ctrl = ws_fused_ctrl(a.ws);
+        KLERG_SPIN_UNTIL(mbar_try_wait(&s_bar[gidx & 1], (unsigned)(gidx >> 1) & 1u), ctrl)
+      }
       for (int c = tid; c < (cnt64 >> 2); c += blockDim.x) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -738,6 +783,7 @@ __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const EvalArgs a) {
         }
       }
     }
+    tile_seq += nt;
     __syncthreads();
     // lanes -> warp sums -> CTA partial for this round's states
 #pragma unroll

@@ -246,7 +246,8 @@ size_t klerg_fused_fault_offset(void);
  * -> dgdx[H][S], du[H][A], djdlam[H], u_star = clamp(u + alpha du)[H][A].
  * Also: traj[H+1][S] (may be NULL), totals[2] = {sum, max} of q_base + q_iter,
  * kl_out[2] = {sum_i p_i (log p_i - log c_i), sum_i c_i}, cost[1] = KL of that
- * footprint + barrier sum (each may be NULL).  v_scratch: ld floats (receives
+ * footprint + barrier sum (each may be NULL).  p must hold ld floats (entries >= N are ignored; whole tile
+ * rows are copied with TMA) and be 16-byte aligned.  v_scratch: ld floats (receives
  * q_base + q_iter of this rank's samples).  Rinv_diag / ctrl_lo / ctrl_hi are
  * HOST arrays of A floats.  Replaces klerg_rollout + klerg_footprint +
  * klerg_kl_gradient_fused + klerg_adjoint with a single launch. */

@@ -246,7 +246,7 @@ def test_robot_sequences_vs_golden(ct, golden_dir, name):
         hist = r.memory_buffer.device_buffer[r.last_hist_idx.cuda()].cpu().numpy() if len(r.last_hist_idx) else None
         if np.allclose(r.u.numpy(), gold[pre + "u_after"], rtol=1e-3, atol=1e-4):
             matched += 1
-            rel_close(r.ctx.p, gold[pre + "p"], what=f"{pre}p")
+            rel_close(r.ctx.p[: r.ctx.n], gold[pre + "p"], what=f"{pre}p")
             rel_close(r.ctx.q_base[: r.ctx.n], gold[pre + "q_base"], what=f"{pre}q_base")
             rel_close(st, gold[pre + "ret_state"], rtol=1e-3, atol_frac=1e-4)
             rel_close(ctrl, gold[pre + "ret_ctrl"], rtol=1e-3, atol_frac=1e-4)
