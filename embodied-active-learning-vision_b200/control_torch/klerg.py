@@ -34,6 +34,7 @@ from .dynamics import DoubleIntegratorEnv, DoubleIntegratorRollEnv, DoubleIntegr
 from .klerg_utils import Lambda
 from .memory_buffer import MemoryBuffer_torch
 from .planner import PlannerContext
+from .target_decoder import DeviceTarget, is_decoder_model
 
 base_path = os.path.dirname(os.path.abspath(__file__))
 
@@ -338,15 +339,28 @@ class Robot(object):
         Returns (values for this rank's slice, pre_renorm).  ``pdf_torch`` is point-wise (vae.py:244-275), so a
         sharded controller evaluates it on its own slice only - reusing the samples already on the device when
         the target lives there; ``init_uniform_grid`` normalises over the whole batch and is evaluated in full."""
-        tdev = torch.device(self.target_dist.device)
         if uniform:
+            tdev = torch.device(self.target_dist.device)
             full = self.target_dist.init_uniform_grid(samples_host.clone().to(tdev)).squeeze()
             return self._shard(full), True
         if self.use_prior:
             raise NotImplementedError("use_prior is not ported")
+        target = self._device_target()
+        tdev = torch.device(target.device)
         if samples_dev is not None and tdev == samples_dev.device:
-            return self.target_dist.pdf_torch(samples_dev.clone()).squeeze(), False
-        return self.target_dist.pdf_torch(self._shard(samples_host).clone().to(tdev)).squeeze(), False
+            return target.pdf_torch(samples_dev.clone()).squeeze(), False
+        return target.pdf_torch(self._shard(samples_host).clone().to(tdev)).squeeze(), False
+
+    def _device_target(self):
+        """The reference's VAE (vae/vae.py) handed in as ``target_dist`` is evaluated on the device
+        (target_decoder.DeviceTarget); any other ``pdf_torch`` provider is called where it lives."""
+        td = self.target_dist
+        if isinstance(td, DeviceTarget) or not is_decoder_model(td):
+            return td
+        cached = getattr(self, "_wrapped_target", None)
+        if cached is None or cached.model is not td:
+            cached = self._wrapped_target = DeviceTarget(td, self.cuda)
+        return cached
 
     def _shard(self, t):
         lo, hi = self.group.shard_bounds(t.shape[0])

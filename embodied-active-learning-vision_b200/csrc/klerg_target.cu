@@ -1,0 +1,514 @@
+// Target density p(s) of the VAE sensor model, evaluated on the device.
+//
+// Replaces VAE.pdf_torch (franka_test/scripts/vae/vae.py:244-275):
+//   latent = [z || s - shift]  ->  decode = Linear(zd+sd,H1) ReLU Linear(H1,H2) ReLU Linear(H2,out)
+//   p(s)   = amax_l exp( mean_z clamp(decode(latent)[:, l], lo, hi) ),  l < ylogvar_dim
+//
+// The first layer folds the (sample-independent) z part into a bias: h1_k = relu(c_zk + sum_d W1x[k][d] x_d);
+// it is produced by CUDA cores straight into shared memory as the A operand.  The second layer - the only dense
+// contraction of the whole KL-ergodic path, [N,H1] x [H1,H2] - runs on the tensor cores: tcgen05.mma kind::tf32,
+// M = 128 samples per tile, accumulators in TMEM (H2 <= 512 columns = the whole TMEM of an SM).  fp32 parity with
+// the reference (1e-4 relative is the bar, ~1e-6 achieved) comes from the 3xTF32 split: every operand is
+// hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), and D += A_lo B_hi + A_hi B_lo + A_hi B_hi.
+// The third layer only needs its first ylogvar_dim rows: a dot product in the TMEM -> register epilogue, fused
+// with bias + ReLU of layer 2, the clamp, the mean over z, exp and amax.
+//
+// Roles inside a CTA (192 threads, one CTA per SM, persistent over sample tiles):
+//   warps 0-3  thread = sample row: produce the A stages (hi/lo), later drain TMEM lane = row (epilogue)
+//   warp 4     one lane streams the pre-split W2 stages global -> shared with TMA bulk copies (cp.async.bulk)
+//   warp 5     one lane issues the tcgen05.mma's and commits stage / accumulator barriers
+// Shared-memory operands use the canonical no-swizzle K-major layout (8 rows x 16 B core matrices):
+//   stage = one MMA K-step (8 tf32 = two 16-byte K chunks): [part hi|lo][chunk 0|1][row][16 B]
+//   so a warp of producer rows writes 512 contiguous bytes per store instruction (conflict-free), and
+//   SBO (8-row group stride) = 128 B, LBO (K chunk stride) = rows * 16 B.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "klerg_b200.h"
+#include "klerg_common.cuh"
+
+namespace klerg {
+namespace {
+
+constexpr int TM = 128;            // samples per tile = UMMA M = TMEM lanes
+constexpr int THREADS = 192;       // 4 producer/epilogue warps + loader warp + MMA warp
+constexpr int A_STAGE = 2 * 2 * TM * 16;  // bytes: [part][chunk][row][16 B]
+constexpr long long SPIN_LIMIT_T = 1ll << 24;
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+struct Dims {
+  int sd, zd, nz, h1, h2, nl, lp1, lp;
+};
+
+__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
+// packed decoder (device): [t1: nz*h1*lp1 f32][e: h2*lp f32][b3: 16 f32][w2s: (h1/8) stages x 64*h2 bytes]
+__host__ __device__ inline size_t off_t1(const Dims&) { return 0; }
+__host__ __device__ inline size_t off_e(const Dims& d) { return align128(sizeof(float) * (size_t)d.nz * d.h1 * d.lp1); }
+__host__ __device__ inline size_t off_b3(const Dims& d) { return off_e(d) + align128(sizeof(float) * (size_t)d.h2 * d.lp); }
+__host__ __device__ inline size_t off_w2(const Dims& d) { return off_b3(d) + 128; }
+__host__ __device__ inline size_t b_stage_bytes(const Dims& d) { return (size_t)64 * d.h2; }
+__host__ __device__ inline size_t packed_bytes(const Dims& d) { return off_w2(d) + (size_t)(d.h1 / 8) * b_stage_bytes(d); }
+
+bool make_dims(int sd, int zd, int nz, int h1, int h2, int nl, Dims& d) {
+  if (sd < 1 || sd > 7) { set_error("target decoder: s_dim=%d outside 1..7", sd); return false; }
+  if (zd < 0 || nz < 1 || nz > 64) { set_error("target decoder: z_dim=%d / z vectors=%d out of range", zd, nz); return false; }
+  if (h1 < 8 || (h1 % 8) || h1 > 1024) { set_error("target decoder: first hidden width %d must be a multiple of 8 in 8..1024", h1); return false; }
+  if (h2 < 32 || (h2 % 32) || h2 > 512) { set_error("target decoder: second hidden width %d must be a multiple of 32 in 32..512 (TMEM columns)", h2); return false; }
+  if (nl < 1 || nl > 15) { set_error("target decoder: ylogvar_dim=%d outside 1..15", nl); return false; }
+  d.sd = sd; d.zd = zd; d.nz = nz; d.h1 = h1; d.h2 = h2; d.nl = nl;
+  d.lp1 = sd <= 3 ? 4 : 8;
+  d.lp = nl <= 3 ? 4 : 16;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// ---- pack: fold z into the first-layer bias, interleave the epilogue table, split W2 into tf32 hi/lo stages ----
+__global__ void pack_decoder_kernel(const Dims d, const float* __restrict__ w1, const float* __restrict__ b1,
+                                    const float* __restrict__ z, const float* __restrict__ w2,
+                                    const float* __restrict__ b2, const float* __restrict__ w3,
+                                    const float* __restrict__ b3, unsigned char* __restrict__ packed) {
+  float* t1 = (float*)(packed + off_t1(d));
+  float* e = (float*)(packed + off_e(d));
+  float* pb3 = (float*)(packed + off_b3(d));
+  uint32_t* w2s = (uint32_t*)(packed + off_w2(d));
+  const long long n_t1 = (long long)d.nz * d.h1 * d.lp1, n_e = (long long)d.h2 * d.lp, n_w = (long long)d.h1 * d.h2;
+  const long long total = n_t1 + n_e + 16 + n_w;
+  const int ld1 = d.zd + d.sd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_t1) {
+      const int slot = (int)(i % d.lp1), k = (int)((i / d.lp1) % d.h1), zi = (int)(i / ((long long)d.lp1 * d.h1));
+      float v = 0.f;
+      if (slot == 0) {
+        v = b1[k];
+        for (int j = 0; j < d.zd; ++j) v = fmaf(w1[(size_t)k * ld1 + j], z[(size_t)zi * d.zd + j], v);
+      } else if (slot <= d.sd) {
+        v = w1[(size_t)k * ld1 + d.zd + slot - 1];
+      }
+      t1[i] = v;
+    } else if (i < n_t1 + n_e) {
+      const long long r = i - n_t1;
+      const int slot = (int)(r % d.lp), j = (int)(r / d.lp);
+      float v = 0.f;
+      if (slot == 0) v = b2[j];
+      else if (slot <= d.nl) v = w3[(size_t)(slot - 1) * d.h2 + j];
+      e[r] = v;
+    } else if (i < n_t1 + n_e + 16) {
+      const int l = (int)(i - n_t1 - n_e);
+      pb3[l] = l < d.nl ? b3[l] : 0.f;
+    } else {
+      // W2[n][k] -> stage ks = k/8: [part][chunk c = (k%8)/4][n][k%4]
+      const long long r = i - n_t1 - n_e - 16;
+      const int k = (int)(r % d.h1), n = (int)(r / d.h1);
+      const float w = w2[r];
+      const uint32_t hi = rna_tf32(w);
+      const uint32_t lo = rna_tf32(w - __uint_as_float(hi));
+      const int ks = k >> 3, c = (k >> 2) & 1, q = k & 3;
+      const size_t stage_words = (size_t)16 * d.h2;  // 64*h2 bytes
+      const size_t base = (size_t)ks * stage_words + ((size_t)c * d.h2 + n) * 4 + q;
+      w2s[base] = hi;
+      w2s[base + (size_t)8 * d.h2] = lo;  // part 1 starts after 2 chunks x h2 rows x 4 words
+    }
+  }
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------------------
+struct DecodeArgs {
+  const unsigned char* packed;
+  const float* samples;
+  const float* shift;
+  float* out;
+  unsigned* fault;
+  long long n;
+  Dims d;
+  float clamp_lo, clamp_hi;
+  int stages, tmem_cols;
+};
+
+struct SmemLayout {
+  size_t a, b, t1, e, bars, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(const Dims& d, int stages) {
+  SmemLayout s;
+  size_t o = 0;
+  s.a = o;  o += (size_t)stages * A_STAGE;
+  s.b = o;  o += (size_t)stages * b_stage_bytes(d);
+  s.t1 = o; o = align128(o + sizeof(float) * (size_t)d.nz * d.h1 * d.lp1);
+  s.e = o;  o = align128(o + sizeof(float) * (size_t)d.h2 * d.lp);
+  s.bars = o; o += 8 * (3 * 8 + 2) + 16;  // full_a[8] full_b[8] empty[8] tmem_full tmem_empty | tmem addr, abort
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool bar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a lost arrival sets the CTA's abort word (reported through *fault) instead of hanging the GPU.
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity, volatile unsigned* abort_word) {
+  for (long long spin = 0; !bar_try_wait(bar, parity); ++spin) {
+    if (spin > SPIN_LIMIT_T || ((spin & 1023) == 1023 && *abort_word)) {
+      *abort_word = 1u;
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 operands, fp32 accumulate
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version 1 [46,48))
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format TF32 (2) [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ inline uint32_t instr_desc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int LP1>
+__device__ __forceinline__ float first_layer(const float* __restrict__ row, const float (&x)[LP1 - 1]) {
+  // row = {c_zk, W1x[k][0..sd-1], 0...}; zero weights make the unused lanes vanish
+  const float4 t = *reinterpret_cast<const float4*>(row);
+  float v = fmaf(t.y, x[0], t.x);
+  v = fmaf(t.z, x[1], v);
+  v = fmaf(t.w, x[2], v);
+  if constexpr (LP1 == 8) {
+    const float4 s = *reinterpret_cast<const float4*>(row + 4);
+    v = fmaf(s.x, x[3], v);
+    v = fmaf(s.y, x[4], v);
+    v = fmaf(s.z, x[5], v);
+    v = fmaf(s.w, x[6], v);
+  }
+  return fmaxf(v, 0.f);
+}
+
+template <int LP1, int LP>
+__global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const DecodeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Dims d = a.d;
+  const SmemLayout sl = smem_layout(d, a.stages);
+  unsigned char* sA = smem + sl.a;
+  unsigned char* sB = smem + sl.b;
+  float* s_t1 = (float*)(smem + sl.t1);
+  float* s_e = (float*)(smem + sl.e);
+  unsigned long long* full_a = (unsigned long long*)(smem + sl.bars);
+  unsigned long long* full_b = full_a + 8;
+  unsigned long long* empty = full_a + 16;
+  unsigned long long* tmem_full = full_a + 24;
+  unsigned long long* tmem_empty = full_a + 25;
+  uint32_t* s_tmem = (uint32_t*)(full_a + 26);
+  volatile unsigned* s_abort = (volatile unsigned*)(s_tmem + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ksteps = d.h1 >> 3;
+  const int stages = a.stages;
+  const long long tiles = (a.n + TM - 1) / TM;
+  const unsigned bstage = (unsigned)b_stage_bytes(d);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      bar_init(&full_a[s], TM);
+      bar_init(&full_b[s], 1);
+      bar_init(&empty[s], 1);
+    }
+    bar_init(tmem_full, 1);
+    bar_init(tmem_empty, TM);
+    *s_abort = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const float4* g1 = (const float4*)(a.packed + off_t1(d));
+    const int n1 = d.nz * d.h1 * d.lp1 / 4;
+    for (int i = threadIdx.x; i < n1; i += THREADS) ((float4*)s_t1)[i] = __ldg(g1 + i);
+    const float4* g2 = (const float4*)(a.packed + off_e(d));
+    const int n2 = d.h2 * d.lp / 4;
+    for (int i = threadIdx.x; i < n2; i += THREADS) ((float4*)s_e)[i] = __ldg(g2 + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp < 4) {
+    // ================= producers of A, then epilogue of the same rows =================
+    const int row = threadIdx.x;
+    const float* b3 = (const float*)(a.packed + off_b3(d));
+    const float inv_nz = 1.0f / (float)d.nz;
+    uint32_t it = 0, acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long rg = tile * TM + row;
+      const bool valid = rg < a.n;
+      float x[LP1 - 1];
+#pragma unroll
+      for (int j = 0; j < LP1 - 1; ++j) {
+        x[j] = 0.f;
+        if (valid && j < d.sd) x[j] = a.samples[rg * d.sd + j] - (a.shift ? a.shift[j] : 0.f);
+      }
+      float ysum[LP - 1];
+#pragma unroll
+      for (int l = 0; l < LP - 1; ++l) ysum[l] = 0.f;
+
+      for (int z = 0; z < d.nz; ++z) {
+        const float* t1z = s_t1 + (size_t)z * d.h1 * LP1;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int s = it % stages;
+          const unsigned ph = (it / stages) & 1u;
+          bar_wait(&empty[s], ph ^ 1u, s_abort);
+          float h[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) h[q] = first_layer<LP1>(t1z + (size_t)(ks * 8 + q) * LP1, x);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            hi[q] = rna_tf32(h[q]);
+            lo[q] = rna_tf32(h[q] - __uint_as_float(hi[q]));
+          }
+          unsigned char* base = sA + (size_t)s * A_STAGE + (size_t)row * 16;
+          *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(base + TM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          *reinterpret_cast<uint4*>(base + 2 * TM * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(base + 3 * TM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+          bar_arrive(&full_a[s]);
+        }
+        // ---- epilogue of (tile, z): bias + ReLU of layer 2, dot with the logvar rows of layer 3 ----
+        bar_wait(tmem_full, acc_phase, s_abort);
+        acc_phase ^= 1u;
+        tc_fence_after();
+        float y[LP - 1];
+#pragma unroll
+        for (int l = 0; l < LP - 1; ++l) y[l] = 0.f;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < d.h2; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const float* erow = s_e + (size_t)c0 * LP;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 ev = *reinterpret_cast<const float4*>(erow + j * LP);
+            const float hj = fmaxf(__uint_as_float(r[j]) + ev.x, 0.f);
+            y[0] = fmaf(ev.y, hj, y[0]);
+            if constexpr (LP == 4) {
+              y[1] = fmaf(ev.z, hj, y[1]);
+              y[2] = fmaf(ev.w, hj, y[2]);
+            } else {
+              y[1] = fmaf(ev.z, hj, y[1]);
+              y[2] = fmaf(ev.w, hj, y[2]);
+#pragma unroll
+              for (int g = 1; g < 4; ++g) {
+                const float4 ew = *reinterpret_cast<const float4*>(erow + j * LP + 4 * g);
+                y[4 * g - 1] = fmaf(ew.x, hj, y[4 * g - 1]);
+                y[4 * g + 0] = fmaf(ew.y, hj, y[4 * g + 0]);
+                y[4 * g + 1] = fmaf(ew.z, hj, y[4 * g + 1]);
+                y[4 * g + 2] = fmaf(ew.w, hj, y[4 * g + 2]);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        bar_arrive(tmem_empty);  // accumulator drained: the MMA warp may start the next (tile, z)
+#pragma unroll
+        for (int l = 0; l < LP - 1; ++l)
+          if (l < d.nl) ysum[l] += fminf(fmaxf(y[l] + b3[l], a.clamp_lo), a.clamp_hi);  // torch.clamp (vae.py:266)
+      }
+      float p = -INFINITY;
+#pragma unroll
+      for (int l = 0; l < LP - 1; ++l)
+        if (l < d.nl) p = fmaxf(p, expf(d.nz > 1 ? ysum[l] * inv_nz : ysum[l]));  // mean over z, exp, amax (vae.py:267-273)
+      if (valid) a.out[rg] = p;
+    }
+  } else if (warp == 4) {
+    // ================= W2 stages: TMA bulk copies, one per K-step =================
+    if (lane == 0) {
+      const unsigned char* w2s = a.packed + off_w2(d);
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+        for (int z = 0; z < d.nz; ++z)
+          for (int ks = 0; ks < ksteps; ++ks, ++it) {
+            const int s = it % stages;
+            const unsigned ph = (it / stages) & 1u;
+            bar_wait(&empty[s], ph ^ 1u, s_abort);
+            bar_expect_tx(&full_b[s], bstage);
+            bulk_g2s(sB + (size_t)s * bstage, w2s + (size_t)ks * bstage, bstage, &full_b[s]);
+          }
+    }
+  } else {
+    // ================= MMA issue =================
+    if (lane == 0) {
+      const int nsplit = d.h2 > 256 ? 2 : 1;
+      const int ncols = d.h2 / nsplit;
+      const uint32_t idesc = instr_desc_tf32(TM, ncols);
+      // LBO = stride between the two 16-byte K chunks of an MMA, SBO = stride between 8-row groups
+      const uint32_t a_lbo = TM * 16, a_sbo = 128, b_lbo = (uint32_t)d.h2 * 16, b_sbo = 128;
+      uint32_t it = 0, item = 0;
+      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+        for (int z = 0; z < d.nz; ++z, ++item) {
+          if (item > 0) bar_wait(tmem_empty, (item - 1) & 1u, s_abort);
+          tc_fence_after();
+          for (int ks = 0; ks < ksteps; ++ks, ++it) {
+            const int s = it % stages;
+            const unsigned ph = (it / stages) & 1u;
+            bar_wait(&full_a[s], ph, s_abort);
+            bar_wait(&full_b[s], ph, s_abort);
+            tc_fence_after();
+            const uint32_t a_hi = smem_addr(sA + (size_t)s * A_STAGE), a_lo = a_hi + 2 * TM * 16;
+            const uint32_t b_hi0 = smem_addr(sB + (size_t)s * bstage), b_lo0 = b_hi0 + 32u * (uint32_t)d.h2;
+            const uint64_t da_hi = smem_desc(a_hi, a_lbo, a_sbo), da_lo = smem_desc(a_lo, a_lbo, a_sbo);
+            for (int nh = 0; nh < nsplit; ++nh) {
+              const uint32_t boff = (uint32_t)(nh * ncols) * 16u;
+              const uint64_t db_hi = smem_desc(b_hi0 + boff, b_lbo, b_sbo), db_lo = smem_desc(b_lo0 + boff, b_lbo, b_sbo);
+              const uint32_t dcol = tmem + (uint32_t)(nh * ncols);
+              tc_mma_tf32(dcol, da_lo, db_hi, idesc, ks > 0 ? 1u : 0u);  // small terms first
+              tc_mma_tf32(dcol, da_hi, db_lo, idesc, 1u);
+              tc_mma_tf32(dcol, da_hi, db_hi, idesc, 1u);
+            }
+            tc_commit(&empty[s]);  // stage free once these MMAs have read it
+          }
+          tc_commit(tmem_full);  // accumulator complete -> epilogue
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && *s_abort && a.fault) atomicExch(a.fault, 1u);
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+template <int LP1, int LP>
+int launch_decoder(const DecodeArgs& a, int grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(target_decoder_kernel<LP1, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+    if (e != cudaSuccess) { set_error("target_decoder: smem opt-in failed: %s", cudaGetErrorString(e)); return -4; }
+    configured = true;
+  }
+  target_decoder_kernel<LP1, LP><<<grid, THREADS, smem, st>>>(a);
+  return check_launch("target_decoder_kernel");
+}
+
+}  // namespace
+}  // namespace klerg
+
+using namespace klerg;
+
+extern "C" size_t klerg_target_decoder_packed_bytes(int32_t s_dim, int32_t z_dim, int32_t n_z, int32_t h1, int32_t h2,
+                                                    int32_t n_logvar) {
+  Dims d;
+  if (!make_dims(s_dim, z_dim, n_z, h1, h2, n_logvar, d)) return 0;
+  return packed_bytes(d);
+}
+
+extern "C" int klerg_target_decoder_pack(const float* w1, const float* b1, const float* z, const float* w2,
+                                         const float* b2, const float* w3, const float* b3, int32_t s_dim,
+                                         int32_t z_dim, int32_t n_z, int32_t h1, int32_t h2, int32_t n_logvar,
+                                         void* packed, void* stream) {
+  Dims d;
+  if (!make_dims(s_dim, z_dim, n_z, h1, h2, n_logvar, d)) return -1;
+  if (!w1 || !b1 || (!z && z_dim > 0) || !w2 || !b2 || !w3 || !b3 || !packed) { set_error("target_decoder_pack: null pointer"); return -1; }
+  if ((uintptr_t)packed & 127) { set_error("target_decoder_pack: packed buffer must be 128-byte aligned"); return -1; }
+  pack_decoder_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(d, w1, b1, z, w2, b2, w3, b3, (unsigned char*)packed);
+  return check_launch("pack_decoder_kernel");
+}
+
+extern "C" int klerg_target_decoder_pdf(const void* packed, int32_t s_dim, int32_t z_dim, int32_t n_z, int32_t h1,
+                                        int32_t h2, int32_t n_logvar, const float* samples, int64_t N,
+                                        const float* shift, float clamp_lo, float clamp_hi, float* p_out,
+                                        uint32_t* fault, void* stream) {
+  Dims d;
+  if (!make_dims(s_dim, z_dim, n_z, h1, h2, n_logvar, d)) return -1;
+  if (N < 0) { set_error("target_decoder_pdf: N < 0"); return -1; }
+  if (N == 0) return 0;
+  if (!packed || !samples || !p_out) { set_error("target_decoder_pdf: null pointer"); return -1; }
+  if ((uintptr_t)packed & 127) { set_error("target_decoder_pdf: packed buffer must be 128-byte aligned"); return -1; }
+  int stages = 8;
+  while (stages >= 2 && smem_layout(d, stages).total > SMEM_MAX) --stages;
+  if (stages < 2) { set_error("target_decoder_pdf: decoder tables (%d z vectors x %d) do not fit in shared memory", n_z, h1); return -2; }
+  DecodeArgs a;
+  a.packed = (const unsigned char*)packed;
+  a.samples = samples;
+  a.shift = shift;
+  a.out = p_out;
+  a.fault = fault;
+  a.n = N;
+  a.d = d;
+  a.clamp_lo = clamp_lo;
+  a.clamp_hi = clamp_hi;
+  a.stages = stages;
+  int cols = 32;
+  while (cols < h2) cols <<= 1;
+  a.tmem_cols = cols;
+  const long long tiles = (N + TM - 1) / TM;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const size_t smem = smem_layout(d, stages).total;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d.lp1 == 4 && d.lp == 4) return launch_decoder<4, 4>(a, grid, smem, st);
+  if (d.lp1 == 8 && d.lp == 4) return launch_decoder<8, 4>(a, grid, smem, st);
+  if (d.lp1 == 4 && d.lp == 16) return launch_decoder<4, 16>(a, grid, smem, st);
+  return launch_decoder<8, 16>(a, grid, smem, st);
+}

@@ -289,6 +289,40 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
 int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t M, float* out,
                       void* stream);
 
+/* ---- target density of the VAE sensor model -------------- */
+
+/* VAE.pdf_torch (franka_test/scripts/vae/vae.py:244-275), the `target_dist`
+ * duck type Robot.get_target_dist calls (klerg.py:463):
+ *   latent = [z || s - shift];  y = decode(latent)[:, :n_logvar]
+ *   p(s) = amax_l exp( mean_z clamp(y_l, clamp_lo, clamp_hi) )
+ * for decode = Linear(z_dim+s_dim, h1) ReLU Linear(h1, h2) ReLU Linear(h2, out)
+ * (vae.py:77-84; hidden_dim [512,256] -> h1 = 256, h2 = 512).  n_z = 1 is the
+ * default `z_samples` row (vae.py:258-259); n_z > 1 the z buffer (vae.py:253-257,
+ * 268-270).  Limits: s_dim 1..7, h1 % 8 == 0 (<= 1024), h2 % 32 == 0 (<= 512),
+ * n_logvar 1..15.
+ *
+ * klerg_target_decoder_pack folds z into the first-layer bias and splits W2 into
+ * tf32 hi/lo operand stages; call it whenever the weights or z change (all
+ * pointers DEVICE, torch.nn.Linear layouts: w1[h1][z_dim+s_dim], w2[h2][h1],
+ * w3[>=n_logvar][h2], z[n_z][z_dim]).  `packed`: klerg_target_decoder_packed_bytes()
+ * bytes, 128-byte aligned.
+ *
+ * klerg_target_decoder_pdf evaluates p for samples[N][s_dim] (raw AoS samples,
+ * the argument of pdf_torch); `shift` = seed_x when the model was built with
+ * dx=True (vae.py:249-250), else NULL.  The second layer runs on the tensor
+ * cores (tcgen05.mma kind::tf32, 3xTF32 split, fp32 accumulate in TMEM).
+ * `fault` (may be NULL): set to 1 if an in-kernel wait timed out. */
+size_t klerg_target_decoder_packed_bytes(int32_t s_dim, int32_t z_dim, int32_t n_z, int32_t h1, int32_t h2,
+                                         int32_t n_logvar);
+int klerg_target_decoder_pack(const float* w1, const float* b1, const float* z, const float* w2,
+                              const float* b2, const float* w3, const float* b3, int32_t s_dim,
+                              int32_t z_dim, int32_t n_z, int32_t h1, int32_t h2, int32_t n_logvar,
+                              void* packed, void* stream);
+int klerg_target_decoder_pdf(const void* packed, int32_t s_dim, int32_t z_dim, int32_t n_z, int32_t h1,
+                             int32_t h2, int32_t n_logvar, const float* samples, int64_t N,
+                             const float* shift, float clamp_lo, float clamp_hi, float* p_out,
+                             uint32_t* fault, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,3 +65,83 @@ def seed_buffer_states(state0, case):
         s[:n] += 0.05 * torch.randn(n, generator=g)
         rows.append(s)
     return rows
+
+
+# ---- VAE target density (vae/vae.py:244-275) ---------------------------------------------------------------
+# name: s_dim, z_dim, hidden_dim (reference order: encoder side first, the decoder reverses it), logvar columns,
+#       z-buffer rows (0 = plain z_samples), dx model, #samples (ragged against the 128-row tiles), weight gain
+TARGET_CASES = {
+    "default": dict(sd=3, zd=16, hidden=[512, 256], nl=1, zbuf=0, dx=False, n=1000, gain=3.0),
+    "pose6_rgbvar": dict(sd=6, zd=8, hidden=[64, 32], nl=3, zbuf=0, dx=False, n=333, gain=4.0),
+    "zbuffer_dx": dict(sd=2, zd=6, hidden=[96, 40], nl=1, zbuf=3, dx=True, n=257, gain=6.5),
+    "wide_logvar": dict(sd=3, zd=4, hidden=[160, 24], nl=9, zbuf=2, dx=False, n=130, gain=1.2),
+}
+
+
+def decoder_weights(case, seed=11, out_extra=5):
+    """Seeded decoder weights [(W, b)] * 3 in torch.nn.Linear layout; `gain` spreads the log-variance over the
+    clamp range so that both clamp limits are exercised."""
+    g = torch.Generator().manual_seed(seed)
+    h2, h1 = case["hidden"]  # decoder = reversed(hidden_dim) (vae.py:79)
+    dims = [case["zd"] + case["sd"], h1, h2, case["nl"] + out_extra]
+    out = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        bound = 1.0 / (a ** 0.5)
+        w = (torch.rand(b, a, generator=g) * 2 - 1) * bound * case["gain"]
+        bias = (torch.rand(b, generator=g) * 2 - 1) * bound
+        out.append((w.contiguous(), bias.contiguous()))
+    return out
+
+
+def target_samples(case, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(case["n"], case["sd"], generator=g) * 2.3 - 1.15).to(torch.float32)
+
+
+class _ZRows:
+    def __init__(self, rows):
+        self.rows = rows
+
+    def get_samples(self):
+        return self.rows.detach().clone()
+
+
+class DecoderModel:
+    """Stand-in with the attributes of the reference's VAE that pdf_torch reads (vae/vae.py:11-110), evaluated
+    on the CPU by the oracle.  Used where the reference itself cannot travel (GPU box)."""
+
+    def __init__(self, case, z_rows, seed_x=None, seed=11, initialised=True, out_extra=5):
+        ws = decoder_weights(case, seed, out_extra)
+        layers = []
+        for i, (w, b) in enumerate(ws):
+            lin = torch.nn.Linear(w.shape[1], w.shape[0])
+            with torch.no_grad():
+                lin.weight.copy_(w)
+                lin.bias.copy_(b)
+            layers.append(lin)
+            if i + 1 < len(ws):
+                layers.append(torch.nn.ReLU())
+        self.decode = torch.nn.Sequential(*layers)
+        self.weights = ws
+        z_rows = torch.as_tensor(z_rows, dtype=torch.float32).reshape(-1, case["zd"])
+        self.use_buffer = case["zbuf"] > 0
+        self.z_buff = _ZRows(z_rows)
+        self.z_samples = z_rows[:1].clone()
+        self.ylogvar_dim = torch.tensor(case["nl"])
+        self.logvar_lims = (-10, 2)
+        self.init = torch.tensor([bool(initialised)])
+        self.dx = bool(case["dx"])
+        self.seed_x = torch.zeros(1, case["sd"]) if seed_x is None else torch.as_tensor(seed_x, dtype=torch.float32).reshape(1, -1)
+        self.device = "cpu"
+        self.dtype = torch.float32
+
+    def z_rows(self):
+        return self.z_buff.get_samples() if self.use_buffer else self.z_samples
+
+    def pdf_torch(self, samples):
+        from oracle import target_oracle
+        return target_oracle.vae_pdf(samples.to("cpu"), self.weights, self.z_rows(), int(self.ylogvar_dim),
+                                     self.logvar_lims, self.seed_x if self.dx else None, bool(self.init))
+
+    def init_uniform_grid(self, x):
+        return x.sum(1) ** 0

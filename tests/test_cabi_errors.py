@@ -78,3 +78,36 @@ def test_python_layer_raises_without_gpu_or_on_status():
         from control_torch import klerg_utils as ku
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ku.traj_footprint_vec(torch.zeros(3, 4), torch.zeros(5, 2), [0, 1], torch.tensor([0.1, 0.1]), 1.0)
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    """include/klerg_b200.h is the boundary: every function it declares is exported by the .so and has a ctypes
+    prototype in _cabi.SIGNATURES (and nothing is bound that the header does not declare)."""
+    import os
+    import re
+    header = open(os.path.join(cabi.INCLUDE, "klerg_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(klerg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) > 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in klerg_b200.h but not exported"
+    assert declared == set(cabi.SIGNATURES), declared ^ set(cabi.SIGNATURES)
+
+
+def test_target_decoder_validation(lib):
+    """VAE target decoder (vae/vae.py:244-275): shapes the tensor-core kernel is not built for are refused loudly."""
+    assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 512, 1) > 4 * 256 * 512 * 2
+    assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 100, 1) == 0  # second hidden width % 32
+    assert "multiple of 32" in err(lib)
+    assert lib.klerg_target_decoder_packed_bytes(9, 16, 1, 256, 512, 1) == 0
+    assert "s_dim" in err(lib)
+    assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 250, 512, 1) == 0
+    assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 512, 16) == 0
+    assert "ylogvar_dim" in err(lib)
+    assert lib.klerg_target_decoder_pdf(None, 3, 16, 1, 256, 512, 1, None, 5, None, -10.0, 2.0, None, None, None) == -1
+    assert "null" in err(lib)
+    assert lib.klerg_target_decoder_pdf(None, 3, 16, 1, 256, 512, 1, None, 0, None, -10.0, 2.0, None, None, None) == 0  # empty
+    assert lib.klerg_target_decoder_pdf(C.c_void_p(64), 3, 16, 1, 256, 512, 1, C.c_void_p(64), 5, None, -10.0, 2.0,
+                                        C.c_void_p(64), None, None) == -1
+    assert "aligned" in err(lib)
+    assert lib.klerg_target_decoder_pack(None, None, None, None, None, None, None, 3, 16, 1, 256, 512, 1, None, None) == -1

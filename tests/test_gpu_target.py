@@ -1,0 +1,132 @@
+"""GPU parity of the target-density decoder (klerg_target_decoder_pdf, tcgen05 3xTF32) against the vectors recorded
+from the reference's VAE.pdf_torch and against the CPU oracle.  Tolerance: 1e-4 relative (BASELINE.json north_star;
+the 3xTF32 split lands around 1e-6)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cases import TARGET_CASES, DecoderModel, MixtureTarget, ROBOT_CASES, robot_kwargs, seed_buffer_states, target_samples  # noqa: E402
+from oracle import klerg_oracle as ko  # noqa: E402
+
+RTOL = 1e-4
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def model_for(name, **kw):
+    case = TARGET_CASES[name]
+    g = np.load(os.path.join(GOLD, f"target_{name}.npz"))
+    return case, g, DecoderModel(case, g["z_rows"], g["seed_x"], out_extra=int(g["out_features"]) - case["nl"], **kw)
+
+
+@pytest.fixture(scope="module")
+def td():
+    import control_torch.target_decoder as m
+    return m
+
+
+@pytest.mark.parametrize("name", sorted(TARGET_CASES))
+def test_pdf_matches_reference_vectors(td, name):
+    case, g, model = model_for(name)
+    dev = td.DeviceTarget(model)
+    p = dev.pdf_torch(target_samples(case))
+    dev.check_fault()
+    assert p.is_cuda and p.shape == (case["n"],)
+    np.testing.assert_allclose(p.cpu().numpy(), g["p"], rtol=RTOL, atol=0)
+    # the numpy entry point (vae.py:238-242)
+    np.testing.assert_allclose(dev.pdf(target_samples(case).numpy()), g["p"], rtol=RTOL, atol=0)
+
+
+def test_uninitialised_model_is_uniform(td):
+    case, g, model = model_for("default", initialised=False)
+    p = td.DeviceTarget(model).pdf_torch(target_samples(case))
+    np.testing.assert_array_equal(p.cpu().numpy(), g["p_uninit"])
+
+
+@pytest.mark.parametrize("n", [0, 1, 127, 128, 129, 148 * 128 + 5, 40_000])
+def test_ragged_sizes_vs_oracle(td, n):
+    case = dict(TARGET_CASES["default"], n=n)
+    g = torch.Generator().manual_seed(n + 1)
+    model = DecoderModel(case, torch.randn(1, case["zd"], generator=g))
+    dev = td.DeviceTarget(model)
+    s = target_samples(case, seed=n)
+    p = dev.pdf_torch(s)
+    dev.check_fault()
+    ref = model.pdf_torch(s)
+    assert tuple(p.shape) == tuple(ref.shape)
+    np.testing.assert_allclose(p.cpu().numpy(), ref.numpy(), rtol=RTOL, atol=0)
+
+
+def test_weights_are_reread_every_call(td):
+    """The trainer keeps updating the model behind the controller (sensor_main_module.py:311-339)."""
+    case, g, model = model_for("pose6_rgbvar")
+    dev = td.DeviceTarget(model)
+    s = target_samples(case)
+    p0 = dev.pdf_torch(s).cpu()
+    with torch.no_grad():
+        model.decode[2].weight.mul_(0.5)
+        model.weights[1] = (model.decode[2].weight.detach().clone(), model.weights[1][1])
+        model.z_samples.add_(0.3)
+    p1 = dev.pdf_torch(s).cpu()
+    dev.check_fault()
+    assert not torch.allclose(p0, p1)
+    np.testing.assert_allclose(p1.numpy(), model.pdf_torch(s).numpy(), rtol=RTOL, atol=0)
+
+
+def test_unsupported_decoder_raises(td):
+    case, g, model = model_for("default")
+    model.decode = torch.nn.Sequential(torch.nn.Linear(19, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4))
+    with pytest.raises(NotImplementedError):
+        td.DeviceTarget(model).pdf_torch(target_samples(case))
+    case2 = dict(TARGET_CASES["default"], hidden=[100, 36])  # h2 = 100 is not a multiple of 32
+    m2 = DecoderModel(case2, torch.zeros(1, case2["zd"]))
+    with pytest.raises(RuntimeError):
+        td.DeviceTarget(m2).pdf_torch(target_samples(case2))
+
+
+def test_robot_step_with_model_target():
+    """Robot(target_dist=<VAE-like model>) evaluates p on the device and steps like the oracle controller that calls
+    the model's own pdf_torch on the CPU."""
+    from control_torch.klerg import Robot
+    rc = ROBOT_CASES["xyz_small"]
+    case = dict(TARGET_CASES["default"])
+    out = []
+    for cls in (ko.OracleRobot, Robot):
+        torch.manual_seed(7)
+        model = DecoderModel(case, torch.randn(1, case["zd"], generator=torch.Generator().manual_seed(2)))
+        r = cls(**robot_kwargs(rc, model))
+        r.test(rc["n"])
+        for s in seed_buffer_states(r.robot.state, rc):
+            r.memory_buffer.push(s)
+        res = [r.step(rc["n"], rc["m"], save_update=True) for _ in range(3)]
+        out.append((res, r.u.clone()))
+        if cls is Robot:
+            assert r._wrapped_target.stats["evals"] >= 3, "the device decoder was not used"
+            r._wrapped_target.check_fault()
+    (ra, ua), (rb, ub) = out
+    for (sa, va, ca), (sb, vb, cb) in zip(ra, rb):
+        np.testing.assert_allclose(sb, sa, rtol=1e-3, atol=1e-5)
+        np.testing.assert_allclose(cb, ca, rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(ub.numpy(), ua.numpy(), rtol=1e-3, atol=1e-5)
+
+
+def test_full_size_properties(td):
+    """BASELINE sizes (1e7 samples, default decoder): size-independent properties - every value inside the clamp
+    image, tile-permutation invariance (p is point-wise), and a strided subset equal to the oracle."""
+    case = dict(TARGET_CASES["default"], n=10_000_000)
+    model = DecoderModel(case, torch.randn(1, case["zd"], generator=torch.Generator().manual_seed(5)))
+    dev = td.DeviceTarget(model)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    s = torch.rand(case["n"], case["sd"], generator=g, device="cuda") * 2.3 - 1.15
+    p = dev.pdf_torch(s)
+    dev.check_fault()
+    assert float(p.min()) >= np.exp(-10.0) * (1 - 1e-6) and float(p.max()) <= np.exp(2.0) * (1 + 1e-6)
+    perm = torch.randperm(case["n"], device="cuda", generator=g)
+    p_perm = dev.pdf_torch(s[perm])
+    assert torch.equal(p_perm, p[perm]), "p must not depend on where a sample sits in a tile"
+    idx = torch.arange(0, case["n"], 9973, device="cuda")
+    ref = model.pdf_torch(s[idx].cpu())
+    np.testing.assert_allclose(p[idx].cpu().numpy(), ref.numpy(), rtol=RTOL, atol=0)
