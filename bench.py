@@ -259,6 +259,48 @@ def eval_roofline(D, H, n_local, peaks, hbm_gbs):
                 grad_bound="mufu" if pairs / mufu > pairs * (3 * D + 1) / fp32 else "fp32")
 
 
+def target_decoder_block(dev, timed):
+    """p(s) of the VAE sensor model (vae/vae.py:244-275) on the tensor cores: klerg_target_decoder_pdf at the c2
+    and c4 workspace sizes, against the tf32 peak (half the measured bf16 peak) and the torch-CPU arithmetic."""
+    from control_torch.target_decoder import DeviceTarget
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16, src = 2250.0, "nominal 2.25 PF bf16 (B200_PROFILING.md fallback)"
+    if os.path.exists(peaks_file):
+        bf16, src = json.load(open(peaks_file))["bf16_tflops"], "MEASURED_PEAKS.json bf16_tflops (burst)"
+    out = {}
+    for tag, n_t, sdim in (("c2", 100_000, 3), ("c4_size", 10_000_000, 6)):
+        model = wl.SyntheticVAETarget(sdim, seed=1)
+        devt = DeviceTarget(model, dev)
+        smp = (torch.rand(n_t, sdim, device=dev) * 2.3 - 1.15).contiguous()
+        devt.refresh()
+        t_kernel = timed(lambda: devt.evaluate_packed(smp), 5)
+        t_call = timed(lambda: devt.pdf_torch(smp), 5)
+        devt.check_fault()
+        zd, h1, h2 = 16, 256, 512
+        flop_alg = 2.0 * n_t * ((zd + sdim) * h1 + h1 * h2 + h2)
+        flop_issued = 3 * 2.0 * n_t * h1 * h2
+        out[tag] = {"samples": n_t, "s_dim": sdim, "ms_kernel": t_kernel * 1e3, "ms_pdf_torch_call": t_call * 1e3,
+                    "samples_per_s": n_t / t_kernel,
+                    "roofline": {"bound": "tensor", "achieved": flop_issued / t_kernel / 1e12, "peak": bf16 / 2, "unit": "TFLOP/s",
+                                 "frac": flop_issued / t_kernel / 1e12 / (bf16 / 2),
+                                 "algorithmic_tflops": flop_alg / t_kernel / 1e12,
+                                 "peak_basis": f"tf32 dense = half of {src}; achieved counts the 3 tf32 MMAs of the 3xTF32 "
+                                               "split (fp32-accurate result); algorithmic = 2*N*(19*256+256*512+512) fp32 flop"}}
+        del smp
+    model = wl.SyntheticVAETarget(3, seed=1)
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    x = torch.rand(100_000, 3) * 2.3 - 1.15
+    model.pdf_torch(x[:1000])
+    t0 = time.perf_counter()
+    model.pdf_torch(x)
+    t_cpu = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": 100_000 / t_cpu, "unit": "samples/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+                           "sample": "pdf_torch of the same decoder with the reference's torch operators on 1e5 samples"}
+    out["note"] = ("ms_pdf_torch_call = the call a controller step makes (weights re-read from the model + H2D + pack + "
+                   "kernel); the L2 is cold for the 1e7-sample input (160 MB in/out)")
+    return out
+
+
 def build_sets(name, n_total, rank, group, dev, engine, Robot, PlannerContext, max_sets=96):
     """Independent input sets (samples, p, q_base, u) resident in HBM; every rank holds its slice."""
     w = wl.WORKLOADS[name]
@@ -490,6 +532,7 @@ def cuda_arm(args):
                       "note": "one launch: shared rollout / forward pass / q, per-target gradient pass + adjoint"}
         del S3, c3, U3, P5, smp5
         torch.cuda.empty_cache()
+        also["target_decoder"] = target_decoder_block(dev, timed)
 
     # ---- with several GPUs: the same eval with the per-GPU workspace held fixed (weak scaling) -------
     if world > 1 and not args.weak and not args.no_also:

@@ -125,6 +125,12 @@ class DeviceTarget:
         if not bool(m.init):
             return self.init_uniform_grid(samples)
         self.refresh()
+        return self.evaluate_packed(samples)
+
+    @torch.no_grad()
+    def evaluate_packed(self, samples):
+        """The decoder kernel alone, on the weights of the last ``refresh()`` (samples [N, s_dim] on the device)."""
+        m = self.model
         sd, zd, nz, h1, h2, nl = self._dims
         if samples.dim() != 2 or samples.shape[1] != sd:
             raise ValueError(f"target decoder: samples must be [N, {sd}]")

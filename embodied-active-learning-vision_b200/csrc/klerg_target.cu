@@ -7,13 +7,16 @@
 // The first layer folds the (sample-independent) z part into a bias: h1_k = relu(c_zk + sum_d W1x[k][d] x_d);
 // it is produced by CUDA cores straight into shared memory as the A operand.  The second layer - the only dense
 // contraction of the whole KL-ergodic path, [N,H1] x [H1,H2] - runs on the tensor cores: tcgen05.mma kind::tf32,
-// M = 128 samples per tile, accumulators in TMEM (H2 <= 512 columns = the whole TMEM of an SM).  fp32 parity with
+// M = 128 samples per tile, accumulators in TMEM.  The H2 outputs are processed in passes of <= 256 TMEM columns
+// (H2 = 512: two passes, A re-produced per pass - cheap next to the MMAs) so that TWO CTAs share an SM (2 x 256
+// columns, half the shared memory each): while one CTA drains its accumulator the other one's MMAs keep the
+// tensor pipe busy (single CTA with a 512-column accumulator: pipe 65 % active; this layout: see profiles/).  fp32 parity with
 // the reference (1e-4 relative is the bar, ~1e-6 achieved) comes from the 3xTF32 split: every operand is
 // hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), and D += A_lo B_hi + A_hi B_lo + A_hi B_hi.
 // The third layer only needs its first ylogvar_dim rows: a dot product in the TMEM -> register epilogue, fused
 // with bias + ReLU of layer 2, the clamp, the mean over z, exp and amax.
 //
-// Roles inside a CTA (192 threads, one CTA per SM, persistent over sample tiles):
+// Roles inside a CTA (192 threads, two CTAs per SM, persistent over sample tiles):
 //   warps 0-3  thread = sample row: produce the A stages (hi/lo), later drain TMEM lane = row (epilogue)
 //   warp 4     one lane streams the pre-split W2 stages global -> shared with TMA bulk copies (cp.async.bulk)
 //   warp 5     one lane issues the tcgen05.mma's and commits stage / accumulator barriers
@@ -36,19 +39,21 @@ constexpr int THREADS = 192;       // 4 producer/epilogue warps + loader warp + 
 constexpr int A_STAGE = 2 * 2 * TM * 16;  // bytes: [part][chunk][row][16 B]
 constexpr long long SPIN_LIMIT_T = 1ll << 24;
 constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr size_t SMEM_HALF = 113 * 1024;  // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 
 struct Dims {
   int sd, zd, nz, h1, h2, nl, lp1, lp;
+  int halves, ncols;  // the H2 outputs are processed as `halves` accumulator passes of `ncols` <= 256 TMEM columns
 };
 
 __host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~(size_t)127; }
-// packed decoder (device): [t1: nz*h1*lp1 f32][e: h2*lp f32][b3: 16 f32][w2s: (h1/8) stages x 64*h2 bytes]
+// packed decoder (device): [t1: nz*h1*lp1 f32][e: h2*lp f32][b3: 16 f32][w2s: halves x (h1/8) stages x 64*ncols bytes]
 __host__ __device__ inline size_t off_t1(const Dims&) { return 0; }
 __host__ __device__ inline size_t off_e(const Dims& d) { return align128(sizeof(float) * (size_t)d.nz * d.h1 * d.lp1); }
 __host__ __device__ inline size_t off_b3(const Dims& d) { return off_e(d) + align128(sizeof(float) * (size_t)d.h2 * d.lp); }
 __host__ __device__ inline size_t off_w2(const Dims& d) { return off_b3(d) + 128; }
-__host__ __device__ inline size_t b_stage_bytes(const Dims& d) { return (size_t)64 * d.h2; }
-__host__ __device__ inline size_t packed_bytes(const Dims& d) { return off_w2(d) + (size_t)(d.h1 / 8) * b_stage_bytes(d); }
+__host__ __device__ inline size_t b_stage_bytes(const Dims& d) { return (size_t)64 * d.ncols; }
+__host__ __device__ inline size_t packed_bytes(const Dims& d) { return off_w2(d) + (size_t)d.halves * (d.h1 / 8) * b_stage_bytes(d); }
 
 bool make_dims(int sd, int zd, int nz, int h1, int h2, int nl, Dims& d) {
   if (sd < 1 || sd > 7) { set_error("target decoder: s_dim=%d outside 1..7", sd); return false; }
@@ -59,6 +64,8 @@ bool make_dims(int sd, int zd, int nz, int h1, int h2, int nl, Dims& d) {
   d.sd = sd; d.zd = zd; d.nz = nz; d.h1 = h1; d.h2 = h2; d.nl = nl;
   d.lp1 = sd <= 3 ? 4 : 8;
   d.lp = nl <= 3 ? 4 : 16;
+  d.halves = h2 > 256 ? 2 : 1;
+  d.ncols = h2 / d.halves;
   return true;
 }
 
@@ -102,17 +109,17 @@ __global__ void pack_decoder_kernel(const Dims d, const float* __restrict__ w1, 
       const int l = (int)(i - n_t1 - n_e);
       pb3[l] = l < d.nl ? b3[l] : 0.f;
     } else {
-      // W2[n][k] -> stage ks = k/8: [part][chunk c = (k%8)/4][n][k%4]
+      // W2[n][k] -> stage (half = n/ncols, ks = k/8): [part][chunk c = (k%8)/4][n % ncols][k%4]
       const long long r = i - n_t1 - n_e - 16;
       const int k = (int)(r % d.h1), n = (int)(r / d.h1);
       const float w = w2[r];
       const uint32_t hi = rna_tf32(w);
       const uint32_t lo = rna_tf32(w - __uint_as_float(hi));
-      const int ks = k >> 3, c = (k >> 2) & 1, q = k & 3;
-      const size_t stage_words = (size_t)16 * d.h2;  // 64*h2 bytes
-      const size_t base = (size_t)ks * stage_words + ((size_t)c * d.h2 + n) * 4 + q;
+      const int ks = k >> 3, c = (k >> 2) & 1, q = k & 3, hf = n / d.ncols, nn = n % d.ncols;
+      const size_t stage_words = (size_t)16 * d.ncols;  // 64*ncols bytes
+      const size_t base = ((size_t)hf * (d.h1 >> 3) + ks) * stage_words + ((size_t)c * d.ncols + nn) * 4 + q;
       w2s[base] = hi;
-      w2s[base + (size_t)8 * d.h2] = lo;  // part 1 starts after 2 chunks x h2 rows x 4 words
+      w2s[base + (size_t)8 * d.ncols] = lo;  // part 1 starts after 2 chunks x ncols rows x 4 words
     }
   }
 }
@@ -240,7 +247,7 @@ __device__ __forceinline__ float first_layer(const float* __restrict__ row, cons
 }
 
 template <int LP1, int LP>
-__global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) target_decoder_kernel(const DecodeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Dims d = a.d;
   const SmemLayout sl = smem_layout(d, a.stages);
@@ -311,6 +318,10 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
 
       for (int z = 0; z < d.nz; ++z) {
         const float* t1z = s_t1 + (size_t)z * d.h1 * LP1;
+        float y[LP - 1];
+#pragma unroll
+        for (int l = 0; l < LP - 1; ++l) y[l] = 0.f;
+        for (int hf = 0; hf < d.halves; ++hf) {  // body kept at the (tile, z) indentation
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
           const int s = it % stages;
           const unsigned ph = (it / stages) & 1u;
@@ -332,19 +343,16 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
           bar_arrive(&full_a[s]);
         }
-        // ---- epilogue of (tile, z): bias + ReLU of layer 2, dot with the logvar rows of layer 3 ----
+        // ---- epilogue of (tile, z, half): bias + ReLU of layer 2, dot with the logvar rows of layer 3 ----
         bar_wait(tmem_full, acc_phase, s_abort);
         acc_phase ^= 1u;
         tc_fence_after();
-        float y[LP - 1];
-#pragma unroll
-        for (int l = 0; l < LP - 1; ++l) y[l] = 0.f;
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < d.h2; c0 += 32) {
+        for (int c0 = 0; c0 < d.ncols; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(trow + (uint32_t)c0, r);
           tmem_ld_wait();
-          const float* erow = s_e + (size_t)c0 * LP;
+          const float* erow = s_e + (size_t)(hf * d.ncols + c0) * LP;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float4 ev = *reinterpret_cast<const float4*>(erow + j * LP);
@@ -368,7 +376,8 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
           }
         }
         tc_fence_before();
-        bar_arrive(tmem_empty);  // accumulator drained: the MMA warp may start the next (tile, z)
+        bar_arrive(tmem_empty);  // accumulator drained: the MMA warp may start the next (tile, z, half)
+        }
 #pragma unroll
         for (int l = 0; l < LP - 1; ++l)
           if (l < d.nl) ysum[l] += fminf(fmaxf(y[l] + b3[l], a.clamp_lo), a.clamp_hi);  // torch.clamp (vae.py:266)
@@ -385,26 +394,24 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
       const unsigned char* w2s = a.packed + off_w2(d);
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-        for (int z = 0; z < d.nz; ++z)
+        for (int zh = 0; zh < d.nz * d.halves; ++zh)
           for (int ks = 0; ks < ksteps; ++ks, ++it) {
-            const int s = it % stages;
+            const int s = it % stages, hf = zh % d.halves;
             const unsigned ph = (it / stages) & 1u;
             bar_wait(&empty[s], ph ^ 1u, s_abort);
             bar_expect_tx(&full_b[s], bstage);
-            bulk_g2s(sB + (size_t)s * bstage, w2s + (size_t)ks * bstage, bstage, &full_b[s]);
+            bulk_g2s(sB + (size_t)s * bstage, w2s + ((size_t)hf * ksteps + ks) * bstage, bstage, &full_b[s]);
           }
     }
   } else {
     // ================= MMA issue =================
     if (lane == 0) {
-      const int nsplit = d.h2 > 256 ? 2 : 1;
-      const int ncols = d.h2 / nsplit;
-      const uint32_t idesc = instr_desc_tf32(TM, ncols);
+      const uint32_t idesc = instr_desc_tf32(TM, d.ncols);
       // LBO = stride between the two 16-byte K chunks of an MMA, SBO = stride between 8-row groups
-      const uint32_t a_lbo = TM * 16, a_sbo = 128, b_lbo = (uint32_t)d.h2 * 16, b_sbo = 128;
+      const uint32_t a_lbo = TM * 16, a_sbo = 128, b_lbo = (uint32_t)d.ncols * 16, b_sbo = 128;
       uint32_t it = 0, item = 0;
       for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-        for (int z = 0; z < d.nz; ++z, ++item) {
+        for (int zh = 0; zh < d.nz * d.halves; ++zh, ++item) {
           if (item > 0) bar_wait(tmem_empty, (item - 1) & 1u, s_abort);
           tc_fence_after();
           for (int ks = 0; ks < ksteps; ++ks, ++it) {
@@ -414,16 +421,12 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
             bar_wait(&full_b[s], ph, s_abort);
             tc_fence_after();
             const uint32_t a_hi = smem_addr(sA + (size_t)s * A_STAGE), a_lo = a_hi + 2 * TM * 16;
-            const uint32_t b_hi0 = smem_addr(sB + (size_t)s * bstage), b_lo0 = b_hi0 + 32u * (uint32_t)d.h2;
+            const uint32_t b_hi = smem_addr(sB + (size_t)s * bstage), b_lo = b_hi + 32u * (uint32_t)d.ncols;
             const uint64_t da_hi = smem_desc(a_hi, a_lbo, a_sbo), da_lo = smem_desc(a_lo, a_lbo, a_sbo);
-            for (int nh = 0; nh < nsplit; ++nh) {
-              const uint32_t boff = (uint32_t)(nh * ncols) * 16u;
-              const uint64_t db_hi = smem_desc(b_hi0 + boff, b_lbo, b_sbo), db_lo = smem_desc(b_lo0 + boff, b_lbo, b_sbo);
-              const uint32_t dcol = tmem + (uint32_t)(nh * ncols);
-              tc_mma_tf32(dcol, da_lo, db_hi, idesc, ks > 0 ? 1u : 0u);  // small terms first
-              tc_mma_tf32(dcol, da_hi, db_lo, idesc, 1u);
-              tc_mma_tf32(dcol, da_hi, db_hi, idesc, 1u);
-            }
+            const uint64_t db_hi = smem_desc(b_hi, b_lbo, b_sbo), db_lo = smem_desc(b_lo, b_lbo, b_sbo);
+            tc_mma_tf32(tmem, da_lo, db_hi, idesc, ks > 0 ? 1u : 0u);  // small terms first
+            tc_mma_tf32(tmem, da_hi, db_lo, idesc, 1u);
+            tc_mma_tf32(tmem, da_hi, db_hi, idesc, 1u);
             tc_commit(&empty[s]);  // stage free once these MMAs have read it
           }
           tc_commit(tmem_full);  // accumulator complete -> epilogue
@@ -486,9 +489,15 @@ extern "C" int klerg_target_decoder_pdf(const void* packed, int32_t s_dim, int32
   if (N == 0) return 0;
   if (!packed || !samples || !p_out) { set_error("target_decoder_pdf: null pointer"); return -1; }
   if ((uintptr_t)packed & 127) { set_error("target_decoder_pdf: packed buffer must be 128-byte aligned"); return -1; }
-  int stages = 8;
-  while (stages >= 2 && smem_layout(d, stages).total > SMEM_MAX) --stages;
-  if (stages < 2) { set_error("target_decoder_pdf: decoder tables (%d z vectors x %d) do not fit in shared memory", n_z, h1); return -2; }
+  // two CTAs per SM (each <= 256 TMEM columns, half the shared memory): one CTA's epilogue overlaps the other's MMAs
+  int stages = 8, per_sm = 2;
+  while (stages >= 3 && smem_layout(d, stages).total > SMEM_HALF) --stages;
+  if (stages < 3) {
+    per_sm = 1;
+    stages = 8;
+    while (stages >= 2 && smem_layout(d, stages).total > SMEM_MAX) --stages;
+    if (stages < 2) { set_error("target_decoder_pdf: decoder tables (%d z vectors x %d) do not fit in shared memory", n_z, h1); return -2; }
+  }
   DecodeArgs a;
   a.packed = (const unsigned char*)packed;
   a.samples = samples;
@@ -501,10 +510,11 @@ extern "C" int klerg_target_decoder_pdf(const void* packed, int32_t s_dim, int32
   a.clamp_hi = clamp_hi;
   a.stages = stages;
   int cols = 32;
-  while (cols < h2) cols <<= 1;
+  while (cols < d.ncols) cols <<= 1;
   a.tmem_cols = cols;
   const long long tiles = (N + TM - 1) / TM;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const long long slots = (long long)per_sm * sm_count();
+  const int grid = (int)(tiles < slots ? tiles : slots);
   const size_t smem = smem_layout(d, stages).total;
   cudaStream_t st = (cudaStream_t)stream;
   if (d.lp1 == 4 && d.lp == 4) return launch_decoder<4, 4>(a, grid, smem, st);

@@ -52,31 +52,40 @@ class MixtureTarget:
 
 
 class SyntheticVAETarget:
-    """Stand-in for the reference's random-init CVAE uncertainty head (scripts/vae/vae.py:244-275):
-    p(x) = exp(clamp(decoder([z || x])[:, 0], -10, 2)), decoder = MLP z+s -> 256 -> 512 -> 1+feat."""
+    """Random-init stand-in for the reference's CVAE as the controller sees it (scripts/vae/vae.py:11-110,244-275):
+    the attributes ``pdf_torch`` reads - ``decode`` (Linear z+s -> 256, ReLU, Linear 256 -> 512, ReLU, Linear
+    512 -> 1+feat), ``z_samples``, ``ylogvar_dim``, ``logvar_lims``, ``init`` - and a torch-CPU ``pdf_torch`` with
+    the reference's operators for the CPU legs.  On a GPU the controller wraps it in ``DeviceTarget``."""
 
-    def __init__(self, s_dim, z_dim=16, hidden=(512, 256), seed=0, device="cpu"):
+    def __init__(self, s_dim, z_dim=16, hidden=(512, 256), seed=0, feat=8):
         g = torch.Generator().manual_seed(seed)
-        dims = [z_dim + s_dim] + list(reversed(hidden)) + [1 + 8]
-        self.layers = []
-        for a, b in zip(dims[:-1], dims[1:]):
+        dims = [z_dim + s_dim] + list(reversed(hidden)) + [1 + feat]
+        layers = []
+        for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
             bound = 1.0 / math.sqrt(a)
-            w = (torch.rand(b, a, generator=g) * 2 - 1) * bound * 3.0
-            bias = (torch.rand(b, generator=g) * 2 - 1) * bound
-            self.layers.append((w.to(device), bias.to(device)))
-        self.z = torch.randn(1, z_dim, generator=g).to(device)
-        self.device = device
+            lin = torch.nn.Linear(a, b)
+            with torch.no_grad():
+                lin.weight.copy_((torch.rand(b, a, generator=g) * 2 - 1) * bound * 3.0)
+                lin.bias.copy_((torch.rand(b, generator=g) * 2 - 1) * bound)
+            layers.append(lin)
+            if i + 2 < len(dims):
+                layers.append(torch.nn.ReLU())
+        self.decode = torch.nn.Sequential(*layers).requires_grad_(False)
+        self.z_samples = torch.randn(1, z_dim, generator=g)
+        self.ylogvar_dim = torch.tensor(1)
+        self.logvar_lims = (-10, 2)
+        self.init = torch.tensor([True])
+        self.dx = False
+        self.use_buffer = False
+        self.device = "cpu"
         self.dtype = torch.float32
 
     @torch.no_grad()
     def pdf_torch(self, x):
-        x = x.to(device=self.device, dtype=torch.float32)
-        h = torch.cat([self.z.repeat(x.shape[0], 1), x], dim=1)
-        for i, (w, b) in enumerate(self.layers):
-            h = torch.nn.functional.linear(h, w, b)
-            if i + 1 < len(self.layers):
-                h = torch.relu(h)
-        return torch.exp(torch.clamp(h[:, :1], -10, 2)).amax(1)
+        x = x.to(device="cpu", dtype=torch.float32)
+        latent = torch.cat([self.z_samples.repeat(x.shape[0], 1), x], dim=1)
+        y = self.decode(latent)[:, :int(self.ylogvar_dim)]
+        return torch.amax(torch.exp(torch.clamp(y, *self.logvar_lims)), 1).squeeze()
 
     def init_uniform_grid(self, x):
         return x.sum(1) ** 0
@@ -84,7 +93,11 @@ class SyntheticVAETarget:
 
 def make_target(kind, lims, seed=1, device="cpu"):
     if kind == "vae":
-        return SyntheticVAETarget(len(lims), seed=seed, device=device)
+        model = SyntheticVAETarget(len(lims), seed=seed)
+        if torch.device(device).type == "cuda":
+            from control_torch.target_decoder import DeviceTarget
+            return DeviceTarget(model, device)
+        return model
     return MixtureTarget(lims, seed=seed, device=device)
 
 
