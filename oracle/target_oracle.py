@@ -46,3 +46,22 @@ def vae_pdf(samples, weights, z_rows, n_logvar, logvar_lims=(-10, 2), shift=None
         var_data = torch.mean(var_data.reshape(z_rows.shape[0], n, n_logvar), 0)  # vae.py:268-270
     var_data = torch.exp(var_data)
     return torch.amax(var_data, 1).squeeze()  # vae.py:273-275
+
+
+@torch.no_grad()
+def trainer_spread_grade(traj, samples, std, pdf_torch, xi=4.0):
+    """The trainer's per-iteration "spread" and "grade" (dist_modules/trainer_module.py:511-538), with
+    ``traj_spread_vec`` restated from control_torch/klerg_utils.py:24-29 and ``pdf_torch`` = the model's density
+    (vae.py:244-275).  traj [M, D] = all replay-buffer states, samples [N, D].  Returns
+    (spread, grade, max_q, entropy_dist)."""
+    dim = samples.shape[1]
+    std_t = torch.tensor([std] * dim)
+    inner = torch.square(traj[:, :dim].unsqueeze(0) - samples.unsqueeze(1)) / torch.abs(std_t)  # klerg_utils.py:7-10
+    max_q = torch.amax(torch.exp(-0.5 * torch.sum(inner, 2)) / 1.0, 1)  # traj_spread_vec, nu = 1 (trainer_module.py:518)
+    max_q = max_q / torch.max(max_q)
+    spread = max_q.mean()
+    entropy_dist = pdf_torch(samples)
+    entropy_dist = entropy_dist ** spread
+    entropy_dist = entropy_dist / entropy_dist.max()
+    grade = torch.clamp(10.0 ** (-torch.log10(entropy_dist.min()) - xi), max=0.01)
+    return spread, grade, max_q, entropy_dist

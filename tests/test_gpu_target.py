@@ -130,3 +130,40 @@ def test_full_size_properties(td):
     idx = torch.arange(0, case["n"], 9973, device="cuda")
     ref = model.pdf_torch(s[idx].cpu())
     np.testing.assert_allclose(p[idx].cpu().numpy(), ref.numpy(), rtol=RTOL, atol=0)
+
+
+def test_trainer_spread_grade_block(td):
+    """the trainer's per-iteration spread / grade block (dist_modules/trainer_module.py:511-538)
+    written exactly as the reference writes it, but on CUDA tensors with this package's drop-ins
+    (control_torch.klerg_utils.traj_spread_vec and the model wrapped in DeviceTarget), against the CPU oracle."""
+    from control_torch.klerg_utils import traj_spread_vec
+    from oracle import target_oracle
+    case = dict(TARGET_CASES["default"], n=5000)
+    g = torch.Generator().manual_seed(12)
+    model = DecoderModel(case, torch.randn(1, case["zd"], generator=g))
+    samples = target_samples(case, seed=4)
+    traj = torch.rand(700, 3, generator=g) * 2 - 1
+    std = 0.05
+    ref = target_oracle.trainer_spread_grade(traj, samples, std, model.pdf_torch)
+
+    device = torch.device("cuda")
+    dev_model = td.DeviceTarget(model)
+    s_dev, t_dev = samples.to(device), traj.to(device)
+    # ---- trainer_module.py:511-538, verbatim modulo `self.` ----
+    dim = s_dev.shape[1]
+    explr_idx = torch.arange(dim, device=device)
+    std_t = torch.tensor([std] * dim, device=device)
+    max_q = traj_spread_vec(t_dev, s_dev, explr_idx, std_t, nu=1.)
+    max_q /= torch.max(max_q)
+    spread = max_q.mean()
+    entropy_dist = dev_model.pdf_torch(s_dev)
+    entropy_dist = entropy_dist**spread
+    entropy_dist /= entropy_dist.max()
+    grade = torch.clamp(10.**(-torch.log10(entropy_dist.min()) - 4), max=0.01)
+    # ----
+    dev_model.check_fault()
+    assert max_q.is_cuda and entropy_dist.is_cuda
+    np.testing.assert_allclose(max_q.cpu().numpy(), ref[2].numpy(), rtol=RTOL, atol=1e-30)
+    np.testing.assert_allclose(float(spread), float(ref[0]), rtol=RTOL)
+    np.testing.assert_allclose(entropy_dist.cpu().numpy(), ref[3].numpy(), rtol=RTOL)
+    np.testing.assert_allclose(float(grade), float(ref[1]), rtol=1e-3)
