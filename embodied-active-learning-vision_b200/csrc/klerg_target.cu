@@ -36,10 +36,12 @@ namespace {
 
 constexpr int TM = 128;            // samples per tile = UMMA M = TMEM lanes
 constexpr int THREADS = 192;       // 4 producer/epilogue warps + loader warp + MMA warp
-constexpr int A_STAGE = 2 * 2 * TM * 16;  // bytes: [part][chunk][row][16 B]
+constexpr int KS = 4;              // MMA K-steps (8 tf32 each) per operand stage: 12 MMAs per tcgen05.commit
+constexpr int A_COL0 = 256;        // TMEM columns [0,256) accumulator, [256,512) A ring (16*KS columns per stage)
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 256 / (16 * KS);  // ring depth limit: the A ring's TMEM columns
 constexpr long long SPIN_LIMIT_T = 1ll << 24;
 constexpr size_t SMEM_MAX = 227 * 1024;
-constexpr size_t SMEM_HALF = 113 * 1024;  // two CTAs per SM (228 KB per SM, 1 KB reserved per CTA)
 
 struct Dims {
   int sd, zd, nz, h1, h2, nl, lp1, lp;
@@ -52,8 +54,8 @@ __host__ __device__ inline size_t off_t1(const Dims&) { return 0; }
 __host__ __device__ inline size_t off_e(const Dims& d) { return align128(sizeof(float) * (size_t)d.nz * d.h1 * d.lp1); }
 __host__ __device__ inline size_t off_b3(const Dims& d) { return off_e(d) + align128(sizeof(float) * (size_t)d.h2 * d.lp); }
 __host__ __device__ inline size_t off_w2(const Dims& d) { return off_b3(d) + 128; }
-__host__ __device__ inline size_t b_stage_bytes(const Dims& d) { return (size_t)64 * d.ncols; }
-__host__ __device__ inline size_t packed_bytes(const Dims& d) { return off_w2(d) + (size_t)d.halves * (d.h1 / 8) * b_stage_bytes(d); }
+__host__ __device__ inline size_t b_step_bytes(const Dims& d) { return (size_t)64 * d.ncols; }  // one K-step of W2: [hi|lo][chunk][ncols][16 B]
+__host__ __device__ inline size_t packed_bytes(const Dims& d) { return off_w2(d) + (size_t)d.halves * (d.h1 / 8) * b_step_bytes(d); }
 
 bool make_dims(int sd, int zd, int nz, int h1, int h2, int nl, Dims& d) {
   if (sd < 1 || sd > 7) { set_error("target decoder: s_dim=%d outside 1..7", sd); return false; }
@@ -143,11 +145,11 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(const Dims& d, int stages) {
   SmemLayout s;
   size_t o = 0;
-  s.a = o;  o += (size_t)stages * A_STAGE;
-  s.b = o;  o += (size_t)stages * b_stage_bytes(d);
+  s.a = 0;
+  s.b = o;  o += (size_t)stages * KS * b_step_bytes(d);
   s.t1 = o; o = align128(o + sizeof(float) * (size_t)d.nz * d.h1 * d.lp1);
   s.e = o;  o = align128(o + sizeof(float) * (size_t)d.h2 * d.lp);
-  s.bars = o; o += 8 * (3 * 8 + 2) + 16;  // full_a[8] full_b[8] empty[8] tmem_full tmem_empty | tmem addr, abort
+  s.bars = o; o += 8 * (3 * MAX_STAGES + 2) + 16;  // full_a full_b empty tmem_full tmem_empty | tmem addr, abort
   s.total = o;
   return s;
 }
@@ -206,6 +208,23 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in TMEM (lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 8 consecutive columns of this thread's TMEM lane <- registers
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 // K-major, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version 1 [46,48))
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -247,27 +266,30 @@ __device__ __forceinline__ float first_layer(const float* __restrict__ row, cons
 }
 
 template <int LP1, int LP>
-__global__ void __launch_bounds__(THREADS, 2) target_decoder_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const DecodeArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const Dims d = a.d;
   const SmemLayout sl = smem_layout(d, a.stages);
-  unsigned char* sA = smem + sl.a;
   unsigned char* sB = smem + sl.b;
   float* s_t1 = (float*)(smem + sl.t1);
   float* s_e = (float*)(smem + sl.e);
   unsigned long long* full_a = (unsigned long long*)(smem + sl.bars);
-  unsigned long long* full_b = full_a + 8;
-  unsigned long long* empty = full_a + 16;
-  unsigned long long* tmem_full = full_a + 24;
-  unsigned long long* tmem_empty = full_a + 25;
-  uint32_t* s_tmem = (uint32_t*)(full_a + 26);
+  unsigned long long* full_b = full_a + MAX_STAGES;
+  unsigned long long* empty = full_b + MAX_STAGES;
+  unsigned long long* tmem_full = empty + MAX_STAGES;
+  unsigned long long* tmem_empty = tmem_full + 1;
+  uint32_t* s_tmem = (uint32_t*)(tmem_empty + 1);
   volatile unsigned* s_abort = (volatile unsigned*)(s_tmem + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ksteps = d.h1 >> 3;
-  const int stages = a.stages;
+  const int ksteps = d.h1 >> 3;                 // MMA K-steps (8 tf32 each) per accumulator pass
+  const int nst = (ksteps + KS - 1) / KS;       // operand stages per pass (KS K-steps each, the last one may be short)
+  const int stages = a.stages;                  // ring depth: W2 stages in shared memory, A stages in TMEM
   const long long tiles = (a.n + TM - 1) / TM;
-  const unsigned bstage = (unsigned)b_stage_bytes(d);
+  const unsigned bstep = (unsigned)b_step_bytes(d);
+  const int passes = d.nz * d.halves;           // accumulator passes per sample tile
+  const long long my_tiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long n_items = my_tiles * passes;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -281,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 2) target_decoder_kernel(const Decode
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   {
@@ -295,142 +317,207 @@ __global__ void __launch_bounds__(THREADS, 2) target_decoder_kernel(const Decode
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *s_tmem;
+  const uint32_t tmem = *s_tmem;  // accumulator: columns [0, ncols); A ring: columns [A_COL0, A_COL0 + stages*16*KS)
 
   if (warp < 4) {
-    // ================= producers of A, then epilogue of the same rows =================
+    // ================= producers of A (TMEM), then epilogue of the same rows =================
     const int row = threadIdx.x;
     const float* b3 = (const float*)(a.packed + off_b3(d));
     const float inv_nz = 1.0f / (float)d.nz;
-    uint32_t it = 0, acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const long long rg = tile * TM + row;
-      const bool valid = rg < a.n;
-      float x[LP1 - 1];
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const long long total_stages = n_items * nst;
+    long long produced = 0;
+    // producer cursor (kept incrementally: no divisions in the loop): stage within the pass, pass within the tile, tile
+    int p_st = 0, p_zh = 0, p_s = 0;
+    unsigned p_ph = 0;
+    long long p_tile = 0, x_tile = -1;
+    int pending = -1;  // A stage whose TMEM stores are issued but not yet signalled
+    int e_zh = 0;      // epilogue cursor
+    long long e_tile = 0;
+    float x[LP1 - 1];
 #pragma unroll
-      for (int j = 0; j < LP1 - 1; ++j) {
-        x[j] = 0.f;
-        if (valid && j < d.sd) x[j] = a.samples[rg * d.sd + j] - (a.shift ? a.shift[j] : 0.f);
-      }
-      float ysum[LP - 1];
+    for (int j = 0; j < LP1 - 1; ++j) x[j] = 0.f;
+    float y[LP - 1], ysum[LP - 1];
 #pragma unroll
-      for (int l = 0; l < LP - 1; ++l) ysum[l] = 0.f;
+    for (int l = 0; l < LP - 1; ++l) y[l] = ysum[l] = 0.f;
+    uint32_t acc_phase = 0;
 
-      for (int z = 0; z < d.nz; ++z) {
-        const float* t1z = s_t1 + (size_t)z * d.h1 * LP1;
-        float y[LP - 1];
+    for (long long item = 0; item < n_items; ++item) {
+      // ---- produce: the rest of this pass plus a head start of one stage into the next pass, so the MMA warp has
+      //      work queued while these threads drain the accumulator ----
+      long long goal = (item + 1) * nst + (stages > 2 ? 1 : 0);
+      if (goal > total_stages) goal = total_stages;
+      for (; produced < goal; ++produced) {
+        const int z = d.halves == 2 ? (p_zh >> 1) : p_zh;
+        if (p_tile != x_tile) {  // first stage of a new sample tile: fetch this row's sample
+          x_tile = p_tile;
+          const long long rg = (blockIdx.x + p_tile * gridDim.x) * TM + row;
+#pragma unroll
+          for (int j = 0; j < LP1 - 1; ++j) {
+            x[j] = 0.f;
+            if (rg < a.n && j < d.sd) x[j] = a.samples[rg * d.sd + j] - (a.shift ? a.shift[j] : 0.f);
+          }
+        }
+        const int ks0 = p_st * KS;
+        const int nk = min(KS, ksteps - ks0);
+        const float* t1z = s_t1 + ((size_t)z * d.h1 + (size_t)ks0 * 8) * LP1;
+        const int sa = p_s;
+        bar_wait(&empty[sa], p_ph ^ 1u, s_abort);
+        tc_fence_after();
+        const uint32_t acol = trow + (uint32_t)(A_COL0 + sa * (16 * KS));
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+          if (kk < nk) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              // tf32 split by truncation: hi keeps the top 10 mantissa bits, lo = h - hi is exact in fp32 and the tensor
+              // core reads its top 10 bits -> |h - hi - lo_tf32| < 2^-20 |h| (cvt.rna is emulated in SASS: ~5x the work)
+              const float h = first_layer<LP1>(t1z + (size_t)(kk * 8 + q) * LP1, x);
+              hi[q] = __float_as_uint(h) & 0xFFFFE000u;
+              lo[q] = __float_as_uint(h - __uint_as_float(hi[q]));
+            }
+            if (kk == 0 && pending >= 0) {  // the previous stage's TMEM stores had this K-step's arithmetic to land
+              asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+              tc_fence_before();
+              bar_arrive(&full_a[pending]);
+            }
+            tmem_st8(acol + kk * 16, hi);
+            tmem_st8(acol + kk * 16 + 8, lo);
+          }
+        }
+        pending = sa;
+        if (++p_s == stages) {
+          p_s = 0;
+          p_ph ^= 1u;
+        }
+        if (++p_st == nst) {
+          p_st = 0;
+          if (++p_zh == passes) {
+            p_zh = 0;
+            ++p_tile;
+          }
+        }
+      }
+      if (pending >= 0) {
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        bar_arrive(&full_a[pending]);
+        pending = -1;
+      }
+      // ---- epilogue of (tile, z, half): bias + ReLU of layer 2, dot with the logvar rows of layer 3 ----
+      const long long t_local = e_tile;
+      const int zh = e_zh;
+      const int hf = d.halves == 2 ? (zh & 1) : 0;
+      if (++e_zh == passes) {
+        e_zh = 0;
+        ++e_tile;
+      }
+      bar_wait(tmem_full, acc_phase, s_abort);
+      acc_phase ^= 1u;
+      tc_fence_after();
+      if (hf == 0) {
 #pragma unroll
         for (int l = 0; l < LP - 1; ++l) y[l] = 0.f;
-        for (int hf = 0; hf < d.halves; ++hf) {  // body kept at the (tile, z) indentation
-        for (int ks = 0; ks < ksteps; ++ks, ++it) {
-          const int s = it % stages;
-          const unsigned ph = (it / stages) & 1u;
-          bar_wait(&empty[s], ph ^ 1u, s_abort);
-          float h[8];
+      }
+      for (int c0 = 0; c0 < d.ncols; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(trow + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const float* erow = s_e + (size_t)(hf * d.ncols + c0) * LP;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) h[q] = first_layer<LP1>(t1z + (size_t)(ks * 8 + q) * LP1, x);
-          uint32_t hi[8], lo[8];
+        for (int j = 0; j < 32; ++j) {
+          const float4 ev = *reinterpret_cast<const float4*>(erow + j * LP);
+          const float hj = fmaxf(__uint_as_float(r[j]) + ev.x, 0.f);
+          y[0] = fmaf(ev.y, hj, y[0]);
+          y[1] = fmaf(ev.z, hj, y[1]);
+          y[2] = fmaf(ev.w, hj, y[2]);
+          if constexpr (LP == 16) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            hi[q] = rna_tf32(h[q]);
-            lo[q] = rna_tf32(h[q] - __uint_as_float(hi[q]));
-          }
-          unsigned char* base = sA + (size_t)s * A_STAGE + (size_t)row * 16;
-          *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(base + TM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *reinterpret_cast<uint4*>(base + 2 * TM * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(base + 3 * TM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
-          bar_arrive(&full_a[s]);
-        }
-        // ---- epilogue of (tile, z, half): bias + ReLU of layer 2, dot with the logvar rows of layer 3 ----
-        bar_wait(tmem_full, acc_phase, s_abort);
-        acc_phase ^= 1u;
-        tc_fence_after();
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < d.ncols; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(trow + (uint32_t)c0, r);
-          tmem_ld_wait();
-          const float* erow = s_e + (size_t)(hf * d.ncols + c0) * LP;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float4 ev = *reinterpret_cast<const float4*>(erow + j * LP);
-            const float hj = fmaxf(__uint_as_float(r[j]) + ev.x, 0.f);
-            y[0] = fmaf(ev.y, hj, y[0]);
-            if constexpr (LP == 4) {
-              y[1] = fmaf(ev.z, hj, y[1]);
-              y[2] = fmaf(ev.w, hj, y[2]);
-            } else {
-              y[1] = fmaf(ev.z, hj, y[1]);
-              y[2] = fmaf(ev.w, hj, y[2]);
-#pragma unroll
-              for (int g = 1; g < 4; ++g) {
-                const float4 ew = *reinterpret_cast<const float4*>(erow + j * LP + 4 * g);
-                y[4 * g - 1] = fmaf(ew.x, hj, y[4 * g - 1]);
-                y[4 * g + 0] = fmaf(ew.y, hj, y[4 * g + 0]);
-                y[4 * g + 1] = fmaf(ew.z, hj, y[4 * g + 1]);
-                y[4 * g + 2] = fmaf(ew.w, hj, y[4 * g + 2]);
-              }
+            for (int g = 1; g < 4; ++g) {
+              const float4 ew = *reinterpret_cast<const float4*>(erow + j * LP + 4 * g);
+              y[4 * g - 1] = fmaf(ew.x, hj, y[4 * g - 1]);
+              y[4 * g + 0] = fmaf(ew.y, hj, y[4 * g + 0]);
+              y[4 * g + 1] = fmaf(ew.z, hj, y[4 * g + 1]);
+              y[4 * g + 2] = fmaf(ew.w, hj, y[4 * g + 2]);
             }
           }
         }
-        tc_fence_before();
-        bar_arrive(tmem_empty);  // accumulator drained: the MMA warp may start the next (tile, z, half)
-        }
+      }
+      tc_fence_before();
+      bar_arrive(tmem_empty);  // accumulator drained: the MMA warp may start the next (tile, z, half)
+      if (hf == d.halves - 1) {
 #pragma unroll
         for (int l = 0; l < LP - 1; ++l)
           if (l < d.nl) ysum[l] += fminf(fmaxf(y[l] + b3[l], a.clamp_lo), a.clamp_hi);  // torch.clamp (vae.py:266)
       }
-      float p = -INFINITY;
+      if (zh == passes - 1) {
+        float p = -INFINITY;
 #pragma unroll
-      for (int l = 0; l < LP - 1; ++l)
-        if (l < d.nl) p = fmaxf(p, expf(d.nz > 1 ? ysum[l] * inv_nz : ysum[l]));  // mean over z, exp, amax (vae.py:267-273)
-      if (valid) a.out[rg] = p;
+        for (int l = 0; l < LP - 1; ++l) {
+          if (l < d.nl) p = fmaxf(p, expf(d.nz > 1 ? ysum[l] * inv_nz : ysum[l]));  // mean over z, exp, amax (vae.py:267-273)
+          ysum[l] = 0.f;
+        }
+        const long long rg = (blockIdx.x + t_local * gridDim.x) * TM + row;
+        if (rg < a.n) a.out[rg] = p;
+      }
     }
   } else if (warp == 4) {
-    // ================= W2 stages: TMA bulk copies, one per K-step =================
+    // ================= W2 stages: one TMA bulk copy per stage (KS K-steps, contiguous in the packed buffer) =================
     if (lane == 0) {
       const unsigned char* w2s = a.packed + off_w2(d);
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-        for (int zh = 0; zh < d.nz * d.halves; ++zh)
-          for (int ks = 0; ks < ksteps; ++ks, ++it) {
-            const int s = it % stages, hf = zh % d.halves;
-            const unsigned ph = (it / stages) & 1u;
-            bar_wait(&empty[s], ph ^ 1u, s_abort);
-            bar_expect_tx(&full_b[s], bstage);
-            bulk_g2s(sB + (size_t)s * bstage, w2s + ((size_t)hf * ksteps + ks) * bstage, bstage, &full_b[s]);
+      int s = 0, zh = 0;
+      unsigned ph = 0;
+      for (long long item = 0; item < n_items; ++item) {
+        const int hf = d.halves == 2 ? (zh & 1) : 0;
+        if (++zh == passes) zh = 0;
+        for (int st = 0; st < nst; ++st) {
+          const int ks0 = st * KS;
+          const unsigned bytes = (unsigned)min(KS, ksteps - ks0) * bstep;
+          bar_wait(&empty[s], ph ^ 1u, s_abort);
+          bar_expect_tx(&full_b[s], bytes);
+          bulk_g2s(sB + (size_t)s * (KS * bstep), w2s + ((size_t)hf * ksteps + ks0) * bstep, bytes, &full_b[s]);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
           }
+        }
+      }
     }
   } else {
-    // ================= MMA issue =================
+    // ================= MMA issue: A from TMEM, B from shared memory; one commit per stage =================
     if (lane == 0) {
       const uint32_t idesc = instr_desc_tf32(TM, d.ncols);
-      // LBO = stride between the two 16-byte K chunks of an MMA, SBO = stride between 8-row groups
-      const uint32_t a_lbo = TM * 16, a_sbo = 128, b_lbo = (uint32_t)d.ncols * 16, b_sbo = 128;
-      uint32_t it = 0, item = 0;
-      for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
-        for (int zh = 0; zh < d.nz * d.halves; ++zh, ++item) {
-          if (item > 0) bar_wait(tmem_empty, (item - 1) & 1u, s_abort);
+      // B: LBO = stride between the two 16-byte K chunks of an MMA, SBO = stride between 8-row groups
+      const uint32_t b_lbo = (uint32_t)d.ncols * 16, b_sbo = 128;
+      int s = 0;
+      unsigned ph = 0;
+      for (long long item = 0; item < n_items; ++item) {
+        if (item > 0) bar_wait(tmem_empty, (unsigned)(item - 1) & 1u, s_abort);
+        tc_fence_after();
+        for (int st = 0; st < nst; ++st) {
+          const int nk = min(KS, ksteps - st * KS);
+          bar_wait(&full_a[s], ph, s_abort);
+          bar_wait(&full_b[s], ph, s_abort);
           tc_fence_after();
-          for (int ks = 0; ks < ksteps; ++ks, ++it) {
-            const int s = it % stages;
-            const unsigned ph = (it / stages) & 1u;
-            bar_wait(&full_a[s], ph, s_abort);
-            bar_wait(&full_b[s], ph, s_abort);
-            tc_fence_after();
-            const uint32_t a_hi = smem_addr(sA + (size_t)s * A_STAGE), a_lo = a_hi + 2 * TM * 16;
-            const uint32_t b_hi = smem_addr(sB + (size_t)s * bstage), b_lo = b_hi + 32u * (uint32_t)d.ncols;
-            const uint64_t da_hi = smem_desc(a_hi, a_lbo, a_sbo), da_lo = smem_desc(a_lo, a_lbo, a_sbo);
+          const uint32_t a0 = tmem + (uint32_t)(A_COL0 + s * (16 * KS));
+          const uint32_t b0 = smem_addr(sB + (size_t)s * (KS * bstep));
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint32_t a_hi = a0 + kk * 16, a_lo = a_hi + 8;
+            const uint32_t b_hi = b0 + kk * bstep, b_lo = b_hi + 32u * (uint32_t)d.ncols;
             const uint64_t db_hi = smem_desc(b_hi, b_lbo, b_sbo), db_lo = smem_desc(b_lo, b_lbo, b_sbo);
-            tc_mma_tf32(tmem, da_lo, db_hi, idesc, ks > 0 ? 1u : 0u);  // small terms first
-            tc_mma_tf32(tmem, da_hi, db_lo, idesc, 1u);
-            tc_mma_tf32(tmem, da_hi, db_hi, idesc, 1u);
-            tc_commit(&empty[s]);  // stage free once these MMAs have read it
+            tc_mma_tf32_ts(tmem, a_lo, db_hi, idesc, (st | kk) ? 1u : 0u);  // small terms first
+            tc_mma_tf32_ts(tmem, a_hi, db_lo, idesc, 1u);
+            tc_mma_tf32_ts(tmem, a_hi, db_hi, idesc, 1u);
           }
-          tc_commit(tmem_full);  // accumulator complete -> epilogue
+          tc_commit(&empty[s]);  // A and W2 stage free once these MMAs have read their operands
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
+        tc_commit(tmem_full);  // accumulator complete -> epilogue
+      }
     }
   }
   tc_fence_before();
@@ -439,7 +526,7 @@ __global__ void __launch_bounds__(THREADS, 2) target_decoder_kernel(const Decode
   if (warp == 5) {
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -489,15 +576,10 @@ extern "C" int klerg_target_decoder_pdf(const void* packed, int32_t s_dim, int32
   if (N == 0) return 0;
   if (!packed || !samples || !p_out) { set_error("target_decoder_pdf: null pointer"); return -1; }
   if ((uintptr_t)packed & 127) { set_error("target_decoder_pdf: packed buffer must be 128-byte aligned"); return -1; }
-  // two CTAs per SM (each <= 256 TMEM columns, half the shared memory): one CTA's epilogue overlaps the other's MMAs
-  int stages = 8, per_sm = 2;
-  while (stages >= 3 && smem_layout(d, stages).total > SMEM_HALF) --stages;
-  if (stages < 3) {
-    per_sm = 1;
-    stages = 8;
-    while (stages >= 2 && smem_layout(d, stages).total > SMEM_MAX) --stages;
-    if (stages < 2) { set_error("target_decoder_pdf: decoder tables (%d z vectors x %d) do not fit in shared memory", n_z, h1); return -2; }
-  }
+  int stages = MAX_STAGES;
+  const int per_sm = 1;  // the CTA owns the SM's whole TMEM (accumulator + A ring)
+  while (stages >= 2 && smem_layout(d, stages).total > SMEM_MAX) --stages;
+  if (stages < 2) { set_error("target_decoder_pdf: decoder tables (%d z vectors x %d) do not fit in shared memory", n_z, h1); return -2; }
   DecodeArgs a;
   a.packed = (const unsigned char*)packed;
   a.samples = samples;
@@ -509,9 +591,7 @@ extern "C" int klerg_target_decoder_pdf(const void* packed, int32_t s_dim, int32
   a.clamp_lo = clamp_lo;
   a.clamp_hi = clamp_hi;
   a.stages = stages;
-  int cols = 32;
-  while (cols < d.ncols) cols <<= 1;
-  a.tmem_cols = cols;
+  a.tmem_cols = TMEM_COLS;
   const long long tiles = (N + TM - 1) / TM;
   const long long slots = (long long)per_sm * sm_count();
   const int grid = (int)(tiles < slots ? tiles : slots);
