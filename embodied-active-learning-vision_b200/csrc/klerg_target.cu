@@ -30,6 +30,7 @@
 
 #include "klerg_b200.h"
 #include "klerg_common.cuh"
+#include "klerg_pair.cuh"
 
 namespace klerg {
 namespace {
@@ -140,7 +141,7 @@ struct DecodeArgs {
 };
 
 struct SmemLayout {
-  size_t a, b, t1, e, bars, total;
+  size_t a, b, t1, e, e2, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const Dims& d, int stages) {
   SmemLayout s;
@@ -149,6 +150,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Dims& d, int stages) {
   s.b = o;  o += (size_t)stages * KS * b_step_bytes(d);
   s.t1 = o; o = align128(o + sizeof(float) * (size_t)d.nz * d.h1 * d.lp1);
   s.e = o;  o = align128(o + sizeof(float) * (size_t)d.h2 * d.lp);
+  s.e2 = o; o = align128(o + (d.nl == 1 ? sizeof(float) * 2 * (size_t)d.h2 : 0));  // single logvar column: {b2 pair, w3 pair}
   s.bars = o; o += 8 * (3 * MAX_STAGES + 2) + 16;  // full_a full_b empty tmem_full tmem_empty | tmem addr, abort
   s.total = o;
   return s;
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
   unsigned char* sB = smem + sl.b;
   float* s_t1 = (float*)(smem + sl.t1);
   float* s_e = (float*)(smem + sl.e);
+  float* s_e2 = (float*)(smem + sl.e2);
   unsigned long long* full_a = (unsigned long long*)(smem + sl.bars);
   unsigned long long* full_b = full_a + MAX_STAGES;
   unsigned long long* empty = full_b + MAX_STAGES;
@@ -313,6 +316,13 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
     const float4* g2 = (const float4*)(a.packed + off_e(d));
     const int n2 = d.h2 * d.lp / 4;
     for (int i = threadIdx.x; i < n2; i += THREADS) ((float4*)s_e)[i] = __ldg(g2 + i);
+    if (d.nl == 1) {  // columns (j, j+1) -> {b2_j, b2_j+1, w3_j, w3_j+1}: one LDS.128 feeds two packed f32x2 operations
+      const float* ge = (const float*)(a.packed + off_e(d));
+      for (int j = threadIdx.x; j < d.h2; j += THREADS) {
+        s_e2[(j >> 1) * 4 + (j & 1)] = __ldg(ge + (size_t)j * d.lp);
+        s_e2[(j >> 1) * 4 + 2 + (j & 1)] = __ldg(ge + (size_t)j * d.lp + 1);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -420,6 +430,29 @@ __global__ void __launch_bounds__(THREADS, 1) target_decoder_kernel(const Decode
 #pragma unroll
         for (int l = 0; l < LP - 1; ++l) y[l] = 0.f;
       }
+      if (LP == 4 && d.nl == 1) {
+        // single logvar column (the reference's default): packed f32x2 arithmetic, two columns per instruction
+        u64 y2a = pack2(0.f, 0.f), y2b = pack2(0.f, 0.f);
+        for (int c0 = 0; c0 < d.ncols; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(trow + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const float4* e2 = reinterpret_cast<const float4*>(s_e2) + ((hf * d.ncols + c0) >> 1);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t0 = e2[j >> 1], t1 = e2[(j >> 1) + 1];
+            float h0, h1, h2, h3;
+            unpack2(add2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), pack2(t0.x, t0.y)), h0, h1);
+            unpack2(add2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), pack2(t1.x, t1.y)), h2, h3);
+            y2a = fma2(pack2(t0.z, t0.w), pack2(fmaxf(h0, 0.f), fmaxf(h1, 0.f)), y2a);
+            y2b = fma2(pack2(t1.z, t1.w), pack2(fmaxf(h2, 0.f), fmaxf(h3, 0.f)), y2b);
+          }
+        }
+        float s0, s1, s2, s3;
+        unpack2(y2a, s0, s1);
+        unpack2(y2b, s2, s3);
+        y[0] += (s0 + s1) + (s2 + s3);
+      } else
       for (int c0 = 0; c0 < d.ncols; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(trow + (uint32_t)c0, r);
