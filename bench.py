@@ -284,6 +284,7 @@ def target_decoder_block(dev, timed):
                     "roofline": {"bound": "tensor", "achieved": flop_issued / t_kernel / 1e12, "peak": bf16 / 2, "unit": "TFLOP/s",
                                  "frac": flop_issued / t_kernel / 1e12 / (bf16 / 2),
                                  "algorithmic_tflops": flop_alg / t_kernel / 1e12,
+                                 "nominal_peak": 1100.0, "frac_nominal": flop_issued / t_kernel / 1e12 / 1100.0,
                                  "peak_basis": f"tf32 dense = half of {src}; achieved counts the 3 tf32 MMAs of the 3xTF32 "
                                                "split (fp32-accurate result); algorithmic = 2*N*(19*256+256*512+512) fp32 flop"}}
         del smp
