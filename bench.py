@@ -586,14 +586,18 @@ def cuda_arm(args):
         ce, ge = robot.stats["cost_evals"] - c0_, robot.stats["grad_evals"] - g0_
         pairs += (ce + 2 * ge) * H * n_total
         steps_e = args.e2e_steps
-        h2d = n * D * 4 + n * 4 + min(m, m_all) * 8 + (ce + ge) // steps_e * H * D * 4 + 2 * D * 4
+        wrapped = getattr(robot, "_wrapped_target", None)  # VAE-like target: p is computed on the device from the
+        p_bytes = n * 4 if wrapped is None else wrapped._staging.numel() * 4  # model's weights (re-read every step)
+        h2d = n * D * 4 + p_bytes + min(m, m_all) * 8 + (ce + ge) // steps_e * H * D * 4 + 2 * D * 4
         d2h = (ge // steps_e) * (H * 4 + H * D * 4) + (ce // steps_e) * 4 + (H + 1) * 2 * D * 4 + 2 * D * 4
         e2e = {"value": pairs / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "control_torch.klerg.Robot.step(num_target_samples=N, num_traj_samples=M, save_update=True)",
                "steps": steps_e, "ms_per_robot_step": t_e2e / steps_e * 1e3, "evals_per_s": (ce + ge) / t_e2e,
                "evals_per_robot_step": (ce + ge) / steps_e,
                "note": "samples drawn by the host torch RNG (reference order) and copied H2D every step together with the "
-                       "target density values; history (M x N) and spread (M_all x N) passes included"}
+                       + ("target density values" if wrapped is None else
+                          "decoder weights of the VAE-like target (p is evaluated on the device by klerg_target_decoder_pdf)")
+                       + "; history (M x N) and spread (M_all x N) passes included"}
 
     # ---- cpu_baseline: the oracle port on this box's host cores (rank 0, N=1 only) ---------------------
     cpu = None

@@ -5,25 +5,27 @@
 //   p(s)   = amax_l exp( mean_z clamp(decode(latent)[:, l], lo, hi) ),  l < ylogvar_dim
 //
 // The first layer folds the (sample-independent) z part into a bias: h1_k = relu(c_zk + sum_d W1x[k][d] x_d);
-// it is produced by CUDA cores straight into shared memory as the A operand.  The second layer - the only dense
-// contraction of the whole KL-ergodic path, [N,H1] x [H1,H2] - runs on the tensor cores: tcgen05.mma kind::tf32,
-// M = 128 samples per tile, accumulators in TMEM.  The H2 outputs are processed in passes of <= 256 TMEM columns
-// (H2 = 512: two passes, A re-produced per pass - cheap next to the MMAs) so that TWO CTAs share an SM (2 x 256
-// columns, half the shared memory each): while one CTA drains its accumulator the other one's MMAs keep the
-// tensor pipe busy (single CTA with a 512-column accumulator: pipe 65 % active; this layout: see profiles/).  fp32 parity with
-// the reference (1e-4 relative is the bar, ~1e-6 achieved) comes from the 3xTF32 split: every operand is
-// hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), and D += A_lo B_hi + A_hi B_lo + A_hi B_hi.
+// CUDA cores compute it and write it straight into TENSOR MEMORY as the A operand (tcgen05.st).  The second layer -
+// the only dense contraction of the whole KL-ergodic path, [N,H1] x [H1,H2] - runs on the tensor cores:
+// tcgen05.mma kind::tf32 in its TS form (A from TMEM, B = W2 from shared memory), M = 128 samples per tile,
+// fp32 accumulator in TMEM.  TMEM columns [0,256) hold the accumulator, [256,512) a ring of A stages; the H2 outputs
+// are processed in passes of <= 256 columns (H2 = 512: two passes, A re-produced per pass - cheap next to the MMAs).
+// fp32 parity with the reference (1e-4 relative is the bar, ~5e-6 measured) comes from the 3xTF32 split: every
+// operand is hi + lo (W2: round-to-nearest halves, split once per weight refresh; A: hi = top 10 mantissa bits,
+// lo = h - hi, exact) and D += A_lo B_hi + A_hi B_lo + A_hi B_hi.
 // The third layer only needs its first ylogvar_dim rows: a dot product in the TMEM -> register epilogue, fused
 // with bias + ReLU of layer 2, the clamp, the mean over z, exp and amax.
 //
-// Roles inside a CTA (192 threads, two CTAs per SM, persistent over sample tiles):
-//   warps 0-3  thread = sample row: produce the A stages (hi/lo), later drain TMEM lane = row (epilogue)
+// Roles inside a CTA (192 threads, one CTA per SM - it owns the SM's whole TMEM -, persistent over sample tiles):
+//   warps 0-3  thread = sample row = TMEM lane: produce the A stages, later drain the accumulator (epilogue); they
+//              run one stage into the next pass before draining, so the MMA lane always has work queued
 //   warp 4     one lane streams the pre-split W2 stages global -> shared with TMA bulk copies (cp.async.bulk)
 //   warp 5     one lane issues the tcgen05.mma's and commits stage / accumulator barriers
-// Shared-memory operands use the canonical no-swizzle K-major layout (8 rows x 16 B core matrices):
-//   stage = one MMA K-step (8 tf32 = two 16-byte K chunks): [part hi|lo][chunk 0|1][row][16 B]
-//   so a warp of producer rows writes 512 contiguous bytes per store instruction (conflict-free), and
-//   SBO (8-row group stride) = 128 B, LBO (K chunk stride) = rows * 16 B.
+// An operand stage = KS = 4 MMA K-steps (32 of the H1 inputs): 12 MMAs per tcgen05.commit (a commit per K-step costs
+// ~80 clk of tensor-pipe time each, measured), one 64 KB bulk copy, 64 TMEM columns of A; the A and W2 stages share
+// one 3-deep mbarrier ring.  W2 in shared memory uses the canonical no-swizzle K-major layout (8 rows x 16 B core
+// matrices): per K-step [part hi|lo][16-byte K chunk 0|1][row][16 B], SBO (8-row group stride) = 128 B,
+// LBO (K chunk stride) = rows * 16 B.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -141,12 +143,11 @@ struct DecodeArgs {
 };
 
 struct SmemLayout {
-  size_t a, b, t1, e, e2, bars, total;
+  size_t b, t1, e, e2, bars, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(const Dims& d, int stages) {
   SmemLayout s;
   size_t o = 0;
-  s.a = 0;
   s.b = o;  o += (size_t)stages * KS * b_step_bytes(d);
   s.t1 = o; o = align128(o + sizeof(float) * (size_t)d.nz * d.h1 * d.lp1);
   s.e = o;  o = align128(o + sizeof(float) * (size_t)d.h2 * d.lp);
@@ -199,18 +200,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 operands, fp32 accumulate
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// same with the A operand in TMEM (lane = row, one 32-bit column per K element)
+// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 operands, fp32 accumulate; A: lane = row, one 32-bit column per K element
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
