@@ -64,7 +64,10 @@ bool make_dims(int sd, int zd, int nz, int h1, int h2, int nl, Dims& d) {
   if (sd < 1 || sd > 7) { set_error("target decoder: s_dim=%d outside 1..7", sd); return false; }
   if (zd < 0 || nz < 1 || nz > 64) { set_error("target decoder: z_dim=%d / z vectors=%d out of range", zd, nz); return false; }
   if (h1 < 8 || (h1 % 8) || h1 > 1024) { set_error("target decoder: first hidden width %d must be a multiple of 8 in 8..1024", h1); return false; }
-  if (h2 < 32 || (h2 % 32) || h2 > 512) { set_error("target decoder: second hidden width %d must be a multiple of 32 in 32..512 (TMEM columns)", h2); return false; }
+  if (h2 < 32 || (h2 % 32) || h2 > 512 || (h2 > 256 && (h2 % 64))) {
+    set_error("target decoder: second hidden width %d must be a multiple of 32 in 32..256 or of 64 in 320..512 (TMEM accumulator passes)", h2);
+    return false;
+  }
   if (nl < 1 || nl > 15) { set_error("target decoder: ylogvar_dim=%d outside 1..15", nl); return false; }
   d.sd = sd; d.zd = zd; d.nz = nz; d.h1 = h1; d.h2 = h2; d.nl = nl;
   d.lp1 = sd <= 3 ? 4 : 8;

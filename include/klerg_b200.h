@@ -298,8 +298,8 @@ int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t
  * for decode = Linear(z_dim+s_dim, h1) ReLU Linear(h1, h2) ReLU Linear(h2, out)
  * (vae.py:77-84; hidden_dim [512,256] -> h1 = 256, h2 = 512).  n_z = 1 is the
  * default `z_samples` row (vae.py:258-259); n_z > 1 the z buffer (vae.py:253-257,
- * 268-270).  Limits: s_dim 1..7, h1 % 8 == 0 (<= 1024), h2 % 32 == 0 (<= 512),
- * n_logvar 1..15.
+ * 268-270).  Limits: s_dim 1..7, h1 % 8 == 0 (<= 1024), h2 % 32 == 0 up to 256 or
+ * h2 % 64 == 0 up to 512, n_logvar 1..15.
  *
  * klerg_target_decoder_pack folds z into the first-layer bias and splits W2 into
  * tf32 hi/lo operand stages; call it whenever the weights or z change (all

@@ -99,6 +99,8 @@ def test_target_decoder_validation(lib):
     assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 512, 1) > 4 * 256 * 512 * 2
     assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 100, 1) == 0  # second hidden width % 32
     assert "multiple of 32" in err(lib)
+    assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 288, 1) == 0  # two accumulator passes need h2 % 64
+    assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 256, 320, 1) > 0
     assert lib.klerg_target_decoder_packed_bytes(9, 16, 1, 256, 512, 1) == 0
     assert "s_dim" in err(lib)
     assert lib.klerg_target_decoder_packed_bytes(3, 16, 1, 250, 512, 1) == 0

@@ -81,10 +81,11 @@ def test_unsupported_decoder_raises(td):
     model.decode = torch.nn.Sequential(torch.nn.Linear(19, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4))
     with pytest.raises(NotImplementedError):
         td.DeviceTarget(model).pdf_torch(target_samples(case))
-    case2 = dict(TARGET_CASES["default"], hidden=[100, 36])  # h2 = 100 is not a multiple of 32
-    m2 = DecoderModel(case2, torch.zeros(1, case2["zd"]))
-    with pytest.raises(RuntimeError):
-        td.DeviceTarget(m2).pdf_torch(target_samples(case2))
+    for hidden in ([100, 40], [288, 40]):  # h2 = 100: not a multiple of 32; 288: two passes of 144 columns
+        case2 = dict(TARGET_CASES["default"], hidden=hidden)
+        m2 = DecoderModel(case2, torch.zeros(1, case2["zd"]))
+        with pytest.raises(RuntimeError, match="second hidden width"):
+            td.DeviceTarget(m2).pdf_torch(target_samples(case2))
 
 
 def test_robot_step_with_model_target():
@@ -167,3 +168,41 @@ def test_trainer_spread_grade_block(td):
     np.testing.assert_allclose(float(spread), float(ref[0]), rtol=RTOL)
     np.testing.assert_allclose(entropy_dist.cpu().numpy(), ref[3].numpy(), rtol=RTOL)
     np.testing.assert_allclose(float(grade), float(ref[1]), rtol=1e-3)
+
+
+SHAPES = [
+    # sd, zd, hidden (reference order: [h2, h1]), nl, zbuf, n
+    (1, 1, [32, 8], 1, 0, 300),        # smallest widths
+    (7, 3, [512, 1024], 1, 0, 700),    # widest first layer the kernel takes (32 operand stages per pass), 7 conditioning dims
+    (3, 16, [256, 72], 2, 0, 500),     # single accumulator pass, K-steps not a multiple of the stage (9 = 4 + 4 + 1)
+    (2, 5, [320, 40], 3, 4, 260),      # two passes of 160 columns, z buffer of 4
+    (6, 16, [512, 256], 15, 0, 390),   # most logvar columns, wide conditioning
+    (4, 8, [448, 136], 5, 6, 129),     # 224-column passes, z buffer of 6 with the wide tables (ring shrinks to fit)
+    (3, 16, [512, 256], 1, 8, 1000),   # the default decoder with a full z buffer of 8
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "sd%d_z%d_h%dx%d_nl%d_zb%d" % (s[0], s[1], s[2][1], s[2][0], s[3], s[4]))
+def test_decoder_shapes_vs_oracle(td, shape):
+    """Every code path of the kernel that depends on the decoder's shape: one or two accumulator passes, short last
+    operand stage, 4- or 8-wide first-layer rows, 4- or 16-wide epilogue rows, packed single-column epilogue, z buffers."""
+    sd, zd, hidden, nl, zbuf, n = shape
+    case = dict(sd=sd, zd=zd, hidden=hidden, nl=nl, zbuf=zbuf, dx=bool(zbuf), n=n, gain=2.5)
+    g = torch.Generator().manual_seed(sum(hidden) + nl)
+    z = torch.randn(max(zbuf, 1), zd, generator=g)
+    model = DecoderModel(case, z, seed_x=torch.rand(1, sd, generator=g) * 0.2)
+    dev = td.DeviceTarget(model)
+    s = target_samples(case, seed=n)
+    p = dev.pdf_torch(s)
+    dev.check_fault()
+    ref = model.pdf_torch(s)
+    assert float(ref.std()) > 0, "degenerate case: the clamp swallowed everything"
+    np.testing.assert_allclose(p.cpu().numpy(), ref.numpy(), rtol=RTOL, atol=0)
+
+
+def test_tables_too_large_is_refused(td):
+    """A z buffer whose first-layer tables cannot share the SM with one W2 ring raises instead of mis-computing."""
+    case = dict(sd=6, zd=4, hidden=[512, 1024], nl=1, zbuf=8, dx=False, n=64, gain=1.0)
+    model = DecoderModel(case, torch.zeros(8, 4))
+    with pytest.raises(RuntimeError, match="do not fit"):
+        td.DeviceTarget(model).pdf_torch(target_samples(case))
