@@ -475,6 +475,9 @@ class Robot(object):
 
             if self.plot_data is not None:
                 self.update_plots(ctx, accepted, samples, samples_dev, hist_dev, p, temp)
+            wrapped = getattr(self, "_wrapped_target", None)
+            if wrapped is not None:
+                wrapped.check_fault()  # a timed-out wait inside the decoder kernel must not pass silently
 
     # ------------------------------------------------------------------ plots (klerg.py:602-682)
     @torch.no_grad()
