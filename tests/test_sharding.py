@@ -71,3 +71,16 @@ def test_sharded_fused_evals_match_single_gpu(name, n):
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mp", "sharded_parity.py"), name, str(n)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "SHARDED_PARITY OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_sharded_robot_step_with_model_target():
+    """2 ranks: Robot.step() with a VAE-like target (tensor-core decoder on each rank's sample slice) against the
+    single-GPU controller."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29900 + os.getpid() % 100
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mp", "sharded_robot_step.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SHARDED_ROBOT OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
