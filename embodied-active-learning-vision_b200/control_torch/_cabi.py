@@ -130,13 +130,15 @@ SIGNATURES = {
                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "klerg_eval_gradient_targets": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _I64, _P, _F, _FP, _F,
                                     _FP, _FP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "klerg_kl_gradient_targets_scratch_bytes": [_I64, _I64],
+    "klerg_kl_gradient_targets": [_KS, _P, _I64, _P, _I64, _I64, _P, _P, C.c_int, _P, _I64, _I64, _F, _P, _P, _P, _P, _P],
     "klerg_target_decoder_packed_bytes": [_I32, _I32, _I32, _I32, _I32, _I32],
     "klerg_target_decoder_pack": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "klerg_target_decoder_pdf": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _F, _F, _P, _P, _P],
     "klerg_eval_costs": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P,
                          _P, _P],
 }
-_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
+_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_kl_gradient_targets_scratch_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
              "klerg_launch_count": C.c_longlong}
 
 

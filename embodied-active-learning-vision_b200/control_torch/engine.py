@@ -197,6 +197,36 @@ def kl_gradient_fused(spec, states, packed, n, v, totals_w, p, floor=FLOOR):
     return grad_part, kl_part
 
 
+_targets_scratch = {}
+
+
+def kl_gradient_targets(spec, states, packed, n, v, totals_w, P, floor=FLOOR):
+    """K belief targets, psi shared (tensor-core contraction): -> (grad_parts [K,H,D] float64, kl_parts [K,2] float64)
+    for this rank's samples.  P [K, ld] rows padded to the sample stride."""
+    lib = cabi.load()
+    states = states.contiguous()
+    H, K = states.shape[0], P.shape[0]
+    dev = packed.device
+    nbytes = lib.klerg_kl_gradient_targets_scratch_bytes(H, K)
+    key = (dev.index, cabi.raw_stream())
+    scr = _targets_scratch.get(key)
+    if scr is None or scr[0].numel() < nbytes:
+        scr = _targets_scratch[key] = (torch.empty(nbytes, dtype=torch.uint8, device=dev),
+                                       torch.zeros(1, dtype=torch.int32, device=dev))
+    grad_parts = torch.empty((K, H, spec.D), dtype=torch.float64, device=dev)
+    kl_parts = torch.empty((K, 2), dtype=torch.float64, device=dev)
+    cabi.check(lib.klerg_kl_gradient_targets(
+        C.byref(spec), cabi.ptr(states), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(v), cabi.ptr(totals_w),
+        totals_w.shape[0], cabi.ptr(P), K, P.shape[1], float(floor), cabi.ptr(grad_parts), cabi.ptr(kl_parts),
+        cabi.ptr(scr[0]), cabi.ptr(scr[1]), cabi.stream_ptr()), "klerg_kl_gradient_targets")
+    return grad_parts, kl_parts
+
+
+def targets_gradient_fault():
+    """True if any klerg_kl_gradient_targets launch reported a timed-out in-kernel wait (one small D2H read each)."""
+    return any(int(f.item()) != 0 for _, f in _targets_scratch.values())
+
+
 def kl_cost(v, n, totals_w, p, p_stats, barrier_sum, group=SINGLE, floor=FLOOR):
     """KL(p||q) + barrier for G candidates: v [G, ld] -> cost [G]."""
     G = v.shape[0]

@@ -1,0 +1,459 @@
+// Shared-psi KL gradient for K belief targets over one workspace / trajectory (BASELINE config 5, fingerprint test mode).
+//
+// kldiv_grad_vec (control_torch/klerg_utils.py:12-15,31-36) for all H planner states and K targets p_k:
+//   dgdx_k[t][d] = sum_i w_ki * (-(x_td - s_id)/|std_d|) * psi(x_t, s_i),   w_ki = p_ki / q_i  (klerg.py:436)
+// psi does not depend on the target, so with K targets the sum over the samples is a contraction
+//   S[(k,d')][t] = sum_i V[(k,d')][i] * psi[t][i],  V[(k,d)][i] = w_ki (s'_id - c_d),  V[(k,D)][i] = w_ki
+//   dgdx_k[t][d] = gfac_d * ((x'_td - c_d) S[(k,D)][t] - S[(k,d)][t])
+// (primes: coordinates pre-scaled so that psi = 2^-|x'-s'|^2; c = centre of the trajectory, which keeps the
+// cancellation in the last line small) - and it runs on the tensor cores: tcgen05.mma kind::tf32, M = 128 rows (k,d'),
+// N = H (padded to 32 or 64) columns, K-dimension = samples, 8 per instruction, 3xTF32 split for fp32-grade sums,
+// one fp32 accumulator in TMEM for the CTA's whole sample range.  The pair kernels recompute psi per target
+// (K * (3D+1) FP32 lane-ops per state-sample pair); here psi costs one forward-style evaluation per pair.
+//
+// Roles inside a CTA (320 threads, one CTA per SM, a contiguous range of samples per CTA, 32 samples per stage):
+//   warp 8     stager: thread = sample: importance-ratio factor maxc/c_i, centred scaled sample, the K target values
+//              -> shared memory; per-target KL terms (sum p (log p - log c), sum c) ride along
+//   warps 0-3  thread = row (k,d') = TMEM lane: V for the stage's 32 samples (hi/lo tf32 halves) -> TMEM (A operand)
+//   warps 4-7  thread = (state t, 16 of the 32 samples): psi -> shared memory (B operand, no-swizzle K-major)
+//   warp 9     one lane issues 12 MMAs per stage and commits
+// At the end warps 0-3 drain the accumulator into a per-CTA partial; a small second kernel adds the partials in CTA
+// order (doubles) and applies the last line above.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "klerg_b200.h"
+#include "klerg_common.cuh"
+#include "klerg_pair.cuh"
+#include "klerg_tc.cuh"
+
+namespace klerg {
+namespace {
+using namespace tc;
+
+constexpr int TG_THREADS = 320;
+constexpr int TG_KS = 4;                 // MMA K-steps (8 samples each) per stage
+constexpr int TG_SPS = 8 * TG_KS;        // samples per stage
+constexpr int TG_STAGES = 4;
+constexpr int TG_ACOL0 = 256;            // TMEM: accumulator columns [0, Hp), A ring [256, 256 + 4*64)
+constexpr int TG_MAXK = 32;
+
+struct TGArgs {
+  KernelDev k;
+  const float* states;  // [H][S] planner states (pre-step trajectory)
+  int H, Hp;            // Hp = H padded to 32 or 64 (MMA N, accumulator columns)
+  const float* packed;  // [D][ld] pre-scaled samples
+  long long N, ld;
+  const float* v;       // q_base + q_iter
+  const double* totals; // [world][1][2] {sum v, max v} per rank
+  int world;
+  float floor;
+  const float* P;       // [K][p_stride]
+  int K, R;             // R = K*(D+1) rows in use
+  long long p_stride;
+  float* part;          // [grid][128][Hp]
+  float* klpart;        // [grid][K][2]
+  double* grad_out;     // [K][H][D]
+  double* kl_out;       // [K][2]
+  unsigned* fault;
+  long long chunk;      // samples per CTA (multiple of TG_SPS)
+};
+
+__host__ __device__ inline size_t tg_slot_floats(int D, int K) { return (size_t)(D + 1 + K) * TG_SPS; }
+__host__ __device__ inline size_t tg_bstage_bytes(int Hp) { return (size_t)TG_KS * 64 * Hp; }
+struct TGSmem {
+  size_t b, slot, xc, bars, total;
+};
+__host__ __device__ inline TGSmem tg_smem(int D, int K, int Hp) {
+  TGSmem s;
+  size_t o = 0;
+  s.b = o;    o += TG_STAGES * tg_bstage_bytes(Hp);
+  s.slot = o; o += TG_STAGES * sizeof(float) * tg_slot_floats(D, K);
+  s.xc = o;   o += sizeof(float) * (64 * KLERG_MAX_D + KLERG_MAX_D);  // centred scaled states [64][D], centre [D]
+  o = (o + 127) & ~(size_t)127;
+  s.bars = o; o += 8 * (4 * TG_STAGES + 1) + 16;
+  s.total = o;
+  return s;
+}
+
+template <int D>
+__global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const TGArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TGSmem sl = tg_smem(D, a.K, a.Hp);
+  unsigned char* sB = smem + sl.b;
+  float* s_slot = (float*)(smem + sl.slot);
+  float* s_xc = (float*)(smem + sl.xc);   // [64][D]
+  float* s_c = s_xc + 64 * D;             // [D]
+  unsigned long long* full_s = (unsigned long long*)(smem + sl.bars);
+  unsigned long long* full_a = full_s + TG_STAGES;
+  unsigned long long* full_b = full_a + TG_STAGES;
+  unsigned long long* empty = full_b + TG_STAGES;
+  unsigned long long* acc_full = empty + TG_STAGES;
+  uint32_t* s_tmem = (uint32_t*)(acc_full + 1);
+  volatile unsigned* s_abort = (volatile unsigned*)(s_tmem + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = a.H, Hp = a.Hp, K = a.K;
+  const size_t slot_f = tg_slot_floats(D, K);
+  const unsigned bstage = (unsigned)tg_bstage_bytes(Hp), bstep = 64u * (unsigned)Hp;
+  const long long lo = (long long)blockIdx.x * a.chunk;
+  long long hi = lo + a.chunk;
+  if (hi > a.N) hi = a.N;
+  const int n_st = hi > lo ? (int)((hi - lo + TG_SPS - 1) / TG_SPS) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TG_STAGES; ++s) {
+      bar_init(&full_s[s], 32);
+      bar_init(&full_a[s], 128);
+      bar_init(&full_b[s], 128);
+      bar_init(&empty[s], 1);
+    }
+    bar_init(acc_full, 1);
+    *s_abort = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // scaled states, then their centre (same arithmetic in every CTA -> bit-identical)
+  for (int e = threadIdx.x; e < 64 * D; e += TG_THREADS) {
+    const int t = e / D, d = e - t * D;
+    s_xc[e] = t < H ? a.states[(size_t)t * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float mn = s_xc[threadIdx.x], mx = mn;
+    for (int t = 1; t < H; ++t) {
+      mn = fminf(mn, s_xc[t * D + threadIdx.x]);
+      mx = fmaxf(mx, s_xc[t * D + threadIdx.x]);
+    }
+    s_c[threadIdx.x] = 0.5f * (mn + mx);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * D; e += TG_THREADS) {
+    const int t = e / D, d = e - t * D;
+    if (t < H) s_xc[e] -= s_c[d];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  if (warp == 8) {
+    // ================= stager: one sample per thread =================
+    double vsum, vmax;
+    gather_totals(a.totals, a.world, 1, 0, vsum, vmax);
+    const float vsum_f = (float)vsum;  // divide by the fp32 sum like the reference
+    const float maxc_f = (float)fmax(vmax / vsum, (double)a.floor);
+    float c_d[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) c_d[d] = s_c[d];
+    float kl_a[TG_MAXK];
+#pragma unroll
+    for (int k = 0; k < TG_MAXK; ++k) kl_a[k] = 0.f;
+    float kl_c = 0.f;
+    int s = 0;
+    unsigned ph = 0;
+    for (int st = 0; st < n_st; ++st) {
+      bar_wait(&empty[s], ph ^ 1u, s_abort);
+      float* slot = s_slot + (size_t)s * slot_f;
+      const long long i = lo + (long long)st * TG_SPS + lane;
+      const bool valid = i < hi;
+      float r = 0.f, logc = 0.f;
+      if (valid) {
+        const float c = fmaxf(a.v[i] / vsum_f, a.floor);
+        r = maxc_f / c;  // p * r = p / q with q = c / max c  (klerg.py:436)
+        logc = logf(c);
+        kl_c += c;
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) slot[d * TG_SPS + lane] = valid ? a.packed[(size_t)d * a.ld + i] - c_d[d] : 0.f;
+      slot[D * TG_SPS + lane] = r;
+#pragma unroll
+      for (int k = 0; k < TG_MAXK; ++k) {
+        if (k < K) {
+          const float p = valid ? a.P[(size_t)k * a.p_stride + i] : 0.f;
+          slot[(D + 1 + k) * TG_SPS + lane] = p;
+          if (valid) kl_a[k] += p * (logf(p) - logc);
+        }
+      }
+      bar_arrive(&full_s[s]);
+      if (++s == TG_STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    kl_c = warp_sum_f(kl_c);
+#pragma unroll
+    for (int k = 0; k < TG_MAXK; ++k) {
+      if (k < K) {
+        const float sa = warp_sum_f(kl_a[k]);
+        if (lane == 0) {
+          a.klpart[((size_t)blockIdx.x * K + k) * 2 + 0] = sa;
+          a.klpart[((size_t)blockIdx.x * K + k) * 2 + 1] = kl_c;
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ================= V producers (A operand in TMEM), later the epilogue =================
+    const int row = threadIdx.x;
+    const bool active = row < a.R;
+    const int k = active ? row / (D + 1) : 0, dd = active ? row - k * (D + 1) : D;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    int s = 0, pending = -1;
+    unsigned ph = 0;
+    for (int st = 0; st < n_st; ++st) {
+      bar_wait(&full_s[s], ph, s_abort);
+      tc_fence_after();
+      const float* slot = s_slot + (size_t)s * slot_f;
+      const float4* rr = reinterpret_cast<const float4*>(slot + D * TG_SPS);
+      const float4* pp = reinterpret_cast<const float4*>(slot + (D + 1 + k) * TG_SPS);
+      const float4* ss = reinterpret_cast<const float4*>(slot + (dd < D ? dd : 0) * TG_SPS);
+      const uint32_t acol = trow + (uint32_t)(TG_ACOL0 + s * (16 * TG_KS));
+#pragma unroll
+      for (int kk = 0; kk < TG_KS; ++kk) {
+        uint32_t hiw[8], low[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 r4 = rr[kk * 2 + h], p4 = pp[kk * 2 + h], s4 = ss[kk * 2 + h];
+          const float w[4] = {p4.x * r4.x, p4.y * r4.y, p4.z * r4.z, p4.w * r4.w};
+          const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float val = active ? (dd < D ? w[q] * sv[q] : w[q]) : 0.f;
+            hiw[h * 4 + q] = __float_as_uint(val) & 0xFFFFE000u;  // tf32 split by truncation, lo exact in fp32
+            low[h * 4 + q] = __float_as_uint(val - __uint_as_float(hiw[h * 4 + q]));
+          }
+        }
+        if (kk == 0 && pending >= 0) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          bar_arrive(&full_a[pending]);
+        }
+        tmem_st8(acol + kk * 16, hiw);
+        tmem_st8(acol + kk * 16 + 8, low);
+      }
+      pending = s;
+      if (++s == TG_STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    if (pending >= 0) {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      bar_arrive(&full_a[pending]);
+    }
+    // ---- epilogue: this row of the accumulator -> the CTA's partial ----
+    float* out = a.part + ((size_t)blockIdx.x * 128 + row) * Hp;
+    if (n_st > 0) {
+      bar_wait(acc_full, 0u, s_abort);
+      tc_fence_after();
+      for (int c0 = 0; c0 < Hp; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(trow + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                    __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+      }
+    } else if (active) {
+      for (int j = 0; j < Hp; ++j) out[j] = 0.f;
+    }
+  } else if (warp < 8) {
+    // ================= psi producers (B operand in shared memory) =================
+    const int tid2 = threadIdx.x - 128;
+    const int t = tid2 & 63, half = tid2 >> 6;  // state, which 16 of the stage's 32 samples
+    const bool row_ok = t < Hp, live = t < H;
+    float x[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) x[d] = s_xc[t * D + d];
+    int s = 0;
+    unsigned ph = 0;
+    for (int st = 0; st < n_st; ++st) {
+      bar_wait(&full_s[s], ph, s_abort);
+      const float* slot = s_slot + (size_t)s * slot_f;
+      unsigned char* bst = sB + (size_t)s * bstage;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int kk = half * 2 + e;
+        uint32_t hiw[8], low[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float e2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            const float4 s4 = *reinterpret_cast<const float4*>(slot + d * TG_SPS + kk * 8 + h * 4);
+            const float df0 = x[d] - s4.x, df1 = x[d] - s4.y, df2 = x[d] - s4.z, df3 = x[d] - s4.w;
+            e2[0] = fmaf(df0, df0, e2[0]);
+            e2[1] = fmaf(df1, df1, e2[1]);
+            e2[2] = fmaf(df2, df2, e2[2]);
+            e2[3] = fmaf(df3, df3, e2[3]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float psi = live ? ex2_neg(e2[q]) : 0.f;
+            hiw[h * 4 + q] = __float_as_uint(psi) & 0xFFFFE000u;
+            low[h * 4 + q] = __float_as_uint(psi - __uint_as_float(hiw[h * 4 + q]));
+          }
+        }
+        if (row_ok) {
+          // K-step block: [hi|lo][16-byte sample chunk 0|1][t][16 B]
+          unsigned char* base = bst + (size_t)kk * bstep + (size_t)t * 16;
+          *reinterpret_cast<uint4*>(base) = make_uint4(hiw[0], hiw[1], hiw[2], hiw[3]);
+          *reinterpret_cast<uint4*>(base + 16 * Hp) = make_uint4(hiw[4], hiw[5], hiw[6], hiw[7]);
+          *reinterpret_cast<uint4*>(base + 32 * Hp) = make_uint4(low[0], low[1], low[2], low[3]);
+          *reinterpret_cast<uint4*>(base + 48 * Hp) = make_uint4(low[4], low[5], low[6], low[7]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bar_arrive(&full_b[s]);
+      if (++s == TG_STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  } else {
+    // ================= MMA issue =================
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_tf32(128, Hp);
+      const uint32_t b_lbo = (uint32_t)Hp * 16, b_sbo = 128;
+      int s = 0;
+      unsigned ph = 0;
+      for (int st = 0; st < n_st; ++st) {
+        bar_wait(&full_a[s], ph, s_abort);
+        bar_wait(&full_b[s], ph, s_abort);
+        tc_fence_after();
+        const uint32_t a0 = tmem + (uint32_t)(TG_ACOL0 + s * (16 * TG_KS));
+        const uint32_t b0 = smem_addr(sB + (size_t)s * bstage);
+#pragma unroll
+        for (int kk = 0; kk < TG_KS; ++kk) {
+          const uint32_t a_hi = a0 + kk * 16, a_lo = a_hi + 8;
+          const uint32_t b_hi = b0 + kk * bstep, b_lo = b_hi + 32u * (uint32_t)Hp;
+          const uint64_t db_hi = smem_desc(b_hi, b_lbo, b_sbo), db_lo = smem_desc(b_lo, b_lbo, b_sbo);
+          tc_mma_tf32_ts(tmem, a_lo, db_hi, idesc, (st | kk) ? 1u : 0u);
+          tc_mma_tf32_ts(tmem, a_hi, db_lo, idesc, 1u);
+          tc_mma_tf32_ts(tmem, a_hi, db_hi, idesc, 1u);
+        }
+        tc_commit(&empty[s]);
+        if (++s == TG_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      if (n_st > 0) tc_commit(acc_full);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && *s_abort && a.fault) atomicExch(a.fault, 1u);
+  if (warp == 9) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// Partials -> grad_out[K][H][D] (doubles, the layout klerg_adjoint takes per target) and kl_out[K][2].
+template <int D>
+__global__ void targets_reduce_kernel(const TGArgs a, int nblk) {
+  __shared__ float s_x[64 * D], s_c[D];
+  for (int e = threadIdx.x; e < 64 * D; e += blockDim.x) {
+    const int t = e / D, d = e - t * D;
+    s_x[e] = t < a.H ? a.states[(size_t)t * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float mn = s_x[threadIdx.x], mx = mn;
+    for (int t = 1; t < a.H; ++t) {
+      mn = fminf(mn, s_x[t * D + threadIdx.x]);
+      mx = fmaxf(mx, s_x[t * D + threadIdx.x]);
+    }
+    s_c[threadIdx.x] = 0.5f * (mn + mx);
+  }
+  __syncthreads();
+  const int total = a.K * a.H * D;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int d = e % D, t = (e / D) % a.H, k = e / (D * a.H);
+    double sd = 0.0, s0 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      const float* p = a.part + ((size_t)b * 128 + (size_t)k * (D + 1)) * a.Hp + t;
+      sd += (double)__ldcg(p + (size_t)d * a.Hp);
+      s0 += (double)__ldcg(p + (size_t)D * a.Hp);
+    }
+    const double xc = (double)(s_x[t * D + d] - s_c[d]);
+    a.grad_out[e] = (double)a.k.gfac[d] * (xc * s0 - sd);
+  }
+  if (a.kl_out)
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.K * 2; e += gridDim.x * blockDim.x) {
+      double acc = 0.0;
+      for (int b = 0; b < nblk; ++b) acc += (double)__ldcg(a.klpart + (size_t)b * a.K * 2 + e);
+      a.kl_out[e] = acc;
+    }
+}
+
+template <int D>
+int launch_targets(TGArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  const TGSmem sl = tg_smem(D, a.K, a.Hp);
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(targets_gradient_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_error("kl_gradient_targets: smem opt-in failed: %s", cudaGetErrorString(e)); return -4; }
+    configured = true;
+  }
+  const int grid = sm_count();
+  long long chunk = (a.N + grid - 1) / grid;
+  chunk = (chunk + TG_SPS - 1) / TG_SPS * TG_SPS;
+  if (chunk < TG_SPS) chunk = TG_SPS;
+  a.chunk = chunk;
+  targets_gradient_kernel<D><<<grid, TG_THREADS, sl.total, st>>>(a);
+  int rc = check_launch("targets_gradient_kernel");
+  if (rc) return rc;
+  targets_reduce_kernel<D><<<8, 256, 0, st>>>(a, grid);
+  return check_launch("targets_reduce_kernel");
+}
+
+}  // namespace
+}  // namespace klerg
+
+using namespace klerg;
+
+extern "C" size_t klerg_kl_gradient_targets_scratch_bytes(int64_t H, int64_t K) {
+  const size_t Hp = H <= 32 ? 32 : 64;
+  return (size_t)sm_count() * (128 * Hp + (size_t)K * 2) * sizeof(float);
+}
+
+extern "C" int klerg_kl_gradient_targets(const klerg_kernel_spec* k, const float* states, int64_t H,
+                                         const float* packed, int64_t N, int64_t ld, const float* v,
+                                         const double* totals, int world, const float* P, int64_t K,
+                                         int64_t p_stride, float floor, double* grad_part, double* kl_part,
+                                         void* scratch, uint32_t* fault, void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (H < 1 || H > 64) { set_error("kl_gradient_targets: H must be in 1..64 (accumulator columns of this kernel)"); return -2; }
+  if (K < 1 || K > TG_MAXK || K * (kd.D + 1) > 128) { set_error("kl_gradient_targets: K*(D+1) must be <= 128 rows (K <= 32)"); return -2; }
+  if (N < 0 || ld < N || (ld & 3) || p_stride < N) { set_error("kl_gradient_targets: bad sizes"); return -1; }
+  if (!states || !packed || !v || !totals || !P || !grad_part || !scratch || world < 1) { set_error("kl_gradient_targets: null pointer"); return -1; }
+  TGArgs a{};
+  a.k = kd; a.states = states; a.H = (int)H; a.Hp = H <= 32 ? 32 : 64;
+  a.packed = packed; a.N = N; a.ld = ld; a.v = v; a.totals = totals; a.world = world; a.floor = floor;
+  a.P = P; a.K = (int)K; a.R = (int)K * (kd.D + 1); a.p_stride = p_stride;
+  a.part = (float*)scratch;
+  a.klpart = a.part + (size_t)sm_count() * 128 * a.Hp;
+  a.grad_out = grad_part; a.kl_out = kl_part; a.fault = fault;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (kd.D) {
+    case 1: return launch_targets<1>(a, st);
+    case 2: return launch_targets<2>(a, st);
+    case 3: return launch_targets<3>(a, st);
+    case 4: return launch_targets<4>(a, st);
+    case 5: return launch_targets<5>(a, st);
+    case 6: return launch_targets<6>(a, st);
+    default: set_error("kl_gradient_targets: D=%d not instantiated (1..6)", kd.D); return -2;
+  }
+}

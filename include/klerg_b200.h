@@ -289,6 +289,20 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
 int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t M, float* out,
                       void* stream);
 
+/* ---- a4 for K belief targets: shared-psi contraction on the tensor cores ---- */
+
+/* kldiv_grad_vec (klerg_utils.py:12-15,31-36) for all H states and K targets p_k over one workspace and one
+ * trajectory (BASELINE config 5): same inputs and outputs as klerg_kl_gradient_fused, per target -
+ *   grad_part[k][H][D] (doubles, this rank's partial), kl_part[k][2] = {sum_i p_ki (log p_ki - log c_i), sum_i c_i}
+ * - but psi(x_t, s_i) is evaluated once per state-sample pair and the sum over the samples runs as a tf32 tensor-core
+ * contraction (3xTF32 split, fp32 accumulate).  Limits: H <= 64, K <= 32, K*(D+1) <= 128.  `scratch`:
+ * klerg_kl_gradient_targets_scratch_bytes(H, K) bytes; `fault` (may be NULL) is set to 1 if an in-kernel wait timed out. */
+size_t klerg_kl_gradient_targets_scratch_bytes(int64_t H, int64_t K);
+int klerg_kl_gradient_targets(const klerg_kernel_spec* k, const float* states, int64_t H, const float* packed,
+                              int64_t N, int64_t ld, const float* v, const double* totals, int world,
+                              const float* P, int64_t K, int64_t p_stride, float floor, double* grad_part,
+                              double* kl_part, void* scratch, uint32_t* fault, void* stream);
+
 /* ---- target density of the VAE sensor model -------------- */
 
 /* VAE.pdf_torch (franka_test/scripts/vae/vae.py:244-275), the `target_dist`

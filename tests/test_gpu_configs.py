@@ -115,3 +115,35 @@ def test_config5_belief_targets():
         du, dj = oracle_grad(s["oracle"], s["samples"], P[k], s["q_base"], U[0])
         close(grads["du"][k], du, rtol=RTOL, atol_frac=5e-5, what=f"target {k} du")
         close(grads["djdlam"][k], dj, rtol=RTOL, atol_frac=5e-5, what=f"target {k} djdlam")
+
+
+@pytest.mark.parametrize("states,H,K,n", [("xyz", 50, 16, 40_000), ("xy", 20, 3, 5_003), ("xyzrpw", 33, 18, 9_000), ("xyz", 64, 32, 700)])
+def test_shared_psi_targets_gradient_vs_per_target_kernel(states, H, K, n):
+    """klerg_kl_gradient_targets (psi once per pair, tensor-core contraction over the samples) against the per-target
+    FP32 kernel klerg_kl_gradient_fused on the same inputs: gradient partials and KL terms of every target."""
+    from control_torch import _cabi as cabi
+    from control_torch import engine
+    D = len(states)
+    g = torch.Generator().manual_seed(H * K + n)
+    lims = torch.tensor([wl.LIMS[c] for c in states])
+    lo, hi = lims[:, 0] * 1.15, lims[:, 1] * 1.15
+    samples = (lo + torch.rand(n, D, generator=g) * (hi - lo)).cuda()
+    std = wl.std_from_ratio([wl.LIMS[c] for c in states], n)
+    spec = cabi.kernel_spec(D, 2 * D, list(range(D)), [std] * D, 1.0)
+    packed = engine.pack_samples(spec, samples)
+    # a wandering trajectory inside the workspace, zero velocities
+    mid, half = lims.mean(1), (lims[:, 1] - lims[:, 0]) / 2
+    walk = torch.cumsum(torch.randn(H, D, generator=g) * 0.06, 0).clamp(-0.9, 0.9)
+    traj = torch.hstack([mid + half * walk, torch.zeros(H, D)]).float().cuda().contiguous()
+    q_base = (torch.rand(n, generator=g) * 0.5).cuda()
+    v, totals = engine.footprint(spec, 0, traj, packed, n, add_in=q_base)
+    totals_w = totals.unsqueeze(0) if totals.dim() == 2 else totals
+    P = torch.zeros((K, packed.shape[1]), device="cuda")
+    for k in range(K):
+        P[k, :n] = wl.make_target("gmm", [wl.LIMS[c] for c in states], seed=40 + k, device="cuda").pdf_torch(samples)
+    gp, kl = engine.kl_gradient_targets(spec, traj, packed, n, v[0], totals_w, P)
+    assert not engine.targets_gradient_fault()
+    for k in range(K):
+        gref, klref = engine.kl_gradient_fused(spec, traj, packed, n, v[0], totals_w, P[k, :n].contiguous())
+        close(gp[k], gref, rtol=RTOL, atol_frac=5e-5, what=f"target {k} gradient partial")
+        close(kl[k], klref, rtol=RTOL, what=f"target {k} KL terms")
