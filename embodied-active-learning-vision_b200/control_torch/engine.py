@@ -331,6 +331,23 @@ def adjoint(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl
     return dgdx, du, dj, ustar
 
 
+def adjoint_targets(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl_hi):
+    """grad_parts [K,world,H,D] float64 -> dgdx [K,H,S], du [K,H,A], djdlam [K,H], u_star [K,H,A] (one launch)."""
+    K, world, H, D = grad_parts.shape
+    dev = grad_parts.device
+    S, A = dyn.S, dyn.A
+    dgdx = torch.empty((K, H, S), dtype=torch.float32, device=dev)
+    du = torch.empty((K, H, A), dtype=torch.float32, device=dev)
+    dj = torch.empty((K, H), dtype=torch.float32, device=dev)
+    ustar = torch.empty((K, H, A), dtype=torch.float32, device=dev)
+    cabi.check(cabi.load().klerg_adjoint_targets(
+        C.byref(dyn), C.byref(spec), H, K, cabi.ptr(grad_parts.contiguous()), world, cabi.ptr(dbarr.contiguous()),
+        cabi.ptr(P), cabi.ptr(traj.contiguous()), cabi.ptr(u.contiguous()), cabi.farr(rinv), float(alpha),
+        cabi.farr(ctrl_lo), cabi.farr(ctrl_hi), cabi.ptr(dgdx), cabi.ptr(du), cabi.ptr(dj), cabi.ptr(ustar),
+        cabi.stream_ptr()), "klerg_adjoint_targets")
+    return dgdx, du, dj, ustar
+
+
 class EvalBuffers:
     """Caller-owned outputs/scratch of the fused evals for one (H, S, A, ld) shape.
 

@@ -170,6 +170,8 @@ class PlannerContext:
         (up to 32 targets per launch)."""
         K = self.P.shape[0]
         u = u.reshape(self.H, -1).contiguous()
+        if self.targets_path == "tensor" or (self.targets_path == "auto" and self._tensor_targets_ok(K)):
+            return self._gradient_targets_tensor(u)
         if not self.fused:
             saved, acc = (self.p, self.p_stats), {k: [] for k in ("du", "djdlam", "u_star", "dgdx")}
             try:
@@ -192,6 +194,38 @@ class PlannerContext:
         self.evals["fwd_pairs"] += self.H * self.n * len(outs)
         self.evals["grad_pairs"] += self.H * self.n * K
         return {k: torch.cat([o[k] for o in outs]) for k in ("du", "djdlam", "u_star", "dgdx")}
+
+    # shared-psi path: psi once per state-sample pair, the sum over the samples as a tensor-core contraction
+    targets_path = "fused"  # "auto" | "fused" | "tensor"
+    TENSOR_MIN_TARGETS = 4  # below this the per-target pair pass inside the fused launch is at least as fast
+
+    def _tensor_targets_ok(self, K):
+        return self.group.world == 1 and self.H <= 64 and K >= self.TENSOR_MIN_TARGETS
+
+    def _gradient_targets_tensor(self, u):
+        """rollout -> forward pass (q_base + q_iter, totals) -> klerg_kl_gradient_targets -> one adjoint launch for all
+        targets.  Single rank, H <= 64, K*(D+1) <= 128 per launch (larger K is split)."""
+        if self.group.world != 1 or self.H > 64:
+            raise RuntimeError("the tensor-core targets path needs a single rank and H <= 64")
+        K = self.P.shape[0]
+        kmax = min(32, 128 // (self.spec.D + 1))
+        ro = engine.rollout(self.dyn, self.bar, self.x0, u, R0=self.R0, want_lin=True)
+        traj = ro["traj"][0]
+        pre = traj[: self.H]
+        v, totals = engine.footprint(self.spec, 0, pre, self.packed, self.n, add_in=self.q_base)
+        totals_w = totals.unsqueeze(0)
+        Pl = ro["P"][0] if ro["P"] is not None else None
+        outs = []
+        for k0 in range(0, K, kmax):
+            gp, _ = engine.kl_gradient_targets(self.spec, pre, self.packed, self.n, v[0], totals_w,
+                                               self.P[k0: k0 + kmax], self.floor)
+            outs.append(engine.adjoint_targets(self.dyn, self.spec, gp.unsqueeze(1), ro["dbarr"][0], Pl, traj, u, self.rinv,
+                                               self.alpha, self.ctrl_lo, self.ctrl_hi))
+        self.evals["grad"] += K
+        self.evals["fwd_pairs"] += self.H * self.n
+        self.evals["grad_pairs"] += self.H * self.n  # psi is evaluated once for all targets
+        dgdx, du, dj, ustar = (torch.cat([o[i] for o in outs]) for i in range(4))
+        return dict(du=du, djdlam=dj, u_star=ustar, dgdx=dgdx)
 
     def q_from(self, v, totals_w):
         """renormalize(q_base + q_iter) given the forward output (for plot_data)."""

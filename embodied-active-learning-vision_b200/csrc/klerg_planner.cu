@@ -330,9 +330,20 @@ struct AdjArgs {
   float* du;
   float* djdlam;
   float* u_star;
+  int64_t gp_stride;  // doubles between the gradient blocks of consecutive targets (one CTA per target)
 };
 
-__global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a) {
+__global__ void __launch_bounds__(256) adjoint_kernel(const AdjArgs a0) {
+  // one CTA per belief target: same trajectory / linearisation / controls, its own gradient and outputs
+  AdjArgs a = a0;
+  {
+    const int64_t kt = blockIdx.x;
+    a.grad_part += kt * a.gp_stride;
+    a.dgdx += kt * a.H * a.d.S;
+    a.du += kt * a.H * a.d.A;
+    a.djdlam += kt * a.H;
+    a.u_star += kt * a.H * a.d.A;
+  }
   extern __shared__ float sh[];  // g[H][S] | P[H][A*A] (optional) | traj[H][S] (SPEED) | u[H][A] | scratch
   const int S = a.d.S, A = a.d.A, D = a.k.D;
   const int64_t H = a.H;
@@ -643,16 +654,16 @@ extern "C" int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x,
   return check_launch("barrier_eval_kernel");
 }
 
-extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H,
-                             const double* grad_part, int world, const float* dbarr, const float* P,
-                             const float* traj, const float* u, const float* Rinv_diag, float alpha,
-                             const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
-                             float* u_star, void* stream) {
+static int launch_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H, const double* grad_part,
+                          int world, int64_t K, int64_t gp_stride, const float* dbarr, const float* P, const float* traj,
+                          const float* u, const float* Rinv_diag, float alpha, const float* ctrl_lo, const float* ctrl_hi,
+                          float* dgdx, float* du, float* djdlam, float* u_star, void* stream) {
   AdjArgs a{};
   if (!make_dyn(dyn, a.d) || !make_kernel_dev(k, a.k)) return -1;
   if (H < 1 || H > KLERG_MAX_H) { set_error("adjoint: H out of range"); return -1; }
+  if (K < 1 || K > 65535) { set_error("adjoint: K out of range"); return -1; }
   a.H = H; a.grad_part = grad_part; a.world = world; a.dbarr = dbarr; a.P = P; a.traj = traj; a.u = u;
-  a.ap.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
+  a.ap.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star; a.gp_stride = gp_stride;
   for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
   const bool speed = a.d.kind == KLERG_DYN_SPEED;
   const size_t smem = sizeof(float) * ((size_t)H * (a.d.S + (P ? a.d.A * a.d.A : 0) + (speed ? a.d.S : 0) + a.d.A) +
@@ -665,8 +676,27 @@ extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec*
     }
     if (smem > 200 * 1024) { set_error("adjoint: horizon too long for shared-memory staging"); return -1; }
   }
-  adjoint_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(a);
+  adjoint_kernel<<<(unsigned)K, 256, smem, (cudaStream_t)stream>>>(a);
   return check_launch("adjoint_kernel");
+}
+
+extern "C" int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H,
+                             const double* grad_part, int world, const float* dbarr, const float* P,
+                             const float* traj, const float* u, const float* Rinv_diag, float alpha,
+                             const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
+                             float* u_star, void* stream) {
+  return launch_adjoint(dyn, k, H, grad_part, world, 1, 0, dbarr, P, traj, u, Rinv_diag, alpha, ctrl_lo, ctrl_hi, dgdx, du,
+                        djdlam, u_star, stream);
+}
+
+extern "C" int klerg_adjoint_targets(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H, int64_t K,
+                                     const double* grad_parts, int world, const float* dbarr, const float* P,
+                                     const float* traj, const float* u, const float* Rinv_diag, float alpha,
+                                     const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du,
+                                     float* djdlam, float* u_star, void* stream) {
+  if (!k) { set_error("kernel spec is null"); return -1; }
+  return launch_adjoint(dyn, k, H, grad_parts, world, K, (int64_t)world * H * k->D, dbarr, P, traj, u, Rinv_diag, alpha,
+                        ctrl_lo, ctrl_hi, dgdx, du, djdlam, u_star, stream);
 }
 
 extern "C" int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t M, float* out,

@@ -11,12 +11,13 @@
 // one fp32 accumulator in TMEM for the CTA's whole sample range.  The pair kernels recompute psi per target
 // (K * (3D+1) FP32 lane-ops per state-sample pair); here psi costs one forward-style evaluation per pair.
 //
-// Roles inside a CTA (320 threads, one CTA per SM, a contiguous range of samples per CTA, 32 samples per stage):
-//   warp 8     stager: thread = sample: importance-ratio factor maxc/c_i, centred scaled sample, the K target values
-//              -> shared memory; per-target KL terms (sum p (log p - log c), sum c) ride along
+// Roles inside a CTA (416 threads, one CTA per SM, a contiguous range of samples per CTA, 32 samples per stage):
+//   warps 8-11 stagers, one per ring slot (four stages' global loads in flight): thread = sample: importance-ratio
+//              factor maxc/c_i, centred scaled sample, the K target values -> shared memory; the per-target KL terms
+//              (sum p (log p - log c), sum c) ride along
 //   warps 0-3  thread = row (k,d') = TMEM lane: V for the stage's 32 samples (hi/lo tf32 halves) -> TMEM (A operand)
 //   warps 4-7  thread = (state t, 16 of the 32 samples): psi -> shared memory (B operand, no-swizzle K-major)
-//   warp 9     one lane issues 12 MMAs per stage and commits
+//   warp 12    one lane issues 12 MMAs per stage and commits
 // At the end warps 0-3 drain the accumulator into a per-CTA partial; a small second kernel adds the partials in CTA
 // order (doubles) and applies the last line above.
 #include <cuda_runtime.h>
@@ -32,7 +33,7 @@ namespace klerg {
 namespace {
 using namespace tc;
 
-constexpr int TG_THREADS = 320;
+constexpr int TG_THREADS = 416;         // warps 0-3 V rows, 4-7 psi, 8-11 stagers (one per ring slot), 12 MMA issue
 constexpr int TG_KS = 4;                 // MMA K-steps (8 samples each) per stage
 constexpr int TG_SPS = 8 * TG_KS;        // samples per stage
 constexpr int TG_STAGES = 4;
@@ -53,7 +54,7 @@ struct TGArgs {
   int K, R;             // R = K*(D+1) rows in use
   long long p_stride;
   float* part;          // [grid][128][Hp]
-  float* klpart;        // [grid][K][2]
+  float* klpart;        // [grid][TG_STAGES][K][2] (one row per stager warp)
   double* grad_out;     // [K][H][D]
   double* kl_out;       // [K][2]
   unsigned* fault;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
-      bar_init(&full_s[s], 32);
+      bar_init(&full_s[s], 32);  // the slot's own stager warp
       bar_init(&full_a[s], 128);
       bar_init(&full_b[s], 128);
       bar_init(&empty[s], 1);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     *s_abort = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -141,8 +142,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == 8) {
-    // ================= stager: one sample per thread =================
+  if (warp >= 8 && warp < 12) {
+    // ================= stagers: warp 8+q owns ring slot q (stages q, q+4, ...), one sample per thread; four stages'
+    // global loads are in flight at once =================
     double vsum, vmax;
     gather_totals(a.totals, a.world, 1, 0, vsum, vmax);
     const float vsum_f = (float)vsum;  // divide by the fp32 sum like the reference
@@ -154,36 +156,38 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 #pragma unroll
     for (int k = 0; k < TG_MAXK; ++k) kl_a[k] = 0.f;
     float kl_c = 0.f;
-    int s = 0;
+    const int s = warp - 8;
     unsigned ph = 0;
-    for (int st = 0; st < n_st; ++st) {
+    for (int st = s; st < n_st; st += TG_STAGES, ph ^= 1u) {
       bar_wait(&empty[s], ph ^ 1u, s_abort);
       float* slot = s_slot + (size_t)s * slot_f;
       const long long i = lo + (long long)st * TG_SPS + lane;
       const bool valid = i < hi;
+      // all global loads first (the shared-memory stores below would otherwise order them one after the other)
+      float pv[TG_MAXK], sv[D], vi = 1.f;
+#pragma unroll
+      for (int k = 0; k < TG_MAXK; ++k) pv[k] = (k < K && valid) ? __ldg(a.P + (size_t)k * a.p_stride + i) : 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sv[d] = valid ? __ldg(a.packed + (size_t)d * a.ld + i) : c_d[d];
+      if (valid) vi = __ldg(a.v + i);
       float r = 0.f, logc = 0.f;
       if (valid) {
-        const float c = fmaxf(a.v[i] / vsum_f, a.floor);
-        r = maxc_f / c;  // p * r = p / q with q = c / max c  (klerg.py:436)
-        logc = logf(c);
+        const float c = fmaxf(__fdividef(vi, vsum_f), a.floor);
+        r = __fdividef(maxc_f, c);  // p * r = p / q with q = c / max c  (klerg.py:436)
+        logc = __logf(c);
         kl_c += c;
       }
 #pragma unroll
-      for (int d = 0; d < D; ++d) slot[d * TG_SPS + lane] = valid ? a.packed[(size_t)d * a.ld + i] - c_d[d] : 0.f;
+      for (int d = 0; d < D; ++d) slot[d * TG_SPS + lane] = sv[d] - c_d[d];
       slot[D * TG_SPS + lane] = r;
 #pragma unroll
       for (int k = 0; k < TG_MAXK; ++k) {
         if (k < K) {
-          const float p = valid ? a.P[(size_t)k * a.p_stride + i] : 0.f;
-          slot[(D + 1 + k) * TG_SPS + lane] = p;
-          if (valid) kl_a[k] += p * (logf(p) - logc);
+          slot[(D + 1 + k) * TG_SPS + lane] = pv[k];
+          if (valid) kl_a[k] += pv[k] * (__logf(pv[k]) - logc);
         }
       }
       bar_arrive(&full_s[s]);
-      if (++s == TG_STAGES) {
-        s = 0;
-        ph ^= 1u;
-      }
     }
     kl_c = warp_sum_f(kl_c);
 #pragma unroll
@@ -191,8 +195,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
       if (k < K) {
         const float sa = warp_sum_f(kl_a[k]);
         if (lane == 0) {
-          a.klpart[((size_t)blockIdx.x * K + k) * 2 + 0] = sa;
-          a.klpart[((size_t)blockIdx.x * K + k) * 2 + 1] = kl_c;
+          a.klpart[(((size_t)blockIdx.x * TG_STAGES + s) * K + k) * 2 + 0] = sa;
+          a.klpart[(((size_t)blockIdx.x * TG_STAGES + s) * K + k) * 2 + 1] = kl_c;
         }
       }
     }
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *s_abort && a.fault) atomicExch(a.fault, 1u);
-  if (warp == 9) {
+  if (warp == 12) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -377,23 +381,30 @@ __global__ void targets_reduce_kernel(const TGArgs a, int nblk) {
     s_c[threadIdx.x] = 0.5f * (mn + mx);
   }
   __syncthreads();
+  // one warp per output: lanes stride over the CTA partials, fixed-order shuffle tree (deterministic)
+  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int total = a.K * a.H * D;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+  for (int e = gw; e < total; e += nw) {
     const int d = e % D, t = (e / D) % a.H, k = e / (D * a.H);
     double sd = 0.0, s0 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = lane; b < nblk; b += 32) {
       const float* p = a.part + ((size_t)b * 128 + (size_t)k * (D + 1)) * a.Hp + t;
       sd += (double)__ldcg(p + (size_t)d * a.Hp);
       s0 += (double)__ldcg(p + (size_t)D * a.Hp);
     }
-    const double xc = (double)(s_x[t * D + d] - s_c[d]);
-    a.grad_out[e] = (double)a.k.gfac[d] * (xc * s0 - sd);
+    sd = warp_reduce(RED_SUM, sd);
+    s0 = warp_reduce(RED_SUM, s0);
+    if (lane == 0) {
+      const double xc = (double)(s_x[t * D + d] - s_c[d]);
+      a.grad_out[e] = (double)a.k.gfac[d] * (xc * s0 - sd);
+    }
   }
   if (a.kl_out)
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.K * 2; e += gridDim.x * blockDim.x) {
+    for (int e = gw; e < a.K * 2; e += nw) {
       double acc = 0.0;
-      for (int b = 0; b < nblk; ++b) acc += (double)__ldcg(a.klpart + (size_t)b * a.K * 2 + e);
-      a.kl_out[e] = acc;
+      for (int b = lane; b < nblk * TG_STAGES; b += 32) acc += (double)__ldcg(a.klpart + (size_t)b * a.K * 2 + e);
+      acc = warp_reduce(RED_SUM, acc);
+      if (lane == 0) a.kl_out[e] = acc;
     }
 }
 
@@ -414,7 +425,7 @@ int launch_targets(TGArgs& a, cudaStream_t st) {
   targets_gradient_kernel<D><<<grid, TG_THREADS, sl.total, st>>>(a);
   int rc = check_launch("targets_gradient_kernel");
   if (rc) return rc;
-  targets_reduce_kernel<D><<<8, 256, 0, st>>>(a, grid);
+  targets_reduce_kernel<D><<<64, 256, 0, st>>>(a, grid);
   return check_launch("targets_reduce_kernel");
 }
 
@@ -425,7 +436,7 @@ using namespace klerg;
 
 extern "C" size_t klerg_kl_gradient_targets_scratch_bytes(int64_t H, int64_t K) {
   const size_t Hp = H <= 32 ? 32 : 64;
-  return (size_t)sm_count() * (128 * Hp + (size_t)K * 2) * sizeof(float);
+  return (size_t)sm_count() * (128 * Hp + (size_t)TG_STAGES * K * 2) * sizeof(float);
 }
 
 extern "C" int klerg_kl_gradient_targets(const klerg_kernel_spec* k, const float* states, int64_t H,

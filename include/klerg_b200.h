@@ -289,6 +289,14 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
 int klerg_gather_rows(const float* table, int32_t S, const int64_t* idx, int64_t M, float* out,
                       void* stream);
 
+/* klerg_adjoint for K belief targets sharing one trajectory (one CTA per target): grad_parts[K][world][H][D],
+ * outputs dgdx[K][H][S], du[K][H][A], djdlam[K][H], u_star[K][H][A]. */
+int klerg_adjoint_targets(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H, int64_t K,
+                          const double* grad_parts, int world, const float* dbarr, const float* P,
+                          const float* traj, const float* u, const float* Rinv_diag, float alpha,
+                          const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
+                          float* u_star, void* stream);
+
 /* ---- a4 for K belief targets: shared-psi contraction on the tensor cores ---- */
 
 /* kldiv_grad_vec (klerg_utils.py:12-15,31-36) for all H states and K targets p_k over one workspace and one

@@ -96,9 +96,12 @@ def test_config4_pose_workspace_long_history(H):
     close(g["djdlam"], dj, rtol=RTOL, atol_frac=5e-5, what="djdlam")
 
 
-def test_config5_belief_targets():
-    """4 belief targets over one workspace: per-target cost and gradient vs the oracle, target by target."""
+@pytest.mark.parametrize("path", ["fused", "tensor"])
+def test_config5_belief_targets(path):
+    """4 belief targets over one workspace: per-target cost and gradient vs the oracle, target by target - through the
+    fused launch (pair pass per target) and through the shared-psi tensor-core contraction."""
     s = setup("c5", 20_000, 300, H=20)
+    s["ctx"].targets_path = path
     lims = [wl.LIMS[c] for c in wl.WORKLOADS["c5"]["states"]]
     P = torch.stack([ko.renormalize(wl.make_target("gmm", lims, seed=10 + k).pdf_torch(s["samples"])) for k in range(4)])
     Pd = P.to(s["dev"])

@@ -109,10 +109,13 @@ def test_config3_full_batch_is_order_invariant():
     assert torch.isfinite(c).all() and float(c.std()) > 0
 
 
-def test_config5_full_gradient_is_linear_in_the_target():
-    """16 belief targets over 1e6 samples: q does not depend on p, so dgdx(p_j + p_k) = dgdx(p_j) + dgdx(p_k)."""
+@pytest.mark.parametrize("path", ["fused", "tensor"])
+def test_config5_full_gradient_is_linear_in_the_target(path):
+    """16 belief targets over 1e6 samples: q does not depend on p, so dgdx(p_j + p_k) = dgdx(p_j) + dgdx(p_k); and the
+    two implementations (pair pass per target / shared-psi tensor-core contraction) agree."""
     s = build("c5", 1_000_000, 3_000)
     ctx = s["ctx_for"](s["samples"], s["p_raw"], 1_000_000)
+    ctx.targets_path = path
     ctx.set_history(s["hist"])
     e = s["engine"]
     P = torch.stack([wl.make_target("gmm", s["lims"], seed=20 + k, device=s["dev"]).pdf_torch(s["samples"]) for k in range(16)])
@@ -123,5 +126,11 @@ def test_config5_full_gradient_is_linear_in_the_target():
     g = ctx.gradient_targets(u)
     assert g["dgdx"].shape == (17, s["H"], 2 * s["D"])
     assert rel(g["dgdx"][3] + g["dgdx"][11], g["dgdx"][16]) < 2e-5
+    if path == "tensor":
+        assert not e.targets_gradient_fault()
+        ctx.targets_path = "fused"
+        g2 = ctx.gradient_targets(u)
+        for key in ("dgdx", "du", "djdlam"):
+            assert rel(g[key], g2[key]) < 1e-4, key
     costs = ctx.costs_targets(u.unsqueeze(0))
     assert costs.shape == (17, 1) and torch.isfinite(costs).all()
