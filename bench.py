@@ -527,10 +527,22 @@ def cuda_arm(args):
         P5 = torch.stack([wl.make_target("gmm", lims5, seed=20 + k, device=dev).pdf_torch(smp5) for k in range(16)])
         st5 = torch.stack([engine.vector_stats(P5[k].contiguous())[:1] for k in range(16)])
         c3.set_targets(P5.contiguous(), st5)
-        t5 = timed(lambda: c3.gradient_targets(c3.u), 5)
+        paths = {}
+        for path in ("fused", "tensor"):
+            c3.targets_path = path
+            paths[path] = timed(lambda: c3.gradient_targets(c3.u), 5)
+        if engine.targets_gradient_fault():
+            raise SystemExit("klerg_kl_gradient_targets reported a timed-out wait; the measurement is void")
+        del c3.targets_path  # back to the class default
+        tensor_default = c3.targets_path != "fused" and c3._tensor_targets_ok(16)
+        t5 = paths["tensor"] if tensor_default else paths["fused"]
         also["c5"] = {"workload": "c5: states=xyz H=50 N=1000000 K=16 belief targets", "ms_per_16_target_gradient": t5 * 1e3,
-                      "pairs_per_s": (1 + 16) * S3["H"] * n5 / t5,
-                      "note": "one launch: shared rollout / forward pass / q, per-target gradient pass + adjoint"}
+                      "target_gradients_per_s": 16 / t5, "state_sample_target_triples_per_s": 16 * S3["H"] * n5 / t5,
+                      "ms_fused_launch_pair_pass_per_target": paths["fused"] * 1e3,
+                      "ms_shared_psi_tensor_core": paths["tensor"] * 1e3, "default_path": "tensor" if tensor_default else "fused",
+                      "note": "fused: one launch - shared rollout / forward pass / q, per-target gradient pair pass + adjoint; "
+                              "tensor: rollout, forward pass, klerg_kl_gradient_targets (psi once per pair, tcgen05 tf32 3xTF32 "
+                              "contraction over the samples for all 16 targets), one adjoint launch"}
         del S3, c3, U3, P5, smp5
         torch.cuda.empty_cache()
         also["target_decoder"] = target_decoder_block(dev, timed)

@@ -11,13 +11,14 @@
 // one fp32 accumulator in TMEM for the CTA's whole sample range.  The pair kernels recompute psi per target
 // (K * (3D+1) FP32 lane-ops per state-sample pair); here psi costs one forward-style evaluation per pair.
 //
-// Roles inside a CTA (416 threads, one CTA per SM, a contiguous range of samples per CTA, 32 samples per stage):
-//   warps 8-11 stagers, one per ring slot (four stages' global loads in flight): thread = sample: importance-ratio
+// Roles inside a CTA (512 threads, one CTA per SM, a contiguous range of samples per CTA, 32 samples per stage):
+//   warps 12-14 stagers, one per ring slot (the global loads of a stage are issued a ring turn ahead): thread = sample: importance-ratio
 //              factor maxc/c_i, centred scaled sample, the K target values -> shared memory; the per-target KL terms
 //              (sum p (log p - log c), sum c) ride along
-//   warps 0-3  thread = row (k,d') = TMEM lane: V for the stage's 32 samples (hi/lo tf32 halves) -> TMEM (A operand)
-//   warps 4-7  thread = (state t, 16 of the 32 samples): psi -> shared memory (B operand, no-swizzle K-major)
-//   warp 12    one lane issues 12 MMAs per stage and commits
+//   warps 0-3  thread = row (k,d') = TMEM lane: V for the stage's samples (hi/lo tf32 halves) -> TMEM (A operand); with
+//              <= 64 rows every row sits on two lanes that split the samples
+//   warps 4-11 thread = (state t, 8 of the 32 samples): psi -> shared memory (B operand, no-swizzle K-major)
+//   warp 15    one lane issues 12 MMAs per stage and commits
 // At the end warps 0-3 drain the accumulator into a per-CTA partial; a small second kernel adds the partials in CTA
 // order (doubles) and applies the last line above.
 #include <cuda_runtime.h>
@@ -33,11 +34,14 @@ namespace klerg {
 namespace {
 using namespace tc;
 
-constexpr int TG_THREADS = 416;         // warps 0-3 V rows, 4-7 psi, 8-11 stagers (one per ring slot), 12 MMA issue
+constexpr int TG_THREADS = 512;         // warps 0-3 V rows, 4-11 psi, 12-14 stagers (one per ring slot), 15 MMA issue
 constexpr int TG_KS = 4;                 // MMA K-steps (8 samples each) per stage
 constexpr int TG_SPS = 8 * TG_KS;        // samples per stage
-constexpr int TG_STAGES = 4;
-constexpr int TG_ACOL0 = 256;            // TMEM: accumulator columns [0, Hp), A ring [256, 256 + 4*64)
+constexpr int TG_ROW = TG_SPS + 4;       // floats per staged row: rows of different targets start 4 banks apart, so the
+                                         // V producers' per-target LDS.128 do not pile onto the same banks
+constexpr int TG_STAGES = 3;             // ring depth (a deeper ring bought nothing: the producers' issue rate is the limit)
+constexpr int TG_ACOL0 = 64;             // TMEM: accumulator columns [0, Hp <= 64), A ring [64, 64 + 3*64)
+constexpr int TG_STAGER0 = 12;           // first stager warp
 constexpr int TG_MAXK = 32;
 
 struct TGArgs {
@@ -61,7 +65,7 @@ struct TGArgs {
   long long chunk;      // samples per CTA (multiple of TG_SPS)
 };
 
-__host__ __device__ inline size_t tg_slot_floats(int D, int K) { return (size_t)(D + 1 + K) * TG_SPS; }
+__host__ __device__ inline size_t tg_slot_floats(int D, int K) { return (size_t)(D + 2 + K) * TG_ROW; }  // D samples rows, r, K targets, ones
 __host__ __device__ inline size_t tg_bstage_bytes(int Hp) { return (size_t)TG_KS * 64 * Hp; }
 struct TGSmem {
   size_t b, slot, xc, bars, total;
@@ -107,14 +111,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     for (int s = 0; s < TG_STAGES; ++s) {
       bar_init(&full_s[s], 32);  // the slot's own stager warp
       bar_init(&full_a[s], 128);
-      bar_init(&full_b[s], 128);
+      bar_init(&full_b[s], 256);
       bar_init(&empty[s], 1);
     }
     bar_init(acc_full, 1);
     *s_abort = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == 15) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -142,9 +146,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp >= 8 && warp < 12) {
-    // ================= stagers: warp 8+q owns ring slot q (stages q, q+4, ...), one sample per thread; four stages'
-    // global loads are in flight at once =================
+  if (warp >= TG_STAGER0 && warp < TG_STAGER0 + TG_STAGES) {
+    // ================= stagers: warp 12+q owns ring slot q (stages q, q+3, ...), one sample per thread; the global
+    // loads of a stage are issued a ring turn ahead =================
     double vsum, vmax;
     gather_totals(a.totals, a.world, 1, 0, vsum, vmax);
     const float vsum_f = (float)vsum;  // divide by the fp32 sum like the reference
@@ -156,20 +160,25 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 #pragma unroll
     for (int k = 0; k < TG_MAXK; ++k) kl_a[k] = 0.f;
     float kl_c = 0.f;
-    const int s = warp - 8;
+    const int s = warp - TG_STAGER0;
     unsigned ph = 0;
-    for (int st = s; st < n_st; st += TG_STAGES, ph ^= 1u) {
-      bar_wait(&empty[s], ph ^ 1u, s_abort);
-      float* slot = s_slot + (size_t)s * slot_f;
+    // The global loads of a stage are issued one ring turn ahead (into registers), so their latency overlaps the
+    // wait for the slot instead of following it.
+    float pv[TG_MAXK], sv[D], vi = 1.f;
+    bool valid = false;
+    auto fetch = [&](int st) {
       const long long i = lo + (long long)st * TG_SPS + lane;
-      const bool valid = i < hi;
-      // all global loads first (the shared-memory stores below would otherwise order them one after the other)
-      float pv[TG_MAXK], sv[D], vi = 1.f;
+      valid = st < n_st && i < hi;
 #pragma unroll
       for (int k = 0; k < TG_MAXK; ++k) pv[k] = (k < K && valid) ? __ldg(a.P + (size_t)k * a.p_stride + i) : 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) sv[d] = valid ? __ldg(a.packed + (size_t)d * a.ld + i) : c_d[d];
-      if (valid) vi = __ldg(a.v + i);
+      vi = valid ? __ldg(a.v + i) : 1.f;
+    };
+    fetch(s);
+    for (int st = s; st < n_st; st += TG_STAGES, ph ^= 1u) {
+      bar_wait(&empty[s], ph ^ 1u, s_abort);
+      float* slot = s_slot + (size_t)s * slot_f;
       float r = 0.f, logc = 0.f;
       if (valid) {
         const float c = fmaxf(__fdividef(vi, vsum_f), a.floor);
@@ -178,16 +187,18 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
         kl_c += c;
       }
 #pragma unroll
-      for (int d = 0; d < D; ++d) slot[d * TG_SPS + lane] = sv[d] - c_d[d];
-      slot[D * TG_SPS + lane] = r;
+      for (int d = 0; d < D; ++d) slot[d * TG_ROW + lane] = sv[d] - c_d[d];
+      slot[D * TG_ROW + lane] = r;
+      slot[(D + 1 + K) * TG_ROW + lane] = 1.f;  // multiplier of the weight rows (d' = D)
 #pragma unroll
       for (int k = 0; k < TG_MAXK; ++k) {
         if (k < K) {
-          slot[(D + 1 + k) * TG_SPS + lane] = pv[k];
+          slot[(D + 1 + k) * TG_ROW + lane] = pv[k];
           if (valid) kl_a[k] += pv[k] * (__logf(pv[k]) - logc);
         }
       }
       bar_arrive(&full_s[s]);
+      fetch(st + TG_STAGES);
     }
     kl_c = warp_sum_f(kl_c);
 #pragma unroll
@@ -202,56 +213,57 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     }
   } else if (warp < 4) {
     // ================= V producers (A operand in TMEM), later the epilogue =================
-    const int row = threadIdx.x;
+    // R <= 64: every row lives on two lanes (l and l + 64), each computing half of a stage's samples (zeros for the
+    // other half) - all four warps share the work; the reduce kernel adds the two accumulator rows
+    const int reps = a.R <= 64 ? 2 : 1, rows_per_rep = 128 / reps;
+    const int row = threadIdx.x % rows_per_rep, myrep = threadIdx.x / rows_per_rep;
     const bool active = row < a.R;
     const int k = active ? row / (D + 1) : 0, dd = active ? row - k * (D + 1) : D;
     const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    int s = 0, pending = -1;
+    int s = 0;
     unsigned ph = 0;
     for (int st = 0; st < n_st; ++st) {
       bar_wait(&full_s[s], ph, s_abort);
       tc_fence_after();
       const float* slot = s_slot + (size_t)s * slot_f;
-      const float4* rr = reinterpret_cast<const float4*>(slot + D * TG_SPS);
-      const float4* pp = reinterpret_cast<const float4*>(slot + (D + 1 + k) * TG_SPS);
-      const float4* ss = reinterpret_cast<const float4*>(slot + (dd < D ? dd : 0) * TG_SPS);
+      // rows beyond R repeat row 0's arithmetic (finite values; their accumulator rows are never read)
+      const ulonglong2* rr = reinterpret_cast<const ulonglong2*>(slot + D * TG_ROW);
+      const ulonglong2* pp = reinterpret_cast<const ulonglong2*>(slot + (D + 1 + k) * TG_ROW);
+      const ulonglong2* ss = reinterpret_cast<const ulonglong2*>(slot + (dd < D ? dd : D + 1 + K) * TG_ROW);
       const uint32_t acol = trow + (uint32_t)(TG_ACOL0 + s * (16 * TG_KS));
 #pragma unroll
       for (int kk = 0; kk < TG_KS; ++kk) {
         uint32_t hiw[8], low[8];
+        if (reps == 2 && (kk >> 1) != myrep) {  // the other lane of this row covers these samples
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 r4 = rr[kk * 2 + h], p4 = pp[kk * 2 + h], s4 = ss[kk * 2 + h];
-          const float w[4] = {p4.x * r4.x, p4.y * r4.y, p4.z * r4.z, p4.w * r4.w};
-          const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+          for (int q = 0; q < 8; ++q) hiw[q] = low[q] = 0u;
+        } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float val = active ? (dd < D ? w[q] * sv[q] : w[q]) : 0.f;
-            hiw[h * 4 + q] = __float_as_uint(val) & 0xFFFFE000u;  // tf32 split by truncation, lo exact in fp32
-            low[h * 4 + q] = __float_as_uint(val - __uint_as_float(hiw[h * 4 + q]));
+          for (int h = 0; h < 2; ++h) {
+            const ulonglong2 r4 = rr[kk * 2 + h], p4 = pp[kk * 2 + h], s4 = ss[kk * 2 + h];
+            // packed f32x2: val = (p * r) * s', tf32 split by truncation (hi = top 10 mantissa bits, lo = val - hi exact)
+            const u64 v0 = mul2(mul2(p4.x, r4.x), s4.x), v1 = mul2(mul2(p4.y, r4.y), s4.y);
+            const u64 h0 = v0 & 0xFFFFE000FFFFE000ull, h1 = v1 & 0xFFFFE000FFFFE000ull;
+            const u64 l0 = sub2(v0, h0), l1 = sub2(v1, h1);
+            hiw[h * 4 + 0] = (uint32_t)h0; hiw[h * 4 + 1] = (uint32_t)(h0 >> 32);
+            hiw[h * 4 + 2] = (uint32_t)h1; hiw[h * 4 + 3] = (uint32_t)(h1 >> 32);
+            low[h * 4 + 0] = (uint32_t)l0; low[h * 4 + 1] = (uint32_t)(l0 >> 32);
+            low[h * 4 + 2] = (uint32_t)l1; low[h * 4 + 3] = (uint32_t)(l1 >> 32);
           }
-        }
-        if (kk == 0 && pending >= 0) {
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          bar_arrive(&full_a[pending]);
         }
         tmem_st8(acol + kk * 16, hiw);
         tmem_st8(acol + kk * 16 + 8, low);
       }
-      pending = s;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      bar_arrive(&full_a[s]);
       if (++s == TG_STAGES) {
         s = 0;
         ph ^= 1u;
       }
     }
-    if (pending >= 0) {
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      bar_arrive(&full_a[pending]);
-    }
     // ---- epilogue: this row of the accumulator -> the CTA's partial ----
-    float* out = a.part + ((size_t)blockIdx.x * 128 + row) * Hp;
+    float* out = a.part + ((size_t)blockIdx.x * 128 + threadIdx.x) * Hp;  // accumulator row = TMEM lane
     if (n_st > 0) {
       bar_wait(acc_full, 0u, s_abort);
       tc_fence_after();
@@ -269,39 +281,39 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     } else if (active) {
       for (int j = 0; j < Hp; ++j) out[j] = 0.f;
     }
-  } else if (warp < 8) {
+  } else if (warp < TG_STAGER0) {
     // ================= psi producers (B operand in shared memory) =================
     const int tid2 = threadIdx.x - 128;
-    const int t = tid2 & 63, half = tid2 >> 6;  // state, which 16 of the stage's 32 samples
+    const int t = tid2 & 63, kk = tid2 >> 6;  // state, which K-step (8 of the stage's 32 samples)
     const bool row_ok = t < Hp, live = t < H;
-    float x[D];
+    u64 x2[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) x[d] = s_xc[t * D + d];
+    for (int d = 0; d < D; ++d) x2[d] = pack2(s_xc[t * D + d], s_xc[t * D + d]);
+    const float live_f = live ? 1.f : 0.f;
     int s = 0;
     unsigned ph = 0;
     for (int st = 0; st < n_st; ++st) {
       bar_wait(&full_s[s], ph, s_abort);
       const float* slot = s_slot + (size_t)s * slot_f;
       unsigned char* bst = sB + (size_t)s * bstage;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int kk = half * 2 + e;
+      {
         uint32_t hiw[8], low[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          float e2[4] = {0.f, 0.f, 0.f, 0.f};
+          u64 e01 = pack2(0.f, 0.f), e23 = e01;
 #pragma unroll
           for (int d = 0; d < D; ++d) {
-            const float4 s4 = *reinterpret_cast<const float4*>(slot + d * TG_SPS + kk * 8 + h * 4);
-            const float df0 = x[d] - s4.x, df1 = x[d] - s4.y, df2 = x[d] - s4.z, df3 = x[d] - s4.w;
-            e2[0] = fmaf(df0, df0, e2[0]);
-            e2[1] = fmaf(df1, df1, e2[1]);
-            e2[2] = fmaf(df2, df2, e2[2]);
-            e2[3] = fmaf(df3, df3, e2[3]);
+            const ulonglong2 s4 = *reinterpret_cast<const ulonglong2*>(slot + d * TG_ROW + kk * 8 + h * 4);
+            const u64 d01 = sub2(x2[d], s4.x), d23 = sub2(x2[d], s4.y);
+            e01 = fma2(d01, d01, e01);
+            e23 = fma2(d23, d23, e23);
           }
+          float e[4];
+          unpack2(e01, e[0], e[1]);
+          unpack2(e23, e[2], e[3]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float psi = live ? ex2_neg(e2[q]) : 0.f;
+            const float psi = ex2_neg(e[q]) * live_f;
             hiw[h * 4 + q] = __float_as_uint(psi) & 0xFFFFE000u;
             low[h * 4 + q] = __float_as_uint(psi - __uint_as_float(hiw[h * 4 + q]));
           }
@@ -340,9 +352,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
           const uint32_t a_hi = a0 + kk * 16, a_lo = a_hi + 8;
           const uint32_t b_hi = b0 + kk * bstep, b_lo = b_hi + 32u * (uint32_t)Hp;
           const uint64_t db_hi = smem_desc(b_hi, b_lbo, b_sbo), db_lo = smem_desc(b_lo, b_lbo, b_sbo);
+#ifdef TG_DEBUG_ONE_MMA
+          tc_mma_tf32_ts(tmem, a_hi, db_hi, idesc, (st | kk) ? 1u : 0u);
+#else
           tc_mma_tf32_ts(tmem, a_lo, db_hi, idesc, (st | kk) ? 1u : 0u);
           tc_mma_tf32_ts(tmem, a_hi, db_lo, idesc, 1u);
           tc_mma_tf32_ts(tmem, a_hi, db_hi, idesc, 1u);
+#endif
         }
         tc_commit(&empty[s]);
         if (++s == TG_STAGES) {
@@ -356,7 +372,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *s_abort && a.fault) atomicExch(a.fault, 1u);
-  if (warp == 12) {
+  if (warp == 15) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -364,9 +380,17 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 }
 
 // Partials -> grad_out[K][H][D] (doubles, the layout klerg_adjoint takes per target) and kl_out[K][2].
+// One CTA per target; thread = (row d' of the target, state t, part of the CTA list): every load is a coalesced
+// run of accumulator columns, partial sums are combined in a fixed order (deterministic).
 template <int D>
-__global__ void targets_reduce_kernel(const TGArgs a, int nblk) {
+__host__ __device__ constexpr int tg_reduce_parts() { return D + 1 <= 4 ? 4 : 2; }  // CTA = (D+1) rows x 64 states x parts <= 1024 threads
+
+template <int D>
+__global__ void __launch_bounds__((D + 1) * 64 * tg_reduce_parts<D>()) targets_reduce_kernel(const TGArgs a, int nblk) {
+  constexpr int PARTS = tg_reduce_parts<D>();
   __shared__ float s_x[64 * D], s_c[D];
+  __shared__ double s_sum[PARTS][D + 1][64];
+  const int k = blockIdx.x;
   for (int e = threadIdx.x; e < 64 * D; e += blockDim.x) {
     const int t = e / D, d = e - t * D;
     s_x[e] = t < a.H ? a.states[(size_t)t * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
@@ -380,32 +404,34 @@ __global__ void targets_reduce_kernel(const TGArgs a, int nblk) {
     }
     s_c[threadIdx.x] = 0.5f * (mn + mx);
   }
-  __syncthreads();
-  // one warp per output: lanes stride over the CTA partials, fixed-order shuffle tree (deterministic)
-  const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const int total = a.K * a.H * D;
-  for (int e = gw; e < total; e += nw) {
-    const int d = e % D, t = (e / D) % a.H, k = e / (D * a.H);
-    double sd = 0.0, s0 = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
-      const float* p = a.part + ((size_t)b * 128 + (size_t)k * (D + 1)) * a.Hp + t;
-      sd += (double)__ldcg(p + (size_t)d * a.Hp);
-      s0 += (double)__ldcg(p + (size_t)D * a.Hp);
-    }
-    sd = warp_reduce(RED_SUM, sd);
-    s0 = warp_reduce(RED_SUM, s0);
-    if (lane == 0) {
-      const double xc = (double)(s_x[t * D + d] - s_c[d]);
-      a.grad_out[e] = (double)a.k.gfac[d] * (xc * s0 - sd);
-    }
+  const int t = threadIdx.x & 63, dd = (threadIdx.x >> 6) % (D + 1), part4 = threadIdx.x / (64 * (D + 1));
+  const int reps = a.R <= 64 ? 2 : 1;
+  double acc = 0.0;
+  if (t < a.Hp) {
+    const int per = (nblk + PARTS - 1) / PARTS, b0 = part4 * per, b1 = min(nblk, b0 + per);
+    for (int b = b0; b < b1; ++b)
+      for (int rp = 0; rp < reps; ++rp)
+        acc += (double)__ldcg(a.part + ((size_t)b * 128 + (size_t)rp * 64 + (size_t)k * (D + 1) + dd) * a.Hp + t);
   }
-  if (a.kl_out)
-    for (int e = gw; e < a.K * 2; e += nw) {
-      double acc = 0.0;
-      for (int b = lane; b < nblk * TG_STAGES; b += 32) acc += (double)__ldcg(a.klpart + (size_t)b * a.K * 2 + e);
-      acc = warp_reduce(RED_SUM, acc);
-      if (lane == 0) a.kl_out[e] = acc;
+  s_sum[part4][dd][t] = acc;
+  __syncthreads();
+  if (part4 == 0 && dd < D && t < a.H) {
+    double sd = 0.0, s0 = 0.0;
+#pragma unroll
+    for (int q = 0; q < PARTS; ++q) {
+      sd += s_sum[q][dd][t];
+      s0 += s_sum[q][D][t];
     }
+    const double xc = (double)(s_x[t * D + dd] - s_c[dd]);
+    a.grad_out[((size_t)k * a.H + t) * D + dd] = (double)a.k.gfac[dd] * (xc * s0 - sd);
+  }
+  if (a.kl_out && threadIdx.x < 64) {  // warps 0-1: the two KL terms of this target
+    const int e = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double kacc = 0.0;
+    for (int b = lane; b < nblk * TG_STAGES; b += 32) kacc += (double)__ldcg(a.klpart + ((size_t)b * a.K + k) * 2 + e);
+    kacc = warp_reduce(RED_SUM, kacc);
+    if (lane == 0) a.kl_out[k * 2 + e] = kacc;
+  }
 }
 
 template <int D>
@@ -425,7 +451,7 @@ int launch_targets(TGArgs& a, cudaStream_t st) {
   targets_gradient_kernel<D><<<grid, TG_THREADS, sl.total, st>>>(a);
   int rc = check_launch("targets_gradient_kernel");
   if (rc) return rc;
-  targets_reduce_kernel<D><<<64, 256, 0, st>>>(a, grid);
+  targets_reduce_kernel<D><<<a.K, (D + 1) * 64 * tg_reduce_parts<D>(), 0, st>>>(a, grid);
   return check_launch("targets_reduce_kernel");
 }
 

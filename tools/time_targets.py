@@ -27,6 +27,18 @@ for fused in (True, False):
     torch.cuda.synchronize()
     print("fused K-target launch" if fused else "16 separate unfused evals", a.elapsed_time(b) / 10, "ms per 16-target gradient")
 ctx.fused = True
+ctx.targets_path = "tensor"
+for _ in range(3):
+    ctx.gradient_targets(u)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    ctx.gradient_targets(u)
+b.record()
+torch.cuda.synchronize()
+print("tensor-core shared-psi path (rollout + forward + targets gradient + adjoints)", a.elapsed_time(b) / 10, "ms per 16-target gradient")
+ctx.targets_path = "fused"
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(10):
