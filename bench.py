@@ -614,7 +614,7 @@ def cuda_arm(args):
     # ---- cpu_baseline: the oracle port on this box's host cores (rank 0, N=1 only) ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = min(n_total, 24_000 if D > 3 else 60_000)  # ~10 s of host work incl. the warm-up step
+        n_cpu = min(n_total, 80_000 if D > 3 else 160_000)  # ~10-15 s of host work incl. the warm-up step on a 16-core box
         m_cpu = min(w["M"], 1000)
         r_cpu = run_oracle_steps(args.workload, n_cpu, m_cpu, 2, 1)
         cpu = {"value": r_cpu["pairs"] / r_cpu["seconds"], "unit": "pairs/s", "cores": r_cpu["cores"], "kind": "port",
