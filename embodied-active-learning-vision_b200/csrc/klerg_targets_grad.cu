@@ -82,7 +82,8 @@ __host__ __device__ inline TGSmem tg_smem(int D, int K, int Hp) {
   return s;
 }
 
-template <int D>
+// KMAX: compile-time bound of the stagers' per-target loops (iterations beyond K would still issue, predicated off)
+template <int D, int KMAX>
 __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const TGArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const TGSmem sl = tg_smem(D, a.K, a.Hp);
@@ -156,21 +157,21 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     float c_d[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) c_d[d] = s_c[d];
-    float kl_a[TG_MAXK];
+    float kl_a[KMAX];
 #pragma unroll
-    for (int k = 0; k < TG_MAXK; ++k) kl_a[k] = 0.f;
+    for (int k = 0; k < KMAX; ++k) kl_a[k] = 0.f;
     float kl_c = 0.f;
     const int s = warp - TG_STAGER0;
     unsigned ph = 0;
     // The global loads of a stage are issued one ring turn ahead (into registers), so their latency overlaps the
     // wait for the slot instead of following it.
-    float pv[TG_MAXK], sv[D], vi = 1.f;
+    float pv[KMAX], sv[D], vi = 1.f;
     bool valid = false;
     auto fetch = [&](int st) {
       const long long i = lo + (long long)st * TG_SPS + lane;
       valid = st < n_st && i < hi;
 #pragma unroll
-      for (int k = 0; k < TG_MAXK; ++k) pv[k] = (k < K && valid) ? __ldg(a.P + (size_t)k * a.p_stride + i) : 0.f;
+      for (int k = 0; k < KMAX; ++k) pv[k] = (k < K && valid) ? __ldg(a.P + (size_t)k * a.p_stride + i) : 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) sv[d] = valid ? __ldg(a.packed + (size_t)d * a.ld + i) : c_d[d];
       vi = valid ? __ldg(a.v + i) : 1.f;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
       slot[D * TG_ROW + lane] = r;
       slot[(D + 1 + K) * TG_ROW + lane] = 1.f;  // multiplier of the weight rows (d' = D)
 #pragma unroll
-      for (int k = 0; k < TG_MAXK; ++k) {
+      for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
           slot[(D + 1 + k) * TG_ROW + lane] = pv[k];
           if (valid) kl_a[k] += pv[k] * (__logf(pv[k]) - logc);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     }
     kl_c = warp_sum_f(kl_c);
 #pragma unroll
-    for (int k = 0; k < TG_MAXK; ++k) {
+    for (int k = 0; k < KMAX; ++k) {
       if (k < K) {
         const float sa = warp_sum_f(kl_a[k]);
         if (lane == 0) {
@@ -439,7 +440,9 @@ int launch_targets(TGArgs& a, cudaStream_t st) {
   static bool configured = false;
   const TGSmem sl = tg_smem(D, a.K, a.Hp);
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(targets_gradient_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(targets_gradient_kernel<D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(targets_gradient_kernel<D, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(targets_gradient_kernel<D, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_error("kl_gradient_targets: smem opt-in failed: %s", cudaGetErrorString(e)); return -4; }
     configured = true;
   }
@@ -448,7 +451,9 @@ int launch_targets(TGArgs& a, cudaStream_t st) {
   chunk = (chunk + TG_SPS - 1) / TG_SPS * TG_SPS;
   if (chunk < TG_SPS) chunk = TG_SPS;
   a.chunk = chunk;
-  targets_gradient_kernel<D><<<grid, TG_THREADS, sl.total, st>>>(a);
+  if (a.K <= 8) targets_gradient_kernel<D, 8><<<grid, TG_THREADS, sl.total, st>>>(a);
+  else if (a.K <= 16) targets_gradient_kernel<D, 16><<<grid, TG_THREADS, sl.total, st>>>(a);
+  else targets_gradient_kernel<D, 32><<<grid, TG_THREADS, sl.total, st>>>(a);
   int rc = check_launch("targets_gradient_kernel");
   if (rc) return rc;
   targets_reduce_kernel<D><<<a.K, (D + 1) * 64 * tg_reduce_parts<D>(), 0, st>>>(a, grid);
