@@ -37,8 +37,6 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps
 
 t_tc = timed(lambda: engine.kl_gradient_targets(spec, traj, packed, n, v[0], totals_w, P))
-gp, _ = engine.kl_gradient_targets(spec, traj, packed, n, v[0], totals_w, P)
-t_adj = timed(lambda: gp.unsqueeze(1).contiguous())
 p0 = P[0, :n].contiguous()
 t_one = timed(lambda: engine.kl_gradient_fused(spec, traj, packed, n, v[0], totals_w, p0))
 print(f"N={n} H={H} K={K}: shared-psi tensor-core gradient {t_tc*1e3:.1f} us for {K} targets "
