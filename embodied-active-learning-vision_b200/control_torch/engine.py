@@ -200,9 +200,10 @@ def kl_gradient_fused(spec, states, packed, n, v, totals_w, p, floor=FLOOR):
 _targets_scratch = {}
 
 
-def kl_gradient_targets(spec, states, packed, n, v, totals_w, P, floor=FLOOR):
-    """K belief targets, psi shared (tensor-core contraction): -> (grad_parts [K,H,D] float64, kl_parts [K,2] float64)
-    for this rank's samples.  P [K, ld] rows padded to the sample stride."""
+def kl_gradient_targets(spec, states, packed, n, v, totals_w, P, floor=FLOOR, want_kl=True):
+    """K belief targets, psi shared (tensor-core contraction): -> (grad_parts [K,H,D] float64, kl_parts [K,2] float64
+    or None) for this rank's samples.  P [K, ld] rows padded to the sample stride.  ``want_kl=False`` skips the
+    per-target KL terms (a log per target and sample)."""
     lib = cabi.load()
     states = states.contiguous()
     H, K = states.shape[0], P.shape[0]
@@ -214,7 +215,7 @@ def kl_gradient_targets(spec, states, packed, n, v, totals_w, P, floor=FLOOR):
         scr = _targets_scratch[key] = (torch.empty(nbytes, dtype=torch.uint8, device=dev),
                                        torch.zeros(1, dtype=torch.int32, device=dev))
     grad_parts = torch.empty((K, H, spec.D), dtype=torch.float64, device=dev)
-    kl_parts = torch.empty((K, 2), dtype=torch.float64, device=dev)
+    kl_parts = torch.empty((K, 2), dtype=torch.float64, device=dev) if want_kl else None
     cabi.check(lib.klerg_kl_gradient_targets(
         C.byref(spec), cabi.ptr(states), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(v), cabi.ptr(totals_w),
         totals_w.shape[0], cabi.ptr(P), K, P.shape[1], float(floor), cabi.ptr(grad_parts), cabi.ptr(kl_parts),

@@ -220,7 +220,7 @@ class PlannerContext:
         outs = []
         for k0 in range(0, K, kmax):
             gp, _ = engine.kl_gradient_targets(self.spec, pre, self.packed, self.n, v[0], totals_w,
-                                               self.P[k0: k0 + kmax], self.floor)
+                                               self.P[k0: k0 + kmax], self.floor, want_kl=False)
             outs.append(engine.adjoint_targets(self.dyn, self.spec, gp.unsqueeze(1), ro["dbarr"][0], Pl, traj, u, self.rinv,
                                                self.alpha, self.ctrl_lo, self.ctrl_hi))
         self.evals["grad"] += K

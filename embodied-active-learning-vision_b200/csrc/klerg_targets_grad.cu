@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) kl_a[k] = 0.f;
     float kl_c = 0.f;
+    const bool want_kl = a.kl_out != nullptr;  // the per-target KL terms cost a log per target and sample
     const int s = warp - TG_STAGER0;
     unsigned ph = 0;
     // The global loads of a stage are issued one ring turn ahead (into registers), so their latency overlaps the
@@ -184,8 +185,10 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
       if (valid) {
         const float c = fmaxf(__fdividef(vi, vsum_f), a.floor);
         r = __fdividef(maxc_f, c);  // p * r = p / q with q = c / max c  (klerg.py:436)
-        logc = __logf(c);
-        kl_c += c;
+        if (want_kl) {
+          logc = __logf(c);
+          kl_c += c;
+        }
       }
 #pragma unroll
       for (int d = 0; d < D; ++d) slot[d * TG_ROW + lane] = sv[d] - c_d[d];
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
           slot[(D + 1 + k) * TG_ROW + lane] = pv[k];
-          if (valid) kl_a[k] += pv[k] * (__logf(pv[k]) - logc);
+          if (want_kl && valid) kl_a[k] += pv[k] * (__logf(pv[k]) - logc);
         }
       }
       bar_arrive(&full_s[s]);

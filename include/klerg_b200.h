@@ -303,7 +303,8 @@ int klerg_adjoint_targets(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k,
  * trajectory (BASELINE config 5): same inputs and outputs as klerg_kl_gradient_fused, per target -
  *   grad_part[k][H][D] (doubles, this rank's partial), kl_part[k][2] = {sum_i p_ki (log p_ki - log c_i), sum_i c_i}
  * - but psi(x_t, s_i) is evaluated once per state-sample pair and the sum over the samples runs as a tf32 tensor-core
- * contraction (3xTF32 split, fp32 accumulate).  Limits: H <= 64, K <= 32, K*(D+1) <= 128.  `scratch`:
+ * contraction (3xTF32 split, fp32 accumulate).  kl_part may be NULL (skips a log per target and sample).
+ * Limits: H <= 64, K <= 32, K*(D+1) <= 128.  `scratch`:
  * klerg_kl_gradient_targets_scratch_bytes(H, K) bytes; `fault` (may be NULL) is set to 1 if an in-kernel wait timed out. */
 size_t klerg_kl_gradient_targets_scratch_bytes(int64_t H, int64_t K);
 int klerg_kl_gradient_targets(const klerg_kernel_spec* k, const float* states, int64_t H, const float* packed,
