@@ -113,3 +113,27 @@ def test_target_decoder_validation(lib):
                                         C.c_void_p(64), None, None) == -1
     assert "aligned" in err(lib)
     assert lib.klerg_target_decoder_pack(None, None, None, None, None, None, None, 3, 16, 1, 256, 512, 1, None, None) == -1
+
+
+def test_targets_gradient_validation(lib):
+    """Shared-psi K-target gradient: the limits of the tensor-core kernel are checked before any launch."""
+    k = spec(D=3, S=6)
+    dummy = C.c_void_p(256)
+    args_ok = (dummy, 10, dummy, 100, 100, dummy, dummy, 1, dummy)
+    assert lib.klerg_kl_gradient_targets(C.byref(k), dummy, 65, dummy, 100, 100, dummy, dummy, 1, dummy, 4, 100, 1e-6,
+                                         dummy, None, dummy, None, None) == -2  # H > 64
+    assert "H must be" in err(lib)
+    assert lib.klerg_kl_gradient_targets(C.byref(k), *args_ok, 33, 100, 1e-6, dummy, None, dummy, None, None) == -2  # K > 32
+    k6 = spec(D=6, S=12)
+    assert lib.klerg_kl_gradient_targets(C.byref(k6), *args_ok, 19, 100, 1e-6, dummy, None, dummy, None, None) == -2  # 19*7 rows
+    assert "128 rows" in err(lib)
+    assert lib.klerg_kl_gradient_targets(C.byref(k), dummy, 10, dummy, 100, 98, dummy, dummy, 1, dummy, 4, 100, 1e-6,
+                                         dummy, None, dummy, None, None) == -1  # ld < N
+    assert lib.klerg_kl_gradient_targets(C.byref(k), None, 10, dummy, 100, 100, dummy, dummy, 1, dummy, 4, 100, 1e-6,
+                                         dummy, None, dummy, None, None) == -1  # null states
+    assert lib.klerg_kl_gradient_targets_scratch_bytes(50, 16) >= 128 * 64 * 4
+    dyn = cabi.dyn_spec(cabi.DYN_DOUBLE, 6, 3, 0.2)
+    three = cabi.farr([1.0] * 3)
+    assert lib.klerg_adjoint_targets(C.byref(dyn), C.byref(k), 10, 0, None, 1, None, None, None, None, three, 1.0, three,
+                                     three, None, None, None, None, None) == -1  # K < 1
+    assert "K out of range" in err(lib)
