@@ -169,7 +169,7 @@ class PlannerContext:
         q are shared by the targets.  Two implementations (``targets_path``): "fused" - one launch, the gradient pair
         pass and the adjoint run per target (psi recomputed per target); "tensor" - psi once per state-sample pair and
         the sum over the samples as a tensor-core contraction for all targets (klerg_kl_gradient_targets), the default
-        ("auto") for >= 4 targets on a single rank with H <= 64 (2.3x faster at BASELINE config 5)."""
+        ("auto") for >= 4 targets on a single rank with H <= 64 (2.5x faster at BASELINE config 5)."""
         K = self.P.shape[0]
         u = u.reshape(self.H, -1).contiguous()
         if self.targets_path == "tensor" or (self.targets_path == "auto" and self._tensor_targets_ok(K)):

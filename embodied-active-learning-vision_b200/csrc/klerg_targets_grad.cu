@@ -11,14 +11,15 @@
 // one fp32 accumulator in TMEM for the CTA's whole sample range.  The pair kernels recompute psi per target
 // (K * (3D+1) FP32 lane-ops per state-sample pair); here psi costs one forward-style evaluation per pair.
 //
-// Roles inside a CTA (512 threads, one CTA per SM, a contiguous range of samples per CTA, 32 samples per stage):
-//   warps 12-14 stagers, one per ring slot (the global loads of a stage are issued a ring turn ahead): thread = sample: importance-ratio
+// Roles inside a CTA (512 threads, one CTA per SM, a contiguous range of samples per CTA, 64 samples per stage - the
+// hand-offs between the roles, not their arithmetic, are what a stage costs):
+//   warps 8-13 stagers, two per ring slot (the global loads of a stage are issued a ring turn ahead): thread = sample: importance-ratio
 //              factor maxc/c_i, centred scaled sample, the K target values -> shared memory; the per-target KL terms
 //              (sum p (log p - log c), sum c) ride along
 //   warps 0-3  thread = row (k,d') = TMEM lane: V for the stage's samples (hi/lo tf32 halves) -> TMEM (A operand); with
 //              <= 64 rows every row sits on two lanes that split the samples
-//   warps 4-11 thread = (state t, 8 of the 32 samples): psi -> shared memory (B operand, no-swizzle K-major)
-//   warp 15    one lane issues 12 MMAs per stage and commits
+//   warps 4-7  thread = (state t, every other K-step of 8 samples): psi -> shared memory (B operand, no-swizzle K-major)
+//   warp 15    one lane issues 24 MMAs per stage and commits
 // At the end warps 0-3 drain the accumulator into a per-CTA partial; a small second kernel adds the partials in CTA
 // order (doubles) and applies the last line above.
 #include <cuda_runtime.h>
@@ -34,14 +35,15 @@ namespace klerg {
 namespace {
 using namespace tc;
 
-constexpr int TG_THREADS = 512;         // warps 0-3 V rows, 4-11 psi, 12-14 stagers (one per ring slot), 15 MMA issue
-constexpr int TG_KS = 4;                 // MMA K-steps (8 samples each) per stage
+constexpr int TG_THREADS = 512;         // warps 0-3 V rows, 4-7 psi, 8-13 stagers (two per ring slot), 15 MMA issue
+constexpr int TG_KS = 8;                 // MMA K-steps (8 samples each) per stage: the per-stage hand-offs are the bound
 constexpr int TG_SPS = 8 * TG_KS;        // samples per stage
 constexpr int TG_ROW = TG_SPS + 4;       // floats per staged row: rows of different targets start 4 banks apart, so the
                                          // V producers' per-target LDS.128 do not pile onto the same banks
 constexpr int TG_STAGES = 3;             // ring depth (a deeper ring bought nothing: the producers' issue rate is the limit)
 constexpr int TG_ACOL0 = 64;             // TMEM: accumulator columns [0, Hp <= 64), A ring [64, 64 + 3*64)
-constexpr int TG_STAGER0 = 12;           // first stager warp
+constexpr int TG_STAGER0 = 8;            // first stager warp; two stager warps per ring slot (32 samples each)
+constexpr int TG_NST = 2 * TG_STAGES;    // stager warps
 constexpr int TG_MAXK = 32;
 
 struct TGArgs {
@@ -110,9 +112,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
-      bar_init(&full_s[s], 32);  // the slot's own stager warp
+      bar_init(&full_s[s], 64);  // the slot's two stager warps
       bar_init(&full_a[s], 128);
-      bar_init(&full_b[s], 256);
+      bar_init(&full_b[s], 128);
       bar_init(&empty[s], 1);
     }
     bar_init(acc_full, 1);
@@ -147,9 +149,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp >= TG_STAGER0 && warp < TG_STAGER0 + TG_STAGES) {
-    // ================= stagers: warp 12+q owns ring slot q (stages q, q+3, ...), one sample per thread; the global
-    // loads of a stage are issued a ring turn ahead =================
+  if (warp >= TG_STAGER0 && warp < TG_STAGER0 + TG_NST) {
+    // ================= stagers: warps 8+2q, 9+2q own ring slot q (stages q, q+3, ...), one sample per thread; the
+    // global loads of a stage are issued a ring turn ahead =================
     double vsum, vmax;
     gather_totals(a.totals, a.world, 1, 0, vsum, vmax);
     const float vsum_f = (float)vsum;  // divide by the fp32 sum like the reference
@@ -162,14 +164,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
     for (int k = 0; k < KMAX; ++k) kl_a[k] = 0.f;
     float kl_c = 0.f;
     const bool want_kl = a.kl_out != nullptr;  // the per-target KL terms cost a log per target and sample
-    const int s = warp - TG_STAGER0;
+    const int s = (warp - TG_STAGER0) >> 1, half = (warp - TG_STAGER0) & 1, col = half * 32 + lane;
     unsigned ph = 0;
     // The global loads of a stage are issued one ring turn ahead (into registers), so their latency overlaps the
     // wait for the slot instead of following it.
     float pv[KMAX], sv[D], vi = 1.f;
     bool valid = false;
     auto fetch = [&](int st) {
-      const long long i = lo + (long long)st * TG_SPS + lane;
+      const long long i = lo + (long long)st * TG_SPS + col;
       valid = st < n_st && i < hi;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) pv[k] = (k < K && valid) ? __ldg(a.P + (size_t)k * a.p_stride + i) : 0.f;
@@ -191,13 +193,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
         }
       }
 #pragma unroll
-      for (int d = 0; d < D; ++d) slot[d * TG_ROW + lane] = sv[d] - c_d[d];
-      slot[D * TG_ROW + lane] = r;
-      slot[(D + 1 + K) * TG_ROW + lane] = 1.f;  // multiplier of the weight rows (d' = D)
+      for (int d = 0; d < D; ++d) slot[d * TG_ROW + col] = sv[d] - c_d[d];
+      slot[D * TG_ROW + col] = r;
+      slot[(D + 1 + K) * TG_ROW + col] = 1.f;  // multiplier of the weight rows (d' = D)
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-          slot[(D + 1 + k) * TG_ROW + lane] = pv[k];
+          slot[(D + 1 + k) * TG_ROW + col] = pv[k];
           if (want_kl && valid) kl_a[k] += pv[k] * (__logf(pv[k]) - logc);
         }
       }
@@ -210,8 +212,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
       if (k < K) {
         const float sa = warp_sum_f(kl_a[k]);
         if (lane == 0) {
-          a.klpart[(((size_t)blockIdx.x * TG_STAGES + s) * K + k) * 2 + 0] = sa;
-          a.klpart[(((size_t)blockIdx.x * TG_STAGES + s) * K + k) * 2 + 1] = kl_c;
+          a.klpart[(((size_t)blockIdx.x * TG_NST + (warp - TG_STAGER0)) * K + k) * 2 + 0] = sa;
+          a.klpart[(((size_t)blockIdx.x * TG_NST + (warp - TG_STAGER0)) * K + k) * 2 + 1] = kl_c;
         }
       }
     }
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
 #pragma unroll
       for (int kk = 0; kk < TG_KS; ++kk) {
         uint32_t hiw[8], low[8];
-        if (reps == 2 && (kk >> 1) != myrep) {  // the other lane of this row covers these samples
+        if (reps == 2 && (kk / (TG_KS / 2)) != myrep) {  // the other lane of this row covers these samples
 #pragma unroll
           for (int q = 0; q < 8; ++q) hiw[q] = low[q] = 0u;
         } else {
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
   } else if (warp < TG_STAGER0) {
     // ================= psi producers (B operand in shared memory) =================
     const int tid2 = threadIdx.x - 128;
-    const int t = tid2 & 63, kk = tid2 >> 6;  // state, which K-step (8 of the stage's 32 samples)
+    const int t = tid2 & 63, grp = tid2 >> 6;  // state; the two groups take alternate K-steps (8 samples each)
     const bool row_ok = t < Hp, live = t < H;
     u64 x2[D];
 #pragma unroll
@@ -300,7 +302,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
       bar_wait(&full_s[s], ph, s_abort);
       const float* slot = s_slot + (size_t)s * slot_f;
       unsigned char* bst = sB + (size_t)s * bstage;
-      {
+#pragma unroll
+      for (int kk = grp; kk < TG_KS; kk += 2) {
         uint32_t hiw[8], low[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) targets_gradient_kernel(const T
         ph ^= 1u;
       }
     }
-  } else {
+  } else if (warp == 15) {
     // ================= MMA issue =================
     if (lane == 0) {
       const uint32_t idesc = instr_desc_tf32(128, Hp);
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__((D + 1) * 64 * tg_reduce_parts<D>()) targets_r
   if (a.kl_out && threadIdx.x < 64) {  // warps 0-1: the two KL terms of this target
     const int e = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double kacc = 0.0;
-    for (int b = lane; b < nblk * TG_STAGES; b += 32) kacc += (double)__ldcg(a.klpart + ((size_t)b * a.K + k) * 2 + e);
+    for (int b = lane; b < nblk * TG_NST; b += 32) kacc += (double)__ldcg(a.klpart + ((size_t)b * a.K + k) * 2 + e);
     kacc = warp_reduce(RED_SUM, kacc);
     if (lane == 0) a.kl_out[k * 2 + e] = kacc;
   }
@@ -470,7 +473,7 @@ using namespace klerg;
 
 extern "C" size_t klerg_kl_gradient_targets_scratch_bytes(int64_t H, int64_t K) {
   const size_t Hp = H <= 32 ? 32 : 64;
-  return (size_t)sm_count() * (128 * Hp + (size_t)TG_STAGES * K * 2) * sizeof(float);
+  return (size_t)sm_count() * (128 * Hp + (size_t)TG_NST * K * 2) * sizeof(float);
 }
 
 extern "C" int klerg_kl_gradient_targets(const klerg_kernel_spec* k, const float* states, int64_t H,
