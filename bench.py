@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary c2 measurement")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="serialise consecutive evals (no programmatic dependent launch overlap)")
     ap.add_argument("--profile-evals", type=int, default=0,
                     help="run this many eager evals inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     return ap.parse_args()
@@ -327,7 +328,7 @@ def build_sets(name, n_total, rank, group, dev, engine, Robot, PlannerContext, m
                              probe.control_lim[:, 1].tolist(), alpha=1.0, group=group)
         g = torch.Generator(device=dev).manual_seed(100 + 17 * s + rank)
         smp = lo.to(dev) + torch.rand(n, D, generator=g, device=dev) * (hi - lo).to(dev)
-        ctx.set_samples(smp, probe.std.tolist(), 1.0)
+        ctx.set_samples(smp, probe.std.tolist(), 1.0, n_total=n_total)
         ctx.set_state(x0)
         p_raw = torch.cat([target.pdf_torch(c) for c in smp.split(1_000_000)]).contiguous()
         p, p_stats, _ = engine.target_weight(2, smp, lo.tolist(), hi.tolist(), None, p_raw, n_total, 1.0, True, group)
@@ -350,9 +351,13 @@ def timed_evals(args, S, K, warmup, world, rank, lib, dev):
         c = sets[i % n_sets]
         return c.gradient(c.u)
 
+    from control_torch import engine as _engine
     for i in range(max(warmup, 3)):
         eval_on(i)
     torch.cuda.synchronize()
+    # the timed evals are independent of one another (separate input sets and outputs): let the next eval's CTAs
+    # start while the previous eval's last CTA is still in its gather + adjoint tail
+    _engine.set_eval_overlap(not args.no_overlap)
     if args.profile_evals:
         torch.cuda.profiler.start()
         for i in range(args.profile_evals):
@@ -414,6 +419,7 @@ def timed_evals(args, S, K, warmup, world, rank, lib, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         dist.barrier()
+    _engine.set_eval_overlap(False)
     return dict(ms_total=ms_total, gpu_launches=gpu_launches, use_graph=use_graph)
 
 

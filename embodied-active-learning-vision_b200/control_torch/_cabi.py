@@ -41,7 +41,11 @@ class DynSpec(C.Structure):
 
 
 class Peers(C.Structure):
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * 8)]
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * 8), ("n_max", C.c_int64)]
+
+
+ABI_VERSION = 5  # mirrors klerg_abi_version() of the library built from this tree (include/klerg_b200.h)
+OPT_EVAL_OVERLAP, OPT_GRID_LIMIT, OPT_PDL, OPT_COOP_WITH_PDL = 1, 2, 3, 4
 
 
 class BarrierSpec(C.Structure):
@@ -128,17 +132,21 @@ SIGNATURES = {
     "klerg_mailbox_close": [_P, C.c_int],
     "klerg_debug_stamps_offset": [],
     "klerg_fused_fault_offset": [],
+    "klerg_set_option": [C.c_int, C.c_int],
+    "klerg_get_option": [C.c_int],
+    "klerg_emu_begin": [],
+    "klerg_emu_launch": [_P],
     "klerg_eval_gradient": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _P, _F, _FP, _F, _FP, _FP,
-                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "klerg_eval_gradient_targets": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _I64, _I64, _P, _F, _FP, _F,
-                                    _FP, _FP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+                                    _FP, _FP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "klerg_kl_gradient_targets_scratch_bytes": [_I64, _I64],
     "klerg_kl_gradient_targets": [_KS, _P, _I64, _P, _I64, _I64, _P, _P, C.c_int, _P, _I64, _I64, _F, _P, _P, _P, _P, _P],
     "klerg_target_decoder_packed_bytes": [_I32, _I32, _I32, _I32, _I32, _I32],
     "klerg_target_decoder_pack": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "klerg_target_decoder_pdf": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _I64, _P, _F, _F, _P, _P, _P],
     "klerg_eval_costs": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P,
-                         _P, _P],
+                         _P, _P, _P],
 }
 _RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_kl_gradient_targets_scratch_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
              "klerg_launch_count": C.c_longlong}
@@ -154,6 +162,11 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback for the KL-ergodic path.")
     lib = C.CDLL(LIB_PATH)
+    lib.klerg_abi_version.restype = C.c_int
+    got = lib.klerg_abi_version()
+    if got != ABI_VERSION:  # a stale .so would have its arguments misbound without any error
+        raise RuntimeError(f"{LIB_PATH} has ABI version {got}, this package binds version {ABI_VERSION}: rebuild it with "
+                           "`python -c 'import __graft_entry__ as g; g.build()'`")
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

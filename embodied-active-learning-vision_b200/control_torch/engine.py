@@ -31,8 +31,15 @@ class Workspace:
     def get(self, G=1):
         if self.buf is None or G > self.G:
             G = max(int(G), 8, self.G)
-            nbytes = cabi.load().klerg_workspace_bytes(G)
+            lib = cabi.load()
+            nbytes = lib.klerg_workspace_bytes(G)
+            old = self.buf
             self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=_dev())
+            if old is not None:
+                # the head of the workspace carries state that must survive a regrowth: the sticky fault word and the
+                # launch / exchange counters of the single-GPU mailbox (the segment records behind it are scratch)
+                head = lib.klerg_workspace_bytes(0)
+                self.buf[:head].copy_(old[:head])
             self.G = G
         return C.c_void_p(self.buf.data_ptr())
 
@@ -80,6 +87,12 @@ class ShardGroup:
             return None
         if getattr(self, "_peers", None) is not None:
             return self._peers
+        cached = _peer_cache.get(id(self.pg))
+        if cached is not None and cached[0] is self.pg:  # one mailbox set per process group, however many controllers
+            self._peers = cached[1]
+            return self._peers
+        if self.world > 8:
+            raise ValueError(f"the fused evals exchange through at most 8 mailboxes (one box); got world={self.world}")
         import torch.distributed as dist
         lib = cabi.load()
         mine, handle = C.c_void_p(), C.create_string_buffer(64)
@@ -98,7 +111,26 @@ class ShardGroup:
         torch.cuda.synchronize()
         dist.barrier(group=self.pg)
         self._peers = peers
+        _peer_cache[id(self.pg)] = (self.pg, peers)
         return peers
+
+    def max_shard(self, n_total):
+        """Samples of the largest shard (every rank sizes its fused grids from it)."""
+        return -(-int(n_total) // self.world)
+
+    def close(self):
+        """Unmap the peers' mailboxes and free this rank's (collective: call on every rank, after a sync)."""
+        cached = _peer_cache.pop(id(self.pg), None)
+        peers = cached[1] if cached is not None else getattr(self, "_peers", None)
+        self._peers = None
+        if peers is None:
+            return
+        lib = cabi.load()
+        torch.cuda.synchronize()
+        for r in range(peers.world):
+            if peers.mailbox[r]:
+                cabi.check(lib.klerg_mailbox_close(C.c_void_p(peers.mailbox[r]), int(r == peers.rank)), "klerg_mailbox_close")
+                peers.mailbox[r] = None
 
     def shard_bounds(self, n_total):
         """Contiguous [lo, hi) slice of the sample axis owned by this rank."""
@@ -107,7 +139,55 @@ class ShardGroup:
         return lo, lo + base + (1 if self.rank < rem else 0)
 
 
+class EmulatedShardGroup(ShardGroup):
+    """One of two ranks of a sample-sharded workspace that both live on ONE GPU (tests of the exchange protocol on a
+    single-GPU box): mailboxes are plain device buffers, and the two ranks' fused evals are recorded and launched as
+    one cooperative grid by ``emulated_pair`` (separately launched kernels that wait on one another are not
+    guaranteed to be co-resident)."""
+
+    def __init__(self, rank, mailboxes):
+        self.pg = None
+        self.world, self.rank = 2, int(rank)
+        self._mail = mailboxes  # keeps the buffers alive
+        peers = cabi.Peers()
+        peers.world, peers.rank = 2, int(rank)
+        for r in range(2):
+            peers.mailbox[r] = mailboxes[r].data_ptr()
+        self._peers = peers
+
+    def gather_blocks(self, block):
+        raise RuntimeError("emulated ranks exchange inside the fused kernels only")
+
+    @staticmethod
+    def make_pair(device=None):
+        n = cabi.load().klerg_mailbox_bytes()
+        mail = [torch.zeros(n, dtype=torch.uint8, device=device or _dev()) for _ in range(2)]
+        return EmulatedShardGroup(0, mail), EmulatedShardGroup(1, mail)
+
+
+def emulated_pair(call_rank0, call_rank1, grid_limit=64):
+    """Run ONE fused eval of each emulated rank (the two callables issue exactly one klerg_eval_* call each) as a
+    single cooperative launch; returns the callables' results."""
+    lib = cabi.load()
+    cabi.check(lib.klerg_set_option(cabi.OPT_GRID_LIMIT, int(grid_limit)), "klerg_set_option")
+    try:
+        cabi.check(lib.klerg_emu_begin(), "klerg_emu_begin")
+        out = (call_rank0(), call_rank1())
+        cabi.check(lib.klerg_emu_launch(cabi.stream_ptr()), "klerg_emu_launch")
+    finally:
+        lib.klerg_set_option(cabi.OPT_GRID_LIMIT, 0)
+    return out
+
+
+_peer_cache = {}
 SINGLE = ShardGroup()
+
+
+def set_eval_overlap(on):
+    """Declare consecutive fused evals on a stream independent (no eval reads what the previous one wrote): the
+    next eval's CTAs then start while the previous eval's last CTA is still in its gather + adjoint tail.  Batches
+    of independent evals (bench, candidate sweeps) only; the planner's evals are separated by host decisions."""
+    cabi.check(cabi.load().klerg_set_option(cabi.OPT_EVAL_OVERLAP, int(bool(on))), "klerg_set_option")
 
 
 def padded(n):
@@ -361,14 +441,17 @@ class EvalBuffers:
         self.H, self.S, self.A, self.ld, self.max_g = H, S, A, ld, max_g
         self.sets = []
         for _ in range(n_sets):
-            # djdlam and u_star are what the host control flow reads after every gradient eval: one buffer, one D2H
-            host_pack = torch.empty(H + H * A, **f32)
+            # djdlam and u_star are what the host control flow reads after every gradient eval: one buffer, one D2H;
+            # the last float is the kernel's copy of the sticky fault word (a timed-out in-kernel wait)
+            host_pack = torch.zeros(H + H * A + 1, **f32)
             self.sets.append(dict(
                 v=torch.empty(ld, **f32), traj=torch.empty((H + 1, S), **f32), totals=torch.empty((1, 2), **f64),
                 cost=torch.empty(1, **f32), dgdx=torch.empty((H, S), **f32), du=torch.empty((H, A), **f32),
-                host_pack=host_pack, djdlam=host_pack[:H], u_star=host_pack[H:].view(H, A), kl=torch.empty(2, **f64)))
+                host_pack=host_pack, djdlam=host_pack[:H], u_star=host_pack[H:H + H * A].view(H, A),
+                fault=host_pack[H + H * A:], kl=torch.empty(2, **f64)))
         self.turn = 0
         self.v_costs = torch.empty((max_g, ld), **f32)
+        self.cost_pack = torch.zeros(max_g + 1, **f32)  # costs of one launch + fault word: one D2H
 
     def next_set(self):
         self.turn = (self.turn + 1) % len(self.sets)
@@ -387,7 +470,7 @@ def eval_gradient(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, p, p_stat
         float(floor), rinv, float(alpha), ctrl_lo, ctrl_hi, cabi.ptr(out["v"]), cabi.ptr(out["traj"]),
         cabi.ptr(out["totals"]), cabi.ptr(out["cost"]) if want_cost else None, cabi.ptr(out["dgdx"]),
         cabi.ptr(out["du"]), cabi.ptr(out["djdlam"]), cabi.ptr(out["u_star"]),
-        cabi.ptr(out["kl"]) if want_cost else None, workspace(8), cabi.stream_ptr()),
+        cabi.ptr(out["kl"]) if want_cost else None, cabi.ptr(out.get("fault")), workspace(8), cabi.stream_ptr()),
         "klerg_eval_gradient")
     return out
 
@@ -408,17 +491,17 @@ def eval_gradient_targets(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, P
         cabi.ptr(u), H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(q_base), cabi.ptr(P), K, stride,
         cabi.ptr(P_stats), float(floor), rinv, float(alpha), ctrl_lo, ctrl_hi, cabi.ptr(v_scratch), cabi.ptr(out["traj"]),
         cabi.ptr(out["totals"]), None, cabi.ptr(out["dgdx"]), cabi.ptr(out["du"]), cabi.ptr(out["djdlam"]),
-        cabi.ptr(out["u_star"]), None, workspace(8), cabi.stream_ptr()), "klerg_eval_gradient_targets")
+        cabi.ptr(out["u_star"]), None, None, workspace(8), cabi.stream_ptr()), "klerg_eval_gradient_targets")
     return out
 
 
-def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, v_scratch, cost, floor=FLOOR):
+def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, v_scratch, cost, floor=FLOOR, fault=None):
     """One fused launch: get_cost of G <= 8 candidates U [G,H,A] -> cost [G] (klerg_eval_costs)."""
     G, H, _ = U.shape
     cabi.check(cabi.load().klerg_eval_costs(
         C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, peers, cabi.ptr(x0), cabi.ptr(R0),
         cabi.ptr(U), G, H, cabi.ptr(packed), int(n), packed.shape[1], cabi.ptr(q_base), cabi.ptr(p), cabi.ptr(p_stats),
-        float(floor), cabi.ptr(v_scratch), None, None, cabi.ptr(cost), workspace(8), cabi.stream_ptr()),
+        float(floor), cabi.ptr(v_scratch), None, None, cabi.ptr(cost), cabi.ptr(fault), workspace(8), cabi.stream_ptr()),
         "klerg_eval_costs")
     return cost
 
@@ -432,7 +515,8 @@ def debug_stamps():
 
 
 def fused_fault():
-    """True if a fused eval on the current stream's workspace gave up waiting at a meeting point."""
+    """True if a fused eval on the current stream's workspace gave up waiting at a meeting point (one small D2H read;
+    the planner reads the kernels' own copy of the word with the results it fetches anyway)."""
     key = (torch.cuda.current_device(), cabi.raw_stream())
     ws = _workspaces.get(key)
     if ws is None or ws.buf is None:

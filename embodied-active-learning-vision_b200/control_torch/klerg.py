@@ -402,10 +402,19 @@ class Robot(object):
         return ctx
 
     def _costs(self, ctx, U_host):
-        """Batched get_cost: U_host [B,H,A] on the host -> list of B python floats (one sync)."""
+        """Batched get_cost: U_host [B,H,A] on the host -> [B] costs on the host (one sync)."""
+        B = U_host.shape[0]
         U = U_host.to(self.cuda, non_blocking=True)
-        c = ctx.costs(U).cpu()
-        self.stats["cost_evals"] += U_host.shape[0]
+        c = ctx.costs(U, view=True)
+        if ctx.fused and B <= ctx.buf.max_g:  # costs + the kernel's copy of the fault word in one D2H
+            pack = ctx.buf.cost_pack.cpu()
+            if pack[-1] != 0:
+                raise RuntimeError("klerg_eval_costs: an in-kernel wait timed out (lost peer or a launch that was not "
+                                   "co-resident); the costs of this step are void")
+            c = pack[:B].clone()
+        else:
+            c = c.cpu()
+        self.stats["cost_evals"] += B
         return c
 
     def kldiv_planner(self, num_target_samples, num_traj_samples, temp=1.0):
@@ -417,7 +426,7 @@ class Robot(object):
             if prev is not None:
                 ctx.buf = prev.buf  # eval scratch / output buffers are reused from step to step when the shapes match
             samples_dev = self._shard(samples).to(self.cuda, non_blocking=True).contiguous()
-            ctx.set_samples(samples_dev, self.std.tolist(), 1.0)
+            ctx.set_samples(samples_dev, self.std.tolist(), 1.0, n_total=samples.shape[0])
             ctx.set_state(self.robot.state.to(self.cuda, non_blocking=True))
             p, p_stats = self._target_on_device(samples, samples_dev, dict(packed_std=ctx.packed), temp,
                                                 uniform=self.uniform_tdist)
@@ -433,9 +442,12 @@ class Robot(object):
                 g = ctx.gradient(u_tmp.to(self.cuda, non_blocking=True), keep=self.plot_data is not None)
                 self.stats["grad_evals"] += 1
                 prev_accepted, accepted = accepted, g
-                if "host_pack" in g:  # fused eval: djdlam and u* share one buffer -> a single D2H copy
+                if "host_pack" in g:  # fused eval: djdlam, u* and the fault word share one buffer -> a single D2H copy
                     pack = g["host_pack"].cpu()
-                    djdlam, u_star = pack[:H], pack[H:].view(H, -1)
+                    if pack[-1] != 0:
+                        raise RuntimeError("klerg_eval_gradient: an in-kernel wait timed out (lost peer or a launch that "
+                                           "was not co-resident); the gradient of this step is void")
+                    djdlam, u_star = pack[:H], pack[H:-1].view(H, -1)
                 else:
                     djdlam = g["djdlam"].cpu()
                     u_star = g["u_star"].cpu()

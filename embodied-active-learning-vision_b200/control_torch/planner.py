@@ -52,9 +52,15 @@ class PlannerContext:
         self.buf = None
 
     # -- per-step inputs ---------------------------------------------------------
-    def set_samples(self, samples_dev, scale, nu=1.0):
-        """samples_dev [n_local, D] raw (this rank's slice); scale = std as the reference uses it."""
+    def set_samples(self, samples_dev, scale, nu=1.0, n_total=None):
+        """samples_dev [n_local, D] raw (this rank's slice); scale = std as the reference uses it.  ``n_total`` = samples
+        over all ranks (a sharded context sizes its fused grids from the largest shard, identically on every rank)."""
         D = samples_dev.shape[1]
+        if self.peers is not None:
+            if n_total is None:
+                n_local = torch.tensor([samples_dev.shape[0]], device=samples_dev.device)
+                n_total = int(self.group.gather_blocks(n_local).sum().item())
+            self.peers.n_max = self.group.max_shard(n_total)
         self.spec = cabi.kernel_spec(D, self.dyn.S, self.explr_locs, [float(s) for s in scale], nu)
         self.samples = samples_dev
         self.n = samples_dev.shape[0]
@@ -82,18 +88,26 @@ class PlannerContext:
         self.x0 = x0_dev.contiguous()
 
     # -- evals -------------------------------------------------------------------
-    def costs(self, U):
-        """U [B,H,A] on the device -> cost [B] (KL + barrier), all on the device."""
+    def costs(self, U, view=False):
+        """U [B,H,A] on the device -> cost [B] (KL + barrier), all on the device.  ``view=True`` (planner): for
+        B <= 8 the result is a view of ``buf.cost_pack``, valid until the next call."""
         if U.dim() == 2:
             U = U.unsqueeze(0)
         B = U.shape[0]
         if self.fused:
             U = U.contiguous()
-            cost = torch.empty(B, dtype=torch.float32, device=U.device)
-            for b0 in range(0, B, self.buf.max_g):
-                b1 = min(B, b0 + self.buf.max_g)
-                engine.eval_costs(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, U[b0:b1], self.packed, self.n,
-                                  self.q_base, self.p, self.p_stats, self.buf.v_costs, cost[b0:b1], self.floor)
+            mg = self.buf.max_g
+            if B <= mg:  # one launch (a line search): costs and the fault word share one buffer -> a single D2H
+                pack = self.buf.cost_pack
+                engine.eval_costs(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, U, self.packed, self.n,
+                                  self.q_base, self.p, self.p_stats, self.buf.v_costs, pack[:B], self.floor, fault=pack[mg:])
+                cost = pack[:B] if view else pack[:B].clone()
+            else:
+                cost = torch.empty(B, dtype=torch.float32, device=U.device)
+                for b0 in range(0, B, mg):
+                    b1 = min(B, b0 + mg)
+                    engine.eval_costs(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, U[b0:b1], self.packed,
+                                      self.n, self.q_base, self.p, self.p_stats, self.buf.v_costs, cost[b0:b1], self.floor)
             self.evals["cost"] += B
             self.evals["fwd_pairs"] += B * self.H * self.n
             return cost
@@ -195,6 +209,8 @@ class PlannerContext:
         self.evals["grad"] += K
         self.evals["fwd_pairs"] += self.H * self.n * len(outs)
         self.evals["grad_pairs"] += self.H * self.n * K
+        if len(outs) == 1:
+            return {k: outs[0][k] for k in ("du", "djdlam", "u_star", "dgdx")}
         return {k: torch.cat([o[k] for o in outs]) for k in ("du", "djdlam", "u_star", "dgdx")}
 
     # shared-psi path: psi once per state-sample pair, the sum over the samples as a tensor-core contraction

@@ -16,15 +16,37 @@ constexpr int GRAD_MAXBLK = 296;  // 148 SMs x 2
 constexpr size_t HEAD_COUNTERS = 256;
 constexpr size_t HEAD_MISC = (size_t)MAXBLK * 8 * sizeof(double);
 constexpr size_t HEAD_GRAD = (size_t)GRAD_MAXBLK * KLERG_MAX_H * KLERG_MAX_D * sizeof(double);
-// fused eval kernels (klerg_fused.cu): control words, world totals, per-CTA partials
-constexpr int FUSED_MAXBLK = 608;  // >= 148 SMs x 4, multiple of 32
+// fused eval kernels (klerg_fused.cu): control words + this GPU's exchange mailbox (see "mailbox layout")
 constexpr int FUSED_MAXG = 8;      // candidates per fused cost launch
-constexpr size_t FUSED_CTRL = 256;                                     // u32: [0] arrive-1 [1] arrive-2 [2] go [3] epoch
-constexpr size_t FUSED_WORLD = (size_t)FUSED_MAXG * 2 * sizeof(double);  // {sum, max} per candidate, all ranks combined
-constexpr size_t FUSED_TOT = (size_t)FUSED_MAXBLK * FUSED_MAXG * 2 * sizeof(double);
-constexpr size_t FUSED_KL = FUSED_TOT;
-constexpr size_t FUSED_GRAD = (size_t)FUSED_MAXBLK * KLERG_MAX_H * KLERG_MAX_D * sizeof(double);
-constexpr size_t FUSED_BYTES = FUSED_CTRL + FUSED_WORLD + FUSED_TOT + FUSED_KL + FUSED_GRAD;
+constexpr size_t FUSED_CTRL = 256;  // u32: [5] sticky fault word; +64: debug stamps (18 x int64)
+
+// ---- mailbox layout (symmetric across ranks; klerg_mailbox_bytes) --------------------------------------------
+// All meeting points of the fused evals are flag-free "LL" exchanges: every value travels as 8-byte words
+// {32 payload bits, 32-bit tag}; an aligned 8-byte store is single-copy atomic, so data and flag arrive together and
+// a waiter simply polls the slot until the tag of the current exchange shows up.  No counters, nothing to reset.
+// A double takes two words (16 B), an fp32 gradient partial one.  Slots are double-buffered by the parity of a
+// device-resident launch counter (epoch) resp. exchange counter (xcount) kept in the mailbox header.
+constexpr int MB_MAXW = 8;          // ranks
+constexpr int LL_MAXBLK = 160;      // CTAs per rank that take part in an exchange (>= 148 SMs)
+constexpr int LL_MAXNV = 2 * FUSED_MAXG;                      // doubles per CTA at a meeting
+constexpr int LL_MAXHD = KLERG_MAX_H * KLERG_MAX_D;           // gradient entries of one eval
+constexpr int LL_BUF_VALS = LL_MAXBLK * LL_MAXNV;             // polled values staged in shared memory (20 KB)
+constexpr size_t MB_HDR = 256;      // u32 [0] epoch  [1] xcount  [2] xdone
+constexpr size_t MB_X1 = (size_t)2 * MB_MAXW * LL_MAXBLK * 2 * 16;   // [par][rank][cta][2]   cross-rank one-hop meeting
+constexpr size_t MB_L1 = (size_t)2 * LL_MAXBLK * LL_MAXNV * 16;      // [par][cta][nv]        local stage
+constexpr size_t MB_R1 = (size_t)2 * MB_MAXW * LL_MAXNV * 16;        // [par][rank][nv]       rank stage
+constexpr size_t MB_KL = (size_t)2 * LL_MAXBLK * LL_MAXNV * 16;      // [par][cta][nv]        KL partials -> finisher
+constexpr size_t MB_GB = (size_t)2 * MB_MAXW * (LL_MAXHD + 16) * 16; // [par][rank][HD+16]    rank sums -> finisher
+constexpr size_t MB_GP = (size_t)2 * LL_MAXHD * LL_MAXBLK * 8;       // [par][e][cta] {fp32, tag} CTA partials
+constexpr size_t MB_OFF_X1 = MB_HDR;
+constexpr size_t MB_OFF_L1 = MB_OFF_X1 + MB_X1;
+constexpr size_t MB_OFF_R1 = MB_OFF_L1 + MB_L1;
+constexpr size_t MB_OFF_KL = MB_OFF_R1 + MB_R1;
+constexpr size_t MB_OFF_GB = MB_OFF_KL + MB_KL;
+constexpr size_t MB_OFF_GP = MB_OFF_GB + MB_GB;
+constexpr size_t MB_BYTES = MB_OFF_GP + MB_GP;
+
+constexpr size_t FUSED_BYTES = FUSED_CTRL + MB_BYTES;  // single GPU: the mailbox lives inside the workspace
 constexpr size_t HEAD_BYTES = HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + FUSED_BYTES;
 constexpr size_t SEG_BYTES = 64 + (size_t)MAXBLK * 2 * sizeof(double);
 
@@ -35,14 +57,7 @@ __host__ __device__ inline double* ws_grad_partials(void* ws) {
 }
 __host__ __device__ inline char* ws_fused_base(void* ws) { return (char*)ws + HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD; }
 __host__ __device__ inline unsigned* ws_fused_ctrl(void* ws) { return (unsigned*)ws_fused_base(ws); }
-__host__ __device__ inline double* ws_fused_world(void* ws) { return (double*)(ws_fused_base(ws) + FUSED_CTRL); }
-__host__ __device__ inline double* ws_fused_tot(void* ws) { return (double*)(ws_fused_base(ws) + FUSED_CTRL + FUSED_WORLD); }
-__host__ __device__ inline double* ws_fused_kl(void* ws) {
-  return (double*)(ws_fused_base(ws) + FUSED_CTRL + FUSED_WORLD + FUSED_TOT);
-}
-__host__ __device__ inline double* ws_fused_grad(void* ws) {
-  return (double*)(ws_fused_base(ws) + FUSED_CTRL + FUSED_WORLD + FUSED_TOT + FUSED_KL);
-}
+__host__ __device__ inline void* ws_fused_mailbox(void* ws) { return ws_fused_base(ws) + FUSED_CTRL; }
 __host__ __device__ inline int* ws_seg_counter(void* ws, int64_t g) {
   return (int*)((char*)ws + HEAD_BYTES + (size_t)g * SEG_BYTES);
 }

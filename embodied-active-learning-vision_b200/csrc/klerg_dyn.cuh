@@ -171,6 +171,9 @@ __host__ __device__ inline int rollout_rot_floats(int G, int H) { return G * (2 
 //   s_red   scratch of 32 floats
 //   s_bsum  [G]          sum_t barr(traj[t+1])  (klerg.py:708)
 //   R_out   [G][9]       rotation after the last step (global or shared, may be NULL)
+//   part    0 = everything; 1 = states only (running sums, rotation chain, angles): what the pair passes need;
+//           2 = the rest (linearisation blocks P, dbarr, barrier sums) from the states and rotations that a
+//               part-1 call left in s_traj / s_rot: only the CTA that runs the adjoint needs it.
 // Ends with a __syncthreads().
 // ---------------------------------------------------------------------------
 // Running sum by ONE warp: out[k] = init + x[0] + ... + x[k] (inclusive) or init + x[0] + ... + x[k-1] (exclusive)
@@ -197,7 +200,7 @@ __device__ __forceinline__ float warp_running_sum(int n, float init, bool exclus
 }
 
 #ifdef KLERG_STAMPS
-__device__ long long g_ro_stamp[8];
+static __device__ long long g_ro_stamp[8];
 #define RO_STAMP(i) if (blockIdx.x == 0 && threadIdx.x == 0) g_ro_stamp[i] = clock64()
 #else
 #define RO_STAMP(i)
@@ -205,7 +208,7 @@ __device__ long long g_ro_stamp[8];
 
 __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const float* x0, const float* R0,
                                      const float* s_u, int G, int H, float* s_traj, float* s_dbarr, float* s_P,
-                                     float* s_rot, float* s_red, float* s_bsum, float* R_out) {
+                                     float* s_rot, float* s_red, float* s_bsum, float* R_out, int part = 0) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   const PinnedParams pp = pin_params(s_red, d.S, d.A, H, d.kind, d.dt);
   const int S = pp.S, a = pp.A, kind = pp.kind;
@@ -213,6 +216,7 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
   const bool single = kind == KLERG_DYN_SINGLE, speed = kind == KLERG_DYN_SPEED, roll = kind == KLERG_DYN_ROLL;
   const float dt = pp.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
   RO_STAMP(0);
+  if (part != 2) {
   // (A) running sums, one warp per (candidate, control): vel_t = v0 + dt sum_{k<t} u_k, then
   //     pos_t = p0 + sum_{k<t} (0.8 dt vel_k + 0.4 dt^2 u_k)  (the closed-form RK4 step summed over time)
   for (int l = tid >> 5; l < G * a; l += nthr >> 5) {
@@ -239,10 +243,12 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
     }
   }
   __syncthreads();
+  }
   RO_STAMP(1);
   if (roll) {
     float* s_E = s_rot;               // [G][H][9]
     float* s_R = s_rot + G * H * 9;   // [G][H+1][9]
+    if (part != 2) {
     // (B) E_t from the pre-step angular velocity, all (g, t) in parallel; R_0
     for (int e = tid; e < G * H; e += nthr) {
       const int g = e / H, t = e - g * H;
@@ -319,9 +325,10 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
     if (R_out)
       for (int e = tid; e < G * 9; e += nthr) R_out[e] = s_R[((size_t)(e / 9) * (H + 1) + H) * 9 + e % 9];
     __syncthreads();
+    }
     RO_STAMP(7);
     // (D2) linearisation block: 0.8 I with the rpw x rpw entries replaced by E(rot) R (dynamics.py:189-211,283-289)
-    if (s_P) {
+    if (s_P && part != 1) {
       for (int e = tid; e < G * H * a * a; e += nthr) {
         const int r = (e % (a * a)) / a, c = e % a;
         s_P[e] = (r == c) ? 0.8f : 0.f;
@@ -341,10 +348,14 @@ __device__ inline void rollout_block(const DynDev& d, const BarDev& bar, const f
           for (int c = 0; c < 3; ++c) Pt[d.rpw[r] * a + d.rpw[c]] = blk[r * 3 + c];
       }
     }
-  } else if (R_out) {
+  } else if (R_out && part != 2) {
     for (int e = tid; e < G * 9; e += nthr) R_out[e] = ((e % 9) % 4 == 0) ? 1.f : 0.f;
   }
   RO_STAMP(2);
+  if (part == 1) {
+    __syncthreads();
+    return;
+  }
   // (E) wall barrier of the post-step states and its derivative at the pre-step states
   for (int g = 0; g < G; ++g) {
     const float* tr = s_traj + (size_t)g * (H + 1) * S;

@@ -1,0 +1,1246 @@
+// Fused KL-ergodic evals: ONE launch per eval (sm_100a).
+//
+//   eval_grad_kernel : Robot.forward + footprint + renormalize + importance ratio +
+//                      kldiv_grad_vec for all H steps + Robot.backward   (klerg.py:409-450, 505-523)
+//                      -> du, djdlam, u*, dgdx, KL cost of the plan
+//   eval_cost_kernel : Robot.get_cost for G <= 8 candidate control sequences (klerg.py:686-710;
+//                      the <= 5 line-search windows of klerg.py:712-751 are one launch)
+//
+// Every CTA redoes the tiny rollout (states only) in shared memory, owns a contiguous slice of the workspace
+// samples, and the CTAs - of this GPU and, with a sample-sharded workspace, of every peer GPU - meet twice:
+//   (1) after the forward pair pass: all-reduce of {sum, max} of q = q_base + q_iter (renormalize needs both
+//       before the importance ratio exists).  One hop: every CTA stores its pair as tagged words into the mailbox
+//       of every rank (plain stores, NVLink for the peers) and polls its own GPU's mailbox until all
+//       world x CTAs pairs are there (klerg_ll.cuh).  No atomics, no leader, no second broadcast.
+//   (2) after the gradient pass: every CTA stores its H*D fp32 partials as tagged words; warps spread over the
+//       grid poll one gradient entry each, add the CTA partials in a fixed order and store the sum into every
+//       rank's mailbox; ONE CTA (the "finisher") polls those sums, adds them in rank order and runs the adjoint
+//       sweep.  All other CTAs leave right after their entry sums.
+// The launches carry the programmatic-dependent-launch attribute and trigger their dependents right after
+// meeting (1): the CTAs of the next eval in the stream start on SMs as the CTAs of this one leave, so the
+// finisher's tail (gather + adjoint, ~5 us) and the launch latency overlap the next eval's rollout / forward
+// pass.  Full grids leave one SM free so that the next eval never has to wait for the finisher's SM.  By
+// default the next eval still waits (griddepcontrol.wait) for this one to complete before it reads its
+// inputs; KLERG_OPT_EVAL_OVERLAP declares consecutive evals independent and drops that wait.
+#pragma once
+#include <cstdio>
+#include <cstring>
+
+#include "klerg_common.cuh"
+#include "klerg_dyn.cuh"
+#include "klerg_ll.cuh"
+#include "klerg_pair.cuh"
+
+namespace klerg {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// one contiguous run of `bytes` (multiple of 16, both sides 16-byte aligned) global -> shared
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Phase stamps (clock64 at the phase boundaries of eval_grad_kernel) are compiled in with -DKLERG_STAMPS.
+#ifdef KLERG_STAMPS
+#define KLERG_STAMP_DECL long long stamp[16]
+#define KLERG_STAMP(i) stamp[i] = clock64()
+#else
+#define KLERG_STAMP_DECL
+#define KLERG_STAMP(i)
+#endif
+
+struct EvalArgs {
+  KernelDev k;
+  DynDev d;
+  BarDev bar;
+  AdjParams ap;
+  Peers peers;
+  int independent;       // 1: inputs do not depend on the previous launch in the stream (no griddepcontrol.wait)
+  // inputs
+  const float* x0;       // [S]
+  const float* R0;       // [9] or NULL
+  const float* u;        // [G][H][A]
+  int G, H;
+  const float* packed;   // [D][ld] scaled samples of this rank
+  int64_t N, ld;
+  const float* q_base;   // [N] or NULL
+  const float* p;        // [K][p_stride] target densities (K = 1: [N])
+  int K;                 // belief targets sharing one workspace / trajectory (gradient eval)
+  int64_t p_stride;
+  const double* p_stats; // [K] = sum p_k over all ranks
+  float floor;
+  // scratch
+  float* v;              // [G][ld]
+  void* ws;
+  // gradient-mode schedule
+  int nchr, nsub, rounds;  // state chunks per round, sample sub-streams, rounds
+  int nwide;               // mixed schedule: the last `nwide` warps own WT+1 states, the others WT
+  int ts;                  // samples staged per tile (multiple of 64)
+  // outputs
+  float* traj;           // [G][H+1][S] or NULL
+  double* totals;        // [G][2] {sum, max} of q_base + q_iter over all ranks, or NULL
+  float* cost;           // [G]
+  float* dgdx;           // [H][S]
+  float* du;             // [H][A]
+  float* djdlam;         // [H]
+  float* u_star;         // [H][A]
+  float* fault_out;      // [1] or NULL: 0 / 1 copy of the sticky fault word next to the outputs the host reads
+  double* kl_out;        // [2] {sum p(log p - log c), sum c} over all ranks, or NULL
+};
+
+// process-wide switches of the fused evals (klerg_set_option)
+struct FusedOptions {
+  int overlap;      // consecutive evals are independent: no griddepcontrol.wait
+  int grid_limit;   // > 0: at most this many CTAs per launch (tests: two emulated ranks share one GPU)
+  int pdl;          // launch with the programmatic-stream-serialization attribute
+  int coop_probe;   // -1 unknown, 0 / 1: the cooperative attribute may be combined with it
+};
+extern FusedOptions g_fused_opt;
+
+// World-2 emulation on ONE GPU (tests): the two ranks' launches are recorded and run as one cooperative grid
+// whose first half acts as rank 0 and second half as rank 1 (separate launches that wait on one another are
+// not guaranteed to be co-resident).
+struct EmuState {
+  int active;
+  int have[2];
+  EvalArgs args[2];
+  int (*launch)(const EvalArgs&, const EvalArgs&, int, int, size_t, cudaStream_t);
+  int nblk, nthreads;
+  size_t smem;
+};
+extern EmuState g_emu;
+
+// block reduction of NQ doubles (fixed order); result valid in thread 0
+template <int NQ>
+__device__ __forceinline__ void block_reduce(const int (&kind)[NQ], double (&val)[NQ], double* sh_red /* [32*NQ] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const double v = warp_reduce(kind[q], val[q]);
+    if (lane == 0) sh_red[warp * NQ + q] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      double v = lane < nwarp ? sh_red[lane * NQ + q] : red_identity(kind[q]);
+      v = warp_reduce(kind[q], v);
+      if (lane == 0) val[q] = v;
+    }
+  }
+}
+
+// Block reduction of G pairs {a_g, b_g} in one go (two barriers in total instead of two per candidate):
+// kind_b = RED_MAX or RED_SUM for the second member; results for all g valid in thread 0.
+__device__ __forceinline__ void block_reduce_pairs(int G, int kind_b, double (&va)[FUSED_MAXG], double (&vb)[FUSED_MAXG],
+                                                   double* sh_red /* [32 * 2 * FUSED_MAXG] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    if (g < G) {
+      const double x = warp_reduce(RED_SUM, va[g]);
+      const double y = warp_reduce(kind_b, vb[g]);
+      if (lane == 0) {
+        sh_red[(warp * FUSED_MAXG + g) * 2 + 0] = x;
+        sh_red[(warp * FUSED_MAXG + g) * 2 + 1] = y;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g) {
+      if (g < G) {
+        double x = lane < nwarp ? sh_red[(lane * FUSED_MAXG + g) * 2 + 0] : 0.0;
+        double y = lane < nwarp ? sh_red[(lane * FUSED_MAXG + g) * 2 + 1] : red_identity(kind_b);
+        x = warp_reduce(RED_SUM, x);
+        y = warp_reduce(kind_b, y);
+        if (lane == 0) {
+          va[g] = x;
+          vb[g] = y;
+        }
+      }
+    }
+  }
+}
+
+// contiguous sample slice of CTA vblk of vnblk: [lo, hi) with lo % 8 == 0, hi <= ld
+__device__ __forceinline__ void cta_slice(int64_t N, int64_t ld, int vblk, int vnblk, int64_t& lo, int64_t& hi) {
+  int64_t per = (N + vnblk - 1) / vnblk;
+  per = (per + 7) & ~(int64_t)7;
+  lo = (int64_t)vblk * per;
+  hi = lo + per;
+  if (hi > ld) hi = ld;
+  if (lo > ld) lo = ld;
+}
+
+// Forward pair pass of one trajectory (T duplicated rows at sh_x2) over this CTA's slice:
+// v[i] = q_base[i] + inv_nu * sum_t psi; returns the slice's {sum, max} of v over i < N.
+template <int D, int P>
+__device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+                                                int64_t hi, double& tsum, double& tmax) {
+  constexpr int SPT = 2 * P;
+  for (int64_t i0 = lo + (int64_t)threadIdx.x * SPT; i0 < hi; i0 += (int64_t)blockDim.x * SPT) {
+    u64 s2[D][P], acc[P];
+    float emin[SPT];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if constexpr (P == 2) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+        s2[d][1] = pack2(s.z, s.w);
+      } else {
+        const float2 s = __ldg(reinterpret_cast<const float2*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+      }
+    }
+    float qb[SPT];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? a.q_base[i0 + q] : 0.f;
+#pragma unroll
+    for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
+    pair_forward<D, P, 0>(sh_x2, T, s2, acc, emin);
+    float o[SPT];
+#pragma unroll
+    for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+      const int64_t i = i0 + q;
+      float v = o[q] * a.k.inv_nu;
+      if (i < a.N) {
+        if (a.q_base) v += qb[q];
+        tsum += (double)v;
+        tmax = fmax(tmax, (double)v);
+      }
+      o[q] = v;
+    }
+    if constexpr (P == 2)
+      *reinterpret_cast<float4*>(v_out + i0) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      *reinterpret_cast<float2*>(v_out + i0) = make_float2(o[0], o[1]);
+  }
+}
+
+// Samples per thread-iteration: 2 (one packed pair) or 4.  A slice of n samples costs ceil(n / (threads * 2P)) * P
+// pair-iterations per thread; for slices of a few samples per thread the quantisation decides (e.g. 6757 samples on
+// 512 threads: 4 iterations of two pairs = 8, or 7 iterations of one pair = 7).
+__device__ __forceinline__ bool narrow_pairs(int64_t lo, int64_t hi) {
+  const int64_t n = hi - lo, bd = blockDim.x;
+  const int64_t it1 = (n + bd * 2 - 1) / (bd * 2), it2 = (n + bd * 4 - 1) / (bd * 4);
+  return it1 < 2 * it2 || it1 <= 1;
+}
+
+template <int D>
+__device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+                                              int64_t hi, double& tsum, double& tmax) {
+  if (narrow_pairs(lo, hi))
+    forward_slice_p<D, 1>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
+  else
+    forward_slice_p<D, 2>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
+}
+
+
+// Forward pair pass of G candidate trajectories over this CTA's slice: samples are loaded once per thread and swept
+// against every candidate (the per-candidate totals live in a small indexed array: two local-memory accesses per
+// H pairs); v[g][i] to HBM; the CTA's {sum, max} per candidate end up in s_in[2g], s_in[2g + 1].
+template <int D, int P>
+__device__ __forceinline__ void forward_candidates(const EvalArgs& a, const u64* s_x2, int G, int H, int64_t lo, int64_t hi,
+                                                   double* s_red, double* s_in) {
+  constexpr int SPT = 2 * P, DP = Row2<D>::DP;
+  const int tid = threadIdx.x;
+  double tsum[FUSED_MAXG], tmax[FUSED_MAXG];
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    tsum[g] = 0.0;
+    tmax[g] = -INFINITY;
+  }
+  for (int64_t i0 = lo + (int64_t)tid * SPT; i0 < hi; i0 += (int64_t)blockDim.x * SPT) {
+    u64 s2[D][P];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if constexpr (P == 2) {
+        const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+        s2[d][1] = pack2(s.z, s.w);
+      } else {
+        const float2 s = __ldg(reinterpret_cast<const float2*>(a.packed + (int64_t)d * a.ld + i0));
+        s2[d][0] = pack2(s.x, s.y);
+      }
+    }
+    float qb[SPT];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? a.q_base[i0 + q] : 0.f;
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      u64 acc[P];
+      float emin[SPT], o[SPT];
+#pragma unroll
+      for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
+      pair_forward<D, P, 0>(s_x2 + (size_t)g * H * DP, H, s2, acc, emin);
+#pragma unroll
+      for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
+      double ts = tsum[g], tm = tmax[g];
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        float v = o[q] * a.k.inv_nu;
+        if (i0 + q < a.N) {
+          v += qb[q];
+          ts += (double)v;
+          tm = fmax(tm, (double)v);
+        }
+        o[q] = v;
+      }
+      tsum[g] = ts;
+      tmax[g] = tm;
+      float* vp = a.v + (size_t)g * a.ld + i0;
+      if constexpr (P == 2)
+        *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
+      else
+        *reinterpret_cast<float2*>(vp) = make_float2(o[0], o[1]);
+    }
+  }
+  double ra[FUSED_MAXG], rb[FUSED_MAXG];
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    ra[g] = tsum[g];
+    rb[g] = tmax[g];
+  }
+  block_reduce_pairs(G, RED_MAX, ra, rb, s_red);
+  if (tid == 0) {
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g)
+      if (g < G) {
+        s_in[2 * g] = ra[g];
+        s_in[2 * g + 1] = rb[g];
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// shared-memory carve-up
+// ---------------------------------------------------------------------------
+// Row stride (floats) of the staged sample tiles: a compile-time constant so that the D+2 row addresses of a
+// tile are immediates off one base register (no address chain, fewer live registers in the pair loop).
+constexpr int TS_ROW = 2048;
+
+struct SmemPlan {
+  size_t u, traj, dbarr, P, rot, x2, xs, tile, part, red, misc, ll, total;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+constexpr size_t LL_SCRATCH_BYTES = sizeof(double) * (LL_BUF_VALS + 32);
+constexpr size_t MISC_BYTES = 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 32;
+
+template <int D>
+__host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, int nwarps, int WT) {
+  SmemPlan p{};
+  size_t o = 0;
+  p.u = o;     o = align16(o + sizeof(float) * H * A);
+  p.traj = o;  o = align16(o + sizeof(float) * (H + 1) * S);
+  p.dbarr = o; o = align16(o + sizeof(float) * H * S);
+  p.P = o;     o = align16(o + (roll ? sizeof(float) * H * A * A : 0));
+  p.rot = o;   o = align16(o + (roll ? sizeof(float) * rollout_rot_floats(1, H) : 0));  // kept for the finisher
+  p.x2 = o;    o = align16(o + sizeof(u64) * H * Row2<D>::DP);
+  p.xs = o;    o = align16(o + sizeof(float) * H * D);
+  // two TMA buffers of rows s_0..s_{D-1}, v -> w, p; the second one doubles as the staging area of meeting (1),
+  // and the finisher's adjoint works in the first
+  size_t tile = sizeof(float) * (size_t)2 * (D + 2) * TS_ROW;
+  const size_t adj = sizeof(double) * ((size_t)H * D + 2) + sizeof(float) * ((size_t)H * S + adjoint_scratch_floats(H, A));
+  if (tile < adj) tile = adj;
+  p.tile = o;  o = align16(o + tile);
+  p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
+  p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
+  p.misc = o;  o = align16(o + MISC_BYTES);
+  p.total = o;
+  return p;
+}
+static_assert(sizeof(float) * 3 * TS_ROW >= LL_SCRATCH_BYTES, "meeting staging must fit one tile buffer (D = 1)");
+
+// ---------------------------------------------------------------------------
+// gradient eval
+// ---------------------------------------------------------------------------
+// MIXED: one chunk per warp, the last a.nwide warps own WT+1 states and the others WT, so that H states tile
+// any warp count exactly (no idle state slots) and the warp count can be a multiple of the 4 SM sub-partitions.
+// vblk / vnblk: index of this CTA among the CTAs of its rank (= blockIdx.x / gridDim.x except in the
+// one-GPU emulation of two ranks).
+template <int D, int WT, bool MIXED>
+__device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk, const int vnblk, unsigned char* smem) {
+  constexpr int WTA = MIXED ? WT + 1 : WT;  // accumulator rows per warp
+  const int H = a.H, S = a.d.S, A = a.d.A;
+  const bool roll = a.d.kind == KLERG_DYN_ROLL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const SmemPlan sp = plan_grad<D>(H, S, A, roll, nwarps, WTA);
+  float* s_u = (float*)(smem + sp.u);
+  float* s_traj = (float*)(smem + sp.traj);
+  float* s_dbarr = (float*)(smem + sp.dbarr);
+  float* s_P = roll ? (float*)(smem + sp.P) : nullptr;
+  float* s_rot = (float*)(smem + sp.rot);
+  u64* s_x2 = (u64*)(smem + sp.x2);
+  float* s_xs = (float*)(smem + sp.xs);
+  float* s_tile = (float*)(smem + sp.tile);
+  float* s_part = (float*)(smem + sp.part);
+  double* s_red = (double*)(smem + sp.red);
+  int* s_flag = (int*)(smem + sp.misc);
+  unsigned* s_epoch = (unsigned*)(smem + sp.misc) + 1;
+  float* s_bsum = (float*)(smem + sp.misc) + 3;
+  constexpr int DP = Row2<D>::DP;
+  unsigned* ctrl = ws_fused_ctrl(a.ws);
+  void* me = a.peers.mail[a.peers.rank];
+  const int world = a.peers.world;
+  const bool finisher = vblk == vnblk - 1;
+
+  KLERG_STAMP_DECL;
+  KLERG_STAMP(0);
+  // ---- phase 0: rollout, states only (every CTA) ----------------------------------------------------
+  float* s_x0 = (float*)(smem + sp.misc) + 4;  // [S] (+ [9] R0)
+  unsigned long long* s_bar = (unsigned long long*)(smem + ((sp.misc + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 7) & ~(size_t)7));  // [2]
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (!a.independent) pdl_wait_prior_grids();  // the previous launch may have produced this one's inputs
+  if (tid == 0) {
+    s_epoch[0] = ld_acquire_u32(mb_hdr(me));      // launches so far on this mailbox
+    s_epoch[1] = ld_acquire_u32(mb_hdr(me) + 1);  // gather exchanges so far
+  }
+  for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
+  if (tid < S) s_x0[tid] = a.x0[tid];
+  if (a.R0 && tid >= 32 && tid < 41) s_x0[KLERG_MAX_S + tid - 32] = a.R0[tid - 32];
+  __syncthreads();
+  KLERG_STAMP(8);
+  rollout_block(a.d, a.bar, s_x0, a.R0 ? s_x0 + KLERG_MAX_S : nullptr, s_u, 1, H, s_traj, nullptr, nullptr, s_rot, (float*)s_red,
+                s_bsum, nullptr, 1);
+  KLERG_STAMP(9);
+  const unsigned epoch = s_epoch[0], xc = s_epoch[1];
+  for (int e = tid; e < H * DP; e += blockDim.x) {
+    const int t = e / DP, d = e - t * DP;
+    float v = 0.f;
+    if (d < D) {
+      v = s_traj[t * S + a.k.explr[d]] * a.k.a[d];  // pre-step states (Robot.forward, klerg.py:419-431)
+      s_xs[t * D + d] = v;
+    }
+    s_x2[e] = pack2(v, v);
+  }
+  if (vblk == 0 && a.traj)
+    for (int e = tid; e < (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
+  __syncthreads();
+
+  KLERG_STAMP(1);
+  // ---- phase 1: forward pair pass, slice totals -------------------------------------------------
+  int64_t lo, hi;
+  cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
+  double* s_world = s_red + 32 * 2;  // [2] all ranks
+  double* s_in = s_world + 2;        // [2] this CTA
+  {
+    double tsum = 0.0, tmax = -INFINITY;
+    forward_slice<D>(a, s_x2, H, a.v, lo, hi, tsum, tmax);
+    const int kinds[2] = {RED_SUM, RED_MAX};
+    double vals[2] = {tsum, tmax};
+    block_reduce<2>(kinds, vals, s_red);
+    if (tid == 0) {
+      s_in[0] = vals[0];
+      s_in[1] = vals[1];
+    }
+  }
+  KLERG_STAMP(2);
+  // The first sample tile of the gradient pass (samples, this CTA's own v, p) does not depend on the grid-wide
+  // totals: its TMA copies are issued now and land while the CTAs meet.
+  fence_proxy_async();  // v was written with ordinary stores and is read back by TMA
+  __syncthreads();
+  if (tid == 0 && hi > lo) {
+    const unsigned bytes = 4u * (unsigned)min((int64_t)a.ts, hi - lo);
+    mbar_expect_tx(&s_bar[0], (D + 2) * bytes);
+#pragma unroll
+    for (int d = 0; d < D; ++d) tma_bulk_g2s(s_tile + (size_t)d * TS_ROW, a.packed + (int64_t)d * a.ld + lo, bytes, &s_bar[0]);
+    tma_bulk_g2s(s_tile + (size_t)D * TS_ROW, a.v + lo, bytes, &s_bar[0]);
+    tma_bulk_g2s(s_tile + (size_t)(D + 1) * TS_ROW, a.p + lo, bytes, &s_bar[0]);
+  }
+  // ---- meeting (1): {sum, max} over every CTA of every rank ----------------------------------------
+  // Slots of this launch's first gather exchange (number xc) are about to be reused from exchange xc - 2: wait until
+  // that one has been consumed (always true in practice; makes the slot reuse safe by construction).
+  if (tid == 0) ll_wait_exchange_free(me, xc, ctrl);
+  ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2, 0x2u, s_in, s_world, (double*)(s_tile + (size_t)(D + 2) * TS_ROW), ctrl);
+  if (vblk == 0 && tid == 0) {
+    // every CTA holds epoch / xc in registers by now: bump the counters for the next launch, which may start
+    // as soon as all CTAs have passed this point
+    st_release_u32(mb_hdr(me) + 1, xc + (unsigned)a.K);
+    st_release_u32(mb_hdr(me), epoch + 1u);
+    __threadfence();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  KLERG_STAMP(3);
+  const double vsum = s_world[0];
+  const double vmax = s_world[1];
+  if (vblk == 0 && tid == 0 && a.totals) {
+    a.totals[0] = vsum;
+    a.totals[1] = vmax;
+  }
+  const float vsum_f = (float)vsum;  // the reference divides by the fp32 sum
+  const float maxc_f = (float)fmax(vmax / vsum, (double)a.floor);
+
+  // ---- phase 2: importance ratio + gradient pair pass ----------------------------------------------
+  const int ts = a.ts;
+  // loop-invariant launch parameters of the pair loop, pinned through shared memory (see pin_params)
+  if (tid == 0) s_flag[4 + KLERG_MAX_S + 9] = a.nsub * 64;
+  __syncthreads();
+  const int pb_step = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 9];
+  const int HD = H * D;
+  const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
+  int tile_seq = 0;  // tiles streamed so far in this launch (same in every thread)
+  for (int kt = 0; kt < a.K; ++kt) {  // belief targets: the forward pass above is shared, p_k differs
+  const float* p_k = a.p + (int64_t)kt * a.p_stride;
+  const unsigned xnum = xc + (unsigned)kt;       // number of this target's gather exchange
+  const int xpar = xnum & 1u;
+  const unsigned xtag = ll_tag(xnum, 0x80u);
+  double kl_a = 0.0, kl_c = 0.0;
+  if (kt > 0 && tid == 0) ll_wait_exchange_free(me, xnum, ctrl);  // ordered before the slot stores by the barriers below
+  for (int r = 0; r < a.rounds; ++r) {
+    int cw = warp % a.nchr, sub = warp / a.nchr;
+    int t0 = (r * a.nchr + cw) * WT, my_wt = WT;
+    bool active = sub < a.nsub && t0 < H;
+    if (MIXED) {
+      const int narrow = nwarps - a.nwide;
+      const bool wide = warp >= narrow;
+      t0 = warp * WT + (wide ? warp - narrow : 0);
+      my_wt = WT + (wide ? 1 : 0);
+      sub = 0;
+      active = true;
+    }
+    u64 xs2[WTA][D], acc[WTA][D];
+#pragma unroll
+    for (int k = 0; k < WTA; ++k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float x = (active && k < my_wt && t0 + k < H) ? s_xs[(t0 + k) * D + d] : 0.f;
+        xs2[k][d] = pack2(x, x);
+        acc[k][d] = pack2(0.f, 0.f);
+      }
+    // Sample tiles stream global -> shared one tile ahead of the pair math:
+    // rows s_0..s_{D-1} (scaled samples), q_base + q_iter (turned into the importance ratio in place), p.
+    const int nt = (int)((hi - lo + ts - 1) / ts);
+    // One thread issues the D+2 row copies of a tile as TMA bulk copies (contiguous runs, no descriptors) that
+    // complete on the tile buffer's mbarrier; everybody else keeps computing.  Tile g of this launch uses buffer
+    // g & 1 and the (g >> 1)-th phase of its barrier.
+    auto issue_tile = [&](int k) {
+      if (tid == 0) {
+        const int gidx = tile_seq + k;
+        float* buf = s_tile + (size_t)(gidx & 1) * (D + 2) * TS_ROW;
+        const int64_t base = lo + (int64_t)k * ts;
+        const unsigned bytes = 4u * (unsigned)min((int64_t)ts, hi - base);  // multiple of 16
+        fence_proxy_async();  // the buffer was last written with ordinary stores (importance ratio, padding)
+        mbar_expect_tx(&s_bar[gidx & 1], (D + 2) * bytes);
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          tma_bulk_g2s(buf + (size_t)d * TS_ROW, a.packed + (int64_t)d * a.ld + base, bytes, &s_bar[gidx & 1]);
+        tma_bulk_g2s(buf + (size_t)D * TS_ROW, a.v + base, bytes, &s_bar[gidx & 1]);
+        tma_bulk_g2s(buf + (size_t)(D + 1) * TS_ROW, p_k + base, bytes, &s_bar[gidx & 1]);
+      }
+    };
+    if (nt > 0 && tile_seq > 0) issue_tile(0);  // the very first tile of the launch was issued before the meeting point
+    for (int k = 0; k < nt; ++k) {
+      const int gidx = tile_seq + k;
+      float* buf = s_tile + (size_t)(gidx & 1) * (D + 2) * TS_ROW;
+      const int64_t base = lo + (int64_t)k * ts;
+      const int cnt = (int)min((int64_t)ts, hi - base);
+      const int cnt64 = (cnt + 63) & ~63;
+      float* wrow = buf + (size_t)D * TS_ROW;
+      const float* prow = buf + (size_t)(D + 1) * TS_ROW;
+      KLERG_SPIN_UNTIL(mbar_try_wait(&s_bar[gidx & 1], (unsigned)(gidx >> 1) & 1u), ctrl)
+      for (int c = tid; c < (cnt64 >> 2); c += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = (c << 2) + q;
+          const int64_t i = base + e;
+          float w = 0.f;
+          if (e < cnt && i < a.N) {
+            const float cc = fmaxf(__fdividef(wrow[e], vsum_f), a.floor);
+            const float pi = prow[e];
+            w = __fdividef(pi * maxc_f, cc);  // p/q with q = c / max c  (klerg.py:436)
+            if (want_kl && r == 0) {
+              kl_a += (double)(pi * (logf(pi) - logf(cc)));
+              kl_c += (double)cc;
+            }
+          } else if (e >= cnt) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) buf[(size_t)d * TS_ROW + e] = 0.f;
+          }
+          wrow[e] = w;
+        }
+      }
+      __syncthreads();  // tile k is ready for everyone; everyone is done with tile k-1
+      if (k + 1 < nt) issue_tile(k + 1);
+      if (active) {
+        for (int pb = sub * 64; pb < cnt64; pb += pb_step) {
+          const int i = pb + 2 * lane;
+          u64 s2[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TS_ROW + i]);
+          const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
+          pair_gradient<D, WTA>(xs2, s2, w2, acc, my_wt == WTA);
+        }
+      }
+    }
+    tile_seq += nt;
+    __syncthreads();
+    // lanes -> warp sums -> CTA partial for this round's states
+#pragma unroll
+    for (int k = 0; k < WTA; ++k)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float x, y;
+        unpack2(acc[k][d], x, y);
+        const float v = warp_sum_f(x + y);
+        if (lane == 0) s_part[(warp * WTA + k) * D + d] = v;
+      }
+    __syncthreads();
+    // this CTA's partial of gradient entry e goes to slot [e][vblk] as ONE tagged word (fp32 value + tag)
+    if (MIXED) {
+      const int narrow = nwarps - a.nwide, narrow_states = narrow * WT;
+      for (int e = tid; e < HD; e += blockDim.x) {
+        const int t = e / D, d = e - t * D;
+        int w, k;
+        if (t < narrow_states) {
+          w = t / WT;
+          k = t - w * WT;
+        } else {
+          const int tt = t - narrow_states;
+          w = narrow + tt / (WT + 1);
+          k = tt - (w - narrow) * (WT + 1);
+        }
+        ll_store_f32(mb_gp(me, xpar, e) + vblk, s_part[(w * WTA + k) * D + d], xtag);
+      }
+    } else
+    for (int e = tid; e < a.nchr * WT * D; e += blockDim.x) {
+      const int c = e / (WT * D), kd = e - c * (WT * D);
+      const int t = (r * a.nchr + c) * WT + kd / D;
+      if (t < H) {
+        float v = 0.f;
+        for (int sb = 0; sb < a.nsub; ++sb) v += s_part[((sb * a.nchr + c) * WT) * D + kd];
+        ll_store_f32(mb_gp(me, xpar, t * D + kd % D) + vblk, v, xtag);
+      }
+    }
+  }
+  if (want_kl) {
+    const int kinds[2] = {RED_SUM, RED_SUM};
+    double vals[2] = {kl_a, kl_c};
+    block_reduce<2>(kinds, vals, s_red);
+    if (tid == 0) {
+      ll_store(mb_kl(me, xpar, vblk), vals[0], xtag);
+      ll_store(mb_kl(me, xpar, vblk) + 2, vals[1], xtag);
+    }
+  }
+
+  // ---- phase 3: warps spread over the grid add the CTA partials of one gradient entry each (fixed order) and
+  //      hand the sum to every rank; the finisher CTA collects the H*D sums of all ranks and runs the adjoint ----
+  KLERG_STAMP(4);
+  for (int e = vblk + vnblk * warp; e < HD; e += vnblk * nwarps) {
+    const u64* row = mb_gp(me, xpar, e);
+    double v = 0.0;
+    for (int b = lane; b < vnblk; b += 32) {
+      float x = 0.f;
+      KLERG_SPIN_UNTIL(ll_try_load_f32(row + b, xtag, x), ctrl)
+      v += (double)x;
+    }
+    v = warp_reduce(RED_SUM, v);
+    if (lane < world) ll_store(mb_gb(a.peers.mail[lane], xpar, a.peers.rank) + 2 * e, v, xtag);
+  }
+  if (!finisher) continue;
+  KLERG_STAMP(5);
+  if (kt == 0) {
+    // what only the adjoint needs: linearisation blocks, dbarr, barrier sum
+    __syncthreads();
+    rollout_block(a.d, a.bar, s_x0, a.R0 ? s_x0 + KLERG_MAX_S : nullptr, s_u, 1, H, s_traj, s_dbarr, s_P, s_rot, (float*)s_red,
+                  s_bsum, nullptr, 2);
+  }
+  __syncthreads();
+  double* s_val = (double*)s_tile;               // [HD + 2]
+  float* s_g = (float*)(s_val + HD + 2);         // [H][S]
+  float* s_scr = s_g + H * S;                    // adjoint scratch
+  if (want_kl) {
+    // KL terms of this rank: CTA partials in CTA order, then to every rank like a gradient entry
+    double* s_stage = (double*)(s_tile + (size_t)(D + 2) * TS_ROW);
+    for (int idx = tid; idx < vnblk * 2; idx += blockDim.x) {
+      double x = 0.0;
+      KLERG_SPIN_UNTIL(ll_try_load(mb_kl(me, xpar, idx >> 1) + 2 * (idx & 1), xtag, x), ctrl)
+      s_stage[idx] = x;
+    }
+    __syncthreads();
+    ll_reduce_staged(s_stage, vnblk, 2, 0u, s_stage + LL_BUF_VALS - 2, s_stage + LL_BUF_VALS);
+    if (tid < world * 2) {
+      const int rr = tid >> 1, i = tid & 1;
+      ll_store(mb_gb(a.peers.mail[rr], xpar, a.peers.rank) + 2 * (HD + i), s_stage[LL_BUF_VALS - 2 + i], xtag);
+    }
+  }
+  for (int e = tid; e < HD + (want_kl ? 2 : 0); e += blockDim.x) {
+    double v = 0.0;
+    for (int rr = 0; rr < world; ++rr) {
+      double x = 0.0;
+      KLERG_SPIN_UNTIL(ll_try_load(mb_gb(me, xpar, rr) + 2 * e, xtag, x), ctrl)
+      v += x;
+    }
+    s_val[e] = v;
+  }
+  if (!want_kl && tid == 0) {
+    s_val[HD] = 0.0;
+    s_val[HD + 1] = 1.0;
+  }
+  KLERG_STAMP(6);
+  for (int e = tid; e < H * S; e += blockDim.x) s_g[e] = 0.f;
+  __syncthreads();
+  for (int e = tid; e < HD; e += blockDim.x) {
+    const int d = e % D;
+    s_g[(e / D) * S + a.k.explr[d]] = (float)(s_val[e] * (double)a.k.gfac[d]);
+  }
+  __syncthreads();
+  for (int e = tid; e < H * S; e += blockDim.x) {
+    const float g = s_g[e];
+    a.dgdx[(size_t)kt * H * S + e] = g;
+    s_g[e] = g - s_dbarr[e];
+  }
+  __syncthreads();
+  adjoint_block(a.d, a.ap, H, s_g, s_P, s_traj, s_u, s_scr, a.du + (size_t)kt * H * A, a.djdlam + (size_t)kt * H,
+                a.u_star + (size_t)kt * H * A);
+  if (tid == 0) {
+    const double sa = s_val[HD], sc = s_val[HD + 1];
+    if (a.kl_out) {
+      a.kl_out[2 * kt] = sa;
+      a.kl_out[2 * kt + 1] = sc;
+    }
+    if (a.cost) {
+      const double spv = a.p_stats[kt];
+      // KL of the PRE-step footprint (what backward() differentiates) + barrier of the post-step states
+      a.cost[kt] = (float)(sa / spv - log(spv) + log(sc)) + *s_bsum;
+    }
+    // this exchange is consumed: its slots may be reused two exchanges from now (in order, one finisher at a time)
+    unsigned* xdone = mb_hdr(me) + 2;
+    KLERG_SPIN_UNTIL(ld_acquire_u32(xdone) == xnum, ctrl)
+    __threadfence();
+    st_release_u32(xdone, xnum + 1u);
+    if (kt == a.K - 1 && a.fault_out) *a.fault_out = ctrl[5] ? 1.f : 0.f;
+#ifdef KLERG_STAMPS
+    // phase stamps of the finisher (SM cycles since its start): profiling aid
+    KLERG_STAMP(7);
+    long long* dbg = (long long*)(ctrl + 16);
+    for (int i = 0; i < 10; ++i) dbg[i] = stamp[i] - stamp[0];
+    for (int i = 0; i < 8; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];
+#endif
+  }
+  __syncthreads();  // the finisher reuses its tile area for the next target
+  }  // targets
+}
+
+template <int D, int WT, int MAXT, bool MIXED>
+__global__ void __launch_bounds__(MAXT) eval_grad_kernel(const __grid_constant__ EvalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  eval_grad_body<D, WT, MIXED>(a, (int)blockIdx.x, (int)gridDim.x, smem);
+}
+// two ranks on one GPU (tests): CTAs [0, nb) act as rank 0 with a0, CTAs [nb, 2 nb) as rank 1 with a1
+template <int D, int WT, int MAXT, bool MIXED>
+__global__ void __launch_bounds__(MAXT) eval_grad_emu_kernel(const __grid_constant__ EvalArgs a0,
+                                                             const __grid_constant__ EvalArgs a1, const int nb) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if ((int)blockIdx.x < nb)
+    eval_grad_body<D, WT, MIXED>(a0, (int)blockIdx.x, nb, smem);
+  else
+    eval_grad_body<D, WT, MIXED>(a1, (int)blockIdx.x - nb, nb, smem);
+}
+
+// ---------------------------------------------------------------------------
+// cost eval of G <= FUSED_MAXG candidates
+// ---------------------------------------------------------------------------
+template <int D>
+__host__ __device__ inline SmemPlan plan_cost(int G, int H, int S, int A, bool roll) {
+  SmemPlan p{};
+  size_t o = 0;
+  p.u = o;    o = align16(o + sizeof(float) * (size_t)G * H * A);
+  p.traj = o; o = align16(o + sizeof(float) * (size_t)G * (H + 1) * S);
+  p.x2 = o;   o = align16(o + sizeof(u64) * (size_t)G * H * Row2<D>::DP);
+  p.tile = o; o = align16(o + (roll ? sizeof(float) * rollout_rot_floats(G, H) : 0));
+  p.red = o;  o = align16(o + sizeof(double) * (32 * 2 * FUSED_MAXG + 4 * FUSED_MAXG));
+  p.misc = o; o = align16(o + 64 + sizeof(float) * FUSED_MAXG);
+  p.ll = o;   o = align16(o + LL_SCRATCH_BYTES);
+  p.total = o;
+  return p;
+}
+
+template <int D>
+__device__ __forceinline__ void eval_cost_body(const EvalArgs& a, const int vblk, const int vnblk, unsigned char* smem) {
+  const int H = a.H, S = a.d.S, A = a.d.A, G = a.G;
+  const int tid = threadIdx.x;
+  const SmemPlan sp = plan_cost<D>(G, H, S, A, a.d.kind == KLERG_DYN_ROLL);
+  float* s_u = (float*)(smem + sp.u);
+  float* s_traj = (float*)(smem + sp.traj);
+  u64* s_x2 = (u64*)(smem + sp.x2);
+  double* s_red = (double*)(smem + sp.red);
+  double* s_world = s_red + 32 * 2 * FUSED_MAXG;  // [2G] all ranks
+  double* s_in = s_world + 2 * FUSED_MAXG;        // [2G] this CTA
+  unsigned* s_epoch = (unsigned*)(smem + sp.misc) + 1;
+  float* s_bsum = (float*)(smem + sp.misc + 64);
+  double* s_ll = (double*)(smem + sp.ll);
+  constexpr int DP = Row2<D>::DP;
+  unsigned* ctrl = ws_fused_ctrl(a.ws);
+  void* me = a.peers.mail[a.peers.rank];
+  const int world = a.peers.world;
+
+  if (!a.independent) pdl_wait_prior_grids();
+  if (tid == 0) {
+    s_epoch[0] = ld_acquire_u32(mb_hdr(me));
+    s_epoch[1] = ld_acquire_u32(mb_hdr(me) + 1);
+  }
+  for (int e = tid; e < G * H * A; e += blockDim.x) s_u[e] = a.u[e];
+  __syncthreads();
+  rollout_block(a.d, a.bar, a.x0, a.R0, s_u, G, H, s_traj, nullptr, nullptr, (float*)(smem + sp.tile), (float*)s_red,
+                s_bsum, nullptr);
+  const unsigned epoch = s_epoch[0], xc = s_epoch[1];
+  for (int e = tid; e < G * H * DP; e += blockDim.x) {
+    const int g = e / (H * DP), r = e - g * (H * DP);
+    const int t = r / DP, d = r - t * DP;
+    float v = 0.f;
+    if (d < D) v = s_traj[((size_t)g * (H + 1) + t + 1) * S + a.k.explr[d]] * a.k.a[d];  // post-step states (klerg.py:688-691)
+    s_x2[e] = pack2(v, v);
+  }
+  if (vblk == 0 && a.traj)
+    for (int e = tid; e < G * (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
+  __syncthreads();
+
+  int64_t lo, hi;
+  cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
+  if (narrow_pairs(lo, hi))
+    forward_candidates<D, 1>(a, s_x2, G, H, lo, hi, s_red, s_in);
+  else
+    forward_candidates<D, 2>(a, s_x2, G, H, lo, hi, s_red, s_in);
+  // meeting (1): {sum, max} per candidate over every CTA of every rank
+  if (tid == 0) ll_wait_exchange_free(me, xc, ctrl);
+  ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2 * G, 0xAAAAu, s_in, s_world, s_ll, ctrl);
+  if (vblk == 0 && tid == 0) {
+    st_release_u32(mb_hdr(me) + 1, xc + 1u);
+    st_release_u32(mb_hdr(me), epoch + 1u);
+    __threadfence();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  if (vblk == 0 && tid < 2 * G && a.totals) a.totals[tid] = s_world[tid];
+
+  // KL partials: sum_i p_i (log p_i - log c_i), sum_i c_i   (klerg.py:694-699 in closed form)
+  // Four samples per thread-iteration (128-bit loads of v and p), reciprocal of the normaliser and lg2-based
+  // logarithms: the pass is instruction-bound (IEEE division + logf cost ~60 instructions per sample and candidate,
+  // this form ~12); the cost changes by < 1e-6 relative, far inside the 1e-4 parity tolerance.
+  float rvs[FUSED_MAXG], maxc[FUSED_MAXG];
+  double sa[FUSED_MAXG], sc[FUSED_MAXG];
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    sa[g] = sc[g] = 0.0;
+    rvs[g] = maxc[g] = 1.f;
+    if (g < G) {
+      const double vsum = s_world[2 * g], vmax = s_world[2 * g + 1];
+      const float vs = (float)vsum;
+      rvs[g] = 1.f / vs;
+      maxc[g] = fmaxf((float)vmax / vs, a.floor);
+    }
+  }
+  const int64_t hiN = hi < a.N ? hi : a.N;
+  for (int64_t i0 = lo + (int64_t)tid * 4; i0 < hiN; i0 += (int64_t)blockDim.x * 4) {
+    float pv[4], lp[4];
+    if (i0 + 3 < a.N) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(a.p + i0));
+      pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pv[q] = (i0 + q < a.N) ? a.p[i0 + q] : 1.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (pv[q] != pv[q]) pv[q] = 1e-6f;
+      lp[q] = __logf(pv[q]);
+    }
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g) {
+      if (g < G) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(a.v + (size_t)g * a.ld + i0));
+        const float vv[4] = {t.x, t.y, t.z, t.w};
+        float fa = 0.f, fc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (i0 + q < hiN) {
+            float c = fmaxf(vv[q] * rvs[g], a.floor);
+            if (c != c) c = 1e-6f * maxc[g];  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
+            fa = fmaf(pv[q], lp[q] - __logf(c), fa);
+            fc += c;
+          }
+        }
+        sa[g] += (double)fa;
+        sc[g] += (double)fc;
+      }
+    }
+  }
+  block_reduce_pairs(G, RED_SUM, sa, sc, s_red);
+  // gather: the CTA's 2G KL terms as tagged values; the finisher adds them in CTA order, then in rank order
+  const int xpar = xc & 1u;
+  const unsigned xtag = ll_tag(xc, 0x80u);
+  if (tid == 0) {
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g)
+      if (g < G) {
+        ll_store(mb_kl(me, xpar, vblk) + 4 * g, sa[g], xtag);
+        ll_store(mb_kl(me, xpar, vblk) + 4 * g + 2, sc[g], xtag);
+      }
+  }
+  if (vblk != vnblk - 1) return;
+  const int nv = 2 * G;
+  for (int idx = tid; idx < vnblk * nv; idx += blockDim.x) {
+    const int b = idx / nv, i = idx - b * nv;
+    double x = 0.0;
+    KLERG_SPIN_UNTIL(ll_try_load(mb_kl(me, xpar, b) + 2 * i, xtag, x), ctrl)
+    s_ll[idx] = x;
+  }
+  __syncthreads();
+  double* s_val = s_world;  // [2G] (the totals are in registers by now)
+  ll_reduce_staged(s_ll, vnblk, nv, 0u, s_val, s_ll + LL_BUF_VALS);
+  if (world > 1) {
+    for (int t = tid; t < world * nv; t += blockDim.x) {
+      const int r = t / nv, i = t - r * nv;
+      ll_store(mb_gb(a.peers.mail[r], xpar, a.peers.rank) + 2 * i, s_val[i], xtag);
+    }
+    __syncthreads();
+    if (tid < nv) {
+      double v = 0.0;
+      for (int r = 0; r < world; ++r) {
+        double x = 0.0;
+        KLERG_SPIN_UNTIL(ll_try_load(mb_gb(me, xpar, r) + 2 * tid, xtag, x), ctrl)
+        v += x;
+      }
+      s_val[tid] = v;
+    }
+    __syncthreads();
+  }
+  if (tid < G) {
+    const double spv = a.p_stats[0];
+    const double dkl = s_val[2 * tid] / spv - log(spv) + log(s_val[2 * tid + 1]);
+    a.cost[tid] = (float)dkl + s_bsum[tid];
+  }
+  if (tid == 0) {
+    unsigned* xdone = mb_hdr(me) + 2;
+    KLERG_SPIN_UNTIL(ld_acquire_u32(xdone) == xc, ctrl)
+    __threadfence();
+    st_release_u32(xdone, xc + 1u);
+    if (a.fault_out) *a.fault_out = ctrl[5] ? 1.f : 0.f;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(512) eval_cost_kernel(const __grid_constant__ EvalArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  eval_cost_body<D>(a, (int)blockIdx.x, (int)gridDim.x, smem);
+}
+template <int D>
+__global__ void __launch_bounds__(512) eval_cost_emu_kernel(const __grid_constant__ EvalArgs a0, const __grid_constant__ EvalArgs a1,
+                                                            const int nb) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if ((int)blockIdx.x < nb)
+    eval_cost_body<D>(a0, (int)blockIdx.x, nb, smem);
+  else
+    eval_cost_body<D>(a1, (int)blockIdx.x - nb, nb, smem);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct GradSchedule {
+  int wt, nwarps, nchr, nsub, rounds;
+  double eff;
+  bool mixed;
+  int nwide;
+};
+
+static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
+
+// Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
+// CTA's warps with as few idle slots as possible.
+static GradSchedule plan_schedule(int D, int H) {
+  if (D >= 4) {
+    // mixed schedule: 16 warps (4 per SM sub-partition, 128 registers), H = q*16 + r -> r warps own q+1 states.
+    // Needs q >= 2 (fewer states per warp would re-read the staged samples too often for the shared-memory bandwidth).
+    const int nw = 16, q = H / nw, r = H % nw, wtmax = D == 4 ? 5 : 4;
+    if (q >= 2 && r > 0 && q + 1 <= wtmax) {
+      GradSchedule m{};
+      m.wt = q; m.nwarps = nw; m.nchr = nw; m.nsub = 1; m.rounds = 1; m.eff = 1.0; m.mixed = true; m.nwide = r;
+      return m;
+    }
+  }
+  const int maxw = grad_max_warps(D);
+  const int wts_small[5] = {5, 4, 3, 2, 1};
+  const int wts_big[3] = {3, 2, 1};
+  const int* wts = D <= 4 ? wts_small : wts_big;
+  const int nw = D <= 4 ? 5 : 3;
+  GradSchedule best{};
+  best.eff = -1.0;
+  for (int i = 0; i < nw; ++i) {
+    const int wt = wts[i];
+    const int nch = (H + wt - 1) / wt;
+    GradSchedule s{};
+    s.wt = wt;
+    if (nch <= maxw) {
+      s.rounds = 1;
+      s.nchr = nch;
+    } else {
+      s.rounds = (nch + maxw - 1) / maxw;
+      s.nchr = (nch + s.rounds - 1) / s.rounds;
+    }
+    s.nsub = maxw / s.nchr;
+    s.nwarps = s.nchr * s.nsub;
+    // useful pair slots / issued pair slots, discounted when few warps are resident or the tile is restaged
+    s.eff = (double)H / ((double)s.rounds * s.nchr * wt) * (0.5 + 0.5 * s.nwarps / maxw) / (1.0 + 0.02 * (s.rounds - 1));
+    if (s.eff > best.eff + 1e-9) best = s;
+  }
+  return best;
+}
+
+
+template <int DUMMY>
+__global__ void fused_probe_kernel() {}
+
+// Launch of a fused eval: programmatic stream serialization (the next fused eval may start while this one's
+// finisher is still busy) and, where the driver accepts the combination, the cooperative attribute (all CTAs
+// co-resident: they wait for one another).  Without it co-residency holds by construction: the grid never
+// exceeds what the device holds at once (pick_grid / resident_ctas) and a launch only waits for CTAs of earlier
+// launches, which never wait for it.
+template <typename K, typename... Args>
+static int fused_launch(K kernel, int nblk, int nthreads, size_t smem, cudaStream_t stream, const char* what, bool force_coop,
+                        Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)nblk);
+  cfg.blockDim = dim3((unsigned)nthreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  const bool pdl = g_fused_opt.pdl && !force_coop;
+  if (pdl && g_fused_opt.coop_probe < 0) {
+    // once per process: may the two attributes be combined?
+    cudaLaunchConfig_t pc{};
+    pc.gridDim = dim3(1);
+    pc.blockDim = dim3(32);
+    pc.stream = stream;
+    cudaLaunchAttribute pa[2];
+    pa[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pa[0].val.programmaticStreamSerializationAllowed = 1;
+    pa[1].id = cudaLaunchAttributeCooperative;
+    pa[1].val.cooperative = 1;
+    pc.attrs = pa;
+    pc.numAttrs = 2;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      const cudaError_t pe = cudaLaunchKernelEx(&pc, fused_probe_kernel<0>);
+      g_fused_opt.coop_probe = pe == cudaSuccess ? 1 : 0;
+      cudaGetLastError();
+    }
+  }
+  if (pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (!pdl || g_fused_opt.coop_probe == 1) {
+    attrs[na].id = cudaLaunchAttributeCooperative;
+    attrs[na].val.cooperative = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed (grid %d x %d threads, %zu B smem): %s", what, nblk, nthreads, smem, cudaGetErrorString(e));
+    cudaGetLastError();
+    return -4;
+  }
+  return check_launch(what);
+}
+
+// resident CTAs per SM for a kernel/block/smem combination (cached per kernel pointer + shape).
+// The dynamic shared-memory limit of a kernel is only ever raised.
+template <typename K>
+static int resident_ctas(K kernel, int nthreads, size_t smem) {
+  struct Key {
+    const void* k;
+    int t;
+    size_t s;
+    int n;
+  };
+  static Key cache[64];
+  static int ncache = 0;
+  static const void* raised_k[64];
+  static size_t raised_s[64];
+  static int nraised = 0;
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].k == (const void*)kernel && cache[i].t == nthreads && cache[i].s == smem) return cache[i].n;
+  if (smem > 48 * 1024) {
+    int slot = -1;
+    for (int i = 0; i < nraised; ++i)
+      if (raised_k[i] == (const void*)kernel) slot = i;
+    if (slot < 0 && nraised < 64) {
+      slot = nraised++;
+      raised_k[slot] = (const void*)kernel;
+      raised_s[slot] = 0;
+    }
+    if (slot < 0 || raised_s[slot] < smem) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (slot >= 0) raised_s[slot] = smem;
+    }
+  }
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, nthreads, smem) != cudaSuccess) n = 0;
+  cudaGetLastError();
+  if (ncache < 64) cache[ncache++] = Key{(const void*)kernel, nthreads, smem, n};
+  return n;
+}
+
+
+// CTAs of a fused eval: at least min_samples_per_cta samples each, at most what the device holds at once.  A grid
+// that would fill every SM leaves one free: the finisher CTA of the previous eval is still running when the next
+// eval's CTAs start (programmatic dependent launch), and with a free SM none of them has to wait for it.
+static int pick_grid(int64_t N, int per_sm, int min_samples_per_cta) {
+  int64_t nblk = (N + min_samples_per_cta - 1) / min_samples_per_cta;
+  int64_t cap = (int64_t)sm_count() * per_sm;
+  if (g_fused_opt.pdl && cap > 8) cap -= 1;
+  if (cap > LL_MAXBLK) cap = LL_MAXBLK;
+  if (g_fused_opt.grid_limit > 0 && cap > g_fused_opt.grid_limit) cap = g_fused_opt.grid_limit;
+  if (nblk > cap) nblk = cap;
+  if (nblk < 1) nblk = 1;
+  return (int)nblk;
+}
+
+// samples that decide the grid: the largest shard, so that every rank launches the same number of CTAs
+static int64_t grid_samples(const EvalArgs& a, int64_t n_max) { return n_max > a.N ? n_max : a.N; }
+
+template <int D, int WT, bool MIXED>
+static int launch_grad_emu(const EvalArgs& a0, const EvalArgs& a1, int nblk, int nthreads, size_t smem, cudaStream_t stream) {
+  constexpr int MAXT = MIXED ? 512 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
+  auto kernel = eval_grad_emu_kernel<D, WT, MAXT, MIXED>;
+  if (resident_ctas(kernel, nthreads, smem) < 1) { set_error("emulated eval_gradient: kernel does not fit on an SM"); return -4; }
+  return fused_launch(kernel, 2 * nblk, nthreads, smem, stream, "eval_grad_emu_kernel", true, a0, a1, nblk);
+}
+
+template <int D, int WT, bool MIXED = false>
+static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, int64_t n_max, cudaStream_t stream) {
+  constexpr int MAXT = MIXED ? 512 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
+  auto kernel = eval_grad_kernel<D, WT, MAXT, MIXED>;
+  const int nthreads = s.nwarps * 32;
+  const bool roll = a.d.kind == KLERG_DYN_ROLL;
+  // tile: up to 2048 samples, but no more than one CTA's slice at full grid
+  int64_t per = (a.N + sm_count() - 1) / sm_count();
+  int ts = 2048;
+  while (ts > 64 && ts / 2 >= per) ts /= 2;
+  a.ts = ts;
+  a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds; a.nwide = s.nwide;
+  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, s.nwarps, MIXED ? WT + 1 : WT);
+  if (sp.total > 220 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
+  const int per_sm = resident_ctas(kernel, nthreads, sp.total);
+  if (per_sm < 1) { set_error("eval_gradient: kernel does not fit on an SM (threads=%d smem=%zu)", nthreads, sp.total); return -4; }
+  const int nblk = pick_grid(grid_samples(a, n_max), 1, 128);
+  if (g_emu.active) {
+    const int r = a.peers.rank;
+    if (a.peers.world != 2 || r < 0 || r > 1) { set_error("emulation records world-2 launches only"); return -1; }
+    g_emu.args[r] = a;
+    g_emu.have[r] = 1;
+    g_emu.launch = launch_grad_emu<D, WT, MIXED>;
+    g_emu.nblk = nblk; g_emu.nthreads = nthreads; g_emu.smem = sp.total;
+    return 0;
+  }
+  return fused_launch(kernel, nblk, nthreads, sp.total, stream, "eval_grad_kernel", false, a);
+}
+
+template <int D>
+int launch_grad_d(EvalArgs& a, int64_t n_max, cudaStream_t stream) {
+  const GradSchedule s = plan_schedule(D, a.H);
+  if constexpr (D >= 4) {
+    if (s.mixed) {
+      if (s.wt == 2) return launch_grad_wt<D, 2, true>(a, s, n_max, stream);
+      if (s.wt == 3) return launch_grad_wt<D, 3, true>(a, s, n_max, stream);
+      if constexpr (D == 4) {
+        if (s.wt == 4) return launch_grad_wt<D, 4, true>(a, s, n_max, stream);
+      }
+      set_error("eval_gradient: no mixed schedule for D=%d H=%d", D, a.H);
+      return -2;
+    }
+  }
+  switch (s.wt) {
+    case 1: return launch_grad_wt<D, 1>(a, s, n_max, stream);
+    case 2: return launch_grad_wt<D, 2>(a, s, n_max, stream);
+    case 3: return launch_grad_wt<D, 3>(a, s, n_max, stream);
+    case 4:
+      if constexpr (D <= 4) return launch_grad_wt<D, 4>(a, s, n_max, stream);
+      break;
+    case 5:
+      if constexpr (D <= 4) return launch_grad_wt<D, 5>(a, s, n_max, stream);
+  }
+  set_error("eval_gradient: no schedule for D=%d H=%d", D, a.H);
+  return -2;
+}
+
+template <int D>
+static int launch_cost_emu(const EvalArgs& a0, const EvalArgs& a1, int nblk, int nthreads, size_t smem, cudaStream_t stream) {
+  auto kernel = eval_cost_emu_kernel<D>;
+  if (resident_ctas(kernel, nthreads, smem) < 1) { set_error("emulated eval_costs: kernel does not fit on an SM"); return -4; }
+  return fused_launch(kernel, 2 * nblk, nthreads, smem, stream, "eval_cost_emu_kernel", true, a0, a1, nblk);
+}
+
+template <int D>
+int launch_cost_d(EvalArgs& a, int64_t n_max, cudaStream_t stream) {
+  auto kernel = eval_cost_kernel<D>;
+  const SmemPlan sp = plan_cost<D>(a.G, a.H, a.d.S, a.d.A, a.d.kind == KLERG_DYN_ROLL);
+  if (sp.total > 200 * 1024) { set_error("eval_costs: G*H too large for shared-memory staging"); return -1; }
+  int nthreads = 512;
+  const int per_sm = resident_ctas(kernel, nthreads, sp.total);
+  if (per_sm < 1) { set_error("eval_costs: kernel does not fit on an SM"); return -4; }
+  const int nblk = pick_grid(grid_samples(a, n_max), 1, 256);
+  if (g_emu.active) {
+    const int r = a.peers.rank;
+    if (a.peers.world != 2 || r < 0 || r > 1) { set_error("emulation records world-2 launches only"); return -1; }
+    g_emu.args[r] = a;
+    g_emu.have[r] = 1;
+    g_emu.launch = launch_cost_emu<D>;
+    g_emu.nblk = nblk; g_emu.nthreads = nthreads; g_emu.smem = sp.total;
+    return 0;
+  }
+  return fused_launch(kernel, nblk, nthreads, sp.total, stream, "eval_cost_kernel", false, a);
+}
+
+}  // namespace klerg

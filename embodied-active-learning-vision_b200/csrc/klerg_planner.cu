@@ -447,7 +447,7 @@ static bool make_lim(int D, const float* lo, const float* hi, LimDev& L) {
 using namespace klerg;
 
 extern "C" const char* klerg_last_error(void) { return g_err; }
-extern "C" int klerg_abi_version(void) { return 4; }
+extern "C" int klerg_abi_version(void) { return 5; }
 extern "C" long long klerg_launch_count(void) { return g_launches; }
 
 // ---- peak-rate microbenchmarks (roofline denominators, used by bench.py only) ----

@@ -212,7 +212,24 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
                   const float* ctrl_lo, const float* ctrl_hi, float* dgdx, float* du, float* djdlam,
                   float* u_star, void* stream);
 
-/* ---- fused evals: one cooperative launch per eval ------------------------- */
+/* ---- fused evals: one launch per eval -------------------------------------- */
+
+/* Process-wide switches of the fused evals.
+ *   KLERG_OPT_EVAL_OVERLAP  1 = consecutive fused evals on a stream are independent (no eval reads what the
+ *                           previous one wrote): the next eval's CTAs do not wait for the previous eval's last
+ *                           CTA (gather + adjoint) to finish.  Default 0: stream order as usual.
+ *   KLERG_OPT_GRID_LIMIT    > 0: at most this many CTAs per fused launch (tests).
+ *   KLERG_OPT_PDL           0 = plain cooperative launches without programmatic dependent launch.
+ *   KLERG_OPT_COOP_WITH_PDL (read-only) 1 / 0 / -1: the driver accepts both attributes / not / not probed yet. */
+enum { KLERG_OPT_EVAL_OVERLAP = 1, KLERG_OPT_GRID_LIMIT = 2, KLERG_OPT_PDL = 3, KLERG_OPT_COOP_WITH_PDL = 4 };
+int klerg_set_option(int key, int value);
+int klerg_get_option(int key);
+/* Two ranks on ONE GPU (tests of the exchange protocol on a single-GPU box): after klerg_emu_begin() the next
+ * klerg_eval_gradient* / klerg_eval_costs call of rank 0 and of rank 1 (peers->world == 2, both mailboxes on this
+ * device) are recorded instead of launched; klerg_emu_launch() runs them as one cooperative grid whose halves
+ * act as the two ranks. */
+int klerg_emu_begin(void);
+int klerg_emu_launch(void* stream);
 
 /* Sample-sharding peers (samples of one workspace split over the GPUs of a
  * box).  mailbox[r] is rank r's exchange buffer
@@ -223,6 +240,8 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
 typedef struct klerg_peers {
   int32_t world, rank;
   void* mailbox[8];
+  int64_t n_max; /* samples of the largest shard: every rank sizes its grid from it, so that all ranks
+                  * launch the same number of CTAs (0 = this rank's N) */
 } klerg_peers;
 size_t klerg_mailbox_bytes(void);
 /* Mailbox plumbing for one-process-per-GPU ranks (CUDA IPC): create allocates and zero-fills this
@@ -250,14 +269,16 @@ size_t klerg_fused_fault_offset(void);
  * rows are copied with TMA) and be 16-byte aligned.  v_scratch: ld floats (receives
  * q_base + q_iter of this rank's samples).  Rinv_diag / ctrl_lo / ctrl_hi are
  * HOST arrays of A floats.  Replaces klerg_rollout + klerg_footprint +
- * klerg_kl_gradient_fused + klerg_adjoint with a single launch. */
+ * klerg_kl_gradient_fused + klerg_adjoint with a single launch.
+ * fault_out (may be NULL): one float next to the outputs the host reads anyway, 1.0 if an in-kernel wait of
+ * this workspace ever timed out (copy of the sticky fault word), else 0.0. */
 int klerg_eval_gradient(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
                         const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t H,
                         const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
                         const double* p_stats, float floor, const float* Rinv_diag, float alpha,
                         const float* ctrl_lo, const float* ctrl_hi, float* v_scratch, float* traj,
                         double* totals, float* cost, float* dgdx, float* du, float* djdlam, float* u_star,
-                        double* kl_out, void* workspace, void* stream);
+                        double* kl_out, float* fault_out, void* workspace, void* stream);
 
 /* The same for K <= 32 belief targets p_k over one workspace and one trajectory (fingerprint test mode,
  * test_fingerprint_main.py swaps robot.target_dist between beliefs; BASELINE config 5): the rollout, the
@@ -270,7 +291,8 @@ int klerg_eval_gradient_targets(const klerg_kernel_spec* k, const klerg_dyn_spec
                                 int64_t K, int64_t p_stride, const double* p_stats, float floor,
                                 const float* Rinv_diag, float alpha, const float* ctrl_lo, const float* ctrl_hi,
                                 float* v_scratch, float* traj, double* totals, float* cost, float* dgdx, float* du,
-                                float* djdlam, float* u_star, double* kl_out, void* workspace, void* stream);
+                                float* djdlam, float* u_star, double* kl_out, float* fault_out, void* workspace,
+                                void* stream);
 
 /* Robot.get_cost (klerg.py:686-710) for G <= 8 candidate control sequences
  * u[G][H][A] in one launch (the line-search windows of klerg.py:712-751):
@@ -280,7 +302,7 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
                      const klerg_peers* peers, const float* x0, const float* R0, const float* u, int64_t G,
                      int64_t H, const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
                      const double* p_stats, float floor, float* v_scratch, float* traj, double* totals,
-                     float* cost, void* workspace, void* stream);
+                     float* cost, float* fault_out, void* workspace, void* stream);
 
 /* ---- a19: memory-buffer selection (memory_buffer.py:52-63) ---------------- */
 

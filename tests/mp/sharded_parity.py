@@ -24,7 +24,7 @@ def build_ctx(probe, group, smp, p_raw, lo, hi, n_total, hist, x0, H, fused=True
     ctx = PlannerContext(probe.planner.spec, probe.barrier.spec(), probe.explr_locs.tolist(), H,
                          torch.diagonal(probe.R_inv).tolist(), probe.control_lim[:, 0].tolist(),
                          probe.control_lim[:, 1].tolist(), alpha=1.0, group=group, fused=fused)
-    ctx.set_samples(smp, probe.std.tolist(), 1.0)
+    ctx.set_samples(smp, probe.std.tolist(), 1.0, n_total=n_total if group.world > 1 else None)
     ctx.set_state(x0)
     p, p_stats, _ = engine.target_weight(2, smp, lo.tolist(), hi.tolist(), None, p_raw, n_total, 1.0, True, group)
     ctx.set_target(p, p_stats)

@@ -54,18 +54,24 @@ def test_fused_eval_validation(lib):
     args = (C.byref(k), C.byref(dyn), None, None, None, None, None)
     # horizon out of range
     assert lib.klerg_eval_gradient(*args, 0, None, 8, 8, None, None, None, 1e-6, three, 1.0, three, three, None, None,
-                                   None, None, None, None, None, None, None, None, None) == -1
+                                   None, None, None, None, None, None, None, None, None, None) == -1
     assert "H out of range" in err(lib)
     # more candidates than one fused launch takes
-    assert lib.klerg_eval_costs(*args, 9, 4, None, 8, 8, None, None, None, 1e-6, None, None, None, None, None, None) == -1
+    assert lib.klerg_eval_costs(*args, 9, 4, None, 8, 8, None, None, None, 1e-6, None, None, None, None, None, None, None) == -1
     assert "G must be" in err(lib)
     # sample leading dimension must be a multiple of 4 and >= N
-    assert lib.klerg_eval_costs(*args, 2, 4, None, 8, 6, None, None, None, 1e-6, None, None, None, None, None, None) == -1
+    assert lib.klerg_eval_costs(*args, 2, 4, None, 8, 6, None, None, None, 1e-6, None, None, None, None, None, None, None) == -1
     peers = cabi.Peers()
     peers.world, peers.rank = 9, 0
     assert lib.klerg_eval_costs(C.byref(k), C.byref(dyn), None, C.byref(peers), None, None, None, 2, 4, None, 8, 8, None,
-                                None, None, 1e-6, None, None, None, None, None, None) == -1
+                                None, None, 1e-6, None, None, None, None, None, None, None) == -1
     assert "world/rank" in err(lib)
+    # options / emulation plumbing (no launches)
+    assert lib.klerg_set_option(99, 1) == -1
+    assert lib.klerg_set_option(cabi.OPT_GRID_LIMIT, 64) == 0 and lib.klerg_get_option(cabi.OPT_GRID_LIMIT) == 64
+    assert lib.klerg_set_option(cabi.OPT_GRID_LIMIT, 0) == 0
+    assert lib.klerg_emu_launch(None) == -1  # nothing recorded
+    assert "emulation" in err(lib)
 
 
 def test_python_layer_raises_without_gpu_or_on_status():
