@@ -14,7 +14,10 @@ import torch
 
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPO_ROOT = os.path.dirname(PKG_ROOT)
-LIB_PATH = os.path.join(PKG_ROOT, "libklerg_b200.so")
+# KLERG_VARIANT=_stamps selects the instrumented build (phase stamps in the fused evals, -DKLERG_STAMPS): a second
+# library next to the product one, used by tools/ only
+VARIANT = os.environ.get("KLERG_VARIANT", "")
+LIB_PATH = os.path.join(PKG_ROOT, f"libklerg_b200{VARIANT}.so")
 CSRC = os.path.join(PKG_ROOT, "csrc")
 INCLUDE = os.path.join(REPO_ROOT, "include")
 
@@ -66,9 +69,9 @@ def build(force=False, verbose=False):
         if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = ["-DKLERG_STAMPS"] if os.environ.get("KLERG_STAMPS") else []  # phase stamps in the fused evals
+    extra = ["-DKLERG_STAMPS"] if (os.environ.get("KLERG_STAMPS") or VARIANT == "_stamps") else []
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + ["-I", INCLUDE]
-    objdir = os.path.join(PKG_ROOT, "build")
+    objdir = os.path.join(PKG_ROOT, "build" + VARIANT)
     os.makedirs(objdir, exist_ok=True)
     # one nvcc per translation unit, in parallel (the fused evals are the long pole), then one link
     procs = []
@@ -131,6 +134,7 @@ SIGNATURES = {
     "klerg_mailbox_open": [C.c_char_p, C.POINTER(C.c_void_p)],
     "klerg_mailbox_close": [_P, C.c_int],
     "klerg_debug_stamps_offset": [],
+    "klerg_debug_cta_stamps_offset": [],
     "klerg_fused_fault_offset": [],
     "klerg_set_option": [C.c_int, C.c_int],
     "klerg_get_option": [C.c_int],
@@ -148,7 +152,7 @@ SIGNATURES = {
     "klerg_eval_costs": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P,
                          _P, _P, _P],
 }
-_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_kl_gradient_targets_scratch_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
+_RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_kl_gradient_targets_scratch_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_debug_cta_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
              "klerg_launch_count": C.c_longlong}
 
 
@@ -171,6 +175,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
+    if os.environ.get("KLERG_PDL") == "0":  # A/B switch: plain cooperative launches of the fused evals
+        lib.klerg_set_option(OPT_PDL, 0)
     _lib = lib
     return lib
 

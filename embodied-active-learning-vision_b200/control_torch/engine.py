@@ -514,6 +514,14 @@ def debug_stamps():
     return ws.buf[off:off + 144].view(torch.int64).cpu().tolist()
 
 
+def debug_cta_stamps():
+    """[160, 8] globaltimer stamps (ns) per CTA of the last fused gradient eval (KLERG_STAMPS builds, single GPU)."""
+    key = (torch.cuda.current_device(), cabi.raw_stream())
+    ws = _workspaces[key]
+    off = cabi.load().klerg_debug_cta_stamps_offset()
+    return ws.buf[off:off + 160 * 64].view(torch.int64).view(160, 8).cpu()
+
+
 def fused_fault():
     """True if a fused eval on the current stream's workspace gave up waiting at a meeting point (one small D2H read;
     the planner reads the kernels' own copy of the word with the results it fetches anyway)."""

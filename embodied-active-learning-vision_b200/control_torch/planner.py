@@ -72,8 +72,8 @@ class PlannerContext:
     def set_target(self, p, p_stats):
         """p [n_local] (or already padded to the sample stride ld), p_stats [1] = global sum of p."""
         ld = self.packed.shape[1]
-        if p.numel() < ld:  # the fused evals copy whole tile rows with TMA: rows are padded to the sample stride
-            pad = torch.zeros(ld, dtype=torch.float32, device=p.device)
+        if p.numel() < ld or p.data_ptr() % 16:  # the fused evals copy whole tile rows with TMA: rows are padded to the
+            pad = torch.zeros(ld, dtype=torch.float32, device=p.device)  # sample stride and 16-byte aligned
             pad[: p.numel()] = p
             p = pad
         self.p, self.p_stats = p, p_stats

@@ -44,7 +44,9 @@ constexpr size_t MB_OFF_R1 = MB_OFF_L1 + MB_L1;
 constexpr size_t MB_OFF_KL = MB_OFF_R1 + MB_R1;
 constexpr size_t MB_OFF_GB = MB_OFF_KL + MB_KL;
 constexpr size_t MB_OFF_GP = MB_OFF_GB + MB_GB;
-constexpr size_t MB_BYTES = MB_OFF_GP + MB_GP;
+constexpr size_t MB_OFF_DBG = MB_OFF_GP + MB_GP;                     // [cta][8] globaltimer stamps (KLERG_STAMPS builds)
+constexpr size_t MB_DBG = (size_t)LL_MAXBLK * 8 * 8;
+constexpr size_t MB_BYTES = MB_OFF_DBG + MB_DBG;
 
 constexpr size_t FUSED_BYTES = FUSED_CTRL + MB_BYTES;  // single GPU: the mailbox lives inside the workspace
 constexpr size_t HEAD_BYTES = HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + FUSED_BYTES;

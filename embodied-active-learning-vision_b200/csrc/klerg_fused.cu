@@ -125,6 +125,7 @@ extern "C" int klerg_mailbox_close(void* ptr, int owner) {
 }
 extern "C" size_t klerg_fused_fault_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 5 * sizeof(unsigned); }
 extern "C" size_t klerg_debug_stamps_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + 64; }
+extern "C" size_t klerg_debug_cta_stamps_offset(void) { return HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + FUSED_CTRL + MB_OFF_DBG; }
 
 // single GPU: the mailbox is the region of the workspace reserved for it
 static void finish_peers(EvalArgs& a, void* workspace) {
@@ -190,6 +191,7 @@ extern "C" int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec
   if (G < 1 || G > FUSED_MAXG) { set_error("eval_costs: G must be in 1..%d", FUSED_MAXG); return -1; }
   if (N < 1 || ld < N || (ld & 3)) { set_error("eval_costs: bad sample sizes"); return -1; }
   if (!workspace || !v_scratch || !cost) { set_error("eval_costs: null output/workspace"); return -1; }
+  if (((uintptr_t)packed | (uintptr_t)p | (uintptr_t)v_scratch) & 15) { set_error("eval_costs: packed, p and v_scratch must be 16-byte aligned"); return -1; }
   a.x0 = x0; a.R0 = R0; a.u = u; a.G = (int)G; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base;
   a.p = p; a.p_stats = p_stats; a.floor = floor; a.v = v_scratch; a.ws = workspace; a.traj = traj; a.totals = totals;
   a.cost = cost; a.K = 1; a.p_stride = 0; a.fault_out = fault_out;

@@ -78,9 +78,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifdef KLERG_STAMPS
 #define KLERG_STAMP_DECL long long stamp[16]
 #define KLERG_STAMP(i) stamp[i] = clock64()
+// per-CTA wall-clock stamps (ns, comparable across SMs) in the debug region of the local mailbox
+#define KLERG_CTA_STAMP(me, vblk, i)                                                   \
+  if (threadIdx.x == 0) {                                                               \
+    unsigned long long t_;                                                              \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                              \
+    ((unsigned long long*)((char*)(me) + MB_OFF_DBG))[(size_t)(vblk) * 8 + (i)] = t_;   \
+  }
 #else
 #define KLERG_STAMP_DECL
 #define KLERG_STAMP(i)
+#define KLERG_CTA_STAMP(me, vblk, i)
 #endif
 
 struct EvalArgs {
@@ -426,6 +434,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
 
   KLERG_STAMP_DECL;
   KLERG_STAMP(0);
+  KLERG_CTA_STAMP(me, vblk, 0);
   // ---- phase 0: rollout, states only (every CTA) ----------------------------------------------------
   float* s_x0 = (float*)(smem + sp.misc) + 4;  // [S] (+ [9] R0)
   unsigned long long* s_bar = (unsigned long long*)(smem + ((sp.misc + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 7) & ~(size_t)7));  // [2]
@@ -462,6 +471,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   __syncthreads();
 
   KLERG_STAMP(1);
+  KLERG_CTA_STAMP(me, vblk, 1);
   // ---- phase 1: forward pair pass, slice totals -------------------------------------------------
   int64_t lo, hi;
   cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
@@ -479,6 +489,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     }
   }
   KLERG_STAMP(2);
+  KLERG_CTA_STAMP(me, vblk, 2);
   // The first sample tile of the gradient pass (samples, this CTA's own v, p) does not depend on the grid-wide
   // totals: its TMA copies are issued now and land while the CTAs meet.
   fence_proxy_async();  // v was written with ordinary stores and is read back by TMA
@@ -506,6 +517,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   __syncthreads();
   pdl_launch_dependents();
   KLERG_STAMP(3);
+  KLERG_CTA_STAMP(me, vblk, 3);
   const double vsum = s_world[0];
   const double vmax = s_world[1];
   if (vblk == 0 && tid == 0 && a.totals) {
@@ -670,6 +682,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   // ---- phase 3: warps spread over the grid add the CTA partials of one gradient entry each (fixed order) and
   //      hand the sum to every rank; the finisher CTA collects the H*D sums of all ranks and runs the adjoint ----
   KLERG_STAMP(4);
+  KLERG_CTA_STAMP(me, vblk, 4);
   for (int e = vblk + vnblk * warp; e < HD; e += vnblk * nwarps) {
     const u64* row = mb_gp(me, xpar, e);
     double v = 0.0;
@@ -681,6 +694,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     v = warp_reduce(RED_SUM, v);
     if (lane < world) ll_store(mb_gb(a.peers.mail[lane], xpar, a.peers.rank) + 2 * e, v, xtag);
   }
+  KLERG_CTA_STAMP(me, vblk, 5);
   if (!finisher) continue;
   KLERG_STAMP(5);
   if (kt == 0) {
@@ -757,6 +771,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
 #ifdef KLERG_STAMPS
     // phase stamps of the finisher (SM cycles since its start): profiling aid
     KLERG_STAMP(7);
+    KLERG_CTA_STAMP(me, vblk, 6);
     long long* dbg = (long long*)(ctrl + 16);
     for (int i = 0; i < 10; ++i) dbg[i] = stamp[i] - stamp[0];
     for (int i = 0; i < 8; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];

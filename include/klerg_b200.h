@@ -254,6 +254,9 @@ int klerg_mailbox_close(void* ptr, int owner);
 /* Byte offset inside `workspace` of 8 int64 SM-cycle stamps left by the last klerg_eval_gradient
  * (start, rollout, forward, meet-1, gradient, meet-2, reduce, end; relative to start). */
 size_t klerg_debug_stamps_offset(void);
+/* KLERG_STAMPS builds, single GPU: byte offset inside `workspace` of [160 CTAs][8] uint64 globaltimer stamps (ns) of the
+ * last klerg_eval_gradient: start, rollout, forward, meeting 1, gradient, entry sums, (finisher) end. */
+size_t klerg_debug_cta_stamps_offset(void);
 /* Byte offset inside `workspace` of a sticky uint32 fault word: non-zero after a fused eval gave
  * up waiting at a meeting point (results of that eval are undefined). */
 size_t klerg_fused_fault_offset(void);

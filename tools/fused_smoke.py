@@ -48,11 +48,9 @@ for fused in (False, True):
             ctx.gradient(U[0])
         torch.cuda.synchronize()
         st = engine.debug_stamps()
-        names = ["rollout", "forward", "meet1", "gradient", "meet2", "reduce", "adjoint+end"]
-        print("phase cycles:", {k: st[i + 1] - st[i] for i, k in enumerate(names)}, "total", st[7],
-              "| inside rollout phase: stage u/x0", st[8], "rollout_block", st[9] - st[8], "x2 staging", st[1] - st[9], "| rollout_block (CTA 0): running sums", st[11], "roll", st[12] - st[11],
-              "barrier loop", st[13] - st[12], "barrier reduce", st[14] - st[13],
-              "| roll: rodrigues", st[15] - st[11], "chain", st[16] - st[15], "euler", st[17] - st[16], "P+rest", st[12] - st[17])
+        names = ["rollout(states)", "forward", "meet1", "gradient", "row sums", "lin+gather", "adjoint+end"]
+        print("finisher CTA, phase cycles:", {k: st[i + 1] - st[i] for i, k in enumerate(names)}, "total", st[7],
+              "| inside rollout phase: stage u/x0", st[8], "rollout_block", st[9] - st[8], "x2 staging", st[1] - st[9])
     res[fused] = dict(cost=c.cpu(), du=gr["du"].cpu(), dj=gr["djdlam"].cpu(), us=gr["u_star"].cpu(), dgdx=gr["dgdx"].cpu(),
                       v=gr["v"][:n].cpu(), tot=gr["totals"].cpu())
 for k in res[True]:
