@@ -48,7 +48,7 @@ class Peers(C.Structure):
 
 
 ABI_VERSION = 5  # mirrors klerg_abi_version() of the library built from this tree (include/klerg_b200.h)
-OPT_EVAL_OVERLAP, OPT_GRID_LIMIT, OPT_PDL, OPT_COOP_WITH_PDL = 1, 2, 3, 4
+OPT_EVAL_OVERLAP, OPT_GRID_LIMIT, OPT_PDL, OPT_COOP_WITH_PDL, OPT_EXACT_PAIRS, OPT_MIXED_WARPS = 1, 2, 3, 4, 5, 6
 
 
 class BarrierSpec(C.Structure):
@@ -107,6 +107,7 @@ SIGNATURES = {
     "klerg_workspace_bytes": [_I64],
     "klerg_pack_samples": [_KS, _P, _I64, _P, _I64, _P],
     "klerg_footprint": [_KS, C.c_int, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P],
+    "klerg_footprint_sum_max": [_KS, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P, _P],
     "klerg_psi_matrix": [_KS, _P, _I64, _P, _I64, _P, _P, _P],
     "klerg_vector_stats": [_P, _I64, _P, _P, _P],
     "klerg_renormalize": [_P, _I64, _F, _P, _P, _P],
@@ -177,6 +178,10 @@ def load():
         fn.restype = _RESTYPES.get(name, C.c_int)
     if os.environ.get("KLERG_PDL") == "0":  # A/B switch: plain cooperative launches of the fused evals
         lib.klerg_set_option(OPT_PDL, 0)
+    if os.environ.get("KLERG_MIXED_WARPS") == "16":  # A/B switch: 16-warp gradient schedule for D >= 5
+        lib.klerg_set_option(OPT_MIXED_WARPS, 16)
+    if os.environ.get("KLERG_EXACT_PAIRS") == "1":  # A/B switch: difference form of the squared distance everywhere
+        lib.klerg_set_option(OPT_EXACT_PAIRS, 1)
     _lib = lib
     return lib
 

@@ -225,6 +225,22 @@ def footprint(spec, mode, states, packed, n, add_in=None, out=None):
     return out, totals
 
 
+def footprint_sum_max(spec, states, t_sum, packed, n):
+    """ONE pass over the squared distances for both memory-buffer passes of a planner step: states [T,S] with the drawn
+    rows first -> (sum over the first t_sum rows [ld], max over all rows [ld], totals [2] of the sum)."""
+    states = states.contiguous()
+    T, S = states.shape
+    assert S == spec.S, (S, spec.S)
+    ld = packed.shape[1]
+    out_sum = torch.empty(ld, dtype=torch.float32, device=packed.device)
+    out_max = torch.empty(ld, dtype=torch.float32, device=packed.device)
+    totals = torch.empty(2, dtype=torch.float64, device=packed.device)
+    cabi.check(cabi.load().klerg_footprint_sum_max(
+        C.byref(spec), cabi.ptr(states) if T > 0 else None, T, int(t_sum), cabi.ptr(packed), int(n), ld, cabi.ptr(out_sum),
+        cabi.ptr(out_max), cabi.ptr(totals), workspace(1), cabi.stream_ptr()), "klerg_footprint_sum_max")
+    return out_sum, out_max, totals
+
+
 def vector_stats(x):
     stats = torch.empty(4, dtype=torch.float64, device=x.device)
     cabi.check(cabi.load().klerg_vector_stats(cabi.ptr(x), x.numel(), cabi.ptr(stats), workspace(), cabi.stream_ptr()),

@@ -366,8 +366,9 @@ class Robot(object):
         lo, hi = self.group.shard_bounds(t.shape[0])
         return t[lo:hi]
 
-    def _target_on_device(self, samples_host, samples_dev, scale_spec, temp, uniform=False, plot=False):
-        """get_target_dist (klerg.py:452-486) -> (p, p_stats) on the device for this rank's sample slice."""
+    def _target_on_device(self, samples_host, samples_dev, scale_spec, temp, uniform=False, plot=False, spread=None):
+        """get_target_dist (klerg.py:452-486) -> (p, p_stats) on the device for this rank's sample slice.
+        ``spread``: max_j psi over all buffer rows, when the caller already has it (fused history pass)."""
         p_raw, pre_renorm = self._pdf(samples_host, uniform, samples_dev)
         p_raw = p_raw.detach().to(torch.float32).to(self.cuda, non_blocking=True).contiguous()
         n_total = samples_host.shape[0]
@@ -376,8 +377,9 @@ class Robot(object):
         if pre_renorm:  # uniform branch renormalises before weighting (klerg.py:456-458)
             p_raw, _, _ = engine.target_weight(2, samples_dev, lo, hi, None, p_raw, n_total, 1.0, True, self.group)
         weighted = self.weight_env or self.weight_temp or plot
-        spread = None
-        if weighted and len(self.memory_buffer) > 0:
+        if not weighted:
+            spread = None
+        elif spread is None and len(self.memory_buffer) > 0:
             spec = cabi.kernel_spec(len(self.explr_idx), self.planner.num_states, self.explr_idx.tolist(),
                                     self.std.tolist(), 1.0)  # NB explr_idx, not explr_locs (klerg.py:473)
             packed = scale_spec["packed_std"]
@@ -392,6 +394,12 @@ class Robot(object):
         p, p_stats, _ = engine.target_weight(mode, samples_dev, lo, hi, spread, p_raw, n_total, temp, weighted,
                                              self.group)
         return p, p_stats
+
+    def _fused_history_ok(self, hist_dev):
+        """Both memory-buffer passes in one: needs the spread at all (a weighting flag), rows to visit, and the same
+        kernel for both (the reference passes explr_idx to one and explr_locs to the other, klerg.py:473 vs :496)."""
+        return bool((self.weight_env or self.weight_temp) and hist_dev.shape[0] > 0
+                    and self.explr_idx.tolist() == self.explr_locs.tolist())
 
     # ------------------------------------------------------------------ planner
     def _context(self):
@@ -428,10 +436,17 @@ class Robot(object):
             samples_dev = self._shard(samples).to(self.cuda, non_blocking=True).contiguous()
             ctx.set_samples(samples_dev, self.std.tolist(), 1.0, n_total=samples.shape[0])
             ctx.set_state(self.robot.state.to(self.cuda, non_blocking=True))
+            spread = None
+            if self._fused_history_ok(hist_dev):
+                # the spread of get_target_dist (all buffer rows, klerg.py:470-475) and the history footprint q_base
+                # (the drawn rows, klerg.py:496) visit the same rows: ONE pass over the squared distances
+                rows, t_sum = self.memory_buffer.partition_device(self.last_hist_idx)
+                ctx.q_base, spread, _ = engine.footprint_sum_max(ctx.spec, rows, t_sum, ctx.packed, ctx.n)
+            else:
+                ctx.set_history(hist_dev)
             p, p_stats = self._target_on_device(samples, samples_dev, dict(packed_std=ctx.packed), temp,
-                                                uniform=self.uniform_tdist)
+                                                uniform=self.uniform_tdist, spread=spread)
             ctx.set_target(p, p_stats)
-            ctx.set_history(hist_dev)
 
             last_cost = self._costs(ctx, self.u.unsqueeze(0))[0]
             accepted = None  # forward output (v, totals) of the last gradient eval, for plot_data

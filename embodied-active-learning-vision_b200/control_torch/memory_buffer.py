@@ -76,6 +76,20 @@ class MemoryBuffer_torch(torch.nn.Module):
         rows = engine.gather_rows(self.device_buffer, idx.to("cuda", non_blocking=True))
         return rows, idx
 
+    def partition_device(self, idx):
+        """All buffer rows on the GPU with the drawn ones first: (rows [len, S], number of drawn rows).
+
+        Both groups keep the buffer's time order (consecutive states of the robot's path are close together, which
+        keeps the staged chunks of the pair pass compact); the order inside a group does not matter to the sums."""
+        n = len(self)
+        m = int(idx.numel())
+        if m >= n:
+            return self.get_all_device(), n
+        drawn = torch.zeros(n, dtype=torch.bool)
+        drawn[idx] = True
+        order = torch.cat([drawn.nonzero().flatten(), (~drawn).nonzero().flatten()])
+        return engine.gather_rows(self.device_buffer, order.to("cuda", non_blocking=True)), m
+
     def sample(self, batch_size):
         rows, _ = self.sample_device(batch_size)
         return rows.to(device="cpu", dtype=self.buffer.dtype)

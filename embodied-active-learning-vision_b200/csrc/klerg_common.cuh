@@ -29,7 +29,7 @@ constexpr size_t FUSED_CTRL = 256;  // u32: [5] sticky fault word; +64: debug st
 constexpr int MB_MAXW = 8;          // ranks
 constexpr int LL_MAXBLK = 160;      // CTAs per rank that take part in an exchange (>= 148 SMs)
 constexpr int LL_MAXNV = 2 * FUSED_MAXG;                      // doubles per CTA at a meeting
-constexpr int LL_MAXHD = KLERG_MAX_H * KLERG_MAX_D;           // gradient entries of one eval
+constexpr int LL_MAXHD = KLERG_MAX_H * (KLERG_MAX_D + 1);     // gather entries of one eval: H*D weighted sums + H weights
 constexpr int LL_BUF_VALS = LL_MAXBLK * LL_MAXNV;             // polled values staged in shared memory (20 KB)
 constexpr size_t MB_HDR = 256;      // u32 [0] epoch  [1] xcount  [2] xdone
 constexpr size_t MB_X1 = (size_t)2 * MB_MAXW * LL_MAXBLK * 2 * 16;   // [par][rank][cta][2]   cross-rank one-hop meeting
@@ -198,7 +198,9 @@ struct KernelDev {
   float a[KLERG_MAX_D];       // sqrt(HALF_LOG2E/|scale|)
   float gfac[KLERG_MAX_D];    // -1/(a*|scale|*nu): scaled-difference sum -> dgdx
   float inv_nu;
+  float x_r2;                 // largest |xc|^2 for which the expanded pair form is used (< 0: never)
 };
+extern int g_exact_pairs;     // KLERG_OPT_EXACT_PAIRS
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

@@ -3,7 +3,7 @@
 
 namespace klerg {
 
-FusedOptions g_fused_opt = {0, 0, 1, -1};
+FusedOptions g_fused_opt = {0, 0, 1, -1, 0};
 EmuState g_emu = {};
 
 template <int D> int launch_grad_d(EvalArgs& a, int64_t n_max, cudaStream_t stream);
@@ -49,6 +49,8 @@ extern "C" int klerg_set_option(int key, int value) {
     case KLERG_OPT_EVAL_OVERLAP: g_fused_opt.overlap = value != 0; return 0;
     case KLERG_OPT_GRID_LIMIT: g_fused_opt.grid_limit = value > 0 ? value : 0; return 0;
     case KLERG_OPT_PDL: g_fused_opt.pdl = value != 0; return 0;
+    case KLERG_OPT_EXACT_PAIRS: g_exact_pairs = value != 0; return 0;
+    case KLERG_OPT_MIXED_WARPS: g_fused_opt.mixed_warps = value == 16 ? 16 : 0; return 0;
     default: set_error("set_option: unknown key %d", key); return -1;
   }
 }
@@ -58,6 +60,8 @@ extern "C" int klerg_get_option(int key) {
     case KLERG_OPT_GRID_LIMIT: return g_fused_opt.grid_limit;
     case KLERG_OPT_PDL: return g_fused_opt.pdl;
     case KLERG_OPT_COOP_WITH_PDL: return g_fused_opt.coop_probe;
+    case KLERG_OPT_EXACT_PAIRS: return g_exact_pairs;
+    case KLERG_OPT_MIXED_WARPS: return g_fused_opt.mixed_warps;
     default: return -1;
   }
 }

@@ -25,6 +25,7 @@
 #pragma once
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "klerg_common.cuh"
 #include "klerg_dyn.cuh"
@@ -48,6 +49,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
@@ -136,6 +140,7 @@ struct FusedOptions {
   int grid_limit;   // > 0: at most this many CTAs per launch (tests: two emulated ranks share one GPU)
   int pdl;          // launch with the programmatic-stream-serialization attribute
   int coop_probe;   // -1 unknown, 0 / 1: the cooperative attribute may be combined with it
+  int mixed_warps;  // 0 = automatic, 16 = never the 12-warp mixed schedule (A/B)
 };
 extern FusedOptions g_fused_opt;
 
@@ -218,32 +223,76 @@ __device__ __forceinline__ void cta_slice(int64_t N, int64_t ld, int vblk, int v
   if (lo > ld) lo = ld;
 }
 
-// Forward pair pass of one trajectory (T duplicated rows at sh_x2) over this CTA's slice:
+// State rows of one eval in shared memory, in both forms (klerg_pair.cuh): duplicated rows for the difference form,
+// {-2 xc, |xc|^2} rows around the centre `ctr` for the expanded form; `xform` says which one the pair passes use.
+struct StateRows {
+  const u64* x2;     // [T][DP]
+  const float* rx;   // [T][NF]
+  const float* ctr;  // [D]
+  bool xform;
+};
+
+// Forward pair pass of one trajectory (T state rows) over this CTA's slice:
 // v[i] = q_base[i] + inv_nu * sum_t psi; returns the slice's {sum, max} of v over i < N.
 template <int D, int P>
-__device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+__device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const StateRows& sr, int T, float* v_out, int64_t lo,
                                                 int64_t hi, double& tsum, double& tmax) {
   constexpr int SPT = 2 * P;
-  for (int64_t i0 = lo + (int64_t)threadIdx.x * SPT; i0 < hi; i0 += (int64_t)blockDim.x * SPT) {
+  u64 c2[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) c2[d] = pack2(sr.ctr[d], sr.ctr[d]);
+  // this thread's next samples are requested before the pair math of the current ones starts (a thread-iteration
+  // is only T state rows long, and the load latency would otherwise be exposed once per iteration); they stay in
+  // the registers the loads return them in until they become current, so that nothing waits for them early
+  typedef typename std::conditional<P == 2, float4, float2>::type vec_t;
+  auto load = [&](int64_t i0, vec_t (&raw)[D], float (&qb)[SPT]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) raw[d] = __ldg(reinterpret_cast<const vec_t*>(a.packed + (int64_t)d * a.ld + i0));
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? __ldg(a.q_base + i0 + q) : 0.f;
+  };
+  const int64_t stride = (int64_t)blockDim.x * SPT;
+  int64_t i0 = lo + (int64_t)threadIdx.x * SPT;
+  vec_t raw[D], raw_n[D];
+  float qb[SPT], qbn[SPT];
+  if (i0 < hi) load(i0, raw, qb);
+  for (; i0 < hi; i0 += stride) {
     u64 s2[D][P], acc[P];
     float emin[SPT];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       if constexpr (P == 2) {
-        const float4 s = __ldg(reinterpret_cast<const float4*>(a.packed + (int64_t)d * a.ld + i0));
-        s2[d][0] = pack2(s.x, s.y);
-        s2[d][1] = pack2(s.z, s.w);
+        s2[d][0] = pack2(raw[d].x, raw[d].y);
+        s2[d][1] = pack2(raw[d].z, raw[d].w);
       } else {
-        const float2 s = __ldg(reinterpret_cast<const float2*>(a.packed + (int64_t)d * a.ld + i0));
-        s2[d][0] = pack2(s.x, s.y);
+        s2[d][0] = pack2(raw[d].x, raw[d].y);
       }
     }
-    float qb[SPT];
-#pragma unroll
-    for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? a.q_base[i0 + q] : 0.f;
+    const bool more = i0 + stride < hi;
 #pragma unroll
     for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
-    pair_forward<D, P, 0>(sh_x2, T, s2, acc, emin);
+    u64 s2n[P];
+    if (sr.xform) {
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        s2[0][q] = sub2(s2[0][q], c2[0]);
+        s2n[q] = mul2(s2[0][q], s2[0][q]);
+#pragma unroll
+        for (int d = 1; d < D; ++d) {
+          s2[d][q] = sub2(s2[d][q], c2[d]);
+          s2n[q] = fma2(s2[d][q], s2[d][q], s2n[q]);
+        }
+      }
+    }
+    // The next samples are requested only now, after the current ones have been consumed: a consumer of loaded data
+    // waits for every load outstanding on its scoreboard, including ones issued after the load it depends on.
+    asm volatile("" ::: "memory");
+    if (more) load(i0 + stride, raw_n, qbn);
+    asm volatile("" ::: "memory");
+    if (sr.xform)
+      pair_forward_x<D, P, 0>(sr.rx, 0, T, s2, s2n, acc, emin);
+    else
+      pair_forward<D, P, 0>(sr.x2, 0, T, s2, acc, emin);
     float o[SPT];
 #pragma unroll
     for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
@@ -262,6 +311,12 @@ __device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const u64* sh
       *reinterpret_cast<float4*>(v_out + i0) = make_float4(o[0], o[1], o[2], o[3]);
     else
       *reinterpret_cast<float2*>(v_out + i0) = make_float2(o[0], o[1]);
+    if (more) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) raw[d] = raw_n[d];
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) qb[q] = qbn[q];
+    }
   }
 }
 
@@ -275,30 +330,69 @@ __device__ __forceinline__ bool narrow_pairs(int64_t lo, int64_t hi) {
 }
 
 template <int D>
-__device__ __forceinline__ void forward_slice(const EvalArgs& a, const u64* sh_x2, int T, float* v_out, int64_t lo,
+__device__ __forceinline__ void forward_slice(const EvalArgs& a, const StateRows& sr, int T, float* v_out, int64_t lo,
                                               int64_t hi, double& tsum, double& tmax) {
   if (narrow_pairs(lo, hi))
-    forward_slice_p<D, 1>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
+    forward_slice_p<D, 1>(a, sr, T, v_out, lo, hi, tsum, tmax);
   else
-    forward_slice_p<D, 2>(a, sh_x2, T, v_out, lo, hi, tsum, tmax);
+    forward_slice_p<D, 2>(a, sr, T, v_out, lo, hi, tsum, tmax);
 }
 
+// Stage the state rows of G trajectories of T rows each in both forms.  Row t of trajectory g is at
+// states[g * seg + t * S] (explored columns a.k.explr, scaled by a.k.a); centre = the middle row of trajectory 0.
+// s_xs[G*T][D] (may be NULL) receives the centred scaled coordinates.  Returns (all threads) whether every row
+// lies within the radius of the expanded form.  Ends with a barrier.
+template <int D>
+__device__ __forceinline__ bool stage_state_rows(const EvalArgs& a, const float* states, int S, int G, int T, size_t seg,
+                                                 u64* s_x2, float* s_rx, float* s_xs, float* s_ctr) {
+  constexpr int DP = Row2<D>::DP, NF = RowX<D>::NF;
+  const int tid = threadIdx.x;
+  float c[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) c[d] = states[(size_t)(T / 2) * S + a.k.explr[d]] * a.k.a[d];
+  if (tid < D) s_ctr[tid] = states[(size_t)(T / 2) * S + a.k.explr[tid]] * a.k.a[tid];
+  bool big = false;
+  for (int r = tid; r < G * T; r += blockDim.x) {
+    const int g = r / T, t = r - g * T;
+    const float* row = states + (size_t)g * seg + (size_t)t * S;
+    float x2n = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float x = row[a.k.explr[d]] * a.k.a[d];
+      const float xc = x - c[d];
+      if (s_xs) s_xs[r * D + d] = xc;
+      s_x2[r * DP + d] = pack2(x, x);
+      s_rx[r * NF + d] = -2.f * xc;
+      x2n = fmaf(xc, xc, x2n);
+    }
+#pragma unroll
+    for (int d = D; d < DP; ++d) s_x2[r * DP + d] = pack2(0.f, 0.f);
+    s_rx[r * NF + D] = x2n;
+#pragma unroll
+    for (int d = D + 1; d < NF; ++d) s_rx[r * NF + d] = 0.f;
+    big |= !(x2n <= a.k.x_r2);
+  }
+  return !__syncthreads_or(big);
+}
 
 // Forward pair pass of G candidate trajectories over this CTA's slice: samples are loaded once per thread and swept
 // against every candidate (the per-candidate totals live in a small indexed array: two local-memory accesses per
 // H pairs); v[g][i] to HBM; the CTA's {sum, max} per candidate end up in s_in[2g], s_in[2g + 1].
 template <int D, int P>
-__device__ __forceinline__ void forward_candidates(const EvalArgs& a, const u64* s_x2, int G, int H, int64_t lo, int64_t hi,
+__device__ __forceinline__ void forward_candidates(const EvalArgs& a, const StateRows& sr, int G, int H, int64_t lo, int64_t hi,
                                                    double* s_red, double* s_in) {
-  constexpr int SPT = 2 * P, DP = Row2<D>::DP;
+  constexpr int SPT = 2 * P, DP = Row2<D>::DP, NF = RowX<D>::NF;
   const int tid = threadIdx.x;
   double tsum[FUSED_MAXG], tmax[FUSED_MAXG];
   for (int g = 0; g < FUSED_MAXG; ++g) {
     tsum[g] = 0.0;
     tmax[g] = -INFINITY;
   }
+  u64 c2[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) c2[d] = pack2(sr.ctr[d], sr.ctr[d]);
   for (int64_t i0 = lo + (int64_t)tid * SPT; i0 < hi; i0 += (int64_t)blockDim.x * SPT) {
-    u64 s2[D][P];
+    u64 s2[D][P], s2n[P];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       if constexpr (P == 2) {
@@ -310,6 +404,18 @@ __device__ __forceinline__ void forward_candidates(const EvalArgs& a, const u64*
         s2[d][0] = pack2(s.x, s.y);
       }
     }
+#pragma unroll
+    for (int q = 0; q < P; ++q) s2n[q] = pack2(0.f, 0.f);
+    if (sr.xform) {
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          s2[d][q] = sub2(s2[d][q], c2[d]);
+          s2n[q] = fma2(s2[d][q], s2[d][q], s2n[q]);
+        }
+      }
+    }
     float qb[SPT];
 #pragma unroll
     for (int q = 0; q < SPT; ++q) qb[q] = (a.q_base && i0 + q < a.N) ? a.q_base[i0 + q] : 0.f;
@@ -319,7 +425,10 @@ __device__ __forceinline__ void forward_candidates(const EvalArgs& a, const u64*
       float emin[SPT], o[SPT];
 #pragma unroll
       for (int q = 0; q < P; ++q) acc[q] = pack2(0.f, 0.f);
-      pair_forward<D, P, 0>(s_x2 + (size_t)g * H * DP, H, s2, acc, emin);
+      if (sr.xform)
+        pair_forward_x<D, P, 0>(sr.rx + (size_t)g * H * NF, 0, H, s2, s2n, acc, emin);
+      else
+        pair_forward<D, P, 0>(sr.x2 + (size_t)g * H * DP, 0, H, s2, acc, emin);
 #pragma unroll
       for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
       double ts = tsum[g], tm = tmax[g];
@@ -364,18 +473,22 @@ __device__ __forceinline__ void forward_candidates(const EvalArgs& a, const u64*
 // ---------------------------------------------------------------------------
 // Row stride (floats) of the staged sample tiles: a compile-time constant so that the D+2 row addresses of a
 // tile are immediates off one base register (no address chain, fewer live registers in the pair loop).
-constexpr int TS_ROW = 2048;
+#define TILE_ROWS(D) ((D) + 3)
+// Sample tiles of the gradient pass live in a ring of NB buffers: TMA fills a buffer, the warps turn it into pair
+// operands (importance ratio, centred coordinates) one tile ahead of the pair math, and the warp that is last to
+// finish a buffer issues the TMA of the tile NB places further on - no CTA-wide barrier inside the pass.
+constexpr int TILE_NB = 4;
 
 struct SmemPlan {
-  size_t u, traj, dbarr, P, rot, x2, xs, tile, part, red, misc, ll, total;
+  size_t u, traj, dbarr, P, rot, x2, rx, xs, tile, adj, part, red, misc, ll, total;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 constexpr size_t LL_SCRATCH_BYTES = sizeof(double) * (LL_BUF_VALS + 32);
-constexpr size_t MISC_BYTES = 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 32;
+constexpr size_t MISC_BYTES = 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 8 + 16 * TILE_NB + 4 * TILE_NB + 8;
 
 template <int D>
-__host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, int nwarps, int WT) {
+__host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, int nwarps, int WT, int tsr) {
   SmemPlan p{};
   size_t o = 0;
   p.u = o;     o = align16(o + sizeof(float) * H * A);
@@ -384,41 +497,47 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.P = o;     o = align16(o + (roll ? sizeof(float) * H * A * A : 0));
   p.rot = o;   o = align16(o + (roll ? sizeof(float) * rollout_rot_floats(1, H) : 0));  // kept for the finisher
   p.x2 = o;    o = align16(o + sizeof(u64) * H * Row2<D>::DP);
+  p.rx = o;    o = align16(o + sizeof(float) * H * RowX<D>::NF);
   p.xs = o;    o = align16(o + sizeof(float) * H * D);
-  // two TMA buffers of rows s_0..s_{D-1}, v -> w, p; the second one doubles as the staging area of meeting (1),
-  // and the finisher's adjoint works in the first
-  size_t tile = sizeof(float) * (size_t)2 * (D + 2) * TS_ROW;
-  const size_t adj = sizeof(double) * ((size_t)H * D + 2) + sizeof(float) * ((size_t)H * S + adjoint_scratch_floats(H, A));
-  if (tile < adj) tile = adj;
-  p.tile = o;  o = align16(o + tile);
-  p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * D);
+  // ring of TMA buffers of rows s_0..s_{D-1}, v -> w, p (+ one row |sc|^2 computed in place); its second half
+  // doubles as the staging area of meeting (1), before the tiles that live there are requested
+  p.tile = o;  o = align16(o + sizeof(float) * (size_t)TILE_NB * TILE_ROWS(D) * tsr);
+  // the finisher's adjoint: gathered sums, dgdx, scratch, KL staging
+  p.adj = o;   o = align16(o + sizeof(double) * ((size_t)H * (D + 1) + 2) +
+                           sizeof(float) * ((size_t)H * S + adjoint_scratch_floats(H, A)) + sizeof(double) * (2 * LL_MAXBLK + 40));
+  p.part = o;  o = align16(o + sizeof(float) * (size_t)nwarps * WT * (D + 1));
   p.red = o;   o = align16(o + sizeof(double) * 32 * 4);
   p.misc = o;  o = align16(o + MISC_BYTES);
   p.total = o;
   return p;
 }
-static_assert(sizeof(float) * 3 * TS_ROW >= LL_SCRATCH_BYTES, "meeting staging must fit one tile buffer (D = 1)");
+static_assert(sizeof(float) * 2 * TILE_ROWS(1) * 768 >= LL_SCRATCH_BYTES, "meeting staging must fit two tile buffers (D = 1, 12 warps)");
 
 // ---------------------------------------------------------------------------
 // gradient eval
 // ---------------------------------------------------------------------------
-// MIXED: one chunk per warp, the last a.nwide warps own WT+1 states and the others WT, so that H states tile
+// MIXED, LEFT > 0 (balanced): every warp owns exactly WT states and the <= LEFT states that remain are shared - each
+// warp evaluates them on its own 64-sample chunks of every tile - so that all warps carry the same load (with
+// unequal state counts the CTA runs at the pace of its widest warps: the ring of sample tiles couples them).
+// MIXED, LEFT == 0: one chunk per warp, the last a.nwide warps own WT+1 states and the others WT, so that H states tile
 // any warp count exactly (no idle state slots) and the warp count can be a multiple of the 4 SM sub-partitions.
 // vblk / vnblk: index of this CTA among the CTAs of its rank (= blockIdx.x / gridDim.x except in the
 // one-GPU emulation of two ranks).
-template <int D, int WT, bool MIXED>
+template <int D, int WT, bool MIXED, int LEFT, int TSR>
 __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk, const int vnblk, unsigned char* smem) {
-  constexpr int WTA = MIXED ? WT + 1 : WT;  // accumulator rows per warp
+  constexpr int WTA = (MIXED && LEFT == 0) ? WT + 1 : WT;  // accumulator rows per warp
+  constexpr int LA = LEFT > 0 ? LEFT : 1;                  // shared (left-over) states, array extent
   const int H = a.H, S = a.d.S, A = a.d.A;
   const bool roll = a.d.kind == KLERG_DYN_ROLL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const SmemPlan sp = plan_grad<D>(H, S, A, roll, nwarps, WTA);
+  const SmemPlan sp = plan_grad<D>(H, S, A, roll, nwarps, WTA + LEFT, TSR);
   float* s_u = (float*)(smem + sp.u);
   float* s_traj = (float*)(smem + sp.traj);
   float* s_dbarr = (float*)(smem + sp.dbarr);
   float* s_P = roll ? (float*)(smem + sp.P) : nullptr;
   float* s_rot = (float*)(smem + sp.rot);
   u64* s_x2 = (u64*)(smem + sp.x2);
+  float* s_rx = (float*)(smem + sp.rx);
   float* s_xs = (float*)(smem + sp.xs);
   float* s_tile = (float*)(smem + sp.tile);
   float* s_part = (float*)(smem + sp.part);
@@ -426,21 +545,29 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   int* s_flag = (int*)(smem + sp.misc);
   unsigned* s_epoch = (unsigned*)(smem + sp.misc) + 1;
   float* s_bsum = (float*)(smem + sp.misc) + 3;
-  constexpr int DP = Row2<D>::DP;
+  float* s_ctr = (float*)(s_red + 32 * 2 + 4);  // [D] centre of the trajectory (scaled coordinates)
+  constexpr int NF = RowX<D>::NF;
+  constexpr int TR = TILE_ROWS(D);  // rows of a sample tile: s_0..s_{D-1}, v -> w, p, |sc|^2
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   void* me = a.peers.mail[a.peers.rank];
   const int world = a.peers.world;
-  const bool finisher = vblk == vnblk - 1;
 
   KLERG_STAMP_DECL;
   KLERG_STAMP(0);
   KLERG_CTA_STAMP(me, vblk, 0);
   // ---- phase 0: rollout, states only (every CTA) ----------------------------------------------------
   float* s_x0 = (float*)(smem + sp.misc) + 4;  // [S] (+ [9] R0)
-  unsigned long long* s_bar = (unsigned long long*)(smem + ((sp.misc + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 7) & ~(size_t)7));  // [2]
+  // tile ring bookkeeping: full[b] (TMA landed), conv[b] (all warps converted their share), done[b] (warps finished)
+  unsigned long long* s_full = (unsigned long long*)(smem + ((sp.misc + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 7) & ~(size_t)7));
+  unsigned long long* s_conv = s_full + TILE_NB;
+  int* s_done = (int*)(s_conv + TILE_NB);
   if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+#pragma unroll
+    for (int b = 0; b < TILE_NB; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_conv[b], (unsigned)nwarps);
+      s_done[b] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (!a.independent) pdl_wait_prior_grids();  // the previous launch may have produced this one's inputs
@@ -457,18 +584,14 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
                 s_bsum, nullptr, 1);
   KLERG_STAMP(9);
   const unsigned epoch = s_epoch[0], xc = s_epoch[1];
-  for (int e = tid; e < H * DP; e += blockDim.x) {
-    const int t = e / DP, d = e - t * DP;
-    float v = 0.f;
-    if (d < D) {
-      v = s_traj[t * S + a.k.explr[d]] * a.k.a[d];  // pre-step states (Robot.forward, klerg.py:419-431)
-      s_xs[t * D + d] = v;
-    }
-    s_x2[e] = pack2(v, v);
-  }
   if (vblk == 0 && a.traj)
     for (int e = tid; e < (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
-  __syncthreads();
+  // pre-step states (Robot.forward, klerg.py:419-431) in both pair forms; the expanded form while the trajectory
+  // stays within its radius around the middle state
+  StateRows sr;
+  sr.x2 = s_x2; sr.rx = s_rx; sr.ctr = s_ctr;
+  sr.xform = stage_state_rows<D>(a, s_traj, S, 1, H, 0, s_x2, s_rx, s_xs, s_ctr);
+  const bool xform = sr.xform;
 
   KLERG_STAMP(1);
   KLERG_CTA_STAMP(me, vblk, 1);
@@ -479,7 +602,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   double* s_in = s_world + 2;        // [2] this CTA
   {
     double tsum = 0.0, tmax = -INFINITY;
-    forward_slice<D>(a, s_x2, H, a.v, lo, hi, tsum, tmax);
+    forward_slice<D>(a, sr, H, a.v, lo, hi, tsum, tmax);
     const int kinds[2] = {RED_SUM, RED_MAX};
     double vals[2] = {tsum, tmax};
     block_reduce<2>(kinds, vals, s_red);
@@ -490,23 +613,37 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   }
   KLERG_STAMP(2);
   KLERG_CTA_STAMP(me, vblk, 2);
-  // The first sample tile of the gradient pass (samples, this CTA's own v, p) does not depend on the grid-wide
-  // totals: its TMA copies are issued now and land while the CTAs meet.
+  // The first sample tiles of the gradient pass (samples, this CTA's own v, p) do not depend on the grid-wide
+  // totals: their TMA copies are issued now and land while the CTAs meet.
+  const int ts = a.ts;
+  const int nt = (int)((hi - lo + ts - 1) / ts);       // tiles per sweep of this CTA's slice
+  const int g_total = a.K * a.rounds * nt;             // the launch's whole tile sequence: (target, round, tile)
+  // Tile g of the sequence goes to ring buffer g % NB; one thread issues its D+2 row copies as TMA bulk copies
+  // (contiguous runs, no descriptors) that complete on the buffer's `full` barrier.
+  auto issue_tile = [&](int g) {
+    const int b = g & (TILE_NB - 1), sidx = g / nt, t = g - sidx * nt;
+    const float* p_g = a.p + (int64_t)(sidx / a.rounds) * a.p_stride;
+    float* buf = s_tile + (size_t)b * TR * TSR;
+    const int64_t base = lo + (int64_t)t * ts;
+    const unsigned bytes = 4u * (unsigned)min((int64_t)ts, hi - base);  // multiple of 16
+    fence_proxy_async();  // the buffer was last written with ordinary stores (importance ratio, padding)
+    mbar_expect_tx(&s_full[b], (D + 2) * bytes);
+#pragma unroll
+    for (int d = 0; d < D; ++d) tma_bulk_g2s(buf + (size_t)d * TSR, a.packed + (int64_t)d * a.ld + base, bytes, &s_full[b]);
+    tma_bulk_g2s(buf + (size_t)D * TSR, a.v + base, bytes, &s_full[b]);
+    tma_bulk_g2s(buf + (size_t)(D + 1) * TSR, p_g + base, bytes, &s_full[b]);
+  };
   fence_proxy_async();  // v was written with ordinary stores and is read back by TMA
   __syncthreads();
-  if (tid == 0 && hi > lo) {
-    const unsigned bytes = 4u * (unsigned)min((int64_t)a.ts, hi - lo);
-    mbar_expect_tx(&s_bar[0], (D + 2) * bytes);
-#pragma unroll
-    for (int d = 0; d < D; ++d) tma_bulk_g2s(s_tile + (size_t)d * TS_ROW, a.packed + (int64_t)d * a.ld + lo, bytes, &s_bar[0]);
-    tma_bulk_g2s(s_tile + (size_t)D * TS_ROW, a.v + lo, bytes, &s_bar[0]);
-    tma_bulk_g2s(s_tile + (size_t)(D + 1) * TS_ROW, a.p + lo, bytes, &s_bar[0]);
-  }
+  if (tid == 0)
+    for (int g = 0; g < 2 && g < g_total; ++g) issue_tile(g);
   // ---- meeting (1): {sum, max} over every CTA of every rank ----------------------------------------
   // Slots of this launch's first gather exchange (number xc) are about to be reused from exchange xc - 2: wait until
   // that one has been consumed (always true in practice; makes the slot reuse safe by construction).
   if (tid == 0) ll_wait_exchange_free(me, xc, ctrl);
-  ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2, 0x2u, s_in, s_world, (double*)(s_tile + (size_t)(D + 2) * TS_ROW), ctrl);
+  ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2, 0x2u, s_in, s_world, (double*)(s_tile + (size_t)2 * TR * TSR), ctrl);
+  if (tid == 0)  // the staging area is free again: request the tiles that live there
+    for (int g = 2; g < TILE_NB && g < g_total; ++g) issue_tile(g);
   if (vblk == 0 && tid == 0) {
     // every CTA holds epoch / xc in registers by now: bump the counters for the next launch, which may start
     // as soon as all CTAs have passed this point
@@ -528,125 +665,264 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   const float maxc_f = (float)fmax(vmax / vsum, (double)a.floor);
 
   // ---- phase 2: importance ratio + gradient pair pass ----------------------------------------------
-  const int ts = a.ts;
-  // loop-invariant launch parameters of the pair loop, pinned through shared memory (see pin_params)
-  if (tid == 0) s_flag[4 + KLERG_MAX_S + 9] = a.nsub * 64;
+  // loop-invariant launch parameters of the pair loop, pinned through shared memory (see pin_params); so are the
+  // few scalars only needed again after the pair loop (they would otherwise cost it registers)
+  if (tid == 0) {
+    s_flag[4 + KLERG_MAX_S + 9] = a.nsub * 64;
+    s_flag[4 + KLERG_MAX_S + 10] = vblk;
+    s_flag[4 + KLERG_MAX_S + 11] = vnblk;
+  }
   __syncthreads();
   const int pb_step = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 9];
-  const int HD = H * D;
+  const int HD = H * D, NE = HD + H;  // gather entries: A[t][d] = sum w psi sc_d, then W[t] = sum w psi
   const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
-  int tile_seq = 0;  // tiles streamed so far in this launch (same in every thread)
+  double kl_a[2] = {0.0, 0.0}, kl_c[2] = {0.0, 0.0};  // by target parity (tiles are converted one tile ahead)
+
+  // Turn this warp's share of tile g = (target kt_g, round r_g, tile t) into pair operands, in place: v -> importance
+  // ratio w = p/q (klerg.py:436); expanded form: samples centred and |sc|^2; rows beyond the slice zeroed.
+  // 64-sample chunks, chunk c by warp c % nwarps, two samples per lane as one packed pair.  Ends with the warp's
+  // arrival on conv[b].
+  auto convert_tile = [&](int g, int kt_g, int r_g, int t) {
+    const int b = g & (TILE_NB - 1);
+    float* buf = s_tile + (size_t)b * TR * TSR;
+    const int64_t base = lo + (int64_t)t * ts;
+    const int cnt = (int)min((int64_t)ts, hi - base);
+    const int cnt64 = (cnt + 63) & ~63;
+    float* wrow = buf + (size_t)D * TSR;
+    const float* prow = buf + (size_t)(D + 1) * TSR;
+    float* nrow = buf + (size_t)(D + 2) * TSR;
+    KLERG_SPIN_UNTIL(mbar_try_wait(&s_full[b], (unsigned)(g / TILE_NB) & 1u), ctrl)
+    for (int c = warp; c < (cnt64 >> 6); c += nwarps) {
+      const int e = (c << 6) + 2 * lane;
+      const float2 vv = *reinterpret_cast<const float2*>(&wrow[e]);
+      const float2 pp = *reinterpret_cast<const float2*>(&prow[e]);
+      const bool in0 = e < cnt && base + e < a.N, in1 = e + 1 < cnt && base + e + 1 < a.N;
+      const float c0 = fmaxf(__fdividef(vv.x, vsum_f), a.floor), c1 = fmaxf(__fdividef(vv.y, vsum_f), a.floor);
+      const float w0 = in0 ? __fdividef(pp.x * maxc_f, c0) : 0.f, w1 = in1 ? __fdividef(pp.y * maxc_f, c1) : 0.f;
+      if (want_kl && r_g == 0) {
+        if (in0) { kl_a[kt_g & 1] += (double)(pp.x * (logf(pp.x) - logf(c0))); kl_c[kt_g & 1] += (double)c0; }
+        if (in1) { kl_a[kt_g & 1] += (double)(pp.y * (logf(pp.y) - logf(c1))); kl_c[kt_g & 1] += (double)c1; }
+      }
+      u64 n2 = pack2(0.f, 0.f);
+      if (e >= cnt) {  // cnt is even: the pair lies beyond the slice as a whole
+#pragma unroll
+        for (int d = 0; d < D; ++d) *reinterpret_cast<u64*>(&buf[(size_t)d * TSR + e]) = pack2(0.f, 0.f);
+      } else if (xform) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          u64* sp2 = reinterpret_cast<u64*>(&buf[(size_t)d * TSR + e]);
+          const u64 sc = sub2(*sp2, pack2(s_ctr[d], s_ctr[d]));
+          *sp2 = sc;
+          n2 = fma2(sc, sc, n2);
+        }
+      }
+      *reinterpret_cast<float2*>(&wrow[e]) = make_float2(w0, w1);
+      *reinterpret_cast<u64*>(&nrow[e]) = n2;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_conv[b]);
+  };
+  static_assert((TILE_NB & (TILE_NB - 1)) == 0, "ring size must be a power of two");
+  if (g_total > 0) convert_tile(0, 0, 0, 0);
+
   for (int kt = 0; kt < a.K; ++kt) {  // belief targets: the forward pass above is shared, p_k differs
-  const float* p_k = a.p + (int64_t)kt * a.p_stride;
-  const unsigned xnum = xc + (unsigned)kt;       // number of this target's gather exchange
-  const int xpar = xnum & 1u;
-  const unsigned xtag = ll_tag(xnum, 0x80u);
-  double kl_a = 0.0, kl_c = 0.0;
-  if (kt > 0 && tid == 0) ll_wait_exchange_free(me, xnum, ctrl);  // ordered before the slot stores by the barriers below
+  if (kt > 0 && tid == 0) ll_wait_exchange_free(me, xc + (unsigned)kt, ctrl);  // ordered before the slot stores by the barriers below
   for (int r = 0; r < a.rounds; ++r) {
     int cw = warp % a.nchr, sub = warp / a.nchr;
     int t0 = (r * a.nchr + cw) * WT, my_wt = WT;
     bool active = sub < a.nsub && t0 < H;
     if (MIXED) {
-      const int narrow = nwarps - a.nwide;
-      const bool wide = warp >= narrow;
-      t0 = warp * WT + (wide ? warp - narrow : 0);
-      my_wt = WT + (wide ? 1 : 0);
+      if (LEFT > 0) {
+        t0 = warp * WT;
+      } else {
+        const int narrow = nwarps - a.nwide;
+        const bool wide = warp >= narrow;
+        t0 = warp * WT + (wide ? warp - narrow : 0);
+        my_wt = WT + (wide ? 1 : 0);
+      }
       sub = 0;
       active = true;
     }
-    u64 xs2[WTA][D], acc[WTA][D];
+    const int left0 = nwarps * WT;  // balanced schedule: first shared state
+    u64 acc[WTA][D], wacc[WTA], lacc[LA][D], lwacc[LA];
 #pragma unroll
-    for (int k = 0; k < WTA; ++k)
+    for (int k = 0; k < WTA; ++k) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const float x = (active && k < my_wt && t0 + k < H) ? s_xs[(t0 + k) * D + d] : 0.f;
-        xs2[k][d] = pack2(x, x);
-        acc[k][d] = pack2(0.f, 0.f);
+      for (int d = 0; d < D; ++d) acc[k][d] = pack2(0.f, 0.f);
+      wacc[k] = pack2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < LA; ++k) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) lacc[k][d] = pack2(0.f, 0.f);
+      lwacc[k] = pack2(0.f, 0.f);
+    }
+    const int g_base = (kt * a.rounds + r) * nt;
+    // The sweep over the slice's tiles exists once per pair form (the form is uniform over the launch), so that only
+    // that form's copy of the warp's states lives in registers: difference form {x', x'} pairs, expanded form
+    // -2 xc and |xc|^2.
+    auto run_tiles = [&](auto xf_tag) {
+      constexpr bool XF = decltype(xf_tag)::value;
+      u64 xs2[XF ? 1 : WTA][D], lxs2[XF ? 1 : LA][D];
+      float m2x[XF ? WTA : 1][D], x2n[XF ? WTA : 1], lm2x[XF ? LA : 1][D], lx2n[XF ? LA : 1];
+#pragma unroll
+      for (int k = 0; k < WTA; ++k) {
+        const bool have = active && k < my_wt && t0 + k < H;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          if constexpr (XF)
+            m2x[k][d] = have ? s_rx[(t0 + k) * NF + d] : 0.f;
+          else
+            xs2[k][d] = have ? s_x2[(t0 + k) * Row2<D>::DP + d] : pack2(0.f, 0.f);
+        }
+        if constexpr (XF) x2n[k] = have ? s_rx[(t0 + k) * NF + D] : 0.f;
       }
-    // Sample tiles stream global -> shared one tile ahead of the pair math:
-    // rows s_0..s_{D-1} (scaled samples), q_base + q_iter (turned into the importance ratio in place), p.
-    const int nt = (int)((hi - lo + ts - 1) / ts);
-    // One thread issues the D+2 row copies of a tile as TMA bulk copies (contiguous runs, no descriptors) that
-    // complete on the tile buffer's mbarrier; everybody else keeps computing.  Tile g of this launch uses buffer
-    // g & 1 and the (g >> 1)-th phase of its barrier.
-    auto issue_tile = [&](int k) {
-      if (tid == 0) {
-        const int gidx = tile_seq + k;
-        float* buf = s_tile + (size_t)(gidx & 1) * (D + 2) * TS_ROW;
-        const int64_t base = lo + (int64_t)k * ts;
-        const unsigned bytes = 4u * (unsigned)min((int64_t)ts, hi - base);  // multiple of 16
-        fence_proxy_async();  // the buffer was last written with ordinary stores (importance ratio, padding)
-        mbar_expect_tx(&s_bar[gidx & 1], (D + 2) * bytes);
+      if constexpr (LEFT > 0) {
 #pragma unroll
-        for (int d = 0; d < D; ++d)
-          tma_bulk_g2s(buf + (size_t)d * TS_ROW, a.packed + (int64_t)d * a.ld + base, bytes, &s_bar[gidx & 1]);
-        tma_bulk_g2s(buf + (size_t)D * TS_ROW, a.v + base, bytes, &s_bar[gidx & 1]);
-        tma_bulk_g2s(buf + (size_t)(D + 1) * TS_ROW, p_k + base, bytes, &s_bar[gidx & 1]);
+        for (int k = 0; k < LA; ++k) {
+          const bool have = left0 + k < H;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            if constexpr (XF)
+              lm2x[k][d] = have ? s_rx[(left0 + k) * NF + d] : 0.f;
+            else
+              lxs2[k][d] = have ? s_x2[(left0 + k) * Row2<D>::DP + d] : pack2(0.f, 0.f);
+          }
+          if constexpr (XF) lx2n[k] = have ? s_rx[(left0 + k) * NF + D] : 0.f;
+        }
+      }
+      for (int t = 0; t < nt; ++t) {
+        const int g = g_base + t, b = g & (TILE_NB - 1);
+        if (g + 1 < g_total) {  // one tile ahead (possibly the next round's / target's first)
+          const bool wrap_t = t + 1 == nt, wrap_r = wrap_t && r + 1 == a.rounds;
+          convert_tile(g + 1, kt + (wrap_r ? 1 : 0), wrap_r ? 0 : r + (wrap_t ? 1 : 0), wrap_t ? 0 : t + 1);
+        }
+        float* buf = s_tile + (size_t)b * TR * TSR;
+        const int64_t base = lo + (int64_t)t * ts;
+        const int cnt = (int)min((int64_t)ts, hi - base);
+        const int cnt64 = (cnt + 63) & ~63;
+        const float* wrow = buf + (size_t)D * TSR;
+        const float* nrow = buf + (size_t)(D + 2) * TSR;
+        KLERG_SPIN_UNTIL(mbar_try_wait(&s_conv[b], (unsigned)(g / TILE_NB) & 1u), ctrl)
+        if (active) {
+          if constexpr (XF) {
+            // warp-uniform: this warp owns WTA or WTA - 1 states
+            auto sweep = [&](auto ns_tag) {
+              constexpr int NS = decltype(ns_tag)::value;
+              for (int pb = sub * 64; pb < cnt64; pb += pb_step) {
+                const int i = pb + 2 * lane;
+                u64 s2[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TSR + i]);
+                const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
+                const u64 n2 = *reinterpret_cast<const u64*>(&nrow[i]);
+                pair_gradient_x<D, WTA, NS>(m2x, x2n, s2, n2, w2, acc, wacc);
+              }
+            };
+            if (WTA == 1 || my_wt == WTA)
+              sweep(std::integral_constant<int, WTA>{});
+            else
+              sweep(std::integral_constant<int, (WTA > 1 ? WTA - 1 : 1)>{});
+          } else {
+            for (int pb = sub * 64; pb < cnt64; pb += pb_step) {
+              const int i = pb + 2 * lane;
+              u64 s2[D];
+#pragma unroll
+              for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TSR + i]);
+              const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
+              pair_gradient<D, WTA>(xs2, s2, w2, acc, my_wt == WTA);
+            }
+          }
+        }
+        if constexpr (LEFT > 0) {
+          // the shared states, on this warp's own 64-sample chunks of the tile (chunk c by warp c % nwarps)
+          if (left0 < H) {
+            for (int c = warp; c < (cnt64 >> 6); c += nwarps) {
+              const int i = (c << 6) + 2 * lane;
+              u64 s2[D];
+#pragma unroll
+              for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TSR + i]);
+              const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
+              if constexpr (XF) {
+                const u64 n2 = *reinterpret_cast<const u64*>(&nrow[i]);
+                pair_gradient_x<D, LA, LA>(lm2x, lx2n, s2, n2, w2, lacc, lwacc);
+              } else {
+                pair_gradient<D, LA>(lxs2, s2, w2, lacc, true);
+              }
+            }
+          }
+        }
+        // this warp is done with buffer b; the last warp to say so requests the tile NB places further on
+        __syncwarp();
+        if (lane == 0) {
+          const int old = atomicAdd(&s_done[b], 1);
+          if (old == nwarps - 1) {
+            s_done[b] = 0;
+            if (g + TILE_NB < g_total) issue_tile(g + TILE_NB);
+          }
+        }
       }
     };
-    if (nt > 0 && tile_seq > 0) issue_tile(0);  // the very first tile of the launch was issued before the meeting point
-    for (int k = 0; k < nt; ++k) {
-      const int gidx = tile_seq + k;
-      float* buf = s_tile + (size_t)(gidx & 1) * (D + 2) * TS_ROW;
-      const int64_t base = lo + (int64_t)k * ts;
-      const int cnt = (int)min((int64_t)ts, hi - base);
-      const int cnt64 = (cnt + 63) & ~63;
-      float* wrow = buf + (size_t)D * TS_ROW;
-      const float* prow = buf + (size_t)(D + 1) * TS_ROW;
-      KLERG_SPIN_UNTIL(mbar_try_wait(&s_bar[gidx & 1], (unsigned)(gidx >> 1) & 1u), ctrl)
-      for (int c = tid; c < (cnt64 >> 2); c += blockDim.x) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int e = (c << 2) + q;
-          const int64_t i = base + e;
-          float w = 0.f;
-          if (e < cnt && i < a.N) {
-            const float cc = fmaxf(__fdividef(wrow[e], vsum_f), a.floor);
-            const float pi = prow[e];
-            w = __fdividef(pi * maxc_f, cc);  // p/q with q = c / max c  (klerg.py:436)
-            if (want_kl && r == 0) {
-              kl_a += (double)(pi * (logf(pi) - logf(cc)));
-              kl_c += (double)cc;
-            }
-          } else if (e >= cnt) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) buf[(size_t)d * TS_ROW + e] = 0.f;
-          }
-          wrow[e] = w;
-        }
-      }
-      __syncthreads();  // tile k is ready for everyone; everyone is done with tile k-1
-      if (k + 1 < nt) issue_tile(k + 1);
-      if (active) {
-        for (int pb = sub * 64; pb < cnt64; pb += pb_step) {
-          const int i = pb + 2 * lane;
-          u64 s2[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TS_ROW + i]);
-          const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
-          pair_gradient<D, WTA>(xs2, s2, w2, acc, my_wt == WTA);
-        }
-      }
-    }
-    tile_seq += nt;
+    if (xform)
+      run_tiles(std::true_type{});
+    else
+      run_tiles(std::false_type{});
     __syncthreads();
-    // lanes -> warp sums -> CTA partial for this round's states
+    // lanes -> warp sums -> CTA partial for this round's states.  Gather entries are A[t][d] and W[t] with
+    // dgdx = gfac (xc W - A); the difference form holds sum w psi (x' - s') directly: A = -acc, W = 0.
 #pragma unroll
-    for (int k = 0; k < WTA; ++k)
+    for (int k = 0; k < WTA; ++k) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         float x, y;
         unpack2(acc[k][d], x, y);
         const float v = warp_sum_f(x + y);
-        if (lane == 0) s_part[(warp * WTA + k) * D + d] = v;
+        if (lane == 0) s_part[(warp * WTA + k) * (D + 1) + d] = xform ? v : -v;
       }
+      float x, y;
+      unpack2(wacc[k], x, y);
+      const float v = warp_sum_f(x + y);
+      if (lane == 0) s_part[(warp * WTA + k) * (D + 1) + D] = v;
+    }
+    float* s_left = s_part + (size_t)nwarps * WTA * (D + 1);  // [nwarps][LEFT][D + 1] partials of the shared states
+    if constexpr (LEFT > 0) {
+#pragma unroll
+      for (int k = 0; k < LA; ++k) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          float x, y;
+          unpack2(lacc[k][d], x, y);
+          const float v = warp_sum_f(x + y);
+          if (lane == 0) s_left[(warp * LA + k) * (D + 1) + d] = xform ? v : -v;
+        }
+        float x, y;
+        unpack2(lwacc[k], x, y);
+        const float v = warp_sum_f(x + y);
+        if (lane == 0) s_left[(warp * LA + k) * (D + 1) + D] = v;
+      }
+    }
     __syncthreads();
-    // this CTA's partial of gradient entry e goes to slot [e][vblk] as ONE tagged word (fp32 value + tag)
-    if (MIXED) {
+    // this CTA's partial of gather entry e goes to slot [e][vblk] as ONE tagged word (fp32 value + tag)
+    {
+    const int my_blk = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 10];
+    const unsigned xnum_ = s_epoch[1] + (unsigned)kt;
+    const int xpar_ = xnum_ & 1u;
+    const unsigned xtag_ = ll_tag(xnum_, 0x80u);
+    if (MIXED && LEFT > 0) {
+      for (int e = tid; e < NE; e += blockDim.x) {
+        const int t = e < HD ? e / D : e - HD, d = e < HD ? e - t * D : D;
+        float v = 0.f;
+        if (t < left0) {
+          v = s_part[t * (D + 1) + d];  // (w * WT + k) = t
+        } else {
+          for (int w = 0; w < nwarps; ++w) v += s_left[(w * LA + (t - left0)) * (D + 1) + d];
+        }
+        ll_store_f32(mb_gp(me, xpar_, e) + my_blk, v, xtag_);
+      }
+    } else if (MIXED) {
       const int narrow = nwarps - a.nwide, narrow_states = narrow * WT;
-      for (int e = tid; e < HD; e += blockDim.x) {
-        const int t = e / D, d = e - t * D;
+      for (int e = tid; e < NE; e += blockDim.x) {
+        const int t = e < HD ? e / D : e - HD, d = e < HD ? e - t * D : D;
         int w, k;
         if (t < narrow_states) {
           w = t / WT;
@@ -656,37 +932,44 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
           w = narrow + tt / (WT + 1);
           k = tt - (w - narrow) * (WT + 1);
         }
-        ll_store_f32(mb_gp(me, xpar, e) + vblk, s_part[(w * WTA + k) * D + d], xtag);
+        ll_store_f32(mb_gp(me, xpar_, e) + my_blk, s_part[(w * WTA + k) * (D + 1) + d], xtag_);
       }
     } else
-    for (int e = tid; e < a.nchr * WT * D; e += blockDim.x) {
-      const int c = e / (WT * D), kd = e - c * (WT * D);
-      const int t = (r * a.nchr + c) * WT + kd / D;
+    for (int e = tid; e < a.nchr * WT * (D + 1); e += blockDim.x) {
+      const int c = e / (WT * (D + 1)), kd = e - c * (WT * (D + 1));
+      const int t = (r * a.nchr + c) * WT + kd / (D + 1), d = kd % (D + 1);
       if (t < H) {
         float v = 0.f;
-        for (int sb = 0; sb < a.nsub; ++sb) v += s_part[((sb * a.nchr + c) * WT) * D + kd];
-        ll_store_f32(mb_gp(me, xpar, t * D + kd % D) + vblk, v, xtag);
+        for (int sb = 0; sb < a.nsub; ++sb) v += s_part[((sb * a.nchr + c) * WT) * (D + 1) + kd];
+        ll_store_f32(mb_gp(me, xpar_, d < D ? t * D + d : HD + t) + my_blk, v, xtag_);
       }
     }
+    }
   }
+  // (re)read what the pair loop did not keep in registers
+  const int vblk_ = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 10], vnblk_ = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 11];
+  const unsigned xnum = s_epoch[1] + (unsigned)kt;  // number of this target's gather exchange
+  const int xpar = xnum & 1u;
+  const unsigned xtag = ll_tag(xnum, 0x80u);
   if (want_kl) {
     const int kinds[2] = {RED_SUM, RED_SUM};
-    double vals[2] = {kl_a, kl_c};
+    double vals[2] = {kl_a[kt & 1], kl_c[kt & 1]};
+    kl_a[kt & 1] = kl_c[kt & 1] = 0.0;
     block_reduce<2>(kinds, vals, s_red);
     if (tid == 0) {
-      ll_store(mb_kl(me, xpar, vblk), vals[0], xtag);
-      ll_store(mb_kl(me, xpar, vblk) + 2, vals[1], xtag);
+      ll_store(mb_kl(me, xpar, vblk_), vals[0], xtag);
+      ll_store(mb_kl(me, xpar, vblk_) + 2, vals[1], xtag);
     }
   }
 
-  // ---- phase 3: warps spread over the grid add the CTA partials of one gradient entry each (fixed order) and
-  //      hand the sum to every rank; the finisher CTA collects the H*D sums of all ranks and runs the adjoint ----
+  // ---- phase 3: warps spread over the grid add the CTA partials of one gather entry each (fixed order) and
+  //      hand the sum to every rank; the finisher CTA collects the sums of all ranks and runs the adjoint ----
   KLERG_STAMP(4);
-  KLERG_CTA_STAMP(me, vblk, 4);
-  for (int e = vblk + vnblk * warp; e < HD; e += vnblk * nwarps) {
+  KLERG_CTA_STAMP(me, vblk_, 4);
+  for (int e = vblk_ + vnblk_ * warp; e < NE; e += vnblk_ * nwarps) {
     const u64* row = mb_gp(me, xpar, e);
     double v = 0.0;
-    for (int b = lane; b < vnblk; b += 32) {
+    for (int b = lane; b < vnblk_; b += 32) {
       float x = 0.f;
       KLERG_SPIN_UNTIL(ll_try_load_f32(row + b, xtag, x), ctrl)
       v += (double)x;
@@ -694,8 +977,8 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     v = warp_reduce(RED_SUM, v);
     if (lane < world) ll_store(mb_gb(a.peers.mail[lane], xpar, a.peers.rank) + 2 * e, v, xtag);
   }
-  KLERG_CTA_STAMP(me, vblk, 5);
-  if (!finisher) continue;
+  KLERG_CTA_STAMP(me, vblk_, 5);
+  if (vblk_ != vnblk_ - 1) continue;
   KLERG_STAMP(5);
   if (kt == 0) {
     // what only the adjoint needs: linearisation blocks, dbarr, barrier sum
@@ -704,25 +987,26 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
                   s_bsum, nullptr, 2);
   }
   __syncthreads();
-  double* s_val = (double*)s_tile;               // [HD + 2]
-  float* s_g = (float*)(s_val + HD + 2);         // [H][S]
+  // the finisher's own scratch (the tile ring may already hold tiles of the next target)
+  double* s_val = (double*)(smem + sp.adj);      // [NE + 2]
+  float* s_g = (float*)(s_val + NE + 2);         // [H][S]
   float* s_scr = s_g + H * S;                    // adjoint scratch
   if (want_kl) {
-    // KL terms of this rank: CTA partials in CTA order, then to every rank like a gradient entry
-    double* s_stage = (double*)(s_tile + (size_t)(D + 2) * TS_ROW);
-    for (int idx = tid; idx < vnblk * 2; idx += blockDim.x) {
+    // KL terms of this rank: CTA partials in CTA order, then to every rank like a gather entry
+    double* s_stage = (double*)(((uintptr_t)(s_scr + adjoint_scratch_floats(H, A)) + 7) & ~(uintptr_t)7);  // [2 vnblk] + [2] + [32]
+    for (int idx = tid; idx < vnblk_ * 2; idx += blockDim.x) {
       double x = 0.0;
       KLERG_SPIN_UNTIL(ll_try_load(mb_kl(me, xpar, idx >> 1) + 2 * (idx & 1), xtag, x), ctrl)
       s_stage[idx] = x;
     }
     __syncthreads();
-    ll_reduce_staged(s_stage, vnblk, 2, 0u, s_stage + LL_BUF_VALS - 2, s_stage + LL_BUF_VALS);
+    ll_reduce_staged(s_stage, vnblk_, 2, 0u, s_stage + 2 * LL_MAXBLK, s_stage + 2 * LL_MAXBLK + 2);
     if (tid < world * 2) {
       const int rr = tid >> 1, i = tid & 1;
-      ll_store(mb_gb(a.peers.mail[rr], xpar, a.peers.rank) + 2 * (HD + i), s_stage[LL_BUF_VALS - 2 + i], xtag);
+      ll_store(mb_gb(a.peers.mail[rr], xpar, a.peers.rank) + 2 * (NE + i), s_stage[2 * LL_MAXBLK + i], xtag);
     }
   }
-  for (int e = tid; e < HD + (want_kl ? 2 : 0); e += blockDim.x) {
+  for (int e = tid; e < NE + (want_kl ? 2 : 0); e += blockDim.x) {
     double v = 0.0;
     for (int rr = 0; rr < world; ++rr) {
       double x = 0.0;
@@ -732,15 +1016,16 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     s_val[e] = v;
   }
   if (!want_kl && tid == 0) {
-    s_val[HD] = 0.0;
-    s_val[HD + 1] = 1.0;
+    s_val[NE] = 0.0;
+    s_val[NE + 1] = 1.0;
   }
   KLERG_STAMP(6);
   for (int e = tid; e < H * S; e += blockDim.x) s_g[e] = 0.f;
   __syncthreads();
   for (int e = tid; e < HD; e += blockDim.x) {
-    const int d = e % D;
-    s_g[(e / D) * S + a.k.explr[d]] = (float)(s_val[e] * (double)a.k.gfac[d]);
+    const int t = e / D, d = e - t * D;
+    // dgdx_t[d] = gfac_d * sum_i w psi (x'_td - s'_id) = gfac_d * (xc_td W_t - A_td), formed in double
+    s_g[t * S + a.k.explr[d]] = (float)(((double)s_xs[e] * s_val[HD + t] - s_val[e]) * (double)a.k.gfac[d]);
   }
   __syncthreads();
   for (int e = tid; e < H * S; e += blockDim.x) {
@@ -752,7 +1037,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   adjoint_block(a.d, a.ap, H, s_g, s_P, s_traj, s_u, s_scr, a.du + (size_t)kt * H * A, a.djdlam + (size_t)kt * H,
                 a.u_star + (size_t)kt * H * A);
   if (tid == 0) {
-    const double sa = s_val[HD], sc = s_val[HD + 1];
+    const double sa = s_val[NE], sc = s_val[NE + 1];
     if (a.kl_out) {
       a.kl_out[2 * kt] = sa;
       a.kl_out[2 * kt + 1] = sc;
@@ -771,30 +1056,30 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
 #ifdef KLERG_STAMPS
     // phase stamps of the finisher (SM cycles since its start): profiling aid
     KLERG_STAMP(7);
-    KLERG_CTA_STAMP(me, vblk, 6);
+    KLERG_CTA_STAMP(me, vblk_, 6);
     long long* dbg = (long long*)(ctrl + 16);
     for (int i = 0; i < 10; ++i) dbg[i] = stamp[i] - stamp[0];
     for (int i = 0; i < 8; ++i) dbg[10 + i] = g_ro_stamp[i] - g_ro_stamp[0];
 #endif
   }
-  __syncthreads();  // the finisher reuses its tile area for the next target
+  __syncthreads();
   }  // targets
 }
 
-template <int D, int WT, int MAXT, bool MIXED>
+template <int D, int WT, int MAXT, bool MIXED, int LEFT>
 __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const __grid_constant__ EvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  eval_grad_body<D, WT, MIXED>(a, (int)blockIdx.x, (int)gridDim.x, smem);
+  eval_grad_body<D, WT, MIXED, LEFT, 2 * MAXT>(a, (int)blockIdx.x, (int)gridDim.x, smem);
 }
 // two ranks on one GPU (tests): CTAs [0, nb) act as rank 0 with a0, CTAs [nb, 2 nb) as rank 1 with a1
-template <int D, int WT, int MAXT, bool MIXED>
+template <int D, int WT, int MAXT, bool MIXED, int LEFT>
 __global__ void __launch_bounds__(MAXT) eval_grad_emu_kernel(const __grid_constant__ EvalArgs a0,
                                                              const __grid_constant__ EvalArgs a1, const int nb) {
   extern __shared__ __align__(16) unsigned char smem[];
   if ((int)blockIdx.x < nb)
-    eval_grad_body<D, WT, MIXED>(a0, (int)blockIdx.x, nb, smem);
+    eval_grad_body<D, WT, MIXED, LEFT, 2 * MAXT>(a0, (int)blockIdx.x, nb, smem);
   else
-    eval_grad_body<D, WT, MIXED>(a1, (int)blockIdx.x - nb, nb, smem);
+    eval_grad_body<D, WT, MIXED, LEFT, 2 * MAXT>(a1, (int)blockIdx.x - nb, nb, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -807,6 +1092,7 @@ __host__ __device__ inline SmemPlan plan_cost(int G, int H, int S, int A, bool r
   p.u = o;    o = align16(o + sizeof(float) * (size_t)G * H * A);
   p.traj = o; o = align16(o + sizeof(float) * (size_t)G * (H + 1) * S);
   p.x2 = o;   o = align16(o + sizeof(u64) * (size_t)G * H * Row2<D>::DP);
+  p.rx = o;   o = align16(o + sizeof(float) * (size_t)G * H * RowX<D>::NF);
   p.tile = o; o = align16(o + (roll ? sizeof(float) * rollout_rot_floats(G, H) : 0));
   p.red = o;  o = align16(o + sizeof(double) * (32 * 2 * FUSED_MAXG + 4 * FUSED_MAXG));
   p.misc = o; o = align16(o + 64 + sizeof(float) * FUSED_MAXG);
@@ -823,13 +1109,14 @@ __device__ __forceinline__ void eval_cost_body(const EvalArgs& a, const int vblk
   float* s_u = (float*)(smem + sp.u);
   float* s_traj = (float*)(smem + sp.traj);
   u64* s_x2 = (u64*)(smem + sp.x2);
+  float* s_rx = (float*)(smem + sp.rx);
   double* s_red = (double*)(smem + sp.red);
   double* s_world = s_red + 32 * 2 * FUSED_MAXG;  // [2G] all ranks
   double* s_in = s_world + 2 * FUSED_MAXG;        // [2G] this CTA
   unsigned* s_epoch = (unsigned*)(smem + sp.misc) + 1;
+  float* s_ctr = (float*)(smem + sp.misc) + 4;    // [D]
   float* s_bsum = (float*)(smem + sp.misc + 64);
   double* s_ll = (double*)(smem + sp.ll);
-  constexpr int DP = Row2<D>::DP;
   unsigned* ctrl = ws_fused_ctrl(a.ws);
   void* me = a.peers.mail[a.peers.rank];
   const int world = a.peers.world;
@@ -844,23 +1131,19 @@ __device__ __forceinline__ void eval_cost_body(const EvalArgs& a, const int vblk
   rollout_block(a.d, a.bar, a.x0, a.R0, s_u, G, H, s_traj, nullptr, nullptr, (float*)(smem + sp.tile), (float*)s_red,
                 s_bsum, nullptr);
   const unsigned epoch = s_epoch[0], xc = s_epoch[1];
-  for (int e = tid; e < G * H * DP; e += blockDim.x) {
-    const int g = e / (H * DP), r = e - g * (H * DP);
-    const int t = r / DP, d = r - t * DP;
-    float v = 0.f;
-    if (d < D) v = s_traj[((size_t)g * (H + 1) + t + 1) * S + a.k.explr[d]] * a.k.a[d];  // post-step states (klerg.py:688-691)
-    s_x2[e] = pack2(v, v);
-  }
   if (vblk == 0 && a.traj)
     for (int e = tid; e < G * (H + 1) * S; e += blockDim.x) a.traj[e] = s_traj[e];
-  __syncthreads();
+  // post-step states of every candidate (klerg.py:688-691) in both pair forms, centred on candidate 0's middle state
+  StateRows sr;
+  sr.x2 = s_x2; sr.rx = s_rx; sr.ctr = s_ctr;
+  sr.xform = stage_state_rows<D>(a, s_traj + S, S, G, H, (size_t)(H + 1) * S, s_x2, s_rx, nullptr, s_ctr);
 
   int64_t lo, hi;
   cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
   if (narrow_pairs(lo, hi))
-    forward_candidates<D, 1>(a, s_x2, G, H, lo, hi, s_red, s_in);
+    forward_candidates<D, 1>(a, sr, G, H, lo, hi, s_red, s_in);
   else
-    forward_candidates<D, 2>(a, s_x2, G, H, lo, hi, s_red, s_in);
+    forward_candidates<D, 2>(a, sr, G, H, lo, hi, s_red, s_in);
   // meeting (1): {sum, max} per candidate over every CTA of every rank
   if (tid == 0) ll_wait_exchange_free(me, xc, ctrl);
   ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2 * G, 0xAAAAu, s_in, s_world, s_ll, ctrl);
@@ -1002,6 +1285,7 @@ struct GradSchedule {
   double eff;
   bool mixed;
   int nwide;
+  int left;  // balanced mixed schedule: states shared by all warps (H - nwarps * wt)
 };
 
 static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
@@ -1009,6 +1293,18 @@ static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
 // Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
 // CTA's warps with as few idle slots as possible.
 static GradSchedule plan_schedule(int D, int H) {
+  if (D >= 5 && g_fused_opt.mixed_warps != 16) {
+    // balanced schedule on 12 warps (3 per SM sub-partition, up to 168 registers): every warp owns 4 states, the
+    // H - 48 <= 2 states that remain are shared (each warp takes them on its own sample chunks).  More states per
+    // warp = more independent FFMA chains in flight per warp and room in the register file to interleave them;
+    // equal state counts = no warp waits for a wider one at the tile ring.
+    const int nw = 12, q = H / nw, r = H % nw;
+    if (q == 4 && r <= 2) {
+      GradSchedule m{};
+      m.wt = q; m.nwarps = nw; m.nchr = nw; m.nsub = 1; m.rounds = 1; m.eff = 1.0; m.mixed = true; m.nwide = 0; m.left = r;
+      return m;
+    }
+  }
   if (D >= 4) {
     // mixed schedule: 16 warps (4 per SM sub-partition, 128 registers), H = q*16 + r -> r warps own q+1 states.
     // Needs q >= 2 (fewer states per warp would re-read the staged samples too often for the shared-memory bandwidth).
@@ -1165,27 +1461,30 @@ static int pick_grid(int64_t N, int per_sm, int min_samples_per_cta) {
 // samples that decide the grid: the largest shard, so that every rank launches the same number of CTAs
 static int64_t grid_samples(const EvalArgs& a, int64_t n_max) { return n_max > a.N ? n_max : a.N; }
 
-template <int D, int WT, bool MIXED>
+template <int D, int WT, int MW, int LEFT>
 static int launch_grad_emu(const EvalArgs& a0, const EvalArgs& a1, int nblk, int nthreads, size_t smem, cudaStream_t stream) {
-  constexpr int MAXT = MIXED ? 512 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
-  auto kernel = eval_grad_emu_kernel<D, WT, MAXT, MIXED>;
+  constexpr bool MIXED = MW > 0;
+  constexpr int MAXT = MIXED ? MW * 32 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
+  auto kernel = eval_grad_emu_kernel<D, WT, MAXT, MIXED, LEFT>;
   if (resident_ctas(kernel, nthreads, smem) < 1) { set_error("emulated eval_gradient: kernel does not fit on an SM"); return -4; }
   return fused_launch(kernel, 2 * nblk, nthreads, smem, stream, "eval_grad_emu_kernel", true, a0, a1, nblk);
 }
 
-template <int D, int WT, bool MIXED = false>
+template <int D, int WT, int MW = 0, int LEFT = 0>
 static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, int64_t n_max, cudaStream_t stream) {
-  constexpr int MAXT = MIXED ? 512 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
-  auto kernel = eval_grad_kernel<D, WT, MAXT, MIXED>;
+  constexpr bool MIXED = MW > 0;
+  constexpr int MAXT = MIXED ? MW * 32 : (D <= 3 ? 20 : (D == 4 ? 16 : 17)) * 32;
+  auto kernel = eval_grad_kernel<D, WT, MAXT, MIXED, LEFT>;
   const int nthreads = s.nwarps * 32;
   const bool roll = a.d.kind == KLERG_DYN_ROLL;
-  // tile: up to 2048 samples, but no more than one CTA's slice at full grid
+  // tile: one 64-sample chunk per warp (every warp converts one chunk of each tile and evaluates the shared states
+  // on it), fewer for slices shorter than that
   int64_t per = (a.N + sm_count() - 1) / sm_count();
-  int ts = 2048;
-  while (ts > 64 && ts / 2 >= per) ts /= 2;
+  int ts = 64 * s.nwarps;
+  while (ts > 64 && ts - 64 >= per) ts -= 64;
   a.ts = ts;
   a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds; a.nwide = s.nwide;
-  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, s.nwarps, MIXED ? WT + 1 : WT);
+  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, s.nwarps, ((MIXED && LEFT == 0) ? WT + 1 : WT) + LEFT, 2 * MAXT);
   if (sp.total > 220 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
   const int per_sm = resident_ctas(kernel, nthreads, sp.total);
   if (per_sm < 1) { set_error("eval_gradient: kernel does not fit on an SM (threads=%d smem=%zu)", nthreads, sp.total); return -4; }
@@ -1195,7 +1494,7 @@ static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, int64_t n_max, cud
     if (a.peers.world != 2 || r < 0 || r > 1) { set_error("emulation records world-2 launches only"); return -1; }
     g_emu.args[r] = a;
     g_emu.have[r] = 1;
-    g_emu.launch = launch_grad_emu<D, WT, MIXED>;
+    g_emu.launch = launch_grad_emu<D, WT, MW, LEFT>;
     g_emu.nblk = nblk; g_emu.nthreads = nthreads; g_emu.smem = sp.total;
     return 0;
   }
@@ -1207,10 +1506,13 @@ int launch_grad_d(EvalArgs& a, int64_t n_max, cudaStream_t stream) {
   const GradSchedule s = plan_schedule(D, a.H);
   if constexpr (D >= 4) {
     if (s.mixed) {
-      if (s.wt == 2) return launch_grad_wt<D, 2, true>(a, s, n_max, stream);
-      if (s.wt == 3) return launch_grad_wt<D, 3, true>(a, s, n_max, stream);
+      if constexpr (D >= 5) {
+        if (s.nwarps == 12 && s.wt == 4) return launch_grad_wt<D, 4, 12, 2>(a, s, n_max, stream);
+      }
+      if (s.wt == 2) return launch_grad_wt<D, 2, 16>(a, s, n_max, stream);
+      if (s.wt == 3) return launch_grad_wt<D, 3, 16>(a, s, n_max, stream);
       if constexpr (D == 4) {
-        if (s.wt == 4) return launch_grad_wt<D, 4, true>(a, s, n_max, stream);
+        if (s.wt == 4) return launch_grad_wt<D, 4, 16>(a, s, n_max, stream);
       }
       set_error("eval_gradient: no mixed schedule for D=%d H=%d", D, a.H);
       return -2;

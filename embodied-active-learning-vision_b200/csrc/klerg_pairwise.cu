@@ -29,25 +29,29 @@ __global__ void pack_samples_kernel(KernelDev k, const float* __restrict__ sampl
 }
 
 // ---------------------------------------------------------------------------
-// forward: footprint (sum) / spread (max), packed f32x2 pair math (klerg_pair.cuh)
+// forward: footprint (sum) / spread (max) / both in one pass, packed f32x2 pair math (klerg_pair.cuh)
 // ---------------------------------------------------------------------------
 constexpr int FP_THREADS = 256;
 
-// state rows staged per pass: 32 KB (D <= 4) / 36 KB (D <= 6) of duplicated {x, x} rows
+// state rows staged per pass: 32 KB (D <= 4) / 36 KB (D <= 6): duplicated {x, x} rows of the difference form or,
+// in the same buffer, the {-2 xc, |xc|^2} rows of the expanded form
 template <int D>
 struct FootChunk {
   static constexpr int ROWS = Row2<D>::DP <= 4 ? 1024 : 768;
+  static_assert(sizeof(float) * RowX<D>::NF <= sizeof(u64) * Row2<D>::DP, "expanded rows must fit the staging buffer");
 };
 
 struct FootArgs {
   KernelDev k;
   const float* states;
   int64_t G, T, seg_stride;
+  int64_t T_sum;  // MODE 2: rows [0, T_sum) enter the sum, all T rows the maximum
   const float* packed;
   int64_t N, ld;
   const float* add_in;
   float* out;
   int64_t out_stride;
+  float* out_max;  // MODE 2: [G][out_stride] max_j psi
   double* totals;
   void* ws;
   int64_t ntiles;
@@ -66,36 +70,74 @@ __device__ __forceinline__ void load_sample_pairs(const float* __restrict__ p, i
   }
 }
 
+// MODE 0: sum (traj_footprint_vec)  1: max (traj_spread_vec)  2: sum over the first T_sum rows and max over all
+// rows in ONE pass over the squared distances (the history footprint q_base and the spread of get_target_dist
+// visit the same memory-buffer rows: klerg.py:470-475 and :496).
+//
+// Every staged chunk of rows is evaluated in the expanded form around its middle row (klerg_pair.cuh: D + 2
+// lane-ops per pair instead of 2D + 1); a chunk whose rows lie further than X_FORM_MAX_R2 from that row (in
+// kernel widths) is evaluated in the exact difference form instead.
 template <int D, int MODE, int P>
 __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a) {
   constexpr int DP = Row2<D>::DP;
+  constexpr int NF = RowX<D>::NF;
   constexpr int SPT = 2 * P;
   constexpr int TILE = FP_THREADS * SPT;
   constexpr int CHUNK = FootChunk<D>::ROWS;
   __shared__ __align__(16) u64 sh[CHUNK * DP];
+  float* shx = reinterpret_cast<float*>(sh);
   const int tid = threadIdx.x;
-  const int nchunk = (int)((a.T + CHUNK - 1) / CHUNK);
+  // chunk schedule: rows [0, T_sum) first, then [T_sum, T) (MODE 2; otherwise T_sum = T)
+  const int64_t Tsum = MODE == 2 ? a.T_sum : a.T;
+  const int nch1 = (int)((Tsum + CHUNK - 1) / CHUNK);
+  const int nchunk = nch1 + (int)((a.T - Tsum + CHUNK - 1) / CHUNK);
 
   for (int64_t g = blockIdx.y; g < a.G; g += gridDim.y) {
     const float* st = a.states + g * a.seg_stride;
     double tsum = 0.0, tmax = -INFINITY;
+    float ctr[D];  // centre of the staged chunk (scaled coordinates), same in every thread
 
-    auto stage = [&](int c) {
-      const int64_t j0 = (int64_t)c * CHUNK;
-      const int rows = (int)min((int64_t)CHUNK, a.T - j0);
+    // stage chunk c; returns true if it was staged in the expanded form
+    auto stage = [&](int c, int& rows) -> bool {
+      const int64_t j0 = c < nch1 ? (int64_t)c * CHUNK : Tsum + (int64_t)(c - nch1) * CHUNK;
+      const int64_t jend = c < nch1 ? Tsum : a.T;
+      rows = (int)min((int64_t)CHUNK, jend - j0);
+      const int64_t jm = j0 + rows / 2;
+#pragma unroll
+      for (int d = 0; d < D; ++d) ctr[d] = st[jm * a.k.S + a.k.explr[d]] * a.k.a[d];
+      bool big = false;
+      for (int j = tid; j < rows; j += FP_THREADS) {
+        float r[NF];
+        float x2n = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float xc = st[(j0 + j) * a.k.S + a.k.explr[d]] * a.k.a[d] - ctr[d];
+          r[d] = -2.f * xc;
+          x2n = fmaf(xc, xc, x2n);
+        }
+        r[D] = x2n;
+#pragma unroll
+        for (int d = D + 1; d < NF; ++d) r[d] = 0.f;
+        big |= !(x2n <= a.k.x_r2);
+        float4* dst = reinterpret_cast<float4*>(shx + (size_t)j * NF);
+#pragma unroll
+        for (int h = 0; h < NF / 4; ++h) dst[h] = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+      }
+      if (!__syncthreads_or(big)) return true;
       for (int e = tid; e < rows * DP; e += FP_THREADS) {
         const int j = e / DP, d = e - j * DP;
         const float v = (d < D) ? st[(j0 + j) * a.k.S + a.k.explr[d]] * a.k.a[d] : 0.f;
         sh[e] = pack2(v, v);
       }
-      return rows;
+      __syncthreads();
+      return false;
     };
 
     int rows_single = 0;
+    bool x_single = false;
     if (nchunk == 1) {
       __syncthreads();
-      rows_single = stage(0);
-      __syncthreads();
+      x_single = stage(0, rows_single);
     }
 
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -128,13 +170,36 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
       for (int q = 0; q < P; ++q) total[q] = pack2(0.f, 0.f);
       for (int c = 0; c < nchunk; ++c) {
         int rows = rows_single;
+        bool xform = x_single;
         if (nchunk > 1) {
           __syncthreads();
-          rows = stage(c);
-          __syncthreads();
+          xform = stage(c, rows);
         }
-        pair_forward<D, P, MODE>(sh, rows, s2, acc, emin);
-        if (MODE == 0 && nchunk > 1) {
+        const bool summed = MODE != 2 || c < nch1;  // MODE 2: the rows behind T_sum only enter the maximum
+        if (xform) {
+          u64 sc[D][P], s2n[P];
+#pragma unroll
+          for (int q = 0; q < P; ++q) {
+            const u64 c0 = pack2(ctr[0], ctr[0]);
+            sc[0][q] = sub2(s2[0][q], c0);
+            s2n[q] = mul2(sc[0][q], sc[0][q]);
+#pragma unroll
+            for (int d = 1; d < D; ++d) {
+              sc[d][q] = sub2(s2[d][q], pack2(ctr[d], ctr[d]));
+              s2n[q] = fma2(sc[d][q], sc[d][q], s2n[q]);
+            }
+          }
+          if (summed)
+            pair_forward_x<D, P, MODE>(shx, 0, rows, sc, s2n, acc, emin);
+          else
+            pair_forward_x<D, P, 1>(shx, 0, rows, sc, s2n, acc, emin);
+        } else {
+          if (summed)
+            pair_forward<D, P, MODE>(sh, 0, rows, s2, acc, emin);
+          else
+            pair_forward<D, P, 1>(sh, 0, rows, s2, acc, emin);
+        }
+        if (MODE != 1 && nchunk > 1) {
 #pragma unroll
           for (int q = 0; q < P; ++q) {
             total[q] = add2(total[q], acc[q]);
@@ -142,19 +207,19 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
           }
         }
       }
-      if (MODE == 0 && nchunk > 1) {
+      if (MODE != 1 && nchunk > 1) {
 #pragma unroll
         for (int q = 0; q < P; ++q) acc[q] = total[q];
       }
 
       // epilogue: scale, add base, store, local totals
-      float o[SPT];
+      float o[SPT], om[SPT];
 #pragma unroll
       for (int q = 0; q < P; ++q) unpack2(acc[q], o[2 * q], o[2 * q + 1]);
 #pragma unroll
       for (int q = 0; q < SPT; ++q) {
-        float v = (MODE == 0) ? o[q] : ex2_neg(emin[q]);  // T = 0: 2^-inf = 0
-        v *= a.k.inv_nu;
+        om[q] = ex2_neg(emin[q]) * a.k.inv_nu;  // T = 0: 2^-inf = 0
+        float v = (MODE == 1) ? om[q] : o[q] * a.k.inv_nu;
         const int64_t i = i0 + q;
         if (a.add_in != nullptr && i < a.N) v += a.add_in[i];
         o[q] = v;
@@ -164,12 +229,23 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
         }
       }
       float* op = a.out + g * a.out_stride + i0;
-      if (SPT == 4 && i0 + 3 < a.N && ((a.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0)) {
+      const bool vec = SPT == 4 && i0 + 3 < a.N && ((a.out_stride & 3) == 0);
+      if (vec && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0)) {
         *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
 #pragma unroll
         for (int q = 0; q < SPT; ++q)
           if (i0 + q < a.N) op[q] = o[q];
+      }
+      if (MODE == 2) {
+        float* mp = a.out_max + g * a.out_stride + i0;
+        if (vec && ((reinterpret_cast<uintptr_t>(a.out_max) & 15) == 0)) {
+          *reinterpret_cast<float4*>(mp) = make_float4(om[0], om[1], om[2], om[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < SPT; ++q)
+            if (i0 + q < a.N) mp[q] = om[q];
+        }
       }
     }
 
@@ -478,11 +554,22 @@ extern "C" int klerg_footprint(const klerg_kernel_spec* k, int mode, const float
   if (!make_kernel_dev(k, kd)) return -1;
   if (G < 1 || N < 0 || T < 0 || ld < N || (ld & 3)) { set_error("footprint: bad sizes"); return -1; }
   if (!workspace || !totals || !out) { set_error("footprint: null output/workspace"); return -1; }
-  FootArgs a{kd, states, G, T, seg_stride, packed, N, ld, add_in, out, out_stride, totals, workspace, 0};
+  FootArgs a{kd, states, G, T, seg_stride, T, packed, N, ld, add_in, out, out_stride, nullptr, totals, workspace, 0};
   if (mode == 0) return launch_footprint_d<0>(a, (cudaStream_t)stream);
   if (mode == 1) return launch_footprint_d<1>(a, (cudaStream_t)stream);
   set_error("footprint: mode must be 0 (sum) or 1 (max)");
   return -1;
+}
+
+extern "C" int klerg_footprint_sum_max(const klerg_kernel_spec* k, const float* states, int64_t T, int64_t T_sum,
+                                       const float* packed, int64_t N, int64_t ld, float* out_sum, float* out_max,
+                                       double* totals, void* workspace, void* stream) {
+  KernelDev kd;
+  if (!make_kernel_dev(k, kd)) return -1;
+  if (N < 0 || T < 0 || T_sum < 0 || T_sum > T || ld < N || (ld & 3)) { set_error("footprint_sum_max: bad sizes"); return -1; }
+  if (!workspace || !totals || !out_sum || !out_max) { set_error("footprint_sum_max: null output/workspace"); return -1; }
+  FootArgs a{kd, states, 1, T, T * kd.S, T_sum, packed, N, ld, nullptr, out_sum, ld, out_max, totals, workspace, 0};
+  return launch_footprint_d<2>(a, (cudaStream_t)stream);
 }
 
 extern "C" int klerg_kl_gradient(const klerg_kernel_spec* k, const float* states, int64_t H, const float* packed,

@@ -47,6 +47,8 @@ int sm_count() {
   return cached;
 }
 
+int g_exact_pairs = 0;
+
 bool make_kernel_dev(const klerg_kernel_spec* k, KernelDev& out) {
   if (!k) { set_error("kernel spec is null"); return false; }
   if (k->D < 1 || k->D > KLERG_MAX_D || k->S < 1) { set_error("kernel spec: D=%d S=%d out of range", k->D, k->S); return false; }
@@ -54,6 +56,7 @@ bool make_kernel_dev(const klerg_kernel_spec* k, KernelDev& out) {
   out.S = k->S;
   const double nu = (double)k->nu;
   out.inv_nu = (float)(1.0 / nu);
+  out.x_r2 = g_exact_pairs ? -1.f : 100.f;  // radius^2 of the expanded pair form (X_FORM_MAX_R2, klerg_pair.cuh)
   for (int d = 0; d < KLERG_MAX_D; ++d) {
     out.explr[d] = 0;
     out.a[d] = 0.f;

@@ -104,6 +104,15 @@ int klerg_footprint(const klerg_kernel_spec* k, int mode, const float* states, i
                     int64_t seg_stride, const float* packed, int64_t N, int64_t ld, const float* add_in,
                     float* out, int64_t out_stride, double* totals, void* workspace, void* stream);
 
+/* Both reductions in ONE pass over the squared distances, for the two memory-buffer passes of a planner step that
+ * visit the same rows (klerg.py:470-475 spread of get_target_dist over ALL buffer rows; klerg.py:496 footprint of
+ * the drawn rows): states[T][S] hold the drawn rows FIRST (T_sum of them, any order) and the remaining buffer rows
+ * behind them;  out_sum[i] = sum_{j < T_sum} psi(states[j], s_i),  out_max[i] = max_{j < T} psi(states[j], s_i)
+ * (both [ld]); totals[0..1] = {sum_i, max_i} of out_sum over this rank's samples. */
+int klerg_footprint_sum_max(const klerg_kernel_spec* k, const float* states, int64_t T, int64_t T_sum,
+                            const float* packed, int64_t N, int64_t ld, float* out_sum, float* out_max,
+                            double* totals, void* workspace, void* stream);
+
 /* a1: psi_fn / dpsi_dx_fn (klerg_utils.py:7-15) materialised: psi[N][T] = psi(states_j[explr], samples_i)
  * and / or dpsi[N][T][D] = -(x_j - s_i)/|scale| * psi * nu (dpsi_dx_fn divides by nu once, through psi).
  * `samples` are the raw AoS samples [N][D].  Either output may be NULL. */
@@ -220,8 +229,15 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
  *                           CTA (gather + adjoint) to finish.  Default 0: stream order as usual.
  *   KLERG_OPT_GRID_LIMIT    > 0: at most this many CTAs per fused launch (tests).
  *   KLERG_OPT_PDL           0 = plain cooperative launches without programmatic dependent launch.
- *   KLERG_OPT_COOP_WITH_PDL (read-only) 1 / 0 / -1: the driver accepts both attributes / not / not probed yet. */
-enum { KLERG_OPT_EVAL_OVERLAP = 1, KLERG_OPT_GRID_LIMIT = 2, KLERG_OPT_PDL = 3, KLERG_OPT_COOP_WITH_PDL = 4 };
+ *   KLERG_OPT_COOP_WITH_PDL (read-only) 1 / 0 / -1: the driver accepts both attributes / not / not probed yet.
+ *   KLERG_OPT_EXACT_PAIRS   1 = every pair pass (footprint, fused evals) evaluates |x - s|^2 from the coordinate
+ *                           differences; default 0: the cheaper expanded form |sc|^2 + |xc|^2 - 2 xc.sc around a centre
+ *                           of the state set wherever the set is narrow enough for it (relative error of psi < 3e-5),
+ *                           the difference form elsewhere.
+ *   KLERG_OPT_MIXED_WARPS   16 = the gradient pass of D >= 5 always runs its 16-warp schedule (A/B switch; default 0:
+ *                           12 warps with 4-5 states each where the horizon allows). */
+enum { KLERG_OPT_EVAL_OVERLAP = 1, KLERG_OPT_GRID_LIMIT = 2, KLERG_OPT_PDL = 3, KLERG_OPT_COOP_WITH_PDL = 4,
+       KLERG_OPT_EXACT_PAIRS = 5, KLERG_OPT_MIXED_WARPS = 6 };
 int klerg_set_option(int key, int value);
 int klerg_get_option(int key);
 /* Two ranks on ONE GPU (tests of the exchange protocol on a single-GPU box): after klerg_emu_begin() the next

@@ -63,7 +63,9 @@ def test_config4_full_history_and_spread_split_properties():
     mw, _ = e.footprint(spec, 1, s["hist"], ctx.packed, n)
     ma, _ = e.footprint(spec, 1, s["hist"][:37_003], ctx.packed, n)
     mb, _ = e.footprint(spec, 1, s["hist"][37_003:], ctx.packed, n)
-    assert torch.equal(torch.maximum(ma[0, :n], mb[0, :n]), mw[0, :n])  # a maximum does not round
+    # a maximum does not round, but every staged chunk of rows is evaluated around its own centre and the chunk
+    # boundaries of the split lists differ from the whole list's
+    assert rel(torch.maximum(ma[0, :n], mb[0, :n]), mw[0, :n]) < 5e-5
     assert float(mw[0, :n].max()) <= 1.0 and float(mw[0, :n].min()) >= 0.0
 
 
