@@ -140,7 +140,7 @@ struct FusedOptions {
   int grid_limit;   // > 0: at most this many CTAs per launch (tests: two emulated ranks share one GPU)
   int pdl;          // launch with the programmatic-stream-serialization attribute
   int coop_probe;   // -1 unknown, 0 / 1: the cooperative attribute may be combined with it
-  int mixed_warps;  // 0 = automatic, 16 = never the 12-warp mixed schedule (A/B)
+  int mixed_warps;  // 12 = balanced 12-warp schedule for D >= 5 where the horizon allows (A/B; measured slower than the default)
 };
 extern FusedOptions g_fused_opt;
 
@@ -474,10 +474,11 @@ __device__ __forceinline__ void forward_candidates(const EvalArgs& a, const Stat
 // Row stride (floats) of the staged sample tiles: a compile-time constant so that the D+2 row addresses of a
 // tile are immediates off one base register (no address chain, fewer live registers in the pair loop).
 #define TILE_ROWS(D) ((D) + 3)
-// Sample tiles of the gradient pass live in a ring of NB buffers: TMA fills a buffer, the warps turn it into pair
-// operands (importance ratio, centred coordinates) one tile ahead of the pair math, and the warp that is last to
-// finish a buffer issues the TMA of the tile NB places further on - no CTA-wide barrier inside the pass.
-constexpr int TILE_NB = 4;
+// Sample tiles of the gradient pass: two buffers of TS_ROW samples; TMA fills one while the warps work on the other.
+// (A deeper ring of smaller tiles without the per-tile CTA barrier was measured and is slower: the per-tile
+// bookkeeping of every warp outweighs the barrier it removes.)
+constexpr int TILE_NB = 2;
+constexpr int TS_ROW = 2048;
 
 struct SmemPlan {
   size_t u, traj, dbarr, P, rot, x2, rx, xs, tile, adj, part, red, misc, ll, total;
@@ -485,7 +486,7 @@ struct SmemPlan {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 constexpr size_t LL_SCRATCH_BYTES = sizeof(double) * (LL_BUF_VALS + 32);
-constexpr size_t MISC_BYTES = 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 8 + 16 * TILE_NB + 4 * TILE_NB + 8;
+constexpr size_t MISC_BYTES = 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 8 + 8 * 4 + 8;
 
 template <int D>
 __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, int nwarps, int WT, int tsr) {
@@ -511,7 +512,7 @@ __host__ __device__ inline SmemPlan plan_grad(int H, int S, int A, bool roll, in
   p.total = o;
   return p;
 }
-static_assert(sizeof(float) * 2 * TILE_ROWS(1) * 768 >= LL_SCRATCH_BYTES, "meeting staging must fit two tile buffers (D = 1, 12 warps)");
+static_assert(sizeof(float) * TILE_ROWS(1) * TS_ROW >= LL_SCRATCH_BYTES, "meeting staging must fit one tile buffer (D = 1)");
 
 // ---------------------------------------------------------------------------
 // gradient eval
@@ -557,17 +558,11 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   KLERG_CTA_STAMP(me, vblk, 0);
   // ---- phase 0: rollout, states only (every CTA) ----------------------------------------------------
   float* s_x0 = (float*)(smem + sp.misc) + 4;  // [S] (+ [9] R0)
-  // tile ring bookkeeping: full[b] (TMA landed), conv[b] (all warps converted their share), done[b] (warps finished)
+  // full[b]: the TMA copies of the tile in buffer b have landed
   unsigned long long* s_full = (unsigned long long*)(smem + ((sp.misc + 16 + sizeof(float) * (KLERG_MAX_S + 9) + 16 + 7) & ~(size_t)7));
-  unsigned long long* s_conv = s_full + TILE_NB;
-  int* s_done = (int*)(s_conv + TILE_NB);
   if (tid == 0) {
 #pragma unroll
-    for (int b = 0; b < TILE_NB; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&s_conv[b], (unsigned)nwarps);
-      s_done[b] = 0;
-    }
+    for (int b = 0; b < TILE_NB; ++b) mbar_init(&s_full[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (!a.independent) pdl_wait_prior_grids();  // the previous launch may have produced this one's inputs
@@ -635,15 +630,12 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   };
   fence_proxy_async();  // v was written with ordinary stores and is read back by TMA
   __syncthreads();
-  if (tid == 0)
-    for (int g = 0; g < 2 && g < g_total; ++g) issue_tile(g);
+  if (tid == 0 && g_total > 0) issue_tile(0);
   // ---- meeting (1): {sum, max} over every CTA of every rank ----------------------------------------
   // Slots of this launch's first gather exchange (number xc) are about to be reused from exchange xc - 2: wait until
   // that one has been consumed (always true in practice; makes the slot reuse safe by construction).
   if (tid == 0) ll_wait_exchange_free(me, xc, ctrl);
-  ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2, 0x2u, s_in, s_world, (double*)(s_tile + (size_t)2 * TR * TSR), ctrl);
-  if (tid == 0)  // the staging area is free again: request the tiles that live there
-    for (int g = 2; g < TILE_NB && g < g_total; ++g) issue_tile(g);
+  ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2, 0x2u, s_in, s_world, (double*)(s_tile + (size_t)TR * TSR), ctrl);
   if (vblk == 0 && tid == 0) {
     // every CTA holds epoch / xc in registers by now: bump the counters for the next launch, which may start
     // as soon as all CTAs have passed this point
@@ -676,13 +668,12 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   const int pb_step = ((volatile int*)s_flag)[4 + KLERG_MAX_S + 9];
   const int HD = H * D, NE = HD + H;  // gather entries: A[t][d] = sum w psi sc_d, then W[t] = sum w psi
   const bool want_kl = a.kl_out != nullptr || a.cost != nullptr;
-  double kl_a[2] = {0.0, 0.0}, kl_c[2] = {0.0, 0.0};  // by target parity (tiles are converted one tile ahead)
+  double kl_a = 0.0, kl_c = 0.0;
 
-  // Turn this warp's share of tile g = (target kt_g, round r_g, tile t) into pair operands, in place: v -> importance
-  // ratio w = p/q (klerg.py:436); expanded form: samples centred and |sc|^2; rows beyond the slice zeroed.
-  // 64-sample chunks, chunk c by warp c % nwarps, two samples per lane as one packed pair.  Ends with the warp's
-  // arrival on conv[b].
-  auto convert_tile = [&](int g, int kt_g, int r_g, int t) {
+  // Turn tile g (in buffer g & 1) into pair operands, in place, by the whole CTA: v -> importance ratio w = p/q
+  // (klerg.py:436); expanded form: samples centred and |sc|^2; rows beyond the slice zeroed.  Two samples per thread
+  // and step, as one packed pair.
+  auto convert_tile = [&](int g, bool with_kl, int t) {
     const int b = g & (TILE_NB - 1);
     float* buf = s_tile + (size_t)b * TR * TSR;
     const int64_t base = lo + (int64_t)t * ts;
@@ -692,16 +683,15 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     const float* prow = buf + (size_t)(D + 1) * TSR;
     float* nrow = buf + (size_t)(D + 2) * TSR;
     KLERG_SPIN_UNTIL(mbar_try_wait(&s_full[b], (unsigned)(g / TILE_NB) & 1u), ctrl)
-    for (int c = warp; c < (cnt64 >> 6); c += nwarps) {
-      const int e = (c << 6) + 2 * lane;
+    for (int e = 2 * tid; e < cnt64; e += 2 * (int)blockDim.x) {
       const float2 vv = *reinterpret_cast<const float2*>(&wrow[e]);
       const float2 pp = *reinterpret_cast<const float2*>(&prow[e]);
       const bool in0 = e < cnt && base + e < a.N, in1 = e + 1 < cnt && base + e + 1 < a.N;
       const float c0 = fmaxf(__fdividef(vv.x, vsum_f), a.floor), c1 = fmaxf(__fdividef(vv.y, vsum_f), a.floor);
       const float w0 = in0 ? __fdividef(pp.x * maxc_f, c0) : 0.f, w1 = in1 ? __fdividef(pp.y * maxc_f, c1) : 0.f;
-      if (want_kl && r_g == 0) {
-        if (in0) { kl_a[kt_g & 1] += (double)(pp.x * (logf(pp.x) - logf(c0))); kl_c[kt_g & 1] += (double)c0; }
-        if (in1) { kl_a[kt_g & 1] += (double)(pp.y * (logf(pp.y) - logf(c1))); kl_c[kt_g & 1] += (double)c1; }
+      if (with_kl) {
+        if (in0) { kl_a += (double)(pp.x * (logf(pp.x) - logf(c0))); kl_c += (double)c0; }
+        if (in1) { kl_a += (double)(pp.y * (logf(pp.y) - logf(c1))); kl_c += (double)c1; }
       }
       u64 n2 = pack2(0.f, 0.f);
       if (e >= cnt) {  // cnt is even: the pair lies beyond the slice as a whole
@@ -719,11 +709,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       *reinterpret_cast<float2*>(&wrow[e]) = make_float2(w0, w1);
       *reinterpret_cast<u64*>(&nrow[e]) = n2;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_conv[b]);
   };
-  static_assert((TILE_NB & (TILE_NB - 1)) == 0, "ring size must be a power of two");
-  if (g_total > 0) convert_tile(0, 0, 0, 0);
 
   for (int kt = 0; kt < a.K; ++kt) {  // belief targets: the forward pass above is shared, p_k differs
   if (kt > 0 && tid == 0) ll_wait_exchange_free(me, xc + (unsigned)kt, ctrl);  // ordered before the slot stores by the barriers below
@@ -793,17 +779,15 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       }
       for (int t = 0; t < nt; ++t) {
         const int g = g_base + t, b = g & (TILE_NB - 1);
-        if (g + 1 < g_total) {  // one tile ahead (possibly the next round's / target's first)
-          const bool wrap_t = t + 1 == nt, wrap_r = wrap_t && r + 1 == a.rounds;
-          convert_tile(g + 1, kt + (wrap_r ? 1 : 0), wrap_r ? 0 : r + (wrap_t ? 1 : 0), wrap_t ? 0 : t + 1);
-        }
+        convert_tile(g, want_kl && r == 0, t);
+        __syncthreads();  // tile g is ready for everyone; everyone is done with tile g - 1
+        if (tid == 0 && g + 1 < g_total) issue_tile(g + 1);  // the other buffer: the next tile (or the next sweep's first)
         float* buf = s_tile + (size_t)b * TR * TSR;
         const int64_t base = lo + (int64_t)t * ts;
         const int cnt = (int)min((int64_t)ts, hi - base);
         const int cnt64 = (cnt + 63) & ~63;
         const float* wrow = buf + (size_t)D * TSR;
         const float* nrow = buf + (size_t)(D + 2) * TSR;
-        KLERG_SPIN_UNTIL(mbar_try_wait(&s_conv[b], (unsigned)(g / TILE_NB) & 1u), ctrl)
         if (active) {
           if constexpr (XF) {
             // warp-uniform: this warp owns WTA or WTA - 1 states
@@ -850,15 +834,6 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
                 pair_gradient<D, LA>(lxs2, s2, w2, lacc, true);
               }
             }
-          }
-        }
-        // this warp is done with buffer b; the last warp to say so requests the tile NB places further on
-        __syncwarp();
-        if (lane == 0) {
-          const int old = atomicAdd(&s_done[b], 1);
-          if (old == nwarps - 1) {
-            s_done[b] = 0;
-            if (g + TILE_NB < g_total) issue_tile(g + TILE_NB);
           }
         }
       }
@@ -953,8 +928,8 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   const unsigned xtag = ll_tag(xnum, 0x80u);
   if (want_kl) {
     const int kinds[2] = {RED_SUM, RED_SUM};
-    double vals[2] = {kl_a[kt & 1], kl_c[kt & 1]};
-    kl_a[kt & 1] = kl_c[kt & 1] = 0.0;
+    double vals[2] = {kl_a, kl_c};
+    kl_a = kl_c = 0.0;
     block_reduce<2>(kinds, vals, s_red);
     if (tid == 0) {
       ll_store(mb_kl(me, xpar, vblk_), vals[0], xtag);
@@ -1069,7 +1044,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
 template <int D, int WT, int MAXT, bool MIXED, int LEFT>
 __global__ void __launch_bounds__(MAXT) eval_grad_kernel(const __grid_constant__ EvalArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  eval_grad_body<D, WT, MIXED, LEFT, 2 * MAXT>(a, (int)blockIdx.x, (int)gridDim.x, smem);
+  eval_grad_body<D, WT, MIXED, LEFT, TS_ROW>(a, (int)blockIdx.x, (int)gridDim.x, smem);
 }
 // two ranks on one GPU (tests): CTAs [0, nb) act as rank 0 with a0, CTAs [nb, 2 nb) as rank 1 with a1
 template <int D, int WT, int MAXT, bool MIXED, int LEFT>
@@ -1077,9 +1052,9 @@ __global__ void __launch_bounds__(MAXT) eval_grad_emu_kernel(const __grid_consta
                                                              const __grid_constant__ EvalArgs a1, const int nb) {
   extern __shared__ __align__(16) unsigned char smem[];
   if ((int)blockIdx.x < nb)
-    eval_grad_body<D, WT, MIXED, LEFT, 2 * MAXT>(a0, (int)blockIdx.x, nb, smem);
+    eval_grad_body<D, WT, MIXED, LEFT, TS_ROW>(a0, (int)blockIdx.x, nb, smem);
   else
-    eval_grad_body<D, WT, MIXED, LEFT, 2 * MAXT>(a1, (int)blockIdx.x - nb, nb, smem);
+    eval_grad_body<D, WT, MIXED, LEFT, TS_ROW>(a1, (int)blockIdx.x - nb, nb, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -1293,7 +1268,7 @@ static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
 // Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
 // CTA's warps with as few idle slots as possible.
 static GradSchedule plan_schedule(int D, int H) {
-  if (D >= 5 && g_fused_opt.mixed_warps != 16) {
+  if (D >= 5 && g_fused_opt.mixed_warps == 12) {
     // balanced schedule on 12 warps (3 per SM sub-partition, up to 168 registers): every warp owns 4 states, the
     // H - 48 <= 2 states that remain are shared (each warp takes them on its own sample chunks).  More states per
     // warp = more independent FFMA chains in flight per warp and room in the register file to interleave them;
@@ -1477,14 +1452,13 @@ static int launch_grad_wt(EvalArgs& a, const GradSchedule& s, int64_t n_max, cud
   auto kernel = eval_grad_kernel<D, WT, MAXT, MIXED, LEFT>;
   const int nthreads = s.nwarps * 32;
   const bool roll = a.d.kind == KLERG_DYN_ROLL;
-  // tile: one 64-sample chunk per warp (every warp converts one chunk of each tile and evaluates the shared states
-  // on it), fewer for slices shorter than that
+  // tile: up to TS_ROW samples, but no more than one CTA's slice at full grid
   int64_t per = (a.N + sm_count() - 1) / sm_count();
-  int ts = 64 * s.nwarps;
-  while (ts > 64 && ts - 64 >= per) ts -= 64;
+  int ts = TS_ROW;
+  while (ts > 64 && ts / 2 >= per) ts /= 2;
   a.ts = ts;
   a.nchr = s.nchr; a.nsub = s.nsub; a.rounds = s.rounds; a.nwide = s.nwide;
-  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, s.nwarps, ((MIXED && LEFT == 0) ? WT + 1 : WT) + LEFT, 2 * MAXT);
+  const SmemPlan sp = plan_grad<D>(a.H, a.d.S, a.d.A, roll, s.nwarps, ((MIXED && LEFT == 0) ? WT + 1 : WT) + LEFT, TS_ROW);
   if (sp.total > 220 * 1024) { set_error("eval_gradient: horizon too long for shared-memory staging"); return -1; }
   const int per_sm = resident_ctas(kernel, nthreads, sp.total);
   if (per_sm < 1) { set_error("eval_gradient: kernel does not fit on an SM (threads=%d smem=%zu)", nthreads, sp.total); return -4; }

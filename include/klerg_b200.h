@@ -234,8 +234,8 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
  *                           differences; default 0: the cheaper expanded form |sc|^2 + |xc|^2 - 2 xc.sc around a centre
  *                           of the state set wherever the set is narrow enough for it (relative error of psi < 3e-5),
  *                           the difference form elsewhere.
- *   KLERG_OPT_MIXED_WARPS   16 = the gradient pass of D >= 5 always runs its 16-warp schedule (A/B switch; default 0:
- *                           12 warps with 4-5 states each where the horizon allows). */
+ *   KLERG_OPT_MIXED_WARPS   12 = the gradient pass of D >= 5 runs a balanced 12-warp schedule (4 states per warp, the
+ *                           rest shared) where the horizon allows (A/B switch; default 0: 16 warps with 3-4 states). */
 enum { KLERG_OPT_EVAL_OVERLAP = 1, KLERG_OPT_GRID_LIMIT = 2, KLERG_OPT_PDL = 3, KLERG_OPT_COOP_WITH_PDL = 4,
        KLERG_OPT_EXACT_PAIRS = 5, KLERG_OPT_MIXED_WARPS = 6 };
 int klerg_set_option(int key, int value);

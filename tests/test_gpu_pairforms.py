@@ -63,11 +63,12 @@ def test_sum_max_pass(D, n, T, t_sum, std, exact_switch):
     close(q[:n], want_q, atol_frac=frac, what="sum over the drawn rows")
     close(m[:n], want_m, atol_frac=frac, what="max over all rows")
     close(tot[0], want_q.double().sum(), rtol=1e-5, what="total")
-    # the separate passes give the same numbers (same arithmetic per chunk)
+    # the separate passes give the same numbers up to the rounding of the expanded form (the chunks of staged rows,
+    # hence their centres, differ where t_sum is not a multiple of the chunk size)
     q2, _ = engine.footprint(spec, 0, st_dev[:t_sum], packed, n)
     m2, _ = engine.footprint(spec, 1, st_dev, packed, n)
-    close(q[:n], q2[0, :n], rtol=2e-6, atol_frac=1e-7, what="one pass vs separate sum pass")
-    close(m[:n], m2[0, :n], rtol=2e-6, atol_frac=1e-7, what="one pass vs separate max pass")
+    close(q[:n], q2[0, :n], rtol=5e-5, atol_frac=1e-7, what="one pass vs separate sum pass")
+    close(m[:n], m2[0, :n], rtol=5e-5, atol_frac=1e-7, what="one pass vs separate max pass")
     # forced exact form
     exact_switch(True)
     q3, m3, _ = engine.footprint_sum_max(spec, st_dev, t_sum, packed, n)
