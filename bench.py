@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--workload", default="c4", choices=list(wl.WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="override the workspace size (total samples)")
     ap.add_argument("--weak", action="store_true", help="--samples per GPU instead of sharding a fixed workspace")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary c2 measurement")
@@ -89,6 +89,7 @@ def run_oracle_steps(name, n, m, steps, warmup, seed=0):
     for row in wl.random_walk_history(name, m):
         r.memory_buffer.push(row)
     pairs = evals = 0
+    hist = spread = evp = 0
     t_total = 0.0
     for k in range(warmup + steps):
         r.n_cost_evals = r.n_grad_evals = 0
@@ -100,7 +101,20 @@ def run_oracle_steps(name, n, m, steps, warmup, seed=0):
             t_total += dt
             pairs += oracle_pairs(r, n, min(m, m_all), m_all)
             evals += r.n_cost_evals + r.n_grad_evals
-    return dict(pairs=pairs, evals=evals, seconds=t_total, cores=cores, steps=steps)
+            hist += min(m, m_all) * n
+            spread += m_all * n
+            evp += (r.n_cost_evals + 2 * r.n_grad_evals) * r.horizon * n
+    return dict(pairs=pairs, evals=evals, seconds=t_total, cores=cores, steps=steps, mix=pair_mix(hist, spread, evp))
+
+
+# bounded sample of every workload for the host CPU legs: the workload's own history size M (same pair mix as the GPU
+# arm's Robot.step()), the sample count reduced so that a Robot.step() of the oracle port takes seconds, not hours
+REF_SAMPLES = {"c1": 1_000, "c2": 20_000, "c3": 20_000, "c4": 4_000, "c5": 20_000}
+
+
+def pair_mix(hist_pairs, spread_pairs, eval_pairs):
+    tot = max(hist_pairs + spread_pairs + eval_pairs, 1)
+    return {"history": hist_pairs / tot, "spread": spread_pairs / tot, "evals": eval_pairs / tot}
 
 
 def reference_arm(args):
@@ -109,26 +123,22 @@ def reference_arm(args):
         return
     w = wl.WORKLOADS[args.workload]
     n_full = args.samples or w["N"]
-    m = min(w["M"], 1000)
-    # bounded sample: probe one step at reduced size, then pick N so that all steps fit ~120 s
-    probe_n = min(n_full, 4_000)
-    probe = run_oracle_steps(args.workload, probe_n, m, 1, 1)
-    rate = probe["pairs"] / probe["seconds"]
-    per_step_pairs_full = probe["pairs"] * (n_full / probe_n)
-    budget = 150.0
+    m = w["M"]
+    n = min(n_full, REF_SAMPLES[args.workload])
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    n_min = min(n_full, 500)
-    t_full = per_step_pairs_full / rate  # seconds of one full-size Robot.step() on these cores
-    n = int(max(n_min, min(n_full, n_full * budget / (t_full * (steps + warm)))))
-    t_n = t_full * n / n_full
-    if t_n * (steps + warm) > 1.5 * budget:  # even the smallest sample does not fit K steps: time fewer steps, say so
-        steps = max(1, int(1.5 * budget / t_n) - warm)
+    # the whole run must end within a few minutes: probe one step, then time as many steps as fit ~150 s
+    probe = run_oracle_steps(args.workload, n, m, 1, 0)
+    t_step = probe["seconds"]
+    budget = 150.0
+    if t_step * (steps + warm) > budget:
+        warm = min(warm, 1)
+        steps = max(1, int(budget / t_step) - warm)
     res = run_oracle_steps(args.workload, n, m, steps, warm)
     value = res["pairs"] / res["seconds"]
     clamp = "" if steps == max(1, args.steps) else f" ({args.steps} steps requested; clamped to fit the time budget)"
     sample = (f"{steps}{clamp} full Robot.step() calls of the oracle port (torch CPU fp32, all host threads) at N={n} samples "
-              f"(workload {args.workload} has N={n_full}), M={m}; the reference itself is Python and cannot travel to "
-              f"the GPU box, the port is pinned to it by tests/golden")
+              f"(workload {args.workload} has N={n_full}) and the workload's own M={m}; the reference itself is Python and "
+              f"cannot travel to the GPU box, the port is pinned to it by tests/golden")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm,
@@ -136,8 +146,10 @@ def reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, n_total=n, n_local=n,
                                   note="host CPU, oracle port of control_torch; a step here is one whole Robot.step() "
-                                       "(history + spread + ~13 evals)"),
-        "evals_per_s": res["evals"] / res["seconds"],
+                                       "(history + spread + ~13 evals) at a REDUCED sample count N (same M, same pair mix "
+                                       "as the GPU arm's e2e Robot.step(); the GPU arm's `also.same_size` runs exactly this "
+                                       "N and M)"),
+        "evals_per_s": res["evals"] / res["seconds"], "pair_mix": res["mix"],
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -145,10 +157,10 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(name, n_total, n_local, note=""):
+def workload_config(name, n_total, n_local, note="", m=None):
     w = wl.WORKLOADS[name]
     big = n_local * 4 * (len(w["states"]) + 3) > L2_BYTES
-    return {"workload": f"{name}: states={w['states']} H={w['H']} N={n_total} (per GPU {n_local}) M={w['M']} "
+    return {"workload": f"{name}: states={w['states']} H={w['H']} N={n_total} (per GPU {n_local}) M={m if m is not None else w['M']} "
                         f"target={w['target']} barrier=on R=0.5 dt=0.2",
             "pairs_per_eval": 2 * w["H"] * n_total,
             "l2_policy": ("alternating independent input sets, each larger than the 126 MB L2" if big else
@@ -282,10 +294,14 @@ def target_decoder_block(dev, timed):
         flop_issued = 3 * 2.0 * n_t * h1 * h2
         out[tag] = {"samples": n_t, "s_dim": sdim, "ms_kernel": t_kernel * 1e3, "ms_pdf_torch_call": t_call * 1e3,
                     "samples_per_s": n_t / t_kernel,
-                    "roofline": {"bound": "tensor", "achieved": flop_issued / t_kernel / 1e12, "peak": bf16 / 2, "unit": "TFLOP/s",
-                                 "frac": flop_issued / t_kernel / 1e12 / (bf16 / 2),
+                    # frac: against the NOMINAL dense tf32 peak (1.1 PFLOP/s); MEASURED_PEAKS.json has no tf32 entry, and the
+                    # figure derived from its bf16 number (half of a power-capped burst) is not a measured tf32 peak.  The
+                    # counter that says how busy the pipe is: ncu sm__pipe_tensor_cycles_active 82.5 % (profiles/r01_ncu_full_target_decoder_1e7.csv)
+                    "roofline": {"bound": "tensor", "achieved": flop_issued / t_kernel / 1e12, "peak": 1100.0, "unit": "TFLOP/s",
+                                 "frac": flop_issued / t_kernel / 1e12 / 1100.0,
+                                 "ncu_pipe_tensor_cycles_active": 0.825,
                                  "algorithmic_tflops": flop_alg / t_kernel / 1e12,
-                                 "nominal_peak": 1100.0, "frac_nominal": flop_issued / t_kernel / 1e12 / 1100.0,
+                                 "derived_peak_from_bf16": bf16 / 2, "frac_of_derived": flop_issued / t_kernel / 1e12 / (bf16 / 2),
                                  "peak_basis": f"tf32 dense = half of {src}; achieved counts the 3 tf32 MMAs of the 3xTF32 "
                                                "split (fp32-accurate result); algorithmic = 2*N*(19*256+256*512+512) fp32 flop"}}
         del smp
@@ -449,6 +465,18 @@ def cuda_arm(args):
     S = build_sets(args.workload, n_total, rank, group, dev, engine, Robot, PlannerContext)
     D, H, n = S["D"], S["H"], S["n"]
     K = args.steps
+    # sharded runs: every rank must hold bit-identical results (they drive identical host control flow)
+    rank_identical = None
+    if world > 1:
+        import torch.distributed as dist
+        c0 = S["sets"][0]
+        g0 = c0.gradient(c0.u)
+        flat = torch.cat([g0["du"].reshape(-1), g0["djdlam"].reshape(-1), g0["u_star"].reshape(-1)]).contiguous()
+        every = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(every, flat)
+        rank_identical = all(torch.equal(every[0], e) for e in every)
+        if not rank_identical:
+            raise SystemExit("ranks disagree on du / djdlam / u* of the same eval: the measurement is void")
     res = timed_evals(args, S, K, args.warmup, world, rank, lib, dev)
     if res is None:
         return
@@ -520,10 +548,13 @@ def cuda_arm(args):
         c3.buf.v_costs = torch.empty((c3.buf.max_g, c3.buf.ld), dtype=torch.float32, device=dev)
         gU = torch.Generator().manual_seed(2)
         U3 = (c3.u.cpu().unsqueeze(0) + 0.1 * torch.randn(1024, S3["H"], S3["D"], generator=gU)).to(dev)
+        l0 = lib.klerg_launch_count()
+        c3.costs(U3)
+        launches_c3 = int(lib.klerg_launch_count() - l0)
         t3 = timed(lambda: c3.costs(U3), 3)
         also["c3"] = {"workload": workload_config("c3", wl.WORKLOADS["c3"]["N"], S3["n"])["workload"] + " B=1024 candidates",
                       "ms_per_batch": t3 * 1e3, "pairs_per_s": 1024 * S3["H"] * S3["n"] / t3, "candidates_per_s": 1024 / t3,
-                      "launches_per_batch": 128,
+                      "launches_per_batch": launches_c3,
                       "roofline_frac": 1024 * S3["H"] * S3["n"] * max((2 * S3["D"] + 1) / peaks["fp32_lane_ops_per_s"],
                                                                     1 / peaks["ex2_per_s"]) / t3,
                       "note": "get_cost of 1024 candidates: 8 candidates per fused launch, forward pair pass only"}
@@ -571,62 +602,98 @@ def cuda_arm(args):
 
     # ---- e2e: Robot.step() through the public API with host buffers ---------------------------------
     e2e = None
+    same_size = None
     if not args.no_e2e:
         kw, m = S["kw"], w["M"]
         del S["sets"][:]  # free the resident sets; the planner owns its buffers
         torch.cuda.empty_cache()
-        torch.manual_seed(7)
-        robot = Robot(process_group=pg, **kw)
-        robot.test(1000)
-        for row in wl.random_walk_history(args.workload, min(m, robot.memory_buffer.capacity), seed=5):
-            robot.memory_buffer.push(row)
-        pairs = 0
-        nwarm = 2
-        for k in range(nwarm + args.e2e_steps):
-            if k == nwarm:
-                torch.cuda.synchronize()
-                if world > 1:
-                    import torch.distributed as dist
-                    dist.barrier()
-                t0 = time.perf_counter()
-                c0_, g0_ = robot.stats["cost_evals"], robot.stats["grad_evals"]
-                pairs = 0
-            m_all = len(robot.memory_buffer)
-            robot.step(n_total, m, save_update=True)
-            if k >= nwarm:
-                pairs += min(m, m_all) * n_total + m_all * n_total
-        torch.cuda.synchronize()
-        t_e2e = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        ce, ge = robot.stats["cost_evals"] - c0_, robot.stats["grad_evals"] - g0_
-        pairs += (ce + 2 * ge) * H * n_total
+
+        def time_robot_steps(n_steps, n_warm, n_samples, device_rng, kwargs):
+            """Robot.step() through the public API, wall clock around the timed steps (max over ranks)."""
+            torch.manual_seed(7)
+            robot = Robot(process_group=pg, **kwargs)
+            robot.device_rng = device_rng
+            robot.test(1000)
+            for row in wl.random_walk_history(args.workload, min(m, robot.memory_buffer.capacity), seed=5):
+                robot.memory_buffer.push(row)
+            hist = spread = 0
+            for k in range(n_warm + n_steps):
+                if k == n_warm:
+                    torch.cuda.synchronize()
+                    if world > 1:
+                        import torch.distributed as dist
+                        dist.barrier()
+                    t0 = time.perf_counter()
+                    c0_, g0_ = robot.stats["cost_evals"], robot.stats["grad_evals"]
+                m_all = len(robot.memory_buffer)
+                robot.step(n_samples, m, save_update=True)
+                if k >= n_warm:
+                    hist += min(m, m_all) * n_samples
+                    spread += m_all * n_samples
+            torch.cuda.synchronize()
+            t = time.perf_counter() - t0
+            if world > 1:
+                import torch.distributed as dist
+                tt = torch.tensor([t], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t = float(tt.item())
+            ce, ge = robot.stats["cost_evals"] - c0_, robot.stats["grad_evals"] - g0_
+            evp = (ce + 2 * ge) * H * n_samples
+            wrapped = getattr(robot, "_wrapped_target", None)
+            on_dev = device_rng and robot._device_draw_ok()
+            del robot
+            torch.cuda.empty_cache()
+            return dict(seconds=t, ce=ce, ge=ge, pairs=hist + spread + evp, mix=pair_mix(hist, spread, evp), wrapped=wrapped,
+                        device_draw=on_dev, m_all=m_all)
+
         steps_e = args.e2e_steps
-        wrapped = getattr(robot, "_wrapped_target", None)  # VAE-like target: p is computed on the device from the
-        p_bytes = n * 4 if wrapped is None else wrapped._staging.numel() * 4  # model's weights (re-read every step)
-        h2d = n * D * 4 + p_bytes + min(m, m_all) * 8 + (ce + ge) // steps_e * H * D * 4 + 2 * D * 4
-        d2h = (ge // steps_e) * (H * 4 + H * D * 4) + (ce // steps_e) * 4 + (H + 1) * 2 * D * 4 + 2 * D * 4
-        e2e = {"value": pairs / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        r = time_robot_steps(steps_e, 2, n_total, True, kw)
+        ce, ge, m_all = r["ce"], r["ge"], r["m_all"]
+        # bytes that cross PCIe per step, from the tensors the step copies
+        n_loc = n
+        per_eval_h2d, per_eval_d2h = H * D * 4, 0
+        sample_bytes = (624 * 4 + 16) if r["device_draw"] else n_loc * D * 4  # generator state vs the samples themselves
+        p_bytes = 0 if r["device_draw"] else (n_loc * 4 if r["wrapped"] is None else r["wrapped"]._staging.numel() * 4)
+        h2d = sample_bytes + p_bytes + min(m, m_all) * 8 + (m_all * 8 if m < m_all else 0) + (ce + ge) // steps_e * per_eval_h2d + 2 * D * 4
+        d2h = (626 * 4 if r["device_draw"] else 0) + (ge // steps_e) * (H * 4 + H * D * 4 + 4) + (ce // steps_e) * 4 * 9 \
+            + (H + 1) * 2 * D * 4 + 2 * D * 4
+        e2e = {"value": r["pairs"] / r["seconds"], "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": "control_torch.klerg.Robot.step(num_target_samples=N, num_traj_samples=M, save_update=True)",
-               "steps": steps_e, "ms_per_robot_step": t_e2e / steps_e * 1e3, "evals_per_s": (ce + ge) / t_e2e,
-               "evals_per_robot_step": (ce + ge) / steps_e,
-               "note": "samples drawn by the host torch RNG (reference order) and copied H2D every step together with the "
-                       + ("target density values" if wrapped is None else
-                          "decoder weights of the VAE-like target (p is evaluated on the device by klerg_target_decoder_pdf)")
-                       + "; history (M x N) and spread (M_all x N) passes included"}
+               "steps": steps_e, "ms_per_robot_step": r["seconds"] / steps_e * 1e3, "evals_per_s": (ce + ge) / r["seconds"],
+               "evals_per_robot_step": (ce + ge) / steps_e, "pair_mix": r["mix"],
+               "note": ("the step's host inputs are the robot state, the controls and torch's CPU generator: the workspace "
+                        "samples are drawn ON THE DEVICE from the generator's state (bit-exact with the host draw, "
+                        "klerg_mt19937_uniform), the host draws the memory-buffer permutation and copies the indices; "
+                        if r["device_draw"] else
+                        "samples drawn by the host torch RNG (reference order) and copied H2D every step; ")
+                       + "the target density is evaluated on the device; history footprint and spread are ONE M_all x N pass; "
+                         "pair_mix: most pairs of a step are history / spread pairs (forward-only, cheaper than eval pairs), "
+                         "which is why e2e pairs/s can exceed the eval-only `value`"}
+        if world == 1 and rank == 0:
+            rh = time_robot_steps(min(3, steps_e), 1, n_total, False, kw)
+            e2e["host_draw"] = {"ms_per_robot_step": rh["seconds"] / min(3, steps_e) * 1e3,
+                                "h2d_bytes_per_step": int(n_loc * D * 4 + min(m, m_all) * 8),
+                                "note": "the same steps with the samples drawn by the host generator and copied H2D (4*N*D bytes)"}
+            # the reference arm's exact problem: reduced N, the workload's own M (same_config comparison)
+            n_ref = min(n_total, REF_SAMPLES[args.workload])
+            kw_ref = wl.robot_kwargs(args.workload, S["target"], n_samples=n_ref)
+            rs = time_robot_steps(10, 2, n_ref, True, kw_ref)
+            same_size = {"workload": workload_config(args.workload, n_ref, n_ref)["workload"],
+                         "ms_per_robot_step": rs["seconds"] / 10 * 1e3, "pairs_per_s": rs["pairs"] / rs["seconds"],
+                         "pair_mix": rs["mix"],
+                         "note": "Robot.step() at the N and M `bench.py --impl reference` runs: same problem on both arms"}
 
     # ---- cpu_baseline: the oracle port on this box's host cores (rank 0, N=1 only) ---------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_cpu = min(n_total, 80_000 if D > 3 else 160_000)  # ~10-15 s of host work incl. the warm-up step on a 16-core box
-        m_cpu = min(w["M"], 1000)
+        n_cpu = min(n_total, REF_SAMPLES[args.workload])  # ~10-30 s of host work incl. the warm-up step
+        m_cpu = w["M"]
         r_cpu = run_oracle_steps(args.workload, n_cpu, m_cpu, 2, 1)
         cpu = {"value": r_cpu["pairs"] / r_cpu["seconds"], "unit": "pairs/s", "cores": r_cpu["cores"], "kind": "port",
                "sample": f"2 OracleRobot.step() calls (torch CPU fp32, all host threads) at N={n_cpu}, M={m_cpu}, "
                          f"H={H}: {r_cpu['evals']} evals in {r_cpu['seconds']:.2f} s",
-               "evals_per_s": r_cpu["evals"] / r_cpu["seconds"]}
+               "evals_per_s": r_cpu["evals"] / r_cpu["seconds"], "ms_per_robot_step": r_cpu["seconds"] / 2 * 1e3,
+               "pair_mix": r_cpu["mix"]}
 
     if rank == 0:
         line = {
@@ -639,6 +706,11 @@ def cuda_arm(args):
             "evals_per_s": evals_per_s, "gpu_launches": res["gpu_launches"], "clocks": clocks, "e2e": e2e,
             "roofline": roof, "cpu_baseline": cpu, "also": also,
         }
+        if same_size is not None:
+            line["also"] = dict(line["also"] or {})
+            line["also"]["same_size"] = same_size
+        if rank_identical is not None:
+            line["rank_identical"] = rank_identical
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -129,6 +129,7 @@ SIGNATURES = {
                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_adjoint_targets": [_DS, _KS, _I64, _I64, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float), _F,
                               C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
+    "klerg_mt19937_uniform": [_P, _I32, _I32, _I64, _I32, _FP, _FP, _I64, _I64, _P, _P, _P],
     "klerg_gather_rows": [_P, _I32, _P, _I64, _P, _P],
     "klerg_mailbox_bytes": [],
     "klerg_mailbox_create": [C.POINTER(C.c_void_p), C.c_char_p],

@@ -549,6 +549,41 @@ def fused_fault():
     return bool(ws.buf[off:off + 4].view(torch.int32).item())
 
 
+# torch.get_rng_state() of the CPU generator (ATen CPUGeneratorImplStateLegacy): seed u64, left i32 @8, seeded i32,
+# next u64 @16, state u64[624] @24, then the normal-distribution cache
+_RNG_LEFT, _RNG_NEXT, _RNG_STATE, _RNG_WORDS = 8, 16, 24, 624
+
+
+def device_uniform(n_rows, low, high, row_lo=0, row_hi=None, device=None):
+    """``Uniform(low, high).sample((n_rows,))`` of torch's CPU default generator, drawn ON THE DEVICE from the
+    generator's own state (klerg_mt19937_uniform): bit-exact samples, and the host generator is left where the host
+    draw would have left it.  Returns rows [row_lo, row_hi) as a CUDA tensor [rows, D]."""
+    import numpy as np
+    dev = device or _dev()
+    low = torch.as_tensor(low, dtype=torch.float32).reshape(-1)
+    span = torch.as_tensor(high, dtype=torch.float32).reshape(-1) - low  # fp32, as Uniform.rsample computes it
+    D = low.numel()
+    row_hi = n_rows if row_hi is None else row_hi
+    blob = torch.get_rng_state()
+    raw = blob.numpy()
+    left = int(raw[_RNG_LEFT:_RNG_LEFT + 4].view(np.int32)[0])
+    nxt = int(raw[_RNG_NEXT:_RNG_NEXT + 8].view(np.uint64)[0])
+    words = torch.from_numpy(raw[_RNG_STATE:_RNG_STATE + 8 * _RNG_WORDS].view(np.uint64).astype(np.uint32).view(np.int32))
+    st_in = words.to(dev, non_blocking=True)
+    st_out = torch.empty(_RNG_WORDS + 2, dtype=torch.int32, device=dev)
+    out = torch.empty((max(row_hi - row_lo, 0), D), dtype=torch.float32, device=dev)
+    cabi.check(cabi.load().klerg_mt19937_uniform(
+        cabi.ptr(st_in), left, nxt, int(n_rows), D, cabi.farr(low.tolist()), cabi.farr(span.tolist()), int(row_lo),
+        int(row_hi), cabi.ptr(out) if out.numel() else None, cabi.ptr(st_out), cabi.stream_ptr()), "klerg_mt19937_uniform")
+    back = st_out.cpu().numpy().view(np.uint32)  # one small D2H: the host generator continues from here
+    new = raw.copy()
+    new[_RNG_LEFT:_RNG_LEFT + 4] = np.array([back[_RNG_WORDS]], dtype=np.int32).view(np.uint8)
+    new[_RNG_NEXT:_RNG_NEXT + 8] = np.array([back[_RNG_WORDS + 1]], dtype=np.uint64).view(np.uint8)
+    new[_RNG_STATE:_RNG_STATE + 8 * _RNG_WORDS] = back[:_RNG_WORDS].astype(np.uint64).view(np.uint8)
+    torch.set_rng_state(torch.from_numpy(new))
+    return out
+
+
 def gather_rows(table, idx):
     """table [cap,S] float32, idx [M] int64 (device) -> [M,S]."""
     M, S = idx.numel(), table.shape[1]

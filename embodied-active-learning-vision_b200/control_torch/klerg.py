@@ -46,6 +46,14 @@ except ImportError:  # package used outside the reference's scripts/ layout
     from franka.franka_utils import find_non_vel_locs, ws_conversion
 
 
+class DeviceSamples:
+    """Workspace samples that only exist on the device: this rank's rows + the row count over all ranks."""
+
+    def __init__(self, local, n_total):
+        self.local = local
+        self.shape = (int(n_total), local.shape[1])
+
+
 def line_search_windows(t_app, idx, horizon, max_app_dur=5):
     """Windows [tau_i, tau_f) the reference's line_search would try, in order (klerg.py:714-738)."""
     if t_app == 0 or t_app == horizon - 1:
@@ -324,14 +332,42 @@ class Robot(object):
         if self.add_recent_history:
             recent = self.memory_buffer.get_recent(self.horizon)
             num_target_samples -= len(recent)
-        samples = self.env_sampler.sample((num_target_samples,))
+        extras = []
         if self.add_recent_history:
-            samples = torch.vstack([samples, recent[:, self.explr_locs]])
+            extras.append(recent[:, self.explr_locs])
         if self.test_corners:
-            samples = torch.vstack([samples, self.corner_samples])
+            extras.append(self.corner_samples)
+        if self._device_draw_ok():
+            # the same draw, continued on the device from the host generator's state (bit-exact samples, the host
+            # generator ends where the host draw would have left it): no 4*N*D-byte host pass and copy per step
+            n_total = num_target_samples + sum(len(e) for e in extras)
+            lo, hi = self.group.shard_bounds(n_total)
+            parts = [engine.device_uniform(num_target_samples, self.env_sampler.low, self.env_sampler.high,
+                                           min(lo, num_target_samples), min(hi, num_target_samples), self.cuda)]
+            off = num_target_samples
+            for e in extras:  # appended rows that fall into this rank's slice
+                a, b = max(lo, off) - off, min(hi, off + len(e)) - off
+                if b > a:
+                    parts.append(e[a:b].to(self.cuda, non_blocking=True))
+                off += len(e)
+            samples = DeviceSamples(torch.cat(parts).contiguous() if len(parts) > 1 else parts[0], n_total)
+        else:
+            samples = self.env_sampler.sample((num_target_samples,))
+            if extras:
+                samples = torch.vstack([samples] + extras)
         hist_dev, hist_idx = self.memory_buffer.sample_device(num_traj_samples)
         self.last_hist_idx = hist_idx
         return samples, hist_dev, torch.ones(1)
+
+    device_rng = True  # draw the workspace samples on the device when nothing needs them on the host
+
+    def _device_draw_ok(self):
+        """The samples can stay on the device when the target density is evaluated there and no plot data (host
+        tensors by contract, klerg.py:659-682) is kept."""
+        if not self.device_rng or self.plot_data is not None or self.uniform_tdist or self.use_prior:
+            return False
+        target = self._device_target()
+        return torch.device(getattr(target, "device", "cpu")).type == "cuda"
 
     def _pdf(self, samples_host, uniform, samples_dev=None):
         """The target density is an INPUT of the path (VAE / belief grid); evaluated where it lives.
@@ -347,7 +383,7 @@ class Robot(object):
             raise NotImplementedError("use_prior is not ported")
         target = self._device_target()
         tdev = torch.device(target.device)
-        if samples_dev is not None and tdev == samples_dev.device:
+        if samples_dev is not None and tdev.type == samples_dev.device.type and tdev.index in (None, samples_dev.device.index):
             return target.pdf_torch(samples_dev.clone()).squeeze(), False
         return target.pdf_torch(self._shard(samples_host).clone().to(tdev)).squeeze(), False
 
@@ -433,7 +469,10 @@ class Robot(object):
             ctx = self.ctx = self._context()
             if prev is not None:
                 ctx.buf = prev.buf  # eval scratch / output buffers are reused from step to step when the shapes match
-            samples_dev = self._shard(samples).to(self.cuda, non_blocking=True).contiguous()
+            if isinstance(samples, DeviceSamples):
+                samples_dev = samples.local
+            else:
+                samples_dev = self._shard(samples).to(self.cuda, non_blocking=True).contiguous()
             ctx.set_samples(samples_dev, self.std.tolist(), 1.0, n_total=samples.shape[0])
             ctx.set_state(self.robot.state.to(self.cuda, non_blocking=True))
             spread = None

@@ -323,6 +323,20 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
                      const double* p_stats, float floor, float* v_scratch, float* traj, double* totals,
                      float* cost, float* fault_out, void* workspace, void* stream);
 
+/* ---- a8: workspace samples of Robot.get_samples (klerg.py:173,375) --------- */
+
+/* samples[i][d] = low[d] + torch.rand(n_rows, D)[i][d] * high_minus_low[d] for rows row_lo <= i < row_hi, drawn with
+ * torch's CPU generator CONTINUED ON THE DEVICE: state624 (device, 624 words) / left / next are the MT19937 state
+ * and counters of torch.get_rng_state() (ATen CPUGeneratorImplStateLegacy: left int32 at byte 8, next uint64 at 16,
+ * state uint64[624] at 24).  The whole stream of n_rows * D numbers is generated (bit-exact with the host draw);
+ * only the requested rows are written: out[(i - row_lo) * D + d].  state_out (device, 626 words) receives the state
+ * followed by left and next after the draw - the caller writes them back with torch.set_rng_state so that the
+ * memory-buffer randperm that follows (memory_buffer.py:58) draws what it would have drawn.  low / high_minus_low:
+ * HOST arrays of D floats (Uniform.low, high - low as torch computes it in fp32). */
+int klerg_mt19937_uniform(const uint32_t* state624, int32_t left, int32_t next, int64_t n_rows, int32_t D,
+                          const float* low, const float* high_minus_low, int64_t row_lo, int64_t row_hi, float* out,
+                          uint32_t* state_out, void* stream);
+
 /* ---- a19: memory-buffer selection (memory_buffer.py:52-63) ---------------- */
 
 /* out[m] = table[idx[m]] for m < M; idx are the host-drawn torch.randperm

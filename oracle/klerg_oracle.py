@@ -43,16 +43,28 @@ def kernel_matrix(states_explr, samples, scale, nu):
     return torch.exp(-0.5 * torch.sum(inner, 2)) / nu
 
 
+PAIR_CHUNK_BYTES = 1 << 28  # the [N, T, D] broadcast of the reference is evaluated in sample chunks of this size
+
+
+def _sample_chunks(samples, n_states):
+    """The reference materialises [N, T, D] (klerg_utils.py:8): 2.4e13 B at BASELINE config 4.  Rows of the result are
+    independent, so the oracle walks the sample axis in chunks - bit-identical per sample."""
+    per = max(1, PAIR_CHUNK_BYTES // (4 * max(1, n_states) * max(1, samples.shape[1])))
+    return [samples] if samples.shape[0] <= per else list(torch.split(samples, per))
+
+
 def footprint_sum(states, samples, explr, scale, nu):
     """q_i = sum_j psi[i, j] (klerg_utils.py:17-22)."""
-    sub = states[:, explr]
-    return torch.sum(kernel_matrix(sub.unsqueeze(0), samples.unsqueeze(1), torch.abs(scale), nu), 1)
+    sub = states[:, explr].unsqueeze(0)
+    return torch.cat([torch.sum(kernel_matrix(sub, c.unsqueeze(1), torch.abs(scale), nu), 1)
+                      for c in _sample_chunks(samples, states.shape[0])])
 
 
 def spread_max(states, samples, explr, scale, nu):
     """max_j psi[i, j] (klerg_utils.py:24-29)."""
-    sub = states[:, explr]
-    return torch.amax(kernel_matrix(sub.unsqueeze(0), samples.unsqueeze(1), torch.abs(scale), nu), 1)
+    sub = states[:, explr].unsqueeze(0)
+    return torch.cat([torch.amax(kernel_matrix(sub, c.unsqueeze(1), torch.abs(scale), nu), 1)
+                      for c in _sample_chunks(samples, states.shape[0])])
 
 
 def kl_gradient(x, samples, explr, scale, weights, nu):
