@@ -46,7 +46,12 @@ constexpr size_t MB_OFF_GB = MB_OFF_KL + MB_KL;
 constexpr size_t MB_OFF_GP = MB_OFF_GB + MB_GB;
 constexpr size_t MB_OFF_DBG = MB_OFF_GP + MB_GP;                     // [cta][8] globaltimer stamps (KLERG_STAMPS builds)
 constexpr size_t MB_DBG = (size_t)LL_MAXBLK * 8 * 8;
-constexpr size_t MB_BYTES = MB_OFF_DBG + MB_DBG;
+// [par] rollout of the launch (states [H+1][S], rotations), published by its first CTA for the CTAs that start later;
+// header word 4 + par holds epoch + 1 once it is complete
+constexpr size_t MB_RO_FLOATS = (size_t)(KLERG_MAX_H + 1) * KLERG_MAX_S + (size_t)(2 * KLERG_MAX_H + 1) * 9;
+constexpr size_t MB_OFF_RO = MB_OFF_DBG + MB_DBG;
+constexpr size_t MB_RO = 2 * ((MB_RO_FLOATS * sizeof(float) + 15) & ~(size_t)15);
+constexpr size_t MB_BYTES = MB_OFF_RO + MB_RO;
 
 constexpr size_t FUSED_BYTES = FUSED_CTRL + MB_BYTES;  // single GPU: the mailbox lives inside the workspace
 constexpr size_t HEAD_BYTES = HEAD_COUNTERS + HEAD_MISC + HEAD_GRAD + FUSED_BYTES;

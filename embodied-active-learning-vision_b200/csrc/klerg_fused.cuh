@@ -569,14 +569,34 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
   if (tid == 0) {
     s_epoch[0] = ld_acquire_u32(mb_hdr(me));      // launches so far on this mailbox
     s_epoch[1] = ld_acquire_u32(mb_hdr(me) + 1);  // gather exchanges so far
+    // The rollout is the same in every CTA.  The launch's first CTA publishes it; a CTA that starts later (with
+    // overlapping launches the first CTA of the next eval starts while this eval's gradient pass is still running
+    // everywhere else) copies it instead of redoing it.
+    s_flag[0] = vblk != 0 && ld_acquire_u32(mb_hdr(me) + 4 + (s_epoch[0] & 1u)) == s_epoch[0] + 1u;
   }
   for (int e = tid; e < H * A; e += blockDim.x) s_u[e] = a.u[e];
   if (tid < S) s_x0[tid] = a.x0[tid];
   if (a.R0 && tid >= 32 && tid < 41) s_x0[KLERG_MAX_S + tid - 32] = a.R0[tid - 32];
   __syncthreads();
   KLERG_STAMP(8);
-  rollout_block(a.d, a.bar, s_x0, a.R0 ? s_x0 + KLERG_MAX_S : nullptr, s_u, 1, H, s_traj, nullptr, nullptr, s_rot, (float*)s_red,
-                s_bsum, nullptr, 1);
+  const int n_rot = roll ? rollout_rot_floats(1, H) : 0;
+  if (s_flag[0]) {
+    const float* ro = mb_ro(me, s_epoch[0] & 1u);
+    for (int e = tid; e < (H + 1) * S; e += blockDim.x) s_traj[e] = __ldcg(ro + e);
+    for (int e = tid; e < n_rot; e += blockDim.x) s_rot[e] = __ldcg(ro + (H + 1) * S + e);
+    __syncthreads();
+  } else {
+    rollout_block(a.d, a.bar, s_x0, a.R0 ? s_x0 + KLERG_MAX_S : nullptr, s_u, 1, H, s_traj, nullptr, nullptr, s_rot, (float*)s_red,
+                  s_bsum, nullptr, 1);
+    if (vblk == 0) {
+      float* ro = mb_ro(me, s_epoch[0] & 1u);
+      for (int e = tid; e < (H + 1) * S; e += blockDim.x) ro[e] = s_traj[e];
+      for (int e = tid; e < n_rot; e += blockDim.x) ro[(H + 1) * S + e] = s_rot[e];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_u32(mb_hdr(me) + 4 + (s_epoch[0] & 1u), s_epoch[0] + 1u);
+    }
+  }
   KLERG_STAMP(9);
   const unsigned epoch = s_epoch[0], xc = s_epoch[1];
   if (vblk == 0 && a.traj)

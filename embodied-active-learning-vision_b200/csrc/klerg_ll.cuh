@@ -43,6 +43,10 @@ __device__ __forceinline__ u64* mb_gp(void* base, int par, int e) {
   return (u64*)((char*)base + MB_OFF_GP) + ((size_t)par * LL_MAXHD + e) * LL_MAXBLK;
 }
 
+__device__ __forceinline__ float* mb_ro(void* base, int par) {
+  return (float*)((char*)base + MB_OFF_RO + (size_t)par * (MB_RO / 2));
+}
+
 // tag of exchange `id` of the launch / exchange numbered `counter` (never 0: mailboxes start zero-filled)
 __device__ __forceinline__ unsigned ll_tag(unsigned counter, unsigned id) {
   return (((counter + 1u) & 0xFFFFFFu) << 8) | (id & 0xFFu);
