@@ -522,6 +522,22 @@ def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, 
     return cost
 
 
+def eval_costs_batch(spec, dyn, bar, x0, R0, U, packed, n, q_base, p, p_stats, floor=FLOOR):
+    """ONE launch: get_cost of any number of candidates U [B,H,A] -> cost [B] (klerg_eval_costs_batch; single GPU)."""
+    lib = cabi.load()
+    B, H, _ = U.shape
+    dev = U.device
+    ld = packed.shape[1]
+    v = torch.empty((B, ld), dtype=torch.float32, device=dev)
+    scratch = torch.empty(lib.klerg_eval_costs_batch_scratch_bytes(B, H, spec.D), dtype=torch.uint8, device=dev)
+    pack = torch.zeros(B + 1, dtype=torch.float32, device=dev)  # costs + fault word
+    cabi.check(lib.klerg_eval_costs_batch(
+        C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, cabi.ptr(x0), cabi.ptr(R0), cabi.ptr(U), B, H,
+        cabi.ptr(packed), int(n), ld, cabi.ptr(q_base), cabi.ptr(p), cabi.ptr(p_stats), float(floor), cabi.ptr(v),
+        cabi.ptr(scratch), None, cabi.ptr(pack), cabi.ptr(pack[B:]), workspace(8), cabi.stream_ptr()), "klerg_eval_costs_batch")
+    return pack[:B], pack[B:]
+
+
 def debug_stamps():
     """SM-cycle stamps of the last fused gradient eval on the current stream's workspace (8 int64)."""
     key = (torch.cuda.current_device(), cabi.raw_stream())

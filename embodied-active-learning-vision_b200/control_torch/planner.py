@@ -102,6 +102,10 @@ class PlannerContext:
                 engine.eval_costs(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, U, self.packed, self.n,
                                   self.q_base, self.p, self.p_stats, self.buf.v_costs, pack[:B], self.floor, fault=pack[mg:])
                 cost = pack[:B] if view else pack[:B].clone()
+            elif self.peers is None and self.batch_costs:
+                # any number of candidates in ONE launch (BASELINE config 3)
+                cost, _ = engine.eval_costs_batch(self.spec, self.dyn, self.bar, self.x0, self.R0, U, self.packed, self.n,
+                                                  self.q_base, self.p, self.p_stats, self.floor)
             else:
                 cost = torch.empty(B, dtype=torch.float32, device=U.device)
                 for b0 in range(0, B, mg):
@@ -212,6 +216,8 @@ class PlannerContext:
         if len(outs) == 1:
             return {k: outs[0][k] for k in ("du", "djdlam", "u_star", "dgdx")}
         return {k: torch.cat([o[k] for o in outs]) for k in ("du", "djdlam", "u_star", "dgdx")}
+
+    batch_costs = True  # more than 8 candidates on a single GPU: klerg_eval_costs_batch instead of launches of 8
 
     # shared-psi path: psi once per state-sample pair, the sum over the samples as a tensor-core contraction
     targets_path = "auto"  # "auto" | "fused" | "tensor"

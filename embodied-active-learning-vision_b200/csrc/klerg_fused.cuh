@@ -380,7 +380,7 @@ __device__ __forceinline__ bool stage_state_rows(const EvalArgs& a, const float*
 // H pairs); v[g][i] to HBM; the CTA's {sum, max} per candidate end up in s_in[2g], s_in[2g + 1].
 template <int D, int P>
 __device__ __forceinline__ void forward_candidates(const EvalArgs& a, const StateRows& sr, int G, int H, int64_t lo, int64_t hi,
-                                                   double* s_red, double* s_in) {
+                                                   double* s_red, double* s_in, float* vbase) {
   constexpr int SPT = 2 * P, DP = Row2<D>::DP, NF = RowX<D>::NF;
   const int tid = threadIdx.x;
   double tsum[FUSED_MAXG], tmax[FUSED_MAXG];
@@ -444,7 +444,7 @@ __device__ __forceinline__ void forward_candidates(const EvalArgs& a, const Stat
       }
       tsum[g] = ts;
       tmax[g] = tm;
-      float* vp = a.v + (size_t)g * a.ld + i0;
+      float* vp = vbase + (size_t)g * a.ld + i0;
       if constexpr (P == 2)
         *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
       else
@@ -1077,6 +1077,63 @@ __global__ void __launch_bounds__(MAXT) eval_grad_emu_kernel(const __grid_consta
     eval_grad_body<D, WT, MIXED, LEFT, TS_ROW>(a1, (int)blockIdx.x - nb, nb, smem);
 }
 
+// KL partials of G candidates over the slice [lo, hi): sa[g] = sum_i p_i (log p_i - log c_i), sc[g] = sum_i c_i
+// (klerg.py:694-699 in closed form), from v[g][i] = q_base + q_iter and the candidates' world totals {sum, max}.
+// Four samples per thread-iteration (128-bit loads of v and p), reciprocal of the normaliser and lg2-based
+// logarithms: the pass is instruction-bound (IEEE division + logf cost ~60 instructions per sample and candidate,
+// this form ~12); the cost changes by < 1e-6 relative, far inside the 1e-4 parity tolerance.
+__device__ __forceinline__ void kl_pass(const EvalArgs& a, int G, const float* vbase, const double* s_world, int64_t lo, int64_t hi,
+                                        double (&sa)[FUSED_MAXG], double (&sc)[FUSED_MAXG]) {
+  const int tid = threadIdx.x;
+  float rvs[FUSED_MAXG], maxc[FUSED_MAXG];
+#pragma unroll
+  for (int g = 0; g < FUSED_MAXG; ++g) {
+    sa[g] = sc[g] = 0.0;
+    rvs[g] = maxc[g] = 1.f;
+    if (g < G) {
+      const double vsum = s_world[2 * g], vmax = s_world[2 * g + 1];
+      const float vs = (float)vsum;
+      rvs[g] = 1.f / vs;
+      maxc[g] = fmaxf((float)vmax / vs, a.floor);
+    }
+  }
+  const int64_t hiN = hi < a.N ? hi : a.N;
+  for (int64_t i0 = lo + (int64_t)tid * 4; i0 < hiN; i0 += (int64_t)blockDim.x * 4) {
+    float pv[4], lp[4];
+    if (i0 + 3 < a.N) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(a.p + i0));
+      pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pv[q] = (i0 + q < a.N) ? a.p[i0 + q] : 1.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (pv[q] != pv[q]) pv[q] = 1e-6f;
+      lp[q] = __logf(pv[q]);
+    }
+#pragma unroll
+    for (int g = 0; g < FUSED_MAXG; ++g) {
+      if (g < G) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(vbase + (size_t)g * a.ld + i0));
+        const float vv[4] = {t.x, t.y, t.z, t.w};
+        float fa = 0.f, fc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (i0 + q < hiN) {
+            float c = fmaxf(vv[q] * rvs[g], a.floor);
+            if (c != c) c = 1e-6f * maxc[g];  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
+            fa = fmaf(pv[q], lp[q] - __logf(c), fa);
+            fc += c;
+          }
+        }
+        sa[g] += (double)fa;
+        sc[g] += (double)fc;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // cost eval of G <= FUSED_MAXG candidates
 // ---------------------------------------------------------------------------
@@ -1136,9 +1193,9 @@ __device__ __forceinline__ void eval_cost_body(const EvalArgs& a, const int vblk
   int64_t lo, hi;
   cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
   if (narrow_pairs(lo, hi))
-    forward_candidates<D, 1>(a, sr, G, H, lo, hi, s_red, s_in);
+    forward_candidates<D, 1>(a, sr, G, H, lo, hi, s_red, s_in, a.v);
   else
-    forward_candidates<D, 2>(a, sr, G, H, lo, hi, s_red, s_in);
+    forward_candidates<D, 2>(a, sr, G, H, lo, hi, s_red, s_in, a.v);
   // meeting (1): {sum, max} per candidate over every CTA of every rank
   if (tid == 0) ll_wait_exchange_free(me, xc, ctrl);
   ll_allreduce(a.peers, vblk, vnblk, epoch, 1u, 2 * G, 0xAAAAu, s_in, s_world, s_ll, ctrl);
@@ -1151,58 +1208,8 @@ __device__ __forceinline__ void eval_cost_body(const EvalArgs& a, const int vblk
   pdl_launch_dependents();
   if (vblk == 0 && tid < 2 * G && a.totals) a.totals[tid] = s_world[tid];
 
-  // KL partials: sum_i p_i (log p_i - log c_i), sum_i c_i   (klerg.py:694-699 in closed form)
-  // Four samples per thread-iteration (128-bit loads of v and p), reciprocal of the normaliser and lg2-based
-  // logarithms: the pass is instruction-bound (IEEE division + logf cost ~60 instructions per sample and candidate,
-  // this form ~12); the cost changes by < 1e-6 relative, far inside the 1e-4 parity tolerance.
-  float rvs[FUSED_MAXG], maxc[FUSED_MAXG];
   double sa[FUSED_MAXG], sc[FUSED_MAXG];
-#pragma unroll
-  for (int g = 0; g < FUSED_MAXG; ++g) {
-    sa[g] = sc[g] = 0.0;
-    rvs[g] = maxc[g] = 1.f;
-    if (g < G) {
-      const double vsum = s_world[2 * g], vmax = s_world[2 * g + 1];
-      const float vs = (float)vsum;
-      rvs[g] = 1.f / vs;
-      maxc[g] = fmaxf((float)vmax / vs, a.floor);
-    }
-  }
-  const int64_t hiN = hi < a.N ? hi : a.N;
-  for (int64_t i0 = lo + (int64_t)tid * 4; i0 < hiN; i0 += (int64_t)blockDim.x * 4) {
-    float pv[4], lp[4];
-    if (i0 + 3 < a.N) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(a.p + i0));
-      pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pv[q] = (i0 + q < a.N) ? a.p[i0 + q] : 1.f;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (pv[q] != pv[q]) pv[q] = 1e-6f;
-      lp[q] = __logf(pv[q]);
-    }
-#pragma unroll
-    for (int g = 0; g < FUSED_MAXG; ++g) {
-      if (g < G) {
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(a.v + (size_t)g * a.ld + i0));
-        const float vv[4] = {t.x, t.y, t.z, t.w};
-        float fa = 0.f, fc = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (i0 + q < hiN) {
-            float c = fmaxf(vv[q] * rvs[g], a.floor);
-            if (c != c) c = 1e-6f * maxc[g];  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
-            fa = fmaf(pv[q], lp[q] - __logf(c), fa);
-            fc += c;
-          }
-        }
-        sa[g] += (double)fa;
-        sc[g] += (double)fc;
-      }
-    }
-  }
+  kl_pass(a, G, a.v, s_world, lo, hi, sa, sc);
   block_reduce_pairs(G, RED_SUM, sa, sc, s_red);
   // gather: the CTA's 2G KL terms as tagged values; the finisher adds them in CTA order, then in rank order
   const int xpar = xc & 1u;

@@ -323,6 +323,17 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
                      const double* p_stats, float floor, float* v_scratch, float* traj, double* totals,
                      float* cost, float* fault_out, void* workspace, void* stream);
 
+/* The same for ANY number of candidates B (BASELINE config 3: 1024 candidates x horizon 50 x 1e6 samples) in ONE launch:
+ * rollouts spread over the grid, forward pair pass per group of 8 candidates over L2-resident samples, one grid-wide
+ * meeting for all candidates' normalisers, KL pass, costs.  Single GPU.  v_scratch: B*ld floats; scratch:
+ * klerg_eval_costs_batch_scratch_bytes(B, H, D) bytes; totals[B][2] may be NULL. */
+size_t klerg_eval_costs_batch_scratch_bytes(int64_t B, int64_t H, int32_t D);
+int klerg_eval_costs_batch(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                           const float* x0, const float* R0, const float* u, int64_t B, int64_t H, const float* packed,
+                           int64_t N, int64_t ld, const float* q_base, const float* p, const double* p_stats,
+                           float floor, float* v_scratch, void* scratch, double* totals, float* cost, float* fault_out,
+                           void* workspace, void* stream);
+
 /* ---- a8: workspace samples of Robot.get_samples (klerg.py:173,375) --------- */
 
 /* samples[i][d] = low[d] + torch.rand(n_rows, D)[i][d] * high_minus_low[d] for rows row_lo <= i < row_hi, drawn with

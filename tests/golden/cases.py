@@ -31,6 +31,8 @@ ROBOT_CASES = {
     "xyzrpw": dict(states="xyzrpw", D=6, horizon=10, cap=40, n=500, m=30, steps=8, std=0.3,
                    x0=[0.1, 0.0, -0.2, 3.0, 0.1, 0.3, 0, 0, 0, 0, 0, 0]),
     "xyXY_vel": dict(states="xyXY", D=4, horizon=10, cap=40, n=500, m=30, steps=8, std=0.1, x0=[0.2, 0.1, 0.0, 0.0], vel=True),
+    "xyXY_speed": dict(states="xyXY", D=4, horizon=10, cap=40, n=500, m=30, steps=8, std=0.1, x0=[0.2, 0.1, 0.0, 0.0], vel=True,
+                       magnitude=True),
     "xy_weightenv": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=8, std=0.05, x0=[0.5, 0.5, 0, 0], weight_env=True),
     "xy_uniform": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=6, std=0.05, x0=[-0.5, 0.5, 0, 0], uniform=True),
 }
@@ -52,6 +54,7 @@ def robot_kwargs(case, target):
         buffer_capacity=case["cap"], std=case["std"], std_plot=case["std"], states=st,
         plot_states=st[:2], tray_lim=np.array(lim), robot_ctrl_lim=np.array(ctrl),
         plot_data=bool(case.get("plot")), uniform_tdist=bool(case.get("uniform")), vel_states=bool(case.get("vel")),
+        use_magnitude=bool(case.get("magnitude")),
     )
 
 

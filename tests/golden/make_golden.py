@@ -199,9 +199,12 @@ def record_utils(ru, rb, rd, rm):
 def main():
     rk, ru, rb, rd, rm = import_reference()
     torch.set_num_threads(1)  # fixed reduction order for reproducible fixtures
-    record_utils(ru, rb, rd, rm)
+    only = sys.argv[1:]  # optional: names of the robot cases to (re)record; default = everything
+    if not only:
+        record_utils(ru, rb, rd, rm)
     for name, case in ROBOT_CASES.items():
-        record_robot_case(rk, name, case)
+        if not only or name in only:
+            record_robot_case(rk, name, case)
 
 
 if __name__ == "__main__":

@@ -63,7 +63,7 @@ def oracle_grad(o, samples, p, q_base, u):
 
 
 def test_config3_batched_candidates():
-    """64 candidates x H=50 x 2e4 samples in chunks of 8 per launch; 6 of them against the oracle."""
+    """64 candidates x H=50 x 2e4 samples in ONE launch (klerg_eval_costs_batch); 6 of them against the oracle."""
     s = setup("c3", 20_000, 300)
     u0 = wl.random_controls((s["H"], s["D"]), seed=1)
     g = torch.Generator().manual_seed(2)
@@ -76,8 +76,15 @@ def test_config3_batched_candidates():
     perm = torch.randperm(64, generator=g)
     got_perm = s["ctx"].costs(U[perm].to(s["dev"])).cpu()
     assert torch.equal(got_perm, got[perm])
+    # one by one through the <= 8-candidate kernel: same numbers up to the rounding of the sums (other grid, other centre
+    # of the expanded pair form)
     one = torch.stack([s["ctx"].costs(U[b:b + 1].to(s["dev"]))[0] for b in (3, 40)]).cpu()
-    assert torch.equal(one, got[[3, 40]])
+    close(one, got[[3, 40]], rtol=2e-6, what="batch vs one by one")
+    # and through launches of 8 (the path of a sharded context): same again
+    s["ctx"].batch_costs = False
+    eight = s["ctx"].costs(U.to(s["dev"])).cpu()
+    s["ctx"].batch_costs = True
+    close(eight, got, rtol=2e-6, what="batch vs launches of 8")
 
 
 @pytest.mark.parametrize("H", [20, 50])
