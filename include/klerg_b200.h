@@ -378,6 +378,19 @@ int klerg_kl_gradient_targets(const klerg_kernel_spec* k, const float* states, i
                               const float* P, int64_t K, int64_t p_stride, float floor, double* grad_part,
                               double* kl_part, void* scratch, uint32_t* fault, void* stream);
 
+/* ---- fingerprint belief update ----------------------------- */
+
+/* FingerprintDist.update_prior (franka_test/scripts/dist_modules/fingerprint_module.py:539-589; meas_footprint_vec
+ * :417-424; numpy renormalize, control/klerg_utils.py:41-54): the per-grid-point normal belief {prior, prior_var}
+ * over grid[G][D] (the 50^D mesh of build_grid, :504-519) after n measurements at locs[n][D].  meas_sum =
+ * sum_j (val_j / 2 + 0.5) over the processed measurement values (process_meas, :470-478; a host scalar).  All arrays
+ * DEVICE float64 like the reference's numpy arrays; posterior / posterior_var may alias prior / prior_var.
+ * scratch: klerg_belief_scratch_bytes(G, n) bytes. */
+size_t klerg_belief_scratch_bytes(int64_t G, int32_t n);
+int klerg_belief_update(const double* grid, int64_t G, int32_t D, const double* locs, int32_t n, double scale,
+                        double meas_sum, const double* prior, const double* prior_var, double* posterior,
+                        double* posterior_var, void* scratch, void* stream);
+
 /* ---- target density of the VAE sensor model -------------- */
 
 /* VAE.pdf_torch (franka_test/scripts/vae/vae.py:244-275), the `target_dist`
