@@ -3,13 +3,17 @@
 // candidate; what changes is the organisation:
 //   A  rollouts: candidate b is rolled out by CTA b % grid only (not by every CTA); its scaled post-step states go to
 //      a small global table [B][H][D] that stays in L2.
-//   B  forward pair pass: for every group of 8 candidates a CTA stages the group's H*8 state rows in shared memory
-//      and sweeps its slice of the workspace samples (1e6 x D floats: L2-resident) against them; q_base + q_iter
-//      goes to HBM (it is needed again once the normaliser is known: storing 4 B per sample and candidate costs
-//      0.6 ms of HBM time per GB, recomputing it a second MUFU-bound pair pass), per-CTA {sum, max} per candidate
-//      to a partial table.
-//   C  every candidate's {sum, max} over all CTAs (candidate b by CTA b % grid, fixed order).
-//   D  KL terms of every candidate over the CTA's slice -> partial table;   E  candidate b's cost by CTA b % grid.
+//   B  forward pair pass.  The work is cut into units {group of 8 candidates} x {chunk of 4 samples per thread} and
+//      CTA k takes the k-th equal share of the unit list (group-major): it touches at most a few groups, stages a
+//      group's H*8 state rows once, and every thread runs the same number of full passes - no pass quantisation of a
+//      per-CTA sample slice (1e6 / 148 = 6757 samples = 3.3 passes of 512 threads) and one block reduction per
+//      touched group instead of one per group.  The workspace samples (1e6 x D floats) are read from L2.
+//      q_base + q_iter goes to HBM (it is needed again once the normaliser is known: storing 4 B per sample and
+//      candidate costs 0.6 ms of HBM time per GB, recomputing it a second MUFU-bound pair pass), per-CTA {sum, max}
+//      per candidate to a partial table.
+//   C  every candidate's {sum, max} over the CTAs that touched its group (candidate b by CTA b % grid, fixed order).
+//   D  KL terms over the CTA's sample slice, one candidate per WARP at a time (p and log p of the slice staged in
+//      shared memory; no block-wide barrier per group) -> partial table;   E  candidate b's cost by CTA b % grid.
 // Four grid-wide meetings in total (flag-free tagged exchanges, klerg_ll.cuh) instead of two per group of 8.
 #include "klerg_fused.cuh"
 
@@ -22,10 +26,11 @@ struct BatchArgs {
   double* part;   // [B][grid][2] {sum, max} of q_base + q_iter per CTA
   double* tot;    // [B][2]
   double* klp;    // [B][grid][2] KL terms per CTA
+  int kl_cap;     // samples of p / log p staged in shared memory for phase D (0: read p from global memory)
 };
 
 template <int D>
-__host__ __device__ inline SmemPlan plan_batch(int H, int S, int A, bool roll) {
+__host__ __device__ inline SmemPlan plan_batch(int H, int S, int A, bool roll, int kl_cap) {
   constexpr int G = FUSED_MAXG;
   SmemPlan p{};
   size_t o = 0;
@@ -37,18 +42,19 @@ __host__ __device__ inline SmemPlan plan_batch(int H, int S, int A, bool roll) {
   p.red = o;  o = align16(o + sizeof(double) * (32 * 2 * FUSED_MAXG + 4 * FUSED_MAXG));
   p.misc = o; o = align16(o + 64 + sizeof(float) * (FUSED_MAXG + KLERG_MAX_D));
   p.ll = o;   o = align16(o + LL_SCRATCH_BYTES);
+  p.xs = o;   o = align16(o + sizeof(float) * 2 * (size_t)kl_cap);
   p.total = o;
   return p;
 }
 
 template <int D>
-__global__ void __launch_bounds__(640) eval_cost_batch_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ BatchArgs b) {
+__global__ void __launch_bounds__(512) eval_cost_batch_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ BatchArgs b) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int G = FUSED_MAXG, DP = Row2<D>::DP, NF = RowX<D>::NF;
   const int H = a.H, S = a.d.S, A = a.d.A, B = b.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int vblk = blockIdx.x, vnblk = gridDim.x;
-  const SmemPlan sp = plan_batch<D>(H, S, A, a.d.kind == KLERG_DYN_ROLL);
+  const SmemPlan sp = plan_batch<D>(H, S, A, a.d.kind == KLERG_DYN_ROLL, b.kl_cap);
   float* s_u = (float*)(smem + sp.u);
   float* s_traj = (float*)(smem + sp.traj);
   u64* s_x2 = (u64*)(smem + sp.x2);
@@ -121,12 +127,16 @@ __global__ void __launch_bounds__(640) eval_cost_batch_kernel(const __grid_const
   }
   const bool xform_all = s_world[1] <= (double)a.k.x_r2;
 
-  // ---- B: forward pair pass, groups of G consecutive candidates -----------------------------------------------
-  int64_t lo, hi;
-  cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
-  const bool narrow = narrow_pairs(lo, hi);
-  for (int g0 = 0; g0 < B; g0 += G) {
-    const int ng = min(G, B - g0);
+  // ---- B: forward pair pass over this CTA's share of the {group, sample chunk} units ----------------------------
+  const bool narrow = a.N < (int64_t)4 * blockDim.x;                  // few samples: one packed pair per thread
+  const int64_t CH = (int64_t)blockDim.x * (narrow ? 2 : 4);          // samples per chunk: one pass of the CTA
+  const int64_t nch = (a.N + CH - 1) / CH;
+  const int64_t U = nch * ((B + G - 1) / G);
+  const int64_t u_lo = U * vblk / vnblk, u_hi = U * (vblk + 1) / vnblk;
+  for (int64_t u = u_lo; u < u_hi;) {
+    const int64_t grp = u / nch, c0 = u - grp * nch;
+    const int64_t c1 = min(nch, c0 + (u_hi - u));
+    const int g0 = (int)grp * G, ng = min(G, B - g0);
     for (int r = tid; r < ng * H; r += blockDim.x) {
       const float* row = b.xrows + ((size_t)g0 * H + r) * D;
       float x2n = 0.f;
@@ -147,6 +157,7 @@ __global__ void __launch_bounds__(640) eval_cost_batch_kernel(const __grid_const
     sr.x2 = s_x2; sr.rx = s_rx; sr.ctr = s_ctr;
     sr.xform = xform_all;
     __syncthreads();
+    const int64_t lo = c0 * CH, hi = min(c1 * CH, a.ld);
     if (narrow)
       forward_candidates<D, 1>(a, sr, ng, H, lo, hi, s_red, s_in, a.v + (size_t)g0 * a.ld);
     else
@@ -154,16 +165,21 @@ __global__ void __launch_bounds__(640) eval_cost_batch_kernel(const __grid_const
     __syncthreads();
     if (tid < 2 * ng) b.part[((size_t)(g0 + (tid >> 1)) * vnblk + vblk) * 2 + (tid & 1)] = s_in[tid];
     __syncthreads();
+    u += c1 - c0;
   }
   __threadfence();
   meet(0.0);
 
-  // ---- C: {sum, max} of every candidate over all CTAs (fixed order), candidate by warp --------------------------
+  // ---- C: {sum, max} of every candidate over the CTAs that touched its group (fixed order), candidate by warp ----
   for (int c = vblk + vnblk * warp; c < B; c += vnblk * nwarps) {
+    const int64_t g_lo = (int64_t)(c / G) * nch, g_hi = g_lo + nch;
     double sv = 0.0, mv = -INFINITY;
     for (int k = lane; k < vnblk; k += 32) {
-      sv += __ldcg(&b.part[((size_t)c * vnblk + k) * 2]);
-      mv = fmax(mv, __ldcg(&b.part[((size_t)c * vnblk + k) * 2 + 1]));
+      const int64_t k_lo = U * k / vnblk, k_hi = U * (k + 1) / vnblk;
+      if (k_lo < g_hi && k_hi > g_lo && k_hi > k_lo) {
+        sv += __ldcg(&b.part[((size_t)c * vnblk + k) * 2]);
+        mv = fmax(mv, __ldcg(&b.part[((size_t)c * vnblk + k) * 2 + 1]));
+      }
     }
     sv = warp_reduce(RED_SUM, sv);
     mv = warp_reduce(RED_MAX, mv);
@@ -179,23 +195,66 @@ __global__ void __launch_bounds__(640) eval_cost_batch_kernel(const __grid_const
   __threadfence();
   meet(0.0);
 
-  // ---- D: KL terms over this CTA's slice --------------------------------------------------------------------------
-  for (int g0 = 0; g0 < B; g0 += G) {
-    const int ng = min(G, B - g0);
-    if (tid < 2 * ng) s_world[tid] = __ldcg(&b.tot[2 * g0 + tid]);
-    __syncthreads();
-    double sa[FUSED_MAXG], sc[FUSED_MAXG];
-    kl_pass(a, ng, a.v + (size_t)g0 * a.ld, s_world, lo, hi, sa, sc);
-    block_reduce_pairs(ng, RED_SUM, sa, sc, s_red);
-    if (tid == 0) {
-#pragma unroll
-      for (int g = 0; g < FUSED_MAXG; ++g)
-        if (g < ng) {
-          b.klp[((size_t)(g0 + g) * vnblk + vblk) * 2] = sa[g];
-          b.klp[((size_t)(g0 + g) * vnblk + vblk) * 2 + 1] = sc[g];
-        }
+  // ---- D: KL terms over this CTA's sample slice, one candidate per warp at a time --------------------------------
+  {
+    int64_t lo, hi;
+    cta_slice(a.N, a.ld, vblk, vnblk, lo, hi);
+    const int n = (int)max((int64_t)0, min(hi, a.N) - lo);
+    const bool staged = n <= b.kl_cap;
+    float* s_p = (float*)(smem + sp.xs);
+    float* s_lp = s_p + b.kl_cap;
+    if (staged) {
+      for (int i = tid; i < ((n + 3) & ~3); i += blockDim.x) {
+        float pv = i < n ? __ldg(a.p + lo + i) : 1.f;
+        if (pv != pv) pv = 1e-6f;
+        s_p[i] = pv;
+        s_lp[i] = __logf(pv);
+      }
     }
     __syncthreads();
+    for (int c = warp; c < B; c += nwarps) {
+      const float vs = (float)__ldcg(&b.tot[2 * c]);
+      const float rvs = 1.f / vs;
+      const float maxc = fmaxf((float)__ldcg(&b.tot[2 * c + 1]) / vs, a.floor);
+      const float* vrow = a.v + (size_t)c * a.ld + lo;
+      double da = 0.0, dc = 0.0;
+#pragma unroll 4
+      for (int i0 = lane * 4; i0 < n; i0 += 128) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(vrow + i0));
+        const float vv[4] = {t.x, t.y, t.z, t.w};
+        float pv[4], lp[4];
+        if (staged) {
+          const float4 tp = *reinterpret_cast<const float4*>(s_p + i0), tl = *reinterpret_cast<const float4*>(s_lp + i0);
+          pv[0] = tp.x; pv[1] = tp.y; pv[2] = tp.z; pv[3] = tp.w;
+          lp[0] = tl.x; lp[1] = tl.y; lp[2] = tl.z; lp[3] = tl.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            pv[q] = (i0 + q < n) ? __ldg(a.p + lo + i0 + q) : 1.f;
+            if (pv[q] != pv[q]) pv[q] = 1e-6f;
+            lp[q] = __logf(pv[q]);
+          }
+        }
+        float fa = 0.f, fc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (i0 + q < n) {
+            float cq = fmaxf(vv[q] * rvs, a.floor);
+            if (cq != cq) cq = 1e-6f * maxc;  // cost_norm: NaN in q -> 1e-6 (q = c / max c)
+            fa = fmaf(pv[q], lp[q] - __logf(cq), fa);
+            fc += cq;
+          }
+        }
+        da += (double)fa;
+        dc += (double)fc;
+      }
+      da = warp_reduce(RED_SUM, da);
+      dc = warp_reduce(RED_SUM, dc);
+      if (lane == 0) {
+        b.klp[((size_t)c * vnblk + vblk) * 2] = da;
+        b.klp[((size_t)c * vnblk + vblk) * 2 + 1] = dc;
+      }
+    }
   }
   __threadfence();
   meet(0.0);
@@ -224,26 +283,19 @@ __global__ void __launch_bounds__(640) eval_cost_batch_kernel(const __grid_const
 }
 
 template <int D>
-static int launch_batch_d(EvalArgs& a, const BatchArgs& b, cudaStream_t stream) {
+static int launch_batch_d(EvalArgs& a, BatchArgs& b, cudaStream_t stream) {
   auto kernel = eval_cost_batch_kernel<D>;
-  const SmemPlan sp = plan_batch<D>(a.H, a.d.S, a.d.A, a.d.kind == KLERG_DYN_ROLL);
-  if (sp.total > 200 * 1024) { set_error("eval_costs_batch: horizon too long for shared-memory staging"); return -1; }
   int64_t want = (a.N + 255) / 256;
   int nblk = want < sm_count() ? (int)want : sm_count();
   if (nblk > LL_MAXBLK) nblk = LL_MAXBLK;
   if (g_fused_opt.grid_limit > 0 && nblk > g_fused_opt.grid_limit) nblk = g_fused_opt.grid_limit;
   if (nblk < 1) nblk = 1;
-  // Threads per CTA: a thread sweeps 4 samples per pass over the candidates, so a slice of `per` samples costs
-  // ceil(per / (4 threads)) passes - pick the thread count that wastes the fewest thread-passes (e.g. 1e6 samples on
-  // 148 CTAs: 6757 per CTA = 3.3 passes of 512 threads, but 2.93 -> 3 passes of 576 threads)
-  const int64_t per = ((a.N + nblk - 1) / nblk + 7) & ~(int64_t)7;
-  int nthreads = 512;
-  double best = 1e300;
-  for (int nt = 384; nt <= 640; nt += 32) {
-    const int64_t passes = (per + 4 * nt - 1) / (4 * nt);
-    const double cost = (double)passes * nt / (nt >= 512 ? 1.0 : 0.97);  // fewer warps hide a little less latency
-    if (cost < best - 1e-9) { best = cost; nthreads = nt; }
-  }
+  // 16 warps: four per scheduler (18 or 20 would leave schedulers unevenly loaded or spill registers)
+  const int nthreads = 512;
+  const int64_t per = ((a.N + nblk - 1) / nblk + 7) & ~(int64_t)7;  // cta_slice
+  b.kl_cap = per <= 16384 ? (int)per : 0;
+  const SmemPlan sp = plan_batch<D>(a.H, a.d.S, a.d.A, a.d.kind == KLERG_DYN_ROLL, b.kl_cap);
+  if (sp.total > 200 * 1024) { set_error("eval_costs_batch: horizon too long for shared-memory staging"); return -1; }
   if (resident_ctas(kernel, nthreads, sp.total) < 1) { set_error("eval_costs_batch: kernel does not fit on an SM"); return -4; }
   return fused_launch(kernel, nblk, nthreads, sp.total, stream, "eval_cost_batch_kernel", false, a, b);
 }
