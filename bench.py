@@ -538,11 +538,38 @@ def cuda_arm(args):
                 fn()
             return time_events(fn, reps) * 1e-3
 
+        def robot_step_ms(name, steps=40):
+            """Robot.step() at the workload's own N and M through the public API (wall clock, one D2H per step)."""
+            w_ = wl.WORKLOADS[name]
+            tgt = wl.make_target(w_["target"], [wl.LIMS[s] for s in w_["states"]], seed=1, device=dev)
+            torch.manual_seed(7)
+            rb = Robot(process_group=None, **wl.robot_kwargs(name, tgt))
+            rb.test(1000)
+            for row in wl.random_walk_history(name, w_["M"], seed=5):
+                rb.memory_buffer.push(row)
+            for _ in range(5):
+                rb.step(w_["N"], w_["M"], save_update=True)
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            for _ in range(steps):
+                rb.step(w_["N"], w_["M"], save_update=True)
+            torch.cuda.synchronize()
+            out = {"ms_per_robot_step": (time.perf_counter() - t0_) / steps * 1e3, "robot_steps_timed": steps,
+                   "planner_loop": "device (klerg_plan_optimize)" if rb.device_loop else "host"}
+            if not args.no_cpu:
+                ro = run_oracle_steps(name, w_["N"], w_["M"], 2, 1)
+                out["cpu_oracle_ms_per_robot_step"] = ro["seconds"] / ro["steps"] * 1e3
+                out["cpu_oracle_cores"] = ro["cores"]
+            return out
+
         S1 = build_sets("c1", wl.WORKLOADS["c1"]["N"], rank, group, dev, engine, Robot, PlannerContext, max_sets=8)
         r1 = timed_evals(args, S1, 2000, 20, world, rank, lib, dev)
         also["c1"] = {"workload": workload_config("c1", wl.WORKLOADS["c1"]["N"], S1["n"])["workload"],
                       "us_per_eval": r1["ms_total"] / 2000 * 1e3, "evals_per_s": 2000 / (r1["ms_total"] * 1e-3)}
         del S1
+        also["c1"].update(robot_step_ms("c1"))
+        if "c2" in also:
+            also["c2"].update(robot_step_ms("c2"))
         S3 = build_sets("c3", wl.WORKLOADS["c3"]["N"], rank, group, dev, engine, Robot, PlannerContext, max_sets=2)
         c3 = S3["sets"][0]
         c3.buf.v_costs = torch.empty((c3.buf.max_g, c3.buf.ld), dtype=torch.float32, device=dev)

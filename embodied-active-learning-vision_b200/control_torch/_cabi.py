@@ -131,6 +131,10 @@ SIGNATURES = {
                               C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_eval_costs_batch_scratch_bytes": [_I64, _I64, _I32],
     "klerg_eval_costs_batch": [_KS, _DS, _BS, _P, _P, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "klerg_plan_scratch_bytes": [_I64, _I32, _I32, _I64],
+    "klerg_plan_result_floats": [_I64, _I32, _I32],
+    "klerg_plan_optimize": [_KS, _DS, _BS, _PS, _P, _P, _P, _I64, _P, _I64, _I64, _P, _P, _P, _F, _FP, _F, _FP, _FP,
+                            _I32, _I32, _I32, _I32, _P, _P, _P, _P],
     "klerg_belief_scratch_bytes": [_I64, _I32],
     "klerg_belief_update": [_P, _I64, _I32, _P, _I32, C.c_double, C.c_double, _P, _P, _P, _P, _P, _P],
     "klerg_mt19937_uniform": [_P, _I32, _I32, _I64, _I32, _FP, _FP, _I64, _I64, _P, _P, _P],
@@ -159,7 +163,8 @@ SIGNATURES = {
                          _P, _P, _P],
 }
 _RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_kl_gradient_targets_scratch_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_debug_cta_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
-             "klerg_launch_count": C.c_longlong, "klerg_eval_costs_batch_scratch_bytes": C.c_size_t, "klerg_belief_scratch_bytes": C.c_size_t}
+             "klerg_launch_count": C.c_longlong, "klerg_eval_costs_batch_scratch_bytes": C.c_size_t, "klerg_belief_scratch_bytes": C.c_size_t, "klerg_plan_scratch_bytes": C.c_size_t,
+             "klerg_plan_result_floats": C.c_int64}
 
 
 def load():

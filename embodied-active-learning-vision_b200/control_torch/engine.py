@@ -522,6 +522,25 @@ def eval_costs(spec, dyn, bar, peers, x0, R0, U, packed, n, q_base, p, p_stats, 
     return cost
 
 
+def plan_optimize(spec, dyn, bar, peers, x0, R0, u, packed, n, q_base, p, p_stats, rinv, alpha, ctrl_lo, ctrl_hi, num_iters,
+                  fixed_lam, lam, buf, floor=FLOOR, max_app_dur=5):
+    """The planner's optimisation loop enqueued at once and decided on the device (klerg_plan_optimize).  ``u`` [H,A]
+    (device) is updated in place; returns the packed result on the device (one D2H for the caller):
+    {last_cost, fault, cost evals, gradient evals, accepted iterations, 0, 0, 0, u[H*A], traj[(H+1)*S]}."""
+    lib = cabi.load()
+    H, A, S = u.shape[-2], dyn.A, dyn.S
+    ld = packed.shape[1]
+    if getattr(buf, "plan_scratch", None) is None:
+        buf.plan_scratch = torch.empty(lib.klerg_plan_scratch_bytes(H, S, A, ld), dtype=torch.uint8, device=u.device)
+        buf.plan_result = torch.zeros(lib.klerg_plan_result_floats(H, S, A), dtype=torch.float32, device=u.device)
+    cabi.check(lib.klerg_plan_optimize(
+        C.byref(spec), C.byref(dyn), C.byref(bar) if bar is not None else None, peers, cabi.ptr(x0), cabi.ptr(R0),
+        cabi.ptr(u), H, cabi.ptr(packed), int(n), ld, cabi.ptr(q_base), cabi.ptr(p), cabi.ptr(p_stats), float(floor), rinv,
+        float(alpha), ctrl_lo, ctrl_hi, int(num_iters), int(bool(fixed_lam)), int(lam), int(max_app_dur),
+        cabi.ptr(buf.plan_scratch), cabi.ptr(buf.plan_result), workspace(8), cabi.stream_ptr()), "klerg_plan_optimize")
+    return buf.plan_result
+
+
 def eval_costs_batch(spec, dyn, bar, x0, R0, U, packed, n, q_base, p, p_stats, floor=FLOOR):
     """ONE launch: get_cost of any number of candidates U [B,H,A] -> cost [B] (klerg_eval_costs_batch; single GPU)."""
     lib = cabi.load()

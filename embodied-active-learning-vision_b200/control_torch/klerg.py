@@ -487,6 +487,9 @@ class Robot(object):
                                                 uniform=self.uniform_tdist, spread=spread)
             ctx.set_target(p, p_stats)
 
+            if self.device_loop and ctx.fused and self.plot_data is None:
+                self._optimize_on_device(ctx)
+                return
             last_cost = self._costs(ctx, self.u.unsqueeze(0))[0]
             accepted = None  # forward output (v, totals) of the last gradient eval, for plot_data
             prev_accepted = None
@@ -544,6 +547,29 @@ class Robot(object):
             wrapped = getattr(self, "_wrapped_target", None)
             if wrapped is not None:
                 wrapped.check_fault()  # a timed-out wait inside the decoder kernel must not pass silently
+
+    device_loop = True  # run the optimisation loop on the device (one D2H per step) unless plot data is kept
+
+    def _optimize_on_device(self, ctx):
+        """Iterations, line searches and accept rules of klerg.py:505-576 decided on the device (klerg_plan_optimize):
+        the same evals in the same order as the host loop below, one packed read-back instead of two per iteration."""
+        H, A = self.horizon, self.planner.num_actions
+        u_dev = self.u.to(self.cuda, non_blocking=True).reshape(H, A).contiguous()
+        pack = ctx.optimize(u_dev, self.num_iters_per_step, self.fixed_lam, getattr(self, "lam", 1)).cpu()
+        if pack[1] != 0:
+            raise RuntimeError("klerg_plan_optimize: an in-kernel wait timed out (lost peer or a launch that was not "
+                               "co-resident); the plan of this step is void")
+        self.last_cost = pack[0].clone()
+        self.stats["cost_evals"] += int(pack[2])
+        self.stats["grad_evals"] += int(pack[3])
+        ctx.evals["cost"] += int(pack[2])
+        ctx.evals["grad"] += int(pack[3])
+        self.u = pack[8:8 + H * A].view(H, A).clone()
+        self.last_plan = pack[8 + H * A:].view(H + 1, -1).clone()
+        self.stats["steps"] += 1
+        wrapped = getattr(self, "_wrapped_target", None)
+        if wrapped is not None:
+            wrapped.check_fault()
 
     # ------------------------------------------------------------------ plots (klerg.py:602-682)
     @torch.no_grad()

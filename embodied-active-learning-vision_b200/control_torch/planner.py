@@ -161,6 +161,15 @@ class PlannerContext:
             out.update(v=v[0], totals=totals_w)
         return out
 
+    def optimize(self, u, num_iters, fixed_lam=False, lam=1):
+        """The whole optimisation loop of kldiv_planner (klerg.py:505-576) without host round trips: ``u`` [H,A] on the
+        device is replaced by the optimised plan; returns the packed result (device) - see engine.plan_optimize."""
+        if not self.fused:
+            raise RuntimeError("the device-resident planner loop needs the fused evals")
+        return engine.plan_optimize(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, u, self.packed, self.n,
+                                    self.q_base, self.p, self.p_stats, self._rinv_c, self.alpha, self._lo_c, self._hi_c,
+                                    num_iters, fixed_lam, lam, self.buf, self.floor)
+
     # -- K belief targets over one workspace (fingerprint test mode, BASELINE config 5) ------------------
     def set_targets(self, P, P_stats):
         """P [K, n_local] target densities p_k on the device, P_stats [K, 1] = their global sums."""

@@ -94,6 +94,12 @@ class DeviceTarget:
         if l2.in_features != h1 or l3.in_features != h2 or l3.out_features < nl or sd < 1:
             raise NotImplementedError("target decoder: inconsistent layer shapes")
         dims = (sd, zd, nz, h1, h2, nl)
+        parts = [l1.weight, l1.bias, z, l2.weight, l2.bias, l3.weight[:nl], l3.bias[:nl]]
+        # Unchanged weights are not packed again: a tensor's version counter moves with every in-place update (an
+        # optimiser step), its storage pointer with every replacement.
+        key = (dims,) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in parts)
+        if self._packed is not None and key == getattr(self, "_pack_key", None):
+            return
         nbytes = lib.klerg_target_decoder_packed_bytes(*dims)
         if nbytes == 0:
             cabi.check(-1, "klerg_target_decoder_packed_bytes")
@@ -102,7 +108,6 @@ class DeviceTarget:
         base = self._packed.data_ptr()
         self._packed_ptr = (base + 127) // 128 * 128
         # one flat H2D copy of everything the pack kernel reads
-        parts = [l1.weight, l1.bias, z, l2.weight, l2.bias, l3.weight[:nl], l3.bias[:nl]]
         flat = torch.cat([p.detach().to(torch.float32).reshape(-1).cpu() for p in parts])
         dev = flat.to(self.cuda, non_blocking=True)
         offs, o = [], 0
@@ -114,6 +119,7 @@ class DeviceTarget:
                    "klerg_target_decoder_pack")
         self._staging = dev  # keep alive until the stream has consumed it
         self._dims = dims
+        self._pack_key = key
         self.stats["packs"] += 1
 
     # ------------------------------------------------------------------ density

@@ -21,6 +21,8 @@ extern template int launch_cost_d<4>(EvalArgs&, int64_t, cudaStream_t);
 extern template int launch_cost_d<5>(EvalArgs&, int64_t, cudaStream_t);
 extern template int launch_cost_d<6>(EvalArgs&, int64_t, cudaStream_t);
 
+const int* g_eval_gate = nullptr;
+
 static bool fill_common(EvalArgs& a, const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
                         const klerg_peers* peers) {
   if (!make_kernel_dev(k, a.k) || !make_dyn(dyn, a.d) || !make_bar(bar, a.bar)) return false;
@@ -134,7 +136,8 @@ extern "C" size_t klerg_debug_cta_stamps_offset(void) { return HEAD_COUNTERS + H
 // single GPU: the mailbox is the region of the workspace reserved for it
 static void finish_peers(EvalArgs& a, void* workspace) {
   if (a.peers.world <= 1) a.peers.mail[0] = ws_fused_mailbox(workspace);
-  a.independent = g_fused_opt.overlap;
+  a.gate = g_eval_gate;
+  a.independent = g_eval_gate ? 0 : g_fused_opt.overlap;
 }
 
 extern "C" int klerg_eval_gradient_targets(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn,

@@ -102,6 +102,10 @@ struct EvalArgs {
   AdjParams ap;
   Peers peers;
   int independent;       // 1: inputs do not depend on the previous launch in the stream (no griddepcontrol.wait)
+  // Device-side gate (klerg_plan_optimize): a word written by an earlier kernel of the stream.  Cost eval: the number
+  // of candidates actually evaluated (<= G; 0: the launch does nothing); gradient eval: 0 = the launch does nothing.
+  // The same value on every rank, so a skipped launch is skipped everywhere (no exchange is left half-done).
+  const int* gate;
   // inputs
   const float* x0;       // [S]
   const float* R0;       // [9] or NULL
@@ -133,6 +137,8 @@ struct EvalArgs {
   float* fault_out;      // [1] or NULL: 0 / 1 copy of the sticky fault word next to the outputs the host reads
   double* kl_out;        // [2] {sum p(log p - log c), sum c} over all ranks, or NULL
 };
+
+extern const int* g_eval_gate;  // EvalArgs::gate of the evals launched while it is set (klerg_plan.cu)
 
 // process-wide switches of the fused evals (klerg_set_option)
 struct FusedOptions {
@@ -566,6 +572,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (!a.independent) pdl_wait_prior_grids();  // the previous launch may have produced this one's inputs
+  if (a.gate && __ldcg(a.gate) <= 0) return;
   if (tid == 0) {
     s_epoch[0] = ld_acquire_u32(mb_hdr(me));      // launches so far on this mailbox
     s_epoch[1] = ld_acquire_u32(mb_hdr(me) + 1);  // gather exchanges so far
@@ -1155,8 +1162,15 @@ __host__ __device__ inline SmemPlan plan_cost(int G, int H, int S, int A, bool r
 
 template <int D>
 __device__ __forceinline__ void eval_cost_body(const EvalArgs& a, const int vblk, const int vnblk, unsigned char* smem) {
-  const int H = a.H, S = a.d.S, A = a.d.A, G = a.G;
+  const int H = a.H, S = a.d.S, A = a.d.A;
   const int tid = threadIdx.x;
+  int G = a.G;
+  if (a.gate) {
+    pdl_wait_prior_grids();
+    const int g = __ldcg(a.gate);
+    if (g <= 0) return;
+    if (g < G) G = g;
+  }
   const SmemPlan sp = plan_cost<D>(G, H, S, A, a.d.kind == KLERG_DYN_ROLL);
   float* s_u = (float*)(smem + sp.u);
   float* s_traj = (float*)(smem + sp.traj);

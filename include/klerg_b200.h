@@ -323,6 +323,25 @@ int klerg_eval_costs(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, cons
                      const double* p_stats, float floor, float* v_scratch, float* traj, double* totals,
                      float* cost, float* fault_out, void* workspace, void* stream);
 
+/* The optimisation loop of Robot.kldiv_planner (klerg.py:505-576) with its line search (klerg.py:712-751), enqueued
+ * at once and decided on the device:  cost(u) | { gradient(u) -> argmin djdlam, line-search windows -> costs of the
+ * candidates -> accept rules } x num_iters | nan_to_num(u), rollout(u).  The evals are the launches above, gated by
+ * a device-side loop state: after the reference's `break` the remaining ones return immediately, and a cost launch
+ * evaluates exactly the candidates the host loop would pass.  Same float32 comparisons in the same order as the host
+ * code.  u[H][A] (device) is the current plan on entry and the optimised plan on return.  fixed_lam != 0: the
+ * window [t_app, t_app + lam) instead of the line search.  max_app_dur: 5 in the reference (klerg.py:712).
+ * result (device, klerg_plan_result_floats(H, S, A) floats, the ONE buffer the host reads back):
+ *   {last_cost, fault, cost evals, gradient evals, accepted iterations, 0, 0, 0, u[H][A], traj[H+1][S] of rollout(u)}.
+ * scratch: klerg_plan_scratch_bytes(H, S, A, ld) bytes (device). */
+size_t klerg_plan_scratch_bytes(int64_t H, int32_t S, int32_t A, int64_t ld);
+int64_t klerg_plan_result_floats(int64_t H, int32_t S, int32_t A);
+int klerg_plan_optimize(const klerg_kernel_spec* k, const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar,
+                        const klerg_peers* peers, const float* x0, const float* R0, float* u, int64_t H,
+                        const float* packed, int64_t N, int64_t ld, const float* q_base, const float* p,
+                        const double* p_stats, float floor, const float* Rinv_diag, float alpha, const float* ctrl_lo,
+                        const float* ctrl_hi, int32_t num_iters, int32_t fixed_lam, int32_t lam, int32_t max_app_dur,
+                        void* scratch, float* result, void* workspace, void* stream);
+
 /* The same for ANY number of candidates B (BASELINE config 3: 1024 candidates x horizon 50 x 1e6 samples) in ONE launch:
  * rollouts spread over the grid, forward pair pass per group of 8 candidates over L2-resident samples, one grid-wide
  * meeting for all candidates' normalisers, KL pass, costs.  Single GPU.  v_scratch: B*ld floats; scratch:

@@ -74,6 +74,16 @@ def test_weights_are_reread_every_call(td):
     dev.check_fault()
     assert not torch.allclose(p0, p1)
     np.testing.assert_allclose(p1.numpy(), model.pdf_torch(s).numpy(), rtol=RTOL, atol=0)
+    # unchanged weights are not packed again (version counters / storage pointers), a replaced parameter is
+    packs = dev.stats["packs"]
+    p2 = dev.pdf_torch(s).cpu()
+    assert dev.stats["packs"] == packs and torch.equal(p1, p2)
+    with torch.no_grad():
+        model.decode[0].bias = torch.nn.Parameter(model.decode[0].bias.detach() + 0.05)
+        model.weights[0] = (model.weights[0][0], model.decode[0].bias.detach().clone())
+    p3 = dev.pdf_torch(s).cpu()
+    assert dev.stats["packs"] == packs + 1 and not torch.allclose(p2, p3)
+    np.testing.assert_allclose(p3.numpy(), model.pdf_torch(s).numpy(), rtol=RTOL, atol=0)
 
 
 def test_unsupported_decoder_raises(td):
