@@ -8,6 +8,7 @@ with one small all-gather per phase and combined in rank order on the device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -181,6 +182,23 @@ def emulated_pair(call_rank0, call_rank1, grid_limit=64):
 
 _peer_cache = {}
 SINGLE = ShardGroup()
+
+
+class nvtx_range:
+    """NVTX range around a phase of Robot.step() (visible in nsys / ncu --nvtx timelines).  KLERG_NVTX=0 turns them off."""
+    enabled = os.environ.get("KLERG_NVTX", "1") != "0"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx_range.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if nvtx_range.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def set_eval_overlap(on):
@@ -565,11 +583,24 @@ def debug_stamps():
     return ws.buf[off:off + 144].view(torch.int64).cpu().tolist()
 
 
-def debug_cta_stamps():
-    """[160, 8] globaltimer stamps (ns) per CTA of the last fused gradient eval (KLERG_STAMPS builds, single GPU)."""
+def debug_cta_stamps(peers=None):
+    """[160, 8] globaltimer stamps (ns) per CTA of the last fused gradient eval (KLERG_STAMPS builds).  ``peers``: the
+    klerg_peers of a sharded context - the stamps then live in this rank's NVLink mailbox, not in the workspace."""
+    lib = cabi.load()
+    if peers is not None:
+        import numpy as np
+        from cuda import cudart
+        mb_off = lib.klerg_debug_cta_stamps_offset() - (lib.klerg_fused_fault_offset() - 20) - 256  # MB_OFF_DBG
+        host = np.zeros(160 * 8, dtype=np.int64)
+        torch.cuda.synchronize()
+        (err,) = cudart.cudaMemcpy(host.ctypes.data, int(peers.mailbox[peers.rank]) + mb_off, host.nbytes,
+                                   cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaMemcpy of the CTA stamps failed: {err}")
+        return torch.from_numpy(host).view(160, 8)
     key = (torch.cuda.current_device(), cabi.raw_stream())
     ws = _workspaces[key]
-    off = cabi.load().klerg_debug_cta_stamps_offset()
+    off = lib.klerg_debug_cta_stamps_offset()
     return ws.buf[off:off + 160 * 64].view(torch.int64).view(160, 8).cpu()
 
 

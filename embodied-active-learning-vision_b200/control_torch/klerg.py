@@ -462,7 +462,8 @@ class Robot(object):
         return c
 
     def kldiv_planner(self, num_target_samples, num_traj_samples, temp=1.0):
-        samples, hist_dev, nu = self.get_samples(num_target_samples, num_traj_samples)
+        with engine.nvtx_range("klerg.get_samples"):
+            samples, hist_dev, nu = self.get_samples(num_target_samples, num_traj_samples)
         with torch.no_grad():
             H = self.horizon
             prev = getattr(self, "ctx", None)
@@ -473,22 +474,26 @@ class Robot(object):
                 samples_dev = samples.local
             else:
                 samples_dev = self._shard(samples).to(self.cuda, non_blocking=True).contiguous()
-            ctx.set_samples(samples_dev, self.std.tolist(), 1.0, n_total=samples.shape[0])
-            ctx.set_state(self.robot.state.to(self.cuda, non_blocking=True))
+            with engine.nvtx_range("klerg.pack_samples"):
+                ctx.set_samples(samples_dev, self.std.tolist(), 1.0, n_total=samples.shape[0])
+                ctx.set_state(self.robot.state.to(self.cuda, non_blocking=True))
             spread = None
-            if self._fused_history_ok(hist_dev):
-                # the spread of get_target_dist (all buffer rows, klerg.py:470-475) and the history footprint q_base
-                # (the drawn rows, klerg.py:496) visit the same rows: ONE pass over the squared distances
-                rows, t_sum = self.memory_buffer.partition_device(self.last_hist_idx)
-                ctx.q_base, spread, _ = engine.footprint_sum_max(ctx.spec, rows, t_sum, ctx.packed, ctx.n)
-            else:
-                ctx.set_history(hist_dev)
-            p, p_stats = self._target_on_device(samples, samples_dev, dict(packed_std=ctx.packed), temp,
-                                                uniform=self.uniform_tdist, spread=spread)
-            ctx.set_target(p, p_stats)
+            with engine.nvtx_range("klerg.history_footprint"):
+                if self._fused_history_ok(hist_dev):
+                    # the spread of get_target_dist (all buffer rows, klerg.py:470-475) and the history footprint q_base
+                    # (the drawn rows, klerg.py:496) visit the same rows: ONE pass over the squared distances
+                    rows, t_sum = self.memory_buffer.partition_device(self.last_hist_idx)
+                    ctx.q_base, spread, _ = engine.footprint_sum_max(ctx.spec, rows, t_sum, ctx.packed, ctx.n)
+                else:
+                    ctx.set_history(hist_dev)
+            with engine.nvtx_range("klerg.target_density"):
+                p, p_stats = self._target_on_device(samples, samples_dev, dict(packed_std=ctx.packed), temp,
+                                                    uniform=self.uniform_tdist, spread=spread)
+                ctx.set_target(p, p_stats)
 
             if self.device_loop and ctx.fused and self.plot_data is None:
-                self._optimize_on_device(ctx)
+                with engine.nvtx_range("klerg.plan_optimize"):
+                    self._optimize_on_device(ctx)
                 return
             last_cost = self._costs(ctx, self.u.unsqueeze(0))[0]
             accepted = None  # forward output (v, totals) of the last gradient eval, for plot_data
