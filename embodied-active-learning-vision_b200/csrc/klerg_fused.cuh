@@ -1321,6 +1321,17 @@ static GradSchedule plan_schedule(int D, int H) {
       return m;
     }
   }
+  if (D >= 5 && g_fused_opt.mixed_warps == 16) {
+    // balanced schedule on 16 warps: every warp owns q states, the r <= 2 states that remain are shared (each warp
+    // takes them on its own 1/16 of a tile's samples) - no warp with one state more that the others wait for at
+    // every tile barrier
+    const int nw = 16, q = H / nw, r = H % nw;
+    if (q == 3 && r >= 1 && r <= 2) {
+      GradSchedule m{};
+      m.wt = q; m.nwarps = nw; m.nchr = nw; m.nsub = 1; m.rounds = 1; m.eff = 1.0; m.mixed = true; m.nwide = 0; m.left = r;
+      return m;
+    }
+  }
   if (D >= 4) {
     // mixed schedule: 16 warps (4 per SM sub-partition, 128 registers), H = q*16 + r -> r warps own q+1 states.
     // Needs q >= 2 (fewer states per warp would re-read the staged samples too often for the shared-memory bandwidth).
@@ -1328,6 +1339,13 @@ static GradSchedule plan_schedule(int D, int H) {
     if (q >= 2 && r > 0 && q + 1 <= wtmax) {
       GradSchedule m{};
       m.wt = q; m.nwarps = nw; m.nchr = nw; m.nsub = 1; m.rounds = 1; m.eff = 1.0; m.mixed = true; m.nwide = r;
+      return m;
+    }
+    if (r == 0 && q >= 3 && q <= wtmax) {
+      // H a multiple of 16: every warp is a "wide" warp of the (q - 1)-state kernel (the same 512-thread, 128-register
+      // kernel; the generic schedule below would take the 17-warp kernel with 96 registers)
+      GradSchedule m{};
+      m.wt = q - 1; m.nwarps = nw; m.nchr = nw; m.nsub = 1; m.rounds = 1; m.eff = 1.0; m.mixed = true; m.nwide = nw;
       return m;
     }
   }
@@ -1523,6 +1541,7 @@ int launch_grad_d(EvalArgs& a, int64_t n_max, cudaStream_t stream) {
     if (s.mixed) {
       if constexpr (D >= 5) {
         if (s.nwarps == 12 && s.wt == 4) return launch_grad_wt<D, 4, 12, 2>(a, s, n_max, stream);
+        if (s.nwarps == 16 && s.wt == 3 && s.left > 0) return launch_grad_wt<D, 3, 16, 2>(a, s, n_max, stream);
       }
       if (s.wt == 2) return launch_grad_wt<D, 2, 16>(a, s, n_max, stream);
       if (s.wt == 3) return launch_grad_wt<D, 3, 16>(a, s, n_max, stream);

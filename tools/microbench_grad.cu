@@ -47,6 +47,65 @@ __global__ void __launch_bounds__(256) probe(int iters, const float* __restrict_
   if (s == 123.456f) out[0] = s;
 }
 
+// experimental variants of pair_gradient_x (klerg_pair.cuh):
+//   SC = 1: the accumulations A += (w psi) sc as scalar FFMAs   SC = 2: the dot products too
+//   FOLD:   the importance weight folded into the exponent (s2n holds |sc|^2 - log2 w): no multiply, no w operand
+template <int D, int WT, int SC, bool FOLD>
+__device__ __forceinline__ void pair_gradient_var(const float (&m2x)[WT][D], const float (&x2n)[WT], const u64 (&sc)[D], u64 s2n,
+                                                  u64 w2, u64 (&A)[WT][D], u64 (&W)[WT]) {
+  float sc0[D], sc1[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) unpack2(sc[d], sc0[d], sc1[d]);
+  float e0[WT], e1[WT];
+  if (SC == 2) {
+    float n0, n1;
+    unpack2(s2n, n0, n1);
+#pragma unroll
+    for (int k = 0; k < WT; ++k) { e0[k] = n0 + x2n[k]; e1[k] = n1 + x2n[k]; }
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int k = 0; k < WT; ++k) { e0[k] = fmaf(m2x[k][d], sc0[d], e0[k]); e1[k] = fmaf(m2x[k][d], sc1[d], e1[k]); }
+  } else {
+    u64 e[WT];
+#pragma unroll
+    for (int k = 0; k < WT; ++k) e[k] = add2(s2n, pack2(x2n[k], x2n[k]));
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+#pragma unroll
+      for (int k = 0; k < WT; ++k) e[k] = fma2(pack2(m2x[k][d], m2x[k][d]), sc[d], e[k]);
+#pragma unroll
+    for (int k = 0; k < WT; ++k) unpack2(e[k], e0[k], e1[k]);
+  }
+  float p0[WT], p1[WT];
+  float w0, w1;
+  unpack2(w2, w0, w1);
+#pragma unroll
+  for (int k = 0; k < WT; ++k) {
+    p0[k] = ex2_neg(e0[k]);
+    p1[k] = ex2_neg(e1[k]);
+    if (!FOLD) { p0[k] *= w0; p1[k] *= w1; }
+  }
+#pragma unroll
+  for (int k = 0; k < WT; ++k) {
+    if (SC >= 1) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float a0, a1;
+        unpack2(A[k][d], a0, a1);
+        a0 = fmaf(p0[k], sc0[d], a0);
+        a1 = fmaf(p1[k], sc1[d], a1);
+        A[k][d] = pack2(a0, a1);
+      }
+    } else {
+      const u64 wp = pack2(p0[k], p1[k]);
+#pragma unroll
+      for (int d = 0; d < D; ++d) A[k][d] = fma2(wp, sc[d], A[k][d]);
+    }
+    W[k] = add2(W[k], pack2(p0[k], p1[k]));
+  }
+}
+
 // gradient loop: NW warps, each owns WT states; sweeps `tiles` tiles of TS samples held in shared memory
 // FORM 0: difference form (pair_gradient)   1: expanded form (pair_gradient_x, interleaved)
 // FORM 2: expanded form, samples NOT reloaded from shared memory (register operands)   3: expanded, no MUFU
@@ -92,6 +151,11 @@ __global__ void __launch_bounds__(NT) grad_loop(int tiles, const float* __restri
         const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
         if (FORM == 0) {
           pair_gradient<D, WT>(xs2, s2, w2, acc, true);
+        } else if (FORM >= 4) {
+          const u64 n2 = *reinterpret_cast<const u64*>(&nrow[i]);
+          // 4: scalar accumulations  5: all scalar  6: packed, w folded  7: scalar accumulations, w folded
+          pair_gradient_var<D, WT, FORM == 4 || FORM == 7 ? 1 : (FORM == 5 ? 2 : 0), FORM == 6 || FORM == 7>(
+              m2x, x2n, s2, n2, (FORM == 6 || FORM == 7) ? n2 : w2, acc, wacc);
         } else {
           const u64 n2 = *reinterpret_cast<const u64*>(&nrow[i]);
           pair_gradient_x<D, WT, WT>(m2x, x2n, s2, n2, w2, acc, wacc);
@@ -194,6 +258,12 @@ int main() {
   GL(6, 3, 0, 512, "grad D=6 diff     16 warps x 3 states")
   GL(6, 4, 1, 512, "grad D=6 expanded 16 warps x 4 states")
   GL(6, 3, 1, 512, "grad D=6 expanded 16 warps x 3 states")
+  GL(6, 4, 4, 512, "grad D=6 expanded 16w x 4, scalar accumulate FFMAs")
+  GL(6, 4, 5, 512, "grad D=6 expanded 16w x 4, all scalar FFMAs")
+  GL(6, 4, 6, 512, "grad D=6 expanded 16w x 4, w folded into exponent")
+  GL(6, 4, 7, 512, "grad D=6 expanded 16w x 4, scalar accumulate + fold")
+  GL(6, 3, 4, 512, "grad D=6 expanded 16w x 3, scalar accumulate FFMAs")
+  GL(6, 3, 7, 512, "grad D=6 expanded 16w x 3, scalar accumulate + fold")
   GL(6, 4, 1, 384, "grad D=6 expanded 12 warps x 4 states")
   GL(6, 5, 1, 384, "grad D=6 expanded 12 warps x 5 states")
   GL(6, 4, 2, 384, "grad D=6 expanded 12 warps x 4, no smem loads")
