@@ -196,7 +196,8 @@ class PlannerContext:
         q are shared by the targets.  Two implementations (``targets_path``): "fused" - one launch, the gradient pair
         pass and the adjoint run per target (psi recomputed per target); "tensor" - psi once per state-sample pair and
         the sum over the samples as a tensor-core contraction for all targets (klerg_kl_gradient_targets), the default
-        ("auto") for >= 4 targets on a single rank with H <= 64 (2.5x faster at BASELINE config 5)."""
+        ("auto") for >= 4 targets with H <= 64 (2.5x faster at BASELINE config 5); sharded contexts all-gather the
+        totals and the per-target partials in rank order."""
         K = self.P.shape[0]
         u = u.reshape(self.H, -1).contiguous()
         if self.targets_path == "tensor" or (self.targets_path == "auto" and self._tensor_targets_ok(K)):
@@ -233,26 +234,29 @@ class PlannerContext:
     TENSOR_MIN_TARGETS = 4  # below this the per-target pair pass inside the fused launch is at least as fast
 
     def _tensor_targets_ok(self, K):
-        return self.group.world == 1 and self.H <= 64 and K >= self.TENSOR_MIN_TARGETS
+        return self.H <= 64 and K >= self.TENSOR_MIN_TARGETS and not isinstance(self.group, engine.EmulatedShardGroup)
 
     def _gradient_targets_tensor(self, u):
         """rollout -> forward pass (q_base + q_iter, totals) -> klerg_kl_gradient_targets -> one adjoint launch for all
         targets.  Single rank, H <= 64, K*(D+1) <= 128 per launch (larger K is split)."""
-        if self.group.world != 1 or self.H > 64:
-            raise RuntimeError("the tensor-core targets path needs a single rank and H <= 64")
+        if self.H > 64:
+            raise RuntimeError("the tensor-core targets path needs H <= 64")
         K = self.P.shape[0]
         kmax = min(32, 128 // (self.spec.D + 1))
         ro = engine.rollout(self.dyn, self.bar, self.x0, u, R0=self.R0, want_lin=True)
         traj = ro["traj"][0]
         pre = traj[: self.H]
         v, totals = engine.footprint(self.spec, 0, pre, self.packed, self.n, add_in=self.q_base)
-        totals_w = totals.unsqueeze(0)
+        # sharded: every rank contracts over its own samples; the {sum, max} of q and the per-target gradient partials
+        # are all-gathered in rank order (one NCCL call each), so every rank adds the same numbers in the same order
+        totals_w = self.group.gather_blocks(totals.reshape(-1)[:2]).reshape(self.group.world, 2).contiguous()
         Pl = ro["P"][0] if ro["P"] is not None else None
         outs = []
         for k0 in range(0, K, kmax):
             gp, _ = engine.kl_gradient_targets(self.spec, pre, self.packed, self.n, v[0], totals_w,
                                                self.P[k0: k0 + kmax], self.floor, want_kl=False)
-            outs.append(engine.adjoint_targets(self.dyn, self.spec, gp.unsqueeze(1), ro["dbarr"][0], Pl, traj, u, self.rinv,
+            gp_w = self.group.gather_blocks(gp).transpose(0, 1).contiguous()  # [K, world, H, D]
+            outs.append(engine.adjoint_targets(self.dyn, self.spec, gp_w, ro["dbarr"][0], Pl, traj, u, self.rinv,
                                                self.alpha, self.ctrl_lo, self.ctrl_hi))
         self.evals["grad"] += K
         self.evals["fwd_pairs"] += self.H * self.n

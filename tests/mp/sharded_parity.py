@@ -106,6 +106,42 @@ def main():
             if not err < 1e-5:
                 ok = False
     dist.barrier()
+    # the same with the shared-psi tensor-core contraction (every rank contracts over its own samples; totals and the
+    # per-target partials are all-gathered in rank order): rank-identical, and equal to the single-GPU contraction
+    K = 6
+    P_all = torch.stack([wl.make_target("gmm", lims, seed=50 + k, device=dev).pdf_torch(smp_all) for k in range(K)])
+    stats = torch.stack([P_all[k].double().sum().reshape(1) for k in range(K)])
+    ctx.set_targets(P_all[:, a:b].contiguous(), stats)
+    if H <= 64:
+        ctx.targets_path = "tensor"
+        gt = ctx.gradient_targets(U[2])
+        ctx.targets_path = "fused"
+        gf = ctx.gradient_targets(U[2])
+        torch.cuda.synchronize()
+        for key, v in gt.items():
+            ref = v.clone()
+            dist.broadcast(ref, 0)
+            if not torch.equal(ref, v):
+                print(f"[rank {rank}] tensor targets/{key} differs from rank 0")
+                ok = False
+        if rank == 0:
+            single = build_ctx(probe, engine.SINGLE, smp_all, p_all, lo, hi, n_total, hist, x0, H)
+            single.set_targets(P_all.contiguous(), stats)
+            single.targets_path = "tensor"
+            g1 = single.gradient_targets(U[2])
+            for key in gt:
+                x, y, z = (t[key].double().cpu().numpy() for t in (gt, g1, gf))
+                err = np.abs(x - y).max() / (np.abs(y).max() + 1e-30)
+                err_f = np.abs(x - z).max() / (np.abs(z).max() + 1e-30)
+                print(f"tensor targets {key}: vs single GPU {err:.3e}, vs the sharded fused per-target pass {err_f:.3e}")
+                # u* = clamp(u + du): its error is du's absolute error, so measure it on du's scale
+                scale = 1.0 if key != "u_star" else max(1.0, float(g1["du"].abs().max()) / float(g1["u_star"].abs().max()))
+                if not (err < 1e-5 * scale and err_f < 2e-4 * scale):
+                    ok = False
+        if engine.targets_gradient_fault():
+            print(f"[rank {rank}] targets contraction reported a fault")
+            ok = False
+    dist.barrier()
     if engine.fused_fault():
         print(f"[rank {rank}] fused eval reported a meeting-point fault")
         ok = False
