@@ -594,7 +594,7 @@ def cuda_arm(args):
         paths = {}
         for path in ("fused", "tensor"):
             c3.targets_path = path
-            paths[path] = timed(lambda: c3.gradient_targets(c3.u), 5)
+            paths[path] = timed(lambda: c3.gradient_targets(c3.u, check=False), 5)
         if engine.targets_gradient_fault():
             raise SystemExit("klerg_kl_gradient_targets reported a timed-out wait; the measurement is void")
         del c3.targets_path  # back to the class default

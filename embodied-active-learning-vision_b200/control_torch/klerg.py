@@ -34,7 +34,7 @@ from .dynamics import DoubleIntegratorEnv, DoubleIntegratorRollEnv, DoubleIntegr
 from .klerg_utils import Lambda
 from .memory_buffer import MemoryBuffer_torch
 from .planner import PlannerContext
-from .target_decoder import DeviceTarget, is_decoder_model
+from .target_decoder import DeviceTarget, decoder_supported, is_decoder_model
 
 base_path = os.path.dirname(os.path.abspath(__file__))
 
@@ -392,6 +392,8 @@ class Robot(object):
         (target_decoder.DeviceTarget); any other ``pdf_torch`` provider is called where it lives."""
         td = self.target_dist
         if isinstance(td, DeviceTarget) or not is_decoder_model(td):
+            return td
+        if not decoder_supported(td):  # e.g. a deeper hidden_dim list or use_chunk_decode: the model's own pdf_torch
             return td
         cached = getattr(self, "_wrapped_target", None)
         if cached is None or cached.model is not td:

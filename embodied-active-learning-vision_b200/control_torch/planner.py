@@ -191,7 +191,19 @@ class PlannerContext:
             self.p, self.p_stats = saved
         return torch.stack(out)
 
-    def gradient_targets(self, u):
+    def check_fault(self):
+        """Raise if an in-kernel wait of any earlier eval of this context's stream timed out (small D2H reads)."""
+        if engine.fused_fault() or engine.targets_gradient_fault():
+            raise RuntimeError("a fused eval or the targets contraction gave up an in-kernel wait (lost peer or a launch "
+                               "that was not co-resident); the results since the last check are void")
+
+    def gradient_targets(self, u, check=True):
+        out = self._gradient_targets(u)
+        if check:  # the caller reads the results next anyway; ``check=False`` keeps the call asynchronous
+            self.check_fault()
+        return out
+
+    def _gradient_targets(self, u):
         """Per-target gradient eval: dict of [K, ...] stacked du, djdlam, u_star, dgdx.  Rollout, forward pair pass and
         q are shared by the targets.  Two implementations (``targets_path``): "fused" - one launch, the gradient pair
         pass and the adjoint run per target (psi recomputed per target); "tensor" - psi once per state-sample pair and

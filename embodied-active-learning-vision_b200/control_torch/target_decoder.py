@@ -47,6 +47,26 @@ def is_decoder_model(target_dist):
     return all(hasattr(target_dist, n) for n in ("decode", "z_samples", "ylogvar_dim", "logvar_lims", "init"))
 
 
+def decoder_supported(model):
+    """True if the model's decoder is one the kernel is built for (Linear-ReLU-Linear-ReLU-Linear with widths the
+    packed layout accepts).  The controller evaluates any other VAE through the model's own ``pdf_torch``."""
+    if not is_decoder_model(model):
+        return False
+    lin = _linears(model.decode)
+    if lin is None or getattr(model, "use_chunk_decode", False):
+        return False
+    l1, l2, l3 = lin
+    try:
+        zd = int(model.z_samples.shape[-1])
+        nz = int(model.z_buff.get_samples().shape[0]) if getattr(model, "use_buffer", False) else 1
+        sd, nl = l1.in_features - zd, int(model.ylogvar_dim)
+    except Exception:  # noqa: BLE001 - an object that only looks like the VAE
+        return False
+    if l2.in_features != l1.out_features or l3.in_features != l2.out_features or l3.out_features < nl or sd < 1:
+        return False
+    return cabi.load().klerg_target_decoder_packed_bytes(sd, zd, max(nz, 1), l1.out_features, l2.out_features, nl) != 0
+
+
 class DeviceTarget:
     """``target_dist`` whose ``pdf_torch`` runs on the GPU (see module docstring)."""
 

@@ -216,3 +216,23 @@ def test_tables_too_large_is_refused(td):
     model = DecoderModel(case, torch.zeros(8, 4))
     with pytest.raises(RuntimeError, match="do not fit"):
         td.DeviceTarget(model).pdf_torch(target_samples(case))
+
+
+def test_robot_falls_back_for_decoders_the_kernel_is_not_built_for(td):
+    """A VAE the reference accepts but the kernel does not cover (here: a Tanh decoder with two layers) is evaluated
+    through the model's own pdf_torch - Robot.step() must keep working (only DeviceTarget itself refuses)."""
+    from control_torch.klerg import Robot
+    rc = ROBOT_CASES["xyz_small"]
+    case = dict(TARGET_CASES["default"])
+    model = DecoderModel(case, torch.zeros(1, case["zd"]))
+    assert td.decoder_supported(model)
+    model.decode = torch.nn.Sequential(torch.nn.Linear(19, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4))
+    assert not td.decoder_supported(model)
+    calls = []
+    model.pdf_torch = lambda s: (calls.append(s.shape[0]), torch.full((s.shape[0],), 0.5) + 0.1 * s[:, 0].cpu().abs())[1]
+    torch.manual_seed(7)
+    r = Robot(**robot_kwargs(rc, model))
+    r.test(rc["n"])
+    assert r._device_target() is model
+    out = r.step(rc["n"], rc["m"], save_update=True)
+    assert calls and all(np.isfinite(o).all() for o in out)
