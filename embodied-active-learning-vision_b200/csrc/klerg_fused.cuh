@@ -328,11 +328,13 @@ __device__ __forceinline__ void forward_slice_p(const EvalArgs& a, const StateRo
 
 // Samples per thread-iteration: 2 (one packed pair) or 4.  A slice of n samples costs ceil(n / (threads * 2P)) * P
 // pair-iterations per thread; for slices of a few samples per thread the quantisation decides (e.g. 6757 samples on
-// 512 threads: 4 iterations of two pairs = 8, or 7 iterations of one pair = 7).
+// 512 threads: 4 iterations of two pairs = 8, or 7 iterations of one pair = 7).  A pair-iteration of the two-pair form
+// is ~10 % cheaper (the state rows are read from shared memory once for both pairs: 3.19e12 against 2.86e12 pairs/s
+// in the isolated D = 6 loop), so the one-pair form has to save more than that to be chosen.
 __device__ __forceinline__ bool narrow_pairs(int64_t lo, int64_t hi) {
   const int64_t n = hi - lo, bd = blockDim.x;
   const int64_t it1 = (n + bd * 2 - 1) / (bd * 2), it2 = (n + bd * 4 - 1) / (bd * 4);
-  return it1 < 2 * it2 || it1 <= 1;
+  return 10 * it1 < 18 * it2 || it1 <= 1;
 }
 
 template <int D>
