@@ -496,7 +496,7 @@ def cuda_arm(args):
         t_launch = ms_total / K * 1e-3
         traffic = None
         try:  # measured once per round with ncu --set full (not re-measured live: ncu cannot run inside the bench)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(f"{args.workload}:{n}")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(f"{args.workload}:{n}")
             traffic = tr["bytes"] if tr else None
         except (OSError, ValueError):
             pass
