@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel SASS mnemonic counts of libklerg_b200.so (cuobjdump -sass): which kernels carry packed FP32 (FFMA2 /
 FADD2 / FMUL2), MUFU.EX2, TMA bulk copies (UBLKCP), tcgen05 MMAs (UTCHMMA / UTCQMMA ...), TMEM stores / loads
-(STTM / LDTM), mbarrier waits (SYNCS), programmatic-dependent-launch instructions (ACQBULK? no: `GRIDDEPCONTROL` shows
-up as ... ) etc.
+(STTM / LDTM), mbarrier waits (SYNCS), programmatic dependent launch (ACQBULK = griddepcontrol.wait, PREEXIT =
+griddepcontrol.launch_dependents) etc.
 
     python tools/sass_summary.py > profiles/r02_sass_summary.txt
 """
@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "embodied-active-learning-vision_b200", "libklerg_b200.so")
 WATCH = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "MUFU.EX2", "MUFU.LG2", "MUFU.RCP", "DADD", "DFMA", "UBLKCP",
-         "UTCHMMA", "UTCQMMA", "UTCBAR", "STTM", "LDTM", "SYNCS", "LDS", "STS", "LDG", "STG", "LD.E", "ST.E", "BAR", "ACQBULK",
+         "UTCHMMA", "UTCQMMA", "UTCBAR", "STTM", "LDTM", "SYNCS", "LDS", "STS", "LDG", "STG", "LD.E", "ST.E", "BAR", "ACQBULK", "PREEXIT",
          "LDL", "STL", "CCTL", "MEMBAR", "ATOM", "RED", "SHFL"]
 
 
