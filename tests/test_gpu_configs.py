@@ -87,10 +87,35 @@ def test_config3_batched_candidates():
     close(eight, got, rtol=2e-6, what="batch vs launches of 8")
 
 
-@pytest.mark.parametrize("H", [20, 50])
+@pytest.mark.parametrize("name,n,B", [("c3", 1003, 9), ("c3", 2048, 17), ("c3", 2050, 12), ("c3", 40_001, 33),
+                                      ("c1", 777, 10), ("c4", 9_999, 11)])
+def test_batch_costs_ragged_sizes(name, n, B):
+    """klerg_eval_costs_batch on sizes around its work-unit boundaries (fewer samples than one pass of the CTA, exactly
+    one chunk, a two-sample tail, B not a multiple of 8; D = 2, 3, 6) against launches of 8 through eval_cost_kernel,
+    and directly for B < 8."""
+    s = setup(name, n, 200, H=12 if name == "c1" else 20)
+    ctx, dev = s["ctx"], s["dev"]
+    g = torch.Generator().manual_seed(B)
+    U = (wl.random_controls((s["H"], s["D"]), seed=3).unsqueeze(0) + 0.1 * torch.randn(B, s["H"], s["D"], generator=g)).to(dev)
+    got = ctx.costs(U).cpu()
+    ctx.batch_costs = False
+    want = ctx.costs(U).cpu()
+    ctx.batch_costs = True
+    close(got, want, rtol=5e-6, what="batch vs launches of 8")
+    for b in (0, B - 1):
+        ref = s["oracle"].get_cost(s["samples"], s["p"].clone(), s["q_base"], U[b].cpu())
+        close(got[b], ref.reshape(()), rtol=5e-4 if name == "c4" else 1e-4, what=f"candidate {b} vs oracle")
+    few, fault = s["engine"].eval_costs_batch(ctx.spec, ctx.dyn, ctx.bar, ctx.x0, ctx.R0, U[:3].contiguous(), ctx.packed, ctx.n,
+                                              ctx.q_base, ctx.p, ctx.p_stats, ctx.floor)
+    close(few.cpu(), want[:3], rtol=5e-6, what="3 candidates through the batch kernel")
+    assert float(fault[0]) == 0.0
+
+
+@pytest.mark.parametrize("H", [20, 48, 50, 64])
 def test_config4_pose_workspace_long_history(H):
     """6-D pose (roll dynamics), 3e4 samples, 2000 history states: cost + gradient eval vs the oracle.
-    H=50 exercises the mixed schedule (14 warps own 3 states, 2 warps own 4), H=20 the uniform one."""
+    H=50 exercises the mixed schedule (14 warps own 3 states, 2 warps own 4), H=20 the uniform one, H=48 / 64 the
+    all-wide schedules of horizons that are multiples of 16 (3 / 4 states per warp)."""
     s = setup("c4", 30_000, 2_000, H=H)
     U = wl.random_controls((3, s["H"], s["D"]), seed=5)
     got = s["ctx"].costs(U.to(s["dev"])).cpu()
