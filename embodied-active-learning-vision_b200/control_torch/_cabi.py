@@ -188,7 +188,7 @@ def load():
         fn.restype = _RESTYPES.get(name, C.c_int)
     if os.environ.get("KLERG_PDL") == "0":  # A/B switch: plain cooperative launches of the fused evals
         lib.klerg_set_option(OPT_PDL, 0)
-    if os.environ.get("KLERG_MIXED_WARPS") in ("12", "16"):  # A/B switch: balanced gradient schedules for D >= 5
+    if os.environ.get("KLERG_MIXED_WARPS") in ("1", "12", "16"):  # A/B switch: gradient schedules for D >= 5
         lib.klerg_set_option(OPT_MIXED_WARPS, int(os.environ["KLERG_MIXED_WARPS"]))
     if os.environ.get("KLERG_EXACT_PAIRS") == "1":  # A/B switch: difference form of the squared distance everywhere
         lib.klerg_set_option(OPT_EXACT_PAIRS, 1)

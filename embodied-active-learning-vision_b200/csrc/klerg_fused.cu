@@ -52,7 +52,7 @@ extern "C" int klerg_set_option(int key, int value) {
     case KLERG_OPT_GRID_LIMIT: g_fused_opt.grid_limit = value > 0 ? value : 0; return 0;
     case KLERG_OPT_PDL: g_fused_opt.pdl = value != 0; return 0;
     case KLERG_OPT_EXACT_PAIRS: g_exact_pairs = value != 0; return 0;
-    case KLERG_OPT_MIXED_WARPS: g_fused_opt.mixed_warps = (value == 12 || value == 16) ? value : 0; return 0;
+    case KLERG_OPT_MIXED_WARPS: g_fused_opt.mixed_warps = (value == 12 || value == 16 || value == 1) ? value : 0; return 0;
     default: set_error("set_option: unknown key %d", key); return -1;
   }
 }

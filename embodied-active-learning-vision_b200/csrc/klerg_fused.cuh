@@ -759,18 +759,20 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       active = true;
     }
     const int left0 = nwarps * WT;  // balanced schedule: first shared state
-    u64 acc[WTA][D], wacc[WTA], lacc[LA][D], lwacc[LA];
+    u64 acc[WTA][D], wacc[WTA];
 #pragma unroll
     for (int k = 0; k < WTA; ++k) {
 #pragma unroll
       for (int d = 0; d < D; ++d) acc[k][d] = pack2(0.f, 0.f);
       wacc[k] = pack2(0.f, 0.f);
     }
-#pragma unroll
-    for (int k = 0; k < LA; ++k) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) lacc[k][d] = pack2(0.f, 0.f);
-      lwacc[k] = pack2(0.f, 0.f);
+    // The shared (left-over) states live in registers only while a tile's share of them is processed: their rows are
+    // re-read from shared memory and their sums go to this warp's slots of s_left after every tile, so that the
+    // register file holds the warp's own WT states and nothing else across the sweep.
+    float* s_left = s_part + (size_t)nwarps * WTA * (D + 1);  // [nwarps][LEFT][D + 1] partials of the shared states
+    if constexpr (LEFT > 0) {
+      if (lane < LA * (D + 1)) s_left[warp * LA * (D + 1) + lane] = 0.f;
+      __syncwarp();
     }
     const int g_base = (kt * a.rounds + r) * nt;
     // The sweep over the slice's tiles exists once per pair form (the form is uniform over the launch), so that only
@@ -778,8 +780,8 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
     // -2 xc and |xc|^2.
     auto run_tiles = [&](auto xf_tag) {
       constexpr bool XF = decltype(xf_tag)::value;
-      u64 xs2[XF ? 1 : WTA][D], lxs2[XF ? 1 : LA][D];
-      float m2x[XF ? WTA : 1][D], x2n[XF ? WTA : 1], lm2x[XF ? LA : 1][D], lx2n[XF ? LA : 1];
+      u64 xs2[XF ? 1 : WTA][D];
+      float m2x[XF ? WTA : 1][D], x2n[XF ? WTA : 1];
 #pragma unroll
       for (int k = 0; k < WTA; ++k) {
         const bool have = active && k < my_wt && t0 + k < H;
@@ -791,20 +793,6 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
             xs2[k][d] = have ? s_x2[(t0 + k) * Row2<D>::DP + d] : pack2(0.f, 0.f);
         }
         if constexpr (XF) x2n[k] = have ? s_rx[(t0 + k) * NF + D] : 0.f;
-      }
-      if constexpr (LEFT > 0) {
-#pragma unroll
-        for (int k = 0; k < LA; ++k) {
-          const bool have = left0 + k < H;
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            if constexpr (XF)
-              lm2x[k][d] = have ? s_rx[(left0 + k) * NF + d] : 0.f;
-            else
-              lxs2[k][d] = have ? s_x2[(left0 + k) * Row2<D>::DP + d] : pack2(0.f, 0.f);
-          }
-          if constexpr (XF) lx2n[k] = have ? s_rx[(left0 + k) * NF + D] : 0.f;
-        }
       }
       for (int t = 0; t < nt; ++t) {
         const int g = g_base + t, b = g & (TILE_NB - 1);
@@ -849,7 +837,23 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
         }
         if constexpr (LEFT > 0) {
           // the shared states, on this warp's own 64-sample chunks of the tile (chunk c by warp c % nwarps)
-          if (left0 < H) {
+          if (left0 < H && warp < (cnt64 >> 6)) {
+            u64 lacc[LA][D], lwacc[LA], lxs2[XF ? 1 : LA][D];
+            float lm2x[XF ? LA : 1][D], lx2n[XF ? LA : 1];
+#pragma unroll
+            for (int k = 0; k < LA; ++k) {
+              const bool have = left0 + k < H;
+#pragma unroll
+              for (int d = 0; d < D; ++d) {
+                lacc[k][d] = pack2(0.f, 0.f);
+                if constexpr (XF)
+                  lm2x[k][d] = have ? s_rx[(left0 + k) * NF + d] : 0.f;
+                else
+                  lxs2[k][d] = have ? s_x2[(left0 + k) * Row2<D>::DP + d] : pack2(0.f, 0.f);
+              }
+              lwacc[k] = pack2(0.f, 0.f);
+              if constexpr (XF) lx2n[k] = have ? s_rx[(left0 + k) * NF + D] : 0.f;
+            }
             for (int c = warp; c < (cnt64 >> 6); c += nwarps) {
               const int i = (c << 6) + 2 * lane;
               u64 s2[D];
@@ -863,6 +867,20 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
                 pair_gradient<D, LA>(lxs2, s2, w2, lacc, true);
               }
             }
+            // lanes -> this warp's running sums in shared memory (lane e owns entry e)
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 0; k < LA; ++k) {
+#pragma unroll
+              for (int d = 0; d <= D; ++d) {
+                float x, y;
+                unpack2(d < D ? lacc[k][d] : lwacc[k], x, y);
+                float v = warp_sum_f(x + y);
+                if (d < D && !XF) v = -v;
+                if (lane == k * (D + 1) + d) mine = v;
+              }
+            }
+            if (lane < LA * (D + 1)) s_left[warp * LA * (D + 1) + lane] += mine;
           }
         }
       }
@@ -887,23 +905,6 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       unpack2(wacc[k], x, y);
       const float v = warp_sum_f(x + y);
       if (lane == 0) s_part[(warp * WTA + k) * (D + 1) + D] = v;
-    }
-    float* s_left = s_part + (size_t)nwarps * WTA * (D + 1);  // [nwarps][LEFT][D + 1] partials of the shared states
-    if constexpr (LEFT > 0) {
-#pragma unroll
-      for (int k = 0; k < LA; ++k) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          float x, y;
-          unpack2(lacc[k][d], x, y);
-          const float v = warp_sum_f(x + y);
-          if (lane == 0) s_left[(warp * LA + k) * (D + 1) + d] = xform ? v : -v;
-        }
-        float x, y;
-        unpack2(lwacc[k], x, y);
-        const float v = warp_sum_f(x + y);
-        if (lane == 0) s_left[(warp * LA + k) * (D + 1) + D] = v;
-      }
     }
     __syncthreads();
     // this CTA's partial of gather entry e goes to slot [e][vblk] as ONE tagged word (fp32 value + tag)
@@ -1311,11 +1312,12 @@ static int grad_max_warps(int D) { return D <= 3 ? 20 : (D == 4 ? 16 : 17); }
 // Choose states-per-warp WT and the warp grid so that (states x sample sub-streams) tiles the
 // CTA's warps with as few idle slots as possible.
 static GradSchedule plan_schedule(int D, int H) {
-  if (D >= 5 && g_fused_opt.mixed_warps == 12) {
+  if (D >= 5 && (g_fused_opt.mixed_warps == 12 || g_fused_opt.mixed_warps == 0)) {
     // balanced schedule on 12 warps (3 per SM sub-partition, up to 168 registers): every warp owns 4 states, the
-    // H - 48 <= 2 states that remain are shared (each warp takes them on its own sample chunks).  More states per
-    // warp = more independent FFMA chains in flight per warp and room in the register file to interleave them;
-    // equal state counts = no warp waits for a wider one at the tile ring.
+    // H - 48 <= 2 states that remain are shared (each warp takes them on its own sample chunks of every tile, with
+    // transient registers: their sums go to shared memory after each tile).  Equal state counts = no warp waits for
+    // a wider one at the tile barrier (the 16-warp split of H = 50 into 14 x 3 + 2 x 4 loses ~6 % there): 630 vs
+    // 647 us per c4 eval.  KLERG_OPT_MIXED_WARPS = 1 selects the 16-warp split instead.
     const int nw = 12, q = H / nw, r = H % nw;
     if (q == 4 && r <= 2) {
       GradSchedule m{};

@@ -234,8 +234,10 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
  *                           differences; default 0: the cheaper expanded form |sc|^2 + |xc|^2 - 2 xc.sc around a centre
  *                           of the state set wherever the set is narrow enough for it (relative error of psi < 3e-5),
  *                           the difference form elsewhere.
- *   KLERG_OPT_MIXED_WARPS   12 = the gradient pass of D >= 5 runs a balanced 12-warp schedule (4 states per warp, the
- *                           rest shared) where the horizon allows (A/B switch; default 0: 16 warps with 3-4 states). */
+ *   KLERG_OPT_MIXED_WARPS   schedule of the gradient pass for D >= 5 (A/B switch).  0 (default): 12 warps with 4 states
+ *                           each and the <= 2 states that remain shared over all warps, where the horizon allows
+ *                           (H = 48..50), else 16 warps with 3-4 states; 1: always the 16-warp split; 16: 16 warps
+ *                           with 3 states each + shared rest (spills at 128 registers: slower; kept for measurement). */
 enum { KLERG_OPT_EVAL_OVERLAP = 1, KLERG_OPT_GRID_LIMIT = 2, KLERG_OPT_PDL = 3, KLERG_OPT_COOP_WITH_PDL = 4,
        KLERG_OPT_EXACT_PAIRS = 5, KLERG_OPT_MIXED_WARPS = 6 };
 int klerg_set_option(int key, int value);
