@@ -766,13 +766,15 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       for (int d = 0; d < D; ++d) acc[k][d] = pack2(0.f, 0.f);
       wacc[k] = pack2(0.f, 0.f);
     }
-    // The shared (left-over) states live in registers only while a tile's share of them is processed: their rows are
-    // re-read from shared memory and their sums go to this warp's slots of s_left after every tile, so that the
-    // register file holds the warp's own WT states and nothing else across the sweep.
+    // The shared (left-over) states: their accumulators stay in registers across the sweep, their rows are re-read from
+    // shared memory for every tile's share of them (the row registers are only live there).
     float* s_left = s_part + (size_t)nwarps * WTA * (D + 1);  // [nwarps][LEFT][D + 1] partials of the shared states
-    if constexpr (LEFT > 0) {
-      if (lane < LA * (D + 1)) s_left[warp * LA * (D + 1) + lane] = 0.f;
-      __syncwarp();
+    u64 lacc[LA][D], lwacc[LA];
+#pragma unroll
+    for (int k = 0; k < LA; ++k) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) lacc[k][d] = pack2(0.f, 0.f);
+      lwacc[k] = pack2(0.f, 0.f);
     }
     const int g_base = (kt * a.rounds + r) * nt;
     // The sweep over the slice's tiles exists once per pair form (the form is uniform over the launch), so that only
@@ -838,20 +840,18 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
         if constexpr (LEFT > 0) {
           // the shared states, on this warp's own 64-sample chunks of the tile (chunk c by warp c % nwarps)
           if (left0 < H && warp < (cnt64 >> 6)) {
-            u64 lacc[LA][D], lwacc[LA], lxs2[XF ? 1 : LA][D];
+            u64 lxs2[XF ? 1 : LA][D];
             float lm2x[XF ? LA : 1][D], lx2n[XF ? LA : 1];
 #pragma unroll
             for (int k = 0; k < LA; ++k) {
               const bool have = left0 + k < H;
 #pragma unroll
               for (int d = 0; d < D; ++d) {
-                lacc[k][d] = pack2(0.f, 0.f);
                 if constexpr (XF)
                   lm2x[k][d] = have ? s_rx[(left0 + k) * NF + d] : 0.f;
                 else
                   lxs2[k][d] = have ? s_x2[(left0 + k) * Row2<D>::DP + d] : pack2(0.f, 0.f);
               }
-              lwacc[k] = pack2(0.f, 0.f);
               if constexpr (XF) lx2n[k] = have ? s_rx[(left0 + k) * NF + D] : 0.f;
             }
             for (int c = warp; c < (cnt64 >> 6); c += nwarps) {
@@ -867,20 +867,6 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
                 pair_gradient<D, LA>(lxs2, s2, w2, lacc, true);
               }
             }
-            // lanes -> this warp's running sums in shared memory (lane e owns entry e)
-            float mine = 0.f;
-#pragma unroll
-            for (int k = 0; k < LA; ++k) {
-#pragma unroll
-              for (int d = 0; d <= D; ++d) {
-                float x, y;
-                unpack2(d < D ? lacc[k][d] : lwacc[k], x, y);
-                float v = warp_sum_f(x + y);
-                if (d < D && !XF) v = -v;
-                if (lane == k * (D + 1) + d) mine = v;
-              }
-            }
-            if (lane < LA * (D + 1)) s_left[warp * LA * (D + 1) + lane] += mine;
           }
         }
       }
@@ -889,6 +875,18 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       run_tiles(std::true_type{});
     else
       run_tiles(std::false_type{});
+    if constexpr (LEFT > 0) {
+#pragma unroll
+      for (int k = 0; k < LA; ++k) {
+#pragma unroll
+        for (int d = 0; d <= D; ++d) {
+          float x, y;
+          unpack2(d < D ? lacc[k][d] : lwacc[k], x, y);
+          const float v = warp_sum_f(x + y);
+          if (lane == 0) s_left[(warp * LA + k) * (D + 1) + d] = (d < D && !xform) ? -v : v;
+        }
+      }
+    }
     __syncthreads();
     // lanes -> warp sums -> CTA partial for this round's states.  Gather entries are A[t][d] and W[t] with
     // dgdx = gfac (xc W - A); the difference form holds sum w psi (x' - s') directly: A = -acc, W = 0.
@@ -1315,8 +1313,8 @@ static GradSchedule plan_schedule(int D, int H) {
   if (D >= 5 && (g_fused_opt.mixed_warps == 12 || g_fused_opt.mixed_warps == 0)) {
     // balanced schedule on 12 warps (3 per SM sub-partition, up to 168 registers): every warp owns 4 states, the
     // H - 48 <= 2 states that remain are shared (each warp takes them on its own sample chunks of every tile, with
-    // transient registers: their sums go to shared memory after each tile).  Equal state counts = no warp waits for
-    // a wider one at the tile barrier (the 16-warp split of H = 50 into 14 x 3 + 2 x 4 loses ~6 % there): 630 vs
+    // their rows re-read per tile, their accumulators kept in registers).  Equal state counts = no warp waits for
+    // a wider one at the tile barrier (the 16-warp split of H = 50 into 14 x 3 + 2 x 4 loses ~6 % there): 616 vs
     // 647 us per c4 eval.  KLERG_OPT_MIXED_WARPS = 1 selects the 16-warp split instead.
     const int nw = 12, q = H / nw, r = H % nw;
     if (q == 4 && r <= 2) {
