@@ -726,6 +726,7 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
       if (e >= cnt) {  // cnt is even: the pair lies beyond the slice as a whole
 #pragma unroll
         for (int d = 0; d < D; ++d) *reinterpret_cast<u64*>(&buf[(size_t)d * TSR + e]) = pack2(0.f, 0.f);
+        if (xform) n2 = pack2(INFINITY, INFINITY);  // w = 0 in the exponent
       } else if (xform) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -734,6 +735,8 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
           *sp2 = sc;
           n2 = fma2(sc, sc, n2);
         }
+        // the weight rides in the exponent: |sc|^2 - log2(w), +inf for w = 0 (2^-inf = 0 = w psi)
+        n2 = sub2(n2, pack2(__log2f(w0), __log2f(w1)));
       }
       *reinterpret_cast<float2*>(&wrow[e]) = make_float2(w0, w1);
       *reinterpret_cast<u64*>(&nrow[e]) = n2;
@@ -817,9 +820,8 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
                 u64 s2[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TSR + i]);
-                const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
                 const u64 n2 = *reinterpret_cast<const u64*>(&nrow[i]);
-                pair_gradient_x<D, WTA, NS>(m2x, x2n, s2, n2, w2, acc, wacc);
+                pair_gradient_xw<D, WTA, NS>(m2x, x2n, s2, n2, acc, wacc);
               }
             };
             if (WTA == 1 || my_wt == WTA)
@@ -859,11 +861,11 @@ __device__ __forceinline__ void eval_grad_body(const EvalArgs& a, const int vblk
               u64 s2[D];
 #pragma unroll
               for (int d = 0; d < D; ++d) s2[d] = *reinterpret_cast<const u64*>(&buf[(size_t)d * TSR + i]);
-              const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
               if constexpr (XF) {
                 const u64 n2 = *reinterpret_cast<const u64*>(&nrow[i]);
-                pair_gradient_x<D, LA, LA>(lm2x, lx2n, s2, n2, w2, lacc, lwacc);
+                pair_gradient_xw<D, LA, LA>(lm2x, lx2n, s2, n2, lacc, lwacc);
               } else {
+                const u64 w2 = *reinterpret_cast<const u64*>(&wrow[i]);
                 pair_gradient<D, LA>(lxs2, s2, w2, lacc, true);
               }
             }
