@@ -47,8 +47,9 @@ class Peers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("mailbox", C.c_void_p * 8), ("n_max", C.c_int64)]
 
 
-ABI_VERSION = 5  # mirrors klerg_abi_version() of the library built from this tree (include/klerg_b200.h)
+ABI_VERSION = 6  # mirrors klerg_abi_version() of the library built from this tree (include/klerg_b200.h)
 OPT_EVAL_OVERLAP, OPT_GRID_LIMIT, OPT_PDL, OPT_COOP_WITH_PDL, OPT_EXACT_PAIRS, OPT_MIXED_WARPS = 1, 2, 3, 4, 5, 6
+OPT_SATURATE_MILLI = 7
 
 
 class BarrierSpec(C.Structure):

@@ -208,6 +208,18 @@ def set_eval_overlap(on):
     cabi.check(cabi.load().klerg_set_option(cabi.OPT_EVAL_OVERLAP, int(bool(on))), "klerg_set_option")
 
 
+_saturate_milli = [0]
+
+
+def set_saturate(app_thresh):
+    """u* of the evals enqueued from now on: 0 = clamp to the control limits (klerg.py:522), t > 0 = the reference's
+    ``saturate`` flag, tanh(u / t) * control_lim[:, 1] (Robot.saturate_control, klerg.py:342-349)."""
+    milli = int(round(1000.0 * float(app_thresh)))
+    if milli != _saturate_milli[0]:
+        cabi.check(cabi.load().klerg_set_option(cabi.OPT_SATURATE_MILLI, milli), "klerg_set_option")
+        _saturate_milli[0] = milli
+
+
 def padded(n):
     return max(4, (int(n) + 3) // 4 * 4)
 

@@ -14,9 +14,13 @@ different is where the work happens:
   kernel behind ``libklerg_b200.so``; the <= 5 line-search candidates of an
   iteration are evaluated as ONE batched launch instead of a serial Python loop.
 
-Not ported (never enabled by the shipped configs):
-``optimize_samples``, ``sample_near_current_loc``, ``saturate``, ``full_cost``,
-``PriorDist``/``use_prior``, the BarrierPush/LQR policies.
+The non-default ``robot_config.yaml`` flags ``saturate``, ``fixed_lam``,
+``ctrlAppSearch: False``, ``sample_near_current_loc``, ``add_recent_history``,
+``test_corners`` and ``PriorDist`` / ``use_prior`` are built (SURVEY section 8
+a22; golden sequences from the live reference).  Not ported: ``optimize_samples``
+(an autograd/Adam pre-conditioner of the samples through the target model),
+``full_cost`` (does not run in the reference itself), ``average_prior`` (reads an
+attribute the reference never defines), the BarrierPush/LQR policies (dmu/dx != 0).
 """
 import itertools
 import math
@@ -44,6 +48,31 @@ except ImportError:  # package used outside the reference's scripts/ layout
     import sys
     sys.path.insert(0, os.path.dirname(base_path))
     from franka.franka_utils import find_non_vel_locs, ws_conversion
+
+
+class PriorDist():
+    """Fixed two-object prior over the named states (klerg.py:27-50): two Gaussians with a shared diagonal covariance,
+    + 1e-5.  Evaluated where the samples live (closed form of MultivariateNormal.log_prob for a diagonal covariance).
+    The reference reads ``prior_dist.device`` without ever setting it; here it is set."""
+
+    def __init__(self, states):
+        base_states = 'xyzrpw'
+        base_duck = [-0.8, -0.8, -0.15, 3.6, 0.5, 0.]
+        base_ball = [0.6, 0.9, -0.15, 2.6, -0.5, 0.]
+        base_covar = [0.2, 0.2, 0.5, 0.2, 0.2, 0.5]
+        pick = lambda tab, dflt: [tab[base_states.rfind(s)] if (s in base_states) else dflt for s in states]
+        self.locs = torch.tensor([pick(base_duck, 0.), pick(base_ball, 0.)], dtype=torch.float32)
+        self.var = torch.tensor(pick(base_covar, 1.), dtype=torch.float32)
+        self.device = 'cuda'
+
+    def pdf(self, x):
+        return self.pdf_torch(torch.as_tensor(x)).cpu().numpy()
+
+    def pdf_torch(self, samples):
+        locs, var = self.locs.to(samples.device), self.var.to(samples.device)
+        half_log_det = 0.5 * torch.log(var).sum() + 0.5 * len(var) * math.log(2 * math.pi)
+        d = samples.unsqueeze(0) - locs.unsqueeze(1)
+        return torch.exp(-0.5 * (d * d / var).sum(2) - half_log_det).sum(0) + 1e-5
 
 
 class DeviceSamples:
@@ -112,11 +141,7 @@ class Robot(object):
         cabi.require_cuda()
         cabi.load()
         self.load_yaml(uniform_tdist)
-        for flag in ("optimize_samples", "sample_near_current_loc", "saturate", "full_cost"):
-            if getattr(self, flag):
-                raise NotImplementedError(f"robot_config flag {flag!r} is not ported to the B200 controller")
-        if not self.ctrlAppSearch:
-            raise NotImplementedError("ctrlAppSearch=False is not ported")
+        self._check_flags()
 
         self.target_dist = target_dist
         for attr, val in zip(['dtype', 'device'], [torch.float32, 'cpu']):
@@ -130,6 +155,7 @@ class Robot(object):
         torch.set_default_dtype(self.dtype)
         self.group = engine.ShardGroup(process_group)
 
+        self.prior_dist = PriorDist(states)
         self.use_prior = False
         self.average_prior = False
         self.pybullet = pybullet
@@ -272,6 +298,11 @@ class Robot(object):
             corner_samples = tmp
         return corner_samples
 
+    def _check_flags(self):
+        for flag in ("optimize_samples", "full_cost", "average_prior"):
+            if getattr(self, flag, False):
+                raise NotImplementedError(f"robot_config flag {flag!r} is not ported to the B200 controller")
+
     # ------------------------------------------------------------------ public API
     def step(self, num_target_samples=50, num_traj_samples=30, save_update=False, temp=1.0):
         self.kldiv_planner(num_target_samples=num_target_samples, num_traj_samples=num_traj_samples, temp=temp)
@@ -329,23 +360,38 @@ class Robot(object):
     # ------------------------------------------------------------------ sampling / target
     def get_samples(self, num_target_samples, num_traj_samples):
         """Host RNG draws in the reference's order: uniform samples, then the buffer permutation."""
+        self._check_flags()
         if self.add_recent_history:
             recent = self.memory_buffer.get_recent(self.horizon)
             num_target_samples -= len(recent)
-        extras = []
+        if self.sample_near_current_loc:
+            num_target_samples = int(num_target_samples * 0.9)
+        n_near = int(num_target_samples / 0.9 * 0.1) if self.sample_near_current_loc else 0
+        fixed = []  # appended rows that need no draw
         if self.add_recent_history:
-            extras.append(recent[:, self.explr_locs])
+            fixed.append(recent[:, self.explr_locs])
         if self.test_corners:
-            extras.append(self.corner_samples)
+            fixed.append(self.corner_samples)
+        n_total = num_target_samples + n_near + sum(len(e) for e in fixed)
+
+        def near_current():
+            """Normal(0, 4 std) around the current exploration state, drawn AFTER the uniform samples (RNG order of
+            klerg.py:375-392; the sampler is what Robot.__init__ creates at klerg.py:181-182)."""
+            if not n_near:
+                return []
+            if not hasattr(self, "loc_sampler"):
+                self.loc_sampler = torch.distributions.Normal(torch.zeros_like(self.std), self.std * 4.)
+            return [self.loc_sampler.sample((n_near,)) + self.robot.state[self.explr_locs].clone()]
+
         if self._device_draw_ok():
             # the same draw, continued on the device from the host generator's state (bit-exact samples, the host
-            # generator ends where the host draw would have left it): no 4*N*D-byte host pass and copy per step
-            n_total = num_target_samples + sum(len(e) for e in extras)
+            # generator ends where the host draw would have left it - device_uniform returns after handing the
+            # state back): no 4*N*D-byte host pass and copy per step
             lo, hi = self.group.shard_bounds(n_total)
             parts = [engine.device_uniform(num_target_samples, self.env_sampler.low, self.env_sampler.high,
                                            min(lo, num_target_samples), min(hi, num_target_samples), self.cuda)]
             off = num_target_samples
-            for e in extras:  # appended rows that fall into this rank's slice
+            for e in near_current() + fixed:  # appended rows that fall into this rank's slice
                 a, b = max(lo, off) - off, min(hi, off + len(e)) - off
                 if b > a:
                     parts.append(e[a:b].to(self.cuda, non_blocking=True))
@@ -353,6 +399,7 @@ class Robot(object):
             samples = DeviceSamples(torch.cat(parts).contiguous() if len(parts) > 1 else parts[0], n_total)
         else:
             samples = self.env_sampler.sample((num_target_samples,))
+            extras = near_current() + fixed
             if extras:
                 samples = torch.vstack([samples] + extras)
         hist_dev, hist_idx = self.memory_buffer.sample_device(num_traj_samples)
@@ -364,8 +411,10 @@ class Robot(object):
     def _device_draw_ok(self):
         """The samples can stay on the device when the target density is evaluated there and no plot data (host
         tensors by contract, klerg.py:659-682) is kept."""
-        if not self.device_rng or self.plot_data is not None or self.uniform_tdist or self.use_prior:
+        if not self.device_rng or self.plot_data is not None or self.uniform_tdist:
             return False
+        if self.use_prior:
+            return True  # PriorDist is evaluated on the device
         target = self._device_target()
         return torch.device(getattr(target, "device", "cpu")).type == "cuda"
 
@@ -379,8 +428,10 @@ class Robot(object):
             tdev = torch.device(self.target_dist.device)
             full = self.target_dist.init_uniform_grid(samples_host.clone().to(tdev)).squeeze()
             return self._shard(full), True
-        if self.use_prior:
-            raise NotImplementedError("use_prior is not ported")
+        if self.use_prior:  # klerg.py:459-461: the fixed prior, renormalised, instead of the model
+            if samples_dev is not None:
+                return self.prior_dist.pdf_torch(samples_dev).squeeze(), True
+            return self.prior_dist.pdf_torch(self._shard(samples_host).to(self.cuda)).squeeze(), True
         target = self._device_target()
         tdev = torch.device(target.device)
         if samples_dev is not None and tdev.type == samples_dev.device.type and tdev.index in (None, samples_dev.device.index):
@@ -464,6 +515,8 @@ class Robot(object):
         return c
 
     def kldiv_planner(self, num_target_samples, num_traj_samples, temp=1.0):
+        # u* = tanh((u + alpha du) / 0.1) * control_lim[:, 1] instead of the clamp (klerg.py:342-349, 519-522)
+        engine.set_saturate(0.1 if self.saturate else 0.0)
         with engine.nvtx_range("klerg.get_samples"):
             samples, hist_dev, nu = self.get_samples(num_target_samples, num_traj_samples)
         with torch.no_grad():
@@ -493,7 +546,7 @@ class Robot(object):
                                                     uniform=self.uniform_tdist, spread=spread)
                 ctx.set_target(p, p_stats)
 
-            if self.device_loop and ctx.fused and self.plot_data is None:
+            if self.device_loop and ctx.fused and self.plot_data is None and self.ctrlAppSearch:
                 with engine.nvtx_range("klerg.plan_optimize"):
                     self._optimize_on_device(ctx)
                 return
@@ -516,7 +569,10 @@ class Robot(object):
                     djdlam = g["djdlam"].cpu()
                     u_star = g["u_star"].cpu()
                 t_app = torch.argmin(djdlam).item()
-                if djdlam[t_app] < 0:
+                if not self.ctrlAppSearch:  # klerg.py:562-563: the whole saturated / clamped step
+                    u_tmp = u_star.clone()
+                    cost = self._costs(ctx, u_tmp.unsqueeze(0))[0]
+                elif djdlam[t_app] < 0:
                     u_app = u_star[t_app]
                     if self.fixed_lam:
                         u_tmp[t_app:t_app + self.lam] = u_app.clone()

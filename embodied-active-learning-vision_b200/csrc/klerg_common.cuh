@@ -206,6 +206,7 @@ struct KernelDev {
   float x_r2;                 // largest |xc|^2 for which the expanded pair form is used (< 0: never)
 };
 extern int g_exact_pairs;     // KLERG_OPT_EXACT_PAIRS
+extern int g_saturate_milli;  // KLERG_OPT_SATURATE_MILLI
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

@@ -399,6 +399,7 @@ struct AdjParams {
   float rinv[KLERG_MAX_A];
   float clo[KLERG_MAX_A], chi[KLERG_MAX_A];
   float alpha;
+  float sat;  // > 0: u* = tanh(us / sat) * chi (Robot.saturate_control, klerg.py:342-349) instead of the clamp
 };
 
 __host__ __device__ inline int adjoint_scratch_floats(int H, int A) { return 5 * H * A + 8; }
@@ -472,7 +473,7 @@ __device__ inline void adjoint_block(const DynDev& d, const AdjParams& ap, int H
       dj += btr * dui;
       du[t * A + i] = dui;
       const float us = su[t * A + i] + ap.alpha * dui;
-      u_star[t * A + i] = fminf(fmaxf(us, ap.clo[i]), ap.chi[i]);
+      u_star[t * A + i] = ap.sat > 0.f ? tanhf(us / ap.sat) * ap.chi[i] : fminf(fmaxf(us, ap.clo[i]), ap.chi[i]);
     }
     djdlam[t] = dj;
   }

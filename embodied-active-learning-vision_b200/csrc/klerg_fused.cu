@@ -53,6 +53,7 @@ extern "C" int klerg_set_option(int key, int value) {
     case KLERG_OPT_PDL: g_fused_opt.pdl = value != 0; return 0;
     case KLERG_OPT_EXACT_PAIRS: g_exact_pairs = value != 0; return 0;
     case KLERG_OPT_MIXED_WARPS: g_fused_opt.mixed_warps = (value == 12 || value == 16 || value == 1) ? value : 0; return 0;
+    case KLERG_OPT_SATURATE_MILLI: g_saturate_milli = value > 0 ? value : 0; return 0;
     default: set_error("set_option: unknown key %d", key); return -1;
   }
 }
@@ -64,6 +65,7 @@ extern "C" int klerg_get_option(int key) {
     case KLERG_OPT_COOP_WITH_PDL: return g_fused_opt.coop_probe;
     case KLERG_OPT_EXACT_PAIRS: return g_exact_pairs;
     case KLERG_OPT_MIXED_WARPS: return g_fused_opt.mixed_warps;
+    case KLERG_OPT_SATURATE_MILLI: return g_saturate_milli;
     default: return -1;
   }
 }
@@ -158,6 +160,7 @@ extern "C" int klerg_eval_gradient_targets(const klerg_kernel_spec* k, const kle
   if (((uintptr_t)packed | (uintptr_t)p | (uintptr_t)v_scratch) & 15) { set_error("eval_gradient: packed, p and v_scratch must be 16-byte aligned"); return -1; }
   for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
   a.ap.alpha = alpha;
+  a.ap.sat = 1e-3f * (float)g_saturate_milli;
   a.x0 = x0; a.R0 = R0; a.u = u; a.G = 1; a.H = (int)H; a.packed = packed; a.N = N; a.ld = ld; a.q_base = q_base; a.p = p;
   a.K = (int)K; a.p_stride = p_stride;
   a.p_stats = p_stats; a.floor = floor; a.v = v_scratch; a.ws = workspace; a.traj = traj; a.totals = totals; a.cost = cost;

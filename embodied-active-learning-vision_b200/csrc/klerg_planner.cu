@@ -48,6 +48,7 @@ int sm_count() {
 }
 
 int g_exact_pairs = 0;
+int g_saturate_milli = 0;
 
 bool make_kernel_dev(const klerg_kernel_spec* k, KernelDev& out) {
   if (!k) { set_error("kernel spec is null"); return false; }
@@ -450,7 +451,7 @@ static bool make_lim(int D, const float* lo, const float* hi, LimDev& L) {
 using namespace klerg;
 
 extern "C" const char* klerg_last_error(void) { return g_err; }
-extern "C" int klerg_abi_version(void) { return 5; }
+extern "C" int klerg_abi_version(void) { return 6; }
 extern "C" long long klerg_launch_count(void) { return g_launches; }
 
 // ---- peak-rate microbenchmarks (roofline denominators, used by bench.py only) ----
@@ -668,6 +669,7 @@ static int launch_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k,
   a.H = H; a.grad_part = grad_part; a.world = world; a.dbarr = dbarr; a.P = P; a.traj = traj; a.u = u;
   a.ap.alpha = alpha; a.dgdx = dgdx; a.du = du; a.djdlam = djdlam; a.u_star = u_star; a.gp_stride = gp_stride;
   for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
+  a.ap.sat = 1e-3f * (float)g_saturate_milli;
   const bool speed = a.d.kind == KLERG_DYN_SPEED;
   const size_t smem = sizeof(float) * ((size_t)H * (a.d.S + (P ? a.d.A * a.d.A : 0) + (speed ? a.d.S : 0) + a.d.A) +
                                        adjoint_scratch_floats((int)H, a.d.A));

@@ -237,9 +237,13 @@ int klerg_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t
  *   KLERG_OPT_MIXED_WARPS   schedule of the gradient pass for D >= 5 (A/B switch).  0 (default): 12 warps with 4 states
  *                           each and the <= 2 states that remain shared over all warps, where the horizon allows
  *                           (H = 48..50), else 16 warps with 3-4 states; 1: always the 16-warp split; 16: 16 warps
- *                           with 3 states each + shared rest (spills at 128 registers: slower; kept for measurement). */
+ *                           with 3 states each + shared rest (spills at 128 registers: slower; kept for measurement).
+ *   KLERG_OPT_SATURATE_MILLI  0 (default): u* = clamp(u + alpha du, ctrl_lo, ctrl_hi) (klerg.py:522); t > 0: the
+ *                           reference's `saturate` flag, u* = tanh((u + alpha du) / (t / 1000)) * ctrl_hi
+ *                           (Robot.saturate_control, klerg.py:342-349; the reference uses t = 100).  Read when an
+ *                           eval / adjoint launch is enqueued. */
 enum { KLERG_OPT_EVAL_OVERLAP = 1, KLERG_OPT_GRID_LIMIT = 2, KLERG_OPT_PDL = 3, KLERG_OPT_COOP_WITH_PDL = 4,
-       KLERG_OPT_EXACT_PAIRS = 5, KLERG_OPT_MIXED_WARPS = 6 };
+       KLERG_OPT_EXACT_PAIRS = 5, KLERG_OPT_MIXED_WARPS = 6, KLERG_OPT_SATURATE_MILLI = 7 };
 int klerg_set_option(int key, int value);
 int klerg_get_option(int key);
 /* Two ranks on ONE GPU (tests of the exchange protocol on a single-GPU box): after klerg_emu_begin() the next

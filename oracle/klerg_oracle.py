@@ -482,6 +482,26 @@ DEFAULT_CFG = dict(
 )  # robot_config.yaml
 
 
+class OraclePrior:
+    """PriorDist (klerg.py:27-50): two fixed Gaussians over the named states, diagonal covariance, + 1e-5."""
+
+    def __init__(self, states):
+        base = "xyzrpw"
+        duck = [-0.8, -0.8, -0.15, 3.6, 0.5, 0.0]
+        ball = [0.6, 0.9, -0.15, 2.6, -0.5, 0.0]
+        cov = [0.2, 0.2, 0.5, 0.2, 0.2, 0.5]
+        pick = lambda tab, dflt: [tab[base.rfind(s)] if s in base else dflt for s in states]
+        covar = torch.diag(torch.FloatTensor(pick(cov, 1.0)))
+        self.tdists = [torch.distributions.MultivariateNormal(torch.FloatTensor(pick(m, 0.0)), covar) for m in (duck, ball)]
+        self.device = "cpu"  # the reference reads prior_dist.device (klerg.py:460) but never sets it: callers must
+
+    def pdf_torch(self, samples):
+        return torch.sum(torch.stack([d.log_prob(samples).exp() for d in self.tdists]), 0) + 1e-5
+
+    def pdf(self, x):
+        return self.pdf_torch(torch.as_tensor(x)).numpy()
+
+
 class OracleRobot:
     """Restatement of ``Robot`` (klerg.py:85-751) for the default 'Roll' policy.
 
@@ -506,6 +526,7 @@ class OracleRobot:
         self.dtype = getattr(target_dist, "dtype", torch.float32)
         torch.set_default_dtype(self.dtype)
         self.use_prior = False
+        self.prior_dist = OraclePrior(states)
         self.pybullet = pybullet
         self.robot_lim = torch.tensor(robot_lim, dtype=self.dtype)
         self.explr_idx = torch.tensor(explr_idx)
@@ -664,9 +685,23 @@ class OracleRobot:
         if save:
             self.memory_buffer.push(x.clone())
 
-    # -- klerg.py:367-407 (default flags) --
+    # -- klerg.py:342-349 --
+    def saturate_control(self, u, app_thresh=0.1):
+        return torch.tanh(u / app_thresh) * self.control_lim[:, 1]
+
+    # -- klerg.py:367-407 (optimize_samples=False) --
     def get_samples(self, n_target, n_hist):
+        if self.add_recent_history:
+            recent = self.memory_buffer.get_recent(self.horizon)
+            n_target -= len(recent)
+        if self.sample_near_current_loc:
+            n_target = int(n_target * 0.9)
         samples = self.env_sampler.sample((n_target,))
+        if self.sample_near_current_loc:  # klerg.py:181-182: Normal(0, 4 std) around the current exploration state
+            near = torch.distributions.Normal(torch.zeros_like(self.std), self.std * 4.0)
+            samples = torch.vstack([samples, near.sample((int(n_target / 0.9 * 0.1),)) + self.robot.state[self.explr_locs].clone()])
+        if self.add_recent_history:
+            samples = torch.vstack([samples, recent[:, self.explr_locs]])
         if self.test_corners:
             samples = torch.vstack([samples, self.corner_samples])
         hist = self.memory_buffer.sample(n_hist)
@@ -677,6 +712,8 @@ class OracleRobot:
         outside = ((samples < self.robot_lim[:, 0]) | (samples > self.robot_lim[:, 1])).sum(1).gt(0)
         if uniform:
             p = renormalize(self.target_dist.init_uniform_grid(samples.clone()).squeeze())
+        elif self.use_prior:  # klerg.py:459-461
+            p = renormalize(self.prior_dist.pdf_torch(samples.clone()).squeeze())
         else:
             p = self.target_dist.pdf_torch(samples.clone()).squeeze()
         if self.weight_env or self.weight_temp or plot:
@@ -770,7 +807,7 @@ class OracleRobot:
             done = True
         return tau_last, done
 
-    # -- klerg.py:489-588 (ctrlAppSearch=True, full_cost=False, fixed_lam=False, saturate=False) --
+    # -- klerg.py:489-588 (full_cost=False) --
     def kldiv_planner(self, n_target, n_hist, temp=1.0):
         samples, hist, nu = self.get_samples(n_target, n_hist)
         with torch.no_grad():
@@ -790,14 +827,22 @@ class OracleRobot:
                 q = renormalize(q_base + q_iter)
                 du, djdlam = self.backward(samples.clone(), p.clone(), q.clone(), nu, lin, traj)
                 self.n_grad_evals += 1
-                u_star = torch.clamp(u_tmp + self.alpha * du, *self.control_lim.T)
+                if self.saturate:
+                    u_star = self.saturate_control(u_tmp + self.alpha * du)
+                else:
+                    u_star = torch.clamp(u_tmp + self.alpha * du, *self.control_lim.T)
                 t_app = torch.argmin(djdlam).item()
                 if self.trace is not None:
                     self.trace.append(dict(kind="grad", idx=idx, u=u_tmp.clone(), x0=self.robot.state.clone(), traj=traj.clone(), q=q.clone(), du=du.clone(), djdlam=djdlam.clone(), dgdx=self._last_dgdx.clone(), t_app=t_app))
-                if djdlam[t_app] < 0:
-                    tau, ok = self.line_search(t_app, u_star[t_app].clone(), p.clone(), q_base.clone(), samples.clone(), idx, last_cost)
-                    if ok:
-                        u_tmp[tau[0] : tau[1]] = u_star[t_app].clone()
+                if not self.ctrlAppSearch:  # klerg.py:562-563: take the whole saturated step
+                    u_tmp = u_star
+                elif djdlam[t_app] < 0:
+                    if self.fixed_lam:  # klerg.py:553-554
+                        u_tmp[t_app : t_app + self.lam] = u_star[t_app].clone()
+                    else:
+                        tau, ok = self.line_search(t_app, u_star[t_app].clone(), p.clone(), q_base.clone(), samples.clone(), idx, last_cost)
+                        if ok:
+                            u_tmp[tau[0] : tau[1]] = u_star[t_app].clone()
                 else:
                     q, traj_samples = prev_q, prev_traj_samples
                     break

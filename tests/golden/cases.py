@@ -35,7 +35,32 @@ ROBOT_CASES = {
                        magnitude=True),
     "xy_weightenv": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=8, std=0.05, x0=[0.5, 0.5, 0, 0], weight_env=True),
     "xy_uniform": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=6, std=0.05, x0=[-0.5, 0.5, 0, 0], uniform=True),
+    # non-default robot_config.yaml flags, set on the constructed controller
+    "xy_saturate_fixedlam": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=8, std=0.05, x0=[0.4, -0.3, 0, 0],
+                                 flags=dict(saturate=True, fixed_lam=True, lam=2)),
+    "xy_noappsearch": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=8, std=0.05, x0=[-0.2, 0.6, 0, 0],
+                           flags=dict(ctrlAppSearch=False)),
+    "xyz_nearloc_recent": dict(states="xyz", D=3, horizon=12, cap=64, n=600, m=40, steps=8, std=0.08, x0=[0.3, 0.2, -0.1, 0, 0, 0],
+                               flags=dict(sample_near_current_loc=True, add_recent_history=True)),
+    "xyz_prior": dict(states="xyz", D=3, horizon=10, cap=40, n=400, m=30, steps=6, std=0.08, x0=[0.0, 0.1, 0.2, 0, 0, 0],
+                      flags=dict(use_prior=True)),
+    "xyw_plot_corners": dict(states="xyw", D=3, horizon=10, cap=50, n=400, m=30, steps=6, std=0.08, x0=[0.2, -0.4, 0.1, 0, 0, 0],
+                             plot=True, flags=dict(test_corners=True)),
 }
+
+
+def apply_case_flags(r, case):
+    """Flags the reference reads from robot_config.yaml, set on a constructed controller (reference, oracle or the
+    B200 mirror alike) together with what Robot.__init__ would have created for them (klerg.py:174-182)."""
+    if case.get("weight_env"):
+        r.weight_env, r.weight_temp = True, False
+    flags = case.get("flags", {})
+    for k, v in flags.items():
+        setattr(r, k, v)
+    if flags.get("sample_near_current_loc") and not hasattr(r, "loc_sampler"):
+        r.loc_sampler = torch.distributions.Normal(torch.zeros_like(r.std), r.std * 4.)
+    if flags.get("use_prior") and not hasattr(r.prior_dist, "device"):
+        r.prior_dist.device = "cpu"  # klerg.py:460 reads it, PriorDist never sets it
 
 LIMS = dict(x=[-1.0, 1.0], y=[-1.0, 1.0], z=[-1.0, 1.0], r=[2.39, 3.89], p=[-0.75, 0.75], w=[-2.0, 2.0])
 CTRL = dict(x=[-1.25, 1.25], y=[-1.25, 1.25], z=[-1.25, 1.25], r=[-0.5, 0.5], p=[-0.5, 0.5], w=[-1.25, 1.25])

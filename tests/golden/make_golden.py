@@ -39,7 +39,7 @@ def import_reference():
 
 
 sys.path.insert(0, HERE)
-from cases import MixtureTarget, ROBOT_CASES, robot_kwargs, seed_buffer_states  # noqa: E402
+from cases import MixtureTarget, ROBOT_CASES, apply_case_flags, robot_kwargs, seed_buffer_states  # noqa: E402
 
 
 def record_robot_case(rk, name, case):
@@ -48,8 +48,7 @@ def record_robot_case(rk, name, case):
     if case["states"] == "xyzrpw":
         target.mu[:, 3] = target.mu[:, 3] * 0.5 + 3.1
     r = rk.Robot(**robot_kwargs(case, target))
-    if case.get("weight_env"):
-        r.weight_env, r.weight_temp = True, False
+    apply_case_flags(r, case)
     out = {}
     log = []
 

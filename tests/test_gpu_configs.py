@@ -119,9 +119,20 @@ def test_config4_pose_workspace_long_history(H):
     s = setup("c4", 30_000, 2_000, H=H)
     U = wl.random_controls((3, s["H"], s["D"]), seed=5)
     got = s["ctx"].costs(U.to(s["dev"])).cpu()
+    ctx = s["ctx"]
+    bar_gpu = s["engine"].rollout(ctx.dyn, ctx.bar, ctx.x0, U.to(s["dev"]), R0=ctx.R0)["barrier"].cpu()
     for b in range(3):
+        s["oracle"].trace = []
         want = s["oracle"].get_cost(s["samples"], s["p"].clone(), s["q_base"], U[b])
+        dkl = float(s["oracle"].trace[-1]["dkl"])
         close(got[b], want.reshape(()), rtol=5e-4, what=f"cost {b}")  # quartic barrier amplifies the fp32 matrix_exp difference
+        # ... and only the barrier: the KL term alone (cost minus the wall barrier of the same rollout) holds the 1e-4 of
+        # the north_star; the absolute term covers the fp32 subtraction of the two parts
+        np.testing.assert_allclose(float(got[b]) - float(bar_gpu[b]), dkl, rtol=1e-4, atol=5e-7 * abs(float(want)),
+                                   err_msg=f"KL part of cost {b}")
+        np.testing.assert_allclose(float(bar_gpu[b]), float(want) - dkl, rtol=2e-3, atol=5e-7 * abs(float(want)),
+                                   err_msg=f"barrier part of cost {b}")
+    s["oracle"].trace = None
     g = s["ctx"].gradient(U[0].to(s["dev"]))
     du, dj = oracle_grad(s["oracle"], s["samples"], s["p"], s["q_base"], U[0])
     close(g["du"], du, rtol=RTOL, atol_frac=5e-5, what="du")

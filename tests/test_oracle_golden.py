@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from cases import ROBOT_CASES, MixtureTarget, robot_kwargs, seed_buffer_states
+from cases import ROBOT_CASES, MixtureTarget, apply_case_flags, robot_kwargs, seed_buffer_states
 from oracle import klerg_oracle as ko
 
 RT = 2e-6
@@ -101,8 +101,7 @@ def build_oracle_robot(name):
     if case["states"] == "xyzrpw":
         target.mu[:, 3] = target.mu[:, 3] * 0.5 + 3.1
     r = ko.OracleRobot(**robot_kwargs(case, target))
-    if case.get("weight_env"):
-        r.weight_env, r.weight_temp = True, False
+    apply_case_flags(r, case)
     r.test(case["n"])
     for s in seed_buffer_states(r.robot.state, case):
         r.memory_buffer.push(s)
