@@ -632,33 +632,116 @@ def fused_fault():
 _RNG_LEFT, _RNG_NEXT, _RNG_STATE, _RNG_WORDS = 8, 16, 24, 624
 
 
-def device_uniform(n_rows, low, high, row_lo=0, row_hi=None, device=None):
-    """``Uniform(low, high).sample((n_rows,))`` of torch's CPU default generator, drawn ON THE DEVICE from the
-    generator's own state (klerg_mt19937_uniform): bit-exact samples, and the host generator is left where the host
-    draw would have left it.  Returns rows [row_lo, row_hi) as a CUDA tensor [rows, D]."""
+def _rng_fields(raw):
     import numpy as np
-    dev = device or _dev()
-    low = torch.as_tensor(low, dtype=torch.float32).reshape(-1)
-    span = torch.as_tensor(high, dtype=torch.float32).reshape(-1) - low  # fp32, as Uniform.rsample computes it
-    D = low.numel()
-    row_hi = n_rows if row_hi is None else row_hi
-    blob = torch.get_rng_state()
-    raw = blob.numpy()
     left = int(raw[_RNG_LEFT:_RNG_LEFT + 4].view(np.int32)[0])
     nxt = int(raw[_RNG_NEXT:_RNG_NEXT + 8].view(np.uint64)[0])
     words = torch.from_numpy(raw[_RNG_STATE:_RNG_STATE + 8 * _RNG_WORDS].view(np.uint64).astype(np.uint32).view(np.int32))
-    st_in = words.to(dev, non_blocking=True)
-    st_out = torch.empty(_RNG_WORDS + 2, dtype=torch.int32, device=dev)
-    out = torch.empty((max(row_hi - row_lo, 0), D), dtype=torch.float32, device=dev)
-    cabi.check(cabi.load().klerg_mt19937_uniform(
-        cabi.ptr(st_in), left, nxt, int(n_rows), D, cabi.farr(low.tolist()), cabi.farr(span.tolist()), int(row_lo),
-        int(row_hi), cabi.ptr(out) if out.numel() else None, cabi.ptr(st_out), cabi.stream_ptr()), "klerg_mt19937_uniform")
-    back = st_out.cpu().numpy().view(np.uint32)  # one small D2H: the host generator continues from here
+    return left, nxt, words
+
+
+def _rng_set_from(raw, back):
+    """Put the state words the kernel handed back (624 words, left, next) into torch's CPU generator."""
+    import numpy as np
     new = raw.copy()
     new[_RNG_LEFT:_RNG_LEFT + 4] = np.array([back[_RNG_WORDS]], dtype=np.int32).view(np.uint8)
     new[_RNG_NEXT:_RNG_NEXT + 8] = np.array([back[_RNG_WORDS + 1]], dtype=np.uint64).view(np.uint8)
     new[_RNG_STATE:_RNG_STATE + 8 * _RNG_WORDS] = back[:_RNG_WORDS].astype(np.uint64).view(np.uint8)
     torch.set_rng_state(torch.from_numpy(new))
+
+
+def _enqueue_uniform(blob, n_rows, low, span, row_lo, row_hi, dev):
+    """klerg_mt19937_uniform on the current stream from the generator state ``blob`` -> (rows, advanced state words)."""
+    left, nxt, words = _rng_fields(blob.numpy())
+    st_in = words.to(dev, non_blocking=True)
+    st_out = torch.empty(_RNG_WORDS + 2, dtype=torch.int32, device=dev)
+    out = torch.empty((max(row_hi - row_lo, 0), low.numel()), dtype=torch.float32, device=dev)
+    cabi.check(cabi.load().klerg_mt19937_uniform(
+        cabi.ptr(st_in), left, nxt, int(n_rows), low.numel(), cabi.farr(low.tolist()), cabi.farr(span.tolist()), int(row_lo),
+        int(row_hi), cabi.ptr(out) if out.numel() else None, cabi.ptr(st_out), cabi.stream_ptr()), "klerg_mt19937_uniform")
+    return out, st_out
+
+
+def _dev_index(dev):
+    dev = torch.device(dev)
+    return torch.cuda.current_device() if dev.index is None else dev.index
+
+
+class UniformPrefetch:
+    """The NEXT step's workspace draw, enqueued speculatively on a side stream from the generator state the current
+    step leaves behind.  The draw of step k+1 is a pure function of (generator state, row count, box); if the next
+    call finds torch's generator exactly where this one expected it (byte comparison of the 5 KB state) and asks for
+    the same draw, the rows are already there and the generator jumps to the recorded end state - bit for bit what
+    the in-line draw would have produced.  Anything else (another consumer of the generator in between, a different
+    sample count or box) discards the speculation.  One serial CTA draws 6e7 numbers in 44 ms: this takes it off the
+    critical path of Robot.step() (it overlaps the history pass of the step before)."""
+
+    def __init__(self):
+        self.pending = None
+        self.stream = None
+        self.back = None
+        self.hits = self.misses = 0
+
+    def launch(self, n_rows, low, high, row_lo, row_hi, device):
+        dev = device or _dev()
+        low = torch.as_tensor(low, dtype=torch.float32).reshape(-1)
+        span = torch.as_tensor(high, dtype=torch.float32).reshape(-1) - low
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(device=dev)
+        if self.pending is not None:  # an unconsumed speculation: let it finish before its hand-back buffer is reused
+            self.pending["ev"].synchronize()
+            self.pending = None
+        blob = torch.get_rng_state()
+        main = torch.cuda.current_stream(dev)
+        self.stream.wait_stream(main)  # not before what is already enqueued (keeps allocator reuse simple)
+        with torch.cuda.stream(self.stream):
+            out, st_out = _enqueue_uniform(blob, n_rows, low, span, row_lo, row_hi, dev)
+            if self.back is None:
+                self.back = torch.empty(_RNG_WORDS + 2, dtype=torch.int32, pin_memory=True)
+            back = self.back  # one speculation in flight at a time: take() or the next launch() has consumed the last
+            back.copy_(st_out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending = dict(key=(int(n_rows), tuple(low.tolist()), tuple(span.tolist()), int(row_lo), int(row_hi), _dev_index(dev)),
+                            blob=blob, out=out, st_out=st_out, back=back, ev=ev)
+
+    def take(self, n_rows, low, span, row_lo, row_hi, dev):
+        p, self.pending = self.pending, None
+        if p is None:
+            return None
+        key = (int(n_rows), tuple(low.tolist()), tuple(span.tolist()), int(row_lo), int(row_hi), _dev_index(dev))
+        if p["key"] != key or not torch.equal(torch.get_rng_state(), p["blob"]):
+            self.misses += 1
+            p["ev"].synchronize()  # let the speculative kernel finish before its buffers go back to the allocator
+            return None
+        import numpy as np
+        p["ev"].synchronize()
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(p["ev"])
+        p["out"].record_stream(main)
+        _rng_set_from(p["blob"].numpy(), p["back"].numpy().view(np.uint32))
+        self.hits += 1
+        return p["out"]
+
+
+def device_uniform(n_rows, low, high, row_lo=0, row_hi=None, device=None, prefetch=None):
+    """``Uniform(low, high).sample((n_rows,))`` of torch's CPU default generator, drawn ON THE DEVICE from the
+    generator's own state (klerg_mt19937_uniform): bit-exact samples, and the host generator is left where the host
+    draw would have left it.  Returns rows [row_lo, row_hi) as a CUDA tensor [rows, D].  ``prefetch``: a
+    UniformPrefetch that may already hold exactly this draw."""
+    import numpy as np
+    dev = device or _dev()
+    low = torch.as_tensor(low, dtype=torch.float32).reshape(-1)
+    span = torch.as_tensor(high, dtype=torch.float32).reshape(-1) - low  # fp32, as Uniform.rsample computes it
+    row_hi = n_rows if row_hi is None else row_hi
+    if prefetch is not None:
+        got = prefetch.take(n_rows, low, span, row_lo, row_hi, dev)
+        if got is not None:
+            return got
+    blob = torch.get_rng_state()
+    out, st_out = _enqueue_uniform(blob, n_rows, low, span, row_lo, row_hi, dev)
+    back = st_out.cpu().numpy().view(np.uint32)  # one small D2H: the host generator continues from here
+    _rng_set_from(blob.numpy(), back)
     return out
 
 

@@ -383,13 +383,16 @@ class Robot(object):
                 self.loc_sampler = torch.distributions.Normal(torch.zeros_like(self.std), self.std * 4.)
             return [self.loc_sampler.sample((n_near,)) + self.robot.state[self.explr_locs].clone()]
 
-        if self._device_draw_ok():
+        if self._device_draw_ok() and num_target_samples * len(self.explr_idx) >= self.device_draw_min_numbers:
             # the same draw, continued on the device from the host generator's state (bit-exact samples, the host
             # generator ends where the host draw would have left it - device_uniform returns after handing the
             # state back): no 4*N*D-byte host pass and copy per step
             lo, hi = self.group.shard_bounds(n_total)
-            parts = [engine.device_uniform(num_target_samples, self.env_sampler.low, self.env_sampler.high,
-                                           min(lo, num_target_samples), min(hi, num_target_samples), self.cuda)]
+            draw = (num_target_samples, self.env_sampler.low, self.env_sampler.high,
+                    min(lo, num_target_samples), min(hi, num_target_samples), self.cuda)
+            if self.prefetch_draw and self._prefetch is None:
+                self._prefetch = engine.UniformPrefetch()
+            parts = [engine.device_uniform(*draw, prefetch=self._prefetch if self.prefetch_draw else None)]
             off = num_target_samples
             for e in near_current() + fixed:  # appended rows that fall into this rank's slice
                 a, b = max(lo, off) - off, min(hi, off + len(e)) - off
@@ -404,9 +407,28 @@ class Robot(object):
                 samples = torch.vstack([samples] + extras)
         hist_dev, hist_idx = self.memory_buffer.sample_device(num_traj_samples)
         self.last_hist_idx = hist_idx
+        # The generator now stands where the next step's draw will find it (unless somebody else draws in between):
+        # enqueue that draw speculatively.  Large workspaces at once - one serial CTA, it overlaps this step's history
+        # pass; small ones after the plan came back (_after_plan), so that the side kernel never delays this step.
+        self._next_draw = None
+        if self.prefetch_draw and isinstance(samples, DeviceSamples):
+            self._next_draw = draw
+            if num_target_samples * len(self.explr_idx) >= self.prefetch_early_numbers:
+                self._after_plan()
         return samples, hist_dev, torch.ones(1)
 
+    prefetch_draw = True              # speculative draw of the next step's samples (engine.UniformPrefetch)
+    prefetch_early_numbers = 2_000_000  # from this many numbers per draw the speculation starts before the history pass
+    _prefetch = None
+    _next_draw = None
+
+    def _after_plan(self):
+        draw, self._next_draw = self._next_draw, None
+        if draw is not None and self._prefetch is not None:
+            self._prefetch.launch(*draw)
+
     device_rng = True  # draw the workspace samples on the device when nothing needs them on the host
+    device_draw_min_numbers = 16_384  # below this the host draw + copy is cheaper than the state hand-over (config 1)
 
     def _device_draw_ok(self):
         """The samples can stay on the device when the target density is evaluated there and no plot data (host
@@ -610,6 +632,7 @@ class Robot(object):
             wrapped = getattr(self, "_wrapped_target", None)
             if wrapped is not None:
                 wrapped.check_fault()  # a timed-out wait inside the decoder kernel must not pass silently
+            self._after_plan()
 
     device_loop = True  # run the optimisation loop on the device (one D2H per step) unless plot data is kept
 
@@ -633,6 +656,7 @@ class Robot(object):
         wrapped = getattr(self, "_wrapped_target", None)
         if wrapped is not None:
             wrapped.check_fault()
+        self._after_plan()
 
     # ------------------------------------------------------------------ plots (klerg.py:602-682)
     @torch.no_grad()

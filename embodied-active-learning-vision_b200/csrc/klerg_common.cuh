@@ -11,7 +11,7 @@ namespace klerg {
 // HEAD: [misc counters 64 x int][misc partials MAXBLK x 8 doubles]
 //       [gradient partials GRAD_MAXBLK x MAX_H*MAX_D doubles][fused-eval region, see FUSED_*]
 // then one SEG record per segment g: [counter + pad 64 B][MAXBLK x 2 doubles]
-constexpr int MAXBLK = 1184;      // 148 SMs x 8
+constexpr int MAXBLK = 9472;      // 148 SMs x 64
 constexpr int GRAD_MAXBLK = 296;  // 148 SMs x 2
 constexpr size_t HEAD_COUNTERS = 256;
 constexpr size_t HEAD_MISC = (size_t)MAXBLK * 8 * sizeof(double);

@@ -269,7 +269,11 @@ static int launch_footprint_spt(const FootArgs& a0, cudaStream_t stream) {
   int64_t gx = a.ntiles < 1 ? 1 : a.ntiles;
   int64_t gy = a.G;
   if (gy > 65535) gy = 65535;
-  const int64_t cap = (int64_t)sms * 8 < MAXBLK ? (int64_t)sms * 8 : MAXBLK;
+  // One or two tiles per CTA at the large sizes (1e7 samples = 9766 tiles): the hardware hands CTAs to SMs as they
+  // free up, so an SM that is slower (it hosts the side-stream draw of the next step, engine.UniformPrefetch) simply
+  // takes fewer, and the tail is one tile, not 1/8 of an SM's share (a static 8 CTAs per SM left ~8 % of the pass
+  // to wave quantisation: 9766 tiles over 1184 CTAs are 8 or 9 tiles each).
+  const int64_t cap = (int64_t)sms * 64 < MAXBLK ? (int64_t)sms * 64 : MAXBLK;
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)gy);
   if (spt == 4)

@@ -59,3 +59,46 @@ def test_robot_sequences_identical_with_device_draw():
     for (x0, v0, c0), (x1, v1, c1) in zip(ra, rb):
         assert np.array_equal(x0, x1) and np.array_equal(v0, v1) and np.array_equal(c0, c1)
     assert torch.equal(ua, ub) and torch.equal(ia, ib) and torch.equal(sa, sb)
+    assert r._prefetch is not None and r._prefetch.hits == 3 and r._prefetch.misses == 0  # steps 2..4 found their draw waiting
+
+
+def test_speculative_draw_hits_and_misses():
+    """engine.UniformPrefetch: the next draw enqueued ahead of time is used only if the generator is found exactly where
+    the speculation started and the same draw is asked for; either way samples and generator equal the host draw."""
+    from control_torch import engine
+    low, high = torch.tensor([-1.0, 0.0, 2.0]), torch.tensor([1.0, 0.5, 4.0])
+    dev = torch.device("cuda")
+    pf = engine.UniformPrefetch()
+
+    def host(n):
+        state = torch.get_rng_state()
+        want = torch.distributions.Uniform(low, high).sample((n,))
+        after = torch.get_rng_state()
+        torch.set_rng_state(state)
+        return want, after
+
+    torch.manual_seed(21)
+    # hit
+    want, after = host(5000)
+    pf.launch(5000, low, high, 0, 5000, dev)
+    got = engine.device_uniform(5000, low, high, prefetch=pf)
+    assert (pf.hits, pf.misses) == (1, 0)
+    assert torch.equal(got.cpu(), want) and torch.equal(torch.get_rng_state(), after)
+    # somebody else consumed the generator in between: the speculation is dropped, the in-line draw runs
+    pf.launch(5000, low, high, 0, 5000, dev)
+    torch.rand(3)
+    want, after = host(5000)
+    got = engine.device_uniform(5000, low, high, prefetch=pf)
+    assert (pf.hits, pf.misses) == (1, 1)
+    assert torch.equal(got.cpu(), want) and torch.equal(torch.get_rng_state(), after)
+    # a different row count, a different row range
+    for args in ((4999, 0, 4999), (5000, 100, 4000)):
+        pf.launch(5000, low, high, 0, 5000, dev)
+        want, after = host(args[0])
+        got = engine.device_uniform(args[0], low, high, args[1], args[2], prefetch=pf)
+        assert torch.equal(got.cpu(), want[args[1]:args[2]]) and torch.equal(torch.get_rng_state(), after)
+    assert (pf.hits, pf.misses) == (1, 3)
+    # nothing pending
+    want, after = host(10)
+    assert torch.equal(engine.device_uniform(10, low, high, prefetch=pf).cpu(), want)
+    assert (pf.hits, pf.misses) == (1, 3)
