@@ -641,7 +641,12 @@ class Robot(object):
         the same evals in the same order as the host loop below, one packed read-back instead of two per iteration."""
         H, A = self.horizon, self.planner.num_actions
         u_dev = self.u.to(self.cuda, non_blocking=True).reshape(H, A).contiguous()
-        pack = ctx.optimize(u_dev, self.num_iters_per_step, self.fixed_lam, getattr(self, "lam", 1)).cpu()
+        pack_dev = ctx.optimize(u_dev, self.num_iters_per_step, self.fixed_lam, getattr(self, "lam", 1))
+        # the next step's speculative draw is enqueued while the loop runs: its side stream waits for everything
+        # enqueued so far, so the draw kernel starts after the loop, and the host pays for the launch while it would
+        # otherwise sit in the read-back below
+        self._after_plan()
+        pack = pack_dev.cpu()
         if pack[1] != 0:
             raise RuntimeError("klerg_plan_optimize: an in-kernel wait timed out (lost peer or a launch that was not "
                                "co-resident); the plan of this step is void")

@@ -658,6 +658,193 @@ extern "C" int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x,
   return check_launch("barrier_eval_kernel");
 }
 
+// ---------------------------------------------------------------------------
+// State-feedback default policies (default_policies.py:53-119): the closed loop is serial in t (u_t depends on x_t),
+// so one warp steps it; H <= 256 steps of a <= 24-state model are a few microseconds.
+// ---------------------------------------------------------------------------
+struct PolicyDev {
+  int kind, use_u;
+  float weight;
+  float K[KLERG_MAX_A * KLERG_MAX_S];
+};
+
+__global__ void __launch_bounds__(32) policy_rollout_kernel(const DynDev d, const PolicyDev pol, const float* __restrict__ x0,
+                                                            const float* __restrict__ R0, const float* __restrict__ u_in,
+                                                            int H, float* __restrict__ u_eff, float* __restrict__ dmudx) {
+  __shared__ float x[KLERG_MAX_S], u[KLERG_MAX_A], Rm[9];
+  const int lane = threadIdx.x, S = d.S, A = d.A;
+  const bool single = d.kind == KLERG_DYN_SINGLE, roll = d.kind == KLERG_DYN_ROLL;
+  const float dt = d.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
+  if (lane < S) x[lane] = x0[lane];
+  __syncwarp();
+  if (roll && lane == 0) {
+    if (R0) {
+      for (int i = 0; i < 9; ++i) Rm[i] = R0[i];
+    } else {
+      float rot[3];
+      for (int k = 0; k < 3; ++k) {
+        rot[k] = x[d.rpw[k]];
+        if (d.has_map) rot[k] = affine_map(rot[k], d.rot_lo[k], d.rot_hi[k], d.ang_lo[k], d.ang_hi[k]);
+      }
+      euler_xyz_to_matrix(rot, Rm);
+    }
+  }
+  __syncwarp();
+  for (int t = 0; t < H; ++t) {
+    // u_t = policy(x_t), dmudx_t
+    for (int e = lane; e < A * S; e += 32) dmudx[(size_t)t * A * S + e] = pol.kind == KLERG_POLICY_LQR ? -pol.K[e] : 0.f;
+    __syncwarp();
+    if (lane < A) {
+      float ui;
+      if (pol.kind == KLERG_POLICY_LQR) {
+        ui = 0.f;
+        for (int j = 0; j < S; ++j) ui = fmaf(pol.K[lane * S + j], x[j], ui);  // (K @ x)_i, then negated
+        ui = -ui;
+      } else {
+        ui = pol.use_u ? u_in[t * A + lane] : 0.f;
+        if (!single) {
+          const float p = x[lane], v = x[A + lane];
+          if ((p >= 1.f && v > 0.f) || (p <= -1.f && v < 0.f)) {
+            ui = -pol.weight * v;
+            dmudx[(size_t)t * A * S + lane * S + A + lane] = -pol.weight;
+          }
+        }
+      }
+      u[lane] = ui;
+      u_eff[t * A + lane] = ui;
+    }
+    __syncwarp();
+    // one exact RK4 step of the integrator model (dynamics.py:7-13,58-65; A nilpotent) + the rotation update
+    float E[9], Rn[9];
+    if (roll && lane == 0) {
+      float w3[3];
+      for (int k = 0; k < 3; ++k) w3[k] = x[A + d.rpw[k]];  // pre-step angular velocity (dynamics.py:270-272)
+      rodrigues(w3, dt, E);
+      matmul3(E, Rm, Rn);
+    }
+    __syncwarp();
+    if (lane < A) {
+      if (single) {
+        x[lane] = fmaf(dt, u[lane], x[lane]);
+      } else {
+        const float v = x[A + lane];
+        x[lane] = x[lane] + c1 * v + c2 * u[lane];
+        x[A + lane] = fmaf(dt, u[lane], v);
+      }
+    }
+    __syncwarp();
+    if (roll && lane == 0) {
+      float rot[3];
+      wrapped_euler_xyz(Rn, rot);
+      for (int k = 0; k < 3; ++k) {
+        float v = rot[k];
+        if (d.has_map) v = affine_map(v, d.ang_lo[k], d.ang_hi[k], d.rot_lo[k], d.rot_hi[k]);
+        x[d.rpw[k]] = v;
+      }
+      for (int i = 0; i < 9; ++i) Rm[i] = Rn[i];
+    }
+    __syncwarp();
+  }
+}
+
+struct AdjPolicyArgs {
+  DynDev d;
+  AdjParams ap;
+  int H;
+  const float *dgdx, *dbarr, *P, *dmudx, *u;
+  float *du, *djdlam, *u_star;
+};
+
+// rho_H = 0; t = H-1..0: rho <- rk4(rho' = g_t - (A_t + B dmudx_t)^T rho, step -dt) (klerg.py:433-450, 590-593 with
+// dynamics.py:7-13), lane j holds rho_j; du_t = -Rinv B^T rho, djdlam_t = rho B du_t, u* as in adjoint_block.
+__global__ void __launch_bounds__(32) adjoint_policy_kernel(const AdjPolicyArgs a) {
+  __shared__ float M[KLERG_MAX_S * KLERG_MAX_S];  // closed-loop A_t + B dmudx_t, row-major [S][S]
+  __shared__ float s_du[KLERG_MAX_A], s_btr[KLERG_MAX_A];
+  const int lane = threadIdx.x, S = a.d.S, A = a.d.A;
+  const bool single = a.d.kind == KLERG_DYN_SINGLE;
+  const float h = -a.d.dt;
+  float rho = 0.f;
+  for (int t = a.H - 1; t >= 0; --t) {
+    for (int e = lane; e < S * S; e += 32) {
+      const int r = e / S, c = e - r * S;
+      float m = 0.f;
+      if (!single) {
+        if (r < A && c >= A) m = a.P ? a.P[(size_t)t * A * A + r * A + (c - A)] : (c - A == r ? 0.8f : 0.f);
+        if (r >= A) m = a.dmudx[(size_t)t * A * S + (r - A) * S + c];  // B = [0; I]
+      } else {
+        m = a.dmudx[(size_t)t * A * S + e];  // A = 0, B = I
+      }
+      M[e] = m;
+    }
+    __syncwarp();
+    const float g = lane < S ? a.dgdx[t * S + lane] - a.dbarr[t * S + lane] : 0.f;
+    auto f = [&](float r) {  // g - M^T r, every lane its own component
+      float acc = 0.f;
+      for (int i = 0; i < S; ++i) acc = fmaf(M[i * S + (lane < S ? lane : 0)], __shfl_sync(0xffffffffu, r, i), acc);
+      return g - acc;
+    };
+    const float k1 = h * f(rho);
+    const float k2 = h * f(rho + k1 / 2.f);
+    const float k3 = h * f(rho + k2 / 2.f);
+    const float k4 = h * f(rho + k3);
+    rho = lane < S ? rho + (1.f / 6.f) * (k1 + 2.f * k2 + 2.f * k3 + k4) : 0.f;
+    // B^T rho: the velocity half (DOUBLE / ROLL) or rho itself (SINGLE)
+    const float btr = __shfl_sync(0xffffffffu, rho, single ? (lane < A ? lane : 0) : (lane < A ? A + lane : 0));
+    if (lane < A) {
+      const float dui = -a.ap.rinv[lane] * btr;
+      s_du[lane] = dui;
+      s_btr[lane] = btr;
+      a.du[t * A + lane] = dui;
+      const float us = a.u[t * A + lane] + a.ap.alpha * dui;
+      a.u_star[t * A + lane] = a.ap.sat > 0.f ? tanhf(us / a.ap.sat) * a.ap.chi[lane] : fminf(fmaxf(us, a.ap.clo[lane]), a.ap.chi[lane]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float dj = 0.f;
+      for (int i = 0; i < A; ++i) dj += s_btr[i] * s_du[i];
+      a.djdlam[t] = dj;
+    }
+    __syncwarp();
+  }
+}
+
+static bool make_policy(const klerg_policy_spec* s, const DynDev& d, PolicyDev& p) {
+  if (!s) { set_error("policy spec is null"); return false; }
+  if (s->kind != KLERG_POLICY_LQR && s->kind != KLERG_POLICY_BARRIER_PUSH) { set_error("policy spec: unknown kind %d", s->kind); return false; }
+  if (d.kind == KLERG_DYN_SPEED) { set_error("state-feedback policies: the speed-state model is not supported"); return false; }
+  p.kind = s->kind; p.use_u = s->use_u; p.weight = s->weight;
+  for (int e = 0; e < KLERG_MAX_A * KLERG_MAX_S; ++e) p.K[e] = e < d.A * d.S ? s->K[e] : 0.f;
+  return true;
+}
+
+extern "C" int klerg_policy_rollout(const klerg_dyn_spec* dyn, const klerg_policy_spec* pol, const float* x0, const float* R0,
+                                    const float* u_in, int64_t H, float* u_eff, float* dmudx, void* stream) {
+  DynDev d;
+  PolicyDev p;
+  if (!make_dyn(dyn, d) || !make_policy(pol, d, p)) return -1;
+  if (H < 1 || H > KLERG_MAX_H) { set_error("policy_rollout: H out of range"); return -1; }
+  if (!x0 || !u_eff || !dmudx || (p.kind == KLERG_POLICY_BARRIER_PUSH && p.use_u && !u_in)) { set_error("policy_rollout: null argument"); return -1; }
+  policy_rollout_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d, p, x0, R0, u_in, (int)H, u_eff, dmudx);
+  return check_launch("policy_rollout_kernel");
+}
+
+extern "C" int klerg_adjoint_policy(const klerg_dyn_spec* dyn, int64_t H, const float* dgdx, const float* dbarr, const float* P,
+                                    const float* dmudx, const float* u, const float* Rinv_diag, float alpha,
+                                    const float* ctrl_lo, const float* ctrl_hi, float* du, float* djdlam, float* u_star,
+                                    void* stream) {
+  AdjPolicyArgs a{};
+  if (!make_dyn(dyn, a.d)) return -1;
+  if (a.d.kind == KLERG_DYN_SPEED) { set_error("adjoint_policy: the speed-state model is not supported"); return -1; }
+  if (H < 1 || H > KLERG_MAX_H) { set_error("adjoint_policy: H out of range"); return -1; }
+  if (!dgdx || !dbarr || !dmudx || !u || !du || !djdlam || !u_star || !Rinv_diag || !ctrl_lo || !ctrl_hi) { set_error("adjoint_policy: null argument"); return -1; }
+  a.H = (int)H; a.dgdx = dgdx; a.dbarr = dbarr; a.P = P; a.dmudx = dmudx; a.u = u; a.du = du; a.djdlam = djdlam; a.u_star = u_star;
+  a.ap.alpha = alpha;
+  a.ap.sat = 1e-3f * (float)g_saturate_milli;
+  for (int i = 0; i < a.d.A; ++i) { a.ap.rinv[i] = Rinv_diag[i]; a.ap.clo[i] = ctrl_lo[i]; a.ap.chi[i] = ctrl_hi[i]; }
+  adjoint_policy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("adjoint_policy_kernel");
+}
+
 static int launch_adjoint(const klerg_dyn_spec* dyn, const klerg_kernel_spec* k, int64_t H, const double* grad_part,
                           int world, int64_t K, int64_t gp_stride, const float* dbarr, const float* P, const float* traj,
                           const float* u, const float* Rinv_diag, float alpha, const float* ctrl_lo, const float* ctrl_hi,

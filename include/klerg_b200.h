@@ -202,6 +202,33 @@ int klerg_rollout(const klerg_dyn_spec* dyn, const klerg_barrier_spec* bar, cons
                   const float* R0, const float* u, int64_t B, int64_t H, float* traj,
                   float* barrier_sum, float* dbarr, float* P, float* R_out, void* stream);
 
+/* ---- a20/a22: state-feedback default policies (default_policies.py:53-119) ----
+ * Robot.forward (klerg.py:409-431) evaluates u_t = policy(x_t) while it rolls the planner out; with the Roll / Zero
+ * policies that is the stored plan and dmu/dx = 0 (every other entry point of this header).  BarrierPush and LQR
+ * feed the state back:
+ *   KLERG_POLICY_LQR           u_t = -K x_t, dmu/dx = -K                              (default_policies.py:100-119)
+ *   KLERG_POLICY_BARRIER_PUSH  u_t = u_in[t] (use_u != 0) or 0, then for every position i with
+ *                              (x_i >= 1 and v_i > 0) or (x_i <= -1 and v_i < 0): u_i = -weight v_i,
+ *                              dmu_i/dv_i = -weight                                   (default_policies.py:53-97)
+ * klerg_policy_rollout runs the closed loop (serial in t: one warp) and returns the controls it applied,
+ * u_eff [H][A], and dmudx [H][A][S]; the open-loop entry points then take u_eff (same trajectory), and
+ * klerg_adjoint_policy is the adjoint sweep of klerg.py:433-450 with the closed-loop linearisation
+ * rho' = dgdx_t - dbarr_t - (A_t + B dmudx_t)^T rho, one RK4 step of -dt per t (SINGLE, DOUBLE and ROLL models). */
+enum { KLERG_POLICY_LQR = 1, KLERG_POLICY_BARRIER_PUSH = 2 };
+typedef struct klerg_policy_spec {
+  int32_t kind;
+  int32_t use_u;                        /* BARRIER_PUSH: replay u_in (iter_idx > 0) or start from zeros        */
+  float weight;                         /* BARRIER_PUSH: 5 in the reference                                   */
+  float K[KLERG_MAX_A * KLERG_MAX_S];   /* LQR gain, row-major [A][S]                                         */
+} klerg_policy_spec;
+int klerg_policy_rollout(const klerg_dyn_spec* dyn, const klerg_policy_spec* pol, const float* x0, const float* R0,
+                         const float* u_in, int64_t H, float* u_eff, float* dmudx, void* stream);
+/* dgdx, dbarr [H][S]; P [H][A*A] or NULL (0.8 I); dmudx [H][A][S]; u [H][A] = u_eff.  Host arrays as klerg_adjoint. */
+int klerg_adjoint_policy(const klerg_dyn_spec* dyn, int64_t H, const float* dgdx, const float* dbarr, const float* P,
+                         const float* dmudx, const float* u, const float* Rinv_diag, float alpha,
+                         const float* ctrl_lo, const float* ctrl_hi, float* du, float* djdlam, float* u_star,
+                         void* stream);
+
 /* barr(x_t) and dbarr(x_t) for T rows of S floats (barrier.py:70-87). */
 int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x, int64_t T, int32_t S,
                        float* value, float* grad, void* stream);
