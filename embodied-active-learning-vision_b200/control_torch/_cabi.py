@@ -52,6 +52,13 @@ OPT_EVAL_OVERLAP, OPT_GRID_LIMIT, OPT_PDL, OPT_COOP_WITH_PDL, OPT_EXACT_PAIRS, O
 OPT_SATURATE_MILLI = 7
 
 
+POLICY_LQR, POLICY_BARRIER_PUSH = 1, 2
+
+
+class PolicySpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("use_u", C.c_int32), ("weight", C.c_float), ("K", C.c_float * (8 * 24))]
+
+
 class BarrierSpec(C.Structure):
     _fields_ = [("n", C.c_int32), ("lo", C.c_float * MAX_S), ("hi", C.c_float * MAX_S),
                 ("weight", C.c_float * MAX_S), ("power", C.c_float * MAX_S)]
@@ -126,6 +133,9 @@ SIGNATURES = {
     "klerg_target_stage3": [_P, _I64, _P, C.c_int, _F, _F, _P, _P, _P, _P],
     "klerg_rollout": [_DS, _BS, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P],
     "klerg_barrier_eval": [_BS, _P, _I64, _I32, _P, _P, _P],
+    "klerg_policy_rollout": [_DS, C.POINTER(PolicySpec), _P, _P, _P, _I64, _P, _P, _P],
+    "klerg_adjoint_policy": [_DS, _I64, _P, _P, _P, _P, _P, C.POINTER(C.c_float), _F, C.POINTER(C.c_float),
+                             C.POINTER(C.c_float), _P, _P, _P, _P],
     "klerg_adjoint": [_DS, _KS, _I64, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float), _F,
                       C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P, _P, _P],
     "klerg_adjoint_targets": [_DS, _KS, _I64, _I64, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_float), _F,
@@ -254,6 +264,18 @@ def dyn_spec(kind, S, A, dt, rpw=(0, 0, 0), ang_map=None):
             d.rot_lo[i], d.rot_hi[i] = float(rot[i][0]), float(rot[i][1])
             d.ang_lo[i], d.ang_hi[i] = float(ang[i][0]), float(ang[i][1])
     return d
+
+
+def policy_spec(kind, use_u=0, weight=0.0, K=None):
+    p = PolicySpec()
+    p.kind, p.use_u, p.weight = int(kind), int(bool(use_u)), float(weight)
+    if K is not None:
+        flat = [float(v) for row in K for v in row]
+        if len(flat) > MAX_A * MAX_S:
+            raise ValueError("policy gain larger than KLERG_MAX_A x KLERG_MAX_S")
+        for i, v in enumerate(flat):
+            p.K[i] = v
+    return p
 
 
 def barrier_spec(lo, hi, weight, power):

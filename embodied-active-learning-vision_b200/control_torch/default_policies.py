@@ -1,8 +1,8 @@
 """Default policies of the planner (reference control_torch/default_policies.py).
 
-Only control-sequence bookkeeping lives here (no arithmetic).  ``Roll`` (default)
-and ``Zero`` have dmu/dx = 0, which the device adjoint sweep assumes;
-``BarrierPush`` and ``LQR`` are not ported (never enabled by the shipped configs).
+``Roll`` (default) and ``Zero`` are control-sequence bookkeeping with dmu/dx = 0, which the fused evals assume.
+``BarrierPush`` and ``LQR`` feed the state back: the planner evaluates their closed loop and the adjoint with
+dmu/dx on the device (klerg_policy_rollout / klerg_adjoint_policy), the classes carry the parameters.
 """
 import torch
 
@@ -51,14 +51,91 @@ class Zero(Roll):
             return torch.zeros(self.num_actions, dtype=self.dtype)
 
 
-def _not_ported(name):
-    class _Missing:
-        def __init__(self, *a, **k):
-            raise NotImplementedError(f"default policy {name!r} is not ported to the B200 controller "
-                                      "(its dmu/dx != 0 needs the general adjoint); use Roll or Zero")
-    _Missing.__name__ = name
-    return _Missing
+class BarrierPush(torch.nn.Module):
+    """Replay the plan (iterations after the first) or start from zeros, and push back with -weight * velocity
+    wherever a position sits on its +-1 wall moving outwards (reference default_policies.py:53-97).  The planner
+    evaluates the closed loop on the device (klerg_policy_rollout); ``__call__`` / ``dx`` are the same rule on host
+    tensors for callers that step the policy themselves."""
+    feedback = True
+
+    def __init__(self, model, horizon):
+        super().__init__()
+        self.num_actions = model.num_actions
+        self.num_states = model.num_states
+        self.dtype = model.dtype
+        self._dx = torch.zeros([model.num_actions, model.num_states], dtype=self.dtype)
+        self.u = iter([])
+        self.b_lim = [[-1., 1.]] * model.num_states
+        self.skip = [s.upper() == s for s in model.states]  # positions only
+        self.weight = 5.
+        if any(not sk for sk in self.skip[model.num_actions:]):
+            # lower-case velocity-magnitude states ('v' of the speed model) index past the controls in the reference
+            raise NotImplementedError("BarrierPush: the speed-state model is not supported (IndexError in the reference)")
+        self._use_u = False
+
+    def reset(self, x=None, u=None, iter_idx=0):
+        self._use_u = iter_idx > 0
+        self.u = iter(u) if iter_idx > 0 else iter([])
+        return u
+
+    def _active(self, x, i):
+        lo, hi = self.b_lim[i]
+        v = x[i + self.num_actions]
+        return bool(((x[i] >= hi) and (v > 0)) or ((x[i] <= lo) and (v < 0)))
+
+    def clipped(self, x, u):
+        for i, skip in enumerate(self.skip):
+            if not skip and self._active(x, i):
+                u[i] = -self.weight * x[i + self.num_actions]
+        return u
+
+    def dx(self, x=None, u=None):
+        dx = self._dx.clone()
+        for i, skip in enumerate(self.skip):
+            if not skip and self._active(x, i):
+                dx[i, i + self.num_actions] = -self.weight
+        return dx
+
+    def __call__(self, x=None):
+        try:
+            u = next(self.u)
+        except StopIteration:
+            u = torch.zeros(self.num_actions, dtype=self.dtype)
+        return self.clipped(x, u)
+
+    def device_spec(self):
+        from . import _cabi as cabi
+        return cabi.policy_spec(cabi.POLICY_BARRIER_PUSH, use_u=self._use_u, weight=self.weight)
 
 
-BarrierPush = _not_ported("BarrierPush")
-LQR = _not_ported("LQR")
+class LQR(torch.nn.Module):
+    """u = -K x with the continuous-time LQR gain of the model linearised at ones (reference
+    default_policies.py:100-119; the Riccati solve is scipy's, on the host, once per controller)."""
+    feedback = True
+
+    def __init__(self, model, horizon):
+        super().__init__()
+        import numpy as np
+        from scipy.linalg import solve_continuous_are
+        A, B = model.get_lin(torch.ones(model.num_states), torch.ones(model.num_actions))
+        A = A.cpu().numpy()
+        B = B.cpu().numpy()
+        if A.shape[0] != 2 * model.num_actions:
+            raise NotImplementedError("LQR: Q is sized for a double-integrator state (positions + velocities)")
+        Q = np.diag([5.] * model.num_actions + [1.] * model.num_actions)
+        Rm = np.eye(model.num_actions) * 100. * horizon
+        Pm = solve_continuous_are(A, B, Q, Rm, balanced=False)
+        self.Klqr = torch.as_tensor(np.linalg.inv(Rm) @ B.T @ Pm, dtype=model.dtype)
+
+    def reset(self, x=None, u=None, iter_idx=0):
+        return u
+
+    def dx(self, x=None, u=None):
+        return -self.Klqr.clone()
+
+    def __call__(self, x):
+        return -self.Klqr @ x
+
+    def device_spec(self):
+        from . import _cabi as cabi
+        return cabi.policy_spec(cabi.POLICY_LQR, K=self.Klqr.tolist())

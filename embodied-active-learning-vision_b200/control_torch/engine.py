@@ -458,6 +458,32 @@ def adjoint(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl
     return dgdx, du, dj, ustar
 
 
+def policy_rollout(dyn, pol, x0, R0, u_in, H):
+    """Closed-loop rollout under a state-feedback default policy (klerg.py:409-431 with default_policies.py:53-119):
+    -> (u_eff [H,A] the controls the policy applied, dmudx [H,A,S])."""
+    dev = x0.device
+    u_eff = torch.empty((H, dyn.A), dtype=torch.float32, device=dev)
+    dmudx = torch.empty((H, dyn.A, dyn.S), dtype=torch.float32, device=dev)
+    cabi.check(cabi.load().klerg_policy_rollout(C.byref(dyn), C.byref(pol), cabi.ptr(x0), cabi.ptr(R0),
+                                                cabi.ptr(u_in.contiguous()) if u_in is not None else None, int(H),
+                                                cabi.ptr(u_eff), cabi.ptr(dmudx), cabi.stream_ptr()), "klerg_policy_rollout")
+    return u_eff, dmudx
+
+
+def adjoint_policy(dyn, dgdx, dbarr, P, dmudx, u, rinv, alpha, ctrl_lo, ctrl_hi):
+    """Adjoint sweep with the closed-loop linearisation A_t + B dmudx_t -> du [H,A], djdlam [H], u_star [H,A]."""
+    H = dgdx.shape[0]
+    dev = dgdx.device
+    du = torch.empty((H, dyn.A), dtype=torch.float32, device=dev)
+    dj = torch.empty(H, dtype=torch.float32, device=dev)
+    ustar = torch.empty((H, dyn.A), dtype=torch.float32, device=dev)
+    cabi.check(cabi.load().klerg_adjoint_policy(
+        C.byref(dyn), H, cabi.ptr(dgdx.contiguous()), cabi.ptr(dbarr.contiguous()), cabi.ptr(P), cabi.ptr(dmudx.contiguous()),
+        cabi.ptr(u.contiguous()), cabi.farr(rinv), float(alpha), cabi.farr(ctrl_lo), cabi.farr(ctrl_hi), cabi.ptr(du),
+        cabi.ptr(dj), cabi.ptr(ustar), cabi.stream_ptr()), "klerg_adjoint_policy")
+    return du, dj, ustar
+
+
 def adjoint_targets(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl_hi):
     """grad_parts [K,world,H,D] float64 -> dgdx [K,H,S], du [K,H,A], djdlam [K,H], u_star [K,H,A] (one launch)."""
     K, world, H, D = grad_parts.shape

@@ -16,11 +16,12 @@ different is where the work happens:
 
 The non-default ``robot_config.yaml`` flags ``saturate``, ``fixed_lam``,
 ``ctrlAppSearch: False``, ``sample_near_current_loc``, ``add_recent_history``,
-``test_corners`` and ``PriorDist`` / ``use_prior`` are built (SURVEY section 8
-a22; golden sequences from the live reference).  Not ported: ``optimize_samples``
-(an autograd/Adam pre-conditioner of the samples through the target model),
-``full_cost`` (does not run in the reference itself), ``average_prior`` (reads an
-attribute the reference never defines), the BarrierPush/LQR policies (dmu/dx != 0).
+``test_corners``, ``PriorDist`` / ``use_prior`` and the BarrierPush / LQR default
+policies are built (golden sequences from the live
+reference).  Not ported: ``optimize_samples`` (an autograd/Adam pre-conditioner of
+the samples through the target model), ``full_cost`` (does not run in the
+reference itself), ``average_prior`` (reads an attribute the reference never
+defines).
 """
 import itertools
 import math
@@ -33,7 +34,7 @@ import yaml
 from . import _cabi as cabi
 from . import engine
 from .barrier import setup_barrier
-from .default_policies import Roll, Zero  # noqa: F401  (looked up by name from the yaml)
+from .default_policies import BarrierPush, LQR, Roll, Zero  # noqa: F401  (looked up by name from the yaml)
 from .dynamics import DoubleIntegratorEnv, DoubleIntegratorRollEnv, DoubleIntegratorSpeedEnv
 from .klerg_utils import Lambda
 from .memory_buffer import MemoryBuffer_torch
@@ -228,9 +229,9 @@ class Robot(object):
         self.control_lim = torch.tensor([[-0.5, 0.5] if state in 'z' else [-1.0, 1.0] for state in states],
                                         dtype=self.dtype)
 
-        policies = {"Roll": Roll, "Zero": Zero}
+        policies = {"Roll": Roll, "Zero": Zero, "BarrierPush": BarrierPush, "LQR": LQR}
         if self.DefaultPolicy not in policies:
-            raise NotImplementedError(f"DefaultPolicy {self.DefaultPolicy!r} is not ported (dmu/dx != 0); use Roll or Zero")
+            raise NotImplementedError(f"DefaultPolicy {self.DefaultPolicy!r} is unknown; use Roll, Zero, BarrierPush or LQR")
         self.policy = policies[self.DefaultPolicy](self.planner, self.horizon)
 
         self.plot_data = plot_data
@@ -568,7 +569,8 @@ class Robot(object):
                                                     uniform=self.uniform_tdist, spread=spread)
                 ctx.set_target(p, p_stats)
 
-            if self.device_loop and ctx.fused and self.plot_data is None and self.ctrlAppSearch:
+            feedback = bool(getattr(self.policy, "feedback", False))  # BarrierPush / LQR: dmu/dx != 0
+            if self.device_loop and ctx.fused and self.plot_data is None and self.ctrlAppSearch and not feedback:
                 with engine.nvtx_range("klerg.plan_optimize"):
                     self._optimize_on_device(ctx)
                 return
@@ -578,7 +580,12 @@ class Robot(object):
             for idx in range(self.num_iters_per_step):
                 # forward(idx): the Roll/Zero policy replays self.u unchanged for idx >= 0
                 u_tmp = self.policy.reset(None, self.u.clone(), idx)
-                g = ctx.gradient(u_tmp.to(self.cuda, non_blocking=True), keep=self.plot_data is not None)
+                if feedback:  # the policy decides the controls along the closed loop (klerg.py:418-420)
+                    g = ctx.gradient(u_tmp.to(self.cuda, non_blocking=True), keep=self.plot_data is not None,
+                                     policy=self.policy.device_spec())
+                    u_tmp = g["u_eff"].cpu()
+                else:
+                    g = ctx.gradient(u_tmp.to(self.cuda, non_blocking=True), keep=self.plot_data is not None)
                 self.stats["grad_evals"] += 1
                 prev_accepted, accepted = accepted, g
                 if "host_pack" in g:  # fused eval: djdlam, u* and the fault word share one buffer -> a single D2H copy
@@ -608,6 +615,9 @@ class Robot(object):
                         tau, success, _, chosen = line_search_select(Js, windows, idx, lam0, last_cost)
                         if success:
                             u_tmp[tau[0]:tau[1]] = u_app.clone()
+                        if feedback:  # u_tmp is the policy's sequence, not self.u: its cost is an evaluation of its own
+                            cost = self._costs(ctx, u_tmp.unsqueeze(0))[0]
+                        elif success:
                             # get_cost(u_tmp) is the evaluation already made for that window
                             cost = Js[chosen] if chosen is not None else self._costs(ctx, u_tmp.unsqueeze(0))[0]
                         else:

@@ -122,8 +122,12 @@ class PlannerContext:
         self.evals["fwd_pairs"] += B * self.H * self.n
         return engine.kl_cost(v, self.n, totals_w, self.p, self.p_stats, ro["barrier"], self.group, self.floor)
 
-    def gradient(self, u, keep=False, want_cost=False):
-        """u [H,A] on the device -> dict(du, djdlam, u_star, dgdx, ...) on the device."""
+    def gradient(self, u, keep=False, want_cost=False, policy=None):
+        """u [H,A] on the device -> dict(du, djdlam, u_star, dgdx, ...) on the device.  ``policy``: a
+        cabi.PolicySpec of a state-feedback default policy (BarrierPush / LQR): the controls are then what the policy
+        applies along the closed loop (returned as ``u_eff``) and the adjoint carries dmu/dx."""
+        if policy is not None:
+            return self._gradient_feedback(u, policy, keep)
         if self.fused:
             o = engine.eval_gradient(self.spec, self.dyn, self.bar, self._peers_ref, self.x0, self.R0, u.reshape(self.H, -1).contiguous(),
                                      self.packed, self.n, self.q_base, self.p, self.p_stats, self._rinv_c, self.alpha,
@@ -157,6 +161,35 @@ class PlannerContext:
         self.evals["fwd_pairs"] += self.H * self.n
         self.evals["grad_pairs"] += self.H * self.n
         out = dict(du=du, djdlam=dj, u_star=ustar, dgdx=dgdx, traj=pre, kl_parts=klparts)
+        if keep:
+            out.update(v=v[0], totals=totals_w)
+        return out
+
+    def _gradient_feedback(self, u, policy, keep):
+        """Robot.forward + backward (klerg.py:409-450) for a policy with dmu/dx != 0: the closed loop fixes the controls
+        (one serial warp), the pair passes run open-loop on them, the adjoint uses A_t + B dmudx_t."""
+        H = self.H
+        u_eff, dmudx = engine.policy_rollout(self.dyn, policy, self.x0, self.R0, u.reshape(H, -1) if u is not None else None, H)
+        ro = engine.rollout(self.dyn, self.bar, self.x0, u_eff, R0=self.R0, want_lin=True)
+        traj = ro["traj"][0]
+        pre = traj[:H]
+        v, totals = engine.footprint(self.spec, 0, pre, self.packed, self.n, add_in=self.q_base)
+        totals_w = self.group.gather_blocks(totals)
+        gpart, klpart = engine.kl_gradient_fused(self.spec, pre, self.packed, self.n, v[0], totals_w, self.p, self.floor)
+        if self.group.world > 1:
+            packed = self.group.gather_blocks(torch.cat([gpart.reshape(-1), klpart]))
+            gparts = packed[:, :-2].reshape(self.group.world, H, self.spec.D).contiguous()
+        else:
+            gparts = gpart.unsqueeze(0)
+        P = ro["P"][0] if ro["P"] is not None else None
+        dgdx, _, _, _ = engine.adjoint(self.dyn, self.spec, gparts, ro["dbarr"][0], P, traj, u_eff, self.rinv, self.alpha,
+                                       self.ctrl_lo, self.ctrl_hi)  # assembles dgdx [H,S] from the partials
+        du, dj, ustar = engine.adjoint_policy(self.dyn, dgdx, ro["dbarr"][0], P, dmudx, u_eff, self.rinv, self.alpha,
+                                              self.ctrl_lo, self.ctrl_hi)
+        self.evals["grad"] += 1
+        self.evals["fwd_pairs"] += H * self.n
+        self.evals["grad_pairs"] += H * self.n
+        out = dict(du=du, djdlam=dj, u_star=ustar, dgdx=dgdx, traj=pre, u_eff=u_eff, dmudx=dmudx)
         if keep:
             out.update(v=v[0], totals=totals_w)
         return out

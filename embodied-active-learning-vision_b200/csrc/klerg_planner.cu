@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(32) policy_rollout_kernel(const DynDev d, cons
   __shared__ float x[KLERG_MAX_S], u[KLERG_MAX_A], Rm[9];
   const int lane = threadIdx.x, S = d.S, A = d.A;
   const bool single = d.kind == KLERG_DYN_SINGLE, roll = d.kind == KLERG_DYN_ROLL;
-  const float dt = d.dt, c1 = 0.8f * dt, c2 = 0.4f * dt * dt;
+  const float dt = d.dt;
   if (lane < S) x[lane] = x0[lane];
   __syncwarp();
   if (roll && lane == 0) {
@@ -724,12 +724,23 @@ __global__ void __launch_bounds__(32) policy_rollout_kernel(const DynDev d, cons
     }
     __syncwarp();
     if (lane < A) {
+      // The policy branches on the state (x_i >= 1, v_i > 0), and BarrierPush's own control u = -5 v with dt = 0.2
+      // lands the velocity EXACTLY on 0 in the reference: the step is evaluated in the reference's operation order
+      // (rk4_integrate, dynamics.py:7-13: k = dt f, x + (1/6)(k1 + 2 k2 + 2 k3 + k4), no contraction), not in the
+      // closed form of the open-loop rollout, so that such ties fall the same way.
+      const float sixth = 0.16666667163372040f;  // float32(1/6.)
+      const float ku = __fmul_rn(dt, u[lane]);   // velocity rate = u at every stage
+      const float su = __fadd_rn(__fadd_rn(__fadd_rn(ku, __fmul_rn(2.f, ku)), __fmul_rn(2.f, ku)), ku);
       if (single) {
-        x[lane] = fmaf(dt, u[lane], x[lane]);
+        x[lane] = __fadd_rn(x[lane], __fmul_rn(sixth, su));
       } else {
         const float v = x[A + lane];
-        x[lane] = x[lane] + c1 * v + c2 * u[lane];
-        x[A + lane] = fmaf(dt, u[lane], v);
+        const float k1 = __fmul_rn(dt, __fmul_rn(0.8f, v));
+        const float k2 = __fmul_rn(dt, __fmul_rn(0.8f, __fadd_rn(v, __fmul_rn(ku, 0.5f))));
+        const float k4 = __fmul_rn(dt, __fmul_rn(0.8f, __fadd_rn(v, ku)));
+        const float sp = __fadd_rn(__fadd_rn(__fadd_rn(k1, __fmul_rn(2.f, k2)), __fmul_rn(2.f, k2)), k4);
+        x[lane] = __fadd_rn(x[lane], __fmul_rn(sixth, sp));
+        x[A + lane] = __fadd_rn(v, __fmul_rn(sixth, su));
       }
     }
     __syncwarp();

@@ -443,6 +443,43 @@ def roll_controls(u, shift):
     return u
 
 
+class OracleFeedback:
+    """The state-feedback default policies (default_policies.py:53-119) as one rule ``act(x, planned) -> (u, dmudx)``.
+
+    'BarrierPush': the planned control (zeros on the first inner iteration), with -5 v_i on every position that sits on
+    its +-1 wall moving outwards; 'LQR': u = -K x, K = R^-1 B^T P of the continuous-time Riccati solution for the
+    model linearised at ones (Q = diag(5 on positions, 1 on velocities), R = 100 * horizon * I)."""
+
+    def __init__(self, name, model, horizon):
+        self.name = name
+        self.a, self.n, self.dtype = model.num_actions, model.num_states, model.dtype
+        if name == "LQR":
+            from scipy.linalg import solve_continuous_are
+            A, B = (m.numpy() for m in model.get_lin(torch.ones(self.n), torch.ones(self.a)))
+            Rm = np.eye(self.a) * 100.0 * horizon
+            Pm = solve_continuous_are(A, B, np.diag([5.0] * self.a + [1.0] * self.a), Rm, balanced=False)
+            self.K = torch.as_tensor(np.linalg.inv(Rm) @ B.T @ Pm, dtype=self.dtype)
+        elif name == "BarrierPush":
+            self.positions = [i for i, s in enumerate(model.states) if s.upper() != s]
+        else:
+            raise ValueError(name)
+
+    def uses_plan(self, idx):
+        return self.name == "BarrierPush" and idx > 0
+
+    def act(self, x, planned):
+        dmudx = torch.zeros([self.a, self.n], dtype=self.dtype)
+        if self.name == "LQR":
+            return -self.K @ x, -self.K.clone()
+        u = planned.clone()
+        for i in self.positions:
+            v = x[i + self.a]
+            if (x[i] >= 1.0 and v > 0) or (x[i] <= -1.0 and v < 0):
+                u[i] = -5.0 * v
+                dmudx[i, i + self.a] = -5.0
+        return u, dmudx
+
+
 # ----------------------------------------------------------------------------
 # line-search window logic (klerg.py:712-751), separated from the cost calls
 # ----------------------------------------------------------------------------
@@ -597,6 +634,14 @@ class OracleRobot:
         self.trace = None
         self.n_cost_evals = 0
         self.n_grad_evals = 0
+        self.feedback = None
+        if self.DefaultPolicy in ("BarrierPush", "LQR"):
+            self.set_policy(self.DefaultPolicy)
+
+    def set_policy(self, name):
+        """DefaultPolicy of robot_config.yaml (klerg.py:200-202): 'Roll' / 'Zero' replay the plan, the others feed back."""
+        self.DefaultPolicy = name
+        self.feedback = OracleFeedback(name, self.planner, self.horizon) if name in ("BarrierPush", "LQR") else None
 
     def _set_sampler(self):
         lo, hi = self.lims[self.explr_idx].T
@@ -680,7 +725,8 @@ class OracleRobot:
         smooth = 0.5 if self.pybullet else 0.8
         full_state[a:] = smooth * full_state[a:] + (1 - smooth) * planned[a:]
         x = self.robot.reset(full_state)
-        self.u = roll_controls(self.u.clone(), -k)
+        if self.feedback is None:  # BarrierPush.reset / LQR.reset hand the plan back unchanged
+            self.u = roll_controls(self.u.clone(), -k)
         self.last_policy_idx = k
         if save:
             self.memory_buffer.push(x.clone())
@@ -733,13 +779,17 @@ class OracleRobot:
     # -- klerg.py:409-431 --
     def forward(self, idx):
         x = self.planner.reset(self.robot.state.clone())
-        u_tmp = roll_controls(self.u.clone(), idx)
+        u_tmp = roll_controls(self.u.clone(), idx) if self.feedback is None else self.u.clone()
         pending = iter(u_tmp)
         lin, traj = [], []
         for t in range(self.horizon):
-            u_tmp[t] = next(pending)
-            A, B = self.planner.get_lin(x, u_tmp[t])
             dmudx = torch.zeros([self.planner.num_actions, self.planner.num_states], dtype=self.dtype)
+            if self.feedback is None:
+                u_tmp[t] = next(pending)
+            else:
+                planned = u_tmp[t] if self.feedback.uses_plan(idx) else torch.zeros(self.planner.num_actions, dtype=self.dtype)
+                u_tmp[t], dmudx = self.feedback.act(x, planned)
+            A, B = self.planner.get_lin(x, u_tmp[t])
             lin.append((A, B, self.barrier.grad(x), dmudx))
             traj.append(x)
             x = self.planner.step(u_tmp[t])

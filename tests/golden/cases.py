@@ -44,6 +44,10 @@ ROBOT_CASES = {
                                flags=dict(sample_near_current_loc=True, add_recent_history=True)),
     "xyz_prior": dict(states="xyz", D=3, horizon=10, cap=40, n=400, m=30, steps=6, std=0.08, x0=[0.0, 0.1, 0.2, 0, 0, 0],
                       flags=dict(use_prior=True)),
+    # state-feedback default policies (default_policies.py:53-119); the BarrierPush case starts on the walls moving outwards
+    "xy_lqr": dict(states="xy", D=2, horizon=10, cap=40, n=300, m=30, steps=8, std=0.05, x0=[0.6, -0.5, 0.3, 0.2], policy="LQR"),
+    "xyz_barrierpush": dict(states="xyz", D=3, horizon=12, cap=40, n=400, m=30, steps=8, std=0.08,
+                            x0=[0.97, -0.98, 0.2, 0.6, -0.5, 0.1], policy="BarrierPush"),
     "xyw_plot_corners": dict(states="xyw", D=3, horizon=10, cap=50, n=400, m=30, steps=6, std=0.08, x0=[0.2, -0.4, 0.1, 0, 0, 0],
                              plot=True, flags=dict(test_corners=True)),
 }
@@ -57,6 +61,13 @@ def apply_case_flags(r, case):
     flags = case.get("flags", {})
     for k, v in flags.items():
         setattr(r, k, v)
+    name = case.get("policy")
+    if name:
+        if hasattr(r, "set_policy"):  # the oracle
+            r.set_policy(name)
+        else:  # reference / B200 mirror: the class of that name from the module the controller took its policy from
+            import sys
+            r.policy = getattr(sys.modules[type(r.policy).__module__], name)(r.planner, r.horizon)
     if flags.get("sample_near_current_loc") and not hasattr(r, "loc_sampler"):
         r.loc_sampler = torch.distributions.Normal(torch.zeros_like(r.std), r.std * 4.)
     if flags.get("use_prior") and not hasattr(r.prior_dist, "device"):

@@ -143,3 +143,28 @@ def test_targets_gradient_validation(lib):
     assert lib.klerg_adjoint_targets(C.byref(dyn), C.byref(k), 10, 0, None, 1, None, None, None, None, three, 1.0, three,
                                      three, None, None, None, None, None) == -1  # K < 1
     assert "K out of range" in err(lib)
+
+
+def test_policy_entry_points_validation(lib):
+    """klerg_policy_rollout / klerg_adjoint_policy (state-feedback default policies): argument checks run before any
+    launch, so they can be exercised without a GPU."""
+    dyn = cabi.dyn_spec(cabi.DYN_DOUBLE, 4, 2, 0.1)
+    pol = cabi.policy_spec(cabi.POLICY_LQR, K=[[1.0, 0.0, 0.5, 0.0], [0.0, 1.0, 0.0, 0.5]])
+    assert lib.klerg_policy_rollout(C.byref(dyn), None, None, None, None, 10, None, None, None) != 0
+    assert b"policy spec is null" in lib.klerg_last_error()
+    bad = cabi.policy_spec(7)
+    assert lib.klerg_policy_rollout(C.byref(dyn), C.byref(bad), None, None, None, 10, None, None, None) != 0
+    assert b"unknown kind" in lib.klerg_last_error()
+    assert lib.klerg_policy_rollout(C.byref(dyn), C.byref(pol), None, None, None, 0, None, None, None) != 0
+    assert b"H out of range" in lib.klerg_last_error()
+    assert lib.klerg_policy_rollout(C.byref(dyn), C.byref(pol), None, None, None, 10, None, None, None) != 0
+    assert b"null argument" in lib.klerg_last_error()
+    speed = cabi.dyn_spec(cabi.DYN_SPEED, 6, 2, 0.1)
+    assert lib.klerg_policy_rollout(C.byref(speed), C.byref(pol), None, None, None, 10, None, None, None) != 0
+    assert b"speed-state model" in lib.klerg_last_error()
+    assert lib.klerg_adjoint_policy(C.byref(speed), 10, None, None, None, None, None, None, 1.0, None, None, None, None, None, None) != 0
+    assert b"speed-state model" in lib.klerg_last_error()
+    assert lib.klerg_adjoint_policy(C.byref(dyn), 10, None, None, None, None, None, None, 1.0, None, None, None, None, None, None) != 0
+    assert b"null argument" in lib.klerg_last_error()
+    with pytest.raises(ValueError):
+        cabi.policy_spec(cabi.POLICY_LQR, K=[[0.0] * 25] * 8)

@@ -212,7 +212,11 @@ def test_evals_vs_golden(ct, golden_dir, name):
         while pre + f"grad{j}/du" in gold:
             traj = torch.from_numpy(gold[pre + f"grad{j}/traj"])
             u = torch.from_numpy(gold[pre + f"grad{j}/u"])
-            g = ctx.gradient(u.to(dev), keep=True)
+            if case.get("policy"):  # state feedback: the j-th inner iteration's closed loop (klerg.py:409-431)
+                r.policy.reset(None, u.clone(), j)
+                g = ctx.gradient(u.to(dev), keep=True, policy=r.policy.device_spec())
+            else:
+                g = ctx.gradient(u.to(dev), keep=True)
             rel_close(g["traj"], traj, rtol=2e-5, atol_frac=2e-6, what=f"{pre}grad{j}/traj")
             q = ctx.q_from(g["v"], g["totals"])
             rel_close(q, gold[pre + f"grad{j}/q"], what=f"{pre}grad{j}/q")
