@@ -116,6 +116,8 @@ SIGNATURES = {
     "klerg_pack_samples": [_KS, _P, _I64, _P, _I64, _P],
     "klerg_footprint": [_KS, C.c_int, _P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P],
     "klerg_footprint_sum_max": [_KS, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P, _P],
+    "klerg_footprint_tc_scratch_bytes": [_I64],
+    "klerg_footprint_sum_max_tc": [_KS, _P, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P, _P, _I64, _P],
     "klerg_psi_matrix": [_KS, _P, _I64, _P, _I64, _P, _P, _P],
     "klerg_vector_stats": [_P, _I64, _P, _P, _P],
     "klerg_renormalize": [_P, _I64, _F, _P, _P, _P],
@@ -175,7 +177,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"klerg_last_error": C.c_char_p, "klerg_target_decoder_packed_bytes": C.c_size_t, "klerg_kl_gradient_targets_scratch_bytes": C.c_size_t, "klerg_workspace_bytes": C.c_size_t, "klerg_mailbox_bytes": C.c_size_t, "klerg_debug_stamps_offset": C.c_size_t, "klerg_debug_cta_stamps_offset": C.c_size_t, "klerg_fused_fault_offset": C.c_size_t,
              "klerg_launch_count": C.c_longlong, "klerg_eval_costs_batch_scratch_bytes": C.c_size_t, "klerg_belief_scratch_bytes": C.c_size_t, "klerg_plan_scratch_bytes": C.c_size_t,
-             "klerg_plan_result_floats": C.c_int64}
+             "klerg_plan_result_floats": C.c_int64, "klerg_footprint_tc_scratch_bytes": C.c_int64}
 
 
 def load():

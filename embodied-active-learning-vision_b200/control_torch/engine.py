@@ -255,9 +255,17 @@ def footprint(spec, mode, states, packed, n, add_in=None, out=None):
     return out, totals
 
 
-def footprint_sum_max(spec, states, t_sum, packed, n):
+FOOTPRINT_TC = os.environ.get("KLERG_FOOTPRINT_TC", "1") != "0"  # the tensor-core form of the history / spread pass
+FOOTPRINT_TC_MIN_PAIRS = 1 << 28  # below this the CUDA-core pass is at least as fast (launches, chunk packing)
+_tc_scratch = {}
+
+
+def footprint_sum_max(spec, states, t_sum, packed, n, tensor_cores=None):
     """ONE pass over the squared distances for both memory-buffer passes of a planner step: states [T,S] with the drawn
-    rows first -> (sum over the first t_sum rows [ld], max over all rows [ld], totals [2] of the sum)."""
+    rows first -> (sum over the first t_sum rows [ld], max over all rows [ld], totals [2] of the sum).  Large passes
+    (history of a 1e7-sample workspace) take the tensor-core form (klerg_footprint_sum_max_tc: distances as one K = 8
+    tf32 MMA step, min / exp / add on the CUDA cores), which falls back on the device when the states leave the radius
+    of the expanded pair form; ``tensor_cores`` forces the choice (tests)."""
     states = states.contiguous()
     T, S = states.shape
     assert S == spec.S, (S, spec.S)
@@ -265,6 +273,20 @@ def footprint_sum_max(spec, states, t_sum, packed, n):
     out_sum = torch.empty(ld, dtype=torch.float32, device=packed.device)
     out_max = torch.empty(ld, dtype=torch.float32, device=packed.device)
     totals = torch.empty(2, dtype=torch.float64, device=packed.device)
+    use_tc = tensor_cores if tensor_cores is not None else (FOOTPRINT_TC and spec.D <= 6 and T >= 256
+                                                           and T * int(n) >= FOOTPRINT_TC_MIN_PAIRS)
+    if use_tc and T > 0 and n > 0:
+        lib = cabi.load()
+        need = int(lib.klerg_footprint_tc_scratch_bytes(T))
+        key = (packed.device.index, cabi.raw_stream())
+        scratch = _tc_scratch.get(key)
+        if scratch is None or scratch.numel() < need:
+            scratch = _tc_scratch[key] = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=packed.device)
+        cabi.check(lib.klerg_footprint_sum_max_tc(
+            C.byref(spec), cabi.ptr(states), T, int(t_sum), cabi.ptr(packed), int(n), ld, cabi.ptr(out_sum),
+            cabi.ptr(out_max), cabi.ptr(totals), workspace(1), cabi.ptr(scratch), scratch.numel(), cabi.stream_ptr()),
+            "klerg_footprint_sum_max_tc")
+        return out_sum, out_max, totals
     cabi.check(cabi.load().klerg_footprint_sum_max(
         C.byref(spec), cabi.ptr(states) if T > 0 else None, T, int(t_sum), cabi.ptr(packed), int(n), ld, cabi.ptr(out_sum),
         cabi.ptr(out_max), cabi.ptr(totals), workspace(1), cabi.stream_ptr()), "klerg_footprint_sum_max")

@@ -55,6 +55,7 @@ struct FootArgs {
   double* totals;
   void* ws;
   int64_t ntiles;
+  const int* gate;  // optional: the launch returns at once when *gate != 0 (the tensor-core pass did the work)
 };
 
 // Load SPT consecutive samples of one dimension starting at i0 as SPT/2 packed pairs.
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(FP_THREADS) footprint_kernel(const FootArgs a)
   constexpr int TILE = FP_THREADS * SPT;
   constexpr int CHUNK = FootChunk<D>::ROWS;
   __shared__ __align__(16) u64 sh[CHUNK * DP];
+  if (a.gate != nullptr && __ldg(a.gate) != 0) return;
   float* shx = reinterpret_cast<float*>(sh);
   const int tid = threadIdx.x;
   // chunk schedule: rows [0, T_sum) first, then [T_sum, T) (MODE 2; otherwise T_sum = T)
@@ -575,6 +577,15 @@ extern "C" int klerg_footprint_sum_max(const klerg_kernel_spec* k, const float* 
   FootArgs a{kd, states, 1, T, T * kd.S, T_sum, packed, N, ld, nullptr, out_sum, ld, out_max, totals, workspace, 0};
   return launch_footprint_d<2>(a, (cudaStream_t)stream);
 }
+
+namespace klerg {
+int launch_footprint_sum_max_gated(const KernelDev& kd, const float* states, int64_t T, int64_t T_sum, const float* packed,
+                                   int64_t N, int64_t ld, float* out_sum, float* out_max, double* totals, void* workspace,
+                                   const int* gate, cudaStream_t stream) {
+  FootArgs a{kd, states, 1, T, T * kd.S, T_sum, packed, N, ld, nullptr, out_sum, ld, out_max, totals, workspace, 0, gate};
+  return launch_footprint_d<2>(a, stream);
+}
+}  // namespace klerg
 
 extern "C" int klerg_kl_gradient(const klerg_kernel_spec* k, const float* states, int64_t H, const float* packed,
                                  int64_t N, int64_t ld, const float* w, float* dgdx, void* workspace,

@@ -113,6 +113,18 @@ int klerg_footprint_sum_max(const klerg_kernel_spec* k, const float* states, int
                             const float* packed, int64_t N, int64_t ld, float* out_sum, float* out_max,
                             double* totals, void* workspace, void* stream);
 
+/* The same pass with the squared distances on the tensor cores: e_ij = |sc_i|^2 + |xc_j|^2 - 2 xc_j . sc_i is a
+ * bilinear form of D + 2 <= 8 terms = one K = 8 step of tcgen05.mma kind::tf32 (3xTF32 split, fp32 accumulation,
+ * samples as TMEM lanes, 128 state rows per accumulator); the CUDA cores keep min / exp / add, so the pass is bound
+ * by the MUFU pipe (one exp per pair) instead of the FP32 pipe.  Around the centre of the states' bounding box; when a
+ * state lies outside the radius of the expanded pair form (klerg_pair.cuh) the launch falls back, on the device, to
+ * the CUDA-core pass of klerg_footprint_sum_max.  D <= 6, T >= 1, N >= 1.  scratch: klerg_footprint_tc_scratch_bytes(T)
+ * bytes of device memory, 128-byte aligned (packed state chunks). */
+int64_t klerg_footprint_tc_scratch_bytes(int64_t T);
+int klerg_footprint_sum_max_tc(const klerg_kernel_spec* k, const float* states, int64_t T, int64_t T_sum,
+                               const float* packed, int64_t N, int64_t ld, float* out_sum, float* out_max,
+                               double* totals, void* workspace, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* a1: psi_fn / dpsi_dx_fn (klerg_utils.py:7-15) materialised: psi[N][T] = psi(states_j[explr], samples_i)
  * and / or dpsi[N][T][D] = -(x_j - s_i)/|scale| * psi * nu (dpsi_dx_fn divides by nu once, through psi).
  * `samples` are the raw AoS samples [N][D].  Either output may be NULL. */

@@ -1,0 +1,84 @@
+"""klerg_footprint_sum_max_tc - the history footprint + spread pass with the squared distances on the tensor cores
+(one K = 8 tf32 MMA step per pair block, 3xTF32) - against the CUDA-core pass and the oracle: ragged sizes around the
+128-sample tiles and the 128-row chunks, empty / full summed part, D = 2, 3, 6, and the on-device fallback when the
+states leave the radius of the expanded pair form."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "embodied-active-learning-vision_b200")]
+from oracle import klerg_oracle as ko  # noqa: E402
+
+
+def _case(D, S, N, T, seed, std=0.2, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    samples = torch.rand(N, D, generator=g) * 2.3 - 1.15
+    walk = torch.cumsum(0.03 * torch.randn(T, S, generator=g), 0)
+    states = (walk - walk.mean(0)) * spread
+    states = states.clamp(-1.0, 1.0)
+    scale = torch.full((D,), std) * torch.tensor([1.0, -1.0] * 4)[:D]  # the sign of std must not matter
+    return samples, states.contiguous(), scale
+
+
+def _flag(engine):
+    from control_torch import _cabi as cabi
+    sc = engine._tc_scratch[(torch.cuda.current_device(), cabi.raw_stream())]
+    return int(sc[32:36].view(torch.int32).item())
+
+
+@pytest.mark.parametrize("D,S,N,T,T_sum", [(6, 12, 5000, 700, 300), (6, 12, 128, 256, 256), (3, 6, 1000, 513, 0),
+                                           (2, 4, 777, 1000, 1000), (6, 12, 4097, 2000, 1500), (4, 8, 130, 129, 1),
+                                           (6, 12, 33_000, 3_000, 2_999)])
+def test_tensor_core_pass_matches_cuda_cores_and_oracle(D, S, N, T, T_sum):
+    from control_torch import _cabi as cabi, engine
+    samples, states, scale = _case(D, S, N, T, seed=N + T)
+    explr = list(range(D))
+    spec = cabi.kernel_spec(D, S, explr, scale.tolist(), 1.0)
+    dev = torch.device("cuda")
+    packed = engine.pack_samples(spec, samples.to(dev))
+    st = states.to(dev)
+    s_tc, m_tc, tot_tc = engine.footprint_sum_max(spec, st, T_sum, packed, N, tensor_cores=True)
+    torch.cuda.synchronize()
+    assert _flag(engine) == 1, "the states lie within the radius: the tensor-core pass must have run"
+    s_cc, m_cc, tot_cc = engine.footprint_sum_max(spec, st, T_sum, packed, N, tensor_cores=False)
+    np.testing.assert_allclose(s_tc[:N].cpu().numpy(), s_cc[:N].cpu().numpy(), rtol=1e-4, atol=1e-37)
+    np.testing.assert_allclose(m_tc[:N].cpu().numpy(), m_cc[:N].cpu().numpy(), rtol=1e-4, atol=1e-37)
+    np.testing.assert_allclose(tot_tc.cpu().numpy(), tot_cc.cpu().numpy(), rtol=1e-5)
+    want_s = ko.footprint_sum(states[:T_sum], samples, torch.tensor(explr), scale, torch.ones(1)) if T_sum else torch.zeros(N)
+    want_m = ko.spread_max(states, samples, torch.tensor(explr), scale, 1.0)
+    np.testing.assert_allclose(s_tc[:N].cpu().numpy(), want_s.numpy(), rtol=1e-4, atol=1e-30)
+    np.testing.assert_allclose(m_tc[:N].cpu().numpy(), want_m.numpy(), rtol=1e-4, atol=1e-30)
+
+
+def test_tensor_core_pass_falls_back_outside_the_radius():
+    """A narrow kernel (std 0.01) puts the states far outside the expanded form's radius around any centre: the flag
+    stays 0 and the CUDA-core pass behind the tensor-core launch produces the result - bit for bit its own."""
+    from control_torch import _cabi as cabi, engine
+    D, S, N, T, T_sum = 3, 6, 3000, 600, 400
+    samples, states, scale = _case(D, S, N, T, seed=5, std=0.01, spread=3.0)
+    spec = cabi.kernel_spec(D, S, list(range(D)), scale.tolist(), 1.0)
+    dev = torch.device("cuda")
+    packed = engine.pack_samples(spec, samples.to(dev))
+    s_tc, m_tc, tot_tc = engine.footprint_sum_max(spec, states.to(dev), T_sum, packed, N, tensor_cores=True)
+    torch.cuda.synchronize()
+    assert _flag(engine) == 0
+    s_cc, m_cc, tot_cc = engine.footprint_sum_max(spec, states.to(dev), T_sum, packed, N, tensor_cores=False)
+    assert torch.equal(s_tc[:N], s_cc[:N]) and torch.equal(m_tc[:N], m_cc[:N]) and torch.equal(tot_tc, tot_cc)
+
+
+def test_tensor_core_pass_validation():
+    from control_torch import _cabi as cabi
+    lib = cabi.load()
+    assert lib.klerg_footprint_tc_scratch_bytes(1000) == 256 + (8 + 2) * 8192
+    spec = cabi.kernel_spec(3, 6, [0, 1, 2], [0.1, 0.1, 0.1], 1.0)
+    import ctypes as C
+    assert lib.klerg_footprint_sum_max_tc(C.byref(spec), None, 10, 11, None, 100, 100, None, None, None, None, None, 0, None) != 0
+    assert b"bad sizes" in lib.klerg_last_error()
+    assert lib.klerg_footprint_sum_max_tc(C.byref(spec), None, 10, 5, None, 100, 100, None, None, None, None, None, 0, None) != 0
+    assert b"null" in lib.klerg_last_error()
