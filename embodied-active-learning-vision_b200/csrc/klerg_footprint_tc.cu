@@ -13,15 +13,16 @@
 // MUFU-bound (1 exp per pair) instead of FP32-pipe-bound (D + 4 lane-ops per pair).
 //
 // One CTA per SM, 128 samples per tile (one sample per TMEM lane), all T state rows streamed past it in chunks of 128
-// (the N of the MMA): D[128 samples][128 states] accumulators, two of them in flight.
-//   warps 0-3 / 4-7  epilogue warpgroups: accumulator buffer 0 / 1 (tcgen05.ld -> min / ex2 / add per sample);
-//                    warps 0-3 also write the tile's A rows {hi | lo} into TMEM (tcgen05.st)
-//   warp 8           streams the packed B chunks (8 KB: {hi | lo} x 2 K-halves x 128 rows x 16 B, K-major, no
+// (the N of the MMA): D[128 samples][128 states] accumulators, three of them in flight.
+//   warps 0-3, 4-7, 8-11  epilogue warpgroups, one accumulator buffer each (tcgen05.ld -> min / ex2 / add per
+//                    sample); warps 0-3 also write the tile's A rows {hi | lo} into TMEM (tcgen05.st)
+//   warp 12          streams the packed B chunks (8 KB: {hi | lo} x 2 K-halves x 128 rows x 16 B, K-major, no
 //                    swizzle - the layout of klerg_targets_grad.cu) global -> shared with TMA bulk copies
-//   warp 9           issues the MMAs (TS form: A from TMEM, B from shared memory), owns the TMEM allocation
+//   warp 13          issues the MMAs (TS form: A from TMEM, B from shared memory), owns the TMEM allocation
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "klerg_b200.h"
 #include "klerg_common.cuh"
@@ -35,9 +36,11 @@ using namespace tc;
 constexpr int FT_ROWS = 128;                         // state rows per chunk (MMA N)
 constexpr int FT_CHUNK_BYTES = 2 * 2 * FT_ROWS * 16; // {hi, lo} x {K 0-3, K 4-7} x rows x 16 B = 8 KB
 constexpr int FT_STAGES = 8;                         // 64 KB ring
-constexpr int FT_THREADS = 320;
+constexpr int FT_NWG = 3;                            // epilogue warpgroups = accumulator buffers in flight
+constexpr int FT_THREADS = 32 * (4 * FT_NWG + 2);
 constexpr int FT_HDR = 256;                          // scratch header: centre[8] floats, ok flag
-constexpr int FT_ACOL = 256;                         // TMEM columns: accumulators [0,128) [128,256), A hi [256,264), lo [264,272)
+constexpr int FT_ACOL = 128 * FT_NWG;                // TMEM columns: FT_NWG accumulators of 128, then A hi [8] | lo [8]
+static_assert(FT_ACOL + 16 <= 512, "TMEM has 512 columns");
 
 struct FTHeader {
   float ctr[8];
@@ -58,6 +61,7 @@ struct FTArgs {
   unsigned char* scratch;
   int nch_sum, nch_all;
   long long ntiles;
+  int dbg;  // measurement switches (KLERG_FT_DEBUG): 1 = one MMA per chunk instead of three (wrong results)
 };
 
 // ---- centre of the states' bounding box (scaled coordinates) and the radius test ------------------------------
@@ -177,12 +181,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
   unsigned char* ring = smem;
   unsigned long long* b_full = reinterpret_cast<unsigned long long*>(smem + (size_t)FT_STAGES * FT_CHUNK_BYTES);
   unsigned long long* b_empty = b_full + FT_STAGES;
-  unsigned long long* acc_full = b_empty + FT_STAGES;  // [2]
-  unsigned long long* acc_empty = acc_full + 2;        // [2]
-  unsigned long long* a_full = acc_empty + 2;          // [1]
+  unsigned long long* acc_full = b_empty + FT_STAGES;  // [FT_NWG]
+  unsigned long long* acc_empty = acc_full + FT_NWG;   // [FT_NWG]
+  unsigned long long* a_full = acc_empty + FT_NWG;     // [1]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_full + 1);
   volatile unsigned* s_abort = reinterpret_cast<volatile unsigned*>(s_tmem + 1);
-  float* s_x = reinterpret_cast<float*>(s_tmem + 4);   // [128][2]: warpgroup 1's {sum, min} of the tile
+  float* s_x = reinterpret_cast<float*>(s_tmem + 4);   // [FT_NWG - 1][128][2]: the other warpgroups' {sum, min} of the tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = a.nch_all;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
       bar_init(&b_full[s], 1);
       bar_init(&b_empty[s], 1);
     }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < FT_NWG; ++g) {
       bar_init(&acc_full[g], 1);
       bar_init(&acc_empty[g], 4);
     }
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
     *s_abort = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == 4 * FT_NWG + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(s_tmem)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
   const int my_tiles = (int)((a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles blockIdx.x, + gridDim.x, ...
   double tsum = 0.0, tmax = -INFINITY;
 
-  if (warp < 8) {
+  if (warp < 4 * FT_NWG) {
     // ================= epilogue warpgroups =================
     const int g = warp >> 2;                       // accumulator buffer of this warpgroup
     const int row = (warp & 3) * 32 + lane;        // sample of the tile = TMEM lane
@@ -252,8 +256,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
       }
       float total = 0.f, emin = INFINITY;
       for (int c = 0; c < nch; ++c, ++gc) {
-        if ((int)(gc & 1) != g) continue;
-        bar_wait(&acc_full[g], (unsigned)((gc >> 1) & 1), s_abort);
+        if ((int)(gc % FT_NWG) != g) continue;
+        bar_wait(&acc_full[g], (unsigned)((gc / FT_NWG) & 1), s_abort);
         tc_fence_after();
         const uint32_t acc = trow + (uint32_t)(g * 128);
         float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -278,14 +282,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
         total += (s[0] + s[1]) + (s[2] + s[3]);  // per-chunk partial: the rounding error grows with sqrt(chunks)
       }
       // combine the two warpgroups; all chunks of the tile are consumed -> every MMA that read A has completed
-      if (g == 1) {
-        s_x[row * 2] = total;
-        s_x[row * 2 + 1] = emin;
+      if (g > 0) {
+        s_x[((g - 1) * 128 + row) * 2] = total;
+        s_x[((g - 1) * 128 + row) * 2 + 1] = emin;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * FT_NWG) : "memory");
       if (g == 0) {
-        total += s_x[row * 2];
-        emin = fminf(emin, s_x[row * 2 + 1]);
+#pragma unroll
+        for (int o = 0; o < FT_NWG - 1; ++o) {  // fixed order
+          total += s_x[(o * 128 + row) * 2];
+          emin = fminf(emin, s_x[(o * 128 + row) * 2 + 1]);
+        }
         if (i < a.N) {
           const float v = total * a.k.inv_nu;
           a.out_sum[i] = v;
@@ -294,9 +301,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
           tmax = fmax(tmax, (double)v);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_x may be rewritten, A may be overwritten
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * FT_NWG) : "memory");  // s_x may be rewritten, A may be overwritten
     }
-  } else if (warp == 8) {
+  } else if (warp == 4 * FT_NWG) {
     // ================= B chunks: TMA bulk copies into the ring =================
     if (lane == 0) {
       const unsigned char* src = a.scratch + FT_HDR;
@@ -320,17 +327,21 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
         bar_wait(a_full, (unsigned)(it & 1), s_abort);
         tc_fence_after();
         for (int c = 0; c < nch; ++c, ++gc) {
-          const int s = (int)(gc % FT_STAGES), buf = (int)(gc & 1);
+          const int s = (int)(gc % FT_STAGES), buf = (int)(gc % FT_NWG);
           const unsigned k = (unsigned)(gc / FT_STAGES);
           bar_wait(&b_full[s], k & 1u, s_abort);
-          bar_wait(&acc_empty[buf], (unsigned)((gc >> 1) & 1) ^ 1u, s_abort);
+          bar_wait(&acc_empty[buf], (unsigned)((gc / FT_NWG) & 1) ^ 1u, s_abort);
           tc_fence_after();
           const uint32_t b0 = smem_addr(ring + (size_t)s * FT_CHUNK_BYTES);
           const uint64_t db_hi = smem_desc(b0, FT_ROWS * 16, 128), db_lo = smem_desc(b0 + 2 * FT_ROWS * 16, FT_ROWS * 16, 128);
           const uint32_t d = tmem + (uint32_t)(buf * 128);
-          tc_mma_tf32_ts(d, a_lo, db_hi, idesc, 0u);
-          tc_mma_tf32_ts(d, a_hi, db_lo, idesc, 1u);
-          tc_mma_tf32_ts(d, a_hi, db_hi, idesc, 1u);
+          if (a.dbg & 1) {
+            tc_mma_tf32_ts(d, a_hi, db_hi, idesc, 0u);
+          } else {
+            tc_mma_tf32_ts(d, a_lo, db_hi, idesc, 0u);
+            tc_mma_tf32_ts(d, a_hi, db_lo, idesc, 1u);
+            tc_mma_tf32_ts(d, a_hi, db_hi, idesc, 1u);
+          }
           tc_commit(&b_empty[s]);
           tc_commit(&acc_full[buf]);
         }
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 4 * FT_NWG + 1) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
@@ -385,11 +396,15 @@ extern "C" int klerg_footprint_sum_max_tc(const klerg_kernel_spec* k, const floa
   a.nch_sum = (int)((T_sum + FT_ROWS - 1) / FT_ROWS);
   a.nch_all = a.nch_sum + (int)((T - T_sum + FT_ROWS - 1) / FT_ROWS);
   a.ntiles = (N + 127) / 128;
+  {
+    const char* e = getenv("KLERG_FT_DEBUG");
+    a.dbg = e ? atoi(e) : 0;
+  }
   ft_centre_kernel<<<1, 256, 0, st>>>(a);
   if (int rc = check_launch("ft_centre_kernel")) return rc;
   ft_pack_states_kernel<<<(unsigned)a.nch_all, FT_ROWS, 0, st>>>(a);
   if (int rc = check_launch("ft_pack_states_kernel")) return rc;
-  size_t smem = (size_t)FT_STAGES * FT_CHUNK_BYTES + 8 * (2 * FT_STAGES + 5) + 16 + sizeof(float) * 256 + 64;
+  size_t smem = (size_t)FT_STAGES * FT_CHUNK_BYTES + 8 * (2 * FT_STAGES + 2 * FT_NWG + 1) + 16 + sizeof(float) * 256 * (FT_NWG - 1) + 64;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
   static bool raised = false;
   if (!raised) {

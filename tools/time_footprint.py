@@ -28,7 +28,7 @@ hi = (torch.tensor([b for _, b in lims]) * 1.15).to(dev)
 smp = lo + torch.rand(n, D, generator=g, device=dev) * (hi - lo)
 packed = engine.pack_samples(spec, smp)
 hist = wl.random_walk_history(name, m).to(dev)
-t_sum = m
+t_sum = int(float(os.environ.get("TSUM_FRAC", "1")) * m)
 res = {}
 for tc in (False, True):
     for _ in range(2):
