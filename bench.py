@@ -690,10 +690,13 @@ def cuda_arm(args):
                "evals_per_robot_step": (ce + ge) / steps_e, "pair_mix": r["mix"],
                "note": ("the step's host inputs are the robot state, the controls and torch's CPU generator: the workspace "
                         "samples are drawn ON THE DEVICE from the generator's state (bit-exact with the host draw, "
-                        "klerg_mt19937_uniform), the host draws the memory-buffer permutation and copies the indices; "
+                        "klerg_mt19937_uniform; the draw of step k+1 runs one step ahead on a side stream and is used only "
+                        "if the generator is found where it was left), the host draws the memory-buffer permutation and "
+                        "copies the indices; "
                         if r["device_draw"] else
                         "samples drawn by the host torch RNG (reference order) and copied H2D every step; ")
-                       + "the target density is evaluated on the device; history footprint and spread are ONE M_all x N pass; "
+                       + "the target density is evaluated on the device; history footprint and spread are ONE M_all x N pass "
+                         "(squared distances on the tensor cores: klerg_footprint_sum_max_tc); "
                          "pair_mix: most pairs of a step are history / spread pairs (forward-only, cheaper than eval pairs), "
                          "which is why e2e pairs/s can exceed the eval-only `value`"}
         if world == 1 and rank == 0:

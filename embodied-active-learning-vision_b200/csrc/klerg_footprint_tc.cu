@@ -22,7 +22,6 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include "klerg_b200.h"
 #include "klerg_common.cuh"
@@ -61,7 +60,6 @@ struct FTArgs {
   unsigned char* scratch;
   int nch_sum, nch_all;
   long long ntiles;
-  int dbg;  // measurement switches (KLERG_FT_DEBUG): 1 = one MMA per chunk instead of three (wrong results)
 };
 
 // ---- centre of the states' bounding box (scaled coordinates) and the radius test ------------------------------
@@ -164,6 +162,9 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// Measured and not kept: taking every 3rd / 4th exponential off the MUFU pipe with a degree-4 polynomial on the FMA
+// pipe (the FlashAttention-4 trick) changed the pass by < 4 % (278 / 286 against 288 ms with the switch compiled in):
+// ncu shows the XU pipe at 81 % with the MIO queue as the top stall - the practical ceiling of MUFU-fed code here.
 template <bool SUMMED>
 __device__ __forceinline__ void ft_consume(const uint32_t (&r)[32], float (&s)[4], float& emin) {
 #pragma unroll
@@ -263,22 +264,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
         float s[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t ra[32], rb[32];
         const bool summed = c < a.nch_sum;
+#define FT_CONSUME(R)                      \
+  if (summed) ft_consume<true>(R, s, emin); \
+  else ft_consume<false>(R, s, emin)
         tmem_ld32(acc, ra);
         tmem_ld_wait32(ra);
         tmem_ld32(acc + 32, rb);
-        if (summed) ft_consume<true>(ra, s, emin); else ft_consume<false>(ra, s, emin);
+        FT_CONSUME(ra);
         tmem_ld_wait32(rb);
         tmem_ld32(acc + 64, ra);
-        if (summed) ft_consume<true>(rb, s, emin); else ft_consume<false>(rb, s, emin);
+        FT_CONSUME(rb);
         tmem_ld_wait32(ra);
         tmem_ld32(acc + 96, rb);
-        if (summed) ft_consume<true>(ra, s, emin); else ft_consume<false>(ra, s, emin);
+        FT_CONSUME(ra);
         tmem_ld_wait32(rb);
         // the accumulator is in registers: hand the buffer back before the last quarter is consumed
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(&acc_empty[g]);
-        if (summed) ft_consume<true>(rb, s, emin); else ft_consume<false>(rb, s, emin);
+        FT_CONSUME(rb);
         total += (s[0] + s[1]) + (s[2] + s[3]);  // per-chunk partial: the rounding error grows with sqrt(chunks)
       }
       // combine the two warpgroups; all chunks of the tile are consumed -> every MMA that read A has completed
@@ -335,13 +339,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
           const uint32_t b0 = smem_addr(ring + (size_t)s * FT_CHUNK_BYTES);
           const uint64_t db_hi = smem_desc(b0, FT_ROWS * 16, 128), db_lo = smem_desc(b0 + 2 * FT_ROWS * 16, FT_ROWS * 16, 128);
           const uint32_t d = tmem + (uint32_t)(buf * 128);
-          if (a.dbg & 1) {
-            tc_mma_tf32_ts(d, a_hi, db_hi, idesc, 0u);
-          } else {
-            tc_mma_tf32_ts(d, a_lo, db_hi, idesc, 0u);
-            tc_mma_tf32_ts(d, a_hi, db_lo, idesc, 1u);
-            tc_mma_tf32_ts(d, a_hi, db_hi, idesc, 1u);
-          }
+          tc_mma_tf32_ts(d, a_lo, db_hi, idesc, 0u);
+          tc_mma_tf32_ts(d, a_hi, db_lo, idesc, 1u);
+          tc_mma_tf32_ts(d, a_hi, db_hi, idesc, 1u);
           tc_commit(&b_empty[s]);
           tc_commit(&acc_full[buf]);
         }
@@ -396,10 +396,6 @@ extern "C" int klerg_footprint_sum_max_tc(const klerg_kernel_spec* k, const floa
   a.nch_sum = (int)((T_sum + FT_ROWS - 1) / FT_ROWS);
   a.nch_all = a.nch_sum + (int)((T - T_sum + FT_ROWS - 1) / FT_ROWS);
   a.ntiles = (N + 127) / 128;
-  {
-    const char* e = getenv("KLERG_FT_DEBUG");
-    a.dbg = e ? atoi(e) : 0;
-  }
   ft_centre_kernel<<<1, 256, 0, st>>>(a);
   if (int rc = check_launch("ft_centre_kernel")) return rc;
   ft_pack_states_kernel<<<(unsigned)a.nch_all, FT_ROWS, 0, st>>>(a);
