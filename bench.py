@@ -562,6 +562,23 @@ def cuda_arm(args):
                 out["cpu_oracle_cores"] = ro["cores"]
             return out
 
+        # the dominant kernel of the e2e step: history footprint + spread of the memory buffer, ONE M x N pass, squared
+        # distances on the tensor cores (klerg_footprint_sum_max_tc) - its own bound is the MUFU pipe (one exp per pair)
+        if S["sets"] and args.workload == "c4":
+            c0 = S["sets"][0]
+            hist4 = wl.random_walk_history(args.workload, w["M"], seed=0).to(dev)
+            pairs4 = float(hist4.shape[0]) * c0.n
+            t_tc = timed(lambda: engine.footprint_sum_max(c0.spec, hist4, hist4.shape[0], c0.packed, c0.n, tensor_cores=True), 2)
+            t_cc = timed(lambda: engine.footprint_sum_max(c0.spec, hist4, hist4.shape[0], c0.packed, c0.n, tensor_cores=False), 2)
+            also["history_pass"] = {
+                "workload": f"{args.workload}: {hist4.shape[0]} buffer rows x {c0.n} samples, sum + max in one pass",
+                "ms_per_pass": t_tc * 1e3, "pairs_per_s": pairs4 / t_tc, "ms_cuda_core_pass": t_cc * 1e3,
+                "roofline": {"bound": "mufu", "achieved": pairs4 / t_tc, "peak": peaks["ex2_per_s"], "unit": "exp/s",
+                             "frac": pairs4 / t_tc / peaks["ex2_per_s"]},
+                "note": "e_ij as one K = 8 tcgen05.mma kind::tf32 step (3xTF32), min / exp / add on the CUDA cores; the "
+                        "CUDA-core pass (D + 4 lane-ops per pair, FP32-pipe bound) beside it"}
+            del hist4, c0
+
         S1 = build_sets("c1", wl.WORKLOADS["c1"]["N"], rank, group, dev, engine, Robot, PlannerContext, max_sets=8)
         r1 = timed_evals(args, S1, 2000, 20, world, rank, lib, dev)
         also["c1"] = {"workload": workload_config("c1", wl.WORKLOADS["c1"]["N"], S1["n"])["workload"],
