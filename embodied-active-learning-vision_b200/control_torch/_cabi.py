@@ -59,6 +59,12 @@ class PolicySpec(C.Structure):
     _fields_ = [("kind", C.c_int32), ("use_u", C.c_int32), ("weight", C.c_float), ("K", C.c_float * (8 * 24))]
 
 
+class TiltSpec(C.Structure):
+    _fields_ = [("r_idx", C.c_int32), ("p_idx", C.c_int32), ("w_idx", C.c_int32), ("has_map", C.c_int32),
+                ("w_lo", C.c_float), ("w_hi", C.c_float), ("tilt_lim", C.c_float), ("power", C.c_float), ("weight", C.c_float),
+                ("rot_lo", C.c_float * 2), ("rot_hi", C.c_float * 2), ("ang_lo", C.c_float * 2), ("ang_hi", C.c_float * 2)]
+
+
 class BarrierSpec(C.Structure):
     _fields_ = [("n", C.c_int32), ("lo", C.c_float * MAX_S), ("hi", C.c_float * MAX_S),
                 ("weight", C.c_float * MAX_S), ("power", C.c_float * MAX_S)]
@@ -135,6 +141,7 @@ SIGNATURES = {
     "klerg_target_stage3": [_P, _I64, _P, C.c_int, _F, _F, _P, _P, _P, _P],
     "klerg_rollout": [_DS, _BS, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P],
     "klerg_barrier_eval": [_BS, _P, _I64, _I32, _P, _P, _P],
+    "klerg_barrier_eval_ext": [_BS, _P, _P, C.POINTER(TiltSpec), _I64, _I32, _P, _P, _P, _P],
     "klerg_policy_rollout": [_DS, C.POINTER(PolicySpec), _P, _P, _P, _I64, _P, _P, _P],
     "klerg_adjoint_policy": [_DS, _I64, _P, _P, _P, _P, _P, C.POINTER(C.c_float), _F, C.POINTER(C.c_float),
                              C.POINTER(C.c_float), _P, _P, _P, _P],

@@ -463,6 +463,21 @@ def barrier_eval(bar, x, want_value=True, want_grad=True):
     return value, grad
 
 
+def barrier_eval_ext(bar, x, x_ref=None, tilt=None, want_value=True, want_grad=True):
+    """BarrierFunction with limits relative to ``x_ref`` rows (VelocityBarrier) and / or the tilt-dependent yaw limits
+    and tilt term of TiltBarrierFunction -> (value [T], grad [T,S], tilt [T] or None)."""
+    x = x.contiguous()
+    T, S = x.shape
+    value = torch.empty(T, dtype=torch.float32, device=x.device) if want_value else None
+    grad = torch.empty((T, S), dtype=torch.float32, device=x.device) if want_grad else None
+    tilt_out = torch.empty(T, dtype=torch.float32, device=x.device) if tilt is not None else None
+    cabi.check(cabi.load().klerg_barrier_eval_ext(
+        C.byref(bar) if bar is not None else None, cabi.ptr(x), cabi.ptr(x_ref.contiguous()) if x_ref is not None else None,
+        C.byref(tilt) if tilt is not None else None, T, S, cabi.ptr(value), cabi.ptr(grad), cabi.ptr(tilt_out),
+        cabi.stream_ptr()), "klerg_barrier_eval_ext")
+    return value, grad, tilt_out
+
+
 def adjoint(dyn, spec, grad_parts, dbarr, P, traj, u, rinv, alpha, ctrl_lo, ctrl_hi):
     """grad_parts [world,H,D] float64 -> dgdx [H,S], du [H,A], djdlam [H], u_star [H,A]."""
     world, H, D = grad_parts.shape

@@ -316,6 +316,58 @@ __global__ void barrier_eval_kernel(BarDev bar, const float* __restrict__ x, int
   }
 }
 
+struct TiltDev {
+  int on, r_idx, p_idx, w_idx, has_map;
+  float w_lo, w_hi, lim, power, weight;
+  float rot_lo[2], rot_hi[2], ang_lo[2], ang_hi[2];
+};
+
+// VelocityBarrier (limits relative to x_ref) and TiltBarrierFunction (tilt-dependent yaw limits + tilt term)
+__global__ void barrier_ext_kernel(BarDev bar, TiltDev tl, const float* __restrict__ x, const float* __restrict__ x_ref,
+                                   int64_t T, int S, float* __restrict__ value, float* __restrict__ grad,
+                                   float* __restrict__ tilt_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float row[KLERG_MAX_S], g[KLERG_MAX_S];
+  for (int i = 0; i < S; ++i) row[i] = x[t * S + i];
+  if (x_ref)
+    for (int i = 0; i < bar.n; ++i) {
+      bar.lo[i] += x_ref[t * S + i];
+      bar.hi[i] += x_ref[t * S + i];
+    }
+  float tv = 0.f, gr = 0.f, gp = 0.f;
+  if (tl.on) {
+    float r = row[tl.r_idx], p = row[tl.p_idx];
+    if (tl.has_map) {
+      r = affine_map(r, tl.rot_lo[0], tl.rot_hi[0], tl.ang_lo[0], tl.ang_hi[0]);
+      p = affine_map(p, tl.rot_lo[1], tl.rot_hi[1], tl.ang_lo[1], tl.ang_hi[1]);
+    }
+    float sr, cr, sp, cp;
+    sincosf(r, &sr, &cr);
+    sincosf(p, &sp, &cp);
+    const float tilt = acosf(cr * cp);
+    bar.lo[tl.w_idx] = tilt / 3.14159265358979323846f * tl.w_lo;
+    bar.hi[tl.w_idx] = tilt / 3.14159265358979323846f * tl.w_hi;
+    if (tilt <= tl.lim) {
+      const float d = tilt - tl.lim;
+      tv = tl.weight * powi_or_f(d, tl.power);
+      const float dd = tl.power * tl.weight * powi_or_f(d, tl.power - 1.f) / sqrtf(-cp * cp * cr * cr + 1.f);
+      gr = dd * sr * cp;
+      gp = dd * sp * cr;
+    }
+    if (tilt_out) tilt_out[t] = tilt;
+  }
+  if (value) value[t] = tv + barrier_value(bar, row);
+  if (grad) {
+    barrier_grad(bar, row, S, g);
+    if (tl.on) {
+      g[tl.r_idx] += gr;
+      g[tl.p_idx] += gp;
+    }
+    for (int i = 0; i < S; ++i) grad[t * S + i] = g[i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // adjoint sweep (klerg.py:433-450, 590-593): stage inputs in shared memory, then adjoint_block
 // ---------------------------------------------------------------------------
@@ -656,6 +708,30 @@ extern "C" int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x,
   if (T < 1) return 0;
   barrier_eval_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(b, x, T, S, value, grad);
   return check_launch("barrier_eval_kernel");
+}
+
+extern "C" int klerg_barrier_eval_ext(const klerg_barrier_spec* bar, const float* x, const float* x_ref, const klerg_tilt_spec* tilt,
+                                      int64_t T, int32_t S, float* value, float* grad, float* tilt_out, void* stream) {
+  BarDev b;
+  if (!make_bar(bar, b)) return -1;
+  if (S < 1 || S > KLERG_MAX_S) { set_error("barrier_eval_ext: S out of range"); return -1; }
+  TiltDev tl{};
+  if (tilt) {
+    if (tilt->r_idx < 0 || tilt->r_idx >= S || tilt->p_idx < 0 || tilt->p_idx >= S || tilt->w_idx < 0 || tilt->w_idx >= b.n) {
+      set_error("barrier_eval_ext: tilt indices out of range");
+      return -1;
+    }
+    tl.on = 1; tl.r_idx = tilt->r_idx; tl.p_idx = tilt->p_idx; tl.w_idx = tilt->w_idx; tl.has_map = tilt->has_map;
+    tl.w_lo = tilt->w_lo; tl.w_hi = tilt->w_hi; tl.lim = tilt->tilt_lim; tl.power = tilt->power; tl.weight = tilt->weight;
+    for (int k = 0; k < 2; ++k) {
+      tl.rot_lo[k] = tilt->rot_lo[k]; tl.rot_hi[k] = tilt->rot_hi[k];
+      tl.ang_lo[k] = tilt->ang_lo[k]; tl.ang_hi[k] = tilt->ang_hi[k];
+    }
+  }
+  if (T < 1) return 0;
+  if (!x) { set_error("barrier_eval_ext: null input"); return -1; }
+  barrier_ext_kernel<<<(unsigned)((T + 127) / 128), 128, 0, (cudaStream_t)stream>>>(b, tl, x, x_ref, T, S, value, grad, tilt_out);
+  return check_launch("barrier_ext_kernel");
 }
 
 // ---------------------------------------------------------------------------

@@ -245,6 +245,23 @@ int klerg_adjoint_policy(const klerg_dyn_spec* dyn, int64_t H, const float* dgdx
 int klerg_barrier_eval(const klerg_barrier_spec* bar, const float* x, int64_t T, int32_t S,
                        float* value, float* grad, void* stream);
 
+/* The two barrier variants the reference keeps beside BarrierFunction (never instantiated by its Robot):
+ *   x_ref != NULL  VelocityBarrier (barrier.py:162-205): the limits of row t are x_ref[t] + {lo, hi} (a band around
+ *                  the other state; weight 0 on the rows the band does not apply to);
+ *   tilt != NULL   TiltBarrierFunction (barrier.py:95-144): tilt = acos(cos r cos p) of the (mapped) roll / pitch
+ *                  angles; the yaw limits become tilt/pi * {w_lo, w_hi}; value += [tilt <= tilt_lim] weight
+ *                  (tilt - tilt_lim)^power, and its derivative lands on the r and p columns (no chain factor for the
+ *                  map, as in the reference).  tilt_out [T] (optional) receives the tilt of every row (the reference
+ *                  leaves the yaw limits of the LAST evaluated row in the wrapped barrier). */
+typedef struct klerg_tilt_spec {
+  int32_t r_idx, p_idx, w_idx, has_map;
+  float w_lo, w_hi;
+  float tilt_lim, power, weight;
+  float rot_lo[2], rot_hi[2], ang_lo[2], ang_hi[2]; /* affine map of r, p from state units to angles */
+} klerg_tilt_spec;
+int klerg_barrier_eval_ext(const klerg_barrier_spec* bar, const float* x, const float* x_ref, const klerg_tilt_spec* tilt,
+                           int64_t T, int32_t S, float* value, float* grad, float* tilt_out, void* stream);
+
 /* ---- a10: adjoint sweep of Robot.backward (klerg.py:433-450, 590-593) ----- */
 
 /* grad_part: `world` blocks of [H][D] doubles (klerg_kl_gradient_fused), summed

@@ -443,6 +443,43 @@ def roll_controls(u, shift):
     return u
 
 
+def tilt_barrier(x, lo, hi, weight, power, r_idx, p_idx, w_idx, w_lim, tilt_lim, tilt_power=4, tilt_weight=10.0,
+                 ang_map=None):
+    """TiltBarrierFunction.barr / dbarr for one state (barrier.py:95-144) -> (value, grad, tilt).  lo / hi / weight /
+    power: the wrapped BarrierFunction's rows (limits already shrunk); w_lim: its ORIGINAL yaw limits [2];
+    ang_map = (in_lim, out_lim) [3,2] of the rot -> angle map or None."""
+    r, p = x[r_idx], x[p_idx]
+    if ang_map is not None:
+        i, o = ang_map
+        r = (r - i[0, 0]) / (i[0, 1] - i[0, 0]) * (o[0, 1] - o[0, 0]) + o[0, 0]
+        p = (p - i[1, 0]) / (i[1, 1] - i[1, 0]) * (o[1, 1] - o[1, 0]) + o[1, 0]
+    tilt = torch.arccos(torch.cos(r) * torch.cos(p))
+    lo, hi = lo.clone(), hi.clone()
+    lo[w_idx], hi[w_idx] = tilt / torch.pi * w_lim[0], tilt / torch.pi * w_lim[1]
+    n = len(lo)
+    below, above = (x[:n] <= lo).to(x.dtype), (x[:n] >= hi).to(x.dtype)
+    value = torch.sum(weight * (below * (x[:n] - lo) ** power + above * (x[:n] - hi) ** power))
+    grad = torch.zeros_like(x)
+    grad[:n] = power * weight * (below * (x[:n] - lo) ** (power - 1) + above * (x[:n] - hi) ** (power - 1))
+    if tilt <= tilt_lim:
+        value = value + tilt_weight * (tilt - tilt_lim) ** tilt_power
+        common = tilt_power * tilt_weight * (tilt - tilt_lim) ** (tilt_power - 1) / torch.sqrt(1 - torch.cos(p) ** 2 * torch.cos(r) ** 2)
+        grad[r_idx] += common * torch.sin(r) * torch.cos(p)
+        grad[p_idx] += common * torch.sin(p) * torch.cos(r)
+    return value, grad, tilt
+
+
+def velocity_barrier(x_new, x_old, band, weight, power, skip):
+    """VelocityBarrier.barr / dbarr for one pair of states (barrier.py:162-205): band [S,2] around x_old on the rows
+    that are not skipped -> (value, grad wrt x_new)."""
+    lim = x_old.unsqueeze(1) + band
+    use = torch.tensor([0.0 if s else 1.0 for s in skip], dtype=x_new.dtype)
+    above, below = (x_new >= lim[:, 1]).to(x_new.dtype), (x_new <= lim[:, 0]).to(x_new.dtype)
+    value = torch.sum(use * weight * (above * (x_new - lim[:, 1]) ** power + below * (x_new - lim[:, 0]) ** power))
+    grad = use * power * weight * (above * (x_new - lim[:, 1]) ** (power - 1) + below * (x_new - lim[:, 0]) ** (power - 1))
+    return value, grad
+
+
 class OracleFeedback:
     """The state-feedback default policies (default_policies.py:53-119) as one rule ``act(x, planned) -> (u, dmudx)``.
 

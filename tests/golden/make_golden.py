@@ -195,12 +195,52 @@ def record_utils(ru, rb, rd, rm):
     print("utils ->", len(out), "arrays")
 
 
+def record_barrier_variants(rb):
+    """TiltBarrierFunction and VelocityBarrier (barrier.py:95-144, 162-205): the two variants the reference keeps
+    beside BarrierFunction -> barrier_variants.npz."""
+    from control_torch.klerg_utils import Lambda
+    from franka.franka_utils import ws_conversion
+    out = {}
+    g = torch.Generator().manual_seed(23)
+    lim = torch.tensor([[-1.0, 1.0], [-1.0, 1.0], [-0.75, 0.75], [2.39, 3.89], [-0.75, 0.75], [-2.0, 2.0]] + [[-1.25, 1.25]] * 6)
+    xs = torch.rand(48, 12, generator=g) * 2.4 - 1.2
+    xs[:, 3] = 2.0 + 2.2 * torch.rand(48, generator=g)
+    xs[:, 5] = 5.0 * torch.rand(48, generator=g) - 2.5
+    out["tilt/lim"], out["tilt/x"] = lim.numpy(), xs.numpy()
+    robot_rpw = torch.tensor([[0.0, 1.0], [0.0, 1.0], [0.0, 1.0]])
+    tray_rpw = torch.tensor([[2.39, 3.89], [-0.75, 0.75], [-2.0, 2.0]])
+    for tag, fn, x_in in (("plain", None, xs), ("mapped", Lambda(ws_conversion, (robot_rpw, tray_rpw)), None)):
+        if x_in is None:  # roll / pitch / yaw columns in the unit "robot" range the map expects
+            x_in = xs.clone()
+            x_in[:, 3:6] = torch.rand(48, 3, generator=g) * 1.3 - 0.15
+            out["tilt/x_mapped"] = x_in.numpy()
+        other = rb.BarrierFunction(b_lim=lim, barr_weight=5.0, b_buff=0.1, power=[4.0] * 12)
+        bar = rb.TiltBarrierFunction(other, "xyzrpw", tilt_lim=2.45, rot_to_angles_fn=fn)
+        out[f"tilt/{tag}/w_b_lim"] = bar.w_b_lim.numpy().copy()
+        out[f"tilt/{tag}/value"] = bar(x_in).numpy()
+        out[f"tilt/{tag}/grad"] = torch.stack([bar.dbarr(x) for x in x_in]).numpy()
+        out[f"tilt/{tag}/w_lim_after"] = other.b_lim[5].numpy().copy()
+    vb = rb.VelocityBarrier("xyzXYZ", b_lim=0.1, power=4, barr_weight=100.0)
+    x_old = torch.rand(40, 6, generator=g) * 2 - 1
+    x_new = x_old + 0.5 * (torch.rand(40, 6, generator=g) - 0.5)
+    x_new[3] = x_old[3]
+    x_new[4, 3:] = x_old[4, 3:] + torch.tensor([0.1, -0.1, 0.05])  # exactly on / inside the band
+    out["vel/x_old"], out["vel/x_new"] = x_old.numpy(), x_new.numpy()
+    out["vel/value"] = torch.stack([vb.barr(a, b) for a, b in zip(x_new, x_old)]).numpy()
+    out["vel/grad"] = torch.stack([vb.dbarr(a, b) for a, b in zip(x_new, x_old)]).numpy()
+    out["vel/call"] = vb(x_old, x_new).numpy()
+    np.savez_compressed(os.path.join(HERE, "barrier_variants.npz"), **out)
+    print("barrier variants ->", len(out), "arrays")
+
+
 def main():
     rk, ru, rb, rd, rm = import_reference()
     torch.set_num_threads(1)  # fixed reduction order for reproducible fixtures
     only = sys.argv[1:]  # optional: names of the robot cases to (re)record; default = everything
     if not only:
         record_utils(ru, rb, rd, rm)
+    if not only or "barrier_variants" in only:
+        record_barrier_variants(rb)
     for name, case in ROBOT_CASES.items():
         if not only or name in only:
             record_robot_case(rk, name, case)
