@@ -44,8 +44,13 @@ static_assert(FT_ACOL + 16 <= 512, "TMEM has 512 columns");
 struct FTHeader {
   float ctr[8];
   int ok;       // 1: every state lies within the expanded form's radius of the centre -> the tensor-core pass runs
-  int pad[7];
+  int pad;
+  unsigned long long next_tile;  // tiles are handed out on demand (zeroed by ft_centre_kernel before every pass)
+  int pad2[4];
+  double stats[4];               // {sum, max, min, #nan} of out_sum (klerg_vector_stats layout) -> totals
 };
+static_assert(sizeof(FTHeader) <= 256, "scratch header");
+constexpr int FT_TSLOTS = 8;  // ring of tile announcements
 
 struct FTArgs {
   KernelDev k;
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(256) ft_centre_kernel(const FTArgs a) {
     for (int w = 1; w < 8; ++w) r2 = fmaxf(r2, s_r2[w]);
     for (int d = 0; d < 8; ++d) h->ctr[d] = c[d];
     h->ok = (r2 <= a.k.x_r2) ? 1 : 0;  // NaN rows fail the test too
+    h->next_tile = 0ull;
   }
 }
 
@@ -185,9 +191,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
   unsigned long long* acc_full = b_empty + FT_STAGES;  // [FT_NWG]
   unsigned long long* acc_empty = acc_full + FT_NWG;   // [FT_NWG]
   unsigned long long* a_full = acc_empty + FT_NWG;     // [1]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(a_full + 1);
+  unsigned long long* tile_ready = a_full + 1;         // [FT_TSLOTS]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tile_ready + FT_TSLOTS);
   volatile unsigned* s_abort = reinterpret_cast<volatile unsigned*>(s_tmem + 1);
-  float* s_x = reinterpret_cast<float*>(s_tmem + 4);   // [FT_NWG - 1][128][2]: the other warpgroups' {sum, min} of the tile
+  volatile int* s_tile = reinterpret_cast<volatile int*>(s_tmem + 4);  // [FT_TSLOTS] announced tile (or -1: no more)
+  float* s_x = reinterpret_cast<float*>(s_tmem + 4 + FT_TSLOTS);  // [FT_NWG - 1][128][2]: the other warpgroups' {sum, min} of the tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = a.nch_all;
@@ -201,6 +209,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
       bar_init(&acc_empty[g], 4);
     }
     bar_init(a_full, 128);
+    for (int q = 0; q < FT_TSLOTS; ++q) bar_init(&tile_ready[q], 1);
     *s_abort = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -212,8 +221,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
-  const int my_tiles = (int)((a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles blockIdx.x, + gridDim.x, ...
-  double tsum = 0.0, tmax = -INFINITY;
+  // Tiles (128 samples) are handed out on demand: the TMA thread - the role that runs furthest ahead - draws the next
+  // tile number from a global counter and announces it (or -1) to the other roles through a ring of FT_TSLOTS slots,
+  // each guarded by an mbarrier.  An SM that is slowed down (it may host the side-stream draw of the next step,
+  // engine.UniformPrefetch) simply takes fewer tiles.  Slot reuse is safe by construction: the TMA thread runs at most
+  // FT_STAGES + FT_NWG chunks ahead of the slowest epilogue warp, i.e. < FT_TSLOTS tiles with >= 2 chunks per tile.
 
   if (warp < 4 * FT_NWG) {
     // ================= epilogue warpgroups =================
@@ -225,8 +237,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
 #pragma unroll
     for (int d = 0; d < 8; ++d) ctr[d] = hdr->ctr[d];
     long long gc = 0;  // chunks of this CTA so far (all tiles)
-    for (int it = 0; it < my_tiles; ++it) {
-      const long long tile = blockIdx.x + (long long)it * gridDim.x;
+    for (int it = 0;; ++it) {
+      bar_wait(&tile_ready[it & (FT_TSLOTS - 1)], (unsigned)((it / FT_TSLOTS) & 1), s_abort);
+      const long long tile = s_tile[it & (FT_TSLOTS - 1)];
+      if (tile < 0 || *s_abort) break;
       const long long i = tile * 128 + row;
       if (g == 0) {
         // A rows of the tile: a_i = (sc_i, 0.., |sc_i|^2, 1) as tf32 hi | lo
@@ -298,11 +312,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
           emin = fminf(emin, s_x[(o * 128 + row) * 2 + 1]);
         }
         if (i < a.N) {
-          const float v = total * a.k.inv_nu;
-          a.out_sum[i] = v;
+          a.out_sum[i] = total * a.k.inv_nu;
           a.out_max[i] = ex2_neg(emin) * a.k.inv_nu;
-          tsum += (double)v;
-          tmax = fmax(tmax, (double)v);
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(128 * FT_NWG) : "memory");  // s_x may be rewritten, A may be overwritten
@@ -311,8 +322,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
     // ================= B chunks: TMA bulk copies into the ring =================
     if (lane == 0) {
       const unsigned char* src = a.scratch + FT_HDR;
+      unsigned long long* next = &reinterpret_cast<FTHeader*>(a.scratch)->next_tile;
       long long gc = 0;
-      for (int it = 0; it < my_tiles; ++it)
+      for (int it = 0;; ++it) {
+        const unsigned long long t = atomicAdd(next, 1ull);
+        s_tile[it & (FT_TSLOTS - 1)] = t < (unsigned long long)a.ntiles ? (int)t : -1;
+        bar_arrive(&tile_ready[it & (FT_TSLOTS - 1)]);
+        if (t >= (unsigned long long)a.ntiles || *s_abort) break;
         for (int c = 0; c < nch; ++c, ++gc) {
           const int s = (int)(gc % FT_STAGES);
           const unsigned k = (unsigned)(gc / FT_STAGES);
@@ -320,6 +336,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
           bar_expect_tx(&b_full[s], FT_CHUNK_BYTES);
           bulk_g2s(ring + (size_t)s * FT_CHUNK_BYTES, src + (size_t)c * FT_CHUNK_BYTES, FT_CHUNK_BYTES, &b_full[s]);
         }
+      }
     }
   } else {
     // ================= MMA issue =================
@@ -327,7 +344,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
       const uint32_t idesc = instr_desc_tf32(128, FT_ROWS);
       const uint32_t a_hi = tmem + FT_ACOL, a_lo = a_hi + 8;
       long long gc = 0;
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = 0;; ++it) {
+        bar_wait(&tile_ready[it & (FT_TSLOTS - 1)], (unsigned)((it / FT_TSLOTS) & 1), s_abort);
+        if (s_tile[it & (FT_TSLOTS - 1)] < 0 || *s_abort) break;
         bar_wait(a_full, (unsigned)(it & 1), s_abort);
         tc_fence_after();
         for (int c = 0; c < nch; ++c, ++gc) {
@@ -356,9 +375,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
   if (threadIdx.x == 0 && *s_abort) atomicExch(ws_fused_ctrl(a.ws) + 5, 1u);  // the sticky fault word of the workspace
-  const int kinds[2] = {RED_SUM, RED_MAX};
-  double vals[2] = {tsum, tmax};
-  grid_reduce<2>(kinds, vals, ws_seg_partials(a.ws, 0), ws_seg_counter(a.ws, 0), blockIdx.x, gridDim.x, a.totals);
+}
+
+// totals[0..1] = {sum, max} of out_sum from the stats a klerg_vector_stats pass left in the header (fixed summation
+// order: the totals do not depend on which SM took which tile)
+__global__ void ft_totals_kernel(const unsigned char* scratch, double* totals) {
+  const FTHeader* h = reinterpret_cast<const FTHeader*>(scratch);
+  if (!h->ok) return;  // the fallback pass writes its own
+  totals[0] = h->stats[0];
+  totals[1] = h->stats[1];
 }
 
 }  // namespace
@@ -396,11 +421,13 @@ extern "C" int klerg_footprint_sum_max_tc(const klerg_kernel_spec* k, const floa
   a.nch_sum = (int)((T_sum + FT_ROWS - 1) / FT_ROWS);
   a.nch_all = a.nch_sum + (int)((T - T_sum + FT_ROWS - 1) / FT_ROWS);
   a.ntiles = (N + 127) / 128;
+  if (a.nch_all < 2) { set_error("footprint_sum_max_tc: at least two 128-row chunks of states (T > 128) are required"); return -1; }
   ft_centre_kernel<<<1, 256, 0, st>>>(a);
   if (int rc = check_launch("ft_centre_kernel")) return rc;
   ft_pack_states_kernel<<<(unsigned)a.nch_all, FT_ROWS, 0, st>>>(a);
   if (int rc = check_launch("ft_pack_states_kernel")) return rc;
-  size_t smem = (size_t)FT_STAGES * FT_CHUNK_BYTES + 8 * (2 * FT_STAGES + 2 * FT_NWG + 1) + 16 + sizeof(float) * 256 * (FT_NWG - 1) + 64;
+  size_t smem = (size_t)FT_STAGES * FT_CHUNK_BYTES + 8 * (2 * FT_STAGES + 2 * FT_NWG + 1 + FT_TSLOTS) + 16 + 4 * FT_TSLOTS +
+                sizeof(float) * 256 * (FT_NWG - 1) + 64;
   if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
   static bool raised = false;
   if (!raised) {
@@ -412,6 +439,9 @@ extern "C" int klerg_footprint_sum_max_tc(const klerg_kernel_spec* k, const floa
   if (grid > a.ntiles) grid = a.ntiles;
   footprint_tc_kernel<<<(unsigned)grid, FT_THREADS, smem, st>>>(a);
   if (int rc = check_launch("footprint_tc_kernel")) return rc;
+  if (int rc = klerg_vector_stats(out_sum, N, reinterpret_cast<FTHeader*>(scratch)->stats, workspace, stream)) return rc;
+  ft_totals_kernel<<<1, 1, 0, st>>>((const unsigned char*)scratch, totals);
+  if (int rc = check_launch("ft_totals_kernel")) return rc;
   // states outside the expanded form's radius: the CUDA-core pass (returns at once when the header says ok)
   return launch_footprint_sum_max_gated(kd, states, T, T_sum, packed, N, ld, out_sum, out_max, totals, workspace,
                                         &reinterpret_cast<const FTHeader*>(scratch)->ok, st);

@@ -32,7 +32,7 @@ def _flag(engine):
     return int(sc[32:36].view(torch.int32).item())
 
 
-@pytest.mark.parametrize("D,S,N,T,T_sum", [(6, 12, 5000, 700, 300), (6, 12, 128, 256, 256), (3, 6, 1000, 513, 0),
+@pytest.mark.parametrize("D,S,N,T,T_sum", [(6, 12, 5000, 700, 300), (6, 12, 128, 256, 256), (3, 6, 1000, 513, 0), (6, 12, 150_000, 300, 200),
                                            (2, 4, 777, 1000, 1000), (6, 12, 4097, 2000, 1500), (4, 8, 130, 129, 1),
                                            (6, 12, 33_000, 3_000, 2_999)])
 def test_tensor_core_pass_matches_cuda_cores_and_oracle(D, S, N, T, T_sum):

@@ -32,6 +32,7 @@ class range_probe:
 
 
 def run(name, steps=40):
+    steps = 6 if wl.WORKLOADS[name]["N"] >= 1_000_000 else steps
     w = wl.WORKLOADS[name]
     lims = [wl.LIMS[s] for s in w["states"]]
     target = wl.make_target(w["target"], lims, seed=1, device=torch.device("cuda"))
