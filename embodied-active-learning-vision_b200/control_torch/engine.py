@@ -273,7 +273,9 @@ def footprint_sum_max(spec, states, t_sum, packed, n, tensor_cores=None):
     out_sum = torch.empty(ld, dtype=torch.float32, device=packed.device)
     out_max = torch.empty(ld, dtype=torch.float32, device=packed.device)
     totals = torch.empty(2, dtype=torch.float64, device=packed.device)
-    use_tc = tensor_cores if tensor_cores is not None else (FOOTPRINT_TC and spec.D <= 6 and T >= 256
+    # long state lists only: a 128-sample tile pays its fixed work (A rows into TMEM, two CTA-wide meetings) once per
+    # T / 128 chunks
+    use_tc = tensor_cores if tensor_cores is not None else (FOOTPRINT_TC and spec.D <= 6 and T >= 1024
                                                            and T * int(n) >= FOOTPRINT_TC_MIN_PAIRS)
     if use_tc and T > 0 and n > 0:
         lib = cabi.load()
