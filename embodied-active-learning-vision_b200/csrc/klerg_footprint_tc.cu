@@ -171,13 +171,15 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
 // Measured and not kept: taking every 3rd / 4th exponential off the MUFU pipe with a degree-4 polynomial on the FMA
 // pipe (the FlashAttention-4 trick) changed the pass by < 4 % (278 / 286 against 288 ms with the switch compiled in):
 // ncu shows the XU pipe at 81 % with the MIO queue as the top stall - the practical ceiling of MUFU-fed code here.
+// eight independent sum chains and two min chains per thread: the dependent FADD / FMNMX latencies stay off the
+// critical path of the three warps that share a scheduler
 template <bool SUMMED>
-__device__ __forceinline__ void ft_consume(const uint32_t (&r)[32], float (&s)[4], float& emin) {
+__device__ __forceinline__ void ft_consume(const uint32_t (&r)[32], float (&s)[8], float (&emin)[2]) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const float e = __uint_as_float(r[j]);
-    emin = fminf(emin, e);
-    if (SUMMED) s[j & 3] += ex2_neg(e);
+    emin[(j >> 1) & 1] = fminf(emin[(j >> 1) & 1], e);
+    if (SUMMED) s[j & 7] += ex2_neg(e);
   }
 }
 
@@ -269,18 +271,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
         tc_fence_before();
         bar_arrive(a_full);
       }
-      float total = 0.f, emin = INFINITY;
+      float total = 0.f, emin2[2] = {INFINITY, INFINITY};
       for (int c = 0; c < nch; ++c, ++gc) {
         if ((int)(gc % FT_NWG) != g) continue;
         bar_wait(&acc_full[g], (unsigned)((gc / FT_NWG) & 1), s_abort);
         tc_fence_after();
         const uint32_t acc = trow + (uint32_t)(g * 128);
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint32_t ra[32], rb[32];
         const bool summed = c < a.nch_sum;
-#define FT_CONSUME(R)                      \
-  if (summed) ft_consume<true>(R, s, emin); \
-  else ft_consume<false>(R, s, emin)
+#define FT_CONSUME(R)                       \
+  if (summed) ft_consume<true>(R, s, emin2); \
+  else ft_consume<false>(R, s, emin2)
         tmem_ld32(acc, ra);
         tmem_ld_wait32(ra);
         tmem_ld32(acc + 32, rb);
@@ -297,9 +299,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
         __syncwarp();
         if (lane == 0) bar_arrive(&acc_empty[g]);
         FT_CONSUME(rb);
-        total += (s[0] + s[1]) + (s[2] + s[3]);  // per-chunk partial: the rounding error grows with sqrt(chunks)
+        total += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));  // per-chunk partial: the rounding error grows with sqrt(chunks)
       }
       // combine the two warpgroups; all chunks of the tile are consumed -> every MMA that read A has completed
+      float emin = fminf(emin2[0], emin2[1]);
       if (g > 0) {
         s_x[((g - 1) * 128 + row) * 2] = total;
         s_x[((g - 1) * 128 + row) * 2 + 1] = emin;
