@@ -5,8 +5,8 @@
 //     e_ij = |sc_i|^2 + |xc_j|^2 - 2 xc_j . sc_i = a_i . b_j,
 //     a_i = (sc_i[0..D), 0.., |sc_i|^2, 1),   b_j = (-2 xc_j[0..D), 0.., 1, |xc_j|^2)
 // (sc = scaled sample - c, xc = scaled state - c, c = centre of the states' bounding box), i.e. exactly ONE K = 8
-// step of a tf32 MMA.  With the 3xTF32 split (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation) the result has
-// fp32-grade accuracy as long as the states stay within the radius of the expanded form around c (the same bound the
+// step of a tf32 MMA.  With the 3xTF32 split (a_lo b_hi + a_hi b_lo + a_hi b_hi, both halves rounded to tf32, fp32
+// accumulation) the result has fp32-grade accuracy as long as the states stay within the radius of the expanded form around c (the same bound the
 // CUDA-core kernels use, KernelDev::x_r2); otherwise the launch falls back to footprint_kernel (gated on the device).
 //
 // What is left for the CUDA cores per pair is what no tensor core can do: min, ex2, add - the pass becomes
@@ -144,10 +144,13 @@ __global__ void __launch_bounds__(FT_ROWS) ft_pack_states_kernel(const FTArgs a)
     }
     b[7] = n;
   }
+  // Both halves are ROUNDED to tf32 (cvt.rna): truncating them - a plain mask for hi, the tensor core's own reading of
+  // the low 13 bits for lo - doubles each half's error and quadruples the dropped lo * lo term; at the edge of the
+  // radius that is the difference between 1.5e-4 and 4e-5 on psi (tests/test_tc_distance_model.py).
   uint32_t hi[8], lo[8];
   for (int d = 0; d < 8; ++d) {
-    hi[d] = __float_as_uint(b[d]) & 0xFFFFE000u;
-    lo[d] = __float_as_uint(b[d] - __uint_as_float(hi[d]));
+    hi[d] = rna_tf32(b[d]);
+    lo[d] = rna_tf32(b[d] - __uint_as_float(hi[d]));
   }
   unsigned char* base = a.scratch + FT_HDR + (size_t)c * FT_CHUNK_BYTES + (size_t)r * 16;
   *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -262,8 +265,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) footprint_tc_kernel(const FTArg
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
-          hi[d] = __float_as_uint(av[d]) & 0xFFFFE000u;
-          lo[d] = __float_as_uint(av[d] - __uint_as_float(hi[d]));
+          hi[d] = rna_tf32(av[d]);
+          lo[d] = rna_tf32(av[d] - __uint_as_float(hi[d]));
         }
         tmem_st8(trow + FT_ACOL, hi);
         tmem_st8(trow + FT_ACOL + 8, lo);

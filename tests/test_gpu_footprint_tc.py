@@ -82,3 +82,37 @@ def test_tensor_core_pass_validation():
     assert b"bad sizes" in lib.klerg_last_error()
     assert lib.klerg_footprint_sum_max_tc(C.byref(spec), None, 10, 5, None, 100, 100, None, None, None, None, None, 0, None) != 0
     assert b"null" in lib.klerg_last_error()
+
+
+@pytest.mark.parametrize("D", [2, 3, 6])
+def test_tensor_core_pass_at_the_edge_of_the_radius_vs_float64(D):
+    """States up to |xc|^2 = 95 (in kernel widths) from the centre - the edge of what the radius guard admits - and
+    samples a few widths from them: sum and max against a float64 evaluation of the same fp32 inputs, 1e-4."""
+    import math
+    from control_torch import _cabi as cabi, engine
+    S, N, T = 2 * D, 2500, 1200
+    g = torch.Generator().manual_seed(40 + D)
+    std = 0.05
+    a = math.sqrt(0.5 * math.log2(math.e) / std)  # scaled coordinate = a * x
+    dirs = torch.randn(T, D, generator=g)
+    dirs = dirs / dirs.norm(dim=1, keepdim=True)
+    radii = torch.sqrt(torch.rand(T, 1, generator=g)) * math.sqrt(95.0) / a
+    radii[:2 * D] = math.sqrt(95.0) / a
+    pos = dirs * radii
+    for d in range(D):  # the bounding box is symmetric, so the centre is the origin and |xc|^2 reaches 95
+        pos[2 * d] = 0.0
+        pos[2 * d, d] = math.sqrt(95.0) / a
+        pos[2 * d + 1] = -pos[2 * d]
+    states = torch.zeros(T, S)
+    states[:, :D] = pos
+    samples = (pos[torch.randint(0, T, (N,), generator=g)] + torch.randn(N, D, generator=g) * (1.5 / a)).contiguous()
+    spec = cabi.kernel_spec(D, S, list(range(D)), [std] * D, 1.0)
+    dev = torch.device("cuda")
+    packed = engine.pack_samples(spec, samples.to(dev))
+    s_tc, m_tc, _ = engine.footprint_sum_max(spec, states.to(dev), T, packed, N, tensor_cores=True)
+    torch.cuda.synchronize()
+    assert _flag(engine) == 1
+    d2 = ((samples.double().unsqueeze(1) - pos.double().unsqueeze(0)) ** 2).sum(2) / (2.0 * std)  # klerg_utils.py:7-10
+    psi = torch.exp(-d2)
+    np.testing.assert_allclose(s_tc[:N].cpu().double().numpy(), psi.sum(1).numpy(), rtol=1e-4)
+    np.testing.assert_allclose(m_tc[:N].cpu().double().numpy(), psi.max(1).values.numpy(), rtol=1e-4)
