@@ -75,31 +75,31 @@ class BarrierPush(torch.nn.Module):
 
     def reset(self, x=None, u=None, iter_idx=0):
         self._use_u = iter_idx > 0
-        self.u = iter(u) if iter_idx > 0 else iter([])
+        self.u = iter(u) if self._use_u else iter([])
         return u
 
-    def _active(self, x, i):
-        lo, hi = self.b_lim[i]
-        v = x[i + self.num_actions]
-        return bool(((x[i] >= hi) and (v > 0)) or ((x[i] <= lo) and (v < 0)))
+    def _pushed(self, x):
+        """Mask [A]: positions on (or beyond) a wall of their +-1 box with the velocity pointing outwards."""
+        a = self.num_actions
+        box = torch.as_tensor(self.b_lim[:a], dtype=x.dtype)
+        pos, vel = x[:a], x[a:2 * a]
+        free = torch.tensor(self.skip[:a])
+        return (((pos >= box[:, 1]) & (vel > 0)) | ((pos <= box[:, 0]) & (vel < 0))) & ~free
 
     def clipped(self, x, u):
-        for i, skip in enumerate(self.skip):
-            if not skip and self._active(x, i):
-                u[i] = -self.weight * x[i + self.num_actions]
+        hit = self._pushed(x)
+        u[hit] = -self.weight * x[self.num_actions:2 * self.num_actions][hit]  # in place: u is a row of the plan
         return u
 
     def dx(self, x=None, u=None):
-        dx = self._dx.clone()
-        for i, skip in enumerate(self.skip):
-            if not skip and self._active(x, i):
-                dx[i, i + self.num_actions] = -self.weight
-        return dx
+        out = self._dx.clone()
+        rows = self._pushed(x).nonzero().flatten()
+        out[rows, rows + self.num_actions] = -self.weight
+        return out
 
     def __call__(self, x=None):
-        try:
-            u = next(self.u)
-        except StopIteration:
+        u = next(self.u, None)
+        if u is None:
             u = torch.zeros(self.num_actions, dtype=self.dtype)
         return self.clipped(x, u)
 

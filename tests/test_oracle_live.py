@@ -78,3 +78,44 @@ def test_robot_steps_match_live_reference(ref, name):
         np.testing.assert_allclose(cb, ca, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(ub.numpy(), ua.numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(pb.numpy(), pa.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_prior_dist_matches_live_reference(ref):
+    rk = ref[0]
+    assert "/root/reference" in rk.__file__
+    x = torch.rand(300, 3, generator=torch.Generator().manual_seed(0)) * 3 - 1.5
+    np.testing.assert_allclose(ko.OraclePrior("xyz").pdf_torch(x).numpy(), rk.PriorDist("xyz").pdf_torch(x).numpy(), rtol=1e-6)
+
+
+def test_feedback_policies_match_live_reference(ref):
+    """BarrierPush / LQR (default_policies.py:53-119): the reference classes, the oracle's rule and the host methods of
+    the B200 mirror (loaded by file path: the package of that name on sys.path is the reference's here)."""
+    import importlib.util
+    rd = ref[3]
+    import control_torch.default_policies as ref_pol
+    assert "/root/reference" in ref_pol.__file__
+    spec = importlib.util.spec_from_file_location("mirror_default_policies", os.path.join(
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "embodied-active-learning-vision_b200", "control_torch",
+        "default_policies.py"))
+    mp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mp)
+    model = rd.DoubleIntegratorEnv(dt=0.2, x0=torch.zeros(6), states="xyz")
+    a, b, o = ref_pol.BarrierPush(model, 10), mp.BarrierPush(model, 10), ko.OracleFeedback("BarrierPush", model, 10)
+    g = torch.Generator().manual_seed(0)
+    for k in range(200):
+        x = torch.rand(6, generator=g) * 3 - 1.5
+        if k % 5 == 0:
+            x[0] = 1.0
+        if k % 7 == 0:
+            x[1] = -1.0
+        u = torch.rand(12, 3, generator=g)
+        for idx in (0, 2):
+            a.reset(x, u.clone(), idx)
+            b.reset(x, u.clone(), idx)
+            ra, rb = a(x), b(x)
+            want, dmu = o.act(x, u[0].clone() if o.uses_plan(idx) else torch.zeros(3))
+            assert torch.equal(ra, rb) and torch.equal(ra, want)
+            assert torch.equal(a.dx(x, ra), b.dx(x, rb)) and torch.equal(a.dx(x, ra), dmu)
+    k_ref = ref_pol.LQR(model, 10).Klqr
+    assert torch.allclose(k_ref, mp.LQR(model, 10).Klqr) and torch.allclose(k_ref, ko.OracleFeedback("LQR", model, 10).K)
+

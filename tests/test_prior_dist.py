@@ -1,5 +1,6 @@
 """PriorDist (klerg.py:27-50) of the B200 mirror - closed form for the diagonal covariance, evaluated where the
-samples live - against the oracle's MultivariateNormal restatement and, when present, the live reference class."""
+samples live - against the oracle's MultivariateNormal restatement (the oracle's is checked against the live reference
+class in test_oracle_live.py)."""
 import os
 import sys
 
@@ -23,14 +24,3 @@ def test_prior_dist_matches_oracle(states):
     got = PriorDist(states).pdf_torch(x)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-6, atol=0)
     assert want.min() >= 1e-5
-
-
-def test_oracle_prior_matches_live_reference():
-    ref = "/root/reference/franka_test/scripts"
-    if not os.path.isdir(ref):
-        pytest.skip("reference tree not present")
-    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    from make_golden import import_reference
-    rk = import_reference()[0]
-    x = torch.rand(300, 3, generator=torch.Generator().manual_seed(0)) * 3 - 1.5
-    np.testing.assert_allclose(ko.OraclePrior("xyz").pdf_torch(x).numpy(), rk.PriorDist("xyz").pdf_torch(x).numpy(), rtol=5e-6)
